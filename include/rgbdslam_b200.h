@@ -1,0 +1,219 @@
+/*
+ * rgbdslam_b200.h — C-ABI of the B200-native hot path of BaptisteHudyma/RGB-D-SLAM.
+ *
+ * The reference has no FFI layer: its seam is three C++ member functions
+ * (SURVEY.md §8b). Each entry point below names the reference interface it replaces.
+ * Everything is plain C: POD structs, caller-allocated buffers, int status (0 = ok).
+ * No torch / Eigen / OpenCV types cross this boundary.
+ *
+ *   Depth_Map_Transformation::get_organized_cloud_array   src/features/primitives/depth_map_transformation.hpp:38-39
+ *   Primitive_Detection::Primitive_Detection / find_primitives   src/features/primitives/primitive_detection.hpp:33,42-45
+ *   Pose_Optimization::compute_optimized_pose               src/pose_optimization/pose_optimization.hpp:27-30
+ *
+ * Units follow the reference: depth and distances in millimetres, angles in radians,
+ * pose = position (mm) + unit quaternion (w,x,y,z) of the camera in the world frame.
+ */
+#ifndef RGBDSLAM_B200_H
+#define RGBDSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define RS_OK 0
+#define RS_ERR_INVALID_ARG 1   /* null pointer, bad size, batch > max_batch ...            */
+#define RS_ERR_CUDA 2          /* a CUDA runtime/driver call failed (see rs_last_error())  */
+#define RS_ERR_NO_DEVICE 3     /* no sm_100 device: the library never falls back to a CPU  */
+#define RS_ERR_CAPACITY 4      /* an output capacity (planes, cylinders, boundary) was hit */
+
+/* ---- capacities (compile-time, shared by kernels, oracle and callers) ---------------- */
+#define RS_MAX_PLANES 128      /* plane segments per frame before merging                  */
+#define RS_MAX_CYL_REGIONS 32  /* cylinder-branch regions per frame                        */
+#define RS_MAX_CYL_SEGS 8      /* sequential-RANSAC sub-segments per region                */
+#define RS_CYL_RANSAC_ITERS 43 /* uint(logf(0.2)/logf(1-0.33^3)), cylinder_segment.cpp:132 */
+
+/* ---- CAPE (planes + cylinders) --------------------------------------------------------
+ * Per-cell record written by the plane-fit kernel: 160 bytes, the "per-cell record" of
+ * SURVEY.md §8d's algorithmic-bytes figure (4·W·H + 160·Ncells per frame).
+ * Mirrors Plane_Segment (plane_segment.hpp:118-140) after init_plane_segment. */
+typedef struct rs_cell_out {
+    int32_t count;      /* _pointCount: pixels with z > 0 (0 if the cell failed the early tests) */
+    int32_t planar;     /* _isPlanar                                                            */
+    double S[9];        /* Sx Sy Sz Sxs Sys Szs Sxy Syz Szx (FP64 sums of FP32 values/products)   */
+    double centroid[3];
+    double normal[3];
+    double d;
+    double mse;         /* DBL_MAX when no fit was made                                           */
+    double score;
+    float tol;          /* _cellDistanceTols[cell], primitive_detection.cpp:201-220               */
+    int32_t reserved;
+} rs_cell_out;
+
+/* One plane segment (entry k of _planeSegments, primitive_detection.hpp:216) after merge_planes. */
+typedef struct rs_plane_out {
+    int32_t merge_label;  /* planeMergeLabels[k] (root id, 0-based)                               */
+    int32_t planar;       /* is_planar() after merging                                            */
+    int32_t is_final;     /* merge_label == k and planar: the plane survives to add_planes_to_primitives */
+    int32_t count;        /* point count                                                          */
+    double S[9];
+    double centroid[3];
+    double normal[3];
+    double d;
+    double mse;
+    double score;
+    int32_t n_boundary;      /* boundary centre points kept (compute_plane_segment_boundary); <3 = dropped by the reference */
+    int32_t boundary_offset; /* first index into the frame's boundary arrays                      */
+} rs_plane_out;
+
+/* One cylinder-branch region (entry of _cylinderSegments, cylinder_segment.hpp). */
+typedef struct rs_cyl_out {
+    int32_t n_cells;     /* activated cells handed to the Cylinder_Segment ctor                  */
+    int32_t n_segments;  /* _segmentCount (0 when the normal-PCA score is < 75)                   */
+    double pca_score;    /* lambda2 / lambda0 of the +-normals covariance                         */
+    double axis[3];
+    double radius[RS_MAX_CYL_SEGS];
+    double center[RS_MAX_CYL_SEGS][3];
+    double mse[RS_MAX_CYL_SEGS];
+    double plane_mse[RS_MAX_CYL_SEGS];   /* MSE of the plane refit over the segment's inliers      */
+    int32_t n_inliers[RS_MAX_CYL_SEGS];
+    int32_t assigned[RS_MAX_CYL_SEGS];   /* >0: cylinder id in cyl_labels; <0: -(plane id) it became; 0: nothing */
+    int32_t kept[RS_MAX_CYL_SEGS];       /* cylinder id survives the opening test of add_cylinders_to_primitives */
+} rs_cyl_out;
+
+typedef struct rs_cape_frame_info {
+    int32_t status;        /* RS_OK or RS_ERR_CAPACITY                                            */
+    int32_t n_planar_cells;
+    int32_t n_seeds;       /* iterations of the seed loop (grow_planes_and_cylinders)             */
+    int32_t n_planes;      /* plane segments before merging                                       */
+    int32_t n_final_planes;
+    int32_t n_cyl_regions;
+    int32_t n_cylinders;   /* cylinder2regionMap.size()                                           */
+    int32_t n_boundary;    /* boundary points written for this frame                              */
+} rs_cape_frame_info;
+
+typedef struct rs_cape_ctx rs_cape_ctx;
+
+/* Replaces Primitive_Detection::Primitive_Detection(w,h) + Depth_Map_Transformation ctor/init_matrices
+ * (depth_map_transformation.cpp:147-173). cell_px = parameters::detection::depthMapPatchSize_px (20).
+ * Intrinsics are the reference's camera-1 fx,fy,cx,cy (parameters.cpp:59-74). Returns NULL on error. */
+rs_cape_ctx* rs_cape_create(int width, int height, int cell_px, double fx, double fy, double cx, double cy,
+                            int max_batch, int device);
+void rs_cape_destroy(rs_cape_ctx* ctx);
+
+int rs_cape_cells_per_frame(const rs_cape_ctx* ctx);    /* hc*vc                                   */
+int rs_cape_max_boundary(const rs_cape_ctx* ctx);       /* boundary-point capacity per frame        */
+
+/* Outputs of one batched CAPE run; any pointer may be NULL to skip that copy.
+ * Leading dimension is the batch; sizes per frame are in brackets. */
+typedef struct rs_cape_outputs {
+    rs_cell_out* cells;          /* [Ncells]                                                       */
+    int32_t* plane_grid;         /* [Ncells] _gridPlaneSegmentMap: 0 none, k = k-th plane segment   */
+    int32_t* plane_labels;       /* [Ncells] merged labels: 0 none, root+1 for final planes         */
+    int32_t* cyl_labels;         /* [Ncells] _gridCylinderSegMap                                    */
+    int32_t* cyl_region_seg;     /* [Ncells] 0 none, 1 + region*RS_MAX_CYL_SEGS + segment           */
+    rs_plane_out* planes;        /* [RS_MAX_PLANES]                                                */
+    rs_cyl_out* cyls;            /* [RS_MAX_CYL_REGIONS]                                           */
+    double* boundary_xyz;        /* [max_boundary][3] camera-frame centre points                   */
+    rs_cape_frame_info* info;    /* [1]                                                            */
+} rs_cape_outputs;
+
+/* Replaces get_organized_cloud_array + find_primitives for a batch of frames
+ * (rgbd_slam.cpp:110-112,295). depth = B x H x W float32, row-major, mm, <=0 invalid, HOST memory.
+ * seed = utils::Random::_seed of the per-frame thread-local engine (random.hpp:17-65; 0 under
+ * MAKE_DETERMINISTIC): the cylinder RANSAC of EVERY frame restarts at mt19937(seed), as the
+ * reference does because find_primitives runs on a fresh std::async thread per frame. */
+int rs_cape_run(rs_cape_ctx* ctx, const float* depth_host, int batch, uint32_t seed, const rs_cape_outputs* out_host);
+
+/* Same, with depth and outputs already resident in device memory (used for the HBM-resident
+ * throughput number; `stream` is a cudaStream_t passed as void*). Asynchronous. */
+int rs_cape_run_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, uint32_t seed,
+                       const rs_cape_outputs* out_dev, void* stream);
+
+/* Only the per-cell plane fit (K1): get_organized_cloud_array + init_planar_cell_fitting.
+ * cells_dev = B x Ncells records in device memory. Asynchronous. */
+int rs_cape_cell_fit_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, rs_cell_out* cells_dev, void* stream);
+
+/* Device scratch owned by the context, for callers that keep data resident (bench, multi-frame pipelines). */
+float* rs_cape_device_depth(rs_cape_ctx* ctx);                  /* max_batch x H x W                 */
+const rs_cape_outputs* rs_cape_device_outputs(rs_cape_ctx* ctx); /* device pointers, max_batch frames */
+
+/* ---- pose solve ------------------------------------------------------------------------- */
+#define RS_FEAT_POINT 0    /* PointOptimizationFeature  (map_point.cpp:16-65)    2 residuals, score 1/5 */
+#define RS_FEAT_PLANE 1    /* PlaneOptimizationFeature  (map_primitive.cpp:15-85) 3 residuals, score 1/3 */
+
+/* One matched feature (an IOptimizationFeature flattened; matches_containers.hpp:122-180). */
+typedef struct rs_match {
+    int32_t type;
+    int32_t reserved;
+    double obs[4];    /* point: (u, v, -, -) screen px.  plane: camera-frame (nx, ny, nz, d)          */
+    double map[4];    /* point: world (X, Y, Z, -) mm.   plane: world-frame (nx, ny, nz, d)           */
+    double sigma[4];  /* standard deviation of the map side (Monte-Carlo variation)                 */
+} rs_match;
+
+#define RS_RNG_REFERENCE 0 /* host std::mt19937 + libstdc++ shuffle/normal_distribution, one stream, as random.hpp/ransac.hpp */
+#define RS_RNG_DEVICE 1    /* counter-based on-device generator (throughput mode)                    */
+
+typedef struct rs_pose_opts {
+    int32_t max_iterations;     /* RANSAC hypotheses; <=0 -> 119 (pose_optimization.cpp:129-132)     */
+    int32_t n_variance;         /* Monte-Carlo LM solves for the covariance; <0 -> 100, 0 -> skip    */
+    int32_t rng_mode;           /* RS_RNG_REFERENCE | RS_RNG_DEVICE                                   */
+    uint32_t seed;
+    double fx, fy, cx, cy;      /* camera-1 intrinsics; all 0 -> reference defaults 550,550,320,240  */
+    int32_t lm_max_fev;         /* <=0 -> 400 (Eigen LevenbergMarquardt default)                     */
+    int32_t reserved;
+} rs_pose_opts;
+
+typedef struct rs_pose_out {
+    int32_t status;            /* 1 = pose and covariance valid (compute_optimized_pose returned true),
+                                  0 = RANSAC failed, -1 = final LM failed, -2 = covariance failed     */
+    int32_t n_inliers;
+    int32_t iterations_run;    /* RANSAC iterations started before the early stop                   */
+    int32_t best_iteration;
+    int32_t n_variance_ok;     /* successful Monte-Carlo solves                                      */
+    int32_t reserved;
+    double score;              /* inlier score of the winning hypothesis                             */
+    double pose[7];            /* x y z qw qx qy qz                                                  */
+    double cov[36];            /* row-major 6x6 of [pos, eulerAngles(0,1,2)] + 1e-3 I                */
+} rs_pose_out;
+
+typedef struct rs_pose_ctx rs_pose_ctx;
+
+rs_pose_ctx* rs_pose_create(int max_batch, int max_matches, int max_iterations, int max_variance, int device);
+void rs_pose_destroy(rs_pose_ctx* ctx);
+
+/* Replaces Pose_Optimization::compute_optimized_pose for a batch of independent frames.
+ * cur_pose = B x 7; matches = B x max_matches rs_match (frame b uses the first n_matches[b]);
+ * out = B records; inlier_mask = B x max_matches bytes (may be NULL). HOST memory. */
+int rs_pose_solve_batched(rs_pose_ctx* ctx, const double* cur_pose, const rs_match* matches, const int32_t* n_matches,
+                          int batch, const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask);
+
+/* Single-frame convenience with the reference's call shape (creates nothing: uses ctx, batch 1). */
+int rs_pose_solve(rs_pose_ctx* ctx, const double cur_pose[7], const rs_match* matches, int n_matches,
+                  const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask);
+
+/* Device-resident variant (inputs uploaded once with rs_pose_upload; outputs stay on the device
+ * until rs_pose_download). Asynchronous on `stream`. RS_RNG_DEVICE only. */
+int rs_pose_upload(rs_pose_ctx* ctx, const double* cur_pose, const rs_match* matches, const int32_t* n_matches, int batch);
+int rs_pose_solve_device(rs_pose_ctx* ctx, int batch, const rs_pose_opts* opts, void* stream);
+int rs_pose_download(rs_pose_ctx* ctx, int batch, rs_pose_out* out, uint8_t* inlier_mask);
+double* rs_pose_device_poses(rs_pose_ctx* ctx); /* B x 7 doubles on the device (the all-gather payload) */
+
+/* Debug/parity taps (RS_RNG_DEVICE): the random inputs the last solve used, so that the checker
+ * can feed the same ones to the oracle. subsets = B x max_iterations x RS_MAX_SUBSET int32 (-1 padded);
+ * normals = B x n_variance x max_matches x 4 doubles. Either may be NULL. */
+#define RS_MAX_SUBSET 16
+int rs_pose_export_random(rs_pose_ctx* ctx, int batch, int32_t* subsets, double* normals);
+
+/* ---- misc ------------------------------------------------------------------------------- */
+const char* rs_last_error(void);
+const char* rs_version(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t rs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBDSLAM_B200_H */

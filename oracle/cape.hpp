@@ -1,0 +1,61 @@
+// TEST INFRASTRUCTURE — CPU oracle (see linalg.hpp header). Restates the reference's CAPE path:
+//   src/features/primitives/{depth_map_transformation,plane_segment,histogram,primitive_detection,
+//   cylinder_segment}.* and src/utils/covariances.cpp:12-19.
+// PARITY UNPINNED: the reference has no test, golden vector or dataset for this path and
+// cannot be compiled here (Eigen/OpenCV/TBB/boost absent). This restatement is the only pin.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../include/rgbdslam_b200.h"
+#include "linalg.hpp"
+
+namespace oracle {
+
+struct CapeConfig {
+    int width = 640, height = 480, cell = 20;
+    double fx = 550, fy = 550, cx = 320, cy = 240;
+};
+
+// Plane_Segment (plane_segment.hpp): 9 sums, count, fit results.
+struct PlaneSeg {
+    int count = 0;
+    bool planar = false;
+    double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // Sx Sy Sz Sxs Sys Szs Sxy Syz Szx
+    Vec3 centroid;
+    Vec3 normal;
+    double d = 0;
+    double mse = DBL_MAX;
+    double score = 0;
+    void clear();                       // clear_plane_parameters, plane_segment.cpp:289-310
+    void expand(const PlaneSeg& o);     // expand_segment, :170-190
+    void fit_plane();                   // :232-284
+    PlaneSeg copy() const;              // copy ctor (:18-36) incl. the PlaneCoordinates re-normalisation
+    bool can_be_merged(const PlaneSeg& p, double maxMatchDistance) const;  // :322-326
+};
+
+double depth_quantization(double z);    // covariances.cpp:12-19
+
+struct CapeFrame {
+    std::vector<rs_cell_out> cells;
+    std::vector<int32_t> plane_grid, plane_labels, cyl_labels, cyl_region_seg;
+    std::vector<rs_plane_out> planes;   // n_planes entries
+    std::vector<rs_cyl_out> cyls;       // n_cyl_regions entries
+    std::vector<double> boundary_xyz;   // 3 * n_boundary
+    rs_cape_frame_info info{};
+};
+
+// Back-projection factors kx[c], ky[r] (point_coordinates.cpp:79-83 via Eigen's 3x3 cofactor inverse).
+void backprojection_factors(const CapeConfig& cfg, std::vector<double>& kx, std::vector<double>& ky);
+
+// get_organized_cloud_array + init_planar_cell_fitting only (K1's scope). cloud (optional) receives the
+// organized cloud [W*H x 3] column-major as the reference builds it.
+void cape_cell_fit(const CapeConfig& cfg, const float* depth, std::vector<PlaneSeg>& grid, std::vector<float>& tols,
+                   std::vector<float>* cloud = nullptr);
+
+// Whole find_primitives (primitive_detection.cpp:119-166) for one frame. seed = utils::Random::_seed.
+void cape_run(const CapeConfig& cfg, const float* depth, uint32_t seed, CapeFrame& out);
+
+void cell_record(const PlaneSeg& s, float tol, rs_cell_out& o);
+
+}  // namespace oracle

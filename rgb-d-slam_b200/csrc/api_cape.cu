@@ -1,0 +1,342 @@
+// C-ABI glue for the CAPE path (include/rgbdslam_b200.h): context, device buffers, TMA descriptor, launches.
+// There is no CPU fallback anywhere in this library: without an sm_100 device every entry point fails loudly.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "cape_internal.cuh"
+
+namespace rs {
+
+static std::mutex g_err_mutex;
+static std::string g_last_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_last_error(const std::string& msg)
+{
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    g_last_error = msg;
+}
+
+int require_blackwell(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_last_error(std::string("no CUDA device visible (") + cudaGetErrorString(e) +
+                       "): this library has no CPU path");
+        return RS_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_last_error("device index out of range");
+        return RS_ERR_INVALID_ARG;
+    }
+    cudaDeviceProp prop;
+    RS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_last_error(std::string("device '") + prop.name + "' is not sm_100 (Blackwell): kernels are built for sm_100a only");
+        return RS_ERR_NO_DEVICE;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(device));
+    return RS_OK;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+struct rs_cape_ctx {
+    int W, H, cell, hc, vc, Nc, max_batch, device, max_boundary;
+    double fx, fy, cx, cy;
+    double* d_kx = nullptr;
+    double* d_ky = nullptr;
+    float* d_depth = nullptr;
+    rs_cape_outputs d_out{};       // device pointers sized for max_batch
+    double* d_uniforms = nullptr;
+    int n_uniforms = 0;
+    uint32_t uniforms_seed = 0;
+    bool uniforms_valid = false;
+    CellFitParams fit{};
+    SegmentParams seg{};
+    // cached tensor map
+    const float* tmap_ptr = nullptr;
+    int tmap_batch = 0;
+    CUtensorMap tmap;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+// Eigen's 3x3 cofactor inverse of the intrinsics applied to (u, v, 1): point_coordinates.cpp:79-83.
+void backprojection_factors(const rs_cape_ctx* c, std::vector<double>& kx, std::vector<double>& ky)
+{
+    const double K[3][3] = {{c->fx, 0, c->cx}, {0, c->fy, c->cy}, {0, 0, 1}};
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return K[i1][j1] * K[i2][j2] - K[i1][j2] * K[i2][j1];
+    };
+    const double c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    const double det = (c00 * K[0][0] + c10 * K[1][0]) + c20 * K[2][0];
+    const double invdet = 1.0 / det;
+    const double i00 = c00 * invdet, i01 = c10 * invdet, i02 = c20 * invdet;
+    const double i10 = cof(0, 1) * invdet, i11 = cof(1, 1) * invdet, i12 = cof(2, 1) * invdet;
+    kx.resize(c->W);
+    ky.resize(c->H);
+    for (int u = 0; u < c->W; ++u) kx[u] = (i00 * double(u) + i01 * 0.0) + i02 * 1.0;
+    for (int v = 0; v < c->H; ++v) ky[v] = (i10 * 0.0 + i11 * double(v)) + i12 * 1.0;
+}
+
+int encode_tmap(rs_cape_ctx* c, const float* depth_dev, int batch)
+{
+    if (c->tmap_ptr == depth_dev && c->tmap_batch == batch) return RS_OK;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_last_error("cuTensorMapEncodeTiled entry point not available from the driver");
+        return RS_ERR_CUDA;
+    }
+    // tensor view of the depth batch: dim0 = pixel column inside a cell, dim1 = cell column, dim2 = image row
+    // (frames are contiguous, so batch*H rows). A {cs, 1, cs} box is one cell, landing dense in shared memory.
+    const cuuint64_t dims[3] = {cuuint64_t(c->cell), cuuint64_t(c->hc), cuuint64_t(batch) * cuuint64_t(c->H)};
+    const cuuint64_t strides[2] = {cuuint64_t(c->cell) * 4, cuuint64_t(c->W) * 4};
+    const cuuint32_t box[3] = {cuuint32_t(c->cell), 1, cuuint32_t(c->cell)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(depth_dev), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+        return RS_ERR_CUDA;
+    }
+    c->tmap_ptr = depth_dev;
+    c->tmap_batch = batch;
+    return RS_OK;
+}
+
+// canonical doubles of std::mt19937(seed) through std::uniform_real_distribution<double>(0,1), i.e. what
+// utils::Random::get_random_double() returns on a fresh thread (random.hpp:17-31).
+int ensure_uniforms(rs_cape_ctx* c, uint32_t seed)
+{
+    if (c->uniforms_valid && c->uniforms_seed == seed) return RS_OK;
+    std::vector<double> u(c->n_uniforms);
+    std::mt19937 eng(seed);
+    std::uniform_real_distribution<double> dist(0.0, 1.0);
+    for (double& v : u) v = dist(eng);
+    RS_CUDA_CHECK(cudaMemcpy(c->d_uniforms, u.data(), sizeof(double) * u.size(), cudaMemcpyHostToDevice));
+    c->uniforms_seed = seed;
+    c->uniforms_valid = true;
+    return RS_OK;
+}
+
+template <class T>
+int dev_alloc(T** p, size_t n)
+{
+    RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * n));
+    RS_CUDA_CHECK(cudaMemset(*p, 0, sizeof(T) * n));
+    return RS_OK;
+}
+
+int create_impl(rs_cape_ctx* c)
+{
+    int rc = require_blackwell(c->device);
+    if (rc != RS_OK) return rc;
+    std::vector<double> kx, ky;
+    backprojection_factors(c, kx, ky);
+    const size_t B = size_t(c->max_batch), Nc = size_t(c->Nc);
+    if ((rc = dev_alloc(&c->d_kx, kx.size()))) return rc;
+    if ((rc = dev_alloc(&c->d_ky, ky.size()))) return rc;
+    RS_CUDA_CHECK(cudaMemcpy(c->d_kx, kx.data(), sizeof(double) * kx.size(), cudaMemcpyHostToDevice));
+    RS_CUDA_CHECK(cudaMemcpy(c->d_ky, ky.data(), sizeof(double) * ky.size(), cudaMemcpyHostToDevice));
+    if ((rc = dev_alloc(&c->d_depth, B * c->W * c->H))) return rc;
+    if ((rc = dev_alloc(&c->d_out.cells, B * Nc))) return rc;
+    if ((rc = dev_alloc(&c->d_out.plane_grid, B * Nc))) return rc;
+    if ((rc = dev_alloc(&c->d_out.plane_labels, B * Nc))) return rc;
+    if ((rc = dev_alloc(&c->d_out.cyl_labels, B * Nc))) return rc;
+    if ((rc = dev_alloc(&c->d_out.cyl_region_seg, B * Nc))) return rc;
+    if ((rc = dev_alloc(&c->d_out.planes, B * RS_MAX_PLANES))) return rc;
+    if ((rc = dev_alloc(&c->d_out.cyls, B * RS_MAX_CYL_REGIONS))) return rc;
+    if ((rc = dev_alloc(&c->d_out.boundary_xyz, B * size_t(c->max_boundary) * 3))) return rc;
+    if ((rc = dev_alloc(&c->d_out.info, B))) return rc;
+    c->n_uniforms = 3 * RS_CYL_RANSAC_ITERS * RS_MAX_CYL_REGIONS * RS_MAX_CYL_SEGS;
+    if ((rc = dev_alloc(&c->d_uniforms, size_t(c->n_uniforms)))) return rc;
+    RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    const unsigned P = unsigned(c->cell) * unsigned(c->cell);
+    c->fit.H = c->H, c->fit.hc = c->hc, c->fit.vc = c->vc, c->fit.cell = c->cell;
+    c->fit.kx = c->d_kx, c->fit.ky = c->d_ky;
+    c->fit.min_zero_point_count = int(static_cast<unsigned>(std::floor(static_cast<float>(P) * 0.7f)));
+    c->fit.sin_merge = sinf(static_cast<float>(18.0f * M_PI / 180.0));
+    c->fit.merge_distance = 50.0f;
+    c->seg.W = c->W, c->seg.H = c->H, c->seg.hc = c->hc, c->seg.vc = c->vc, c->seg.cell = c->cell;
+    c->seg.kx = c->d_kx, c->seg.ky = c->d_ky;
+    c->seg.cos_merge = std::cos(18.0f * M_PI / 180.0);
+    c->seg.uniforms = c->d_uniforms, c->seg.n_uniforms = c->n_uniforms;
+    c->seg.max_boundary = c->max_boundary;
+    return RS_OK;
+}
+
+int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t seed, const rs_cape_outputs* o,
+                    cudaStream_t stream, bool cells_only)
+{
+    if (!c || !depth_dev || batch <= 0 || batch > c->max_batch || !o || !o->cells) {
+        set_last_error("rs_cape_run: invalid argument (null pointer or batch out of range)");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc = encode_tmap(c, depth_dev, batch);
+    if (rc != RS_OK) return rc;
+    CellFitParams fp = c->fit;
+    fp.batch = batch;
+    if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream)) != RS_OK) return rc;
+    if (cells_only) return RS_OK;
+    if (!o->plane_grid || !o->plane_labels || !o->cyl_labels || !o->cyl_region_seg || !o->planes || !o->cyls ||
+        !o->boundary_xyz || !o->info) {
+        set_last_error("rs_cape_run_device: all device output buffers are required");
+        return RS_ERR_INVALID_ARG;
+    }
+    if ((rc = ensure_uniforms(c, seed)) != RS_OK) return rc;
+    SegmentParams sp = c->seg;
+    sp.batch = batch;
+    SegmentBuffers sb;
+    sb.depth = depth_dev;
+    sb.cells = o->cells;
+    sb.plane_grid = o->plane_grid;
+    sb.plane_labels = o->plane_labels;
+    sb.cyl_labels = o->cyl_labels;
+    sb.cyl_region_seg = o->cyl_region_seg;
+    sb.planes = o->planes;
+    sb.cyls = o->cyls;
+    sb.boundary_xyz = o->boundary_xyz;
+    sb.info = o->info;
+    return launch_cape_segment(sp, sb, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+rs_cape_ctx* rs_cape_create(int width, int height, int cell_px, double fx, double fy, double cx, double cy, int max_batch,
+                            int device)
+{
+    if (width <= 0 || height <= 0 || cell_px <= 0 || cell_px % 4 != 0 || width < cell_px || height < cell_px ||
+        max_batch <= 0 || width % 4 != 0) {
+        set_last_error("rs_cape_create: invalid geometry (cell_px and width must be multiples of 4)");
+        return nullptr;
+    }
+    rs_cape_ctx* c = new rs_cape_ctx();
+    c->W = width, c->H = height, c->cell = cell_px;
+    c->hc = width / cell_px, c->vc = height / cell_px, c->Nc = c->hc * c->vc;
+    c->fx = fx, c->fy = fy, c->cx = cx, c->cy = cy;
+    c->max_batch = max_batch, c->device = device;
+    c->max_boundary = 2 * c->Nc;
+    if (create_impl(c) != RS_OK) {
+        rs_cape_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void rs_cape_destroy(rs_cape_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_kx);
+    cudaFree(c->d_ky);
+    cudaFree(c->d_depth);
+    cudaFree(c->d_out.cells);
+    cudaFree(c->d_out.plane_grid);
+    cudaFree(c->d_out.plane_labels);
+    cudaFree(c->d_out.cyl_labels);
+    cudaFree(c->d_out.cyl_region_seg);
+    cudaFree(c->d_out.planes);
+    cudaFree(c->d_out.cyls);
+    cudaFree(c->d_out.boundary_xyz);
+    cudaFree(c->d_out.info);
+    cudaFree(c->d_uniforms);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rs_cape_cells_per_frame(const rs_cape_ctx* c) { return c ? c->Nc : 0; }
+int rs_cape_max_boundary(const rs_cape_ctx* c) { return c ? c->max_boundary : 0; }
+float* rs_cape_device_depth(rs_cape_ctx* c) { return c ? c->d_depth : nullptr; }
+const rs_cape_outputs* rs_cape_device_outputs(rs_cape_ctx* c) { return c ? &c->d_out : nullptr; }
+
+int rs_cape_cell_fit_device(rs_cape_ctx* c, const float* depth_dev, int batch, rs_cell_out* cells_dev, void* stream)
+{
+    rs_cape_outputs o{};
+    o.cells = cells_dev;
+    return run_device_impl(c, depth_dev, batch, 0, &o, static_cast<cudaStream_t>(stream), true);
+}
+
+int rs_cape_run_device(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t seed, const rs_cape_outputs* out_dev,
+                       void* stream)
+{
+    return run_device_impl(c, depth_dev, batch, seed, out_dev, static_cast<cudaStream_t>(stream), false);
+}
+
+int rs_cape_run(rs_cape_ctx* c, const float* depth_host, int batch, uint32_t seed, const rs_cape_outputs* out)
+{
+    if (!c || !depth_host || !out || batch <= 0 || batch > c->max_batch) {
+        set_last_error("rs_cape_run: invalid argument (null pointer or batch out of range)");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t B = size_t(batch), Nc = size_t(c->Nc);
+    cudaStream_t s = c->stream;
+    RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth, depth_host, sizeof(float) * B * c->W * c->H, cudaMemcpyHostToDevice, s));
+    const bool cells_only = !out->plane_grid && !out->plane_labels && !out->cyl_labels && !out->cyl_region_seg &&
+                            !out->planes && !out->cyls && !out->boundary_xyz && !out->info;
+    int rc = run_device_impl(c, c->d_depth, batch, seed, &c->d_out, s, cells_only);
+    if (rc != RS_OK) return rc;
+    const rs_cape_outputs& d = c->d_out;
+#define RS_D2H(field, count)                                                                                      \
+    if (out->field)                                                                                               \
+    RS_CUDA_CHECK(cudaMemcpyAsync(out->field, d.field, sizeof(*d.field) * (count), cudaMemcpyDeviceToHost, s))
+    RS_D2H(cells, B * Nc);
+    RS_D2H(plane_grid, B * Nc);
+    RS_D2H(plane_labels, B * Nc);
+    RS_D2H(cyl_labels, B * Nc);
+    RS_D2H(cyl_region_seg, B * Nc);
+    RS_D2H(planes, B * RS_MAX_PLANES);
+    RS_D2H(cyls, B * RS_MAX_CYL_REGIONS);
+    RS_D2H(boundary_xyz, B * size_t(c->max_boundary) * 3);
+    RS_D2H(info, B);
+#undef RS_D2H
+    RS_CUDA_CHECK(cudaStreamSynchronize(s));
+    return RS_OK;
+}
+
+const char* rs_last_error(void)
+{
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    copy = g_last_error;
+    return copy.c_str();
+}
+const char* rs_version(void) { return "rgbdslam_b200 0.1 (sm_100a)"; }
+uint64_t rs_launch_count(void) { return g_launch_count.load(); }
+
+}  // extern "C"

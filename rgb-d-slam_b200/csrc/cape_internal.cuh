@@ -1,0 +1,47 @@
+// Internal declarations shared by the CAPE kernels and the C-ABI glue (not part of the public header).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace rs {
+
+struct CellFitParams {
+    int H, hc, vc, batch, cell;
+    const double* kx;  // [W]  back-projection factor per image column (device)
+    const double* ky;  // [H]  per image row
+    int min_zero_point_count;   // floor(P * 0.7f), plane_segment.hpp:33-34
+    float sin_merge;            // sinf(float(18 deg)), primitive_detection.cpp:189-190
+    float merge_distance;       // 50 mm
+    int items_per_strip, total_items;  // filled by the launcher
+};
+
+int launch_cape_cell_fit(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream);
+
+struct SegmentParams {
+    int W, H, hc, vc, cell, batch;
+    const double* kx;
+    const double* ky;
+    double cos_merge;            // cos(18 deg) in FP64 (plane_segment.cpp:324)
+    const double* uniforms;      // canonical doubles of mt19937(seed) (cylinder RANSAC draws), device
+    int n_uniforms;
+    int max_boundary;
+};
+
+struct SegmentBuffers {
+    const float* depth;          // B x H x W
+    const rs_cell_out* cells;    // B x Nc
+    int32_t* plane_grid;
+    int32_t* plane_labels;
+    int32_t* cyl_labels;
+    int32_t* cyl_region_seg;
+    rs_plane_out* planes;        // B x RS_MAX_PLANES
+    rs_cyl_out* cyls;            // B x RS_MAX_CYL_REGIONS
+    double* boundary_xyz;        // B x max_boundary x 3
+    rs_cape_frame_info* info;    // B
+};
+
+int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream);
+
+}  // namespace rs

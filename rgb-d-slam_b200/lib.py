@@ -1,0 +1,225 @@
+"""ctypes binding of librgbdslam_b200.so — the drop-in C-ABI of the CUDA hot path (include/rgbdslam_b200.h).
+
+Host-side mirror of the reference's call surface:
+  PrimitiveDetection.find_primitives   <-> Primitive_Detection::find_primitives (primitive_detection.hpp:42-45)
+                                            + Depth_Map_Transformation::get_organized_cloud_array (fused)
+  PoseOptimization.compute_optimized_pose <-> Pose_Optimization::compute_optimized_pose (pose_optimization.hpp:27-30)
+There is no CPU fallback: if the shared library is missing or no sm_100 GPU is visible these raise."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librgbdslam_b200.so")
+_lib = None
+
+
+class RsError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the CUDA library (built by build.py). Raises if it is missing — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RsError("librgbdslam_b200.so is not built (run `python rgb-d-slam_b200/build.py`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u32, dbl = C.c_void_p, C.c_int, C.c_uint32, C.c_double
+    lib.rs_cape_create.restype = vp
+    lib.rs_cape_create.argtypes = [i32, i32, i32, dbl, dbl, dbl, dbl, i32, i32]
+    lib.rs_cape_destroy.argtypes = [vp]
+    lib.rs_cape_cells_per_frame.argtypes = [vp]
+    lib.rs_cape_max_boundary.argtypes = [vp]
+    lib.rs_cape_run.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs)]
+    lib.rs_cape_run_device.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs), vp]
+    lib.rs_cape_cell_fit_device.argtypes = [vp, vp, i32, vp, vp]
+    lib.rs_cape_device_depth.restype = vp
+    lib.rs_cape_device_depth.argtypes = [vp]
+    lib.rs_cape_device_outputs.restype = C.POINTER(abi.CapeOutputs)
+    lib.rs_cape_device_outputs.argtypes = [vp]
+    lib.rs_last_error.restype = C.c_char_p
+    lib.rs_version.restype = C.c_char_p
+    lib.rs_launch_count.restype = C.c_uint64
+    if hasattr(lib, "rs_pose_create"):
+        lib.rs_pose_create.restype = vp
+        lib.rs_pose_create.argtypes = [i32, i32, i32, i32, i32]
+        lib.rs_pose_destroy.argtypes = [vp]
+        lib.rs_pose_solve_batched.argtypes = [vp, vp, vp, vp, i32, C.POINTER(abi.PoseOpts), vp, vp]
+        lib.rs_pose_solve.argtypes = [vp, vp, vp, i32, C.POINTER(abi.PoseOpts), vp, vp]
+        lib.rs_pose_upload.argtypes = [vp, vp, vp, vp, i32]
+        lib.rs_pose_solve_device.argtypes = [vp, i32, C.POINTER(abi.PoseOpts), vp]
+        lib.rs_pose_download.argtypes = [vp, i32, vp, vp]
+        lib.rs_pose_device_poses.restype = vp
+        lib.rs_pose_device_poses.argtypes = [vp]
+        lib.rs_pose_export_random.argtypes = [vp, i32, vp, vp]
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().rs_last_error().decode()
+
+
+def _check(rc, what):
+    if rc != abi.RS_OK:
+        raise RsError("%s failed (status %d): %s" % (what, rc, last_error()))
+
+
+def launch_count():
+    return int(load().rs_launch_count())
+
+
+class PrimitiveDetection:
+    """Batched CAPE plane/cylinder extraction on one GPU.
+
+    Mirrors Primitive_Detection(width, height) + find_primitives(...) of the reference; the organized point cloud is
+    never materialised (the back-projection is fused into the plane-fit kernel)."""
+
+    def __init__(self, width=640, height=480, cell_px=20, fx=550.0, fy=550.0, cx=320.0, cy=240.0, max_batch=1, device=0):
+        lib = load()
+        self._lib = lib
+        self.width, self.height, self.cell_px, self.max_batch, self.device = width, height, cell_px, max_batch, device
+        self._ctx = lib.rs_cape_create(width, height, cell_px, fx, fy, cx, cy, max_batch, device)
+        if not self._ctx:
+            raise RsError("rs_cape_create failed: " + last_error())
+        self.n_cells = lib.rs_cape_cells_per_frame(self._ctx)
+        self.max_boundary = lib.rs_cape_max_boundary(self._ctx)
+        self.hc, self.vc = width // cell_px, height // cell_px
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rs_cape_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def find_primitives(self, depth, seed=0, cells_only=False, out=None):
+        """depth: float32 [B,H,W] (or [H,W]) host array in mm. Returns a dict of numpy outputs (see abi.py)."""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        if depth.ndim == 2:
+            depth = depth[None]
+        B = depth.shape[0]
+        if depth.shape[1:] != (self.height, self.width):
+            raise ValueError("depth must be [B,%d,%d]" % (self.height, self.width))
+        if out is None:
+            arrs, st = abi.alloc_cape_outputs(B, self.n_cells, self.max_boundary)
+        else:
+            arrs, st = out
+        if cells_only:
+            st = abi.CapeOutputs(cells=arrs["cells"].ctypes.data)
+        _check(self._lib.rs_cape_run(self._ctx, depth.ctypes.data, B, seed, C.byref(st)), "rs_cape_run")
+        return arrs
+
+    # --- device-resident entry points (pointers are raw CUDA device addresses, e.g. torch.Tensor.data_ptr()) ---
+    def device_depth_ptr(self):
+        return self._lib.rs_cape_device_depth(self._ctx)
+
+    def device_outputs(self):
+        return self._lib.rs_cape_device_outputs(self._ctx).contents
+
+    def run_device(self, depth_ptr, batch, seed=0, outputs=None, stream=0):
+        o = outputs if outputs is not None else self.device_outputs()
+        _check(self._lib.rs_cape_run_device(self._ctx, depth_ptr, batch, seed, C.byref(o), stream), "rs_cape_run_device")
+
+    def cell_fit_device(self, depth_ptr, batch, cells_ptr=None, stream=0):
+        if cells_ptr is None:
+            cells_ptr = self.device_outputs().cells
+        _check(self._lib.rs_cape_cell_fit_device(self._ctx, depth_ptr, batch, cells_ptr, stream), "rs_cape_cell_fit_device")
+
+
+def make_matches(n):
+    return np.zeros((n,), dtype=abi.match_dtype)
+
+
+class PoseOptimization:
+    """Batched RANSAC + Levenberg-Marquardt pose solve (+ Monte-Carlo covariance) on one GPU."""
+
+    def __init__(self, max_batch=1, max_matches=512, max_iterations=119, max_variance=100, device=0):
+        lib = load()
+        if not hasattr(lib, "rs_pose_create"):
+            raise RsError("this build of librgbdslam_b200.so has no pose solver")
+        self._lib = lib
+        self.max_batch, self.max_matches = max_batch, max_matches
+        self.max_iterations, self.max_variance = max_iterations, max_variance
+        self._ctx = lib.rs_pose_create(max_batch, max_matches, max_iterations, max_variance, device)
+        if not self._ctx:
+            raise RsError("rs_pose_create failed: " + last_error())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rs_pose_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def options(max_iterations=0, n_variance=-1, rng_mode=abi.RS_RNG_REFERENCE, seed=0, intrinsics=None, lm_max_fev=0):
+        o = abi.PoseOpts()
+        o.max_iterations, o.n_variance, o.rng_mode, o.seed, o.lm_max_fev = max_iterations, n_variance, rng_mode, seed, lm_max_fev
+        if intrinsics is not None:
+            o.fx, o.fy, o.cx, o.cy = intrinsics
+        return o
+
+    def compute_optimized_pose(self, cur_pose, matches, n_matches=None, opts=None):
+        """cur_pose [B,7] (x y z qw qx qy qz); matches [B,max_matches] of abi.match_dtype (or a list of 1-D arrays).
+        Returns (pose_out[B] structured array, inlier_mask[B,max_matches] uint8)."""
+        cur_pose = np.ascontiguousarray(np.atleast_2d(cur_pose), dtype=np.float64)
+        B = cur_pose.shape[0]
+        if isinstance(matches, (list, tuple)):
+            n_matches = np.array([len(m) for m in matches], dtype=np.int32)
+            packed = np.zeros((B, self.max_matches), dtype=abi.match_dtype)
+            for b, m in enumerate(matches):
+                packed[b, :len(m)] = m
+            matches = packed
+        matches = np.ascontiguousarray(matches)
+        if matches.ndim == 1:
+            matches = matches[None]
+        if matches.shape[1] != self.max_matches:
+            raise ValueError("matches must be [B, max_matches=%d]" % self.max_matches)
+        if n_matches is None:
+            n_matches = np.full((B,), matches.shape[1], dtype=np.int32)
+        n_matches = np.ascontiguousarray(n_matches, dtype=np.int32)
+        out = np.zeros((B,), dtype=abi.pose_out_dtype)
+        mask = np.zeros((B, self.max_matches), dtype=np.uint8)
+        o = opts if opts is not None else self.options()
+        _check(self._lib.rs_pose_solve_batched(self._ctx, cur_pose.ctypes.data, matches.ctypes.data, n_matches.ctypes.data,
+                                               B, C.byref(o), out.ctypes.data, mask.ctypes.data), "rs_pose_solve_batched")
+        return out, mask
+
+    def upload(self, cur_pose, matches, n_matches):
+        cur_pose = np.ascontiguousarray(cur_pose, dtype=np.float64)
+        matches = np.ascontiguousarray(matches)
+        n_matches = np.ascontiguousarray(n_matches, dtype=np.int32)
+        _check(self._lib.rs_pose_upload(self._ctx, cur_pose.ctypes.data, matches.ctypes.data, n_matches.ctypes.data,
+                                        cur_pose.shape[0]), "rs_pose_upload")
+
+    def solve_device(self, batch, opts, stream=0):
+        _check(self._lib.rs_pose_solve_device(self._ctx, batch, C.byref(opts), stream), "rs_pose_solve_device")
+
+    def download(self, batch):
+        out = np.zeros((batch,), dtype=abi.pose_out_dtype)
+        mask = np.zeros((batch, self.max_matches), dtype=np.uint8)
+        _check(self._lib.rs_pose_download(self._ctx, batch, out.ctypes.data, mask.ctypes.data), "rs_pose_download")
+        return out, mask
+
+    def device_poses_ptr(self):
+        return self._lib.rs_pose_device_poses(self._ctx)
+
+    def export_random(self, batch, n_iterations, n_variance):
+        subsets = np.full((batch, n_iterations, abi.RS_MAX_SUBSET), -1, dtype=np.int32)
+        normals = np.zeros((batch, max(n_variance, 1), self.max_matches, 4), dtype=np.float64)
+        _check(self._lib.rs_pose_export_random(self._ctx, batch, subsets.ctypes.data, normals.ctypes.data), "rs_pose_export_random")
+        return subsets, normals

@@ -1,0 +1,153 @@
+"""Synthetic inputs of the benchmark / parity workloads (SURVEY.md §8d "scene v0" and the pose correspondence sets).
+Pure numpy, deterministic per frame index. Units: millimetres / pixels / radians."""
+import numpy as np
+
+from . import abi
+
+# world <- camera axis change of the reference: x-forward/y-left/z-up <- x-right/y-down/z-forward
+# (camera_transformation.cpp:11-17; numerically [[0,0,1],[-1,0,0],[0,-1,0]])
+C_CAM_TO_WORLD = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+
+
+def intrinsics(scale=1):
+    return (550.0 * scale, 550.0 * scale, 320.0 * scale, 240.0 * scale)
+
+
+def scene_v0_depth(frame_index, width=640, height=480, sigma=1.0, zero_prob=0.02):
+    """One synthetic depth frame: four planes + a vertical cylinder, N(0, sigma) range noise on valid pixels and 2 %
+    invalid pixels. Returns float32 [H, W]. RNG = default_rng(frame_index): normal((H,W)) then random((H,W))."""
+    scale = width / 640.0
+    fx, fy, cx, cy = intrinsics(scale)
+    u = np.arange(width, dtype=np.float64)
+    v = np.arange(height, dtype=np.float64)
+    dx = ((u - cx) / fx)[None, :]
+    dy = ((v - cy) / fy)[:, None]
+    dx = np.broadcast_to(dx, (height, width))
+    dy = np.broadcast_to(dy, (height, width))
+    planes = [((0.0, 0.0, -1.0), 2500.0), ((0.0, -1.0, -0.05), 900.0), ((1.0, 0.0, -0.2), 1400.0),
+              ((-1.0, 0.0, -0.3), 1600.0)]
+    depth = np.full((height, width), np.inf)
+    for n, d0 in planes:
+        n = np.asarray(n, dtype=np.float64)
+        n = n / np.linalg.norm(n)
+        nr = n[0] * dx + n[1] * dy + n[2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = -d0 / nr
+        ok = (nr < 0) & (t > 0)
+        depth = np.where(ok & (t < depth), t, depth)
+    # vertical cylinder (axis parallel to y) through (x, z) = (300, 1800), radius 250: near root
+    a = dx * dx + 1.0
+    b = -2.0 * (300.0 * dx + 1800.0)
+    c = 300.0 ** 2 + 1800.0 ** 2 - 250.0 ** 2
+    disc = b * b - 4 * a * c
+    with np.errstate(invalid="ignore"):
+        t = (-b - np.sqrt(disc)) / (2 * a)
+    ok = (disc > 0) & (t > 0)
+    depth = np.where(ok & (t < depth), t, depth)
+    valid = np.isfinite(depth)
+    depth = np.where(valid, depth, 0.0)
+    rng = np.random.default_rng(frame_index)
+    noise = rng.normal(0.0, sigma, (height, width))
+    drop = rng.random((height, width)) < zero_prob
+    depth = np.where(valid, depth + noise, 0.0)
+    depth = np.where(drop, 0.0, depth)
+    return depth.astype(np.float32)
+
+
+def scene_v0_batch(first_frame, batch, width=640, height=480):
+    return np.stack([scene_v0_depth(first_frame + i, width, height) for i in range(batch)])
+
+
+# ---- pose helpers (numpy restatement used only to BUILD synthetic correspondences) --------------------
+def quat_from_euler(yaw, pitch, roll):
+    """AngleAxis(roll,X)*AngleAxis(pitch,Y)*AngleAxis(yaw,Z) as (w,x,y,z) (angle_utils.cpp:6-11)."""
+    def q(axis, ang):
+        s = np.sin(ang / 2)
+        return np.array([np.cos(ang / 2), *(s * np.asarray(axis, dtype=np.float64))])
+
+    def mul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                         a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3],
+                         a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1]])
+    return mul(mul(q((1, 0, 0), roll), q((0, 1, 0), pitch)), q((0, 0, 1), yaw))
+
+
+def quat_to_rot(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def camera_to_world(pose7):
+    """4x4 camera->world of a pose (x y z qw qx qy qz): C * [R t; 0 1] (camera_transformation.cpp:19-23)."""
+    T = np.eye(4)
+    T[:3, :3] = quat_to_rot(pose7[3:7])
+    T[:3, 3] = pose7[:3]
+    Cm = np.eye(4)
+    Cm[:3, :3] = C_CAM_TO_WORLD
+    return Cm @ T
+
+
+def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.1, scale=1, guess=0.9):
+    """Matched features of one frame: returns (true_pose7, guess_pose7, matches[n_points+n_planes]).
+    The last outlier_frac of each kind are outliers built like the reference's tests build them."""
+    rng = np.random.default_rng(1000 + frame_index)
+    fx, fy, cx, cy = intrinsics(scale)
+    d2r = np.pi / 180.0
+    yaw, pitch, roll = 45 * d2r, -45 * d2r, 20 * d2r
+    true_pose = np.concatenate([[10.0, 10.0, 10.0], quat_from_euler(yaw, pitch, roll)])
+    guess_pose = np.concatenate([np.array([10.0, 10.0, 10.0]) * guess, quat_from_euler(yaw * guess, pitch * guess, roll * guess)])
+    c2w = camera_to_world(true_pose)
+    w2c = np.linalg.inv(c2w)
+    m = np.zeros((n_points + n_planes,), dtype=abi.match_dtype)
+
+    # points: uniform in a 2 m x 2 m x (1..3 m) frustum in front of the true pose
+    pc = np.stack([rng.uniform(-1000, 1000, n_points), rng.uniform(-1000, 1000, n_points), rng.uniform(1000, 3000, n_points)], 1)
+    pw = (c2w[:3, :3] @ pc.T).T + c2w[:3, 3]
+    uv = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1) + rng.normal(0, 0.5, (n_points, 2))
+    n_out_pt = int(round(n_points * outlier_frac))
+    if n_out_pt:
+        uv[n_points - n_out_pt:, 0] = rng.uniform(0, 640 * scale, n_out_pt)
+        uv[n_points - n_out_pt:, 1] = rng.uniform(0, 480 * scale, n_out_pt)
+    m["type"][:n_points] = abi.RS_FEAT_POINT
+    m["obs"][:n_points, :2] = uv
+    m["map"][:n_points, :3] = pw
+    m["sigma"][:n_points, :3] = 5.0
+
+    # planes: random world planes transformed exactly to the camera frame (+ U(-5,5) mm on the observed d)
+    nw = rng.normal(size=(n_planes, 3))
+    nw /= np.linalg.norm(nw, axis=1, keepdims=True)
+    dw = rng.uniform(500, 3000, n_planes)
+    Rc, tc = c2w[:3, :3], c2w[:3, 3]
+    ncam = (Rc.T @ nw.T).T
+    dcam = nw @ tc + dw
+    dcam = dcam + rng.uniform(-5, 5, n_planes)
+    n_out_pl = int(round(n_planes * outlier_frac))
+    if n_out_pl:
+        r = rng.normal(size=(n_out_pl, 3))
+        ncam[n_planes - n_out_pl:] = r / np.linalg.norm(r, axis=1, keepdims=True)
+        dcam[n_planes - n_out_pl:] = rng.uniform(-100, 100, n_out_pl)
+    sl = slice(n_points, n_points + n_planes)
+    m["type"][sl] = abi.RS_FEAT_PLANE
+    m["obs"][sl, :3] = ncam
+    m["obs"][sl, 3] = dcam
+    m["map"][sl, :3] = nw
+    m["map"][sl, 3] = dw
+    m["sigma"][sl] = np.array([0.01, 0.01, 0.01, 1.0])
+    del w2c
+    return true_pose, guess_pose, m
+
+
+def pose_batch(first_frame, batch, max_matches, **kw):
+    cur = np.zeros((batch, 7))
+    truth = np.zeros((batch, 7))
+    matches = np.zeros((batch, max_matches), dtype=abi.match_dtype)
+    n = np.zeros((batch,), dtype=np.int32)
+    for b in range(batch):
+        t, g, m = pose_correspondences(first_frame + b, **kw)
+        truth[b], cur[b] = t, g
+        matches[b, :len(m)] = m
+        n[b] = len(m)
+    return truth, cur, matches, n

@@ -1,0 +1,115 @@
+"""TEST INFRASTRUCTURE: ctypes binding of the CPU oracle (oracle/_build/liboracle.so). Only tests/, smoke() and
+bench.py's CPU-baseline legs may import this; the product package never does."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+
+import rgbd_slam_b200 as rs  # noqa: E402  (abi structs only)
+
+abi = rs.abi
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        build()
+    lib = C.CDLL(LIB)
+    vp, i32, u32, dbl = C.c_void_p, C.c_int, C.c_uint32, C.c_double
+    lib.orc_cape_run.argtypes = [i32, i32, i32, dbl, dbl, dbl, dbl, vp, i32, u32, i32, C.POINTER(abi.CapeOutputs)]
+    lib.orc_cape_cell_fit.argtypes = [i32, i32, i32, dbl, dbl, dbl, dbl, vp, i32, vp, vp]
+    lib.orc_eigen3.argtypes = [vp, vp, vp]
+    lib.orc_world_to_camera.argtypes = [vp, vp, vp]
+    lib.orc_pose_coefficients.argtypes = [vp, vp]
+    lib.orc_pose_from_coefficients.argtypes = [vp, vp, vp]
+    lib.orc_quaternion_from_euler.argtypes = [dbl, dbl, dbl, vp]
+    lib.orc_residual_count.argtypes = [vp, i32]
+    lib.orc_pose_residuals.argtypes = [vp, vp, i32, vp, vp]
+    lib.orc_pose_lm.argtypes = [vp, vp, i32, vp, i32, vp]
+    lib.orc_pose_solve.argtypes = [vp, vp, vp, i32, i32, i32, u32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.orc_process_frames.restype = dbl
+    lib.orc_process_frames.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, u32, i32, vp]
+    lib.orc_ref_test_features.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32]
+    _lib = lib
+    return lib
+
+
+def cape_run(depth, cell=20, K=(550.0, 550.0, 320.0, 240.0), seed=0):
+    lib = load()
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    if depth.ndim == 2:
+        depth = depth[None]
+    B, H, W = depth.shape
+    Nc = (W // cell) * (H // cell)
+    arrs, st = abi.alloc_cape_outputs(B, Nc, 2 * Nc)
+    lib.orc_cape_run(W, H, cell, *K, depth.ctypes.data, B, seed, 2 * Nc, C.byref(st))
+    return arrs
+
+
+def cape_cell_fit(depth, cell=20, K=(550.0, 550.0, 320.0, 240.0), want_cloud=False):
+    lib = load()
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    if depth.ndim == 2:
+        depth = depth[None]
+    B, H, W = depth.shape
+    Nc = (W // cell) * (H // cell)
+    cells = np.zeros((B, Nc), dtype=abi.cell_dtype)
+    cloud = np.zeros((B, 3, W * H), dtype=np.float32) if want_cloud else None
+    lib.orc_cape_cell_fit(W, H, cell, *K, depth.ctypes.data, B, cells.ctypes.data, cloud.ctypes.data if want_cloud else None)
+    return (cells, cloud) if want_cloud else cells
+
+
+def pose_solve(cur_pose, matches, K=(550.0, 550.0, 320.0, 240.0), max_iterations=0, n_variance=-1, seed=0, subsets=None,
+               normals=None, max_matches=0, lm_max_fev=0, taps=False):
+    lib = load()
+    Kc = np.asarray(K, dtype=np.float64)
+    cur = np.ascontiguousarray(cur_pose, dtype=np.float64)
+    m = np.ascontiguousarray(matches)
+    n = len(m)
+    out = np.zeros((1,), dtype=abi.pose_out_dtype)
+    mask = np.zeros((n,), dtype=np.uint8)
+    iters = max_iterations if max_iterations > 0 else lib.orc_ransac_default_iterations()
+    cand_poses = np.zeros((iters, 7))
+    cand_ok = np.zeros((iters,), dtype=np.int32)
+    cand_scores = np.zeros((iters,))
+    subsets_out = np.full((iters, abi.RS_MAX_SUBSET), -1, dtype=np.int32)
+    if subsets is not None:
+        subsets = np.ascontiguousarray(subsets, dtype=np.int32)
+    if normals is not None:
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+    lib.orc_pose_solve(Kc.ctypes.data, cur.ctypes.data, m.ctypes.data, n, max_iterations, n_variance, seed,
+                       subsets.ctypes.data if subsets is not None else None,
+                       normals.ctypes.data if normals is not None else None, max_matches, lm_max_fev,
+                       out.ctypes.data, mask.ctypes.data, cand_poses.ctypes.data, cand_ok.ctypes.data,
+                       cand_scores.ctypes.data, subsets_out.ctypes.data)
+    if taps:
+        return out[0], mask, dict(cand_poses=cand_poses, cand_ok=cand_ok, cand_scores=cand_scores, subsets=subsets_out)
+    return out[0], mask
+
+
+def ref_test_features(true_pose, point_error=5.0, point_outliers=0.0, plane_error=5.0, plane_outliers=-1.0):
+    """Scenario builder of tests/test_pose_optimization.cpp. outliers < 0 disables that feature kind."""
+    lib = load()
+    tp = np.ascontiguousarray(true_pose, dtype=np.float64)
+    buf = np.zeros((512,), dtype=abi.match_dtype)
+    n = lib.orc_ref_test_features(tp.ctypes.data, point_error, point_outliers, plane_error, plane_outliers, buf.ctypes.data, 512)
+    return buf[:n].copy()
+
+
+def quaternion_from_euler(yaw, pitch, roll):
+    q = np.zeros(4)
+    load().orc_quaternion_from_euler(yaw, pitch, roll, q.ctypes.data)
+    return q

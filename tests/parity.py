@@ -1,0 +1,93 @@
+"""Comparison helpers of the parity tests (GPU library vs CPU oracle)."""
+import numpy as np
+
+
+def label_bijection(ref, got):
+    """Labels must agree up to a permutation: builds ref->got from first co-occurrence, 0 <-> 0. Returns the map."""
+    ref = np.asarray(ref).ravel()
+    got = np.asarray(got).ravel()
+    assert ref.shape == got.shape
+    fwd, bwd = {0: 0}, {0: 0}
+    for r, g in zip(ref.tolist(), got.tolist()):
+        if r in fwd:
+            assert fwd[r] == g, "label conflict: ref %d -> %d and %d" % (r, fwd[r], g)
+        else:
+            fwd[r] = g
+        if g in bwd:
+            assert bwd[g] == r, "label conflict: got %d <- %d and %d" % (g, bwd[g], r)
+        else:
+            bwd[g] = r
+    return fwd
+
+
+def assert_cells_match(ref, got, rtol=1e-4, exact_report=None):
+    """Per-cell records: integer fields bit-exact; normals / d within rtol (north_star: 1e-4 relative);
+    sums / mse / score tight. Returns the fraction of cells whose FP64 fields are bit-identical."""
+    assert np.array_equal(ref["count"], got["count"]), "point counts differ"
+    assert np.array_equal(ref["planar"], got["planar"]), "planar flags differ at cells %s" % np.argwhere(
+        ref["planar"] != got["planar"])[:8].tolist()
+    np.testing.assert_allclose(got["S"], ref["S"], rtol=1e-12, atol=1e-6)
+    pl = ref["planar"] == 1
+    fitted = ref["mse"] < 1e300
+    # normals: n.n_ref >= 1 - 1e-8 ; d: relative 1e-4
+    dots = np.sum(ref["normal"][fitted] * got["normal"][fitted], axis=-1)
+    assert np.all(dots >= 1 - 1e-8), "normal mismatch, min dot %r" % dots.min()
+    np.testing.assert_allclose(got["d"][fitted], ref["d"][fitted], rtol=rtol, atol=1e-6)
+    np.testing.assert_allclose(got["centroid"], ref["centroid"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(got["mse"][fitted], ref["mse"][fitted], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got["score"][fitted], ref["score"][fitted], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(got["mse"][~fitted], ref["mse"][~fitted])
+    np.testing.assert_allclose(got["tol"][pl], ref["tol"][pl], rtol=1e-6)
+    assert np.all(got["tol"][~pl] == 0)
+    same = np.ones(ref.shape, dtype=bool)
+    for f in ("S", "centroid", "normal"):
+        same &= np.all(ref[f] == got[f], axis=-1)
+    for f in ("d", "mse", "score", "tol"):
+        same &= ref[f] == got[f]
+    return float(same.mean())
+
+
+def assert_frame_match(ref, got, b=0, rtol=1e-4):
+    """Whole find_primitives output of frame b."""
+    ri, gi = ref["info"][b], got["info"][b]
+    for f in ("status", "n_planar_cells", "n_seeds", "n_planes", "n_final_planes", "n_cyl_regions", "n_cylinders", "n_boundary"):
+        assert ri[f] == gi[f], "info.%s: oracle %d, gpu %d" % (f, ri[f], gi[f])
+    # integer label grids: bit-exact up to permutation (they are in fact produced in the same order)
+    label_bijection(ref["plane_grid"][b], got["plane_grid"][b])
+    fwd = label_bijection(ref["plane_labels"][b], got["plane_labels"][b])
+    label_bijection(ref["cyl_labels"][b], got["cyl_labels"][b])
+    label_bijection(ref["cyl_region_seg"][b], got["cyl_region_seg"][b])
+    P = ri["n_planes"]
+    rp, gp = ref["planes"][b][:P], got["planes"][b][:P]
+    for f in ("merge_label", "planar", "is_final", "count", "n_boundary", "boundary_offset"):
+        assert np.array_equal(rp[f], gp[f]), "planes.%s differ: %s vs %s" % (f, rp[f], gp[f])
+    dots = np.sum(rp["normal"] * gp["normal"], axis=-1)
+    assert np.all(dots >= 1 - 1e-8)
+    np.testing.assert_allclose(gp["d"], rp["d"], rtol=rtol)
+    np.testing.assert_allclose(gp["S"], rp["S"], rtol=1e-12, atol=1e-6)
+    np.testing.assert_allclose(gp["mse"], rp["mse"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(gp["score"], rp["score"], rtol=1e-6)
+    nb = ri["n_boundary"]
+    np.testing.assert_allclose(got["boundary_xyz"][b][:nb], ref["boundary_xyz"][b][:nb], rtol=1e-12)
+    R = ri["n_cyl_regions"]
+    rc, gc = ref["cyls"][b][:R], got["cyls"][b][:R]
+    for f in ("n_cells", "n_segments", "n_inliers", "assigned", "kept"):
+        assert np.array_equal(rc[f], gc[f]), "cyls.%s differ" % f
+    np.testing.assert_allclose(gc["pca_score"], rc["pca_score"], rtol=1e-6)
+    for r in range(R):
+        ns = rc["n_segments"][r]
+        if ns:
+            assert abs(np.dot(rc["axis"][r], gc["axis"][r])) >= 1 - 1e-8
+        np.testing.assert_allclose(gc["radius"][r][:ns], rc["radius"][r][:ns], rtol=rtol)
+        np.testing.assert_allclose(gc["center"][r][:ns], rc["center"][r][:ns], rtol=rtol, atol=1e-6)
+        np.testing.assert_allclose(gc["mse"][r][:ns], rc["mse"][r][:ns], rtol=1e-6, atol=1e-9)
+    return fwd
+
+
+def pose_close(ref_pose, got_pose, rtol=1e-4):
+    """Pose parity (north_star): position within rtol of |t| (floor 1e-3 mm), quaternion sign-aligned."""
+    ref_pose, got_pose = np.asarray(ref_pose), np.asarray(got_pose)
+    tn = max(np.linalg.norm(ref_pose[:3]), 1.0)
+    dt = np.linalg.norm(ref_pose[:3] - got_pose[:3])
+    qd = abs(float(np.dot(ref_pose[3:], got_pose[3:])))
+    return dt <= max(rtol * tn, 1e-3) and qd >= 1 - 1e-8, dt, qd

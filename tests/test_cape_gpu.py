@@ -1,0 +1,95 @@
+"""GPU parity: CAPE through the C-ABI (librgbdslam_b200.so) vs the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import parity
+import rgbd_slam_b200 as rs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def det():
+    d = rs.PrimitiveDetection(640, 480, 20, max_batch=8)
+    yield d
+    d.close()
+
+
+def test_cell_fit_matches_oracle(det):
+    depth = rs.synth.scene_v0_batch(0, 4)
+    got = det.find_primitives(depth, cells_only=True)["cells"]
+    ref = ol.cape_cell_fit(depth)
+    for b in range(4):
+        frac = parity.assert_cells_match(ref[b], got[b])
+        # sums of FP32 values in FP64 are exact unless a cell straddles the optical axis; expect most cells bit-identical
+        assert frac > 0.9, "only %.3f of the cells are bit-identical" % frac
+
+
+def test_find_primitives_matches_oracle(det):
+    depth = rs.synth.scene_v0_batch(0, 8)
+    got = det.find_primitives(depth, seed=0)
+    ref = ol.cape_run(depth, seed=0)
+    for b in range(8):
+        parity.assert_frame_match(ref, got, b)
+    assert np.array_equal(ref["plane_labels"], got["plane_labels"])
+    assert np.array_equal(ref["cyl_labels"], got["cyl_labels"])
+
+
+def test_seed_changes_cylinder_draws_consistently(det):
+    depth = rs.synth.scene_v0_batch(3, 2)
+    for seed in (1, 12345):
+        got = det.find_primitives(depth, seed=seed)
+        ref = ol.cape_run(depth, seed=seed)
+        for b in range(2):
+            parity.assert_frame_match(ref, got, b)
+
+
+def test_edge_cases(det):
+    H, W = 480, 640
+    rng = np.random.default_rng(7)
+    frames = []
+    frames.append(np.zeros((H, W), np.float32))                                    # empty depth
+    frames.append(np.full((H, W), 1500.0, np.float32))                             # exact plane: singular scatter
+    f = rs.synth.scene_v0_depth(11)
+    f[:, ::2] = 0                                                                  # 50 % invalid columns
+    frames.append(f)
+    f = rs.synth.scene_v0_depth(12)
+    f[200:280, :] += 400.0                                                         # depth step through cell rows
+    frames.append(f)
+    frames.append((rng.uniform(500, 4000, (H, W))).astype(np.float32))             # pure noise: nothing planar
+    f = rs.synth.scene_v0_depth(13)
+    f[rng.random((H, W)) < 0.35] = 0                                               # ragged validity around the 280 limit
+    frames.append(f)
+    depth = np.stack(frames)
+    got = det.find_primitives(depth, seed=0)
+    ref = ol.cape_run(depth, seed=0)
+    for b in range(len(frames)):
+        parity.assert_cells_match(ref["cells"][b], got["cells"][b])
+        parity.assert_frame_match(ref, got, b)
+
+
+def test_large_cells_1280x960():
+    d = rs.PrimitiveDetection(1280, 960, 40, *rs.synth.intrinsics(2), max_batch=2)
+    depth = rs.synth.scene_v0_batch(0, 2, 1280, 960)
+    got = d.find_primitives(depth, seed=0)
+    ref = ol.cape_run(depth, cell=40, K=rs.synth.intrinsics(2), seed=0)
+    for b in range(2):
+        parity.assert_cells_match(ref["cells"][b], got["cells"][b])
+        parity.assert_frame_match(ref, got, b)
+    d.close()
+
+
+def test_batch_size_independent(det):
+    depth = rs.synth.scene_v0_batch(20, 8)
+    full = det.find_primitives(depth, seed=0)
+    one = det.find_primitives(depth[5:6], seed=0)
+    assert full["cells"][5].tobytes() == one["cells"][0].tobytes()
+    assert np.array_equal(full["plane_labels"][5], one["plane_labels"][0])
+
+
+def test_invalid_arguments(det):
+    with pytest.raises(rs.RsError):
+        det.find_primitives(rs.synth.scene_v0_batch(0, 9))   # batch > max_batch
+    with pytest.raises(rs.RsError):
+        rs.PrimitiveDetection(640, 480, 18)                    # cell side not a multiple of 4
