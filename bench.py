@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the RGB-D per-frame hot path (CAPE plane/cylinder segmentation + RANSAC/LM pose solve).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework on N B200s (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU path (restated oracle) on the host cores
+
+A "step" = one pass of the hot path over one batch of synthetic 640x480 RGB-D frames per GPU (BASELINE.json
+configs[2]/[3]: full frame = CAPE plane + cylinder extraction, then the 300-point / 20-plane RANSAC-LM pose solve
+with its 100-sample Monte-Carlo covariance). Frames shard across ranks with no data-path collective; the single
+collective is the all-gather of the per-frame poses (weak scaling: frames per GPU fixed).
+Prints ONE JSON line on rank 0 (see README / DESIGN.md "Measurement")."""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, CELL = 640, 480, 20
+N_CELLS = (W // CELL) * (H // CELL)
+N_POINTS, N_PLANES = 300, 20
+MAX_MATCHES = N_POINTS + N_PLANES
+K1_BYTES_PER_FRAME = 4 * W * H + 160 * N_CELLS  # depth read once + one 160 B record per cell
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--frames-per-gpu", type=int, default=256)
+    p.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 10))")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def make_inputs(first_frame, n_frames):
+    import rgbd_slam_b200 as rs
+    depth = np.empty((n_frames, H, W), dtype=np.float32)
+    for i in range(n_frames):
+        depth[i] = rs.synth.scene_v0_depth(first_frame + i)
+    truth, cur, matches, n = rs.synth.pose_batch(first_frame, n_frames, MAX_MATCHES, n_points=N_POINTS, n_planes=N_PLANES)
+    return depth, truth, cur, matches, n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [v.strip() for v in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_port_frames_per_s(depth, cur, matches, n, n_threads, frames=None):
+    """Times the CPU oracle (restated reference path: CAPE + RANSAC/LM pose + covariance) on `frames` frames."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    lib = ol.load()
+    B = len(depth) if frames is None else min(frames, len(depth))
+    K = np.array([550.0, 550.0, 320.0, 240.0])
+    poses = np.zeros((B, 7))
+    sec = lib.orc_process_frames(W, H, CELL, K.ctypes.data, depth.ctypes.data, cur.ctypes.data, matches.ctypes.data,
+                                 n.ctypes.data, MAX_MATCHES, B, 1, 1, 119, 100, 0, n_threads, poses.ctypes.data)
+    return B / sec, sec, B
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path. The reference binary cannot be built
+    (Eigen / OpenCV C++ / TBB / boost / flann absent, no network), so this is the restated oracle, all host threads
+    over the frame loop (the reference's TBB build parallelises the RANSAC / variance loops instead)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = min(args.frames_per_gpu, 64)
+    depth, truth, cur, matches, n = make_inputs(0, sample)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_frames_per_s(depth, cur, matches, n, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_frames_per_s(depth, cur, matches, n, threads)
+    sec = time.perf_counter() - t0
+    fps = sample * args.steps / sec
+    line = {
+        "impl": "reference", "metric": "RGB-D frames/sec (640x480)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "640x480 full frame: CAPE plane+cylinder extraction + 300-point/20-plane RANSAC-LM pose "
+                               "solve + 100-sample covariance (BASELINE configs[2])", "frames_per_step": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d synthetic frames per step, frame loop over %d host threads" % (sample, threads)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import rgbd_slam_b200 as rs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    F = args.frames_per_gpu
+    steps, warmup = args.steps, max(args.warmup, 3)
+    depth, truth, cur, matches, n = make_inputs(rank * F, F)
+
+    det = rs.PrimitiveDetection(W, H, CELL, max_batch=F, device=local_rank)
+    solver = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=119, max_variance=100, device=local_rank)
+    opts = solver.options(seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE)
+
+    # ---- HBM-resident leg: inputs live on the device before the timed region ----
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    d_depth = torch.from_numpy(depth).cuda()
+    solver.upload(cur, matches, n)
+    gathered = torch.zeros((world, F, 7), dtype=torch.float64, device="cuda")
+
+    class _DevPtr:  # zero-copy torch view of the library's pose buffer (the all-gather payload)
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3}
+    poses_view = torch.as_tensor(_DevPtr(solver.device_poses_ptr(), (F, 7)), device="cuda")
+
+    def step():
+        det.run_device(d_depth.data_ptr(), F, seed=0, stream=sptr)
+        solver.solve_device(F, opts, stream=sptr)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), poses_view.view(-1))
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    det.set_timing(steps)
+    solver.set_timing(steps)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = rs.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = rs.launch_count() - launches0
+    clocks = sampler.stop()
+    k1_ms = float(np.mean([det.kernel_ms(s)[0] for s in range(steps)]))
+    seg_ms = float(np.mean([det.kernel_ms(s)[1] for s in range(steps)]))
+    pose_ms = np.mean([solver.kernel_ms(s) for s in range(steps)], axis=0)
+    det.set_timing(0)
+    solver.set_timing(0)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * F * steps / (ms_total * 1e-3)
+
+    # sanity: the timed work produced valid poses close to the synthetic truth
+    out, _ = solver.download(F)
+    ok_frac = float((out["status"] == 1).mean())
+    pos_err = float(np.median(np.linalg.norm(out["pose"][:, :3] - truth[:, :3], axis=1)))
+
+    # ---- end-to-end leg: host (pinned) buffers through the public host API, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = args.e2e_steps or min(steps, 10)
+        h_depth = torch.from_numpy(depth).pin_memory()
+        h_depth_np = h_depth.numpy()
+        arrs, st = rs.abi.alloc_cape_outputs(F, det.n_cells, det.max_boundary)
+        wanted = ("plane_labels", "cyl_labels", "planes", "cyls", "boundary_xyz", "info")
+        pinned = {}
+        for k in wanted:  # results land in pinned host memory
+            tns = torch.empty(arrs[k].nbytes, dtype=torch.uint8).pin_memory()
+            pinned[k] = tns
+            arrs[k] = tns.numpy().view(arrs[k].dtype).reshape(arrs[k].shape)
+        st = rs.abi.CapeOutputs(**{k: arrs[k].ctypes.data for k in wanted})
+        h_matches = torch.from_numpy(matches.view(np.uint8).reshape(F, -1)).pin_memory()
+        h_matches_np = h_matches.numpy().view(rs.abi.match_dtype).reshape(F, MAX_MATCHES)
+
+        def e2e_step():
+            det.find_primitives(h_depth_np, seed=0, out=(arrs, st))
+            o, m = solver.compute_optimized_pose(cur, h_matches_np, n, opts)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered.view(-1), poses_view.view(-1))
+                torch.cuda.synchronize()
+            return o
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            o = e2e_step()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+        h2d = int(h_depth_np.nbytes + h_matches_np.nbytes + cur.nbytes + n.nbytes)
+        d2h = int(sum(arrs[k].nbytes for k in wanted) + o.nbytes + F * MAX_MATCHES)
+        e2e = {"value": world * F * e2e_steps / sec, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "timing": "host wall clock around synchronous C-ABI calls, max over ranks"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        fps_all, sec_all, nf = cpu_port_frames_per_s(depth, cur, matches, n, threads)
+        fps_1, sec_1, nf1 = cpu_port_frames_per_s(depth, cur, matches, n, 1, frames=32)
+        cpu = {"value": fps_all, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "the %d frames of one step, frame loop over %d host threads (%.2f s); 1 thread on %d frames: %.1f frames/s"
+                         % (nf, threads, sec_all, nf1, fps_1),
+               "value_1_thread": fps_1}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = K1_BYTES_PER_FRAME * F / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("frames_per_launch") == F:
+                traffic = tj.get("dram_bytes_per_launch")
+        line = {
+            "metric": "RGB-D frames/sec (640x480)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "640x480 full frame: CAPE plane+cylinder extraction + 300-point/20-plane RANSAC-LM pose solve + "
+                            "100-sample covariance (BASELINE configs[2]), batch of %d frames per GPU per step (configs[3] batch)" % F,
+                "frames_per_gpu": F, "cell_px": CELL, "cells_per_frame": N_CELLS, "ransac_hypotheses": 119, "n_variance": 100,
+                "l2": "inputs larger than L2 (%.0f MB of depth per step per GPU vs 126 MB)" % (depth.nbytes / 1e6),
+                "rng": "RS_RNG_DEVICE (counter-based on-device draws)", "collective": "all-gather of [frames x 7] f64 poses" if world > 1 else "none",
+            },
+            "roofline": {"kernel": "cape_cell_fit (K1)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_launch": K1_BYTES_PER_FRAME * F, "ms_per_launch": k1_ms},
+            "kernels_ms_per_step": {"cape_cell_fit": k1_ms, "cape_segment": seg_ms, "pose_prepare": float(pose_ms[0]),
+                                    "pose_ransac_final_lm": float(pose_ms[1]), "pose_variance": float(pose_ms[2]),
+                                    "pose_covariance": float(pose_ms[3])},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "check": {"frames_with_valid_pose": ok_frac, "median_position_error_mm": pos_err},
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

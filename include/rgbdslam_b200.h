@@ -140,6 +140,14 @@ int rs_cape_cell_fit_device(rs_cape_ctx* ctx, const float* depth_dev, int batch,
 float* rs_cape_device_depth(rs_cape_ctx* ctx);                  /* max_batch x H x W                 */
 const rs_cape_outputs* rs_cape_device_outputs(rs_cape_ctx* ctx); /* device pointers, max_batch frames */
 
+/* Per-kernel device timing (replaces the cv::getTickCount accumulators of Primitive_Detection,
+ * primitive_detection.hpp:233-239 / .cpp:124-165). n_slots > 0 allocates n_slots rings of CUDA events that
+ * every following run records on its launching stream around each kernel (run i uses slot i % n_slots);
+ * n_slots = 0 turns it off. rs_cape_kernel_ms waits for that slot's events and returns
+ * ms[0] = plane-fit kernel (K1), ms[1] = segmentation kernel (K2-K4; 0 for cell-fit-only runs). */
+int rs_cape_set_timing(rs_cape_ctx* ctx, int n_slots);
+int rs_cape_kernel_ms(rs_cape_ctx* ctx, int slot, float ms[2]);
+
 /* ---- pose solve ------------------------------------------------------------------------- */
 #define RS_FEAT_POINT 0    /* PointOptimizationFeature  (map_point.cpp:16-65)    2 residuals, score 1/5 */
 #define RS_FEAT_PLANE 1    /* PlaneOptimizationFeature  (map_primitive.cpp:15-85) 3 residuals, score 1/3 */
@@ -200,6 +208,12 @@ int rs_pose_upload(rs_pose_ctx* ctx, const double* cur_pose, const rs_match* mat
 int rs_pose_solve_device(rs_pose_ctx* ctx, int batch, const rs_pose_opts* opts, void* stream);
 int rs_pose_download(rs_pose_ctx* ctx, int batch, rs_pose_out* out, uint8_t* inlier_mask);
 double* rs_pose_device_poses(rs_pose_ctx* ctx); /* B x 7 doubles on the device (the all-gather payload) */
+
+/* Per-kernel device timing, as rs_cape_set_timing (replaces the static timing doubles of Pose_Optimization,
+ * pose_optimization.hpp:97-102). ms[0] = prepare, ms[1] = RANSAC + final LM, ms[2] = Monte-Carlo LM solves,
+ * ms[3] = covariance reduction. */
+int rs_pose_set_timing(rs_pose_ctx* ctx, int n_slots);
+int rs_pose_kernel_ms(rs_pose_ctx* ctx, int slot, float ms[4]);
 
 /* Debug/parity taps (RS_RNG_DEVICE): the random inputs the last solve used, so that the checker
  * can feed the same ones to the oracle. subsets = B x max_iterations x RS_MAX_SUBSET int32 (-1 padded);

@@ -797,6 +797,7 @@ PoseSolveResult pose_solve(const Intrinsics& K, const Pose7& cur, const std::vec
     PoseSolveResult R;
     rs_pose_out& out = R.out;
     out = rs_pose_out{};
+    out.best_iteration = -1;
     std::vector<rs_match> feats = featsIn;
     normalize_features(feats);
     const size_t Nf = feats.size();

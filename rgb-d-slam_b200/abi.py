@@ -1,5 +1,5 @@
 """ctypes mirror of include/rgbdslam_b200.h (POD structs and constants). Shared by the product binding (lib.py)
-and by the test-side oracle binding (tests/oracle_lib.py); contains no computation."""
+and by the test-side checker binding under tests/; contains no computation."""
 import ctypes as C
 
 import numpy as np

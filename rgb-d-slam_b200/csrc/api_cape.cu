@@ -86,6 +86,9 @@ struct rs_cape_ctx {
     int tmap_batch = 0;
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;  // 3 per timing slot
+    int timing_slots = 0;
+    uint64_t run_counter = 0;
 };
 
 namespace {
@@ -209,7 +212,14 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     if (rc != RS_OK) return rc;
     CellFitParams fp = c->fit;
     fp.batch = batch;
+    cudaEvent_t* ev = c->timing_slots > 0 ? &c->events[size_t(c->run_counter % uint64_t(c->timing_slots)) * 3] : nullptr;
+    ++c->run_counter;
+    if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], stream));
     if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream)) != RS_OK) return rc;
+    if (ev) {
+        RS_CUDA_CHECK(cudaEventRecord(ev[1], stream));
+        if (cells_only) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+    }
     if (cells_only) return RS_OK;
     if (!o->plane_grid || !o->plane_labels || !o->cyl_labels || !o->cyl_region_seg || !o->planes || !o->cyls ||
         !o->boundary_xyz || !o->info) {
@@ -230,7 +240,9 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     sb.cyls = o->cyls;
     sb.boundary_xyz = o->boundary_xyz;
     sb.info = o->info;
-    return launch_cape_segment(sp, sb, stream);
+    if ((rc = launch_cape_segment(sp, sb, stream)) != RS_OK) return rc;
+    if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+    return RS_OK;
 }
 
 }  // namespace
@@ -275,8 +287,37 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_out.boundary_xyz);
     cudaFree(c->d_out.info);
     cudaFree(c->d_uniforms);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+int rs_cape_set_timing(rs_cape_ctx* c, int n_slots)
+{
+    if (!c || n_slots < 0 || n_slots > 4096) {
+        set_last_error("rs_cape_set_timing: invalid argument");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    c->events.assign(size_t(n_slots) * 3, nullptr);
+    for (cudaEvent_t& e : c->events) RS_CUDA_CHECK(cudaEventCreate(&e));
+    c->timing_slots = n_slots;
+    c->run_counter = 0;
+    return RS_OK;
+}
+
+int rs_cape_kernel_ms(rs_cape_ctx* c, int slot, float ms[2])
+{
+    if (!c || !ms || slot < 0 || slot >= c->timing_slots || uint64_t(slot) >= c->run_counter) {
+        set_last_error("rs_cape_kernel_ms: timing is off or that slot has not been recorded");
+        return RS_ERR_INVALID_ARG;
+    }
+    cudaEvent_t* ev = &c->events[size_t(slot) * 3];
+    RS_CUDA_CHECK(cudaEventSynchronize(ev[2]));
+    RS_CUDA_CHECK(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
+    RS_CUDA_CHECK(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));
+    return RS_OK;
 }
 
 int rs_cape_cells_per_frame(const rs_cape_ctx* c) { return c ? c->Nc : 0; }

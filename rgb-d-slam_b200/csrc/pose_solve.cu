@@ -1,0 +1,1291 @@
+// K5 / K6 — per-frame RANSAC + Levenberg-Marquardt pose solve and its Monte-Carlo covariance.
+//
+// Replaces  Pose_Optimization::{compute_optimized_pose, compute_pose_with_ransac, compute_optimized_global_pose,
+//           get_features_inliers_outliers, compute_pose_variance, compute_random_variation_of_pose}
+//           (src/pose_optimization/pose_optimization.cpp:33-72,107-437,482-501),
+//           Global_Pose_Estimator::operator() + the coefficient <-> pose maps (levenberg_marquardt_functors.cpp:14-38,
+//           74-98,128-169), ransac::get_random_subset_with_score (ransac.hpp:77-103), the Point/Plane
+//           IOptimizationFeature implementations (map_point.cpp:16-65, map_primitive.cpp:15-85) and the transforms
+//           they call (camera_transformation.cpp:11-71, point_coordinates.cpp:245-278, plane_coordinates.cpp:20-56),
+//           plus Eigen::LevenbergMarquardt<NumericalDiff<F, Forward>>::minimize (MINPACK lmdif: forward-difference
+//           Jacobian, trust region with lmpar / qrsolv).
+//
+// Mapping (B200): ONE WARP PER LM PROBLEM. Features are lane-strided; every lane evaluates its features' residuals
+// at x and at the six forward-difference points, forms its rows of J, and accumulates the 6x6 J^T J, the 6x1 J^T r
+// and |r|^2 in FP64 registers; a warp-shuffle butterfly reduces the 28 sums. The m x 6 Jacobian is never stored.
+// Lane 0 then does the MINPACK step on shared-memory 6x6 state: the triangular factor R of J P = Q R is obtained as
+// the pivoted Cholesky factor of the column-scaled J^T J (same R up to row signs, to which lmpar is invariant), and
+// Q^T r = R^-T P^T J^T r. The trust-region logic (lmpar, qrsolv, ratio tests, stop codes 1-8, nfev accounting incl.
+// the redundant f(x) of NumericalDiff) is MINPACK's, so iterates follow the reference's path up to rounding.
+//   pose_ransac_kernel   : one CTA per frame, one warp per hypothesis, chunks of WARPS hypotheses with the
+//                          reference's serial best-so-far / early-stop rule applied between chunks by thread 0
+//                          (hypotheses are independent: each LM starts from the current pose), then the final LM
+//                          on the winning inlier set.
+//   pose_variance_kernel : one warp per Monte-Carlo sample (perturbed copy of the inlier set in shared memory).
+//   pose_covariance_kernel: one thread per frame, sums in sample order, 6x6 covariance + validity.
+// FP64 throughout (forward differences with h = 1.49e-8 |x| on mm-scale coordinates need it).
+#include <float.h>
+
+#include "plane_fit.cuh"  // make_givens
+#include "pose_internal.cuh"
+
+namespace rs {
+
+namespace {
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double kSqrtEps = 1.4901161193847656e-08;  // sqrt(DBL_EPSILON): ftol, xtol and the difference step
+constexpr int kRunning = -100;
+
+// parameters.hpp:23-44
+constexpr double kPointInlierPx = 3.0;                       // float 3.0f
+constexpr double kPlaneInlierMm = 50.0;                      // float 50.0f
+constexpr double kPlaneInlierNormal = 0.20000000298023224;   // float 0.2f
+constexpr double kEarlyStopProportion = 0.800000011920929;   // double initialised from 0.80f
+constexpr double kPointScore = 1.0 / 5.0;                    // 1 / minimumPointForOptimization
+constexpr double kPlaneScore = 1.0 / 3.0;                    // 1 / minimumPlanesForOptimization
+
+// world <- camera rotation of the pose: R' = C * R(q), t' = C * t with C = [[0,0,1],[-1,0,0],[0,-1,0]]
+// (camera_transformation.cpp:11-23). world->camera is then p_c = R'^T (P - t') and the plane world->camera map
+// (inverse of [[R',0],[-t'^T R',1]], :52-71) is n_c = R'^T n_w, d_c = t'.n_w + d_w.
+struct Xform {
+    double R[9];
+    double t[3];
+};
+
+struct WarpLM {
+    double x[6], xt[6], diag[6], qtf[6], p[6], wa1[6], wa2[6], wa3[6], g[6], h[6], sdiag[6], xs[6];
+    double A[36];  // J^T J, then scratch of the factorisation
+    double R[36];  // upper-triangular factor, row-major
+    double s[36];  // qrsolv working copy
+    Xform T[7];    // transforms at x (0) and x + h_j e_j (1..6); T[0] is reused for the trial point
+    double fnorm, par, delta, xnorm, gnorm, pnorm;
+    int perm[6];
+    int rank, status, nfev, iter, again, pad;
+};
+
+// Features of one LM problem: indices into the frame arrays (idx == nullptr: identity), lane-strided.
+struct Problem {
+    int n;
+    const short* idx;
+    const int32_t* type;  // [M]
+    const double* obs;    // [4][M]
+    const double* map;    // [4][M]
+    int M;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// levenberg_marquardt_functors.cpp:29-38,82-86 + PoseBase normalisation (pose.cpp:18-22)
+__device__ inline void quaternion_from_coefficients(const double* x, double q[4])
+{
+    const double alpha = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
+    const double divider = 1.0 / (alpha + 1.0);
+    q[0] = 2.0 * x[3] * divider;
+    q[1] = 2.0 * x[4] * divider;
+    q[2] = 2.0 * x[5] * divider;
+    q[3] = (1.0 - alpha) * divider;
+    const double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (nn > 0.0) {
+        q[0] /= nn, q[1] /= nn, q[2] /= nn, q[3] /= nn;
+    }
+}
+
+// Quaternion (w,x,y,z) -> rotation (Eigen toRotationMatrix), row-major
+__device__ inline void quat_to_rot(const double q[4], double r[9])
+{
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    r[0] = 1.0 - (tyy + tzz), r[1] = txy - twz, r[2] = txz + twy;
+    r[3] = txy + twz, r[4] = 1.0 - (txx + tzz), r[5] = tyz - twx;
+    r[6] = txz - twy, r[7] = tyz + twx, r[8] = 1.0 - (txx + tyy);
+}
+
+__device__ inline void make_xform(const double* x, Xform& T)
+{
+    double q[4], r[9];
+    quaternion_from_coefficients(x, q);
+    quat_to_rot(q, r);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        T.R[0 + j] = r[6 + j];
+        T.R[3 + j] = -r[0 + j];
+        T.R[6 + j] = -r[3 + j];
+    }
+    T.t[0] = x[2], T.t[1] = -x[0], T.t[2] = -x[1];
+}
+
+// levenberg_marquardt_functors.cpp:14-27,74-80
+__device__ inline void coefficients_from_pose(const double* pose7, double x[6])
+{
+    x[0] = pose7[0], x[1] = pose7[1], x[2] = pose7[2];
+    const double divider = 1.0 / fmax(1.0 + pose7[6], 0.001);
+    x[3] = pose7[3] * divider;
+    x[4] = pose7[4] * divider;
+    x[5] = pose7[5] * divider;
+}
+
+// MatrixBase::eulerAngles(0,1,2) of R(q) (PoseBase::get_vector, pose.hpp:30-35)
+__device__ inline void pose_vector6(const double* x, double v[6])
+{
+    double q[4], m[9];
+    quaternion_from_coefficients(x, q);
+    quat_to_rot(q, m);
+    v[0] = x[0], v[1] = x[1], v[2] = x[2];
+    double r0 = atan2(m[5], m[8]), r1;
+    const double c2 = sqrt(m[0] * m[0] + m[1] * m[1]);
+    if (r0 > 0.0) {
+        r0 -= kPi;
+        r1 = atan2(-m[2], -c2);
+    }
+    else {
+        r1 = atan2(-m[2], c2);
+    }
+    const double s1 = sin(r0), c1 = cos(r0);
+    const double r2 = atan2(s1 * m[6] - c1 * m[3], c1 * m[4] - s1 * m[7]);
+    v[3] = -r0, v[4] = -r1, v[5] = -r2;
+}
+
+// WorldCoordinate::get_signed_distance_2D_px (point_coordinates.cpp:245-260)
+__device__ __forceinline__ void point_distance(const double o0, const double o1, const double X, const double Y,
+                                               const double Z, const Xform& T, const PoseIntrinsics& K, double& du,
+                                               double& dv)
+{
+    const double d0 = X - T.t[0], d1 = Y - T.t[1], d2 = Z - T.t[2];
+    const double xc = (T.R[0] * d0 + T.R[3] * d1) + T.R[6] * d2;
+    const double yc = (T.R[1] * d0 + T.R[4] * d1) + T.R[7] * d2;
+    const double zc = (T.R[2] * d0 + T.R[5] * d1) + T.R[8] * d2;
+    const double inv = 1.0 / zc;
+    const double u = inv * (K.fx * xc + K.cx * zc);
+    const double v = inv * (K.fy * yc + K.cy * zc);
+    if (u != u || v != v) {
+        du = DBL_MAX, dv = DBL_MAX;
+        return;
+    }
+    du = o0 - u;
+    dv = o1 - v;
+}
+
+// PlaneWorldCoordinates::to_camera_coordinates (plane_coordinates.cpp:20-24): n renormalised, d kept
+__device__ __forceinline__ void plane_to_camera(const double n0, const double n1, const double n2, const double dw,
+                                                const Xform& T, double np[3], double& dp)
+{
+    double v0 = (T.R[0] * n0 + T.R[3] * n1) + T.R[6] * n2;
+    double v1 = (T.R[1] * n0 + T.R[4] * n1) + T.R[7] * n2;
+    double v2 = (T.R[2] * n0 + T.R[5] * n1) + T.R[8] * n2;
+    const double z = (v0 * v0 + v1 * v1) + v2 * v2;
+    if (z > 0.0) {
+        const double s = sqrt(z);
+        v0 /= s, v1 /= s, v2 /= s;
+    }
+    np[0] = v0, np[1] = v1, np[2] = v2;
+    dp = ((T.t[0] * n0 + T.t[1] * n1) + T.t[2] * n2) + dw;
+}
+
+// One feature's residual entries (Global_Pose_Estimator::operator(), levenberg_marquardt_functors.cpp:128-169):
+// point -> 1/2 (du, dv); plane -> 1/3 (d_c n_c - d_p n_p). Returns the entry count.
+__device__ __forceinline__ int feature_residual(const int type, const double o[4], const double m[4], const Xform& T,
+                                                const PoseIntrinsics& K, double r[3])
+{
+    if (type == RS_FEAT_POINT) {
+        double du, dv;
+        point_distance(o[0], o[1], m[0], m[1], m[2], T, K, du, dv);
+        r[0] = du * 1.0 / 2.0;
+        r[1] = dv * 1.0 / 2.0;
+        r[2] = 0.0;
+        return 2;
+    }
+    double np[3], dp;
+    plane_to_camera(m[0], m[1], m[2], m[3], T, np, dp);
+    r[0] = (o[3] * o[0] - dp * np[0]) * 1.0 / 3.0;
+    r[1] = (o[3] * o[1] - dp * np[1]) * 1.0 / 3.0;
+    r[2] = (o[3] * o[2] - dp * np[2]) * 1.0 / 3.0;
+    return 3;
+}
+
+__device__ __forceinline__ double angle_distance(const double a, const double b)
+{
+    return atan2(sin(a - b), cos(a - b));  // distance_utils.cpp:6-9
+}
+
+// IOptimizationFeature::is_inlier (map_point.cpp:34-38, map_primitive.cpp:33-49)
+__device__ __forceinline__ bool feature_is_inlier(const int type, const double o[4], const double m[4], const Xform& T,
+                                                  const PoseIntrinsics& K)
+{
+    if (type == RS_FEAT_POINT) {
+        double du, dv;
+        point_distance(o[0], o[1], m[0], m[1], m[2], T, K, du, dv);
+        const double dist = (du >= DBL_MAX || dv >= DBL_MAX) ? DBL_MAX : fabs(du) + fabs(dv);
+        return dist <= kPointInlierPx;
+    }
+    double np[3], dp;
+    plane_to_camera(m[0], m[1], m[2], m[3], T, np, dp);
+    return fabs(angle_distance(o[0], np[0])) <= kPlaneInlierNormal && fabs(angle_distance(o[1], np[1])) <= kPlaneInlierNormal &&
+           fabs(angle_distance(o[2], np[2])) <= kPlaneInlierNormal && fabs(o[3] - dp) <= kPlaneInlierMm;
+}
+
+__device__ __forceinline__ void load_feature(const Problem& P, const int k, int& type, double o[4], double m[4])
+{
+    const int i = P.idx ? int(P.idx[k]) : k;
+    type = P.type[i];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        o[c] = P.obs[c * P.M + i];
+        m[c] = P.map[c * P.M + i];
+    }
+}
+
+// |f(x)|^2 over the problem's features with transform T (warp-wide result)
+__device__ inline double eval_sumsq(const Problem& P, const Xform& T, const PoseIntrinsics& K, const int lane)
+{
+    double ss = 0.0;
+    for (int k = lane; k < P.n; k += 32) {
+        int type;
+        double o[4], m[4], r[3];
+        load_feature(P, k, type, o, m);
+        feature_residual(type, o, m, T, K, r);
+        ss += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    }
+    return warp_sum(ss);
+}
+
+// ---- lane-0 algebra on the shared 6x6 state ---------------------------------------------------------------------
+__device__ inline double norm6(const double* v)
+{
+    double s = 0.0;
+    for (int i = 0; i < 6; ++i) s += v[i] * v[i];
+    return sqrt(s);
+}
+
+// R (upper, with column permutation perm) such that R^T R = P^T (J^T J) P, via diagonal-pivoted Cholesky of the
+// column-scaled matrix; qtf = R^-T P^T (J^T r) = first 6 entries of Q^T r. wa2 = column norms of J.
+__device__ inline void factorize(WarpLM& S)
+{
+    double* C = S.A;
+    for (int j = 0; j < 6; ++j) S.wa2[j] = sqrt(fmax(C[j * 6 + j], 0.0));
+    double sc[6];
+    for (int j = 0; j < 6; ++j) sc[j] = S.wa2[j] > 0.0 ? 1.0 / S.wa2[j] : 1.0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) C[i * 6 + j] = C[i * 6 + j] * sc[i] * sc[j];
+    for (int j = 0; j < 6; ++j) S.perm[j] = j;
+    for (int i = 0; i < 36; ++i) S.R[i] = 0.0;
+    int rank = 6;
+    for (int k = 0; k < 6; ++k) {
+        int piv = k;
+        double best = C[k * 6 + k];
+        for (int i = k + 1; i < 6; ++i)
+            if (C[i * 6 + i] > best) {
+                best = C[i * 6 + i];
+                piv = i;
+            }
+        if (piv != k) {
+            for (int j = 0; j < 6; ++j) {
+                const double t = C[k * 6 + j];
+                C[k * 6 + j] = C[piv * 6 + j];
+                C[piv * 6 + j] = t;
+            }
+            for (int i = 0; i < 6; ++i) {
+                const double t = C[i * 6 + k];
+                C[i * 6 + k] = C[i * 6 + piv];
+                C[i * 6 + piv] = t;
+            }
+            for (int i = 0; i < k; ++i) {
+                const double t = S.R[i * 6 + k];
+                S.R[i * 6 + k] = S.R[i * 6 + piv];
+                S.R[i * 6 + piv] = t;
+            }
+            const int t = S.perm[k];
+            S.perm[k] = S.perm[piv];
+            S.perm[piv] = t;
+        }
+        // the scaled matrix has unit diagonal: a pivot at rounding level means a dependent column
+        if (!(best > 64.0 * DBL_EPSILON)) {
+            rank = k;
+            break;
+        }
+        const double rkk = sqrt(best);
+        S.R[k * 6 + k] = rkk;
+        for (int j = k + 1; j < 6; ++j) S.R[k * 6 + j] = C[k * 6 + j] / rkk;
+        for (int i = k + 1; i < 6; ++i)
+            for (int j = i; j < 6; ++j) {
+                C[i * 6 + j] -= S.R[k * 6 + i] * S.R[k * 6 + j];
+                C[j * 6 + i] = C[i * 6 + j];
+            }
+    }
+    S.rank = rank;
+    // undo the column scaling: R[:, j] *= |J col perm[j]|
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) S.R[i * 6 + j] *= S.wa2[S.perm[j]];
+    // qtf: forward substitution with R^T
+    for (int i = 0; i < 6; ++i) {
+        if (i >= rank) {
+            S.qtf[i] = 0.0;
+            continue;
+        }
+        double sum = S.g[S.perm[i]];
+        for (int k = 0; k < i; ++k) sum -= S.R[k * 6 + i] * S.qtf[k];
+        S.qtf[i] = sum / S.R[i * 6 + i];
+    }
+}
+
+// unsupported/Eigen/src/NonLinearOptimization/qrsolv.h on the 6x6 working copy s
+__device__ inline void qrsolv(WarpLM& S, const double* diag /* sqrt(par) * diag */, double* x)
+{
+    double* s = S.s;
+    double wa[6];
+    for (int j = 0; j < 6; ++j) {
+        x[j] = s[j * 6 + j];
+        wa[j] = S.qtf[j];
+    }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < i; ++j) s[i * 6 + j] = s[j * 6 + i];
+    for (int j = 0; j < 6; ++j) {
+        const int l = S.perm[j];
+        if (diag[l] == 0.0) break;
+        for (int k = j; k < 6; ++k) S.sdiag[k] = 0.0;
+        S.sdiag[j] = diag[l];
+        double qtbpj = 0.0;
+        for (int k = j; k < 6; ++k) {
+            double gc, gs;
+            make_givens(-s[k * 6 + k], S.sdiag[k], gc, gs);
+            s[k * 6 + k] = gc * s[k * 6 + k] + gs * S.sdiag[k];
+            const double temp = gc * wa[k] + gs * qtbpj;
+            qtbpj = -gs * wa[k] + gc * qtbpj;
+            wa[k] = temp;
+            for (int i = k + 1; i < 6; ++i) {
+                const double t = gc * s[i * 6 + k] + gs * S.sdiag[i];
+                S.sdiag[i] = -gs * s[i * 6 + k] + gc * S.sdiag[i];
+                s[i * 6 + k] = t;
+            }
+        }
+    }
+    int nsing = 0;
+    while (nsing < 6 && S.sdiag[nsing] != 0.0) ++nsing;
+    for (int j = nsing; j < 6; ++j) wa[j] = 0.0;
+    for (int i = nsing - 1; i >= 0; --i) {
+        double sum = wa[i];
+        for (int j = i + 1; j < nsing; ++j) sum -= s[j * 6 + i] * wa[j];
+        wa[i] = sum / s[i * 6 + i];
+    }
+    for (int j = 0; j < 6; ++j) {
+        S.sdiag[j] = s[j * 6 + j];
+        s[j * 6 + j] = x[j];
+    }
+    for (int j = 0; j < 6; ++j) x[S.perm[j]] = wa[j];
+}
+
+// unsupported/Eigen/src/NonLinearOptimization/lmpar.h (lmpar2): trust-region parameter and step S.xs
+__device__ inline void lmpar(WarpLM& S)
+{
+    const double dwarf = DBL_MIN;
+    const double delta = S.delta;
+    double* wa1 = S.wa1;
+    double* wa2 = S.wa3;  // scratch (S.wa2 holds the column norms)
+    double* x = S.xs;
+    const int rank = S.rank;
+    for (int j = 0; j < 6; ++j) wa1[j] = (j < rank) ? S.qtf[j] : 0.0;
+    for (int i = rank - 1; i >= 0; --i) {
+        double sum = wa1[i];
+        for (int j = i + 1; j < rank; ++j) sum -= S.R[i * 6 + j] * wa1[j];
+        wa1[i] = sum / S.R[i * 6 + i];
+    }
+    for (int j = 0; j < 6; ++j) x[S.perm[j]] = wa1[j];
+
+    int iter = 0;
+    for (int j = 0; j < 6; ++j) wa2[j] = S.diag[j] * x[j];
+    double dxnorm = norm6(wa2);
+    double fp = dxnorm - delta;
+    if (fp <= 0.1 * delta) {
+        S.par = 0.0;
+        return;
+    }
+    double parl = 0.0;
+    if (rank == 6) {
+        for (int j = 0; j < 6; ++j) wa1[j] = S.diag[S.perm[j]] * wa2[S.perm[j]] / dxnorm;
+        for (int i = 0; i < 6; ++i) {
+            double sum = wa1[i];
+            for (int j = 0; j < i; ++j) sum -= S.R[j * 6 + i] * wa1[j];
+            wa1[i] = sum / S.R[i * 6 + i];
+        }
+        const double temp = norm6(wa1);
+        parl = fp / delta / temp / temp;
+    }
+    for (int j = 0; j < 6; ++j) {
+        double sum = 0.0;
+        for (int i = 0; i <= j; ++i) sum += S.R[i * 6 + j] * S.qtf[i];
+        wa1[j] = sum / S.diag[S.perm[j]];
+    }
+    const double gnorm = norm6(wa1);
+    double paru = gnorm / delta;
+    if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
+    double par = S.par;
+    par = fmax(par, parl);
+    par = fmin(par, paru);
+    if (par == 0.0) par = gnorm / dxnorm;
+
+    for (int i = 0; i < 36; ++i) S.s[i] = S.R[i];
+    while (true) {
+        ++iter;
+        if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
+        const double sq = sqrt(par);
+        double dsc[6];
+        for (int j = 0; j < 6; ++j) dsc[j] = sq * S.diag[j];
+        qrsolv(S, dsc, x);
+        for (int j = 0; j < 6; ++j) wa2[j] = S.diag[j] * x[j];
+        dxnorm = norm6(wa2);
+        double temp = fp;
+        fp = dxnorm - delta;
+        if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        for (int j = 0; j < 6; ++j) wa1[j] = S.diag[S.perm[j]] * (wa2[S.perm[j]] / dxnorm);
+        for (int j = 0; j < 6; ++j) {
+            wa1[j] /= S.sdiag[j];
+            temp = wa1[j];
+            for (int i = j + 1; i < 6; ++i) wa1[i] -= S.s[i * 6 + j] * temp;
+        }
+        temp = norm6(wa1);
+        const double parc = fp / delta / temp / temp;
+        if (fp > 0.0) parl = fmax(parl, par);
+        if (fp < 0.0) paru = fmin(paru, par);
+        par = fmax(parl, par + parc);
+    }
+    S.par = par;
+}
+
+// Eigen::LevenbergMarquardt<NumericalDiff<F,Forward>>::minimize on S.x (in/out). Whole warp must call; returns the
+// Eigen status (<= 0 failure, 1..8 MINPACK info). m = residual count of the problem.
+__device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m, const int maxfev,
+                                const int lane)
+{
+    if (m < 6 || maxfev <= 0) return 0;  // ImproperInputParameters
+    if (lane == 0) make_xform(S.x, S.T[0]);
+    __syncwarp();
+    {
+        const double ss = eval_sumsq(P, S.T[0], K, lane);
+        if (lane == 0) {
+            S.fnorm = sqrt(ss);
+            S.par = 0.0, S.delta = 0.0, S.xnorm = 0.0;
+            S.iter = 1, S.nfev = 1, S.status = kRunning;
+        }
+    }
+    __syncwarp();
+
+    while (true) {
+        // ---- forward-difference Jacobian (NumericalDiff::df): h_j = sqrt(eps) |x_j|, or sqrt(eps) when x_j == 0 ----
+        if (lane < 7) {
+            double xx[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) xx[j] = S.x[j];
+            if (lane > 0) {
+                double h = kSqrtEps * fabs(xx[lane - 1]);
+                if (h == 0.0) h = kSqrtEps;
+                xx[lane - 1] += h;
+                S.h[lane - 1] = h;
+            }
+            make_xform(xx, S.T[lane]);
+        }
+        __syncwarp();
+        double a[21], g[6];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) a[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = 0.0;
+        double ih[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ih[j] = S.h[j];
+        for (int k = lane; k < P.n; k += 32) {
+            int type;
+            double o[4], mm[4], r[3], rj[3], J[3][6];
+            load_feature(P, k, type, o, mm);
+            const int cnt = feature_residual(type, o, mm, S.T[0], K, r);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                feature_residual(type, o, mm, S.T[j + 1], K, rj);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) J[c][j] = (rj[c] - r[c]) / ih[j];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c < cnt) {
+                    int t = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        g[i] += J[c][i] * r[c];
+#pragma unroll
+                        for (int j = i; j < 6; ++j) a[t++] += J[c][i] * J[c][j];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 21; ++i) a[i] = warp_sum(a[i]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = warp_sum(g[i]);
+
+        if (lane == 0) {
+            S.nfev += 7;  // NumericalDiff re-evaluates f(x) and then one evaluation per column
+            int t = 0;
+            for (int i = 0; i < 6; ++i) {
+                S.g[i] = g[i];
+                for (int j = i; j < 6; ++j) {
+                    S.A[i * 6 + j] = a[t];
+                    S.A[j * 6 + i] = a[t];
+                    ++t;
+                }
+            }
+            factorize(S);
+            if (S.iter == 1) {
+                double tt[6];
+                for (int j = 0; j < 6; ++j) {
+                    S.diag[j] = (S.wa2[j] == 0.0) ? 1.0 : S.wa2[j];
+                    tt[j] = S.diag[j] * S.x[j];
+                }
+                S.xnorm = norm6(tt);
+                S.delta = 100.0 * S.xnorm;
+                if (S.delta == 0.0) S.delta = 100.0;
+            }
+            double gnorm = 0.0;
+            if (S.fnorm != 0.0)
+                for (int j = 0; j < 6; ++j)
+                    if (S.wa2[S.perm[j]] != 0.0) {
+                        double sum = 0.0;
+                        for (int i = 0; i <= j; ++i) sum += S.R[i * 6 + j] * (S.qtf[i] / S.fnorm);
+                        gnorm = fmax(gnorm, fabs(sum / S.wa2[S.perm[j]]));
+                    }
+            S.gnorm = gnorm;
+            if (gnorm <= 0.0) S.status = 4;  // CosinusTooSmall (gtol = 0)
+            for (int j = 0; j < 6; ++j) S.diag[j] = fmax(S.diag[j], S.wa2[j]);
+        }
+        __syncwarp();
+        if (S.status != kRunning) break;
+
+        // ---- inner loop: trust-region step until the ratio is acceptable ----
+        while (true) {
+            if (lane == 0) {
+                lmpar(S);
+                double tt[6];
+                for (int j = 0; j < 6; ++j) {
+                    S.p[j] = -S.xs[j];
+                    S.xt[j] = S.x[j] + S.p[j];
+                    tt[j] = S.diag[j] * S.p[j];
+                }
+                S.pnorm = norm6(tt);
+                if (S.iter == 1) S.delta = fmin(S.delta, S.pnorm);
+                make_xform(S.xt, S.T[0]);
+            }
+            __syncwarp();
+            const double ss1 = eval_sumsq(P, S.T[0], K, lane);
+            if (lane == 0) {
+                ++S.nfev;
+                const double fnorm = S.fnorm, fnorm1 = sqrt(ss1), pnorm = S.pnorm;
+                double actred = -1.0;
+                if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+                for (int i = 0; i < 6; ++i) {
+                    double sum = 0.0;
+                    for (int j = i; j < 6; ++j) sum += S.R[i * 6 + j] * S.p[S.perm[j]];
+                    S.wa3[i] = sum;
+                }
+                const double r1 = norm6(S.wa3) / fnorm;
+                const double temp1 = r1 * r1;
+                const double r2 = sqrt(S.par) * pnorm / fnorm;
+                const double temp2 = r2 * r2;
+                const double prered = temp1 + temp2 / 0.5;
+                const double dirder = -(temp1 + temp2);
+                double ratio = 0.0;
+                if (prered != 0.0) ratio = actred / prered;
+                if (ratio <= 0.25) {
+                    double temp = 0.0;
+                    if (actred >= 0.0) temp = 0.5;
+                    if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
+                    if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+                    S.delta = temp * fmin(S.delta, pnorm / 0.1);
+                    S.par /= temp;
+                }
+                else if (!(S.par != 0.0 && ratio < 0.75)) {
+                    S.delta = pnorm / 0.5;
+                    S.par = 0.5 * S.par;
+                }
+                if (ratio >= 1e-4) {
+                    double tt[6];
+                    for (int j = 0; j < 6; ++j) {
+                        S.x[j] = S.xt[j];
+                        tt[j] = S.diag[j] * S.x[j];
+                    }
+                    S.xnorm = norm6(tt);
+                    S.fnorm = fnorm1;
+                    ++S.iter;
+                }
+                const double ftol = kSqrtEps, xtol = kSqrtEps;
+                int status = kRunning;
+                if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && S.delta <= xtol * S.xnorm)
+                    status = 3;
+                else if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0)
+                    status = 1;
+                else if (S.delta <= xtol * S.xnorm)
+                    status = 2;
+                else if (S.nfev >= maxfev)
+                    status = 5;
+                else if (fabs(actred) <= DBL_EPSILON && prered <= DBL_EPSILON && 0.5 * ratio <= 1.0)
+                    status = 6;
+                else if (S.delta <= DBL_EPSILON * S.xnorm)
+                    status = 7;
+                else if (S.gnorm <= DBL_EPSILON)
+                    status = 8;
+                S.status = status;
+                S.again = (status == kRunning && ratio < 1e-4) ? 1 : 0;
+            }
+            __syncwarp();
+            if (S.status != kRunning || !S.again) break;
+        }
+        if (S.status != kRunning) break;
+    }
+    const int status = S.status;
+    __syncwarp();
+    return status;
+}
+
+// compute_optimized_global_pose (pose_optimization.cpp:302-359) for the whole warp. x0 -> S.x; returns success and
+// leaves the optimised coefficients in S.x.
+__device__ bool optimize_pose_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const double* x0, const int m,
+                                   const double score, const int maxfev, const int lane)
+{
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) finite = finite && isfinite(x0[j]);
+    if (!finite || m <= 1 || score < 1.0) return false;
+    if (lane == 0)
+        for (int j = 0; j < 6; ++j) S.x[j] = x0[j];
+    __syncwarp();
+    const int status = lm_minimize_warp(S, P, K, m, maxfev, lane);
+    if (status <= 0) return false;
+    double v6[6];
+    pose_vector6(S.x, v6);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ok = ok && !(v6[j] != v6[j]);
+    return ok;
+}
+
+// ---- counter-based generator of the RS_RNG_DEVICE mode --------------------------------------------------------------
+__host__ __device__ inline uint64_t mix64(uint64_t z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ inline uint64_t rng_key(const uint32_t seed, const uint32_t domain, const uint32_t frame)
+{
+    return mix64((uint64_t(seed) << 32) ^ (uint64_t(domain) << 24) ^ frame);
+}
+// four standard normals for (frame, sample, feature): two Box-Muller pairs
+__device__ inline void device_normals(const uint32_t seed, const int frame, const int sample, const int feature,
+                                      double g[4])
+{
+    const uint64_t key = rng_key(seed, 2u, uint32_t(frame));
+    const uint64_t ctr = (uint64_t(uint32_t(sample)) << 32) | (uint64_t(uint32_t(feature)) << 1);
+#pragma unroll
+    for (int pair = 0; pair < 2; ++pair) {
+        const uint64_t a = mix64(key ^ mix64(ctr + uint64_t(pair)));
+        const uint64_t b = mix64(a ^ 0xd1342543de82ef95ull);
+        const double u1 = (double(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
+        const double u2 = double(b >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        g[2 * pair] = rad * cs;
+        g[2 * pair + 1] = rad * sn;
+    }
+}
+
+// ---- kernels ----------------------------------------------------------------------------------------------------------
+
+// AoS -> SoA, PlaneCoordinates normalisation of both plane sides, validity (compute_optimized_pose :269-282),
+// total score in list order. One CTA per frame.
+__global__ void __launch_bounds__(THREADS) pose_prepare_kernel(const PoseBuffers buf, const PoseLaunch prm)
+{
+    const int b = blockIdx.x;
+    const int M = buf.max_matches;
+    int n = buf.n_matches[b];
+    n = n < 0 ? 0 : (n > M ? M : n);
+    const rs_match* src = buf.matches_aos + size_t(b) * M;
+    int32_t* type = buf.type + size_t(b) * M;
+    double* obs = buf.obs + size_t(b) * 4 * M;
+    double* map = buf.map + size_t(b) * 4 * M;
+    double* sig = buf.sigma + size_t(b) * 4 * M;
+    __shared__ int s_invalid;
+    if (threadIdx.x == 0) s_invalid = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        if (i < n) {
+            const rs_match f = src[i];
+            const int ty = (f.type == RS_FEAT_POINT) ? RS_FEAT_POINT : RS_FEAT_PLANE;
+            double o[4] = {f.obs[0], f.obs[1], f.obs[2], f.obs[3]};
+            double m[4] = {f.map[0], f.map[1], f.map[2], f.map[3]};
+            const int k = (ty == RS_FEAT_POINT) ? 3 : 4;
+            const int ko = (ty == RS_FEAT_POINT) ? 2 : 4;
+            bool bad = false;
+            for (int c = 0; c < ko; ++c) bad = bad || (o[c] != o[c]);
+            for (int c = 0; c < k; ++c) bad = bad || (m[c] != m[c]) || !(f.sigma[c] >= 0.0);
+            if (bad) atomicOr(&s_invalid, 1);
+            if (ty == RS_FEAT_PLANE) {
+                normalize3(o);
+                normalize3(m);
+            }
+            else {
+                o[2] = 0.0, o[3] = 0.0, m[3] = 0.0;
+            }
+            type[i] = ty;
+            for (int c = 0; c < 4; ++c) {
+                obs[c * M + i] = o[c];
+                map[c * M + i] = m[c];
+                sig[c * M + i] = (c < k) ? f.sigma[c] : 0.0;
+            }
+            buf.mask[size_t(b) * M + i] = 0;
+        }
+        else {
+            type[i] = RS_FEAT_POINT;
+            for (int c = 0; c < 4; ++c) obs[c * M + i] = 0.0, map[c * M + i] = 0.0, sig[c * M + i] = 0.0;
+            buf.mask[size_t(b) * M + i] = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PoseFrameState st;
+        st.n = n;
+        st.valid = s_invalid ? 0 : 1;
+        double score = 0.0;
+        int res = 0;
+        for (int i = 0; i < n; ++i) {
+            const bool pt = src[i].type == RS_FEAT_POINT;
+            score += pt ? kPointScore : kPlaneScore;
+            res += pt ? 2 : 3;
+        }
+        st.total_score = score;
+        st.residuals = res;
+        st.stage = 0;
+        for (int j = 0; j < 6; ++j) st.final_x[j] = 0.0;
+        buf.state[b] = st;
+        rs_pose_out o;
+        o.status = 0, o.n_inliers = 0, o.iterations_run = 0, o.best_iteration = -1, o.n_variance_ok = 0, o.reserved = 0;
+        o.score = 0.0;
+        for (int j = 0; j < 7; ++j) o.pose[j] = buf.cur_pose[b * 7 + j];
+        for (int j = 0; j < 36; ++j) o.cov[j] = 0.0;
+        buf.out[b] = o;
+        for (int j = 0; j < 7; ++j) buf.poses[b * 7 + j] = o.pose[j];
+    }
+}
+
+struct RansacShared {
+    double best_x[6];
+    double max_score;
+    int best_inliers, best_iteration, can_quit, started;
+    double hyp_x[WARPS][6];
+    double hyp_score[WARPS];
+    int hyp_ok[WARPS];
+    int hyp_inliers[WARPS];
+};
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) / 16 * 16; }
+
+// shared-memory carve-up of the RANSAC kernel
+struct RansacSmem {
+    int32_t* type;
+    double* obs;
+    double* map;
+    WarpLM* lm;
+    unsigned* hyp_mask;   // [WARPS][words]
+    unsigned* best_mask;  // [words]
+    short* subset;        // [WARPS][RS_MAX_SUBSET]
+    short* inlier_idx;    // [M]
+    RansacShared* sh;
+};
+__host__ __device__ inline size_t ransac_carve(RansacSmem* s, unsigned char* base, const int M)
+{
+    const int words = (M + 31) / 32;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char* p = base ? base + o : nullptr;
+        o = align16(o + bytes);
+        return p;
+    };
+    unsigned char* obs = take(sizeof(double) * 4 * M);
+    unsigned char* map = take(sizeof(double) * 4 * M);
+    unsigned char* lm = take(sizeof(WarpLM) * WARPS);
+    unsigned char* sh = take(sizeof(RansacShared));
+    unsigned char* type = take(sizeof(int32_t) * M);
+    unsigned char* hm = take(sizeof(unsigned) * WARPS * words);
+    unsigned char* bm = take(sizeof(unsigned) * words);
+    unsigned char* sub = take(sizeof(short) * WARPS * RS_MAX_SUBSET);
+    unsigned char* ii = take(sizeof(short) * M);
+    if (s) {
+        s->obs = reinterpret_cast<double*>(obs), s->map = reinterpret_cast<double*>(map);
+        s->lm = reinterpret_cast<WarpLM*>(lm), s->sh = reinterpret_cast<RansacShared*>(sh);
+        s->type = reinterpret_cast<int32_t*>(type), s->hyp_mask = reinterpret_cast<unsigned*>(hm);
+        s->best_mask = reinterpret_cast<unsigned*>(bm), s->subset = reinterpret_cast<short*>(sub);
+        s->inlier_idx = reinterpret_cast<short*>(ii);
+    }
+    return o;
+}
+
+// compute_pose_with_ransac (pose_optimization.cpp:107-262): one CTA per frame.
+__global__ void __launch_bounds__(THREADS) pose_ransac_kernel(const PoseBuffers buf, const PoseLaunch prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int M = buf.max_matches;
+    const int words = (M + 31) / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RansacSmem sm;
+    ransac_carve(&sm, smem_raw, M);
+    const PoseFrameState st = buf.state[b];
+    const int n = st.n;
+    if (!st.valid || st.total_score < 1.0) return;  // out[b] already says status 0, pose = current pose
+
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        sm.type[i] = buf.type[size_t(b) * M + i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            sm.obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
+            sm.map[c * M + i] = buf.map[(size_t(b) * 4 + c) * M + i];
+        }
+    }
+    double x0[6];
+    coefficients_from_pose(buf.cur_pose + b * 7, x0);
+    RansacShared& sh = *sm.sh;
+    if (threadIdx.x == 0) {
+        sh.max_score = 1.0;
+        sh.best_inliers = 0, sh.best_iteration = -1, sh.can_quit = 0, sh.started = 0;
+        for (int j = 0; j < 6; ++j) sh.best_x[j] = x0[j];
+    }
+    for (int i = threadIdx.x; i < words; i += blockDim.x) sm.best_mask[i] = 0u;
+    __syncthreads();
+
+    const int maxIterations = prm.max_iterations;
+    const unsigned inliersToStop = unsigned(ceil(double(n) * kEarlyStopProportion));
+    WarpLM& S = sm.lm[warp];
+    short* subset = sm.subset + warp * RS_MAX_SUBSET;
+    unsigned* hmask = sm.hyp_mask + warp * words;
+    Problem P;
+    P.type = sm.type, P.obs = sm.obs, P.map = sm.map, P.M = M;
+
+    for (int chunk = 0; chunk < maxIterations; chunk += WARPS) {
+        const int it = chunk + warp;
+        if (it < maxIterations) {
+            // ---- random subset: ransac::get_random_subset_with_score (ransac.hpp:77-103) ----
+            int cnt = 0, m = 0;
+            double cumulated = 0.0;
+            bool ok = false;
+            int32_t* used = buf.subsets_used + (size_t(b) * buf.max_iterations + it) * RS_MAX_SUBSET;
+            if (lane == 0) {
+                if (buf.subsets_in) {
+                    // host-drawn (std::mt19937 + std::shuffle), already in the reference's prepended order
+                    const int32_t* in = buf.subsets_in + (size_t(b) * buf.max_iterations + it) * RS_MAX_SUBSET;
+                    for (int k = 0; k < RS_MAX_SUBSET; ++k) {
+                        const int idx = in[k];
+                        if (idx >= 0 && idx < n) subset[cnt++] = short(idx);
+                    }
+                    for (int k = cnt - 1; k >= 0; --k) cumulated += sm.type[subset[k]] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
+                }
+                else {
+                    // distinct uniform picks until the cumulated score reaches 1, each pick PREPENDED
+                    const uint64_t key = rng_key(prm.seed, 1u, uint32_t(b)) ^ mix64(uint64_t(uint32_t(it)) << 20);
+                    short picks[RS_MAX_SUBSET];
+                    uint64_t ctr = 0;
+                    while (cnt < RS_MAX_SUBSET && cnt < n && cumulated < 1.0) {
+                        const int idx = int(mix64(key + ctr++) % uint64_t(n));
+                        bool dup = false;
+                        for (int k = 0; k < cnt; ++k) dup = dup || (picks[k] == idx);
+                        if (dup) continue;
+                        picks[cnt++] = short(idx);
+                        cumulated += sm.type[idx] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
+                    }
+                    for (int k = 0; k < cnt; ++k) subset[k] = picks[cnt - 1 - k];
+                }
+                for (int k = 0; k < RS_MAX_SUBSET; ++k) used[k] = k < cnt ? int(subset[k]) : -1;
+                for (int k = 0; k < cnt; ++k) m += sm.type[subset[k]] == RS_FEAT_POINT ? 2 : 3;
+            }
+            cnt = __shfl_sync(FULL, cnt, 0);
+            m = __shfl_sync(FULL, m, 0);
+            cumulated = __shfl_sync(FULL, cumulated, 0);
+            __syncwarp();
+            ok = cumulated >= 1.0;
+            if (ok) {
+                P.n = cnt;
+                P.idx = subset;
+                ok = optimize_pose_warp(S, P, prm.K, x0, m, cumulated, prm.lm_max_fev, lane);
+            }
+            int nIn = 0;
+            double score = 0.0;
+            if (ok) {
+                // ---- get_features_inliers_outliers (pose_optimization.cpp:33-72) over all features ----
+                if (lane == 0) make_xform(S.x, S.T[0]);
+                __syncwarp();
+                for (int w = 0; w < words; ++w) {
+                    const int i = w * 32 + lane;
+                    bool in = false;
+                    if (i < n) {
+                        double o[4], mm[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) o[c] = sm.obs[c * M + i], mm[c] = sm.map[c * M + i];
+                        in = feature_is_inlier(sm.type[i], o, mm, S.T[0], prm.K);
+                    }
+                    const unsigned bits = __ballot_sync(FULL, in);
+                    if (lane == 0) hmask[w] = bits;
+                    nIn += __popc(bits);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    // the score is accumulated in list order, like the reference's running double
+                    for (int w = 0; w < words; ++w) {
+                        unsigned bits = hmask[w];
+                        while (bits) {
+                            const int i = w * 32 + (__ffs(bits) - 1);
+                            bits &= bits - 1;
+                            score += sm.type[i] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) {
+                sh.hyp_ok[warp] = ok ? 1 : 0;
+                sh.hyp_score[warp] = score;
+                sh.hyp_inliers[warp] = nIn;
+                for (int j = 0; j < 6; ++j) sh.hyp_x[warp][j] = S.x[j];
+            }
+        }
+        __syncthreads();
+        // ---- the reference's serial bookkeeping over this chunk, in iteration order (:151-227) ----
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < WARPS; ++w) {
+                const int iteration = chunk + w;
+                if (iteration >= maxIterations || sh.can_quit) break;
+                ++sh.started;
+                if (!sh.hyp_ok[w]) continue;
+                const double score = sh.hyp_score[w];
+                if (score < 1.0) continue;
+                const bool canOverload =
+                        (score > sh.max_score) || (fabs(score - sh.max_score) <= 0.1 && sh.best_inliers < sh.hyp_inliers[w]);
+                if (canOverload) {
+                    sh.max_score = score;
+                    for (int j = 0; j < 6; ++j) sh.best_x[j] = sh.hyp_x[w][j];
+                    for (int k = 0; k < words; ++k) sm.best_mask[k] = sm.hyp_mask[w * words + k];
+                    sh.best_inliers = sh.hyp_inliers[w];
+                    sh.best_iteration = iteration;
+                }
+                if (iteration >= 3 && unsigned(sh.best_inliers) > inliersToStop) sh.can_quit = 1;
+            }
+        }
+        __syncthreads();
+        if (sh.can_quit) break;
+    }
+
+    // ---- final optimisation on the winning inlier set, from the winning pose (:229-262) ----
+    if (warp != 0) return;
+    int nInl = 0, m = 0;
+    double inlierScore = 0.0;
+    if (lane == 0) {
+        for (int w = 0; w < words; ++w) {
+            unsigned bits = sm.best_mask[w];
+            while (bits) {
+                const int i = w * 32 + (__ffs(bits) - 1);
+                bits &= bits - 1;
+                sm.inlier_idx[nInl++] = short(i);
+                const bool pt = sm.type[i] == RS_FEAT_POINT;
+                inlierScore += pt ? kPointScore : kPlaneScore;
+                m += pt ? 2 : 3;
+            }
+        }
+    }
+    nInl = __shfl_sync(FULL, nInl, 0);
+    m = __shfl_sync(FULL, m, 0);
+    inlierScore = __shfl_sync(FULL, inlierScore, 0);
+    __syncwarp();
+    rs_pose_out* out = buf.out + b;
+    if (lane == 0) {
+        out->n_inliers = sh.best_inliers;
+        out->iterations_run = sh.started;
+        out->best_iteration = sh.best_iteration;
+        out->score = sh.max_score;
+    }
+    if (inlierScore < 1.0) return;  // status stays 0
+    double bx[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) bx[j] = sh.best_x[j];
+    P.n = nInl;
+    P.idx = sm.inlier_idx;
+    const bool ok = optimize_pose_warp(S, P, prm.K, bx, m, inlierScore, prm.lm_max_fev, lane);
+    if (!ok) {
+        if (lane == 0) out->status = -1;
+        return;
+    }
+    for (int i = lane; i < n; i += 32) buf.mask[size_t(b) * M + i] = (sm.best_mask[i >> 5] >> (i & 31)) & 1u;
+    if (lane == 0) {
+        double q[4];
+        quaternion_from_coefficients(S.x, q);
+        for (int j = 0; j < 3; ++j) out->pose[j] = S.x[j];
+        for (int j = 0; j < 4; ++j) out->pose[3 + j] = q[j];
+        for (int j = 0; j < 7; ++j) buf.poses[b * 7 + j] = out->pose[j];
+        out->status = prm.n_variance == 0 ? 1 : -2;  // -2 until the covariance kernel validates it
+        PoseFrameState* stp = buf.state + b;
+        stp->stage = 1;
+        for (int j = 0; j < 6; ++j) stp->final_x[j] = S.x[j];
+    }
+}
+
+// compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
+// grid (ceil(n_variance / WARPS), B), one warp per Monte-Carlo sample.
+__global__ void __launch_bounds__(THREADS) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.y;
+    const int M = buf.max_matches;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PoseFrameState st = buf.state[b];
+    if (st.stage != 1) return;
+    const int n = st.n;
+    // carve: obs[4][M] | pmap[WARPS][4][M] | WarpLM[WARPS] | type[M] | idx[M] | count
+    double* s_obs = reinterpret_cast<double*>(smem_raw);
+    double* s_pmap = s_obs + 4 * M;
+    WarpLM* s_lm = reinterpret_cast<WarpLM*>(s_pmap + size_t(WARPS) * 4 * M);
+    int32_t* s_type = reinterpret_cast<int32_t*>(s_lm + WARPS);
+    short* s_idx = reinterpret_cast<short*>(s_type + M);
+    __shared__ int s_cnt, s_m;
+    __shared__ double s_score;
+
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        s_type[i] = buf.type[size_t(b) * M + i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s_obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int cnt = 0, m = 0;
+        double score = 0.0;
+        for (int i = 0; i < n; ++i)
+            if (buf.mask[size_t(b) * M + i]) {
+                s_idx[cnt++] = short(i);
+                const bool pt = s_type[i] == RS_FEAT_POINT;
+                score += pt ? kPointScore : kPlaneScore;
+                m += pt ? 2 : 3;
+            }
+        s_cnt = cnt, s_m = m, s_score = score;
+    }
+    __syncthreads();
+    const int sample = blockIdx.x * WARPS + warp;
+    if (sample >= prm.n_variance) return;
+    const int cnt = s_cnt;
+    double* pmap = s_pmap + size_t(warp) * 4 * M;
+    const double* gmap = buf.map + size_t(b) * 4 * M;
+    const double* gsig = buf.sigma + size_t(b) * 4 * M;
+    for (int k = lane; k < cnt; k += 32) {
+        const int i = s_idx[k];
+        double g[4];
+        if (buf.normals_in) {
+            const double* src = buf.normals_in + ((size_t(b) * prm.n_variance + sample) * M + i) * 4;
+            g[0] = src[0], g[1] = src[1], g[2] = src[2], g[3] = src[3];
+        }
+        else {
+            device_normals(prm.seed, b, sample, i, g);
+        }
+        if (s_type[i] == RS_FEAT_POINT) {
+            // map_point.cpp:49-58
+#pragma unroll
+            for (int c = 0; c < 3; ++c) pmap[c * M + i] = gmap[c * M + i] + g[c] * gsig[c * M + i];
+            pmap[3 * M + i] = 0.0;
+        }
+        else {
+            // map_primitive.cpp:66-77: perturbed normal renormalised (twice: vector + PlaneCoordinates ctor)
+            double nn[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) nn[c] = gmap[c * M + i] + g[c] * gsig[c * M + i];
+            normalize3(nn);
+            normalize3(nn);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) pmap[c * M + i] = nn[c];
+            pmap[3 * M + i] = gmap[3 * M + i] + g[3] * gsig[3 * M + i];
+        }
+    }
+    __syncwarp();
+    Problem P;
+    P.n = cnt, P.idx = s_idx, P.type = s_type, P.obs = s_obs, P.map = pmap, P.M = M;
+    WarpLM& S = s_lm[warp];
+    double x0[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) x0[j] = st.final_x[j];
+    const bool ok = optimize_pose_warp(S, P, prm.K, x0, s_m, s_score, prm.lm_max_fev, lane);
+    if (lane == 0) {
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (ok) pose_vector6(S.x, v);
+        double* dst = buf.v6 + (size_t(b) * buf.max_variance + sample) * 6;
+        for (int j = 0; j < 6; ++j) dst[j] = v[j];
+        buf.v_ok[size_t(b) * buf.max_variance + sample] = ok ? 1 : 0;
+    }
+}
+
+// is_covariance_valid (covariances.hpp:13-44): finite, isApprox-symmetric, LDLT without a negative pivot
+__device__ bool covariance_valid(const double* c)
+{
+    for (int i = 0; i < 36; ++i)
+        if (!isfinite(c[i])) return false;
+    double diff2 = 0.0, n2 = 0.0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            const double dd = c[i * 6 + j] - c[j * 6 + i];
+            diff2 += dd * dd;
+            n2 += c[i * 6 + j] * c[i * 6 + j];
+        }
+    if (!(diff2 <= 1e-12 * 1e-12 * n2)) return false;
+    double a[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) a[i * 6 + j] = c[(i < j ? i : j) * 6 + (i < j ? j : i)];
+    bool neg = false;
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        double best = fabs(a[k * 6 + k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (fabs(a[i * 6 + i]) > best) {
+                best = fabs(a[i * 6 + i]);
+                p = i;
+            }
+        if (p != k) {
+            for (int j = 0; j < 6; ++j) {
+                const double t = a[k * 6 + j];
+                a[k * 6 + j] = a[p * 6 + j];
+                a[p * 6 + j] = t;
+            }
+            for (int i = 0; i < 6; ++i) {
+                const double t = a[i * 6 + k];
+                a[i * 6 + k] = a[i * 6 + p];
+                a[i * 6 + p] = t;
+            }
+        }
+        const double dkk = a[k * 6 + k];
+        if (dkk < 0.0) neg = true;
+        if (fabs(dkk) <= DBL_MIN) break;
+        for (int i = k + 1; i < 6; ++i) {
+            const double l = a[i * 6 + k] / dkk;
+            for (int j = k + 1; j < 6; ++j) a[i * 6 + j] -= l * a[k * 6 + j];
+        }
+    }
+    return !neg;
+}
+
+// compute_pose_variance's reduction (pose_optimization.cpp:414-437): one thread per frame, sums in sample order.
+__global__ void pose_covariance_kernel(const PoseBuffers buf, const PoseLaunch prm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= prm.batch) return;
+    if (buf.state[b].stage != 1 || prm.n_variance <= 0) return;
+    const double* v6 = buf.v6 + size_t(b) * buf.max_variance * 6;
+    const int32_t* vok = buf.v_ok + size_t(b) * buf.max_variance;
+    rs_pose_out* out = buf.out + b;
+    double medium[6] = {0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int s = 0; s < prm.n_variance; ++s)
+        if (vok[s]) {
+            for (int j = 0; j < 6; ++j) medium[j] += v6[s * 6 + j];
+            ++cnt;
+        }
+    out->n_variance_ok = cnt;
+    if (unsigned(cnt) < unsigned(prm.n_variance) / 2u) {
+        out->status = -2;
+        return;
+    }
+    for (int j = 0; j < 6; ++j) medium[j] /= double(cnt);
+    double cov[36];
+    for (int i = 0; i < 36; ++i) cov[i] = 0.0;
+    for (int s = 0; s < prm.n_variance; ++s)
+        if (vok[s]) {
+            double def[6];
+            for (int j = 0; j < 6; ++j) def[j] = v6[s * 6 + j] - medium[j];
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) cov[i * 6 + j] += def[i] * def[j];
+        }
+    for (int i = 0; i < 36; ++i) cov[i] /= double(cnt - 1);
+    for (int i = 0; i < 6; ++i) cov[i * 6 + i] += 0.001;
+    for (int i = 0; i < 36; ++i) out->cov[i] = cov[i];
+    out->status = covariance_valid(cov) ? 1 : -2;
+}
+
+__global__ void pose_export_normals_kernel(const PoseLaunch prm, const int M, double* normals)
+{
+    const size_t total = size_t(prm.batch) * prm.n_variance * M;
+    for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += size_t(gridDim.x) * blockDim.x) {
+        const int i = int(t % M);
+        const int sample = int((t / M) % prm.n_variance);
+        const int b = int(t / (size_t(M) * prm.n_variance));
+        double g[4];
+        device_normals(prm.seed, b, sample, i, g);
+        for (int c = 0; c < 4; ++c) normals[t * 4 + c] = g[c];
+    }
+}
+
+size_t variance_smem_bytes(const int M)
+{
+    return sizeof(double) * 4 * M + sizeof(double) * size_t(WARPS) * 4 * M + sizeof(WarpLM) * WARPS + sizeof(int32_t) * M +
+           sizeof(short) * M + 16;
+}
+
+}  // namespace
+
+int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
+{
+    pose_prepare_kernel<<<prm.batch, THREADS, 0, stream>>>(buf, prm);
+    RS_LAUNCH_CHECK();
+    return RS_OK;
+}
+
+int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
+{
+    const size_t smem = ransac_carve(nullptr, nullptr, buf.max_matches);
+    static size_t configured = 0;
+    if (smem > configured) {
+        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    pose_ransac_kernel<<<prm.batch, THREADS, smem, stream>>>(buf, prm);
+    RS_LAUNCH_CHECK();
+    return RS_OK;
+}
+
+int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
+{
+    if (prm.n_variance <= 0) return RS_OK;
+    const size_t smem = variance_smem_bytes(buf.max_matches);
+    static size_t configured = 0;
+    if (smem > configured) {
+        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    const dim3 grid((prm.n_variance + WARPS - 1) / WARPS, prm.batch);
+    pose_variance_kernel<<<grid, THREADS, smem, stream>>>(buf, prm);
+    RS_LAUNCH_CHECK();
+    return RS_OK;
+}
+
+int launch_pose_covariance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
+{
+    if (prm.n_variance <= 0) return RS_OK;
+    pose_covariance_kernel<<<(prm.batch + 63) / 64, 64, 0, stream>>>(buf, prm);
+    RS_LAUNCH_CHECK();
+    return RS_OK;
+}
+
+int launch_pose_export_normals(const PoseBuffers& buf, const PoseLaunch& prm, double* normals, cudaStream_t stream)
+{
+    pose_export_normals_kernel<<<148 * 4, 256, 0, stream>>>(prm, buf.max_matches, normals);
+    RS_LAUNCH_CHECK();
+    return RS_OK;
+}
+
+}  // namespace rs

@@ -42,6 +42,8 @@ def load():
     lib.rs_cape_device_depth.argtypes = [vp]
     lib.rs_cape_device_outputs.restype = C.POINTER(abi.CapeOutputs)
     lib.rs_cape_device_outputs.argtypes = [vp]
+    lib.rs_cape_set_timing.argtypes = [vp, i32]
+    lib.rs_cape_kernel_ms.argtypes = [vp, i32, vp]
     lib.rs_last_error.restype = C.c_char_p
     lib.rs_version.restype = C.c_char_p
     lib.rs_launch_count.restype = C.c_uint64
@@ -57,6 +59,8 @@ def load():
         lib.rs_pose_device_poses.restype = vp
         lib.rs_pose_device_poses.argtypes = [vp]
         lib.rs_pose_export_random.argtypes = [vp, i32, vp, vp]
+        lib.rs_pose_set_timing.argtypes = [vp, i32]
+        lib.rs_pose_kernel_ms.argtypes = [vp, i32, vp]
     _lib = lib
     return lib
 
@@ -129,6 +133,15 @@ class PrimitiveDetection:
     def run_device(self, depth_ptr, batch, seed=0, outputs=None, stream=0):
         o = outputs if outputs is not None else self.device_outputs()
         _check(self._lib.rs_cape_run_device(self._ctx, depth_ptr, batch, seed, C.byref(o), stream), "rs_cape_run_device")
+
+    def set_timing(self, n_slots):
+        _check(self._lib.rs_cape_set_timing(self._ctx, n_slots), "rs_cape_set_timing")
+
+    def kernel_ms(self, slot):
+        """(plane-fit kernel ms, segmentation kernel ms) of the run that used this timing slot."""
+        ms = (C.c_float * 2)()
+        _check(self._lib.rs_cape_kernel_ms(self._ctx, slot, ms), "rs_cape_kernel_ms")
+        return float(ms[0]), float(ms[1])
 
     def cell_fit_device(self, depth_ptr, batch, cells_ptr=None, stream=0):
         if cells_ptr is None:
@@ -214,6 +227,15 @@ class PoseOptimization:
         mask = np.zeros((batch, self.max_matches), dtype=np.uint8)
         _check(self._lib.rs_pose_download(self._ctx, batch, out.ctypes.data, mask.ctypes.data), "rs_pose_download")
         return out, mask
+
+    def set_timing(self, n_slots):
+        _check(self._lib.rs_pose_set_timing(self._ctx, n_slots), "rs_pose_set_timing")
+
+    def kernel_ms(self, slot):
+        """(prepare, RANSAC + final LM, Monte-Carlo LM solves, covariance) ms of the run that used this slot."""
+        ms = (C.c_float * 4)()
+        _check(self._lib.rs_pose_kernel_ms(self._ctx, slot, ms), "rs_pose_kernel_ms")
+        return tuple(float(v) for v in ms)
 
     def device_poses_ptr(self):
         return self._lib.rs_pose_device_poses(self._ctx)

@@ -1,0 +1,154 @@
+"""CPU: pins of the CAPE oracle. The reference has no test / golden vector for this path, so the pins are
+(1) numpy restatements of the per-cell arithmetic, (2) numpy.linalg for the 3x3 eigen-solver, (3) the scene statistics
+recorded in SURVEY.md Appendix C(5), and (4) the committed golden fixtures (tools/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import rgbd_slam_b200 as rs
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def numpy_cell_sums(depth, cell=20, K=(550.0, 550.0, 320.0, 240.0)):
+    """A.2 + A.3 step 4 in numpy: FP64 back-projection cast to float, FP32 products, FP64 sums."""
+    H, W = depth.shape
+    fx, fy, cx, cy = K
+    invdet = 1.0 / (fx * fy)
+    kx = (fy * invdet) * np.arange(W, dtype=np.float64) + (-cx * fy) * invdet
+    ky = (fx * invdet) * np.arange(H, dtype=np.float64) + (-fx * cy) * invdet
+    z = depth.astype(np.float32)
+    x = (z.astype(np.float64) * kx[None, :]).astype(np.float32)
+    y = (z.astype(np.float64) * ky[:, None]).astype(np.float32)
+    valid = z > 0
+    vc, hc = H // cell, W // cell
+    out = np.zeros((vc * hc, 10))
+    for r in range(vc):
+        for c in range(hc):
+            sl = (slice(r * cell, (r + 1) * cell), slice(c * cell, (c + 1) * cell))
+            v = valid[sl]
+            xs, ys, zs = x[sl][v], y[sl][v], z[sl][v]
+            f64 = lambda a: a.astype(np.float64).sum()  # noqa: E731
+            out[r * hc + c] = [v.sum(), f64(xs), f64(ys), f64(zs), f64(xs * xs), f64(ys * ys), f64(zs * zs), f64(xs * ys),
+                               f64(ys * zs), f64(zs * xs)]
+    return out
+
+
+def test_cell_sums_match_numpy():
+    depth = rs.synth.scene_v0_depth(0)
+    cells = ol.cape_cell_fit(depth)[0]
+    ref = numpy_cell_sums(depth)
+    fitted = cells["count"] > 0
+    assert fitted.sum() > 700
+    assert np.array_equal(cells["count"][fitted], ref[fitted, 0].astype(np.int32))
+    np.testing.assert_allclose(cells["S"][fitted], ref[fitted, 1:], rtol=1e-12)
+
+
+def test_organized_cloud_layout():
+    """get_organized_cloud_array: rows of a cell contiguous, raster order inside the cell (A.2)."""
+    depth = rs.synth.scene_v0_depth(1)
+    _, cloud = ol.cape_cell_fit(depth, want_cloud=True)
+    cloud = cloud[0]  # [3, W*H] column-major cloud: x column, y column, z column
+    H, W, cs = 480, 640, 20
+    hc = W // cs
+    for (r, c) in [(0, 0), (17, 33), (240, 320), (479, 639), (100, 619)]:
+        idx = ((r // cs) * hc + c // cs) * cs * cs + (r % cs) * cs + (c % cs)
+        z = depth[r, c]
+        if z > 0:
+            assert cloud[2, idx] == z
+            assert cloud[0, idx] == np.float32(np.float64(z) * ((c - 320.0) / 550.0)) or abs(
+                cloud[0, idx] - z * (c - 320.0) / 550.0) <= 1e-4 * abs(z)
+        else:
+            assert cloud[0, idx] == 0 and cloud[1, idx] == 0 and cloud[2, idx] == 0
+
+
+def test_eigen3_matches_numpy():
+    lib = ol.load()
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        a = rng.normal(size=(3, 3)) * 10 ** rng.uniform(-3, 6)
+        a = a @ a.T
+        ev, q = np.zeros(3), np.zeros(9)
+        lib.orc_eigen3(np.ascontiguousarray(a).ctypes.data, ev.ctypes.data, q.ctypes.data)
+        w, v = np.linalg.eigh(a)
+        np.testing.assert_allclose(ev, w, rtol=1e-9, atol=1e-12 * abs(w).max())
+        q = q.reshape(3, 3)
+        for k in range(3):
+            if k == 0 or (w[k] - w[k - 1]) > 1e-6 * abs(w).max():
+                if k == 2 or (w[k + 1] - w[k]) > 1e-6 * abs(w).max():
+                    assert abs(np.dot(q[:, k], v[:, k])) > 1 - 1e-8
+
+
+def test_plane_fit_recovers_known_plane():
+    """Every planar cell of the back wall (n = (0,0,-1), d0 = 2500) must carry that plane within the noise."""
+    depth = rs.synth.scene_v0_depth(2)
+    r = ol.cape_run(depth)
+    lab = r["plane_labels"][0].reshape(24, 32)
+    wall = lab[2, 10]
+    assert wall > 0
+    p = r["planes"][0][wall - 1]
+    n, d = p["normal"], p["d"]
+    assert abs(abs(n[2]) - 1) < 1e-4 and abs(d - 2500) < 2.0
+
+
+def test_scene_v0_statistics():
+    """719/768 planar cells, 10 seeds -> 8 plane regions + 2 cylinder-branch regions."""
+    r = ol.cape_run(rs.synth.scene_v0_depth(0))
+    info = r["info"][0]
+    assert info["n_planar_cells"] == 719
+    assert info["n_seeds"] == 10
+    assert info["n_planes"] == 8
+    assert info["n_cyl_regions"] == 2
+    cyl = r["cyls"][0][0]
+    assert cyl["n_segments"] == 1 and abs(cyl["radius"][0] - 250) < 10          # the synthetic cylinder: r = 250 mm
+    assert abs(abs(cyl["axis"][1]) - 1) < 1e-3                                     # axis parallel to y
+
+
+def test_histogram_bin1_quirk_is_reproduced():
+    """remove_point sets the bin to 1 instead of -1 (histogram.hpp:110-112): the oracle must keep running and stay
+    deterministic when bin 1 becomes the fullest bin (a floor-like plane seen from above: theta in [9.5, 18.9) deg)."""
+    H, W = 480, 640
+    u, v = np.meshgrid(np.arange(W), np.arange(H))
+    dx, dy = (u - 320.0) / 550.0, (v - 240.0) / 550.0
+    n = np.array([np.sin(0.25), 0.0, -np.cos(0.25)])
+    z = -2000.0 / (n[0] * dx + n[1] * dy + n[2])
+    rng = np.random.default_rng(5)
+    depth = (z + rng.normal(0, 1.0, z.shape)).astype(np.float32)
+    a = ol.cape_run(depth)
+    b = ol.cape_run(depth)
+    assert a["info"][0]["n_planes"] >= 1
+    assert np.array_equal(a["plane_labels"], b["plane_labels"])
+
+
+def test_golden_fixture():
+    g = np.load(os.path.join(GOLDEN, "cape_scene_v0.npz"))
+    depth = rs.synth.scene_v0_batch(0, 4)
+    r = ol.cape_run(depth, seed=0)
+    assert np.array_equal(r["plane_labels"], g["plane_labels"])
+    assert np.array_equal(r["plane_grid"], g["plane_grid"])
+    assert np.array_equal(r["cyl_labels"], g["cyl_labels"])
+    assert r["info"].tobytes() == g["info"].tobytes()
+    assert np.array_equal(r["cells"]["count"], g["cell_count"])
+    assert np.array_equal(r["cells"]["planar"], g["cell_planar"])
+    np.testing.assert_allclose(r["cells"]["normal"], g["cell_normal"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(r["cells"]["d"], g["cell_d"], rtol=1e-12)
+    np.testing.assert_allclose(r["planes"]["normal"][:, :16], g["plane_normal"], atol=1e-12)
+    np.testing.assert_allclose(r["planes"]["d"][:, :16], g["plane_d"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["empty", "flat", "noise"])
+def test_degenerate_frames(case):
+    H, W = 480, 640
+    if case == "empty":
+        depth = np.zeros((H, W), np.float32)
+    elif case == "flat":
+        depth = np.full((H, W), 1500.0, np.float32)  # exact plane: the det == 0 guard rejects cells (A.4)
+    else:
+        depth = np.random.default_rng(0).uniform(500, 4000, (H, W)).astype(np.float32)
+    r = ol.cape_run(depth)
+    info = r["info"][0]
+    assert info["status"] == 0
+    if case != "flat":
+        assert info["n_planes"] == 0 and not r["plane_labels"].any()

@@ -1,0 +1,184 @@
+"""GPU parity: the RANSAC + LM pose solve (and its Monte-Carlo covariance) through the C-ABI vs the CPU oracle on the
+same inputs AND the same random draws. Tolerance (north_star): pose within 1e-4 relative; integer outputs (inlier
+mask, iteration counters, status) exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import parity
+import ref_scenarios as scn
+import rgbd_slam_b200 as rs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+M = 320
+
+
+@pytest.fixture(scope="module")
+def solver():
+    s = rs.PoseOptimization(max_batch=8, max_matches=M, max_iterations=119, max_variance=100)
+    yield s
+    s.close()
+
+
+def lm_coefficients(pose):
+    """levenberg_marquardt_functors.cpp:14-27: [t, qw/(1+qz), qx/(1+qz), qy/(1+qz)]"""
+    d = 1.0 / max(1.0 + pose[6], 0.001)
+    return np.array([pose[0], pose[1], pose[2], pose[3] * d, pose[4] * d, pose[5] * d])
+
+
+def assert_out_match(ref, got, ref_mask, got_mask, n, cov_rtol=2e-3, strict=True):
+    assert got["status"] == ref["status"], (got["status"], ref["status"])
+    assert got["iterations_run"] == ref["iterations_run"]
+    assert got["best_iteration"] == ref["best_iteration"]
+    assert got["n_inliers"] == ref["n_inliers"]
+    assert np.array_equal(got_mask[:n], ref_mask[:n])
+    assert abs(got["score"] - ref["score"]) <= 1e-9
+    ok, dt, qd = parity.pose_close(ref["pose"], got["pose"], rtol=1e-4 if strict else 1e-2)
+    assert ok, "pose differs: |dt| = %g mm, |q.q_ref| = %r" % (dt, qd)
+    if ref["status"] == 1 and ref["n_variance_ok"] > 0:
+        assert got["n_variance_ok"] == ref["n_variance_ok"]
+        rc, gc = ref["cov"].reshape(6, 6), got["cov"].reshape(6, 6)
+        assert np.all(np.isfinite(gc)) and np.allclose(gc, gc.T) and np.linalg.eigvalsh(gc).min() > 0
+        # Quirk of the reference: the forward-difference step is h = sqrt(eps) * |x_j| (Eigen NumericalDiff), so when a
+        # pose coordinate is ~0 (but not exactly 0) the step underflows the residuals' resolution and that Jacobian
+        # column is rounding noise (or exactly zero, freezing the coordinate). The Monte-Carlo covariance is then
+        # noise-driven in the reference itself; values are only compared when no position coordinate is near zero.
+        if strict and np.abs(lm_coefficients(ref["pose"])).min() > 1e-3:
+            scale = np.sqrt(np.outer(np.diag(rc), np.diag(rc)))
+            err = np.abs(gc - rc) / (cov_rtol * scale + 1e-12)
+            assert err.max() <= 1.0, "covariance differs: worst entry %s x tolerance" % err.max()
+
+
+def test_reference_rng_matches_oracle(solver):
+    """RS_RNG_REFERENCE: host std::mt19937 stream (shuffles, then the Gaussian draws) exactly as the reference/oracle."""
+    B = 8
+    truth, cur, matches, n = rs.synth.pose_batch(0, B, M)
+    opts = solver.options(seed=11, rng_mode=rs.abi.RS_RNG_REFERENCE)
+    out, mask = solver.compute_optimized_pose(cur, matches, n, opts)
+    for b in range(B):
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], seed=11 + b)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
+        assert rout["status"] == 1
+        assert np.linalg.norm(out[b]["pose"][:3] - truth[b][:3]) < 3.0
+
+
+def test_golden_fixture(solver):
+    g = np.load(os.path.join(GOLDEN, "pose_synth_v0.npz"))
+    for f in range(4):
+        truth, guess, m = rs.synth.pose_correspondences(f)
+        out, mask = solver.compute_optimized_pose(guess[None], m[None], opts=solver.options(seed=f))
+        assert out[0]["status"] == g["status"][f]
+        assert out[0]["n_inliers"] == g["n_inliers"][f]
+        assert out[0]["iterations_run"] == g["iterations_run"][f]
+        assert np.array_equal(mask[0], g["mask"][f])
+        ok, dt, qd = parity.pose_close(g["pose"][f], out[0]["pose"])
+        assert ok, (dt, qd)
+
+
+def test_device_rng_matches_oracle_on_exported_draws(solver):
+    """RS_RNG_DEVICE: the counter-based draws are exported and fed to the oracle; results must agree."""
+    B = 4
+    truth, cur, matches, n = rs.synth.pose_batch(100, B, M)
+    opts = solver.options(seed=5, rng_mode=rs.abi.RS_RNG_DEVICE)
+    out, mask = solver.compute_optimized_pose(cur, matches, n, opts)
+    subsets, normals = solver.export_random(B, 119, 100)
+    for b in range(B):
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], subsets=subsets[b], normals=normals[b], max_matches=M)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
+    # the draws themselves: distinct indices, score reached, Gaussian moments
+    s = subsets[0]
+    for it in range(out[0]["iterations_run"]):   # hypotheses after the early stop are never drawn
+        idx = s[it][s[it] >= 0]
+        assert len(set(idx.tolist())) == len(idx) and 3 <= len(idx) <= 5
+    g = normals[:, :, :, :3].ravel()
+    assert abs(g.mean()) < 0.01 and abs(g.std() - 1) < 0.01
+
+
+def test_device_resident_entry_points(solver):
+    B = 8
+    truth, cur, matches, n = rs.synth.pose_batch(200, B, M)
+    opts = solver.options(seed=9, rng_mode=rs.abi.RS_RNG_DEVICE)
+    out_h, mask_h = solver.compute_optimized_pose(cur, matches, n, opts)
+    solver.upload(cur, matches, n)
+    solver.solve_device(B, opts)
+    out_d, mask_d = solver.download(B)
+    assert out_h.tobytes() == out_d.tobytes() and np.array_equal(mask_h, mask_d)
+    assert (out_d["status"] == 1).all()
+
+
+@pytest.mark.parametrize("scenario", scn.SCENARIOS, ids=[s[0] for s in scn.SCENARIOS])
+def test_reference_scenarios(scenario):
+    """The reference's own 40 pose tests, through the C-ABI, with the reference's tolerances AND against the oracle."""
+    truth, guess, feats = scn.build(scenario)
+    s = rs.PoseOptimization(max_batch=1, max_matches=len(feats))
+    failures = []
+    for seed in range(3):
+        out, mask = s.compute_optimized_pose(guess[None], feats[None], opts=s.options(seed=seed))
+        rout, rmask = ol.pose_solve(guess, feats, seed=seed)
+        # when the oracle itself lands on the degenerate far-away consensus (multi*_100PercentOutliers, see
+        # test_oracle_pose.py) the LM valley is flat: integer outputs must still agree, the pose only loosely
+        strict = scn.check_reference_tolerance(truth, rout["pose"]) is None
+        assert_out_match(rout, out[0], rmask, mask[0], len(feats), cov_rtol=2e-2, strict=strict)
+        err = "status %d" % out[0]["status"] if out[0]["status"] != 1 else scn.check_reference_tolerance(truth, out[0]["pose"])
+        if err:
+            failures.append((seed, err))
+    s.close()
+    if scenario[0].endswith("100PercentOutliers") and scenario[0].startswith("multi"):
+        assert len(failures) <= 1, failures   # seed-dependent in the reference too, see test_oracle_pose.py
+    else:
+        assert not failures, failures
+
+
+def test_failure_and_ragged_batches(solver):
+    """Ragged n_matches, a frame with too little score, a frame with a NaN feature, an all-outlier frame."""
+    B = 5
+    truth, cur, matches, n = rs.synth.pose_batch(300, B, M)
+    n[1] = 4                                    # 4 points: score 0.8 < 1
+    matches[2]["map"][7, 1] = np.nan            # invalid feature
+    n[3] = 137                                  # ragged
+    rng = np.random.default_rng(0)
+    matches[4]["obs"][:300, 0] = rng.uniform(0, 640, 300)   # every point observation random: no consensus
+    matches[4]["obs"][:300, 1] = rng.uniform(0, 480, 300)
+    opts = solver.options(seed=21)
+    out, mask = solver.compute_optimized_pose(cur, matches, n, opts)
+    for b in range(B):
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], seed=21 + b)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
+    assert out[0]["status"] == 1 and out[1]["status"] == 0 and out[2]["status"] == 0 and out[3]["status"] == 1
+    np.testing.assert_array_equal(out[1]["pose"], cur[1])
+    assert mask[1].sum() == 0 and mask[3][137:].sum() == 0
+
+
+def test_many_hypotheses_1024():
+    """BASELINE config 5: 1024 RANSAC hypotheses per frame."""
+    s = rs.PoseOptimization(max_batch=2, max_matches=M, max_iterations=1024, max_variance=100)
+    truth, cur, matches, n = rs.synth.pose_batch(400, 2, M, outlier_frac=0.3)
+    opts = s.options(max_iterations=1024, seed=2, rng_mode=rs.abi.RS_RNG_DEVICE)
+    out, mask = s.compute_optimized_pose(cur, matches, n, opts)
+    subsets, normals = s.export_random(2, 1024, 100)
+    for b in range(2):
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], max_iterations=1024, subsets=subsets[b], normals=normals[b],
+                                    max_matches=M)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
+        assert out[b]["status"] == 1
+    s.close()
+
+
+def test_batch_size_independent(solver):
+    truth, cur, matches, n = rs.synth.pose_batch(500, 8, M)
+    opts = solver.options(seed=0, rng_mode=rs.abi.RS_RNG_REFERENCE)
+    full, fmask = solver.compute_optimized_pose(cur, matches, n, opts)
+    o3 = solver.options(seed=3, rng_mode=rs.abi.RS_RNG_REFERENCE)   # frame b uses mt19937(seed + b)
+    one, omask = solver.compute_optimized_pose(cur[3:4], matches[3:4], n[3:4], o3)
+    assert full[3].tobytes() == one[0].tobytes() and np.array_equal(fmask[3], omask[0])
+
+
+def test_invalid_arguments(solver):
+    truth, cur, matches, n = rs.synth.pose_batch(0, 2, M)
+    with pytest.raises(rs.RsError):
+        solver.compute_optimized_pose(cur, matches, n, solver.options(max_iterations=5000))
+    with pytest.raises(rs.RsError):
+        solver.solve_device(2, solver.options(rng_mode=rs.abi.RS_RNG_REFERENCE))
