@@ -26,15 +26,20 @@
 // FP64 throughout (forward differences with h = 1.49e-8 |x| on mm-scale coordinates need it).
 #include <float.h>
 
-#include "plane_fit.cuh"  // make_givens
+#include "plane_fit.cuh"  // normalize3
 #include "pose_internal.cuh"
 
 namespace rs {
 
 namespace {
 
-constexpr int WARPS = 8;
+constexpr int WARPS = 8;             // warps per CTA of the Monte-Carlo kernel (one sample each)
 constexpr int THREADS = WARPS * 32;
+// RANSAC: hypotheses evaluated concurrently per frame. The reference never stops before iteration 3, so the first
+// chunk (iterations 0..3) is always needed; larger chunks would only add hypotheses the serial reference skips
+// after its early stop (and the CTA waits for the slowest LM of a chunk).
+constexpr int RWARPS = 4;
+constexpr int RTHREADS = RWARPS * 32;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double kSqrtEps = 1.4901161193847656e-08;  // sqrt(DBL_EPSILON): ftol, xtol and the difference step
 constexpr int kRunning = -100;
@@ -56,10 +61,10 @@ struct Xform {
 };
 
 struct WarpLM {
-    double x[6], xt[6], diag[6], qtf[6], p[6], wa1[6], wa2[6], wa3[6], g[6], h[6], sdiag[6], xs[6];
-    double A[36];  // J^T J, then scratch of the factorisation
-    double R[36];  // upper-triangular factor, row-major
-    double s[36];  // qrsolv working copy
+    double x[6], xt[6], diag[6], p[6], wa2[6], sc[6], g[6], h[6], dinv[6], xs[6];
+    double A[36];  // J^T J
+    double C[36];  // column-scaled copy S A S
+    double L[36];  // pivoted LDL^T of C (unit lower factor below the diagonal)
     Xform T[7];    // transforms at x (0) and x + h_j e_j (1..6); T[0] is reused for the trial point
     double fnorm, par, delta, xnorm, gnorm, pnorm;
     int perm[6];
@@ -260,6 +265,12 @@ __device__ inline double eval_sumsq(const Problem& P, const Xform& T, const Pose
 }
 
 // ---- lane-0 algebra on the shared 6x6 state ---------------------------------------------------------------------
+// MINPACK's lmder/lmpar work on the triangular factor R of J P = Q R and on Q^T r. Every quantity they need is a
+// function of A = J^T J = P R^T R P^T and g = J^T r = P R^T (Q^T r):   the Gauss-Newton step solves A x = g, the
+// damped step solves (A + par D^2) x = g, |J p|^2 = p^T A p, (R^T Q^T r)_j = g_perm(j), and the Newton correction of
+// lmpar is w^T (A + par D^2)^-1 w. They are evaluated here with LDL^T factorisations (no square roots, six
+// reciprocals) of the column-scaled matrix C = S A S, S = diag(1/|J_j|), which removes the mm-vs-quaternion scale
+// disparity of the columns before the squared condition number can hurt. Same iterates as lmpar/qrsolv up to rounding.
 __device__ inline double norm6(const double* v)
 {
     double s = 0.0;
@@ -267,142 +278,109 @@ __device__ inline double norm6(const double* v)
     return sqrt(s);
 }
 
-// R (upper, with column permutation perm) such that R^T R = P^T (J^T J) P, via diagonal-pivoted Cholesky of the
-// column-scaled matrix; qtf = R^-T P^T (J^T r) = first 6 entries of Q^T r. wa2 = column norms of J.
+// In: S.A, S.g. Out: S.wa2 (column norms of J), S.sc (1/norm), S.C (scaled A), pivoted LDL^T of C in S.L / S.dinv /
+// S.perm, S.rank.
 __device__ inline void factorize(WarpLM& S)
 {
-    double* C = S.A;
-    for (int j = 0; j < 6; ++j) S.wa2[j] = sqrt(fmax(C[j * 6 + j], 0.0));
-    double sc[6];
-    for (int j = 0; j < 6; ++j) sc[j] = S.wa2[j] > 0.0 ? 1.0 / S.wa2[j] : 1.0;
+    for (int j = 0; j < 6; ++j) {
+        S.wa2[j] = sqrt(fmax(S.A[j * 6 + j], 0.0));
+        S.sc[j] = S.wa2[j] > 0.0 ? 1.0 / S.wa2[j] : 1.0;
+    }
     for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) C[i * 6 + j] = C[i * 6 + j] * sc[i] * sc[j];
+        for (int j = 0; j < 6; ++j) {
+            const double c = S.A[i * 6 + j] * S.sc[i] * S.sc[j];
+            S.C[i * 6 + j] = c;
+            S.L[i * 6 + j] = c;
+        }
+    double* M = S.L;
     for (int j = 0; j < 6; ++j) S.perm[j] = j;
-    for (int i = 0; i < 36; ++i) S.R[i] = 0.0;
     int rank = 6;
     for (int k = 0; k < 6; ++k) {
         int piv = k;
-        double best = C[k * 6 + k];
+        double best = M[k * 6 + k];
         for (int i = k + 1; i < 6; ++i)
-            if (C[i * 6 + i] > best) {
-                best = C[i * 6 + i];
+            if (M[i * 6 + i] > best) {
+                best = M[i * 6 + i];
                 piv = i;
             }
         if (piv != k) {
             for (int j = 0; j < 6; ++j) {
-                const double t = C[k * 6 + j];
-                C[k * 6 + j] = C[piv * 6 + j];
-                C[piv * 6 + j] = t;
+                const double t = M[k * 6 + j];
+                M[k * 6 + j] = M[piv * 6 + j];
+                M[piv * 6 + j] = t;
             }
             for (int i = 0; i < 6; ++i) {
-                const double t = C[i * 6 + k];
-                C[i * 6 + k] = C[i * 6 + piv];
-                C[i * 6 + piv] = t;
-            }
-            for (int i = 0; i < k; ++i) {
-                const double t = S.R[i * 6 + k];
-                S.R[i * 6 + k] = S.R[i * 6 + piv];
-                S.R[i * 6 + piv] = t;
+                const double t = M[i * 6 + k];
+                M[i * 6 + k] = M[i * 6 + piv];
+                M[i * 6 + piv] = t;
             }
             const int t = S.perm[k];
             S.perm[k] = S.perm[piv];
             S.perm[piv] = t;
         }
-        // the scaled matrix has unit diagonal: a pivot at rounding level means a dependent column
+        // C has a unit diagonal: a pivot at rounding level means a column that depends on the previous ones
         if (!(best > 64.0 * DBL_EPSILON)) {
             rank = k;
             break;
         }
-        const double rkk = sqrt(best);
-        S.R[k * 6 + k] = rkk;
-        for (int j = k + 1; j < 6; ++j) S.R[k * 6 + j] = C[k * 6 + j] / rkk;
-        for (int i = k + 1; i < 6; ++i)
-            for (int j = i; j < 6; ++j) {
-                C[i * 6 + j] -= S.R[k * 6 + i] * S.R[k * 6 + j];
-                C[j * 6 + i] = C[i * 6 + j];
-            }
+        const double dinv = 1.0 / best;
+        S.dinv[k] = dinv;
+        double col[6];
+        for (int i = k + 1; i < 6; ++i) col[i] = M[i * 6 + k];
+        for (int i = k + 1; i < 6; ++i) {
+            const double lik = col[i] * dinv;
+            for (int j = k + 1; j < 6; ++j) M[i * 6 + j] -= lik * col[j];
+            M[i * 6 + k] = lik;
+        }
     }
     S.rank = rank;
-    // undo the column scaling: R[:, j] *= |J col perm[j]|
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) S.R[i * 6 + j] *= S.wa2[S.perm[j]];
-    // qtf: forward substitution with R^T
-    for (int i = 0; i < 6; ++i) {
-        if (i >= rank) {
-            S.qtf[i] = 0.0;
-            continue;
-        }
-        double sum = S.g[S.perm[i]];
-        for (int k = 0; k < i; ++k) sum -= S.R[k * 6 + i] * S.qtf[k];
-        S.qtf[i] = sum / S.R[i * 6 + i];
-    }
 }
 
-// unsupported/Eigen/src/NonLinearOptimization/qrsolv.h on the 6x6 working copy s
-__device__ inline void qrsolv(WarpLM& S, const double* diag /* sqrt(par) * diag */, double* x)
+// quadratic form v^T C^-1 v through the pivoted factorisation (full rank only); v in original ordering
+__device__ inline double quad_form_pivoted(const WarpLM& S, const double* v)
 {
-    double* s = S.s;
-    double wa[6];
-    for (int j = 0; j < 6; ++j) {
-        x[j] = s[j * 6 + j];
-        wa[j] = S.qtf[j];
+    double z[6], q = 0.0;
+    for (int i = 0; i < 6; ++i) {
+        double sum = v[S.perm[i]];
+        for (int j = 0; j < i; ++j) sum -= S.L[i * 6 + j] * z[j];
+        z[i] = sum;
+        q += sum * sum * S.dinv[i];
     }
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < i; ++j) s[i * 6 + j] = s[j * 6 + i];
-    for (int j = 0; j < 6; ++j) {
-        const int l = S.perm[j];
-        if (diag[l] == 0.0) break;
-        for (int k = j; k < 6; ++k) S.sdiag[k] = 0.0;
-        S.sdiag[j] = diag[l];
-        double qtbpj = 0.0;
-        for (int k = j; k < 6; ++k) {
-            double gc, gs;
-            make_givens(-s[k * 6 + k], S.sdiag[k], gc, gs);
-            s[k * 6 + k] = gc * s[k * 6 + k] + gs * S.sdiag[k];
-            const double temp = gc * wa[k] + gs * qtbpj;
-            qtbpj = -gs * wa[k] + gc * qtbpj;
-            wa[k] = temp;
-            for (int i = k + 1; i < 6; ++i) {
-                const double t = gc * s[i * 6 + k] + gs * S.sdiag[i];
-                S.sdiag[i] = -gs * s[i * 6 + k] + gc * S.sdiag[i];
-                s[i * 6 + k] = t;
-            }
-        }
-    }
-    int nsing = 0;
-    while (nsing < 6 && S.sdiag[nsing] != 0.0) ++nsing;
-    for (int j = nsing; j < 6; ++j) wa[j] = 0.0;
-    for (int i = nsing - 1; i >= 0; --i) {
-        double sum = wa[i];
-        for (int j = i + 1; j < nsing; ++j) sum -= s[j * 6 + i] * wa[j];
-        wa[i] = sum / s[i * 6 + i];
-    }
-    for (int j = 0; j < 6; ++j) {
-        S.sdiag[j] = s[j * 6 + j];
-        s[j * 6 + j] = x[j];
-    }
-    for (int j = 0; j < 6; ++j) x[S.perm[j]] = wa[j];
+    return q;
 }
 
-// unsupported/Eigen/src/NonLinearOptimization/lmpar.h (lmpar2): trust-region parameter and step S.xs
+// basic solution of C u = b on the leading `rank` pivots (zeros elsewhere), returned in original ordering
+__device__ inline void solve_pivoted(const WarpLM& S, const double* b, double* u)
+{
+    double z[6];
+    const int r = S.rank;
+    for (int i = 0; i < r; ++i) {
+        double sum = b[S.perm[i]];
+        for (int j = 0; j < i; ++j) sum -= S.L[i * 6 + j] * z[j];
+        z[i] = sum;
+    }
+    for (int i = r - 1; i >= 0; --i) {
+        double sum = z[i] * S.dinv[i];
+        for (int j = i + 1; j < r; ++j) sum -= S.L[j * 6 + i] * z[j];
+        z[i] = sum;
+    }
+    for (int i = 0; i < 6; ++i) u[S.perm[i]] = i < r ? z[i] : 0.0;
+}
+
+// unsupported/Eigen/src/NonLinearOptimization/lmpar.h (lmpar2): trust-region parameter S.par and step S.xs
 __device__ inline void lmpar(WarpLM& S)
 {
     const double dwarf = DBL_MIN;
     const double delta = S.delta;
-    double* wa1 = S.wa1;
-    double* wa2 = S.wa3;  // scratch (S.wa2 holds the column norms)
     double* x = S.xs;
-    const int rank = S.rank;
-    for (int j = 0; j < 6; ++j) wa1[j] = (j < rank) ? S.qtf[j] : 0.0;
-    for (int i = rank - 1; i >= 0; --i) {
-        double sum = wa1[i];
-        for (int j = i + 1; j < rank; ++j) sum -= S.R[i * 6 + j] * wa1[j];
-        wa1[i] = sum / S.R[i * 6 + i];
+    double sg[6], u[6], wa2[6], w[6];
+    for (int j = 0; j < 6; ++j) sg[j] = S.sc[j] * S.g[j];
+    // Gauss-Newton direction
+    solve_pivoted(S, sg, u);
+    for (int j = 0; j < 6; ++j) {
+        x[j] = S.sc[j] * u[j];
+        wa2[j] = S.diag[j] * x[j];
     }
-    for (int j = 0; j < 6; ++j) x[S.perm[j]] = wa1[j];
-
-    int iter = 0;
-    for (int j = 0; j < 6; ++j) wa2[j] = S.diag[j] * x[j];
     double dxnorm = norm6(wa2);
     double fp = dxnorm - delta;
     if (fp <= 0.1 * delta) {
@@ -410,22 +388,16 @@ __device__ inline void lmpar(WarpLM& S)
         return;
     }
     double parl = 0.0;
-    if (rank == 6) {
-        for (int j = 0; j < 6; ++j) wa1[j] = S.diag[S.perm[j]] * wa2[S.perm[j]] / dxnorm;
-        for (int i = 0; i < 6; ++i) {
-            double sum = wa1[i];
-            for (int j = 0; j < i; ++j) sum -= S.R[j * 6 + i] * wa1[j];
-            wa1[i] = sum / S.R[i * 6 + i];
-        }
-        const double temp = norm6(wa1);
-        parl = fp / delta / temp / temp;
+    if (S.rank == 6) {
+        for (int j = 0; j < 6; ++j) w[j] = S.sc[j] * (S.diag[j] * wa2[j] / dxnorm);
+        parl = fp / delta / quad_form_pivoted(S, w);
     }
+    double gn = 0.0;
     for (int j = 0; j < 6; ++j) {
-        double sum = 0.0;
-        for (int i = 0; i <= j; ++i) sum += S.R[i * 6 + j] * S.qtf[i];
-        wa1[j] = sum / S.diag[S.perm[j]];
+        const double t = S.g[j] / S.diag[j];
+        gn += t * t;
     }
-    const double gnorm = norm6(wa1);
+    const double gnorm = sqrt(gn);
     double paru = gnorm / delta;
     if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
     double par = S.par;
@@ -433,27 +405,60 @@ __device__ inline void lmpar(WarpLM& S)
     par = fmin(par, paru);
     if (par == 0.0) par = gnorm / dxnorm;
 
-    for (int i = 0; i < 36; ++i) S.s[i] = S.R[i];
+    double e2[6];
+    for (int j = 0; j < 6; ++j) {
+        const double e = S.diag[j] * S.sc[j];
+        e2[j] = e * e;
+    }
+    int iter = 0;
     while (true) {
         ++iter;
         if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-        const double sq = sqrt(par);
-        double dsc[6];
-        for (int j = 0; j < 6; ++j) dsc[j] = sq * S.diag[j];
-        qrsolv(S, dsc, x);
-        for (int j = 0; j < 6; ++j) wa2[j] = S.diag[j] * x[j];
+        // LDL^T of C + par E^2 (lower triangle, no pivoting: positive definite for par > 0)
+        double M[36], dinv[6];
+        for (int i = 0; i < 6; ++i) {
+            for (int j = 0; j < i; ++j) M[i * 6 + j] = S.C[i * 6 + j];
+            M[i * 6 + i] = S.C[i * 6 + i] + par * e2[i];
+        }
+        for (int k = 0; k < 6; ++k) {
+            const double dk = 1.0 / M[k * 6 + k];
+            dinv[k] = dk;
+            double col[6];
+            for (int i = k + 1; i < 6; ++i) col[i] = M[i * 6 + k];
+            for (int i = k + 1; i < 6; ++i) {
+                const double lik = col[i] * dk;
+                for (int j = k + 1; j <= i; ++j) M[i * 6 + j] -= lik * col[j];
+                M[i * 6 + k] = lik;
+            }
+        }
+        double z[6];
+        for (int i = 0; i < 6; ++i) {
+            double sum = sg[i];
+            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
+            z[i] = sum;
+        }
+        for (int i = 5; i >= 0; --i) {
+            double sum = z[i] * dinv[i];
+            for (int j = i + 1; j < 6; ++j) sum -= M[j * 6 + i] * z[j];
+            z[i] = sum;
+        }
+        for (int j = 0; j < 6; ++j) {
+            x[j] = S.sc[j] * z[j];
+            wa2[j] = S.diag[j] * x[j];
+        }
         dxnorm = norm6(wa2);
-        double temp = fp;
+        const double temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-        for (int j = 0; j < 6; ++j) wa1[j] = S.diag[S.perm[j]] * (wa2[S.perm[j]] / dxnorm);
-        for (int j = 0; j < 6; ++j) {
-            wa1[j] /= S.sdiag[j];
-            temp = wa1[j];
-            for (int i = j + 1; i < 6; ++i) wa1[i] -= S.s[i * 6 + j] * temp;
+        // Newton correction: parc = fp / delta / (w^T (A + par D^2)^-1 w), w = D^2 x / |D x|
+        double q = 0.0;
+        for (int i = 0; i < 6; ++i) {
+            double sum = S.sc[i] * (S.diag[i] * (wa2[i] / dxnorm));
+            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
+            z[i] = sum;
+            q += sum * sum * dinv[i];
         }
-        temp = norm6(wa1);
-        const double parc = fp / delta / temp / temp;
+        const double parc = fp / delta / q;
         if (fp > 0.0) parl = fmax(parl, par);
         if (fp < 0.0) paru = fmin(paru, par);
         par = fmax(parl, par + parc);
@@ -489,7 +494,7 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
                 double h = kSqrtEps * fabs(xx[lane - 1]);
                 if (h == 0.0) h = kSqrtEps;
                 xx[lane - 1] += h;
-                S.h[lane - 1] = h;
+                S.h[lane - 1] = 1.0 / h;  // the difference quotient's rounding is far below the forward-difference error
             }
             make_xform(xx, S.T[lane]);
         }
@@ -511,7 +516,7 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
             for (int j = 0; j < 6; ++j) {
                 feature_residual(type, o, mm, S.T[j + 1], K, rj);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) J[c][j] = (rj[c] - r[c]) / ih[j];
+                for (int c = 0; c < 3; ++c) J[c][j] = (rj[c] - r[c]) * ih[j];
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -553,14 +558,11 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
                 S.delta = 100.0 * S.xnorm;
                 if (S.delta == 0.0) S.delta = 100.0;
             }
+            // gnorm = max_j |J_j . r| / (|J_j| |r|)
             double gnorm = 0.0;
             if (S.fnorm != 0.0)
                 for (int j = 0; j < 6; ++j)
-                    if (S.wa2[S.perm[j]] != 0.0) {
-                        double sum = 0.0;
-                        for (int i = 0; i <= j; ++i) sum += S.R[i * 6 + j] * (S.qtf[i] / S.fnorm);
-                        gnorm = fmax(gnorm, fabs(sum / S.wa2[S.perm[j]]));
-                    }
+                    if (S.wa2[j] != 0.0) gnorm = fmax(gnorm, fabs((S.g[j] / S.fnorm) * S.sc[j]));
             S.gnorm = gnorm;
             if (gnorm <= 0.0) S.status = 4;  // CosinusTooSmall (gtol = 0)
             for (int j = 0; j < 6; ++j) S.diag[j] = fmax(S.diag[j], S.wa2[j]);
@@ -587,17 +589,18 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
             if (lane == 0) {
                 ++S.nfev;
                 const double fnorm = S.fnorm, fnorm1 = sqrt(ss1), pnorm = S.pnorm;
+                const double inv_fnorm = 1.0 / fnorm;
                 double actred = -1.0;
-                if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+                if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 * inv_fnorm) * (fnorm1 * inv_fnorm);
+                // |J p|^2 = p^T A p
+                double pAp = 0.0;
                 for (int i = 0; i < 6; ++i) {
                     double sum = 0.0;
-                    for (int j = i; j < 6; ++j) sum += S.R[i * 6 + j] * S.p[S.perm[j]];
-                    S.wa3[i] = sum;
+                    for (int j = 0; j < 6; ++j) sum += S.A[i * 6 + j] * S.p[j];
+                    pAp += sum * S.p[i];
                 }
-                const double r1 = norm6(S.wa3) / fnorm;
-                const double temp1 = r1 * r1;
-                const double r2 = sqrt(S.par) * pnorm / fnorm;
-                const double temp2 = r2 * r2;
+                const double temp1 = fmax(pAp, 0.0) * inv_fnorm * inv_fnorm;
+                const double temp2 = S.par * (pnorm * inv_fnorm) * (pnorm * inv_fnorm);
                 const double prered = temp1 + temp2 / 0.5;
                 const double dirder = -(temp1 + temp2);
                 double ratio = 0.0;
@@ -789,10 +792,10 @@ struct RansacShared {
     double best_x[6];
     double max_score;
     int best_inliers, best_iteration, can_quit, started;
-    double hyp_x[WARPS][6];
-    double hyp_score[WARPS];
-    int hyp_ok[WARPS];
-    int hyp_inliers[WARPS];
+    double hyp_x[RWARPS][6];
+    double hyp_score[RWARPS];
+    int hyp_ok[RWARPS];
+    int hyp_inliers[RWARPS];
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) / 16 * 16; }
@@ -803,9 +806,9 @@ struct RansacSmem {
     double* obs;
     double* map;
     WarpLM* lm;
-    unsigned* hyp_mask;   // [WARPS][words]
+    unsigned* hyp_mask;   // [RWARPS][words]
     unsigned* best_mask;  // [words]
-    short* subset;        // [WARPS][RS_MAX_SUBSET]
+    short* subset;        // [RWARPS][RS_MAX_SUBSET]
     short* inlier_idx;    // [M]
     RansacShared* sh;
 };
@@ -820,12 +823,12 @@ __host__ __device__ inline size_t ransac_carve(RansacSmem* s, unsigned char* bas
     };
     unsigned char* obs = take(sizeof(double) * 4 * M);
     unsigned char* map = take(sizeof(double) * 4 * M);
-    unsigned char* lm = take(sizeof(WarpLM) * WARPS);
+    unsigned char* lm = take(sizeof(WarpLM) * RWARPS);
     unsigned char* sh = take(sizeof(RansacShared));
     unsigned char* type = take(sizeof(int32_t) * M);
-    unsigned char* hm = take(sizeof(unsigned) * WARPS * words);
+    unsigned char* hm = take(sizeof(unsigned) * RWARPS * words);
     unsigned char* bm = take(sizeof(unsigned) * words);
-    unsigned char* sub = take(sizeof(short) * WARPS * RS_MAX_SUBSET);
+    unsigned char* sub = take(sizeof(short) * RWARPS * RS_MAX_SUBSET);
     unsigned char* ii = take(sizeof(short) * M);
     if (s) {
         s->obs = reinterpret_cast<double*>(obs), s->map = reinterpret_cast<double*>(map);
@@ -838,7 +841,7 @@ __host__ __device__ inline size_t ransac_carve(RansacSmem* s, unsigned char* bas
 }
 
 // compute_pose_with_ransac (pose_optimization.cpp:107-262): one CTA per frame.
-__global__ void __launch_bounds__(THREADS) pose_ransac_kernel(const PoseBuffers buf, const PoseLaunch prm)
+__global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
@@ -878,7 +881,7 @@ __global__ void __launch_bounds__(THREADS) pose_ransac_kernel(const PoseBuffers 
     Problem P;
     P.type = sm.type, P.obs = sm.obs, P.map = sm.map, P.M = M;
 
-    for (int chunk = 0; chunk < maxIterations; chunk += WARPS) {
+    for (int chunk = 0; chunk < maxIterations; chunk += RWARPS) {
         const int it = chunk + warp;
         if (it < maxIterations) {
             // ---- random subset: ransac::get_random_subset_with_score (ransac.hpp:77-103) ----
@@ -966,7 +969,7 @@ __global__ void __launch_bounds__(THREADS) pose_ransac_kernel(const PoseBuffers 
         __syncthreads();
         // ---- the reference's serial bookkeeping over this chunk, in iteration order (:151-227) ----
         if (threadIdx.x == 0) {
-            for (int w = 0; w < WARPS; ++w) {
+            for (int w = 0; w < RWARPS; ++w) {
                 const int iteration = chunk + w;
                 if (iteration >= maxIterations || sh.can_quit) break;
                 ++sh.started;
@@ -1253,7 +1256,7 @@ int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream
         RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
     }
-    pose_ransac_kernel<<<prm.batch, THREADS, smem, stream>>>(buf, prm);
+    pose_ransac_kernel<<<prm.batch, RTHREADS, smem, stream>>>(buf, prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }
