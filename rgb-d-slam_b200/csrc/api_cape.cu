@@ -121,10 +121,16 @@ int encode_tmap(rs_cape_ctx* c, const float* depth_dev, int batch)
         return RS_ERR_CUDA;
     }
     // tensor view of the depth batch: dim0 = pixel column inside a cell, dim1 = cell column, dim2 = image row
-    // (frames are contiguous, so batch*H rows). A {cs, 1, cs} box is one cell, landing dense in shared memory.
+    // (frames are contiguous, so batch*H rows). A {cs, 8, R} box is R rows of 8 adjacent cells, landing dense in shared
+    // memory as [row][cell][px]; cells beyond the last cell column are zero-filled by the TMA unit.
+    const int boxRows = cape_cell_fit_box_rows(c->cell);
+    if (boxRows <= 0) {
+        set_last_error("rs_cape: unsupported cell size (the plane-fit kernel is built for 20 and 40 px cells)");
+        return RS_ERR_INVALID_ARG;
+    }
     const cuuint64_t dims[3] = {cuuint64_t(c->cell), cuuint64_t(c->hc), cuuint64_t(batch) * cuuint64_t(c->H)};
     const cuuint64_t strides[2] = {cuuint64_t(c->cell) * 4, cuuint64_t(c->W) * 4};
-    const cuuint32_t box[3] = {cuuint32_t(c->cell), 1, cuuint32_t(c->cell)};
+    const cuuint32_t box[3] = {cuuint32_t(c->cell), cuuint32_t(cape_cell_fit_box_cells()), cuuint32_t(boxRows)};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(depth_dev), dims, strides, box,
                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -4,14 +4,17 @@
 //                   Plane_Segment::init_plane_segment + fit_plane         (plane_segment.cpp:44-168,205-284)
 //                   Primitive_Detection::init_planar_cell_fitting          (primitive_detection.cpp:187-221)
 //
-// Mapping: one warp owns a run of CPI consecutive cells of one cell-row ("item"). For every cell the warp's lane 0
-// TMA-loads the cs x cs depth tile (a 3-D tiled tensor map over [row][cell-col][px] makes it land as a dense,
-// bank-conflict-free cs*cs float tile) into a STAGES-deep per-warp ring guarded by mbarriers; lanes read float4
-// columns, back-project in FP64 (cast to float, as the reference's cloud), and accumulate the nine sums of FP32
-// values/products in FP64. The cross-shaped continuity test runs lane-parallel from the same tile. After the CPI
-// cells are reduced, the 3x3 eigen-solves are done lane-parallel (one cell per lane) — a warp-wide solve per cell
-// would spend ~5x the accumulation time on 1/32-utilised FP64 issue slots. Records (160 B) are staged in shared
-// memory and written with 16-byte coalesced stores.
+// Mapping: one warp owns a run of up to 32 consecutive cells of one cell-row. The run is consumed as "items" of
+// 8 cells, FOUR LANES PER CELL: a 3-D tiled TMA box {cs px, 8 cells, R rows} (R*cs*8*4 = 6400 B) lands as
+// [row][cell][px] in a 2-slot per-warp ring guarded by mbarriers; lane (c = lane/4, j = lane%4) reads the float4
+// j, j+4, j+8, ... of cell c's part of the box (LDS.128, at most 2-way bank conflicts), back-projects in FP64
+// (cast to float, as the reference's cloud) and accumulates the nine sums of FP32 values / FP32 products in FP64.
+// The pixel loop is branch-free: an invalid pixel (z <= 0) contributes exact zeros, as its (0,0,0) cloud row does.
+// Per item the sums are reduced over the 4 lanes of a cell with two shuffle steps (instead of five for a warp-wide
+// cell) and handed to lane 8*item + c, so that after four items every lane holds one cell; the cross-shaped
+// continuity test runs from small per-warp copies of the middle row / middle column, split over the 4 lanes of
+// the cell. The 3x3 eigen-solves are then lane-parallel (one cell per lane) and every lane stores its own 160-byte
+// record with 16-byte stores.
 //
 // Compiled with -fmad=false: products are FP32-rounded then accumulated in FP64 exactly as the reference does.
 #include <cuda.h>
@@ -24,247 +27,291 @@ namespace rs {
 
 namespace {
 
-constexpr int REC_STRIDE = 176;  // bytes per staged record (160 used), multiple of 16
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CELLS_PER_ITEM = 8;
+constexpr int WARPS = 4;
 
-// per-cell accumulator staged in shared memory between the accumulate and the fit phase (<= REC_STRIDE bytes)
-struct CellAcc {
-    double S[9];
-    int count;
-    int ok;          // continuity tests passed and enough positive pixels
-    float p0[3];     // cloud row 0 of the cell (x,y,z) — zeros when the pixel is invalid
-    float pl[3];     // cloud row P-1
-};
-static_assert(sizeof(CellAcc) <= REC_STRIDE, "accumulator must fit the record slot");
-
-// Lane-parallel restatement of is_cell_{horizontal,vertical}_continuous (plane_segment.cpp:44-100).
-// Elements e_i = base[i*stride], i = 0..n-1. Reference: last = max(e_0, e_1); fail if last <= 0; for i = 1..n-1:
-// a positive e_i must satisfy |e_i - last| <= 4*quant(e_i) and then becomes `last`. Because any failure rejects the
-// cell, `last` at step i is the nearest positive element in [1, i-1] (or the initial max when there is none).
-__device__ __forceinline__ bool continuity_scan(const float* base, const int stride, const int n, const int lane)
+// Indices e_i = base[i * stride], i in [0, n). Reference (plane_segment.cpp:44-100): last = max(e_0, e_1); fail if
+// last <= 0; for i = 1..n-1 a positive e_i must satisfy |e_i - last| <= 4 quant(e_i) and then becomes `last`.
+// Because any failure rejects the cell, `last` at step i is the nearest positive element in [1, i-1] (or the initial
+// max when there is none): this checks the elements [lo, hi) only, looking backwards for their predecessor.
+__device__ __forceinline__ bool continuity_segment(const float* base, const int stride, const int lo, const int hi,
+                                                   const float init)
 {
-    const float e0 = base[0], e1 = base[stride];
-    float carry = fmaxf(e0, e1);
-    if (carry <= 0.f) return false;
+    float prev = init;
+    for (int i = lo - 1; i >= 1; --i) {
+        const float z = base[i * stride];
+        if (z > 0.f) {
+            prev = z;
+            break;
+        }
+    }
     bool ok = true;
-    for (int first = 1; first < n; first += 32) {
-        const int i = first + lane;
-        const float z = (i < n) ? base[i * stride] : 0.f;
-        const bool valid = z > 0.f;
-        const unsigned mask = __ballot_sync(0xffffffffu, valid);
-        const unsigned lower = mask & ((1u << lane) - 1u);
-        const int src = lower ? (31 - __clz(lower)) : 0;
-        const float pz = __shfl_sync(0xffffffffu, z, src);
-        const float prev = lower ? pz : carry;
-        if (valid) {
+    for (int i = lo; i < hi; ++i) {
+        const float z = base[i * stride];
+        if (z > 0.f) {
             const float diff = fabsf(z - prev);
             if (!(static_cast<double>(diff) <= 4.0 * depth_quantization(static_cast<double>(z)))) ok = false;
+            prev = z;
         }
-        const int hi = mask ? (31 - __clz(mask)) : 0;
-        const float cz = __shfl_sync(0xffffffffu, z, hi);
-        if (mask) carry = cz;
     }
-    return __all_sync(0xffffffffu, ok);
+    return ok;
 }
 
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+template <int CS>
+struct Geometry {
+    static constexpr int G = CS / 4;                                 // float4 groups per cell row
+    static constexpr int R = 6400 / (CS * CELLS_PER_ITEM * 4);       // rows per TMA box (10 @20 px, 5 @40 px)
+    static constexpr int NBOX = CS / R;                              // boxes per item
+    static constexpr int BOX_BYTES = R * CS * CELLS_PER_ITEM * 4;    // 6400
+    static constexpr int F4_PER_CELL_BOX = R * G;                    // float4 of one cell in one box (50)
+    static constexpr int ITERS = (F4_PER_CELL_BOX + 3) / 4;          // per-lane trips per box (13)
+    static constexpr int ROW_FLOATS = CS * CELLS_PER_ITEM;           // one box row in floats
+    static constexpr int MID_BYTES = 2 * CELLS_PER_ITEM * CS * 4;    // middle row + middle column copies
+    static constexpr int WARP_BYTES = (2 * BOX_BYTES + MID_BYTES + 16 + 127) / 128 * 128;  // TMA destinations stay 128-B aligned
+    static_assert(CS % 4 == 0 && CS % R == 0 && R * CS * CELLS_PER_ITEM * 4 == 6400, "unsupported cell size");
+};
 
-template <int CS, int CPI, int STAGES, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (CS <= 20 ? 2 : 1)) cape_cell_fit_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                    const CellFitParams prm, rs_cell_out* __restrict__ cells)
+template <int CS>
+__global__ void __launch_bounds__(WARPS * 32, (CS <= 20 ? 4 : 3))
+        cape_cell_fit_kernel(const __grid_constant__ CUtensorMap tmap, const CellFitParams prm, rs_cell_out* __restrict__ cells)
 {
+    using Geo = Geometry<CS>;
     constexpr int P = CS * CS;
-    constexpr int G = CS / 4;              // float4 groups per tile row
-    constexpr int RPI = 32 / G;            // tile rows covered per iteration
-    constexpr int ACTIVE = RPI * G;        // lanes that own a float4 column
-    constexpr int ITERS = (CS + RPI - 1) / RPI;
-    constexpr int TILE_BYTES = P * 4;
-    constexpr int SLOT_BYTES = (TILE_BYTES + 127) / 128 * 128;
-    static_assert(CS % 4 == 0 && G <= 32, "cell side must be a multiple of 4 and <= 128");
+    constexpr int G = Geo::G, R = Geo::R, NBOX = Geo::NBOX;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem_raw + size_t(warp) * (size_t(STAGES) * SLOT_BYTES + size_t(CPI) * REC_STRIDE + 128);
-    float* ring = reinterpret_cast<float*>(wbase);
-    unsigned char* recs = wbase + size_t(STAGES) * SLOT_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(recs + size_t(CPI) * REC_STRIDE);
+    unsigned char* wbase = smem_raw + size_t(warp) * Geo::WARP_BYTES;
+    float* midrow = reinterpret_cast<float*>(wbase + 2 * Geo::BOX_BYTES);   // [8][CS]
+    float* midcol = midrow + CELLS_PER_ITEM * CS;                            // [8][CS] (CS-1 used)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + 2 * Geo::BOX_BYTES + Geo::MID_BYTES);
 
-    const int item = blockIdx.x * WARPS + warp;
-    if (item >= prm.total_items) return;
-    const int ips = prm.items_per_strip;
-    const int b = item / (prm.vc * ips);
-    const int rem = item - b * prm.vc * ips;
+    const int unit = blockIdx.x * WARPS + warp;
+    if (unit >= prm.total_items) return;
+    const int ips = prm.items_per_strip;               // 32-cell runs per cell-row
+    const int b = unit / (prm.vc * ips);
+    const int rem = unit - b * prm.vc * ips;
     const int cr = rem / ips;
-    const int c0 = (rem - cr * ips) * CPI;
-    const int ncell = min(CPI, prm.hc - c0);
-    const int row0 = b * prm.H + cr * CS;  // first image row of the strip in the [B*H] row dimension
+    const int c0 = (rem - cr * ips) * 32;
+    const int ncell = min(32, prm.hc - c0);
+    const int nitems = (ncell + CELLS_PER_ITEM - 1) / CELLS_PER_ITEM;
+    const int nbox = nitems * NBOX;
+    const int row0 = b * prm.H + cr * CS;              // first image row of the strip in the [B*H] row dimension
 
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
         fence_barrier_init();
         fence_proxy_async();
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s)
-            if (s < ncell) {
-                mbar_arrive_expect_tx(&bars[s], TILE_BYTES);
-                tma_load_3d(reinterpret_cast<unsigned char*>(ring) + size_t(s) * SLOT_BYTES, &tmap, 0, c0 + s, row0, &bars[s]);
+        for (int q = 0; q < 2; ++q)
+            if (q < nbox) {
+                mbar_arrive_expect_tx(&bars[q], Geo::BOX_BYTES);
+                tma_load_3d(wbase + q * Geo::BOX_BYTES, &tmap, 0, c0 + (q / NBOX) * CELLS_PER_ITEM, row0 + (q % NBOX) * R, &bars[q]);
             }
     }
     __syncwarp();
 
-    // lane -> (float4 column group g, first tile row r0)
-    const bool active = lane < ACTIVE;
-    const int g = lane % G, r0 = lane / G;
-    double kyr[ITERS];
-#pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
-        const int r = r0 + k * RPI;
-        kyr[k] = (active && r < CS) ? __ldg(prm.ky + cr * CS + r) : 0.0;
-    }
-    constexpr int LAST_LANE = ((CS - 1) % RPI) * G + (G - 1);
-    constexpr int LAST_K = (CS - 1) / RPI;
+    const int c = lane >> 2, j = lane & 3;             // cell inside the item, lane inside the cell
+    const double* kyrow = prm.ky + cr * CS;
 
-    for (int i = 0; i < ncell; ++i) {
-        const int slot = i % STAGES;
-        const float* tile = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(ring) + size_t(slot) * SLOT_BYTES);
-        mbar_wait(&bars[slot], (i / STAGES) & 1);
+    // this lane's final cell (lane = 8 * item + cell): sums, count, flags, first / last cloud rows
+    double F0 = 0, F1 = 0, F2 = 0, F3 = 0, F4 = 0, F5 = 0, F6 = 0, F7 = 0, F8 = 0;
+    int fcount = 0, fok = 0;
+    float fp0x = 0.f, fp0y = 0.f, fp0z = 0.f, fplx = 0.f, fply = 0.f, fplz = 0.f;
 
-        const int col0 = (c0 + i) * CS + g * 4;
-        double kxr[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) kxr[j] = active ? __ldg(prm.kx + col0 + j) : 0.0;
+    double S0 = 0, S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0, S6 = 0, S7 = 0, S8 = 0;
+    int cnt = 0;
+    float p0x = 0.f, p0y = 0.f, p0z = 0.f, plx = 0.f, ply = 0.f, plz = 0.f;
 
-        double S0 = 0, S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0, S6 = 0, S7 = 0, S8 = 0;
-        int cnt = 0;
-        float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, fxl = 0.f, fyl = 0.f, fzl = 0.f;
-#pragma unroll
-        for (int k = 0; k < ITERS; ++k) {
-            const int r = r0 + k * RPI;
-            if (active && r < CS) {
-                const float4 v = *reinterpret_cast<const float4*>(tile + r * CS + g * 4);
+    for (int q = 0; q < nbox; ++q) {
+        const int slot = q & 1;
+        const int item = q / NBOX, bq = q - item * NBOX;
+        const float* tile = reinterpret_cast<const float*>(wbase + slot * Geo::BOX_BYTES);
+        const float* ctile = tile + c * CS;            // this cell's columns inside a box row
+        const int colbase = (c0 + item * CELLS_PER_ITEM + c) * CS;
+        mbar_wait(&bars[slot], (q >> 1) & 1);
+
+        // ---- branch-free accumulation of this lane's float4s of the box ----
+        int r = 0, g = j;                              // flat index j + 4k -> (row r, group g); G >= 5 > 4
+        if (g >= G) {
+            g -= G;
+            ++r;
+        }
+#pragma unroll 1
+        for (int k = 0; k < Geo::ITERS; ++k) {
+            if (r < R) {
+                const float4 v = *reinterpret_cast<const float4*>(ctile + r * Geo::ROW_FLOATS + g * 4);
+                const double2 kxa = __ldg(reinterpret_cast<const double2*>(prm.kx + colbase + g * 4));
+                const double2 kxb = __ldg(reinterpret_cast<const double2*>(prm.kx + colbase + g * 4 + 2));
+                const double kyv = __ldg(kyrow + bq * R + r);
                 const float zz[4] = {v.x, v.y, v.z, v.w};
+                const double kxr[4] = {kxa.x, kxa.y, kxb.x, kxb.y};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float z = zz[j];
-                    if (z > 0.f) {
-                        ++cnt;
-                        const double zd = static_cast<double>(z);
-                        const float x = static_cast<float>(zd * kxr[j]);
-                        const float y = static_cast<float>(zd * kyr[k]);
-                        S0 += static_cast<double>(x);
-                        S1 += static_cast<double>(y);
-                        S2 += zd;
-                        S3 += static_cast<double>(x * x);
-                        S4 += static_cast<double>(y * y);
-                        S5 += static_cast<double>(z * z);
-                        S6 += static_cast<double>(x * y);
-                        S7 += static_cast<double>(y * z);
-                        S8 += static_cast<double>(x * z);
-                        if (k == 0 && j == 0 && lane == 0) fx0 = x, fy0 = y, fz0 = z;
-                        if (k == LAST_K && j == 3 && lane == LAST_LANE) fxl = x, fyl = y, fzl = z;
-                    }
+                for (int t = 0; t < 4; ++t) {
+                    const bool valid = zz[t] > 0.f;
+                    const float z = valid ? zz[t] : 0.f;
+                    cnt += valid ? 1 : 0;
+                    const double zd = static_cast<double>(z);
+                    const float x = static_cast<float>(zd * kxr[t]);
+                    const float y = static_cast<float>(zd * kyv);
+                    S0 += static_cast<double>(x);
+                    S1 += static_cast<double>(y);
+                    S2 += zd;
+                    S3 += static_cast<double>(x * x);
+                    S4 += static_cast<double>(y * y);
+                    S5 += static_cast<double>(z * z);
+                    S6 += static_cast<double>(x * y);
+                    S7 += static_cast<double>(y * z);
+                    S8 += static_cast<double>(x * z);
                 }
             }
-        }
-        // cross-shaped continuity test from the tile: middle row, then middle column without its last row
-        const bool hcont = continuity_scan(tile + (CS / 2) * CS, 1, CS, lane);
-        const bool vcont = continuity_scan(tile + CS / 2, CS, CS - 1, lane);
-        __syncwarp();
-        // the tile is consumed: refill the slot with cell i + STAGES
-        if (lane == 0 && i + STAGES < ncell) {
-            mbar_arrive_expect_tx(&bars[slot], TILE_BYTES);
-            tma_load_3d(const_cast<float*>(tile), &tmap, 0, c0 + i + STAGES, row0, &bars[slot]);
-        }
-
-        const int total = __reduce_add_sync(0xffffffffu, cnt);
-        S0 = warp_sum(S0);
-        S1 = warp_sum(S1);
-        S2 = warp_sum(S2);
-        S3 = warp_sum(S3);
-        S4 = warp_sum(S4);
-        S5 = warp_sum(S5);
-        S6 = warp_sum(S6);
-        S7 = warp_sum(S7);
-        S8 = warp_sum(S8);
-        CellAcc* acc = reinterpret_cast<CellAcc*>(recs + size_t(i) * REC_STRIDE);
-        if (lane == 0) {
-            acc->S[0] = S0, acc->S[1] = S1, acc->S[2] = S2, acc->S[3] = S3, acc->S[4] = S4;
-            acc->S[5] = S5, acc->S[6] = S6, acc->S[7] = S7, acc->S[8] = S8;
-            acc->count = total;
-            acc->ok = (hcont && vcont && total >= P / 2) ? 1 : 0;
-            acc->p0[0] = fx0, acc->p0[1] = fy0, acc->p0[2] = fz0;
-        }
-        if (lane == LAST_LANE) acc->pl[0] = fxl, acc->pl[1] = fyl, acc->pl[2] = fzl;
-    }
-    __syncwarp();
-
-    // ---- fit phase: one cell per lane -----------------------------------------------------------
-    for (int base = 0; base < ncell; base += 32) {
-        const int ci = base + lane;
-        rs_cell_out rec;
-        if (ci < ncell) {
-            const CellAcc a = *reinterpret_cast<const CellAcc*>(recs + size_t(ci) * REC_STRIDE);
-            PlaneModel pm;
-            plane_clear(pm);
-            float tol = 0.f;
-            if (a.ok) {
-                pm.count = a.count;
-#pragma unroll
-                for (int s = 0; s < 9; ++s) pm.S[s] = a.S[s];
-                if (a.count >= prm.min_zero_point_count) {
-                    plane_fit(pm);
-                    const double q = depth_quantization(pm.c[2]);
-                    pm.planar = (pm.mse <= q * q) ? 1 : 0;
-                }
-                if (pm.planar) {
-                    const float dx = a.pl[0] - a.p0[0], dy = a.pl[1] - a.p0[1], dz = a.pl[2] - a.p0[2];
-                    const float diameter = sqrtf((dx * dx + dy * dy) + dz * dz);
-                    tol = fminf(prm.merge_distance, diameter * prm.sin_merge * sqrtf(static_cast<float>(pm.count)));
-                }
+            g += 4;
+            if (g >= G) {
+                g -= G;
+                ++r;
             }
-            rec.count = pm.count;
-            rec.planar = pm.planar;
-#pragma unroll
-            for (int s = 0; s < 9; ++s) rec.S[s] = pm.S[s];
-#pragma unroll
-            for (int s = 0; s < 3; ++s) rec.centroid[s] = pm.c[s], rec.normal[s] = pm.n[s];
-            rec.d = pm.d;
-            rec.mse = pm.mse;
-            rec.score = pm.score;
-            rec.tol = tol;
-            rec.reserved = 0;
+        }
+        // ---- first / last cloud row of the cell (merge tolerance, primitive_detection.cpp:201-220) ----
+        if (j == 0 && bq == 0) {
+            const float z = ctile[0];
+            if (z > 0.f) {
+                const double zd = static_cast<double>(z);
+                p0x = static_cast<float>(zd * __ldg(prm.kx + colbase));
+                p0y = static_cast<float>(zd * __ldg(kyrow));
+                p0z = z;
+            }
+        }
+        if (j == 0 && bq == NBOX - 1) {
+            const float z = ctile[(R - 1) * Geo::ROW_FLOATS + CS - 1];
+            if (z > 0.f) {
+                const double zd = static_cast<double>(z);
+                plx = static_cast<float>(zd * __ldg(prm.kx + colbase + CS - 1));
+                ply = static_cast<float>(zd * __ldg(kyrow + CS - 1));
+                plz = z;
+            }
+        }
+        // ---- keep the middle row / middle column for the continuity test ----
+        {
+            constexpr int MIDBOX = (CS / 2) / R, MIDROW = (CS / 2) % R;
+            if (bq == MIDBOX)
+                for (int t = j; t < CS; t += 4) midrow[c * CS + t] = ctile[MIDROW * Geo::ROW_FLOATS + t];
+            for (int t = j; t < R; t += 4) midcol[c * CS + bq * R + t] = ctile[t * Geo::ROW_FLOATS + CS / 2];
         }
         __syncwarp();
-        if (ci < ncell) *reinterpret_cast<rs_cell_out*>(recs + size_t(ci) * REC_STRIDE) = rec;
-        __syncwarp();
+        // the box is consumed: refill the slot with box q + 2
+        if (lane == 0 && q + 2 < nbox) {
+            const int qn = q + 2;
+            mbar_arrive_expect_tx(&bars[slot], Geo::BOX_BYTES);
+            tma_load_3d(wbase + slot * Geo::BOX_BYTES, &tmap, 0, c0 + (qn / NBOX) * CELLS_PER_ITEM, row0 + (qn % NBOX) * R, &bars[slot]);
+        }
+        if (bq != NBOX - 1) continue;
+
+        // ---- item finished: reduce the 4 lanes of each cell, run the continuity test, hand over to lane 8*item+c ----
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            cnt += __shfl_xor_sync(FULL, cnt, o);
+            S0 += __shfl_xor_sync(FULL, S0, o);
+            S1 += __shfl_xor_sync(FULL, S1, o);
+            S2 += __shfl_xor_sync(FULL, S2, o);
+            S3 += __shfl_xor_sync(FULL, S3, o);
+            S4 += __shfl_xor_sync(FULL, S4, o);
+            S5 += __shfl_xor_sync(FULL, S5, o);
+            S6 += __shfl_xor_sync(FULL, S6, o);
+            S7 += __shfl_xor_sync(FULL, S7, o);
+            S8 += __shfl_xor_sync(FULL, S8, o);
+        }
+        bool cont = true;
+        {
+            // horizontal: CS elements of the middle row; vertical: CS-1 elements of the middle column
+            const float* hr = midrow + c * CS;
+            const float* vcq = midcol + c * CS;
+            const float hinit = fmaxf(hr[0], hr[1]);
+            const float vinit = fmaxf(vcq[0], vcq[1]);
+            constexpr int HSEG = (CS - 1 + 3) / 4, VSEG = (CS - 2 + 3) / 4;
+            const int hlo = 1 + j * HSEG, hhi = min(hlo + HSEG, CS);
+            const int vlo = 1 + j * VSEG, vhi = min(vlo + VSEG, CS - 1);
+            cont = hinit > 0.f && vinit > 0.f;
+            if (cont) cont = continuity_segment(hr, 1, hlo, hhi, hinit) && continuity_segment(vcq, 1, vlo, vhi, vinit);
+        }
+        const unsigned bad = __ballot_sync(FULL, !cont);
+        const int okc = (((bad >> (lane & ~3)) & 0xfu) == 0u && cnt >= P / 2) ? 1 : 0;
+
+        const int src = (lane & 7) * 4;                // leader lane of cell (lane & 7) of this item
+        const bool mine = (lane >> 3) == item;
+        {
+            const double t0 = __shfl_sync(FULL, S0, src), t1 = __shfl_sync(FULL, S1, src), t2 = __shfl_sync(FULL, S2, src);
+            const double t3 = __shfl_sync(FULL, S3, src), t4 = __shfl_sync(FULL, S4, src), t5 = __shfl_sync(FULL, S5, src);
+            const double t6 = __shfl_sync(FULL, S6, src), t7 = __shfl_sync(FULL, S7, src), t8 = __shfl_sync(FULL, S8, src);
+            const int tc = __shfl_sync(FULL, cnt, src), tk = __shfl_sync(FULL, okc, src);
+            const float a0 = __shfl_sync(FULL, p0x, src), a1 = __shfl_sync(FULL, p0y, src), a2 = __shfl_sync(FULL, p0z, src);
+            const float b0 = __shfl_sync(FULL, plx, src), b1 = __shfl_sync(FULL, ply, src), b2 = __shfl_sync(FULL, plz, src);
+            if (mine) {
+                F0 = t0, F1 = t1, F2 = t2, F3 = t3, F4 = t4, F5 = t5, F6 = t6, F7 = t7, F8 = t8;
+                fcount = tc, fok = tk;
+                fp0x = a0, fp0y = a1, fp0z = a2, fplx = b0, fply = b1, fplz = b2;
+            }
+        }
+        S0 = S1 = S2 = S3 = S4 = S5 = S6 = S7 = S8 = 0.0;
+        cnt = 0;
+        p0x = p0y = p0z = plx = ply = plz = 0.f;
+        __syncwarp();                                   // midrow / midcol are rewritten by the next item
     }
 
-    // ---- coalesced 16-byte stores of the ncell * 160 B record run -------------------------------------
-    uint4* dst = reinterpret_cast<uint4*>(cells + (size_t(b) * prm.vc + cr) * prm.hc + c0);
-    for (int t = lane; t < ncell * 10; t += 32) {
-        const int r = t / 10, part = t - r * 10;
-        dst[t] = *reinterpret_cast<const uint4*>(recs + size_t(r) * REC_STRIDE + part * 16);
+    // ---- fit phase: one cell per lane (plane_segment.cpp:102-168 after the sums, primitive_detection.cpp:201-220) ----
+    if (lane >= ncell) return;
+    PlaneModel pm;
+    plane_clear(pm);
+    float tol = 0.f;
+    if (fok) {
+        pm.count = fcount;
+        pm.S[0] = F0, pm.S[1] = F1, pm.S[2] = F2, pm.S[3] = F3, pm.S[4] = F4, pm.S[5] = F5, pm.S[6] = F6, pm.S[7] = F7, pm.S[8] = F8;
+        if (fcount >= prm.min_zero_point_count) {
+            plane_fit(pm);
+            const double qz = depth_quantization(pm.c[2]);
+            pm.planar = (pm.mse <= qz * qz) ? 1 : 0;
+        }
+        if (pm.planar) {
+            const float dx = fplx - fp0x, dy = fply - fp0y, dz = fplz - fp0z;
+            const float diameter = sqrtf((dx * dx + dy * dy) + dz * dz);
+            tol = fminf(prm.merge_distance, diameter * prm.sin_merge * sqrtf(static_cast<float>(pm.count)));
+        }
     }
+    // 160-byte record, ten 16-byte stores
+    double2* dst = reinterpret_cast<double2*>(cells + (size_t(b) * prm.vc + cr) * prm.hc + c0 + lane);
+    double2 head;
+    head.x = __hiloint2double(pm.planar, pm.count);    // {int32 count, int32 planar} little-endian
+    head.y = pm.S[0];
+    dst[0] = head;
+    dst[1] = make_double2(pm.S[1], pm.S[2]);
+    dst[2] = make_double2(pm.S[3], pm.S[4]);
+    dst[3] = make_double2(pm.S[5], pm.S[6]);
+    dst[4] = make_double2(pm.S[7], pm.S[8]);
+    dst[5] = make_double2(pm.c[0], pm.c[1]);
+    dst[6] = make_double2(pm.c[2], pm.n[0]);
+    dst[7] = make_double2(pm.n[1], pm.n[2]);
+    dst[8] = make_double2(pm.d, pm.mse);
+    double2 tail;
+    tail.x = pm.score;
+    tail.y = __hiloint2double(0, __float_as_int(tol));  // {float tol, int32 reserved}
+    dst[9] = tail;
 }
 
-template <int CS, int CPI, int STAGES, int WARPS>
+template <int CS>
 int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream)
 {
-    constexpr int SLOT_BYTES = (CS * CS * 4 + 127) / 128 * 128;
-    constexpr size_t smem = size_t(WARPS) * (size_t(STAGES) * SLOT_BYTES + size_t(CPI) * REC_STRIDE + 128);
-    auto kernel = cape_cell_fit_kernel<CS, CPI, STAGES, WARPS>;
+    using Geo = Geometry<CS>;
+    constexpr size_t smem = size_t(WARPS) * Geo::WARP_BYTES;
+    auto kernel = cape_cell_fit_kernel<CS>;
     static bool configured = false;
     if (!configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        RS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     CellFitParams p = prm;
-    p.items_per_strip = (prm.hc + CPI - 1) / CPI;
+    p.items_per_strip = (prm.hc + 31) / 32;
     p.total_items = prm.batch * prm.vc * p.items_per_strip;
     const int grid = (p.total_items + WARPS - 1) / WARPS;
     kernel<<<grid, WARPS * 32, smem, stream>>>(tmap, p, cells);
@@ -274,20 +321,14 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
 
 }  // namespace
 
+// rows per TMA box for a cell size (the C-ABI glue encodes the tensor map with box {cell, 8, rows})
+int cape_cell_fit_box_rows(int cell) { return cell == 20 ? Geometry<20>::R : (cell == 40 ? Geometry<40>::R : 0); }
+int cape_cell_fit_box_cells() { return CELLS_PER_ITEM; }
+
 int launch_cape_cell_fit(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream)
 {
-    // cells per warp-item: long runs amortise the lane-parallel eigen-solves; short runs keep small batches
-    // spread over all 148 SMs.
-    const long cellsTotal = long(prm.batch) * prm.vc * prm.hc;
-    const bool big = cellsTotal >= 148L * 16 * 32;  // >= one 32-cell item per resident warp
-    if (prm.cell == 20) {
-        if (big) return launch_variant<20, 32, 4, 8>(tmap, prm, cells, stream);
-        return launch_variant<20, 8, 4, 8>(tmap, prm, cells, stream);
-    }
-    if (prm.cell == 40) {
-        if (big) return launch_variant<40, 32, 3, 8>(tmap, prm, cells, stream);
-        return launch_variant<40, 8, 3, 8>(tmap, prm, cells, stream);
-    }
+    if (prm.cell == 20) return launch_variant<20>(tmap, prm, cells, stream);
+    if (prm.cell == 40) return launch_variant<40>(tmap, prm, cells, stream);
     set_last_error("cape_cell_fit: unsupported cell size (built for 20 and 40 px)");
     return RS_ERR_INVALID_ARG;
 }

@@ -18,6 +18,9 @@ struct CellFitParams {
 };
 
 int launch_cape_cell_fit(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream);
+// TMA box of the plane-fit kernel: {cell px, cape_cell_fit_box_cells() cells, cape_cell_fit_box_rows(cell) rows}
+int cape_cell_fit_box_rows(int cell);
+int cape_cell_fit_box_cells();
 
 struct SegmentParams {
     int W, H, hc, vc, cell, batch;

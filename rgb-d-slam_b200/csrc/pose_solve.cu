@@ -64,11 +64,12 @@ struct WarpLM {
     double x[6], xt[6], diag[6], p[6], wa2[6], sc[6], g[6], h[6], dinv[6], xs[6];
     double A[36];  // J^T J
     double C[36];  // column-scaled copy S A S
-    double L[36];  // pivoted LDL^T of C (unit lower factor below the diagonal)
+    double L[36];  // pivoted LDL^T of C (unit lower factor below the diagonal); slow path only
+    double Lp[21]; // fast path: unpivoted LDL^T of C, packed lower triangle (unit factor below the diagonal)
     Xform T[7];    // transforms at x (0) and x + h_j e_j (1..6); T[0] is reused for the trial point
     double fnorm, par, delta, xnorm, gnorm, pnorm;
     int perm[6];
-    int rank, status, nfev, iter, again, pad;
+    int rank, status, nfev, iter, again, fast;
 };
 
 // Features of one LM problem: indices into the frame arrays (idx == nullptr: identity), lane-strided.
@@ -271,27 +272,106 @@ __device__ inline double eval_sumsq(const Problem& P, const Xform& T, const Pose
 // lmpar is w^T (A + par D^2)^-1 w. They are evaluated here with LDL^T factorisations (no square roots, six
 // reciprocals) of the column-scaled matrix C = S A S, S = diag(1/|J_j|), which removes the mm-vs-quaternion scale
 // disparity of the columns before the squared condition number can hurt. Same iterates as lmpar/qrsolv up to rounding.
-__device__ inline double norm6(const double* v)
+__device__ __forceinline__ double norm6(const double* v)
 {
     double s = 0.0;
+#pragma unroll
     for (int i = 0; i < 6; ++i) s += v[i] * v[i];
     return sqrt(s);
 }
 
-// In: S.A, S.g. Out: S.wa2 (column norms of J), S.sc (1/norm), S.C (scaled A), pivoted LDL^T of C in S.L / S.dinv /
-// S.perm, S.rank.
+// Packed lower-triangular index; with fully unrolled loops every index is a compile-time constant, so the 6x6
+// working sets below live in registers (no local-memory round trips on the serial lane-0 path).
+#define RS_T(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+// In-place LDL^T of a packed symmetric positive definite 6x6: m(i,j), j < i, becomes l_ij; dinv = 1 / pivots.
+// Returns false when a pivot is not above `tiny`.
+__device__ __forceinline__ bool ldl6_packed(double m[21], double dinv[6], const double tiny)
+{
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double dk = m[RS_T(k, k)];
+        ok = ok && (dk > tiny);
+        const double inv = 1.0 / dk;
+        dinv[k] = inv;
+        double col[6];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) col[i] = m[RS_T(i, k)];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const double lik = col[i] * inv;
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) m[RS_T(i, j)] -= lik * col[j];
+            m[RS_T(i, k)] = lik;
+        }
+    }
+    return ok;
+}
+
+// z <- L^-1 z (unit lower factor, packed)
+__device__ __forceinline__ void forward6_packed(const double m[21], double z[6])
+{
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        double sum = z[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) sum -= m[RS_T(i, j)] * z[j];
+        z[i] = sum;
+    }
+}
+
+// solves (L D L^T) u = b in place
+__device__ __forceinline__ void solve6_packed(const double m[21], const double dinv[6], double z[6])
+{
+    forward6_packed(m, z);
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double sum = z[i] * dinv[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) sum -= m[RS_T(j, i)] * z[j];
+        z[i] = sum;
+    }
+}
+
+// In: S.A, S.g. Out: S.wa2 (column norms of J), S.sc (1/norm), S.C (scaled A) and its LDL^T: unpivoted in S.Lp / S.dinv
+// (S.fast = 1, the usual full-rank case) or, when a pivot collapses, diagonally pivoted in S.L / S.dinv / S.perm with
+// the detected S.rank.
 __device__ inline void factorize(WarpLM& S)
 {
-    for (int j = 0; j < 6; ++j) {
-        S.wa2[j] = sqrt(fmax(S.A[j * 6 + j], 0.0));
-        S.sc[j] = S.wa2[j] > 0.0 ? 1.0 / S.wa2[j] : 1.0;
-    }
-    for (int i = 0; i < 6; ++i)
+    {
+        double sc[6], m[21], dinv[6];
+#pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const double c = S.A[i * 6 + j] * S.sc[i] * S.sc[j];
-            S.C[i * 6 + j] = c;
-            S.L[i * 6 + j] = c;
+            const double n = sqrt(fmax(S.A[j * 6 + j], 0.0));
+            S.wa2[j] = n;
+            sc[j] = n > 0.0 ? 1.0 / n : 1.0;
+            S.sc[j] = sc[j];
         }
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const double c = S.A[i * 6 + j] * sc[i] * sc[j];
+                S.C[i * 6 + j] = c;
+                S.C[j * 6 + i] = c;
+                m[RS_T(i, j)] = c;
+            }
+        if (ldl6_packed(m, dinv, 64.0 * DBL_EPSILON)) {
+#pragma unroll
+            for (int i = 0; i < 21; ++i) S.Lp[i] = m[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                S.dinv[i] = dinv[i];
+                S.perm[i] = i;
+            }
+            S.rank = 6;
+            S.fast = 1;
+            return;
+        }
+    }
+    S.fast = 0;
+    for (int i = 0; i < 36; ++i) S.L[i] = S.C[i];
     double* M = S.L;
     for (int j = 0; j < 6; ++j) S.perm[j] = j;
     int rank = 6;
@@ -374,9 +454,21 @@ __device__ inline void lmpar(WarpLM& S)
     const double delta = S.delta;
     double* x = S.xs;
     double sg[6], u[6], wa2[6], w[6];
+#pragma unroll
     for (int j = 0; j < 6; ++j) sg[j] = S.sc[j] * S.g[j];
     // Gauss-Newton direction
-    solve_pivoted(S, sg, u);
+    if (S.fast) {
+        double m[21], dinv[6];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) m[i] = S.Lp[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dinv[i] = S.dinv[i], u[i] = sg[i];
+        solve6_packed(m, dinv, u);
+    }
+    else {
+        solve_pivoted(S, sg, u);
+    }
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         x[j] = S.sc[j] * u[j];
         wa2[j] = S.diag[j] * x[j];
@@ -389,8 +481,21 @@ __device__ inline void lmpar(WarpLM& S)
     }
     double parl = 0.0;
     if (S.rank == 6) {
+#pragma unroll
         for (int j = 0; j < 6; ++j) w[j] = S.sc[j] * (S.diag[j] * wa2[j] / dxnorm);
-        parl = fp / delta / quad_form_pivoted(S, w);
+        if (S.fast) {
+            double m[21];
+#pragma unroll
+            for (int i = 0; i < 21; ++i) m[i] = S.Lp[i];
+            forward6_packed(m, w);
+            double q = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) q += w[i] * w[i] * S.dinv[i];
+            parl = fp / delta / q;
+        }
+        else {
+            parl = fp / delta / quad_form_pivoted(S, w);
+        }
     }
     double gn = 0.0;
     for (int j = 0; j < 6; ++j) {
@@ -406,6 +511,7 @@ __device__ inline void lmpar(WarpLM& S)
     if (par == 0.0) par = gnorm / dxnorm;
 
     double e2[6];
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         const double e = S.diag[j] * S.sc[j];
         e2[j] = e * e;
@@ -414,34 +520,18 @@ __device__ inline void lmpar(WarpLM& S)
     while (true) {
         ++iter;
         if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-        // LDL^T of C + par E^2 (lower triangle, no pivoting: positive definite for par > 0)
-        double M[36], dinv[6];
+        // LDL^T of C + par E^2 (packed lower triangle, no pivoting: positive definite for par > 0)
+        double M[21], dinv[6], z[6];
+#pragma unroll
         for (int i = 0; i < 6; ++i) {
-            for (int j = 0; j < i; ++j) M[i * 6 + j] = S.C[i * 6 + j];
-            M[i * 6 + i] = S.C[i * 6 + i] + par * e2[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) M[RS_T(i, j)] = S.C[i * 6 + j];
+            M[RS_T(i, i)] = S.C[i * 6 + i] + par * e2[i];
+            z[i] = sg[i];
         }
-        for (int k = 0; k < 6; ++k) {
-            const double dk = 1.0 / M[k * 6 + k];
-            dinv[k] = dk;
-            double col[6];
-            for (int i = k + 1; i < 6; ++i) col[i] = M[i * 6 + k];
-            for (int i = k + 1; i < 6; ++i) {
-                const double lik = col[i] * dk;
-                for (int j = k + 1; j <= i; ++j) M[i * 6 + j] -= lik * col[j];
-                M[i * 6 + k] = lik;
-            }
-        }
-        double z[6];
-        for (int i = 0; i < 6; ++i) {
-            double sum = sg[i];
-            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
-            z[i] = sum;
-        }
-        for (int i = 5; i >= 0; --i) {
-            double sum = z[i] * dinv[i];
-            for (int j = i + 1; j < 6; ++j) sum -= M[j * 6 + i] * z[j];
-            z[i] = sum;
-        }
+        ldl6_packed(M, dinv, 0.0);
+        solve6_packed(M, dinv, z);
+#pragma unroll
         for (int j = 0; j < 6; ++j) {
             x[j] = S.sc[j] * z[j];
             wa2[j] = S.diag[j] * x[j];
@@ -452,12 +542,11 @@ __device__ inline void lmpar(WarpLM& S)
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
         // Newton correction: parc = fp / delta / (w^T (A + par D^2)^-1 w), w = D^2 x / |D x|
         double q = 0.0;
-        for (int i = 0; i < 6; ++i) {
-            double sum = S.sc[i] * (S.diag[i] * (wa2[i] / dxnorm));
-            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
-            z[i] = sum;
-            q += sum * sum * dinv[i];
-        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) z[i] = S.sc[i] * (S.diag[i] * (wa2[i] / dxnorm));
+        forward6_packed(M, z);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) q += z[i] * z[i] * dinv[i];
         const double parc = fp / delta / q;
         if (fp > 0.0) parl = fmax(parl, par);
         if (fp < 0.0) paru = fmin(paru, par);
@@ -1047,7 +1136,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
 
 // compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
 // grid (ceil(n_variance / WARPS), B), one warp per Monte-Carlo sample.
-__global__ void __launch_bounds__(THREADS) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
+__global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.y;

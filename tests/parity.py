@@ -84,10 +84,11 @@ def assert_frame_match(ref, got, b=0, rtol=1e-4):
     return fwd
 
 
-def pose_close(ref_pose, got_pose, rtol=1e-4):
-    """Pose parity (north_star): position within rtol of |t| (floor 1e-3 mm), quaternion sign-aligned."""
+def pose_close(ref_pose, got_pose, rtol=1e-4, qtol=1e-8):
+    """Pose parity (north_star): position within rtol of |t| (floor 1e-3 mm), quaternion sign-aligned
+    (|q.q_ref| >= 1 - qtol, i.e. 1e-8 <-> 2.8e-4 rad)."""
     ref_pose, got_pose = np.asarray(ref_pose), np.asarray(got_pose)
     tn = max(np.linalg.norm(ref_pose[:3]), 1.0)
     dt = np.linalg.norm(ref_pose[:3] - got_pose[:3])
     qd = abs(float(np.dot(ref_pose[3:], got_pose[3:])))
-    return dt <= max(rtol * tn, 1e-3) and qd >= 1 - 1e-8, dt, qd
+    return dt <= max(rtol * tn, 1e-3) and qd >= 1 - qtol, dt, qd

@@ -36,7 +36,7 @@ def assert_out_match(ref, got, ref_mask, got_mask, n, cov_rtol=2e-3, strict=True
     assert got["n_inliers"] == ref["n_inliers"]
     assert np.array_equal(got_mask[:n], ref_mask[:n])
     assert abs(got["score"] - ref["score"]) <= 1e-9
-    ok, dt, qd = parity.pose_close(ref["pose"], got["pose"], rtol=1e-4 if strict else 1e-2)
+    ok, dt, qd = parity.pose_close(ref["pose"], got["pose"], rtol=1e-4 if strict else 1e-2, qtol=1e-8 if strict else 1e-5)
     assert ok, "pose differs: |dt| = %g mm, |q.q_ref| = %r" % (dt, qd)
     if ref["status"] == 1 and ref["n_variance_ok"] > 0:
         assert got["n_variance_ok"] == ref["n_variance_ok"]
