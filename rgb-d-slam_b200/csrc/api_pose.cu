@@ -61,6 +61,7 @@ int create_impl(rs_pose_ctx* c)
     if ((rc = dev_alloc(&b.state, B))) return rc;
     if ((rc = dev_alloc(&b.out, B))) return rc;
     if ((rc = dev_alloc(&b.mask, B * M))) return rc;
+    if ((rc = dev_alloc(&b.inlier_idx, B * M))) return rc;
     if ((rc = dev_alloc(&b.poses, B * 7))) return rc;
     if ((rc = dev_alloc(&b.subsets_used, B * size_t(c->max_iterations) * RS_MAX_SUBSET))) return rc;
     if ((rc = dev_alloc(&b.v6, B * size_t(c->max_variance) * 6))) return rc;
@@ -289,6 +290,7 @@ void rs_pose_destroy(rs_pose_ctx* c)
     cudaFree(b.state);
     cudaFree(b.out);
     cudaFree(b.mask);
+    cudaFree(b.inlier_idx);
     cudaFree(b.poses);
     cudaFree(b.subsets_used);
     cudaFree(b.v6);

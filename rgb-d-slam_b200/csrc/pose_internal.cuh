@@ -18,6 +18,9 @@ struct PoseFrameState {
     int stage;            // 0 = failed before/inside RANSAC, 1 = final pose available (variance may run)
     double total_score;   // sum of get_score() in list order
     double final_x[6];    // LM coefficients of the final pose (start point of the Monte-Carlo solves)
+    int n_inliers;        // winning inlier set: size, residual count and score in list order (inputs of every Monte-Carlo solve)
+    int inlier_residuals;
+    double inlier_score;
 };
 
 // Device buffers of one pose context (SoA feature layout: component-major, stride = max_matches).
@@ -33,6 +36,7 @@ struct PoseBuffers {
     PoseFrameState* state;         // B
     rs_pose_out* out;              // B
     uint8_t* mask;                 // B x M
+    int16_t* inlier_idx;           // B x M : indices of the winning inlier set, ascending (written by the RANSAC kernel)
     double* poses;                 // B x 7 (the all-gather payload)
     const int32_t* subsets_in;     // B x max_iterations x RS_MAX_SUBSET (RS_RNG_REFERENCE), or null
     int32_t* subsets_used;         // B x max_iterations x RS_MAX_SUBSET

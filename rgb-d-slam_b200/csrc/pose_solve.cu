@@ -61,18 +61,17 @@ struct Xform {
 };
 
 struct WarpLM {
-    double x[6], xt[6], diag[6], p[6], wa2[6], sc[6], g[6], h[6], dinv[6], xs[6];
-    double A[36];  // J^T J
-    double C[36];  // column-scaled copy S A S
-    double L[36];  // pivoted LDL^T of C (unit lower factor below the diagonal); slow path only
-    double Lp[21]; // fast path: unpivoted LDL^T of C, packed lower triangle (unit factor below the diagonal)
-    Xform T[7];    // transforms at x (0) and x + h_j e_j (1..6); T[0] is reused for the trial point
+    double x[6], xt[6], diag[6], p[6], wa2[6], sc[6], g[6], xs[6];
+    double A[36];     // J^T J (full, symmetric)
+    double C[21];     // packed lower triangle of the column-scaled S A S
+    Xform T;          // transform at the point being evaluated (x, then the trial points)
+    double Rk[3][9];  // R'(x + h_k e_k) for the three rotation coefficients (scratch of the Jacobian set-up)
+    double dR[27];    // forward-difference derivative of R' along the three rotation coefficients
+    double ih[3];     // 1 / h_k of those differences
     double fnorm, par, delta, xnorm, gnorm, pnorm;
-    int perm[6];
-    int rank, status, nfev, iter, again, fast;
+    int status, nfev, iter, again;
 };
 
-// Features of one LM problem: indices into the frame arrays (idx == nullptr: identity), lane-strided.
 struct Problem {
     int n;
     const short* idx;
@@ -219,9 +218,15 @@ __device__ __forceinline__ int feature_residual(const int type, const double o[4
     return 3;
 }
 
-__device__ __forceinline__ double angle_distance(const double a, const double b)
+// distance_utils.cpp:6-9: atan2(sin(a - b), cos(a - b)). The arguments are components of unit normals, so |a - b| <= 2 < pi
+// and the expression is a - b up to a few ulp; the libm chain (three FP64 transcendentals per component) is only
+// evaluated when that could decide the comparison with the threshold.
+__device__ __noinline__ double angle_distance_exact(const double a, const double b) { return atan2(sin(a - b), cos(a - b)); }
+__device__ __forceinline__ bool angle_within(const double a, const double b, const double thr)
 {
-    return atan2(sin(a - b), cos(a - b));  // distance_utils.cpp:6-9
+    const double d = fabs(a - b);
+    if (fabs(d - thr) > 1e-9) return d <= thr;
+    return fabs(angle_distance_exact(a, b)) <= thr;
 }
 
 // IOptimizationFeature::is_inlier (map_point.cpp:34-38, map_primitive.cpp:33-49)
@@ -236,8 +241,8 @@ __device__ __forceinline__ bool feature_is_inlier(const int type, const double o
     }
     double np[3], dp;
     plane_to_camera(m[0], m[1], m[2], m[3], T, np, dp);
-    return fabs(angle_distance(o[0], np[0])) <= kPlaneInlierNormal && fabs(angle_distance(o[1], np[1])) <= kPlaneInlierNormal &&
-           fabs(angle_distance(o[2], np[2])) <= kPlaneInlierNormal && fabs(o[3] - dp) <= kPlaneInlierMm;
+    return angle_within(o[0], np[0], kPlaneInlierNormal) && angle_within(o[1], np[1], kPlaneInlierNormal) &&
+           angle_within(o[2], np[2], kPlaneInlierNormal) && fabs(o[3] - dp) <= kPlaneInlierMm;
 }
 
 __device__ __forceinline__ void load_feature(const Problem& P, const int k, int& type, double o[4], double m[4])
@@ -265,6 +270,114 @@ __device__ inline double eval_sumsq(const Problem& P, const Xform& T, const Pose
     return warp_sum(ss);
 }
 
+// ---- Jacobian -------------------------------------------------------------------------------------------------------
+// Eigen::NumericalDiff<F, Forward> differentiates the residual vector: column j = (f(x + h_j e_j) - f(x)) / h_j with
+// h_j = sqrt(eps) |x_j|. The residuals depend on x only through the transform (R', t'), t' is LINEAR in x0..x2 and R'
+// depends on x3..x5 only, so the same forward difference is taken here one level down - on the transform instead of on
+// every residual:  dR'_k = (R'(x + h_k e_k) - R'(x)) / h_k  (three 3x3 matrices per Jacobian, built once per iteration by
+// three lanes) - and carried to the residual rows by the chain rule per feature. The translation columns are exact; the
+// rotation columns differ from the reference's by its O(h) truncation term (1e-8 relative) which is two orders below
+// the rounding noise (1e-6 relative: residuals of ~100 px known to 1e-14, divided by h ~ 1e-8) that ANY evaluation order
+// of the reference's own difference quotient carries. Cost per point: one projection + ~60 FMA instead of seven
+// projections. nfev still counts the 7 evaluations NumericalDiff would have made, so stop code 5 fires at the same place.
+__device__ __forceinline__ void accumulate_row(const double (&J)[6], const double r, double (&a)[32])
+{
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        a[21 + i] += J[i] * r;
+#pragma unroll
+        for (int j = i; j < 6; ++j) a[t++] += J[i] * J[j];
+    }
+}
+
+// rows of one feature at S.T / S.dR, accumulated into a[0..20] (upper triangle of J^T J, row-major) and a[21..26] (J^T r)
+__device__ __forceinline__ void feature_jacobian(const int type, const double (&o)[4], const double (&m)[4], const Xform& T,
+                                                 const double* __restrict__ dR, const PoseIntrinsics& K, double (&a)[32])
+{
+    if (type == RS_FEAT_POINT) {
+        const double d0 = m[0] - T.t[0], d1 = m[1] - T.t[1], d2 = m[2] - T.t[2];
+        const double xc = (T.R[0] * d0 + T.R[3] * d1) + T.R[6] * d2;
+        const double yc = (T.R[1] * d0 + T.R[4] * d1) + T.R[7] * d2;
+        const double zc = (T.R[2] * d0 + T.R[5] * d1) + T.R[8] * d2;
+        const double inv = 1.0 / zc;
+        const double u = inv * (K.fx * xc + K.cx * zc);
+        const double v = inv * (K.fy * yc + K.cy * zc);
+        if (u != u || v != v) return;  // residual DBL_MAX at x and at every x + h: a zero row in the reference too
+        const double r0 = (o[0] - u) * 0.5, r1 = (o[1] - v) * 0.5;
+        // d r0 = A0 dxc + B0 dzc, d r1 = A1 dyc + B1 dzc
+        const double A0 = -0.5 * K.fx * inv, B0 = (0.5 * K.fx * xc) * (inv * inv);
+        const double A1 = -0.5 * K.fy * inv, B1 = (0.5 * K.fy * yc) * (inv * inv);
+        double J0[6], J1[6];
+        // x0 -> d1 += 1, x1 -> d2 += 1, x2 -> d0 -= 1  (t' = (x2, -x0, -x1))
+        J0[0] = A0 * T.R[3] + B0 * T.R[5], J1[0] = A1 * T.R[4] + B1 * T.R[5];
+        J0[1] = A0 * T.R[6] + B0 * T.R[8], J1[1] = A1 * T.R[7] + B1 * T.R[8];
+        J0[2] = -(A0 * T.R[0] + B0 * T.R[2]), J1[2] = -(A1 * T.R[1] + B1 * T.R[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double* D = dR + 9 * k;
+            const double dx = (D[0] * d0 + D[3] * d1) + D[6] * d2;
+            const double dy = (D[1] * d0 + D[4] * d1) + D[7] * d2;
+            const double dz = (D[2] * d0 + D[5] * d1) + D[8] * d2;
+            J0[3 + k] = A0 * dx + B0 * dz;
+            J1[3 + k] = A1 * dy + B1 * dz;
+        }
+        accumulate_row(J0, r0, a);
+        accumulate_row(J1, r1, a);
+        return;
+    }
+    // plane: r = (d_o n_o - d_p n_p) / 3, n_p = R'^T n / |R'^T n|, d_p = t'.n + d_w
+    const double v0 = (T.R[0] * m[0] + T.R[3] * m[1]) + T.R[6] * m[2];
+    const double v1 = (T.R[1] * m[0] + T.R[4] * m[1]) + T.R[7] * m[2];
+    const double v2 = (T.R[2] * m[0] + T.R[5] * m[1]) + T.R[8] * m[2];
+    const double z = (v0 * v0 + v1 * v1) + v2 * v2;
+    const double is = z > 0.0 ? 1.0 / sqrt(z) : 1.0;
+    const double np[3] = {v0 * is, v1 * is, v2 * is};
+    const double dp = ((T.t[0] * m[0] + T.t[1] * m[1]) + T.t[2] * m[2]) + m[3];
+    const double third = 1.0 / 3.0;
+    double J[3][6], r[3];
+    // d d_p / d x0 = -n1, / d x1 = -n2, / d x2 = +n0
+    const double c0 = m[1] * third, c1 = m[2] * third, c2 = -m[0] * third;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r[c] = (o[3] * o[c] - dp * np[c]) * third;
+        J[c][0] = c0 * np[c];
+        J[c][1] = c1 * np[c];
+        J[c][2] = c2 * np[c];
+    }
+    const double f = -dp * is * third;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double* D = dR + 9 * k;
+        const double w0 = (D[0] * m[0] + D[3] * m[1]) + D[6] * m[2];
+        const double w1 = (D[1] * m[0] + D[4] * m[1]) + D[7] * m[2];
+        const double w2 = (D[2] * m[0] + D[5] * m[1]) + D[8] * m[2];
+        const double along = (np[0] * w0 + np[1] * w1) + np[2] * w2;  // removed by the renormalisation
+        J[0][3 + k] = f * (w0 - along * np[0]);
+        J[1][3 + k] = f * (w1 - along * np[1]);
+        J[2][3 + k] = f * (w2 - along * np[2]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) accumulate_row(J[c], r[c], a);
+}
+
+// Sum over the warp of 32 per-lane values each, by recursive halving: after the five exchange levels lane L holds the
+// warp total of entry L in v[0] (31 exchanges instead of the 32 x 5 of a butterfly all-reduce).
+__device__ __forceinline__ double reduce_scatter32(double (&v)[32], const int lane)
+{
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, half);
+        }
+    }
+    return v[0];
+}
+
 // ---- lane-0 algebra on the shared 6x6 state ---------------------------------------------------------------------
 // MINPACK's lmder/lmpar work on the triangular factor R of J P = Q R and on Q^T r. Every quantity they need is a
 // function of A = J^T J = P R^T R P^T and g = J^T r = P R^T (Q^T r):   the Gauss-Newton step solves A x = g, the
@@ -281,12 +394,12 @@ __device__ __forceinline__ double norm6(const double* v)
 }
 
 // Packed lower-triangular index; with fully unrolled loops every index is a compile-time constant, so the 6x6
-// working sets below live in registers (no local-memory round trips on the serial lane-0 path).
+// working set below lives in registers (no local-memory round trips on the serial lane-0 path).
 #define RS_T(i, j) ((i) * ((i) + 1) / 2 + (j))
 
 // In-place LDL^T of a packed symmetric positive definite 6x6: m(i,j), j < i, becomes l_ij; dinv = 1 / pivots.
 // Returns false when a pivot is not above `tiny`.
-__device__ __forceinline__ bool ldl6_packed(double m[21], double dinv[6], const double tiny)
+__device__ __forceinline__ bool ldl6_packed(double (&m)[21], double (&dinv)[6], const double tiny)
 {
     bool ok = true;
 #pragma unroll
@@ -310,7 +423,7 @@ __device__ __forceinline__ bool ldl6_packed(double m[21], double dinv[6], const 
 }
 
 // z <- L^-1 z (unit lower factor, packed)
-__device__ __forceinline__ void forward6_packed(const double m[21], double z[6])
+__device__ __forceinline__ void forward6_packed(const double (&m)[21], double (&z)[6])
 {
 #pragma unroll
     for (int i = 1; i < 6; ++i) {
@@ -321,10 +434,9 @@ __device__ __forceinline__ void forward6_packed(const double m[21], double z[6])
     }
 }
 
-// solves (L D L^T) u = b in place
-__device__ __forceinline__ void solve6_packed(const double m[21], const double dinv[6], double z[6])
+// z <- L^-T D^-1 z
+__device__ __forceinline__ void backward6_packed(const double (&m)[21], const double (&dinv)[6], double (&z)[6])
 {
-    forward6_packed(m, z);
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double sum = z[i] * dinv[i];
@@ -334,168 +446,83 @@ __device__ __forceinline__ void solve6_packed(const double m[21], const double d
     }
 }
 
-// In: S.A, S.g. Out: S.wa2 (column norms of J), S.sc (1/norm), S.C (scaled A) and its LDL^T: unpivoted in S.Lp / S.dinv
-// (S.fast = 1, the usual full-rank case) or, when a pivot collapses, diagonally pivoted in S.L / S.dinv / S.perm with
-// the detected S.rank.
-__device__ inline void factorize(WarpLM& S)
+// Rank-deficient / ill-conditioned J (a pivot of the unpivoted factorisation collapsed): MINPACK's pivoted path.
+// Diagonally pivoted LDL^T of C gives the rank and the basic Gauss-Newton solution (zeros on the dependent columns);
+// parl = 0 when the rank is deficient. Rare (degenerate subsets, a frozen coordinate), so plain loops on local arrays.
+__device__ __noinline__ void lmpar_deficient(WarpLM& S)
 {
-    {
-        double sc[6], m[21], dinv[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const double n = sqrt(fmax(S.A[j * 6 + j], 0.0));
-            S.wa2[j] = n;
-            sc[j] = n > 0.0 ? 1.0 / n : 1.0;
-            S.sc[j] = sc[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                const double c = S.A[i * 6 + j] * sc[i] * sc[j];
-                S.C[i * 6 + j] = c;
-                S.C[j * 6 + i] = c;
-                m[RS_T(i, j)] = c;
-            }
-        if (ldl6_packed(m, dinv, 64.0 * DBL_EPSILON)) {
-#pragma unroll
-            for (int i = 0; i < 21; ++i) S.Lp[i] = m[i];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                S.dinv[i] = dinv[i];
-                S.perm[i] = i;
-            }
-            S.rank = 6;
-            S.fast = 1;
-            return;
-        }
+    const double dwarf = DBL_MIN, delta = S.delta;
+    double M[36], dinv[6], sg[6], e2[6], z[6], x[6], wa2[6];
+    int perm[6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) M[i * 6 + j] = M[j * 6 + i] = S.C[RS_T(i, j)];
+    for (int j = 0; j < 6; ++j) {
+        perm[j] = j;
+        sg[j] = S.sc[j] * S.g[j];
+        const double e = S.diag[j] * S.sc[j];
+        e2[j] = e * e;
     }
-    S.fast = 0;
-    for (int i = 0; i < 36; ++i) S.L[i] = S.C[i];
-    double* M = S.L;
-    for (int j = 0; j < 6; ++j) S.perm[j] = j;
     int rank = 6;
     for (int k = 0; k < 6; ++k) {
         int piv = k;
         double best = M[k * 6 + k];
         for (int i = k + 1; i < 6; ++i)
-            if (M[i * 6 + i] > best) {
-                best = M[i * 6 + i];
-                piv = i;
-            }
+            if (M[i * 6 + i] > best) best = M[i * 6 + i], piv = i;
         if (piv != k) {
             for (int j = 0; j < 6; ++j) {
                 const double t = M[k * 6 + j];
-                M[k * 6 + j] = M[piv * 6 + j];
-                M[piv * 6 + j] = t;
+                M[k * 6 + j] = M[piv * 6 + j], M[piv * 6 + j] = t;
             }
             for (int i = 0; i < 6; ++i) {
                 const double t = M[i * 6 + k];
-                M[i * 6 + k] = M[i * 6 + piv];
-                M[i * 6 + piv] = t;
+                M[i * 6 + k] = M[i * 6 + piv], M[i * 6 + piv] = t;
             }
-            const int t = S.perm[k];
-            S.perm[k] = S.perm[piv];
-            S.perm[piv] = t;
+            const int t = perm[k];
+            perm[k] = perm[piv], perm[piv] = t;
         }
         // C has a unit diagonal: a pivot at rounding level means a column that depends on the previous ones
         if (!(best > 64.0 * DBL_EPSILON)) {
             rank = k;
             break;
         }
-        const double dinv = 1.0 / best;
-        S.dinv[k] = dinv;
-        double col[6];
-        for (int i = k + 1; i < 6; ++i) col[i] = M[i * 6 + k];
+        dinv[k] = 1.0 / best;
         for (int i = k + 1; i < 6; ++i) {
-            const double lik = col[i] * dinv;
-            for (int j = k + 1; j < 6; ++j) M[i * 6 + j] -= lik * col[j];
-            M[i * 6 + k] = lik;
+            const double lik = M[i * 6 + k] * dinv[k];
+            for (int j = k + 1; j <= i; ++j) M[i * 6 + j] -= lik * M[j * 6 + k];
         }
+        for (int i = k + 1; i < 6; ++i) M[i * 6 + k] *= dinv[k];
     }
-    S.rank = rank;
-}
-
-// quadratic form v^T C^-1 v through the pivoted factorisation (full rank only); v in original ordering
-__device__ inline double quad_form_pivoted(const WarpLM& S, const double* v)
-{
-    double z[6], q = 0.0;
-    for (int i = 0; i < 6; ++i) {
-        double sum = v[S.perm[i]];
-        for (int j = 0; j < i; ++j) sum -= S.L[i * 6 + j] * z[j];
-        z[i] = sum;
-        q += sum * sum * S.dinv[i];
-    }
-    return q;
-}
-
-// basic solution of C u = b on the leading `rank` pivots (zeros elsewhere), returned in original ordering
-__device__ inline void solve_pivoted(const WarpLM& S, const double* b, double* u)
-{
-    double z[6];
-    const int r = S.rank;
-    for (int i = 0; i < r; ++i) {
-        double sum = b[S.perm[i]];
-        for (int j = 0; j < i; ++j) sum -= S.L[i * 6 + j] * z[j];
+    // basic solution on the leading `rank` pivots
+    for (int i = 0; i < rank; ++i) {
+        double sum = sg[perm[i]];
+        for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
         z[i] = sum;
     }
-    for (int i = r - 1; i >= 0; --i) {
-        double sum = z[i] * S.dinv[i];
-        for (int j = i + 1; j < r; ++j) sum -= S.L[j * 6 + i] * z[j];
+    for (int i = rank - 1; i >= 0; --i) {
+        double sum = z[i] * dinv[i];
+        for (int j = i + 1; j < rank; ++j) sum -= M[j * 6 + i] * z[j];
         z[i] = sum;
     }
-    for (int i = 0; i < 6; ++i) u[S.perm[i]] = i < r ? z[i] : 0.0;
-}
-
-// unsupported/Eigen/src/NonLinearOptimization/lmpar.h (lmpar2): trust-region parameter S.par and step S.xs
-__device__ inline void lmpar(WarpLM& S)
-{
-    const double dwarf = DBL_MIN;
-    const double delta = S.delta;
-    double* x = S.xs;
-    double sg[6], u[6], wa2[6], w[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) sg[j] = S.sc[j] * S.g[j];
-    // Gauss-Newton direction
-    if (S.fast) {
-        double m[21], dinv[6];
-#pragma unroll
-        for (int i = 0; i < 21; ++i) m[i] = S.Lp[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) dinv[i] = S.dinv[i], u[i] = sg[i];
-        solve6_packed(m, dinv, u);
-    }
-    else {
-        solve_pivoted(S, sg, u);
-    }
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        x[j] = S.sc[j] * u[j];
-        wa2[j] = S.diag[j] * x[j];
-    }
+    for (int i = 0; i < 6; ++i) x[perm[i]] = i < rank ? S.sc[perm[i]] * z[i] : 0.0;
+    for (int j = 0; j < 6; ++j) wa2[j] = S.diag[j] * x[j];
     double dxnorm = norm6(wa2);
     double fp = dxnorm - delta;
     if (fp <= 0.1 * delta) {
         S.par = 0.0;
+        for (int j = 0; j < 6; ++j) S.xs[j] = x[j];
         return;
     }
     double parl = 0.0;
-    if (S.rank == 6) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) w[j] = S.sc[j] * (S.diag[j] * wa2[j] / dxnorm);
-        if (S.fast) {
-            double m[21];
-#pragma unroll
-            for (int i = 0; i < 21; ++i) m[i] = S.Lp[i];
-            forward6_packed(m, w);
-            double q = 0.0;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) q += w[i] * w[i] * S.dinv[i];
-            parl = fp / delta / q;
+    if (rank == 6) {
+        double q = 0.0;
+        for (int i = 0; i < 6; ++i) {
+            const int pi = perm[i];
+            double sum = S.sc[pi] * (S.diag[pi] * wa2[pi] / dxnorm);
+            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
+            z[i] = sum;
+            q += sum * sum * dinv[i];
         }
-        else {
-            parl = fp / delta / quad_form_pivoted(S, w);
-        }
+        parl = fp / delta / q;
     }
     double gn = 0.0;
     for (int j = 0; j < 6; ++j) {
@@ -505,33 +532,33 @@ __device__ inline void lmpar(WarpLM& S)
     const double gnorm = sqrt(gn);
     double paru = gnorm / delta;
     if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
-    double par = S.par;
-    par = fmax(par, parl);
-    par = fmin(par, paru);
+    double par = fmin(fmax(S.par, parl), paru);
     if (par == 0.0) par = gnorm / dxnorm;
-
-    double e2[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        const double e = S.diag[j] * S.sc[j];
-        e2[j] = e * e;
-    }
-    int iter = 0;
-    while (true) {
-        ++iter;
+    for (int iter = 1;; ++iter) {
         if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-        // LDL^T of C + par E^2 (packed lower triangle, no pivoting: positive definite for par > 0)
-        double M[21], dinv[6], z[6];
-#pragma unroll
+        // unpivoted LDL^T of C + par E^2 (positive definite for par > 0)
         for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int j = 0; j < i; ++j) M[RS_T(i, j)] = S.C[i * 6 + j];
-            M[RS_T(i, i)] = S.C[i * 6 + i] + par * e2[i];
-            z[i] = sg[i];
+            for (int j = 0; j < i; ++j) M[i * 6 + j] = S.C[RS_T(i, j)];
+            M[i * 6 + i] = S.C[RS_T(i, i)] + par * e2[i];
         }
-        ldl6_packed(M, dinv, 0.0);
-        solve6_packed(M, dinv, z);
-#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            dinv[k] = 1.0 / M[k * 6 + k];
+            for (int i = k + 1; i < 6; ++i) {
+                const double lik = M[i * 6 + k] * dinv[k];
+                for (int j = k + 1; j <= i; ++j) M[i * 6 + j] -= lik * M[j * 6 + k];
+            }
+            for (int i = k + 1; i < 6; ++i) M[i * 6 + k] *= dinv[k];
+        }
+        for (int i = 0; i < 6; ++i) {
+            double sum = sg[i];
+            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
+            z[i] = sum;
+        }
+        for (int i = 5; i >= 0; --i) {
+            double sum = z[i] * dinv[i];
+            for (int j = i + 1; j < 6; ++j) sum -= M[j * 6 + i] * z[j];
+            z[i] = sum;
+        }
         for (int j = 0; j < 6; ++j) {
             x[j] = S.sc[j] * z[j];
             wa2[j] = S.diag[j] * x[j];
@@ -540,31 +567,117 @@ __device__ inline void lmpar(WarpLM& S)
         const double temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-        // Newton correction: parc = fp / delta / (w^T (A + par D^2)^-1 w), w = D^2 x / |D x|
         double q = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) z[i] = S.sc[i] * (S.diag[i] * (wa2[i] / dxnorm));
-        forward6_packed(M, z);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) q += z[i] * z[i] * dinv[i];
+        for (int i = 0; i < 6; ++i) {
+            double sum = S.sc[i] * (S.diag[i] * (wa2[i] / dxnorm));
+            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
+            z[i] = sum;
+            q += sum * sum * dinv[i];
+        }
         const double parc = fp / delta / q;
         if (fp > 0.0) parl = fmax(parl, par);
         if (fp < 0.0) paru = fmin(paru, par);
         par = fmax(parl, par + parc);
     }
     S.par = par;
+    for (int j = 0; j < 6; ++j) S.xs[j] = x[j];
+}
+
+// unsupported/Eigen/src/NonLinearOptimization/lmpar.h (lmpar2): trust-region parameter S.par and step S.xs.
+// One factorise-and-solve body serves the Gauss-Newton step (pass 0, par = 0) and the damped steps (passes 1..10).
+__device__ __forceinline__ void lmpar(WarpLM& S)
+{
+    const double dwarf = DBL_MIN;
+    const double delta = S.delta;
+    double sg[6], e2[6], x[6], wa2[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        sg[j] = S.sc[j] * S.g[j];
+        const double e = S.diag[j] * S.sc[j];
+        e2[j] = e * e;
+    }
+    double par = 0.0, parl = 0.0, paru = 0.0, fp = 0.0;
+    int iter = 0;
+#pragma unroll 1
+    while (true) {
+        double M[21], dinv[6], z[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) M[RS_T(i, j)] = S.C[RS_T(i, j)];
+            M[RS_T(i, i)] = S.C[RS_T(i, i)] + par * e2[i];
+            z[i] = sg[i];
+        }
+        const bool ok = ldl6_packed(M, dinv, 64.0 * DBL_EPSILON);
+        if (iter == 0 && !ok) {
+            lmpar_deficient(S);
+            return;
+        }
+        forward6_packed(M, z);
+        backward6_packed(M, dinv, z);
+        double dx2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            x[j] = S.sc[j] * z[j];
+            wa2[j] = S.diag[j] * x[j];
+            dx2 += wa2[j] * wa2[j];
+        }
+        const double dxnorm = sqrt(dx2);
+        const double temp = fp;
+        fp = dxnorm - delta;
+        if (iter == 0) {
+            if (fp <= 0.1 * delta) break;  // the Gauss-Newton step is inside the trust region: par = 0
+        }
+        else if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10)
+            break;
+        // Newton correction fp / delta / (w^T (C + par E^2)^-1 w), w = S D^2 x / |D x| (at par = 0 this is parl)
+        double q = 0.0;
+        const double idx = 1.0 / dxnorm;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) z[i] = S.sc[i] * (S.diag[i] * (wa2[i] * idx));
+        forward6_packed(M, z);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) q += z[i] * z[i] * dinv[i];
+        const double parc = fp / delta / q;
+        if (iter == 0) {
+            parl = parc;
+            double gn = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double t = S.g[j] / S.diag[j];
+                gn += t * t;
+            }
+            const double gnorm = sqrt(gn);
+            paru = gnorm / delta;
+            if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
+            par = fmin(fmax(S.par, parl), paru);
+            if (par == 0.0) par = gnorm / dxnorm;
+        }
+        else {
+            if (fp > 0.0) parl = fmax(parl, par);
+            if (fp < 0.0) paru = fmin(paru, par);
+            par = fmax(parl, par + parc);
+        }
+        if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
+        ++iter;
+    }
+    S.par = par;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) S.xs[j] = x[j];
 }
 
 // Eigen::LevenbergMarquardt<NumericalDiff<F,Forward>>::minimize on S.x (in/out). Whole warp must call; returns the
-// Eigen status (<= 0 failure, 1..8 MINPACK info). m = residual count of the problem.
-__device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m, const int maxfev,
-                                const int lane)
+// Eigen status (<= 0 failure, 1..8 MINPACK info). m = residual count of the problem. One copy per kernel (noinline):
+// the body is ~3k instructions and the serial lane-0 chains are latency bound, so instruction-cache residency matters
+// more than call overhead.
+__device__ __noinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m,
+                                             const int maxfev, const int lane)
 {
     if (m < 6 || maxfev <= 0) return 0;  // ImproperInputParameters
-    if (lane == 0) make_xform(S.x, S.T[0]);
+    if (lane == 0) make_xform(S.x, S.T);
     __syncwarp();
     {
-        const double ss = eval_sumsq(P, S.T[0], K, lane);
+        const double ss = eval_sumsq(P, S.T, K, lane);
         if (lane == 0) {
             S.fnorm = sqrt(ss);
             S.par = 0.0, S.delta = 0.0, S.xnorm = 0.0;
@@ -573,72 +686,76 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
     }
     __syncwarp();
 
+#pragma unroll 1
     while (true) {
-        // ---- forward-difference Jacobian (NumericalDiff::df): h_j = sqrt(eps) |x_j|, or sqrt(eps) when x_j == 0 ----
-        if (lane < 7) {
+        // ---- Jacobian set-up: R'(x) on lane 0, R'(x + h_k e_k) on lanes 1..3, then the 27 difference quotients ----
+        if (lane < 4) {
             double xx[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) xx[j] = S.x[j];
-            if (lane > 0) {
-                double h = kSqrtEps * fabs(xx[lane - 1]);
-                if (h == 0.0) h = kSqrtEps;
-                xx[lane - 1] += h;
-                S.h[lane - 1] = 1.0 / h;  // the difference quotient's rounding is far below the forward-difference error
+            double h = 0.0;
+#pragma unroll
+            for (int j = 3; j < 6; ++j)
+                if (lane == j - 2) {
+                    h = kSqrtEps * fabs(xx[j]);  // NumericalDiff: h = sqrt(eps) |x_j|, or sqrt(eps) when x_j == 0
+                    if (h == 0.0) h = kSqrtEps;
+                    xx[j] += h;
+                }
+            Xform Tk;
+            make_xform(xx, Tk);
+            if (lane == 0)
+                S.T = Tk;
+            else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) S.Rk[lane - 1][i] = Tk.R[i];
+                S.ih[lane - 1] = 1.0 / h;
             }
-            make_xform(xx, S.T[lane]);
         }
         __syncwarp();
-        double a[21], g[6];
+        if (lane < 27) {
+            const int k = lane / 9, i = lane - 9 * k;
+            S.dR[lane] = (S.Rk[k][i] - S.T.R[i]) * S.ih[k];
+        }
+        __syncwarp();
+        double a[32];
 #pragma unroll
-        for (int i = 0; i < 21; ++i) a[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) g[i] = 0.0;
-        double ih[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) ih[j] = S.h[j];
+        for (int i = 0; i < 32; ++i) a[i] = 0.0;
+#pragma unroll 1
         for (int k = lane; k < P.n; k += 32) {
             int type;
-            double o[4], mm[4], r[3], rj[3], J[3][6];
+            double o[4], mm[4];
             load_feature(P, k, type, o, mm);
-            const int cnt = feature_residual(type, o, mm, S.T[0], K, r);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                feature_residual(type, o, mm, S.T[j + 1], K, rj);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) J[c][j] = (rj[c] - r[c]) * ih[j];
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (c < cnt) {
-                    int t = 0;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        g[i] += J[c][i] * r[c];
-#pragma unroll
-                        for (int j = i; j < 6; ++j) a[t++] += J[c][i] * J[c][j];
-                    }
-                }
-            }
+            feature_jacobian(type, o, mm, S.T, S.dR, K, a);
         }
-#pragma unroll
-        for (int i = 0; i < 21; ++i) a[i] = warp_sum(a[i]);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) g[i] = warp_sum(g[i]);
+        const double mine = reduce_scatter32(a, lane);
+        if (lane < 21) {
+            int i = 0, rem = lane;
+            while (rem >= 6 - i) rem -= 6 - i, ++i;
+            const int j = i + rem;
+            S.A[i * 6 + j] = mine;
+            S.A[j * 6 + i] = mine;
+        }
+        else if (lane < 27)
+            S.g[lane - 21] = mine;
+        __syncwarp();
 
         if (lane == 0) {
             S.nfev += 7;  // NumericalDiff re-evaluates f(x) and then one evaluation per column
-            int t = 0;
-            for (int i = 0; i < 6; ++i) {
-                S.g[i] = g[i];
-                for (int j = i; j < 6; ++j) {
-                    S.A[i * 6 + j] = a[t];
-                    S.A[j * 6 + i] = a[t];
-                    ++t;
-                }
+            double sc[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double n = sqrt(fmax(S.A[j * 6 + j], 0.0));
+                S.wa2[j] = n;
+                sc[j] = n > 0.0 ? 1.0 / n : 1.0;
+                S.sc[j] = sc[j];
             }
-            factorize(S);
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) S.C[RS_T(i, j)] = S.A[i * 6 + j] * sc[i] * sc[j];
             if (S.iter == 1) {
                 double tt[6];
+#pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     S.diag[j] = (S.wa2[j] == 0.0) ? 1.0 : S.wa2[j];
                     tt[j] = S.diag[j] * S.x[j];
@@ -649,21 +766,27 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
             }
             // gnorm = max_j |J_j . r| / (|J_j| |r|)
             double gnorm = 0.0;
-            if (S.fnorm != 0.0)
+            if (S.fnorm != 0.0) {
+                const double ifn = 1.0 / S.fnorm;
+#pragma unroll
                 for (int j = 0; j < 6; ++j)
-                    if (S.wa2[j] != 0.0) gnorm = fmax(gnorm, fabs((S.g[j] / S.fnorm) * S.sc[j]));
+                    if (S.wa2[j] != 0.0) gnorm = fmax(gnorm, fabs((S.g[j] * ifn) * sc[j]));
+            }
             S.gnorm = gnorm;
             if (gnorm <= 0.0) S.status = 4;  // CosinusTooSmall (gtol = 0)
+#pragma unroll
             for (int j = 0; j < 6; ++j) S.diag[j] = fmax(S.diag[j], S.wa2[j]);
         }
         __syncwarp();
         if (S.status != kRunning) break;
 
         // ---- inner loop: trust-region step until the ratio is acceptable ----
+#pragma unroll 1
         while (true) {
             if (lane == 0) {
                 lmpar(S);
                 double tt[6];
+#pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     S.p[j] = -S.xs[j];
                     S.xt[j] = S.x[j] + S.p[j];
@@ -671,10 +794,10 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
                 }
                 S.pnorm = norm6(tt);
                 if (S.iter == 1) S.delta = fmin(S.delta, S.pnorm);
-                make_xform(S.xt, S.T[0]);
+                make_xform(S.xt, S.T);
             }
             __syncwarp();
-            const double ss1 = eval_sumsq(P, S.T[0], K, lane);
+            const double ss1 = eval_sumsq(P, S.T, K, lane);
             if (lane == 0) {
                 ++S.nfev;
                 const double fnorm = S.fnorm, fnorm1 = sqrt(ss1), pnorm = S.pnorm;
@@ -683,8 +806,10 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
                 if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 * inv_fnorm) * (fnorm1 * inv_fnorm);
                 // |J p|^2 = p^T A p
                 double pAp = 0.0;
+#pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     double sum = 0.0;
+#pragma unroll
                     for (int j = 0; j < 6; ++j) sum += S.A[i * 6 + j] * S.p[j];
                     pAp += sum * S.p[i];
                 }
@@ -708,6 +833,7 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
                 }
                 if (ratio >= 1e-4) {
                     double tt[6];
+#pragma unroll
                     for (int j = 0; j < 6; ++j) {
                         S.x[j] = S.xt[j];
                         tt[j] = S.diag[j] * S.x[j];
@@ -747,8 +873,8 @@ __device__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsic
 
 // compute_optimized_global_pose (pose_optimization.cpp:302-359) for the whole warp. x0 -> S.x; returns success and
 // leaves the optimised coefficients in S.x.
-__device__ bool optimize_pose_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const double* x0, const int m,
-                                   const double score, const int maxfev, const int lane)
+__device__ __forceinline__ bool optimize_pose_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const double* x0,
+                                                   const int m, const double score, const int maxfev, const int lane)
 {
     bool finite = true;
 #pragma unroll
@@ -759,12 +885,12 @@ __device__ bool optimize_pose_warp(WarpLM& S, const Problem& P, const PoseIntrin
     __syncwarp();
     const int status = lm_minimize_warp(S, P, K, m, maxfev, lane);
     if (status <= 0) return false;
-    double v6[6];
-    pose_vector6(S.x, v6);
+    // the reference rejects a pose whose [position, Euler angles] vector has a NaN: that vector is finite exactly
+    // when the coefficients and the quaternion built from them are
     bool ok = true;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) ok = ok && !(v6[j] != v6[j]);
-    return ok;
+    for (int j = 0; j < 6; ++j) ok = ok && isfinite(S.x[j]);
+    return ok && isfinite(S.x[3] * S.x[3] + S.x[4] * S.x[4] + S.x[5] * S.x[5]);
 }
 
 // ---- counter-based generator of the RS_RNG_DEVICE mode --------------------------------------------------------------
@@ -779,7 +905,10 @@ __device__ inline uint64_t rng_key(const uint32_t seed, const uint32_t domain, c
 {
     return mix64((uint64_t(seed) << 32) ^ (uint64_t(domain) << 24) ^ frame);
 }
-// four standard normals for (frame, sample, feature): two Box-Muller pairs
+// Four standard normals for (frame, sample, feature): two Box-Muller pairs, each from one 64-bit counter hash. The pair
+// is evaluated in FP32 with the MUFU intrinsics (24-bit uniforms, |g| <= 5.8) and widened: a Monte-Carlo perturbation
+// needs the distribution, not 53 bits, and the FP64 log / sqrt / sincospi chain was 10 % of the variance kernel.
+// pose_export_normals_kernel returns exactly these values, which is how the oracle is fed the same draws.
 __device__ inline void device_normals(const uint32_t seed, const int frame, const int sample, const int feature,
                                       double g[4])
 {
@@ -788,14 +917,13 @@ __device__ inline void device_normals(const uint32_t seed, const int frame, cons
 #pragma unroll
     for (int pair = 0; pair < 2; ++pair) {
         const uint64_t a = mix64(key ^ mix64(ctr + uint64_t(pair)));
-        const uint64_t b = mix64(a ^ 0xd1342543de82ef95ull);
-        const double u1 = (double(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
-        const double u2 = double(b >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
-        const double rad = sqrt(-2.0 * log(u1));
-        double sn, cs;
-        sincospi(2.0 * u2, &sn, &cs);
-        g[2 * pair] = rad * cs;
-        g[2 * pair + 1] = rad * sn;
+        const float u1 = (float(uint32_t(a >> 40)) + 1.0f) * 5.9604644775390625e-08f;        // (0, 1]
+        const float u2 = float(uint32_t(a >> 8) & 0xffffffu) * 5.9604644775390625e-08f;     // [0, 1)
+        const float rad = sqrtf(-2.0f * __logf(u1));
+        float sn, cs;
+        __sincosf(6.2831853071795865f * u2, &sn, &cs);
+        g[2 * pair] = double(rad * cs);
+        g[2 * pair + 1] = double(rad * sn);
     }
 }
 
@@ -1020,7 +1148,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
             double score = 0.0;
             if (ok) {
                 // ---- get_features_inliers_outliers (pose_optimization.cpp:33-72) over all features ----
-                if (lane == 0) make_xform(S.x, S.T[0]);
+                if (lane == 0) make_xform(S.x, S.T);
                 __syncwarp();
                 for (int w = 0; w < words; ++w) {
                     const int i = w * 32 + lane;
@@ -1029,7 +1157,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                         double o[4], mm[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) o[c] = sm.obs[c * M + i], mm[c] = sm.map[c * M + i];
-                        in = feature_is_inlier(sm.type[i], o, mm, S.T[0], prm.K);
+                        in = feature_is_inlier(sm.type[i], o, mm, S.T, prm.K);
                     }
                     const unsigned bits = __ballot_sync(FULL, in);
                     if (lane == 0) hmask[w] = bits;
@@ -1131,7 +1259,11 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
         PoseFrameState* stp = buf.state + b;
         stp->stage = 1;
         for (int j = 0; j < 6; ++j) stp->final_x[j] = S.x[j];
+        stp->n_inliers = nInl;
+        stp->inlier_residuals = m;
+        stp->inlier_score = inlierScore;
     }
+    for (int k = lane; k < nInl; k += 32) buf.inlier_idx[size_t(b) * M + k] = sm.inlier_idx[k];
 }
 
 // compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
@@ -1151,31 +1283,16 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
     WarpLM* s_lm = reinterpret_cast<WarpLM*>(s_pmap + size_t(WARPS) * 4 * M);
     int32_t* s_type = reinterpret_cast<int32_t*>(s_lm + WARPS);
     short* s_idx = reinterpret_cast<short*>(s_type + M);
-    __shared__ int s_cnt, s_m;
-    __shared__ double s_score;
-
+    const int cnt = st.n_inliers;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         s_type[i] = buf.type[size_t(b) * M + i];
+        if (i < cnt) s_idx[i] = buf.inlier_idx[size_t(b) * M + i];
 #pragma unroll
         for (int c = 0; c < 4; ++c) s_obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int cnt = 0, m = 0;
-        double score = 0.0;
-        for (int i = 0; i < n; ++i)
-            if (buf.mask[size_t(b) * M + i]) {
-                s_idx[cnt++] = short(i);
-                const bool pt = s_type[i] == RS_FEAT_POINT;
-                score += pt ? kPointScore : kPlaneScore;
-                m += pt ? 2 : 3;
-            }
-        s_cnt = cnt, s_m = m, s_score = score;
-    }
-    __syncthreads();
     const int sample = blockIdx.x * WARPS + warp;
     if (sample >= prm.n_variance) return;
-    const int cnt = s_cnt;
     double* pmap = s_pmap + size_t(warp) * 4 * M;
     const double* gmap = buf.map + size_t(b) * 4 * M;
     const double* gsig = buf.sigma + size_t(b) * 4 * M;
@@ -1214,7 +1331,7 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
     double x0[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) x0[j] = st.final_x[j];
-    const bool ok = optimize_pose_warp(S, P, prm.K, x0, s_m, s_score, prm.lm_max_fev, lane);
+    const bool ok = optimize_pose_warp(S, P, prm.K, x0, st.inlier_residuals, st.inlier_score, prm.lm_max_fev, lane);
     if (lane == 0) {
         double v[6] = {0, 0, 0, 0, 0, 0};
         if (ok) pose_vector6(S.x, v);
