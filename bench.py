@@ -187,9 +187,17 @@ def main():
             self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3}
     poses_view = torch.as_tensor(_DevPtr(solver.device_poses_ptr(), (F, 7)), device="cuda")
 
+    pose_stream = torch.cuda.Stream()
+    pptr = pose_stream.cuda_stream
+
     def step():
+        # CAPE and the pose solve of a frame are independent (the reference runs find_primitives on its own thread):
+        # K1 (HBM bound) runs alone, then the latency-bound segmentation (main stream) and RANSAC / LM (pose stream)
+        # share the SMs; the main stream joins the pose stream before the collective / the next step.
         det.run_device(d_depth.data_ptr(), F, seed=0, stream=sptr)
-        solver.solve_device(F, opts, stream=sptr)
+        det.stream_wait_fit(pptr)
+        solver.solve_device(F, opts, stream=pptr)
+        stream.wait_stream(pose_stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), poses_view.view(-1))
 
@@ -308,7 +316,8 @@ def main():
                             "100-sample covariance (BASELINE configs[2]), batch of %d frames per GPU per step (configs[3] batch)" % F,
                 "frames_per_gpu": F, "cell_px": CELL, "cells_per_frame": N_CELLS, "ransac_hypotheses": 119, "n_variance": 100,
                 "l2": "inputs larger than L2 (%.0f MB of depth per step per GPU vs 126 MB)" % (depth.nbytes / 1e6),
-                "rng": "RS_RNG_DEVICE (counter-based on-device draws)", "collective": "all-gather of [frames x 7] f64 poses" if world > 1 else "none",
+                "rng": "RS_RNG_DEVICE (counter-based on-device draws)",
+                "streams": "K1 alone, then cape_segment (main stream) beside pose_prepare/ransac/variance/covariance (pose stream); kernels_ms_per_step are per-kernel event times and overlap", "collective": "all-gather of [frames x 7] f64 poses" if world > 1 else "none",
             },
             "roofline": {"kernel": "cape_cell_fit (K1)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -136,6 +136,12 @@ int rs_cape_run_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, uint
  * cells_dev = B x Ncells records in device memory. Asynchronous. */
 int rs_cape_cell_fit_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, rs_cell_out* cells_dev, void* stream);
 
+/* Makes `stream` wait until the most recent plane-fit kernel (K1) launched through this context has finished.
+ * The reference runs find_primitives on its own std::async thread beside the rest of the frame (rgbd_slam.cpp:288-300);
+ * the device-side equivalent is a second stream: the HBM-bound K1 gets the GPU to itself and the latency-bound kernels
+ * (cell-graph segmentation here, RANSAC in the pose context) then share the SMs. */
+int rs_cape_stream_wait_fit(rs_cape_ctx* ctx, void* stream);
+
 /* Device scratch owned by the context, for callers that keep data resident (bench, multi-frame pipelines). */
 float* rs_cape_device_depth(rs_cape_ctx* ctx);                  /* max_batch x H x W                 */
 const rs_cape_outputs* rs_cape_device_outputs(rs_cape_ctx* ctx); /* device pointers, max_batch frames */

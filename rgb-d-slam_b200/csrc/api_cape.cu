@@ -86,6 +86,7 @@ struct rs_cape_ctx {
     int tmap_batch = 0;
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
+    cudaEvent_t fit_done = nullptr;   // recorded after every K1 launch (rs_cape_stream_wait_fit)
     std::vector<cudaEvent_t> events;  // 3 per timing slot
     int timing_slots = 0;
     uint64_t run_counter = 0;
@@ -191,6 +192,7 @@ int create_impl(rs_cape_ctx* c)
     c->n_uniforms = 3 * RS_CYL_RANSAC_ITERS * RS_MAX_CYL_REGIONS * RS_MAX_CYL_SEGS;
     if ((rc = dev_alloc(&c->d_uniforms, size_t(c->n_uniforms)))) return rc;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->fit_done, cudaEventDisableTiming));
 
     const unsigned P = unsigned(c->cell) * unsigned(c->cell);
     c->fit.H = c->H, c->fit.hc = c->hc, c->fit.vc = c->vc, c->fit.cell = c->cell;
@@ -222,6 +224,7 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     ++c->run_counter;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], stream));
     if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream)) != RS_OK) return rc;
+    RS_CUDA_CHECK(cudaEventRecord(c->fit_done, stream));
     if (ev) {
         RS_CUDA_CHECK(cudaEventRecord(ev[1], stream));
         if (cells_only) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
@@ -294,6 +297,7 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_out.info);
     cudaFree(c->d_uniforms);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    if (c->fit_done) cudaEventDestroy(c->fit_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -323,6 +327,16 @@ int rs_cape_kernel_ms(rs_cape_ctx* c, int slot, float ms[2])
     RS_CUDA_CHECK(cudaEventSynchronize(ev[2]));
     RS_CUDA_CHECK(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
     RS_CUDA_CHECK(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));
+    return RS_OK;
+}
+
+int rs_cape_stream_wait_fit(rs_cape_ctx* c, void* stream)
+{
+    if (!c) {
+        set_last_error("rs_cape_stream_wait_fit: null context");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->fit_done, 0));
     return RS_OK;
 }
 

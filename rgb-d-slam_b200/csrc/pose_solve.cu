@@ -22,7 +22,7 @@
 //                          (hypotheses are independent: each LM starts from the current pose), then the final LM
 //                          on the winning inlier set.
 //   pose_variance_kernel : one warp per Monte-Carlo sample (perturbed copy of the inlier set in shared memory).
-//   pose_covariance_kernel: one thread per frame, sums in sample order, 6x6 covariance + validity.
+//   pose_covariance_kernel: one warp per frame, 6x6 covariance (one entry per lane, summed in sample order) + validity.
 // FP64 throughout (forward differences with h = 1.49e-8 |x| on mm-scale coordinates need it).
 #include <float.h>
 
@@ -667,10 +667,10 @@ __device__ __forceinline__ void lmpar(WarpLM& S)
 }
 
 // Eigen::LevenbergMarquardt<NumericalDiff<F,Forward>>::minimize on S.x (in/out). Whole warp must call; returns the
-// Eigen status (<= 0 failure, 1..8 MINPACK info). m = residual count of the problem. One copy per kernel (noinline):
-// the body is ~3k instructions and the serial lane-0 chains are latency bound, so instruction-cache residency matters
-// more than call overhead.
-__device__ __noinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m,
+// Eigen status (<= 0 failure, 1..8 MINPACK info). m = residual count of the problem. Inlined at exactly ONE call site per
+// kernel: the body is ~4k instructions and the serial lane-0 chains are latency bound, so instruction-cache residency
+// matters, and inlining lets the compiler see that S and the feature arrays live in shared memory (LDS, not generic LD).
+__device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m,
                                              const int maxfev, const int lane)
 {
     if (m < 6 || maxfev <= 0) return 0;  // ImproperInputParameters
@@ -1098,15 +1098,19 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
     Problem P;
     P.type = sm.type, P.obs = sm.obs, P.map = sm.map, P.M = M;
 
-    for (int chunk = 0; chunk < maxIterations; chunk += RWARPS) {
+    rs_pose_out* out = buf.out + b;
+    // One loop, one LM call site (the LM body is inlined once): passes 0.. are RANSAC chunks of RWARPS hypotheses, the
+    // last pass is the final optimisation on the winning inlier set, run by warp 0 after the others have left.
+    bool finalPass = false;
+    for (int chunk = 0;; chunk += RWARPS) {
         const int it = chunk + warp;
-        if (it < maxIterations) {
+        int cnt = 0, m = 0;
+        double cumulated = 0.0;
+        double xs[6];
+        if (!finalPass) {
             // ---- random subset: ransac::get_random_subset_with_score (ransac.hpp:77-103) ----
-            int cnt = 0, m = 0;
-            double cumulated = 0.0;
-            bool ok = false;
-            int32_t* used = buf.subsets_used + (size_t(b) * buf.max_iterations + it) * RS_MAX_SUBSET;
-            if (lane == 0) {
+            if (lane == 0 && it < maxIterations) {
+                int32_t* used = buf.subsets_used + (size_t(b) * buf.max_iterations + it) * RS_MAX_SUBSET;
                 if (buf.subsets_in) {
                     // host-drawn (std::mt19937 + std::shuffle), already in the reference's prepended order
                     const int32_t* in = buf.subsets_in + (size_t(b) * buf.max_iterations + it) * RS_MAX_SUBSET;
@@ -1134,54 +1138,103 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                 for (int k = 0; k < RS_MAX_SUBSET; ++k) used[k] = k < cnt ? int(subset[k]) : -1;
                 for (int k = 0; k < cnt; ++k) m += sm.type[subset[k]] == RS_FEAT_POINT ? 2 : 3;
             }
-            cnt = __shfl_sync(FULL, cnt, 0);
-            m = __shfl_sync(FULL, m, 0);
-            cumulated = __shfl_sync(FULL, cumulated, 0);
-            __syncwarp();
-            ok = cumulated >= 1.0;
-            if (ok) {
-                P.n = cnt;
-                P.idx = subset;
-                ok = optimize_pose_warp(S, P, prm.K, x0, m, cumulated, prm.lm_max_fev, lane);
-            }
-            int nIn = 0;
-            double score = 0.0;
-            if (ok) {
-                // ---- get_features_inliers_outliers (pose_optimization.cpp:33-72) over all features ----
-                if (lane == 0) make_xform(S.x, S.T);
-                __syncwarp();
-                for (int w = 0; w < words; ++w) {
-                    const int i = w * 32 + lane;
-                    bool in = false;
-                    if (i < n) {
-                        double o[4], mm[4];
+            P.idx = subset;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) o[c] = sm.obs[c * M + i], mm[c] = sm.map[c * M + i];
-                        in = feature_is_inlier(sm.type[i], o, mm, S.T, prm.K);
-                    }
-                    const unsigned bits = __ballot_sync(FULL, in);
-                    if (lane == 0) hmask[w] = bits;
-                    nIn += __popc(bits);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    // the score is accumulated in list order, like the reference's running double
-                    for (int w = 0; w < words; ++w) {
-                        unsigned bits = hmask[w];
-                        while (bits) {
-                            const int i = w * 32 + (__ffs(bits) - 1);
-                            bits &= bits - 1;
-                            score += sm.type[i] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
-                        }
-                    }
-                }
-            }
+            for (int j = 0; j < 6; ++j) xs[j] = x0[j];
+        }
+        else {
+            // ---- final optimisation on the winning inlier set, from the winning pose (:229-262) ----
             if (lane == 0) {
-                sh.hyp_ok[warp] = ok ? 1 : 0;
-                sh.hyp_score[warp] = score;
-                sh.hyp_inliers[warp] = nIn;
-                for (int j = 0; j < 6; ++j) sh.hyp_x[warp][j] = S.x[j];
+                for (int w = 0; w < words; ++w) {
+                    unsigned bits = sm.best_mask[w];
+                    while (bits) {
+                        const int i = w * 32 + (__ffs(bits) - 1);
+                        bits &= bits - 1;
+                        sm.inlier_idx[cnt++] = short(i);
+                        const bool pt = sm.type[i] == RS_FEAT_POINT;
+                        cumulated += pt ? kPointScore : kPlaneScore;
+                        m += pt ? 2 : 3;
+                    }
+                }
+                out->n_inliers = sh.best_inliers;
+                out->iterations_run = sh.started;
+                out->best_iteration = sh.best_iteration;
+                out->score = sh.max_score;
             }
+            P.idx = sm.inlier_idx;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) xs[j] = sh.best_x[j];
+        }
+        cnt = __shfl_sync(FULL, cnt, 0);
+        m = __shfl_sync(FULL, m, 0);
+        cumulated = __shfl_sync(FULL, cumulated, 0);
+        __syncwarp();
+        bool ok = cumulated >= 1.0;  // a hypothesis without enough score is skipped; final: status stays 0
+        if (finalPass && !ok) return;
+        if (ok) {
+            P.n = cnt;
+            ok = optimize_pose_warp(S, P, prm.K, xs, m, cumulated, prm.lm_max_fev, lane);
+        }
+        if (finalPass) {
+            if (!ok) {
+                if (lane == 0) out->status = -1;
+                return;
+            }
+            for (int i = lane; i < n; i += 32) buf.mask[size_t(b) * M + i] = (sm.best_mask[i >> 5] >> (i & 31)) & 1u;
+            if (lane == 0) {
+                double q[4];
+                quaternion_from_coefficients(S.x, q);
+                for (int j = 0; j < 3; ++j) out->pose[j] = S.x[j];
+                for (int j = 0; j < 4; ++j) out->pose[3 + j] = q[j];
+                for (int j = 0; j < 7; ++j) buf.poses[b * 7 + j] = out->pose[j];
+                out->status = prm.n_variance == 0 ? 1 : -2;  // -2 until the covariance kernel validates it
+                PoseFrameState* stp = buf.state + b;
+                stp->stage = 1;
+                for (int j = 0; j < 6; ++j) stp->final_x[j] = S.x[j];
+                stp->n_inliers = cnt;
+                stp->inlier_residuals = m;
+                stp->inlier_score = cumulated;
+            }
+            for (int k = lane; k < cnt; k += 32) buf.inlier_idx[size_t(b) * M + k] = sm.inlier_idx[k];
+            return;
+        }
+        int nIn = 0;
+        double score = 0.0;
+        if (ok) {
+            // ---- get_features_inliers_outliers (pose_optimization.cpp:33-72) over all features ----
+            if (lane == 0) make_xform(S.x, S.T);
+            __syncwarp();
+            for (int w = 0; w < words; ++w) {
+                const int i = w * 32 + lane;
+                bool in = false;
+                if (i < n) {
+                    double o[4], mm[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) o[c] = sm.obs[c * M + i], mm[c] = sm.map[c * M + i];
+                    in = feature_is_inlier(sm.type[i], o, mm, S.T, prm.K);
+                }
+                const unsigned bits = __ballot_sync(FULL, in);
+                if (lane == 0) hmask[w] = bits;
+                nIn += __popc(bits);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // the score is accumulated in list order, like the reference's running double
+                for (int w = 0; w < words; ++w) {
+                    unsigned bits = hmask[w];
+                    while (bits) {
+                        const int i = w * 32 + (__ffs(bits) - 1);
+                        bits &= bits - 1;
+                        score += sm.type[i] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            sh.hyp_ok[warp] = ok ? 1 : 0;
+            sh.hyp_score[warp] = score;
+            sh.hyp_inliers[warp] = nIn;
+            for (int j = 0; j < 6; ++j) sh.hyp_x[warp][j] = S.x[j];
         }
         __syncthreads();
         // ---- the reference's serial bookkeeping over this chunk, in iteration order (:151-227) ----
@@ -1191,12 +1244,12 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                 if (iteration >= maxIterations || sh.can_quit) break;
                 ++sh.started;
                 if (!sh.hyp_ok[w]) continue;
-                const double score = sh.hyp_score[w];
-                if (score < 1.0) continue;
+                const double hs = sh.hyp_score[w];
+                if (hs < 1.0) continue;
                 const bool canOverload =
-                        (score > sh.max_score) || (fabs(score - sh.max_score) <= 0.1 && sh.best_inliers < sh.hyp_inliers[w]);
+                        (hs > sh.max_score) || (fabs(hs - sh.max_score) <= 0.1 && sh.best_inliers < sh.hyp_inliers[w]);
                 if (canOverload) {
-                    sh.max_score = score;
+                    sh.max_score = hs;
                     for (int j = 0; j < 6; ++j) sh.best_x[j] = sh.hyp_x[w][j];
                     for (int k = 0; k < words; ++k) sm.best_mask[k] = sm.hyp_mask[w * words + k];
                     sh.best_inliers = sh.hyp_inliers[w];
@@ -1206,64 +1259,11 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
             }
         }
         __syncthreads();
-        if (sh.can_quit) break;
-    }
-
-    // ---- final optimisation on the winning inlier set, from the winning pose (:229-262) ----
-    if (warp != 0) return;
-    int nInl = 0, m = 0;
-    double inlierScore = 0.0;
-    if (lane == 0) {
-        for (int w = 0; w < words; ++w) {
-            unsigned bits = sm.best_mask[w];
-            while (bits) {
-                const int i = w * 32 + (__ffs(bits) - 1);
-                bits &= bits - 1;
-                sm.inlier_idx[nInl++] = short(i);
-                const bool pt = sm.type[i] == RS_FEAT_POINT;
-                inlierScore += pt ? kPointScore : kPlaneScore;
-                m += pt ? 2 : 3;
-            }
+        if (sh.can_quit || chunk + RWARPS >= maxIterations) {
+            if (warp != 0) return;
+            finalPass = true;
         }
     }
-    nInl = __shfl_sync(FULL, nInl, 0);
-    m = __shfl_sync(FULL, m, 0);
-    inlierScore = __shfl_sync(FULL, inlierScore, 0);
-    __syncwarp();
-    rs_pose_out* out = buf.out + b;
-    if (lane == 0) {
-        out->n_inliers = sh.best_inliers;
-        out->iterations_run = sh.started;
-        out->best_iteration = sh.best_iteration;
-        out->score = sh.max_score;
-    }
-    if (inlierScore < 1.0) return;  // status stays 0
-    double bx[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) bx[j] = sh.best_x[j];
-    P.n = nInl;
-    P.idx = sm.inlier_idx;
-    const bool ok = optimize_pose_warp(S, P, prm.K, bx, m, inlierScore, prm.lm_max_fev, lane);
-    if (!ok) {
-        if (lane == 0) out->status = -1;
-        return;
-    }
-    for (int i = lane; i < n; i += 32) buf.mask[size_t(b) * M + i] = (sm.best_mask[i >> 5] >> (i & 31)) & 1u;
-    if (lane == 0) {
-        double q[4];
-        quaternion_from_coefficients(S.x, q);
-        for (int j = 0; j < 3; ++j) out->pose[j] = S.x[j];
-        for (int j = 0; j < 4; ++j) out->pose[3 + j] = q[j];
-        for (int j = 0; j < 7; ++j) buf.poses[b * 7 + j] = out->pose[j];
-        out->status = prm.n_variance == 0 ? 1 : -2;  // -2 until the covariance kernel validates it
-        PoseFrameState* stp = buf.state + b;
-        stp->stage = 1;
-        for (int j = 0; j < 6; ++j) stp->final_x[j] = S.x[j];
-        stp->n_inliers = nInl;
-        stp->inlier_residuals = m;
-        stp->inlier_score = inlierScore;
-    }
-    for (int k = lane; k < nInl; k += 32) buf.inlier_idx[size_t(b) * M + k] = sm.inlier_idx[k];
 }
 
 // compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
@@ -1389,10 +1389,12 @@ __device__ bool covariance_valid(const double* c)
     return !neg;
 }
 
-// compute_pose_variance's reduction (pose_optimization.cpp:414-437): one thread per frame, sums in sample order.
-__global__ void pose_covariance_kernel(const PoseBuffers buf, const PoseLaunch prm)
+// compute_pose_variance's reduction (pose_optimization.cpp:414-437): one warp per frame. Lanes split the samples for
+// the mean, then lane e < 21 owns one entry of the upper triangle and sums it over the samples in sample order.
+__global__ void __launch_bounds__(128) pose_covariance_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (b >= prm.batch) return;
     if (buf.state[b].stage != 1 || prm.n_variance <= 0) return;
     const double* v6 = buf.v6 + size_t(b) * buf.max_variance * 6;
@@ -1400,30 +1402,49 @@ __global__ void pose_covariance_kernel(const PoseBuffers buf, const PoseLaunch p
     rs_pose_out* out = buf.out + b;
     double medium[6] = {0, 0, 0, 0, 0, 0};
     int cnt = 0;
-    for (int s = 0; s < prm.n_variance; ++s)
+    for (int s = lane; s < prm.n_variance; s += 32)
         if (vok[s]) {
+#pragma unroll
             for (int j = 0; j < 6; ++j) medium[j] += v6[s * 6 + j];
             ++cnt;
         }
-    out->n_variance_ok = cnt;
+    cnt = __reduce_add_sync(FULL, cnt);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) medium[j] = warp_sum(medium[j]);
+    if (lane == 0) out->n_variance_ok = cnt;
     if (unsigned(cnt) < unsigned(prm.n_variance) / 2u) {
-        out->status = -2;
+        if (lane == 0) out->status = -2;
         return;
     }
+#pragma unroll
     for (int j = 0; j < 6; ++j) medium[j] /= double(cnt);
-    double cov[36];
-    for (int i = 0; i < 36; ++i) cov[i] = 0.0;
+    int ei = 0, ej = 0;
+    {
+        int rem = lane < 21 ? lane : 0;
+        while (rem >= 6 - ei) rem -= 6 - ei, ++ei;
+        ej = ei + rem;
+    }
+    double mi = 0.0, mj = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        if (j == ei) mi = medium[j];
+        if (j == ej) mj = medium[j];
+    }
+    double acc = 0.0;
     for (int s = 0; s < prm.n_variance; ++s)
-        if (vok[s]) {
-            double def[6];
-            for (int j = 0; j < 6; ++j) def[j] = v6[s * 6 + j] - medium[j];
-            for (int i = 0; i < 6; ++i)
-                for (int j = 0; j < 6; ++j) cov[i * 6 + j] += def[i] * def[j];
-        }
-    for (int i = 0; i < 36; ++i) cov[i] /= double(cnt - 1);
-    for (int i = 0; i < 6; ++i) cov[i * 6 + i] += 0.001;
-    for (int i = 0; i < 36; ++i) out->cov[i] = cov[i];
-    out->status = covariance_valid(cov) ? 1 : -2;
+        if (vok[s]) acc += (v6[s * 6 + ei] - mi) * (v6[s * 6 + ej] - mj);
+    acc /= double(cnt - 1);
+    if (ei == ej) acc += 0.001;
+    if (lane < 21) {
+        out->cov[ei * 6 + ej] = acc;
+        out->cov[ej * 6 + ei] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double cov[36];
+        for (int i = 0; i < 36; ++i) cov[i] = out->cov[i];
+        out->status = covariance_valid(cov) ? 1 : -2;
+    }
 }
 
 __global__ void pose_export_normals_kernel(const PoseLaunch prm, const int M, double* normals)
@@ -1485,7 +1506,7 @@ int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStre
 int launch_pose_covariance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
 {
     if (prm.n_variance <= 0) return RS_OK;
-    pose_covariance_kernel<<<(prm.batch + 63) / 64, 64, 0, stream>>>(buf, prm);
+    pose_covariance_kernel<<<(prm.batch + 3) / 4, 128, 0, stream>>>(buf, prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }

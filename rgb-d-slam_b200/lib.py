@@ -38,6 +38,7 @@ def load():
     lib.rs_cape_run.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs)]
     lib.rs_cape_run_device.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs), vp]
     lib.rs_cape_cell_fit_device.argtypes = [vp, vp, i32, vp, vp]
+    lib.rs_cape_stream_wait_fit.argtypes = [vp, vp]
     lib.rs_cape_device_depth.restype = vp
     lib.rs_cape_device_depth.argtypes = [vp]
     lib.rs_cape_device_outputs.restype = C.POINTER(abi.CapeOutputs)
@@ -133,6 +134,10 @@ class PrimitiveDetection:
     def run_device(self, depth_ptr, batch, seed=0, outputs=None, stream=0):
         o = outputs if outputs is not None else self.device_outputs()
         _check(self._lib.rs_cape_run_device(self._ctx, depth_ptr, batch, seed, C.byref(o), stream), "rs_cape_run_device")
+
+    def stream_wait_fit(self, stream):
+        """`stream` (cudaStream_t as int) waits for the latest plane-fit kernel of this context."""
+        _check(self._lib.rs_cape_stream_wait_fit(self._ctx, stream), "rs_cape_stream_wait_fit")
 
     def set_timing(self, n_slots):
         _check(self._lib.rs_cape_set_timing(self._ctx, n_slots), "rs_cape_set_timing")
