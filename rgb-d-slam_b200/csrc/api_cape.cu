@@ -76,6 +76,7 @@ struct rs_cape_ctx {
     float* d_depth = nullptr;
     rs_cape_outputs d_out{};       // device pointers sized for max_batch
     double* d_uniforms = nullptr;
+    double* d_scratch = nullptr;   // per-frame scratch of the segmentation kernel
     int n_uniforms = 0;
     uint32_t uniforms_seed = 0;
     bool uniforms_valid = false;
@@ -189,6 +190,7 @@ int create_impl(rs_cape_ctx* c)
     if ((rc = dev_alloc(&c->d_out.cyls, B * RS_MAX_CYL_REGIONS))) return rc;
     if ((rc = dev_alloc(&c->d_out.boundary_xyz, B * size_t(c->max_boundary) * 3))) return rc;
     if ((rc = dev_alloc(&c->d_out.info, B))) return rc;
+    if ((rc = dev_alloc(&c->d_scratch, B * cape_segment_scratch_doubles_per_frame(c->Nc)))) return rc;
     c->n_uniforms = 3 * RS_CYL_RANSAC_ITERS * RS_MAX_CYL_REGIONS * RS_MAX_CYL_SEGS;
     if ((rc = dev_alloc(&c->d_uniforms, size_t(c->n_uniforms)))) return rc;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -249,6 +251,7 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     sb.cyls = o->cyls;
     sb.boundary_xyz = o->boundary_xyz;
     sb.info = o->info;
+    sb.scratch = c->d_scratch;
     if ((rc = launch_cape_segment(sp, sb, stream)) != RS_OK) return rc;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
     return RS_OK;
@@ -296,6 +299,7 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_out.boundary_xyz);
     cudaFree(c->d_out.info);
     cudaFree(c->d_uniforms);
+    cudaFree(c->d_scratch);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->fit_done) cudaEventDestroy(c->fit_done);
     if (c->stream) cudaStreamDestroy(c->stream);

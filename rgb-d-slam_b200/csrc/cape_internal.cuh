@@ -43,8 +43,10 @@ struct SegmentBuffers {
     rs_cyl_out* cyls;            // B x RS_MAX_CYL_REGIONS
     double* boundary_xyz;        // B x max_boundary x 3
     rs_cape_frame_info* info;    // B
+    double* scratch;             // B x cape_segment_scratch_doubles_per_frame(Nc): projected normals / centroids of the cylinder branch
 };
 
 int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream);
+size_t cape_segment_scratch_doubles_per_frame(int n_cells);
 
 }  // namespace rs

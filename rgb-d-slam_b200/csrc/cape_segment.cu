@@ -1,4 +1,4 @@
-// K2-K4 `cape_segment` — one CTA per frame over the cell graph produced by K1.
+// K2-K4 `cape_segment` — ONE WARP PER FRAME over the cell graph produced by K1.
 //
 // Replaces  Primitive_Detection::{init_histogram, grow_planes_and_cylinders, grow_plane_segment_at_seed,
 //           region_growing, cylinder_fitting, merge_planes, get_connected_components_matrix,
@@ -6,12 +6,20 @@
 //           (primitive_detection.cpp:239-776), Histogram<N> (histogram.hpp:35-113) and
 //           Cylinder_Segment's ctor + run_ransac_loop (cylinder_segment.cpp:35-322).
 //
-// The seed loop is inherently sequential (each seed depends on the histogram state left by the previous one), so
-// the parallel axes are: frames (one CTA each), cells inside every scan, and the BFS frontier of the region growing
-// (the reference's recursive DFS computes a reachability set in a directed graph; a frontier BFS gives the same set).
-// Every FP64 sum whose order is fixed by the reference (merging cell sums in index order, LLS sums, MSAC cost) is
-// evaluated in that same order by one thread so that results are bit-identical to the restated reference; all other
-// work is spread over the CTA. Compiled with -fmad=false.
+// The seed loop is inherently sequential (each seed depends on the histogram state left by the previous one) and the
+// chains inside it (ordered FP64 sums, the 3x3 eigen-solve of every refit, the MSAC cost) are serial by construction,
+// so a frame is latency bound. The mapping therefore spends as little of the SM as possible per frame - one warp, no
+// block-wide barrier anywhere - and lets the batch supply the parallelism (two frames per SM, every frame of a
+// 256-frame batch resident at once, and room left on each SM for the pose kernels that run beside this one):
+//   * the cell graph (normals, centroids, d, MSE, tolerances) is staged once in shared memory;
+//   * the merge predicate can_be_merged(u -> v) of every grid edge depends only on the two cells, so it is evaluated
+//     ONCE per frame into four bit planes (one 64-bit word per cell row and direction) instead of once per visit;
+//   * region growing (the reference's recursive DFS = reachability in that directed graph) is a bit-parallel flood
+//     fill: one lane per cell row, a shift/AND/OR row sweep until the row is stable, neighbour rows read from shared
+//     memory, repeated until no row changes - tens of instructions per pass instead of a CTA-wide scan with barriers;
+//   * every FP64 sum whose order is fixed by the reference (merging cell sums in index order, LLS sums, MSAC cost) is
+//     evaluated in that same order by one lane, from operands gathered by the whole warp, so that results are
+//     bit-identical to the restated reference. Compiled with -fmad=false.
 #include "cape_internal.cuh"
 #include "plane_fit.cuh"
 
@@ -19,49 +27,43 @@ namespace rs {
 
 namespace {
 
-constexpr int T = 256;
-constexpr int NW = T / 32;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int STAGE_CELLS = 64;   // cells gathered per round of an ordered sum
+constexpr int MAX_ROWS = 64;      // cell rows / columns the bit planes can hold
+typedef unsigned long long u64;
 
 struct Scalars {
-    int best_bin, cand_count, seed, changed;
-    int untried, n_planes, n_cyl_regions, n_cylinders, n_seeds, n_boundary, status;
-    int cnt, flag, uniform_cursor;
-    double dscr[NW];
-    int iscr[NW];
-    int iscr2[NW];
+    int n_planes, n_cyl_regions, n_cylinders, n_seeds, n_boundary, status, uniform_cursor;
     PlaneModel work;       // plane being grown / refit
     PlaneModel work2;
-    // cylinder scalars
     double axis[3], radius, inv_r2, center[3];
     double dval[8];
-    int nleft, nids, best_count, cand_cnt_tmp;
 };
 
 struct Smem {
     double* cn;    // [Nc][3] cell normals
-    double* cd;    // [Nc]
     double* cc;    // [Nc][3] centroids
+    double* cd;    // [Nc]
     double* cmse;  // [Nc]
-    double* pn;    // [Nc][3] projected normals (cylinder, local ids)
-    double* pc;    // [Nc][3] projected centroids
-    double* val;   // [Nc] scratch values
-    float* tol;    // [Nc]
-    int* bins;     // [Nc]
-    int* hist;     // [cs*cs]
-    int* list;     // [Nc] ordered activated cells (local -> global)
-    int* ids;      // [Nc] remaining local ids (cylinder RANSAC)
-    int* plab;     // [Nc] final merged labels
-    short* gplane; // [Nc] _gridPlaneSegmentMap
-    short* gcyl;   // [Nc] _gridCylinderSegMap
-    unsigned char *unassigned, *activated, *planar, *mleft, *inlA, *inlB, *m0, *m1;
-    // planes (compact copy for predicates; sums live in the global record)
-    double* pln;   // [RS_MAX_PLANES][3]
+    double* val;   // [Nc] scratch values (cylinder branch)
+    double* stage; // [STAGE_CELLS][10] operands of the ordered sums
+    double* pln;   // [RS_MAX_PLANES][3] planes (compact copy for predicates; sums live in the global record)
     double* plc;   // [RS_MAX_PLANES][3]
     double* pld;   // [RS_MAX_PLANES]
+    u64 *U, *ACT, *EL, *ER, *EU, *ED;  // [MAX_ROWS] bit planes: unassigned, activated, merge edges from the 4 neighbours
+    Scalars* sc;
+    float* tol;    // [Nc]
+    int* hist;     // [cs*cs]
     int* plabel;   // [RS_MAX_PLANES] merge labels
     int* pplanar;  // [RS_MAX_PLANES]
     unsigned* conn; // [RS_MAX_PLANES][RS_MAX_PLANES/32]
-    Scalars* sc;
+    short* bins;   // [Nc]
+    short* list;   // [Nc] ordered activated cells (local -> global)
+    short* ids;    // [Nc] remaining local ids (cylinder RANSAC)
+    short* plab;   // [Nc] final merged labels
+    short* gplane; // [Nc] _gridPlaneSegmentMap
+    short* gcyl;   // [Nc] _gridCylinderSegMap
+    unsigned char *planar, *mleft, *inlA, *inlB, *m0, *m1;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -75,89 +77,60 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int Nc, in
         return p;
     };
     double* cn = reinterpret_cast<double*>(take(sizeof(double) * 3 * Nc));
-    double* cd = reinterpret_cast<double*>(take(sizeof(double) * Nc));
     double* cc = reinterpret_cast<double*>(take(sizeof(double) * 3 * Nc));
+    double* cd = reinterpret_cast<double*>(take(sizeof(double) * Nc));
     double* cmse = reinterpret_cast<double*>(take(sizeof(double) * Nc));
-    double* pn = reinterpret_cast<double*>(take(sizeof(double) * 3 * Nc));
-    double* pc = reinterpret_cast<double*>(take(sizeof(double) * 3 * Nc));
     double* val = reinterpret_cast<double*>(take(sizeof(double) * Nc));
+    double* stage = reinterpret_cast<double*>(take(sizeof(double) * STAGE_CELLS * 10));
     double* pln = reinterpret_cast<double*>(take(sizeof(double) * 3 * RS_MAX_PLANES));
     double* plc = reinterpret_cast<double*>(take(sizeof(double) * 3 * RS_MAX_PLANES));
     double* pld = reinterpret_cast<double*>(take(sizeof(double) * RS_MAX_PLANES));
+    u64* planes64 = reinterpret_cast<u64*>(take(sizeof(u64) * 6 * MAX_ROWS));
     Scalars* sc = reinterpret_cast<Scalars*>(take(sizeof(Scalars)));
     float* tol = reinterpret_cast<float*>(take(sizeof(float) * Nc));
-    int* bins = reinterpret_cast<int*>(take(sizeof(int) * Nc));
     int* hist = reinterpret_cast<int*>(take(sizeof(int) * nbins));
-    int* list = reinterpret_cast<int*>(take(sizeof(int) * Nc));
-    int* ids = reinterpret_cast<int*>(take(sizeof(int) * Nc));
-    int* plab = reinterpret_cast<int*>(take(sizeof(int) * Nc));
     int* plabel = reinterpret_cast<int*>(take(sizeof(int) * RS_MAX_PLANES));
     int* pplanar = reinterpret_cast<int*>(take(sizeof(int) * RS_MAX_PLANES));
     unsigned* conn = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * RS_MAX_PLANES * (RS_MAX_PLANES / 32)));
-    short* gplane = reinterpret_cast<short*>(take(sizeof(short) * Nc));
-    short* gcyl = reinterpret_cast<short*>(take(sizeof(short) * Nc));
-    unsigned char* u8[8];
-    for (int i = 0; i < 8; ++i) u8[i] = take(size_t(Nc));
+    short* sh[6];
+    for (int i = 0; i < 6; ++i) sh[i] = reinterpret_cast<short*>(take(sizeof(short) * Nc));
+    unsigned char* u8[6];
+    for (int i = 0; i < 6; ++i) u8[i] = take(size_t(Nc));
     if (s) {
-        s->cn = cn, s->cd = cd, s->cc = cc, s->cmse = cmse, s->pn = pn, s->pc = pc, s->val = val;
-        s->pln = pln, s->plc = plc, s->pld = pld, s->sc = sc, s->tol = tol, s->bins = bins, s->hist = hist;
-        s->list = list, s->ids = ids, s->plab = plab, s->plabel = plabel, s->pplanar = pplanar, s->conn = conn;
-        s->gplane = gplane, s->gcyl = gcyl;
-        s->unassigned = u8[0], s->activated = u8[1], s->planar = u8[2], s->mleft = u8[3];
-        s->inlA = u8[4], s->inlB = u8[5], s->m0 = u8[6], s->m1 = u8[7];
+        s->cn = cn, s->cc = cc, s->cd = cd, s->cmse = cmse, s->val = val, s->stage = stage;
+        s->pln = pln, s->plc = plc, s->pld = pld, s->sc = sc, s->tol = tol, s->hist = hist;
+        s->U = planes64, s->ACT = planes64 + MAX_ROWS, s->EL = planes64 + 2 * MAX_ROWS, s->ER = planes64 + 3 * MAX_ROWS;
+        s->EU = planes64 + 4 * MAX_ROWS, s->ED = planes64 + 5 * MAX_ROWS;
+        s->plabel = plabel, s->pplanar = pplanar, s->conn = conn;
+        s->bins = sh[0], s->list = sh[1], s->ids = sh[2], s->plab = sh[3], s->gplane = sh[4], s->gcyl = sh[5];
+        s->planar = u8[0], s->mleft = u8[1], s->inlA = u8[2], s->inlB = u8[3], s->m0 = u8[4], s->m1 = u8[5];
     }
     return o;
 }
 
-// ---- block-wide helpers (all threads must call) ----------------------------------------------------
-__device__ __forceinline__ int block_sum_int(int v, int* scr)
-{
-    v = __reduce_add_sync(0xffffffffu, v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) scr[w] = v;
-    __syncthreads();
-    int r = 0;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) r += scr[i];
-    return r;
-}
-
-// exclusive prefix (in index order) of a 0/1 flag over the CTA; returns the CTA total through *total
-__device__ __forceinline__ int block_scan_flag(bool flag, int* scr, int* total)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, flag);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) scr[w] = __popc(m);
-    __syncthreads();
-    int before = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        if (i < w) before += scr[i];
-        tot += scr[i];
-    }
-    *total = tot;
-    return before + __popc(m & ((1u << l) - 1u));
-}
-
-// lexicographic minimum of (key, idx) over the CTA
-__device__ __forceinline__ void block_min_key(double& key, int& idx, double* dscr, int* iscr)
+// ---- warp-wide helpers (all 32 lanes must call) ---------------------------------------------------
+// lexicographic minimum of (key, idx) over the warp
+__device__ __forceinline__ void warp_min_key(double& key, int& idx)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ok = __shfl_xor_sync(0xffffffffu, key, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        const double ok = __shfl_xor_sync(FULL, key, o);
+        const int oi = __shfl_xor_sync(FULL, idx, o);
         if (ok < key || (ok == key && oi < idx)) key = ok, idx = oi;
     }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) dscr[w] = key, iscr[w] = idx;
-    __syncthreads();
-    key = dscr[0], idx = iscr[0];
+}
+
+// exclusive prefix of `v` over the lanes; *total = warp sum
+__device__ __forceinline__ int warp_excl_scan(const int v, const int lane, int* total)
+{
+    int inc = v;
 #pragma unroll
-    for (int i = 1; i < NW; ++i)
-        if (dscr[i] < key || (dscr[i] == key && iscr[i] < idx)) key = dscr[i], idx = iscr[i];
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    *total = __shfl_sync(FULL, inc, 31);
+    return inc - v;
 }
 
 // Histogram::remove_point (histogram.hpp:103-113) — quirk: the bin becomes 1, not -1.
@@ -190,7 +163,7 @@ __device__ __forceinline__ void store_plane_record(rs_plane_out& o, const PlaneM
 }
 
 // new plane segment := copy-construct (re-normalises the normal, plane_segment.cpp:18-36) and push_back.
-// Must be called by thread 0 only. Returns the 1-based plane id or 0 when the capacity is exhausted.
+// Must be called by lane 0 only. Returns the 1-based plane id or 0 when the capacity is exhausted.
 __device__ int push_plane(const Smem& s, rs_plane_out* planes, const PlaneModel& src)
 {
     Scalars& sc = *s.sc;
@@ -207,23 +180,35 @@ __device__ int push_plane(const Smem& s, rs_plane_out* planes, const PlaneModel&
     return k + 1;
 }
 
-// S/count of `dst` += sums of the listed cells, in list order (threads 0..9; one running sum each).
-__device__ __forceinline__ void ordered_expand(PlaneModel& dst, const rs_cell_out* cells, const int* list, int n,
-                                               const unsigned char* filter)
+// S/count of `dst` += sums of the listed cells, in list order. The operands are gathered STAGE_CELLS cells at a time
+// by the whole warp (coalesced 80-byte reads of the records K1 wrote); lanes 0..9 then run one ordered sum each.
+__device__ void ordered_expand(const Smem& s, PlaneModel& dst, const rs_cell_out* __restrict__ cells, const short* list,
+                               const int n, const unsigned char* filter, const int lane)
 {
-    const int t = threadIdx.x;
-    if (t < 9) {
-        double acc = dst.S[t];
-        for (int j = 0; j < n; ++j)
-            if (!filter || filter[j]) acc += cells[list[j]].S[t];
-        dst.S[t] = acc;
+    double acc = 0.0;
+    if (lane < 9) acc = dst.S[lane];
+    if (lane == 9) acc = static_cast<double>(dst.count);  // point counts stay far below 2^53: the double sum is exact
+    for (int base = 0; base < n; base += STAGE_CELLS) {
+        const int m = min(STAGE_CELLS, n - base);
+        for (int idx = lane; idx < m * 10; idx += 32) {
+            const int j = idx / 10, t = idx - 10 * j;
+            double v = 0.0;
+            if (!filter || filter[base + j]) {
+                const rs_cell_out* c = cells + list[base + j];
+                v = t < 9 ? c->S[t] : static_cast<double>(c->count);
+            }
+            s.stage[idx] = v;
+        }
+        __syncwarp();
+        if (lane < 10) {
+            for (int j = 0; j < m; ++j)
+                if (!filter || filter[base + j]) acc += s.stage[j * 10 + lane];
+        }
+        __syncwarp();
     }
-    else if (t == 9) {
-        int acc = dst.count;
-        for (int j = 0; j < n; ++j)
-            if (!filter || filter[j]) acc += cells[list[j]].count;
-        dst.count = acc;
-    }
+    if (lane < 9) dst.S[lane] = acc;
+    if (lane == 9) dst.count = static_cast<int>(acc);
+    __syncwarp();
 }
 
 // cv::erode / cv::dilate on the cell grid, 3x3 kernels, one output cell.
@@ -248,30 +233,33 @@ __device__ __forceinline__ unsigned char morph_at(const unsigned char* m, int ro
 }
 
 // ---- cylinder branch (cylinder_segment.cpp:35-322 + primitive_detection.cpp:413-501) ------------
+// pn / pc: projected normals / centroids of the region's cells, [m][3] each, in this frame's global scratch.
 __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const rs_cell_out* cells, rs_plane_out* planes,
-                                 rs_cyl_out* cyls, int32_t* cyl_region_seg, const int m, const int Nc)
+                                 rs_cyl_out* cyls, int32_t* cyl_region_seg, double* pn, double* pc, const int m,
+                                 const int Nc, const int lane)
 {
     Scalars& sc = *s.sc;
-    const int t = threadIdx.x;
     if (sc.n_cyl_regions >= RS_MAX_CYL_REGIONS) {
-        if (t == 0) sc.status = RS_ERR_CAPACITY;
+        if (lane == 0) sc.status = RS_ERR_CAPACITY;
+        __syncwarp();
         return;
     }
     const int region = sc.n_cyl_regions;
     rs_cyl_out& co = cyls[region];
-    __syncthreads();
+    __syncwarp();
 
-    // covariance of [N -N] (3 x 2m), summed column by column: six unique entries, one thread each
-    if (t < 6) {
-        const int r = (t < 3) ? 0 : (t < 5 ? 1 : 2);
-        const int c = (t < 3) ? t : (t < 5 ? t - 2 : 2);
+    // covariance of [N -N] (3 x 2m), summed column by column: six unique entries, one lane each
+    if (lane < 6) {
+        const int r = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
+        const int c = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
         double acc = 0;
         for (int j = 0; j < m; ++j) acc += s.cn[3 * s.list[j] + r] * s.cn[3 * s.list[j] + c];
         for (int j = 0; j < m; ++j) acc += (-s.cn[3 * s.list[j] + r]) * (-s.cn[3 * s.list[j] + c]);
-        sc.dval[t] = acc / static_cast<double>(2 * m - 1);
+        sc.dval[lane] = acc / static_cast<double>(2 * m - 1);
     }
-    __syncthreads();
-    if (t == 0) {
+    __syncwarp();
+    int flag = 0;
+    if (lane == 0) {
         // entries: 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2); lower triangle a10=(0,1), a20=(0,2), a21=(1,2)
         double ev[3], q[3][3];
         self_adjoint_eigen3(sc.dval[0], sc.dval[1], sc.dval[3], sc.dval[2], sc.dval[4], sc.dval[5], ev, q);
@@ -280,54 +268,52 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
         co.n_segments = 0;
         co.pca_score = score;
         sc.axis[0] = q[0][0], sc.axis[1] = q[1][0], sc.axis[2] = q[2][0];
-        sc.flag = !(score < 75.0);  // cylinderRansacMinimumScore (float 75)
-        if (sc.flag)
+        flag = !(score < 75.0);  // cylinderRansacMinimumScore (float 75)
+        if (flag)
             for (int i = 0; i < 3; ++i) co.axis[i] = sc.axis[i];
         sc.n_cyl_regions = region + 1;
     }
-    __syncthreads();
-    if (!sc.flag) return;
+    flag = __shfl_sync(FULL, flag, 0);
+    __syncwarp();
+    if (!flag) return;
 
     const double ax = sc.axis[0], ay = sc.axis[1], az = sc.axis[2];
-    for (int j = t; j < m; j += T) {
+    for (int j = lane; j < m; j += 32) {
         const int gi = s.list[j];
         const double c0 = s.cc[3 * gi], c1 = s.cc[3 * gi + 1], c2 = s.cc[3 * gi + 2];
         const double cdot = (ax * c0 + ay * c1) + az * c2;
-        s.pc[3 * j] = c0 - cdot * ax;
-        s.pc[3 * j + 1] = c1 - cdot * ay;
-        s.pc[3 * j + 2] = c2 - cdot * az;
+        pc[3 * j] = c0 - cdot * ax;
+        pc[3 * j + 1] = c1 - cdot * ay;
+        pc[3 * j + 2] = c2 - cdot * az;
         const double n0 = s.cn[3 * gi], n1 = s.cn[3 * gi + 1], n2 = s.cn[3 * gi + 2];
         const double ndot = (ax * n0 + ay * n1) + az * n2;
         const double p0 = n0 - ndot * ax, p1 = n1 - ndot * ay, p2 = n2 - ndot * az;
         const double nn = sqrt((p0 * p0 + p1 * p1) + p2 * p2);
-        s.pn[3 * j] = p0 / nn;
-        s.pn[3 * j + 1] = p1 / nn;
-        s.pn[3 * j + 2] = p2 / nn;
+        pn[3 * j] = p0 / nn;
+        pn[3 * j + 1] = p1 / nn;
+        pn[3 * j + 2] = p2 / nn;
         s.mleft[j] = 1;
-        s.ids[j] = j;
+        s.ids[j] = static_cast<short>(j);
     }
-    if (t == 0) {
-        sc.nleft = m;
-        sc.nids = m;
-    }
-    __syncthreads();
+    __syncwarp();
+    int nleft = m, nIds = m;   // warp-uniform
 
     const unsigned minimumCellActivated = static_cast<unsigned>(0.65 / 100.0 * static_cast<double>(Nc));
     const float maxSqrtDist = 0.04f;
     const double maxSqrtDistD = static_cast<double>(maxSqrtDist);
     int segId = 0;
-    while (static_cast<unsigned>(sc.nleft) > minimumCellActivated && sc.nleft > 0.1 * m) {
+    while (static_cast<unsigned>(nleft) > minimumCellActivated && nleft > 0.1 * m) {
         // ---- run_ransac_loop ----
-        const int nIds = sc.nids;
         unsigned char* best = s.inlA;
         unsigned char* cand = s.inlB;
         int bestCount = 0;
         if (nIds >= 3) {
             const unsigned accepted = static_cast<unsigned>(floor(0.9 * nIds));
             double minHypothesisDist = static_cast<double>(maxSqrtDist * static_cast<float>(nIds));
-            for (int j = t; j < m; j += T) best[j] = 0;
+            for (int j = lane; j < m; j += 32) best[j] = 0;
+            __syncwarp();
             for (int it = 0; it < RS_CYL_RANSAC_ITERS; ++it) {
-                if (t == 0) {
+                if (lane == 0) {
                     int id[3];
                     for (int k = 0; k < 3; ++k) {
                         double u = 0.0;
@@ -337,12 +323,12 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
                             sc.status = RS_ERR_CAPACITY;
                         id[k] = s.ids[static_cast<unsigned>(floor(u * static_cast<double>(static_cast<unsigned>(nIds))))];
                     }
-                    const double* n1 = s.pn + 3 * id[0];
-                    const double* n2 = s.pn + 3 * id[1];
-                    const double* n3 = s.pn + 3 * id[2];
-                    const double* c1 = s.pc + 3 * id[0];
-                    const double* c2 = s.pc + 3 * id[1];
-                    const double* c3 = s.pc + 3 * id[2];
+                    const double* n1 = pn + 3 * id[0];
+                    const double* n2 = pn + 3 * id[1];
+                    const double* n3 = pn + 3 * id[2];
+                    const double* c1 = pc + 3 * id[0];
+                    const double* c2 = pc + 3 * id[1];
+                    const double* c3 = pc + 3 * id[2];
                     double sn[3], sm[3], tt[3];
                     for (int k = 0; k < 3; ++k) {
                         sn[k] = (n1[k] + n2[k]) + n3[k];
@@ -356,15 +342,15 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
                     sc.inv_r2 = 1.0 / (radius * radius);
                     for (int k = 0; k < 3; ++k) sc.center[k] = (sm[k] - radius * sn[k]) / 3.0;
                 }
-                __syncthreads();
+                __syncwarp();
                 const double radius = sc.radius, invr2 = sc.inv_r2, e0 = sc.center[0], e1 = sc.center[1], e2 = sc.center[2];
-                for (int j = t; j < m; j += T) {
+                for (int j = lane; j < m; j += 32) {
                     double v = -1.0;  // not part of this RANSAC round
                     unsigned char in = 0;
                     if (s.mleft[j]) {
-                        const double d0 = (s.pc[3 * j] - radius * s.pn[3 * j]) - e0;
-                        const double d1 = (s.pc[3 * j + 1] - radius * s.pn[3 * j + 1]) - e1;
-                        const double d2 = (s.pc[3 * j + 2] - radius * s.pn[3 * j + 2]) - e2;
+                        const double d0 = (pc[3 * j] - radius * pn[3 * j]) - e0;
+                        const double d1 = (pc[3 * j + 1] - radius * pn[3 * j + 1]) - e1;
+                        const double d2 = (pc[3 * j + 2] - radius * pn[3 * j + 2]) - e2;
                         const double distance = ((d0 * d0 + d1 * d1) + d2 * d2) * invr2;
                         if (distance < maxSqrtDistD) {
                             v = distance;
@@ -376,74 +362,68 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
                     s.val[j] = v;
                     cand[j] = in;
                 }
-                __syncthreads();
-                if (t == 0) {
+                __syncwarp();
+                int better = 0, candCount = 0;
+                double dist = 0.0;
+                if (lane == 0) {
                     // MSAC cost in cell order, exactly as the reference accumulates it
-                    double dist = 0.0;
-                    int cnt = 0;
                     for (int j = 0; j < m; ++j) {
                         const double v = s.val[j];
                         if (v >= 0.0) dist += v;
-                        cnt += cand[j];
+                        candCount += cand[j];
                     }
-                    sc.flag = 0;
-                    sc.cnt = 0;
-                    if (dist < minHypothesisDist) {
-                        sc.dval[0] = dist;
-                        sc.flag = 1;
-                        sc.cand_cnt_tmp = cnt;
-                    }
+                    better = dist < minHypothesisDist ? 1 : 0;
                 }
-                __syncthreads();
+                better = __shfl_sync(FULL, better, 0);
                 bool stop = false;
-                if (sc.flag) {
-                    minHypothesisDist = sc.dval[0];
+                if (better) {
+                    minHypothesisDist = __shfl_sync(FULL, dist, 0);
                     unsigned char* tmp = best;
                     best = cand;
                     cand = tmp;
                     const int prevCount = bestCount;
-                    bestCount = sc.cand_cnt_tmp;
+                    bestCount = __shfl_sync(FULL, candCount, 0);
                     // quirk: the early stop looks at the PREVIOUS best set (vectors swapped before the test)
                     if (static_cast<unsigned>(prevCount) > accepted) stop = true;
                 }
-                __syncthreads();
+                __syncwarp();
                 if (stop) break;
             }
         }
         if (bestCount < 6) break;
         if (segId >= RS_MAX_CYL_SEGS) {
-            if (t == 0) sc.status = RS_ERR_CAPACITY;
+            if (lane == 0) sc.status = RS_ERR_CAPACITY;
             break;
         }
 
         // ---- LLS over the inliers, ordered sums (7 running sums) ----
-        if (t < 7) {
+        if (lane < 7) {
             double acc = 0.0;
             for (int j = 0; j < m; ++j)
                 if (best[j]) {
-                    if (t < 3)
-                        acc += s.pn[3 * j + t];
-                    else if (t < 6)
-                        acc += s.pc[3 * j + (t - 3)];
+                    if (lane < 3)
+                        acc += pn[3 * j + lane];
+                    else if (lane < 6)
+                        acc += pc[3 * j + (lane - 3)];
                     else
-                        acc += (s.pn[3 * j] * s.pc[3 * j] + s.pn[3 * j + 1] * s.pc[3 * j + 1]) + s.pn[3 * j + 2] * s.pc[3 * j + 2];
+                        acc += (pn[3 * j] * pc[3 * j] + pn[3 * j + 1] * pc[3 * j + 1]) + pn[3 * j + 2] * pc[3 * j + 2];
                 }
-            sc.dval[t] = acc;
+            sc.dval[lane] = acc;
         }
-        __syncthreads();
-        if (t == 0) {
+        __syncwarp();
+        if (lane == 0) {
             // rebuild the remaining id list in index order, drop the inliers from the mask
-            int nl = sc.nleft, k = 0;
+            int nl = nleft, k = 0;
             for (int j = 0; j < m; ++j) {
                 if (best[j]) {
                     s.mleft[j] = 0;
                     nl--;
                 }
                 else if (s.mleft[j])
-                    s.ids[k++] = j;
+                    s.ids[k++] = static_cast<short>(j);
             }
-            sc.nleft = nl;
-            sc.nids = k;
+            nleft = nl;
+            nIds = k;
             const double cntd = static_cast<double>(static_cast<size_t>(bestCount));
             const double inv2 = 1.0 / static_cast<double>(static_cast<size_t>(bestCount) * static_cast<size_t>(bestCount));
             const double* sn = sc.dval;
@@ -457,7 +437,9 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
             if (radius < 0) radius = -radius;
             sc.radius = radius;
         }
-        __syncthreads();
+        nleft = __shfl_sync(FULL, nleft, 0);
+        nIds = __shfl_sync(FULL, nIds, 0);
+        __syncwarp();
         {
             // per-inlier squared point-to-axis distance error, using the UNPROJECTED centroids (:199-218)
             const double P1[3] = {sc.center[0], sc.center[1], sc.center[2]};
@@ -465,7 +447,7 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
             const double D[3] = {P2[0] - P1[0], P2[1] - P1[1], P2[2] - P1[2]};
             const double P1P2 = sqrt(dot3(D, D));
             const double radius = sc.radius;
-            for (int j = t; j < m; j += T) {
+            for (int j = lane; j < m; j += 32) {
                 double v = 0.0;
                 if (best[j]) {
                     const int gi = s.list[j];
@@ -479,11 +461,11 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
             }
         }
         // plane refit over the segment's inlier cells (find_plane_segment_in_cylinder)
-        if (t == 0) plane_clear(sc.work2);
-        __syncthreads();
-        ordered_expand(sc.work2, cells, s.list, m, best);
-        __syncthreads();
-        if (t == 0) {
+        if (lane == 0) plane_clear(sc.work2);
+        __syncwarp();
+        ordered_expand(s, sc.work2, cells, s.list, m, best, lane);
+        int f = 0;
+        if (lane == 0) {
             double mse = 0.0;
             for (int j = 0; j < m; ++j)
                 if (best[j]) mse += s.val[j];
@@ -500,33 +482,32 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
             if (sc.work2.mse < mse) {
                 const int id = push_plane(s, planes, sc.work2);
                 assigned = -id;
-                sc.flag = id;   // > 0: label inliers as plane `id`
+                f = id;    // > 0: label inliers as plane `id`
             }
             else {
                 const int id = ++sc.n_cylinders;
                 assigned = id;
-                sc.flag = -id;  // < 0: label inliers as cylinder `id`
+                f = -id;   // < 0: label inliers as cylinder `id`
             }
             co.assigned[segId] = assigned;
             co.kept[segId] = 0;
         }
-        __syncthreads();
-        {
-            const int f = sc.flag;
-            for (int j = t; j < m; j += T)
-                if (best[j]) {
-                    if (f > 0)
-                        s.gplane[s.list[j]] = static_cast<short>(f);
-                    else if (f < 0)
-                        s.gcyl[s.list[j]] = static_cast<short>(-f);
-                }
-        }
-        __syncthreads();
+        f = __shfl_sync(FULL, f, 0);
+        __syncwarp();
+        for (int j = lane; j < m; j += 32)
+            if (best[j]) {
+                if (f > 0)
+                    s.gplane[s.list[j]] = static_cast<short>(f);
+                else if (f < 0)
+                    s.gcyl[s.list[j]] = static_cast<short>(-f);
+            }
+        __syncwarp();
         ++segId;
     }
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams prm, const SegmentBuffers buf)
+__global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams prm, const SegmentBuffers buf)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Nc = prm.hc * prm.vc, hc = prm.hc, vc = prm.vc, cs = prm.cell;
@@ -534,7 +515,7 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
     Smem s;
     carve(&s, smem_raw, Nc, nbins);
     Scalars& sc = *s.sc;
-    const int t = threadIdx.x;
+    const int lane = threadIdx.x;
     const int frame = blockIdx.x;
     const rs_cell_out* cells = buf.cells + size_t(frame) * Nc;
     rs_plane_out* planes = buf.planes + size_t(frame) * RS_MAX_PLANES;
@@ -542,16 +523,19 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
     int32_t* out_region_seg = buf.cyl_region_seg + size_t(frame) * Nc;
     const float* depth = buf.depth + size_t(frame) * prm.W * prm.H;
     double* boundary = buf.boundary_xyz + size_t(frame) * prm.max_boundary * 3;
+    double* pn = buf.scratch + size_t(frame) * Nc * 6;
+    double* pc = pn + size_t(Nc) * 3;
 
     // ---- load the cell graph, init_histogram (primitive_detection.cpp:239-265, histogram.hpp:35-62) ----
-    for (int i = t; i < nbins; i += T) s.hist[i] = 0;
-    if (t == 0) {
+    for (int i = lane; i < nbins; i += 32) s.hist[i] = 0;
+    for (int i = lane; i < 6 * MAX_ROWS; i += 32) s.U[i] = 0ull;   // the six bit planes are contiguous
+    if (lane == 0) {
         sc.n_planes = 0, sc.n_cyl_regions = 0, sc.n_cylinders = 0, sc.n_seeds = 0, sc.n_boundary = 0;
         sc.status = RS_OK, sc.uniform_cursor = 0;
     }
-    __syncthreads();
-    int myPlanar = 0;
-    for (int i = t; i < Nc; i += T) {
+    __syncwarp();
+    int nPlanar = 0;
+    for (int i = lane; i < Nc; i += 32) {
         const rs_cell_out& c = cells[i];
         s.cn[3 * i] = c.normal[0], s.cn[3 * i + 1] = c.normal[1], s.cn[3 * i + 2] = c.normal[2];
         s.cc[3 * i] = c.centroid[0], s.cc[3 * i + 1] = c.centroid[1], s.cc[3 * i + 2] = c.centroid[2];
@@ -559,13 +543,12 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
         s.cmse[i] = c.mse;
         s.tol[i] = c.tol;
         s.planar[i] = c.planar ? 1 : 0;
-        s.unassigned[i] = c.planar ? 1 : 0;
         s.gplane[i] = 0;
         s.gcyl[i] = 0;
         out_region_seg[i] = 0;
         int bin = -1;
         if (c.planar) {
-            ++myPlanar;
+            ++nPlanar;
             const double theta = acos(-c.normal[2]);
             const double phi = atan2(c.normal[0], c.normal[1]);
             const int xQ = static_cast<int>(floor((cs - 1) * (theta - 0.0) / (kPi - 0.0)));
@@ -573,71 +556,90 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
             if (xQ > 0) yQ = static_cast<int>(floor((cs - 1) * (phi - (-kPi)) / (kPi - (-kPi))));
             bin = yQ * cs + xQ;
             if (bin >= 0 && bin < nbins) atomicAdd(&s.hist[bin], 1);
+            const int y = i / hc, x = i - y * hc;
+            atomicOr(&s.U[y], 1ull << x);
         }
-        s.bins[i] = bin;
+        s.bins[i] = static_cast<short>(bin);
     }
-    const int nPlanar = block_sum_int(myPlanar, sc.iscr);
-    if (t == 0) sc.untried = nPlanar;
-    __syncthreads();
+    nPlanar = __reduce_add_sync(FULL, nPlanar);
+    __syncwarp();
+
+    // ---- merge edges of the cell graph, once per frame: bit x of E?[y] = can_be_merged(neighbour -> (y, x)) ----
+    for (int i = lane; i < Nc; i += 32) {
+        if (!s.planar[i]) continue;
+        const int y = i / hc, x = i - y * hc;
+        const double tolI = static_cast<double>(s.tol[i]);
+        const u64 bit = 1ull << x;
+        if (x > 0 && s.planar[i - 1] &&
+            plane_can_merge(s.cn + 3 * (i - 1), s.cd[i - 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
+            atomicOr(&s.EL[y], bit);
+        if (x < hc - 1 && s.planar[i + 1] &&
+            plane_can_merge(s.cn + 3 * (i + 1), s.cd[i + 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
+            atomicOr(&s.ER[y], bit);
+        if (y > 0 && s.planar[i - hc] &&
+            plane_can_merge(s.cn + 3 * (i - hc), s.cd[i - hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
+            atomicOr(&s.EU[y], bit);
+        if (y < vc - 1 && s.planar[i + hc] &&
+            plane_can_merge(s.cn + 3 * (i + hc), s.cd[i + hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
+            atomicOr(&s.ED[y], bit);
+    }
+    __syncwarp();
 
     const unsigned planeSeedCount = static_cast<unsigned>(0.8 / 100.0 * Nc);
     const unsigned minimumCellActivated = static_cast<unsigned>(0.65 / 100.0 * Nc);
 
     // ---- grow_planes_and_cylinders (primitive_detection.cpp:267-310) ----
+    int untried = nPlanar;
     int guard = 0;
-    while (sc.untried > 0) {
+    while (untried > 0) {
         // most frequent bin: strictly greatest count, lowest index on ties (histogram.hpp:69-84)
+        int bestBin;
         {
             double key = 1.0;  // -count as key so that the minimum is the fullest bin
             int idx = 0x7fffffff;
-            for (int i = t; i < nbins; i += T) {
+            for (int i = lane; i < nbins; i += 32) {
                 const int h = s.hist[i];
                 if (h > 0) {
                     const double k = -static_cast<double>(h);
                     if (k < key || (k == key && i < idx)) key = k, idx = i;
                 }
             }
-            block_min_key(key, idx, sc.dscr, sc.iscr);
-            if (t == 0) sc.best_bin = (key < 0.0) ? idx : -1;
+            warp_min_key(key, idx);
+            bestBin = (key < 0.0) ? idx : -1;
         }
-        __syncthreads();
-        const int bestBin = sc.best_bin;
         // candidates of that bin, min-MSE seed (first strictly smallest; stop at MSE <= 0) (:286-298)
+        int seed, candCount = 0;
         {
             double key = DBL_MAX;
             int idx = 0x7fffffff;
-            int cnt = 0;
             if (bestBin >= 0) {
-                for (int i = t; i < Nc; i += T)
+                for (int i = lane; i < Nc; i += 32)
                     if (s.bins[i] == bestBin) {
-                        ++cnt;
+                        ++candCount;
                         const double mse = s.cmse[i];
                         const double k = (mse <= 0.0) ? 0.0 : mse;
                         if (k < key || (k == key && i < idx)) key = k, idx = i;
                     }
             }
-            cnt = block_sum_int(cnt, sc.iscr2);
-            block_min_key(key, idx, sc.dscr, sc.iscr);
-            if (t == 0) {
-                sc.cand_count = cnt;
-                sc.seed = (key < DBL_MAX) ? idx : -1;
-            }
+            candCount = __reduce_add_sync(FULL, candCount);
+            warp_min_key(key, idx);
+            seed = (key < DBL_MAX) ? idx : -1;
         }
-        __syncthreads();
-        if (static_cast<unsigned>(sc.cand_count) < planeSeedCount) break;
-        if (sc.seed < 0) break;
-        const int seed = sc.seed;
-        if (t == 0) sc.n_seeds++;
+        if (static_cast<unsigned>(candCount) < planeSeedCount) break;
+        if (seed < 0) break;
+        if (lane == 0) sc.n_seeds++;
 
         // ---- grow_plane_segment_at_seed (:312-389) ----
         // A non-planar seed changes no state in the reference (:318-322), which would then spin forever; it is
         // unreachable (only planar cells carry a bin id). Leave the loop instead of hanging the GPU.
         if (!s.planar[seed] || ++guard > 4 * Nc + nbins) {
-            if (t == 0) sc.status = RS_ERR_CAPACITY;
+            if (lane == 0) sc.status = RS_ERR_CAPACITY;
             break;
         }
-        for (int i = t; i < Nc; i += T) s.activated[i] = 0;
-        if (t == 0) {
+        for (int r = lane; r < MAX_ROWS; r += 32) s.ACT[r] = 0ull;
+        const int seedY = seed / hc, seedX = seed - seedY * hc;
+        int flag = 0;
+        if (lane == 0) {
             // newPlaneSegment = copy of the seed (normal re-normalised by the copy ctor)
             PlaneModel& w = sc.work;
             const rs_cell_out& c = cells[seed];
@@ -648,111 +650,102 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
             w.d = c.d, w.mse = c.mse, w.score = c.score;
             normalize3(w.n);
             // region_growing's first test: new segment -> seed cell (:795-803)
-            sc.flag = 0;
-            if (s.unassigned[seed] &&
+            if (((s.U[seedY] >> seedX) & 1ull) &&
                 plane_can_merge(w.n, w.d, s.cn + 3 * seed, s.cc + 3 * seed, static_cast<double>(s.tol[seed]), prm.cos_merge))
-                sc.flag = 1;
+                flag = 1;
         }
-        __syncthreads();
-        if (sc.flag) {
-            if (t == 0) s.activated[seed] = 1;
-            __syncthreads();
-            // frontier BFS: a cell joins when some activated 4-neighbour u satisfies can_be_merged(u, cell, tol[cell])
+        flag = __shfl_sync(FULL, flag, 0);
+        __syncwarp();
+        if (flag) {
+            if (lane == 0) s.ACT[seedY] = 1ull << seedX;
+            __syncwarp();
+            // bit-parallel flood fill: a cell joins when some activated 4-neighbour u has can_be_merged(u -> cell)
             while (true) {
-                int changed = 0;
-                for (int i = t; i < Nc; i += T) {
-                    if (!s.unassigned[i] || s.activated[i]) continue;
-                    const int y = i / hc, x = i - y * hc;
-                    const double tolI = static_cast<double>(s.tol[i]);
-                    bool join = false;
-                    if (x > 0 && s.activated[i - 1] &&
-                        plane_can_merge(s.cn + 3 * (i - 1), s.cd[i - 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-                        join = true;
-                    if (!join && x < hc - 1 && s.activated[i + 1] &&
-                        plane_can_merge(s.cn + 3 * (i + 1), s.cd[i + 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-                        join = true;
-                    if (!join && y > 0 && s.activated[i - hc] &&
-                        plane_can_merge(s.cn + 3 * (i - hc), s.cd[i - hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-                        join = true;
-                    if (!join && y < vc - 1 && s.activated[i + hc] &&
-                        plane_can_merge(s.cn + 3 * (i + hc), s.cd[i + hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-                        join = true;
-                    if (join) {
-                        s.m0[i] = 1;
-                        changed = 1;
+                bool changed = false;
+                for (int r = lane; r < vc; r += 32) {
+                    const u64 a = s.ACT[r];
+                    const u64 open = s.U[r];
+                    const u64 up = r > 0 ? s.ACT[r - 1] : 0ull;
+                    const u64 dn = r < vc - 1 ? s.ACT[r + 1] : 0ull;
+                    const u64 el = s.EL[r], er = s.ER[r];
+                    u64 na = a | (open & ((up & s.EU[r]) | (dn & s.ED[r])));
+                    while (true) {
+                        const u64 nb = na | (open & (((na << 1) & el) | ((na >> 1) & er)));
+                        if (nb == na) break;
+                        na = nb;
                     }
-                    else
-                        s.m0[i] = 0;
+                    if (na != a) {
+                        s.ACT[r] = na;
+                        changed = true;
+                    }
                 }
-                changed = __syncthreads_or(changed);
-                if (!changed) break;
-                for (int i = t; i < Nc; i += T)
-                    if (s.unassigned[i] && !s.activated[i] && s.m0[i]) s.activated[i] = 1;
-                __syncthreads();
+                __syncwarp();
+                if (!__any_sync(FULL, changed)) break;
             }
         }
         // ordered list of the activated cells (index order)
+        int cnt;
         {
             int base = 0;
-            for (int c0 = 0; c0 < Nc; c0 += T) {
-                const int i = c0 + t;
-                const bool f = (i < Nc) && s.activated[i];
+            for (int r0 = 0; r0 < vc; r0 += 32) {
+                const int r = r0 + lane;
+                u64 bits = r < vc ? s.ACT[r] : 0ull;
                 int tot;
-                const int pos = block_scan_flag(f, sc.iscr, &tot);
-                if (f) s.list[base + pos] = i;
+                int pos = base + warp_excl_scan(__popcll(bits), lane, &tot);
+                while (bits) {
+                    const int x = __ffsll(static_cast<long long>(bits)) - 1;
+                    bits &= bits - 1;
+                    s.list[pos++] = static_cast<short>(r * hc + x);
+                }
                 base += tot;
             }
-            if (t == 0) sc.cnt = base;
+            cnt = base;
         }
-        __syncthreads();
-        const int cnt = sc.cnt;
+        __syncwarp();
         // merge activated cells & remove them from the histogram (:343-360)
-        ordered_expand(sc.work, cells, s.list, cnt, nullptr);
-        for (int j = t; j < cnt; j += T) {
-            const int i = s.list[j];
-            hist_remove_atomic(s, i, nbins);
-            s.unassigned[i] = 0;
-        }
-        __syncthreads();
-        if (t == 0) sc.untried -= cnt;
+        ordered_expand(s, sc.work, cells, s.list, cnt, nullptr, lane);
+        for (int j = lane; j < cnt; j += 32) hist_remove_atomic(s, s.list[j], nbins);
+        for (int r = lane; r < vc; r += 32) s.U[r] &= ~s.ACT[r];
+        __syncwarp();
+        untried -= cnt;
         if (cnt == 0 || static_cast<unsigned>(cnt) < minimumCellActivated) {
-            if (t == 0) {
+            if (lane == 0) {
                 // _histogram.remove_point(seedId)
                 const int b = s.bins[seed];
                 if (b >= 0 && b < nbins && s.hist[b] != 0) s.hist[b] -= 1;
                 s.bins[seed] = 1;
             }
-            __syncthreads();
+            __syncwarp();
             continue;
         }
-        if (t == 0) {
+        int f = 0;
+        if (lane == 0) {
             plane_fit(sc.work);
-            sc.flag = 0;
             if (sc.work.planar) {
                 if (sc.work.score > 100)
-                    sc.flag = push_plane(s, planes, sc.work);  // add_plane_segment_to_features (:391-411)
+                    f = push_plane(s, planes, sc.work);  // add_plane_segment_to_features (:391-411)
                 else if (cnt > 5)
-                    sc.flag = -1;
+                    f = -1;
             }
         }
-        __syncthreads();
-        const int f = sc.flag;
+        f = __shfl_sync(FULL, f, 0);
+        __syncwarp();
         if (f > 0) {
-            for (int j = t; j < cnt; j += T) s.gplane[s.list[j]] = static_cast<short>(f);
+            for (int j = lane; j < cnt; j += 32) s.gplane[s.list[j]] = static_cast<short>(f);
         }
         else if (f < 0) {
-            cylinder_fitting(s, prm, cells, planes, cyls, out_region_seg, cnt, Nc);
+            cylinder_fitting(s, prm, cells, planes, cyls, out_region_seg, pn, pc, cnt, Nc, lane);
         }
-        __syncthreads();
+        __syncwarp();
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- merge_planes (:503-560) with get_connected_components_matrix (:736-776) ----
     const int P = sc.n_planes;
     constexpr int CW = RS_MAX_PLANES / 32;
-    for (int i = t; i < RS_MAX_PLANES * CW; i += T) s.conn[i] = 0;
-    __syncthreads();
-    for (int i = t; i < Nc; i += T) {
+    for (int i = lane; i < RS_MAX_PLANES * CW; i += 32) s.conn[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < Nc; i += 32) {
         const int row = i / hc, col = i - row * hc;
         if (row >= vc - 1 || col >= hc - 1) continue;  // last row / column are never scan origins
         const int id = s.gplane[i];
@@ -767,8 +760,8 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
             atomicOr(&s.conn[(bl - 1) * CW + ((id - 1) >> 5)], 1u << ((id - 1) & 31));
         }
     }
-    __syncthreads();
-    if (t == 0) {
+    __syncwarp();
+    if (lane == 0) {
         for (int row = 0; row < P; ++row) {
             bool expanded = false;
             const int planeId = s.plabel[row];
@@ -801,41 +794,43 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- final labels + per-plane record tail ----
-    for (int i = t; i < Nc; i += T) {
+    for (int i = lane; i < Nc; i += 32) {
         const int id = s.gplane[i];
         int lab = 0;
         if (id > 0) {
             const int root = s.plabel[id - 1];
             if (s.plabel[root] == root && s.pplanar[root]) lab = root + 1;
         }
-        s.plab[i] = lab;
+        s.plab[i] = static_cast<short>(lab);
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- boundary points per final plane (compute_plane_segment_boundary, :650-703) ----
     const unsigned pixelPerCellSide = static_cast<unsigned>(sqrtf(static_cast<float>(cs * cs)));
     int nFinal = 0;
+    int nBoundary = 0;   // warp-uniform running count
+    int status = RS_OK;
     for (int k = 0; k < P; ++k) {
         const bool isFinal = (s.plabel[k] == k) && s.pplanar[k];
-        if (t == 0) {
+        if (lane == 0) {
             planes[k].merge_label = s.plabel[k];
             planes[k].is_final = isFinal ? 1 : 0;
             planes[k].n_boundary = 0;
-            planes[k].boundary_offset = sc.n_boundary;
+            planes[k].boundary_offset = nBoundary;
         }
         if (!isFinal) continue;
         ++nFinal;
-        for (int i = t; i < Nc; i += T) s.m0[i] = (s.plab[i] == k + 1) ? 1 : 0;
-        __syncthreads();
+        for (int i = lane; i < Nc; i += 32) s.m0[i] = (s.plab[i] == k + 1) ? 1 : 0;
+        __syncwarp();
         const double maxBoundaryDistance = 3 * sqrt(planes[k].mse);
         const double n0 = s.pln[3 * k], n1 = s.pln[3 * k + 1], n2 = s.pln[3 * k + 2], dd = s.pld[k];
-        int base = sc.n_boundary;
+        int base = nBoundary;
         const int start = base;
-        for (int c0 = 0; c0 < Nc; c0 += T) {
-            const int i = c0 + t;
+        for (int c0 = 0; c0 < Nc; c0 += 32) {
+            const int i = c0 + lane;
             bool keep = false;
             double px = 0, py = 0, pz = 0;
             if (i < Nc) {
@@ -854,80 +849,75 @@ __global__ void __launch_bounds__(T, 1) cape_segment_kernel(const SegmentParams 
                     }
                 }
             }
-            int tot;
-            const int pos = block_scan_flag(keep, sc.iscr, &tot);
+            const unsigned m = __ballot_sync(FULL, keep);
             if (keep) {
-                const int o = base + pos;
+                const int o = base + __popc(m & ((1u << lane) - 1u));
                 if (o < prm.max_boundary) {
                     boundary[3 * o] = px, boundary[3 * o + 1] = py, boundary[3 * o + 2] = pz;
                 }
             }
-            base += tot;
+            base += __popc(m);
         }
-        __syncthreads();
-        if (t == 0) {
-            if (base > prm.max_boundary) {
-                sc.status = RS_ERR_CAPACITY;
-                base = prm.max_boundary;
-            }
-            planes[k].n_boundary = base - start;
-            sc.n_boundary = base;
+        if (base > prm.max_boundary) {
+            status = RS_ERR_CAPACITY;
+            base = prm.max_boundary;
         }
-        __syncthreads();
+        if (lane == 0) planes[k].n_boundary = base - start;
+        nBoundary = base;
+        __syncwarp();
     }
 
     // ---- cylinders: opening test of add_cylinders_to_primitives (:705-734) ----
-    for (int ci = 1; ci <= sc.n_cylinders; ++ci) {
-        for (int i = t; i < Nc; i += T) s.m0[i] = (s.gcyl[i] == ci) ? 1 : 0;
-        __syncthreads();
-        for (int i = t; i < Nc; i += T) s.m1[i] = morph_at(s.m0, i / hc, i % hc, vc, hc, false, true, false);
-        __syncthreads();
-        for (int i = t; i < Nc; i += T) s.m0[i] = morph_at(s.m1, i / hc, i % hc, vc, hc, true, true, false);
-        __syncthreads();
+    const int nCyl = sc.n_cylinders;
+    for (int ci = 1; ci <= nCyl; ++ci) {
+        for (int i = lane; i < Nc; i += 32) s.m0[i] = (s.gcyl[i] == ci) ? 1 : 0;
+        __syncwarp();
+        for (int i = lane; i < Nc; i += 32) s.m1[i] = morph_at(s.m0, i / hc, i % hc, vc, hc, false, true, false);
+        __syncwarp();
+        for (int i = lane; i < Nc; i += 32) s.m0[i] = morph_at(s.m1, i / hc, i % hc, vc, hc, true, true, false);
+        __syncwarp();
         int mn = 255, mx = 0;
-        for (int i = t; i < Nc; i += T) {
+        for (int i = lane; i < Nc; i += 32) {
             const int v = morph_at(s.m0, i / hc, i % hc, vc, hc, true, true, false);
             mn = min(mn, v);
             mx = max(mx, v);
         }
-        mn = __reduce_min_sync(0xffffffffu, mn);
-        mx = __reduce_max_sync(0xffffffffu, mx);
-        __syncthreads();
-        if ((t & 31) == 0) sc.iscr[t >> 5] = mn, sc.iscr2[t >> 5] = mx;
-        __syncthreads();
-        if (t == 0) {
-            for (int w = 1; w < NW; ++w) mn = min(mn, sc.iscr[w]), mx = max(mx, sc.iscr2[w]);
+        mn = __reduce_min_sync(FULL, mn);
+        mx = __reduce_max_sync(FULL, mx);
+        if (lane == 0) {
             const int kept = !(mx <= 0 || mn >= mx);
             for (int r = 0; r < sc.n_cyl_regions; ++r)
                 for (int sg = 0; sg < cyls[r].n_segments; ++sg)
                     if (cyls[r].assigned[sg] == ci) cyls[r].kept[sg] = kept;
         }
-        __syncthreads();
+        __syncwarp();
     }
 
     // ---- write the label grids and the frame info ----
     int32_t* o_grid = buf.plane_grid + size_t(frame) * Nc;
     int32_t* o_lab = buf.plane_labels + size_t(frame) * Nc;
     int32_t* o_cyl = buf.cyl_labels + size_t(frame) * Nc;
-    for (int i = t; i < Nc; i += T) {
+    for (int i = lane; i < Nc; i += 32) {
         o_grid[i] = s.gplane[i];
         o_lab[i] = s.plab[i];
         o_cyl[i] = s.gcyl[i];
     }
-    if (t == 0) {
+    if (lane == 0) {
         rs_cape_frame_info& info = buf.info[frame];
-        info.status = sc.status;
+        info.status = sc.status != RS_OK ? sc.status : status;
         info.n_planar_cells = nPlanar;
         info.n_seeds = sc.n_seeds;
         info.n_planes = P;
         info.n_final_planes = nFinal;
         info.n_cyl_regions = sc.n_cyl_regions;
         info.n_cylinders = sc.n_cylinders;
-        info.n_boundary = sc.n_boundary;
+        info.n_boundary = nBoundary;
     }
 }
 
 }  // namespace
+
+size_t cape_segment_scratch_doubles_per_frame(int n_cells) { return size_t(n_cells) * 6; }
 
 int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream)
 {
@@ -937,8 +927,8 @@ int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cud
         set_last_error("cape_segment: the cell grid does not fit in shared memory (" + std::to_string(smem) + " B > 227 KB)");
         return RS_ERR_INVALID_ARG;
     }
-    if (Nc > 32767) {
-        set_last_error("cape_segment: too many cells");
+    if (prm.hc > MAX_ROWS || prm.vc > MAX_ROWS || Nc > 32767 || prm.cell * prm.cell > 32767) {
+        set_last_error("cape_segment: at most 64 x 64 cells (one 64-bit word per cell row and merge direction)");
         return RS_ERR_INVALID_ARG;
     }
     static size_t configured = 0;
@@ -949,7 +939,7 @@ int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cud
     // the plane/cylinder record arrays are zeroed so that unused entries read as empty
     RS_CUDA_CHECK(cudaMemsetAsync(buf.planes, 0, sizeof(rs_plane_out) * size_t(prm.batch) * RS_MAX_PLANES, stream));
     RS_CUDA_CHECK(cudaMemsetAsync(buf.cyls, 0, sizeof(rs_cyl_out) * size_t(prm.batch) * RS_MAX_CYL_REGIONS, stream));
-    cape_segment_kernel<<<prm.batch, T, smem, stream>>>(prm, buf);
+    cape_segment_kernel<<<prm.batch, 32, smem, stream>>>(prm, buf);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }
