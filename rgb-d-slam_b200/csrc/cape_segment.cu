@@ -28,7 +28,7 @@ namespace rs {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int STAGE_CELLS = 64;   // cells gathered per round of an ordered sum
+constexpr int STAGE_CELLS = 128;  // cells gathered per round of an ordered sum
 constexpr int MAX_ROWS = 64;      // cell rows / columns the bit planes can hold
 typedef unsigned long long u64;
 
@@ -53,6 +53,7 @@ struct Smem {
     u64 *U, *ACT, *EL, *ER, *EU, *ED;  // [MAX_ROWS] bit planes: unassigned, activated, merge edges from the 4 neighbours
     Scalars* sc;
     float* tol;    // [Nc]
+    float* cz;     // [Nc] depth of the cell's centre pixel (boundary points)
     int* hist;     // [cs*cs]
     int* plabel;   // [RS_MAX_PLANES] merge labels
     int* pplanar;  // [RS_MAX_PLANES]
@@ -63,7 +64,7 @@ struct Smem {
     short* plab;   // [Nc] final merged labels
     short* gplane; // [Nc] _gridPlaneSegmentMap
     short* gcyl;   // [Nc] _gridCylinderSegMap
-    unsigned char *planar, *mleft, *inlA, *inlB, *m0, *m1;
+    unsigned char *planar, *mleft, *inlA, *inlB;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -88,22 +89,23 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int Nc, in
     u64* planes64 = reinterpret_cast<u64*>(take(sizeof(u64) * 6 * MAX_ROWS));
     Scalars* sc = reinterpret_cast<Scalars*>(take(sizeof(Scalars)));
     float* tol = reinterpret_cast<float*>(take(sizeof(float) * Nc));
+    float* cz = reinterpret_cast<float*>(take(sizeof(float) * Nc));
     int* hist = reinterpret_cast<int*>(take(sizeof(int) * nbins));
     int* plabel = reinterpret_cast<int*>(take(sizeof(int) * RS_MAX_PLANES));
     int* pplanar = reinterpret_cast<int*>(take(sizeof(int) * RS_MAX_PLANES));
     unsigned* conn = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * RS_MAX_PLANES * (RS_MAX_PLANES / 32)));
     short* sh[6];
     for (int i = 0; i < 6; ++i) sh[i] = reinterpret_cast<short*>(take(sizeof(short) * Nc));
-    unsigned char* u8[6];
-    for (int i = 0; i < 6; ++i) u8[i] = take(size_t(Nc));
+    unsigned char* u8[4];
+    for (int i = 0; i < 4; ++i) u8[i] = take(size_t(Nc));
     if (s) {
         s->cn = cn, s->cc = cc, s->cd = cd, s->cmse = cmse, s->val = val, s->stage = stage;
-        s->pln = pln, s->plc = plc, s->pld = pld, s->sc = sc, s->tol = tol, s->hist = hist;
+        s->pln = pln, s->plc = plc, s->pld = pld, s->sc = sc, s->tol = tol, s->cz = cz, s->hist = hist;
         s->U = planes64, s->ACT = planes64 + MAX_ROWS, s->EL = planes64 + 2 * MAX_ROWS, s->ER = planes64 + 3 * MAX_ROWS;
         s->EU = planes64 + 4 * MAX_ROWS, s->ED = planes64 + 5 * MAX_ROWS;
         s->plabel = plabel, s->pplanar = pplanar, s->conn = conn;
         s->bins = sh[0], s->list = sh[1], s->ids = sh[2], s->plab = sh[3], s->gplane = sh[4], s->gcyl = sh[5];
-        s->planar = u8[0], s->mleft = u8[1], s->inlA = u8[2], s->inlB = u8[3], s->m0 = u8[4], s->m1 = u8[5];
+        s->planar = u8[0], s->mleft = u8[1], s->inlA = u8[2], s->inlB = u8[3];
     }
     return o;
 }
@@ -209,27 +211,6 @@ __device__ void ordered_expand(const Smem& s, PlaneModel& dst, const rs_cell_out
     if (lane < 9) dst.S[lane] = acc;
     if (lane == 9) dst.count = static_cast<int>(acc);
     __syncwarp();
-}
-
-// cv::erode / cv::dilate on the cell grid, 3x3 kernels, one output cell.
-__device__ __forceinline__ unsigned char morph_at(const unsigned char* m, int row, int col, int vc, int hc, bool erode,
-                                                  bool cross, bool borderZero)
-{
-    unsigned char v = erode ? 255 : 0;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            if (cross && dx != 0 && dy != 0) continue;
-            const int yy = row + dy, xx = col + dx;
-            unsigned char nv;
-            if (yy < 0 || yy >= vc || xx < 0 || xx >= hc) {
-                if (!borderZero) continue;
-                nv = 0;
-            }
-            else
-                nv = m[yy * hc + xx];
-            v = erode ? (nv < v ? nv : v) : (nv > v ? nv : v);
-        }
-    return v;
 }
 
 // ---- cylinder branch (cylinder_segment.cpp:35-322 + primitive_detection.cpp:413-501) ------------
@@ -534,6 +515,14 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
         sc.status = RS_OK, sc.uniform_cursor = 0;
     }
     __syncwarp();
+    const unsigned pixelPerCellSide = static_cast<unsigned>(sqrtf(static_cast<float>(cs * cs)));
+    // centre pixel of every cell (the only depth the boundary step reads): fetched here, all loads in flight at once
+    for (int i = lane; i < Nc; i += 32) {
+        const int row = i / hc, col = i - row * hc;
+        const int centerX = static_cast<int>(col * pixelPerCellSide + pixelPerCellSide / 2);
+        const int centerY = static_cast<int>(row * pixelPerCellSide + pixelPerCellSide / 2);
+        s.cz[i] = __ldg(depth + size_t(centerY) * prm.W + centerX);
+    }
     int nPlanar = 0;
     for (int i = lane; i < Nc; i += 32) {
         const rs_cell_out& c = cells[i];
@@ -556,8 +545,6 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
             if (xQ > 0) yQ = static_cast<int>(floor((cs - 1) * (phi - (-kPi)) / (kPi - (-kPi))));
             bin = yQ * cs + xQ;
             if (bin >= 0 && bin < nbins) atomicAdd(&s.hist[bin], 1);
-            const int y = i / hc, x = i - y * hc;
-            atomicOr(&s.U[y], 1ull << x);
         }
         s.bins[i] = static_cast<short>(bin);
     }
@@ -565,23 +552,34 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
     __syncwarp();
 
     // ---- merge edges of the cell graph, once per frame: bit x of E?[y] = can_be_merged(neighbour -> (y, x)) ----
-    for (int i = lane; i < Nc; i += 32) {
-        if (!s.planar[i]) continue;
-        const int y = i / hc, x = i - y * hc;
-        const double tolI = static_cast<double>(s.tol[i]);
-        const u64 bit = 1ull << x;
-        if (x > 0 && s.planar[i - 1] &&
-            plane_can_merge(s.cn + 3 * (i - 1), s.cd[i - 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-            atomicOr(&s.EL[y], bit);
-        if (x < hc - 1 && s.planar[i + 1] &&
-            plane_can_merge(s.cn + 3 * (i + 1), s.cd[i + 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-            atomicOr(&s.ER[y], bit);
-        if (y > 0 && s.planar[i - hc] &&
-            plane_can_merge(s.cn + 3 * (i - hc), s.cd[i - hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-            atomicOr(&s.EU[y], bit);
-        if (y < vc - 1 && s.planar[i + hc] &&
-            plane_can_merge(s.cn + 3 * (i + hc), s.cd[i + hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge))
-            atomicOr(&s.ED[y], bit);
+    // one row at a time, lane = column (two halves when the grid is wider than 32 cells): the words come out of ballots
+    for (int y = 0; y < vc; ++y) {
+        u64 wU = 0, wL = 0, wR = 0, wUp = 0, wDn = 0;
+        for (int x0 = 0; x0 < hc; x0 += 32) {
+            const int x = x0 + lane;
+            bool pl = false, eL = false, eR = false, eU = false, eD = false;
+            if (x < hc) {
+                const int i = y * hc + x;
+                pl = s.planar[i] != 0;
+                if (pl) {
+                    const double tolI = static_cast<double>(s.tol[i]);
+                    eL = x > 0 && s.planar[i - 1] &&
+                         plane_can_merge(s.cn + 3 * (i - 1), s.cd[i - 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge);
+                    eR = x < hc - 1 && s.planar[i + 1] &&
+                         plane_can_merge(s.cn + 3 * (i + 1), s.cd[i + 1], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge);
+                    eU = y > 0 && s.planar[i - hc] &&
+                         plane_can_merge(s.cn + 3 * (i - hc), s.cd[i - hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge);
+                    eD = y < vc - 1 && s.planar[i + hc] &&
+                         plane_can_merge(s.cn + 3 * (i + hc), s.cd[i + hc], s.cn + 3 * i, s.cc + 3 * i, tolI, prm.cos_merge);
+                }
+            }
+            wU |= static_cast<u64>(__ballot_sync(FULL, pl)) << x0;
+            wL |= static_cast<u64>(__ballot_sync(FULL, eL)) << x0;
+            wR |= static_cast<u64>(__ballot_sync(FULL, eR)) << x0;
+            wUp |= static_cast<u64>(__ballot_sync(FULL, eU)) << x0;
+            wDn |= static_cast<u64>(__ballot_sync(FULL, eD)) << x0;
+        }
+        if (lane == 0) s.U[y] = wU, s.EL[y] = wL, s.ER[y] = wR, s.EU[y] = wUp, s.ED[y] = wDn;
     }
     __syncwarp();
 
@@ -809,7 +807,10 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
     __syncwarp();
 
     // ---- boundary points per final plane (compute_plane_segment_boundary, :650-703) ----
-    const unsigned pixelPerCellSide = static_cast<unsigned>(sqrtf(static_cast<float>(cs * cs)));
+    // mask rows as 64-bit words (ACT is free now): boundary = dilate3x3(mask) & ~erode_cross(mask), erosion with a zero
+    // border, dilation ignoring it - a handful of shifts per row instead of 14 taps per cell.
+    const u64 rowMask = hc >= 64 ? ~0ull : ((1ull << hc) - 1ull);
+    u64* MK = s.ACT;   // [MAX_ROWS] plane mask
     int nFinal = 0;
     int nBoundary = 0;   // warp-uniform running count
     int status = RS_OK;
@@ -823,40 +824,54 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
         }
         if (!isFinal) continue;
         ++nFinal;
-        for (int i = lane; i < Nc; i += 32) s.m0[i] = (s.plab[i] == k + 1) ? 1 : 0;
+        for (int y = 0; y < vc; ++y) {
+            u64 w = 0;
+            for (int x0 = 0; x0 < hc; x0 += 32) {
+                const int x = x0 + lane;
+                w |= static_cast<u64>(__ballot_sync(FULL, x < hc && s.plab[y * hc + x] == k + 1)) << x0;
+            }
+            if (lane == 0) MK[y] = w;
+        }
         __syncwarp();
         const double maxBoundaryDistance = 3 * sqrt(planes[k].mse);
         const double n0 = s.pln[3 * k], n1 = s.pln[3 * k + 1], n2 = s.pln[3 * k + 2], dd = s.pld[k];
+        const int start = nBoundary;
         int base = nBoundary;
-        const int start = base;
-        for (int c0 = 0; c0 < Nc; c0 += 32) {
-            const int i = c0 + lane;
-            bool keep = false;
-            double px = 0, py = 0, pz = 0;
-            if (i < Nc) {
-                const int row = i / hc, col = i - row * hc;
-                const int er = morph_at(s.m0, row, col, vc, hc, true, true, true);
-                const int di = morph_at(s.m0, row, col, vc, hc, false, false, false);
-                if (di - er > 0) {
-                    const int centerX = static_cast<int>(col * pixelPerCellSide + pixelPerCellSide / 2);
-                    const int centerY = static_cast<int>(row * pixelPerCellSide + pixelPerCellSide / 2);
-                    const double z = static_cast<double>(depth[size_t(centerY) * prm.W + centerX]);
+        for (int r0 = 0; r0 < vc; r0 += 32) {
+            const int r = r0 + lane;
+            u64 keepBits = 0;
+            if (r < vc) {
+                const u64 m = MK[r];
+                const u64 up = r > 0 ? MK[r - 1] : 0ull, dn = r < vc - 1 ? MK[r + 1] : 0ull;
+                const u64 er = m & (m << 1) & (m >> 1) & up & dn;
+                const u64 di = ((m | (m << 1) | (m >> 1)) | (up | (up << 1) | (up >> 1)) | (dn | (dn << 1) | (dn >> 1))) & rowMask;
+                u64 bits = di & ~er;
+                while (bits) {
+                    const int x = __ffsll(static_cast<long long>(bits)) - 1;
+                    bits &= bits - 1;
+                    const double z = static_cast<double>(s.cz[r * hc + x]);
                     if (z > 0) {
-                        px = z * prm.kx[centerX];
-                        py = z * prm.ky[centerY];
-                        pz = z;
-                        if (fabs(((n0 * px + n1 * py) + n2 * pz) + dd) < maxBoundaryDistance) keep = true;
+                        const int centerX = static_cast<int>(x * pixelPerCellSide + pixelPerCellSide / 2);
+                        const int centerY = static_cast<int>(r * pixelPerCellSide + pixelPerCellSide / 2);
+                        const double px = z * prm.kx[centerX], py = z * prm.ky[centerY];
+                        if (fabs(((n0 * px + n1 * py) + n2 * z) + dd) < maxBoundaryDistance) keepBits |= 1ull << x;
                     }
                 }
             }
-            const unsigned m = __ballot_sync(FULL, keep);
-            if (keep) {
-                const int o = base + __popc(m & ((1u << lane) - 1u));
+            int tot;
+            int o = base + warp_excl_scan(__popcll(keepBits), lane, &tot);
+            while (keepBits) {
+                const int x = __ffsll(static_cast<long long>(keepBits)) - 1;
+                keepBits &= keepBits - 1;
                 if (o < prm.max_boundary) {
-                    boundary[3 * o] = px, boundary[3 * o + 1] = py, boundary[3 * o + 2] = pz;
+                    const double z = static_cast<double>(s.cz[r * hc + x]);
+                    const int centerX = static_cast<int>(x * pixelPerCellSide + pixelPerCellSide / 2);
+                    const int centerY = static_cast<int>(r * pixelPerCellSide + pixelPerCellSide / 2);
+                    boundary[3 * o] = z * prm.kx[centerX], boundary[3 * o + 1] = z * prm.ky[centerY], boundary[3 * o + 2] = z;
                 }
+                ++o;
             }
-            base += __popc(m);
+            base += tot;
         }
         if (base > prm.max_boundary) {
             status = RS_ERR_CAPACITY;
@@ -867,25 +882,46 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
         __syncwarp();
     }
 
-    // ---- cylinders: opening test of add_cylinders_to_primitives (:705-734) ----
+    // ---- cylinders: opening test of add_cylinders_to_primitives (:705-734): dilate, erode, erode with the cross
+    // kernel, borders ignored (taps outside the grid do not contribute) ----
     const int nCyl = sc.n_cylinders;
     for (int ci = 1; ci <= nCyl; ++ci) {
-        for (int i = lane; i < Nc; i += 32) s.m0[i] = (s.gcyl[i] == ci) ? 1 : 0;
-        __syncwarp();
-        for (int i = lane; i < Nc; i += 32) s.m1[i] = morph_at(s.m0, i / hc, i % hc, vc, hc, false, true, false);
-        __syncwarp();
-        for (int i = lane; i < Nc; i += 32) s.m0[i] = morph_at(s.m1, i / hc, i % hc, vc, hc, true, true, false);
-        __syncwarp();
-        int mn = 255, mx = 0;
-        for (int i = lane; i < Nc; i += 32) {
-            const int v = morph_at(s.m0, i / hc, i % hc, vc, hc, true, true, false);
-            mn = min(mn, v);
-            mx = max(mx, v);
+        u64* A = s.ACT;
+        u64* Bm = s.EL;
+        for (int y = 0; y < vc; ++y) {
+            u64 w = 0;
+            for (int x0 = 0; x0 < hc; x0 += 32) {
+                const int x = x0 + lane;
+                w |= static_cast<u64>(__ballot_sync(FULL, x < hc && s.gcyl[y * hc + x] == ci)) << x0;
+            }
+            if (lane == 0) A[y] = w;
         }
-        mn = __reduce_min_sync(FULL, mn);
-        mx = __reduce_max_sync(FULL, mx);
+        __syncwarp();
+        const u64 first = 1ull, last = 1ull << (hc - 1);
+        for (int r = lane; r < vc; r += 32) {   // dilate
+            const u64 m = A[r];
+            Bm[r] = (m | (m << 1) | (m >> 1) | (r > 0 ? A[r - 1] : 0ull) | (r < vc - 1 ? A[r + 1] : 0ull)) & rowMask;
+        }
+        __syncwarp();
+        for (int pass = 0; pass < 2; ++pass) {  // erode twice: Bm -> A -> Bm
+            const u64* src = pass == 0 ? Bm : A;
+            u64* dst = pass == 0 ? A : Bm;
+            for (int r = lane; r < vc; r += 32) {
+                const u64 m = src[r];
+                dst[r] = m & ((m << 1) | first) & ((m >> 1) | last) & (r > 0 ? src[r - 1] : ~0ull) &
+                         (r < vc - 1 ? src[r + 1] : ~0ull) & rowMask;
+            }
+            __syncwarp();
+        }
+        bool anySet = false, anyClear = false;
+        for (int r = lane; r < vc; r += 32) {
+            anySet = anySet || Bm[r] != 0ull;
+            anyClear = anyClear || Bm[r] != rowMask;
+        }
+        anySet = __any_sync(FULL, anySet);
+        anyClear = __any_sync(FULL, anyClear);
         if (lane == 0) {
-            const int kept = !(mx <= 0 || mn >= mx);
+            const int kept = (anySet && anyClear) ? 1 : 0;   // !(max <= 0 || min >= max) on a 0/1 mask
             for (int r = 0; r < sc.n_cyl_regions; ++r)
                 for (int sg = 0; sg < cyls[r].n_segments; ++sg)
                     if (cyls[r].assigned[sg] == ci) cyls[r].kept[sg] = kept;
