@@ -204,6 +204,15 @@ void rs_pose_destroy(rs_pose_ctx* ctx);
 int rs_pose_solve_batched(rs_pose_ctx* ctx, const double* cur_pose, const rs_match* matches, const int32_t* n_matches,
                           int batch, const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask);
 
+/* The same call split in two, so that the solve overlaps other work of the frame (the reference runs find_primitives
+ * on a std::async thread beside the rest of RGBD_SLAM::track, rgbd_slam.cpp:288-300): _begin enqueues the upload, the
+ * kernels and the download on the context's stream and returns (RS_RNG_DEVICE; with RS_RNG_REFERENCE the host-side
+ * random draws make it block until the covariance kernel is enqueued); _end waits. The host buffers, `out` and
+ * `inlier_mask` must stay valid (and should be pinned) until _end returns. */
+int rs_pose_solve_batched_begin(rs_pose_ctx* ctx, const double* cur_pose, const rs_match* matches, const int32_t* n_matches,
+                                int batch, const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask);
+int rs_pose_solve_batched_end(rs_pose_ctx* ctx);
+
 /* Single-frame convenience with the reference's call shape (creates nothing: uses ctx, batch 1). */
 int rs_pose_solve(rs_pose_ctx* ctx, const double cur_pose[7], const rs_match* matches, int n_matches,
                   const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask);

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -87,6 +88,8 @@ struct rs_cape_ctx {
     int tmap_batch = 0;
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy legs of the chunk pipeline of rs_cape_run
+    std::vector<cudaEvent_t> chunk_events;                     // 2 per chunk: depth landed, results ready
     cudaEvent_t fit_done = nullptr;   // recorded after every K1 launch (rs_cape_stream_wait_fit)
     std::vector<cudaEvent_t> events;  // 3 per timing slot
     int timing_slots = 0;
@@ -94,6 +97,10 @@ struct rs_cape_ctx {
 };
 
 namespace {
+
+// rs_cape_run moves a host batch through the GPU in chunks of this many frames: the H2D copy of chunk k+1, the kernels
+// of chunk k and the D2H copy of chunk k-1 overlap (three streams), so a batch costs its PCIe time, not the sum.
+constexpr int kChunkFrames = 32;
 
 // Eigen's 3x3 cofactor inverse of the intrinsics applied to (u, v, 1): point_coordinates.cpp:79-83.
 void backprojection_factors(const rs_cape_ctx* c, std::vector<double>& kx, std::vector<double>& ky)
@@ -194,6 +201,10 @@ int create_impl(rs_cape_ctx* c)
     c->n_uniforms = 3 * RS_CYL_RANSAC_ITERS * RS_MAX_CYL_REGIONS * RS_MAX_CYL_SEGS;
     if ((rc = dev_alloc(&c->d_uniforms, size_t(c->n_uniforms)))) return rc;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    c->chunk_events.assign(2 * size_t((c->max_batch + kChunkFrames - 1) / kChunkFrames), nullptr);
+    for (cudaEvent_t& e : c->chunk_events) RS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->fit_done, cudaEventDisableTiming));
 
     const unsigned P = unsigned(c->cell) * unsigned(c->cell);
@@ -211,7 +222,7 @@ int create_impl(rs_cape_ctx* c)
 }
 
 int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t seed, const rs_cape_outputs* o,
-                    cudaStream_t stream, bool cells_only)
+                    cudaStream_t stream, bool cells_only, bool timing = true)
 {
     if (!c || !depth_dev || batch <= 0 || batch > c->max_batch || !o || !o->cells) {
         set_last_error("rs_cape_run: invalid argument (null pointer or batch out of range)");
@@ -222,8 +233,8 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     if (rc != RS_OK) return rc;
     CellFitParams fp = c->fit;
     fp.batch = batch;
-    cudaEvent_t* ev = c->timing_slots > 0 ? &c->events[size_t(c->run_counter % uint64_t(c->timing_slots)) * 3] : nullptr;
-    ++c->run_counter;
+    cudaEvent_t* ev = (timing && c->timing_slots > 0) ? &c->events[size_t(c->run_counter % uint64_t(c->timing_slots)) * 3] : nullptr;
+    if (timing) ++c->run_counter;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], stream));
     if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream)) != RS_OK) return rc;
     RS_CUDA_CHECK(cudaEventRecord(c->fit_done, stream));
@@ -302,6 +313,10 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_scratch);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->fit_done) cudaEventDestroy(c->fit_done);
+    for (cudaEvent_t e : c->chunk_events)
+        if (e) cudaEventDestroy(e);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -369,28 +384,50 @@ int rs_cape_run(rs_cape_ctx* c, const float* depth_host, int batch, uint32_t see
         return RS_ERR_INVALID_ARG;
     }
     RS_CUDA_CHECK(cudaSetDevice(c->device));
-    const size_t B = size_t(batch), Nc = size_t(c->Nc);
-    cudaStream_t s = c->stream;
-    RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth, depth_host, sizeof(float) * B * c->W * c->H, cudaMemcpyHostToDevice, s));
+    const size_t Nc = size_t(c->Nc), px = size_t(c->W) * c->H, mb = size_t(c->max_boundary);
     const bool cells_only = !out->plane_grid && !out->plane_labels && !out->cyl_labels && !out->cyl_region_seg &&
                             !out->planes && !out->cyls && !out->boundary_xyz && !out->info;
-    int rc = run_device_impl(c, c->d_depth, batch, seed, &c->d_out, s, cells_only);
-    if (rc != RS_OK) return rc;
     const rs_cape_outputs& d = c->d_out;
-#define RS_D2H(field, count)                                                                                      \
-    if (out->field)                                                                                               \
-    RS_CUDA_CHECK(cudaMemcpyAsync(out->field, d.field, sizeof(*d.field) * (count), cudaMemcpyDeviceToHost, s))
-    RS_D2H(cells, B * Nc);
-    RS_D2H(plane_grid, B * Nc);
-    RS_D2H(plane_labels, B * Nc);
-    RS_D2H(cyl_labels, B * Nc);
-    RS_D2H(cyl_region_seg, B * Nc);
-    RS_D2H(planes, B * RS_MAX_PLANES);
-    RS_D2H(cyls, B * RS_MAX_CYL_REGIONS);
-    RS_D2H(boundary_xyz, B * size_t(c->max_boundary) * 3);
-    RS_D2H(info, B);
+    int rc;
+    if (!cells_only && (rc = ensure_uniforms(c, seed)) != RS_OK) return rc;
+    int k = 0;
+    for (int f0 = 0; f0 < batch; f0 += kChunkFrames, ++k) {
+        const size_t n = size_t(std::min(kChunkFrames, batch - f0)), o = size_t(f0);
+        cudaEvent_t landed = c->chunk_events[2 * k], ready = c->chunk_events[2 * k + 1];
+        RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth + o * px, depth_host + o * px, sizeof(float) * n * px, cudaMemcpyHostToDevice,
+                                      c->h2d_stream));
+        RS_CUDA_CHECK(cudaEventRecord(landed, c->h2d_stream));
+        RS_CUDA_CHECK(cudaStreamWaitEvent(c->stream, landed, 0));
+        rs_cape_outputs dchunk;
+        dchunk.cells = d.cells + o * Nc;
+        dchunk.plane_grid = d.plane_grid + o * Nc;
+        dchunk.plane_labels = d.plane_labels + o * Nc;
+        dchunk.cyl_labels = d.cyl_labels + o * Nc;
+        dchunk.cyl_region_seg = d.cyl_region_seg + o * Nc;
+        dchunk.planes = d.planes + o * RS_MAX_PLANES;
+        dchunk.cyls = d.cyls + o * RS_MAX_CYL_REGIONS;
+        dchunk.boundary_xyz = d.boundary_xyz + o * mb * 3;
+        dchunk.info = d.info + o;
+        if ((rc = run_device_impl(c, c->d_depth + o * px, int(n), seed, &dchunk, c->stream, cells_only, false)) != RS_OK) return rc;
+        RS_CUDA_CHECK(cudaEventRecord(ready, c->stream));
+        RS_CUDA_CHECK(cudaStreamWaitEvent(c->d2h_stream, ready, 0));
+#define RS_D2H(field, per_frame)                                                                                         \
+    if (out->field)                                                                                                      \
+    RS_CUDA_CHECK(cudaMemcpyAsync(out->field + o * (per_frame), d.field + o * (per_frame), sizeof(*d.field) * n * (per_frame), \
+                                  cudaMemcpyDeviceToHost, c->d2h_stream))
+        RS_D2H(cells, Nc);
+        RS_D2H(plane_grid, Nc);
+        RS_D2H(plane_labels, Nc);
+        RS_D2H(cyl_labels, Nc);
+        RS_D2H(cyl_region_seg, Nc);
+        RS_D2H(planes, size_t(RS_MAX_PLANES));
+        RS_D2H(cyls, size_t(RS_MAX_CYL_REGIONS));
+        RS_D2H(boundary_xyz, mb * 3);
+        RS_D2H(info, size_t(1));
 #undef RS_D2H
-    RS_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    RS_CUDA_CHECK(cudaStreamSynchronize(c->d2h_stream));
+    RS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return RS_OK;
 }
 

@@ -107,7 +107,7 @@ int resolve_launch(const rs_pose_ctx* c, const rs_pose_opts* opts, int batch, Po
 }
 
 int upload_impl(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches, const int32_t* n_matches, int batch,
-                cudaStream_t s)
+                cudaStream_t s, bool host_types = true)
 {
     if (!c || !cur_pose || !matches || !n_matches || batch <= 0 || batch > c->max_batch) {
         set_last_error("rs_pose: invalid argument (null pointer or batch out of range)");
@@ -124,7 +124,8 @@ int upload_impl(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches,
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_n, n_matches, sizeof(int32_t) * batch, cudaMemcpyHostToDevice, s));
     for (int b = 0; b < batch; ++b) {
         c->h_n[b] = n_matches[b];
-        for (int i = 0; i < n_matches[b]; ++i) c->h_type[size_t(b) * c->M + i] = matches[size_t(b) * c->M + i].type;
+        if (host_types)  // only the host-side reference RNG (std::shuffle / normal draws per inlier) reads the types
+            for (int i = 0; i < n_matches[b]; ++i) c->h_type[size_t(b) * c->M + i] = matches[size_t(b) * c->M + i].type;
     }
     return RS_OK;
 }
@@ -327,8 +328,8 @@ int rs_pose_kernel_ms(rs_pose_ctx* c, int slot, float ms[4])
     return RS_OK;
 }
 
-int rs_pose_solve_batched(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches, const int32_t* n_matches,
-                          int batch, const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask)
+int rs_pose_solve_batched_begin(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches, const int32_t* n_matches,
+                                int batch, const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask)
 {
     if (!c || !out) {
         set_last_error("rs_pose_solve_batched: null context or output");
@@ -337,9 +338,32 @@ int rs_pose_solve_batched(rs_pose_ctx* c, const double* cur_pose, const rs_match
     PoseLaunch prm;
     int rc = resolve_launch(c, opts, batch, prm);
     if (rc != RS_OK) return rc;
-    if ((rc = upload_impl(c, cur_pose, matches, n_matches, batch, c->stream)) != RS_OK) return rc;
-    if ((rc = solve_impl(c, batch, prm, c->stream, prm.rng_mode == RS_RNG_REFERENCE)) != RS_OK) return rc;
-    return download_impl(c, batch, out, inlier_mask, c->stream);
+    const bool reference_rng = prm.rng_mode == RS_RNG_REFERENCE;
+    if ((rc = upload_impl(c, cur_pose, matches, n_matches, batch, c->stream, reference_rng)) != RS_OK) return rc;
+    if ((rc = solve_impl(c, batch, prm, c->stream, reference_rng)) != RS_OK) return rc;
+    RS_CUDA_CHECK(cudaMemcpyAsync(out, c->buf.out, sizeof(rs_pose_out) * batch, cudaMemcpyDeviceToHost, c->stream));
+    if (inlier_mask)
+        RS_CUDA_CHECK(cudaMemcpyAsync(inlier_mask, c->buf.mask, size_t(batch) * c->M, cudaMemcpyDeviceToHost, c->stream));
+    return RS_OK;
+}
+
+int rs_pose_solve_batched_end(rs_pose_ctx* c)
+{
+    if (!c) {
+        set_last_error("rs_pose_solve_batched_end: null context");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    RS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return RS_OK;
+}
+
+int rs_pose_solve_batched(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches, const int32_t* n_matches,
+                          int batch, const rs_pose_opts* opts, rs_pose_out* out, uint8_t* inlier_mask)
+{
+    const int rc = rs_pose_solve_batched_begin(c, cur_pose, matches, n_matches, batch, opts, out, inlier_mask);
+    if (rc != RS_OK) return rc;
+    return rs_pose_solve_batched_end(c);
 }
 
 int rs_pose_solve(rs_pose_ctx* c, const double cur_pose[7], const rs_match* matches, int n_matches,

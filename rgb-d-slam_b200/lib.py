@@ -51,6 +51,8 @@ def load():
     if hasattr(lib, "rs_pose_create"):
         lib.rs_pose_create.restype = vp
         lib.rs_pose_create.argtypes = [i32, i32, i32, i32, i32]
+        lib.rs_pose_solve_batched_begin.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+        lib.rs_pose_solve_batched_end.argtypes = [vp]
         lib.rs_pose_destroy.argtypes = [vp]
         lib.rs_pose_solve_batched.argtypes = [vp, vp, vp, vp, i32, C.POINTER(abi.PoseOpts), vp, vp]
         lib.rs_pose_solve.argtypes = [vp, vp, vp, i32, C.POINTER(abi.PoseOpts), vp, vp]
@@ -194,6 +196,12 @@ class PoseOptimization:
     def compute_optimized_pose(self, cur_pose, matches, n_matches=None, opts=None):
         """cur_pose [B,7] (x y z qw qx qy qz); matches [B,max_matches] of abi.match_dtype (or a list of 1-D arrays).
         Returns (pose_out[B] structured array, inlier_mask[B,max_matches] uint8)."""
+        self.compute_optimized_pose_begin(cur_pose, matches, n_matches, opts)
+        return self.compute_optimized_pose_end()
+
+    def compute_optimized_pose_begin(self, cur_pose, matches, n_matches=None, opts=None, out=None, mask=None):
+        """Enqueues the solve and returns; compute_optimized_pose_end() waits and hands back (pose_out, inlier_mask).
+        `out` / `mask` may be caller-provided (e.g. pinned) arrays; all host arrays must stay alive until _end."""
         cur_pose = np.ascontiguousarray(np.atleast_2d(cur_pose), dtype=np.float64)
         B = cur_pose.shape[0]
         if isinstance(matches, (list, tuple)):
@@ -210,11 +218,22 @@ class PoseOptimization:
         if n_matches is None:
             n_matches = np.full((B,), matches.shape[1], dtype=np.int32)
         n_matches = np.ascontiguousarray(n_matches, dtype=np.int32)
-        out = np.zeros((B,), dtype=abi.pose_out_dtype)
-        mask = np.zeros((B, self.max_matches), dtype=np.uint8)
+        if out is None:
+            out = np.zeros((B,), dtype=abi.pose_out_dtype)
+        if mask is None:
+            mask = np.zeros((B, self.max_matches), dtype=np.uint8)
         o = opts if opts is not None else self.options()
-        _check(self._lib.rs_pose_solve_batched(self._ctx, cur_pose.ctypes.data, matches.ctypes.data, n_matches.ctypes.data,
-                                               B, C.byref(o), out.ctypes.data, mask.ctypes.data), "rs_pose_solve_batched")
+        self._pending = (out, mask, cur_pose, matches, n_matches, o)  # keep the host buffers alive until _end
+        _check(self._lib.rs_pose_solve_batched_begin(self._ctx, cur_pose.ctypes.data, matches.ctypes.data,
+                                                     n_matches.ctypes.data, B, C.byref(o), out.ctypes.data, mask.ctypes.data),
+               "rs_pose_solve_batched_begin")
+
+    def compute_optimized_pose_end(self):
+        if getattr(self, "_pending", None) is None:
+            raise RuntimeError("compute_optimized_pose_end without a pending compute_optimized_pose_begin")
+        _check(self._lib.rs_pose_solve_batched_end(self._ctx), "rs_pose_solve_batched_end")
+        out, mask = self._pending[0], self._pending[1]
+        self._pending = None
         return out, mask
 
     def upload(self, cur_pose, matches, n_matches):
