@@ -286,10 +286,36 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
+        # same leg from the raw CV_16U sensor image (the reference's examples convertTo(CV_32F) on the host first)
+        h_d16 = torch.from_numpy(np.clip(np.rint(depth), 0, 65535).astype(np.uint16)).pin_memory()
+        h_d16_np = h_d16.numpy()
+
+        def e2e_u16_step():
+            solver.compute_optimized_pose_begin(cur, h_matches_np, n, opts, out=h_pose_out_np, mask=h_mask_np)
+            det.find_primitives_u16(h_d16_np, alpha=1.0, seed=0, out=(arrs, st))
+            return solver.compute_optimized_pose_end()[0]
+
+        for _ in range(2):
+            e2e_u16_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_u16_step()
+        torch.cuda.synchronize()
+        t16 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+        sec16 = float(t16.item())
         h2d = int(h_depth_np.nbytes + h_matches_np.nbytes + cur.nbytes + n.nbytes)
         d2h = int(sum(arrs[k].nbytes for k in wanted) + o.nbytes + F * MAX_MATCHES)
         e2e = {"value": world * F * e2e_steps / sec, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e2e_steps, "timing": "host wall clock around the C-ABI calls (pose solve begin -> find_primitives, chunk-pipelined copies -> pose solve end), max over ranks"}
+               "steps": e2e_steps,
+               "u16_depth": {"value": world * F * e2e_steps / sec16, "unit": "frames/s",
+                             "h2d_bytes_per_step": int(h_d16_np.nbytes + h_matches_np.nbytes + cur.nbytes + n.nbytes),
+                             "note": "rs_cape_run_u16: CV_16U sensor image, convertTo(CV_32F) on the device"},
+               "timing": "host wall clock around the C-ABI calls (pose solve begin -> find_primitives, chunk-pipelined copies -> pose solve end), max over ranks"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None

@@ -127,6 +127,12 @@ typedef struct rs_cape_outputs {
  * reference does because find_primitives runs on a fresh std::async thread per frame. */
 int rs_cape_run(rs_cape_ctx* ctx, const float* depth_host, int batch, uint32_t seed, const rs_cape_outputs* out_host);
 
+/* Same from the raw sensor image: CV_16U depth converted as cv::Mat::convertTo(CV_32F, alpha) does (float(src) *
+ * float(alpha); examples/main_TUM.cpp:242 uses alpha = 1/5, main_CAPE.cpp:59 alpha = 1). The conversion runs on the
+ * device, so the host-to-device copy is half the size of the float image. */
+int rs_cape_run_u16(rs_cape_ctx* ctx, const uint16_t* depth_host, double alpha, int batch, uint32_t seed,
+                    const rs_cape_outputs* out_host);
+
 /* Same, with depth and outputs already resident in device memory (used for the HBM-resident
  * throughput number; `stream` is a cudaStream_t passed as void*). Asynchronous. */
 int rs_cape_run_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, uint32_t seed,

@@ -78,6 +78,7 @@ struct rs_cape_ctx {
     rs_cape_outputs d_out{};       // device pointers sized for max_batch
     double* d_uniforms = nullptr;
     double* d_scratch = nullptr;   // per-frame scratch of the segmentation kernel
+    uint16_t* d_depth16 = nullptr; // staging for rs_cape_run_u16 (allocated on first use)
     int n_uniforms = 0;
     uint32_t uniforms_seed = 0;
     bool uniforms_valid = false;
@@ -89,6 +90,7 @@ struct rs_cape_ctx {
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy legs of the chunk pipeline of rs_cape_run
+    cudaStream_t seg_streams[4] = {nullptr, nullptr, nullptr, nullptr};  // segmentation of chunk k runs on [k % 4]
     std::vector<cudaEvent_t> chunk_events;                     // 2 per chunk: depth landed, results ready
     cudaEvent_t fit_done = nullptr;   // recorded after every K1 launch (rs_cape_stream_wait_fit)
     std::vector<cudaEvent_t> events;  // 3 per timing slot
@@ -101,6 +103,23 @@ namespace {
 // rs_cape_run moves a host batch through the GPU in chunks of this many frames: the H2D copy of chunk k+1, the kernels
 // of chunk k and the D2H copy of chunk k-1 overlap (three streams), so a batch costs its PCIe time, not the sum.
 constexpr int kChunkFrames = 32;
+
+// cv::Mat::convertTo(CV_32F, alpha) of a CV_16U depth image (examples/main_TUM.cpp:242, main_CAPE.cpp:59): OpenCV's
+// cvtScale 16u -> 32f works in float: dst = float(src) * float(alpha). Eight pixels per thread (16-byte load, two
+// 16-byte stores); n8 = pixel count / 8.
+__global__ void depth_u16_to_f32_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, const size_t n8, const float alpha)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+        const uint4 v = __ldg(src + i);
+        float4 a, b;
+        a.x = __fmul_rn(float(v.x & 0xffffu), alpha), a.y = __fmul_rn(float(v.x >> 16), alpha);
+        a.z = __fmul_rn(float(v.y & 0xffffu), alpha), a.w = __fmul_rn(float(v.y >> 16), alpha);
+        b.x = __fmul_rn(float(v.z & 0xffffu), alpha), b.y = __fmul_rn(float(v.z >> 16), alpha);
+        b.z = __fmul_rn(float(v.w & 0xffffu), alpha), b.w = __fmul_rn(float(v.w >> 16), alpha);
+        dst[2 * i] = a;
+        dst[2 * i + 1] = b;
+    }
+}
 
 // Eigen's 3x3 cofactor inverse of the intrinsics applied to (u, v, 1): point_coordinates.cpp:79-83.
 void backprojection_factors(const rs_cape_ctx* c, std::vector<double>& kx, std::vector<double>& ky)
@@ -203,6 +222,7 @@ int create_impl(rs_cape_ctx* c)
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (cudaStream_t& ss : c->seg_streams) RS_CUDA_CHECK(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
     c->chunk_events.assign(2 * size_t((c->max_batch + kChunkFrames - 1) / kChunkFrames), nullptr);
     for (cudaEvent_t& e : c->chunk_events) RS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->fit_done, cudaEventDisableTiming));
@@ -222,7 +242,8 @@ int create_impl(rs_cape_ctx* c)
 }
 
 int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t seed, const rs_cape_outputs* o,
-                    cudaStream_t stream, bool cells_only, bool timing = true)
+                    cudaStream_t stream, bool cells_only, bool timing = true, cudaStream_t seg_stream = nullptr,
+                    size_t scratch_frame = 0)
 {
     if (!c || !depth_dev || batch <= 0 || batch > c->max_batch || !o || !o->cells) {
         set_last_error("rs_cape_run: invalid argument (null pointer or batch out of range)");
@@ -262,7 +283,12 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     sb.cyls = o->cyls;
     sb.boundary_xyz = o->boundary_xyz;
     sb.info = o->info;
-    sb.scratch = c->d_scratch;
+    sb.scratch = c->d_scratch + scratch_frame * cape_segment_scratch_doubles_per_frame(c->Nc);
+    if (seg_stream && seg_stream != stream) {
+        // the latency-bound segmentation of this chunk runs beside the plane fit / segmentation of the next ones
+        RS_CUDA_CHECK(cudaStreamWaitEvent(seg_stream, c->fit_done, 0));
+        return launch_cape_segment(sp, sb, seg_stream);
+    }
     if ((rc = launch_cape_segment(sp, sb, stream)) != RS_OK) return rc;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
     return RS_OK;
@@ -311,12 +337,15 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_out.info);
     cudaFree(c->d_uniforms);
     cudaFree(c->d_scratch);
+    cudaFree(c->d_depth16);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->fit_done) cudaEventDestroy(c->fit_done);
     for (cudaEvent_t e : c->chunk_events)
         if (e) cudaEventDestroy(e);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (cudaStream_t ss : c->seg_streams)
+        if (ss) cudaStreamDestroy(ss);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -377,9 +406,10 @@ int rs_cape_run_device(rs_cape_ctx* c, const float* depth_dev, int batch, uint32
     return run_device_impl(c, depth_dev, batch, seed, out_dev, static_cast<cudaStream_t>(stream), false);
 }
 
-int rs_cape_run(rs_cape_ctx* c, const float* depth_host, int batch, uint32_t seed, const rs_cape_outputs* out)
+static int run_host_impl(rs_cape_ctx* c, const float* depth_host, const uint16_t* depth16_host, float alpha, int batch,
+                         uint32_t seed, const rs_cape_outputs* out)
 {
-    if (!c || !depth_host || !out || batch <= 0 || batch > c->max_batch) {
+    if (!c || (!depth_host && !depth16_host) || !out || batch <= 0 || batch > c->max_batch) {
         set_last_error("rs_cape_run: invalid argument (null pointer or batch out of range)");
         return RS_ERR_INVALID_ARG;
     }
@@ -394,10 +424,19 @@ int rs_cape_run(rs_cape_ctx* c, const float* depth_host, int batch, uint32_t see
     for (int f0 = 0; f0 < batch; f0 += kChunkFrames, ++k) {
         const size_t n = size_t(std::min(kChunkFrames, batch - f0)), o = size_t(f0);
         cudaEvent_t landed = c->chunk_events[2 * k], ready = c->chunk_events[2 * k + 1];
-        RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth + o * px, depth_host + o * px, sizeof(float) * n * px, cudaMemcpyHostToDevice,
-                                      c->h2d_stream));
+        if (depth16_host)
+            RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth16 + o * px, depth16_host + o * px, sizeof(uint16_t) * n * px,
+                                          cudaMemcpyHostToDevice, c->h2d_stream));
+        else
+            RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth + o * px, depth_host + o * px, sizeof(float) * n * px, cudaMemcpyHostToDevice,
+                                          c->h2d_stream));
         RS_CUDA_CHECK(cudaEventRecord(landed, c->h2d_stream));
         RS_CUDA_CHECK(cudaStreamWaitEvent(c->stream, landed, 0));
+        if (depth16_host) {
+            depth_u16_to_f32_kernel<<<148 * 8, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_depth16 + o * px),
+                                                                   reinterpret_cast<float4*>(c->d_depth + o * px), n * px / 8, alpha);
+            RS_LAUNCH_CHECK();
+        }
         rs_cape_outputs dchunk;
         dchunk.cells = d.cells + o * Nc;
         dchunk.plane_grid = d.plane_grid + o * Nc;
@@ -408,8 +447,10 @@ int rs_cape_run(rs_cape_ctx* c, const float* depth_host, int batch, uint32_t see
         dchunk.cyls = d.cyls + o * RS_MAX_CYL_REGIONS;
         dchunk.boundary_xyz = d.boundary_xyz + o * mb * 3;
         dchunk.info = d.info + o;
-        if ((rc = run_device_impl(c, c->d_depth + o * px, int(n), seed, &dchunk, c->stream, cells_only, false)) != RS_OK) return rc;
-        RS_CUDA_CHECK(cudaEventRecord(ready, c->stream));
+        cudaStream_t seg = c->seg_streams[k % 4];
+        if ((rc = run_device_impl(c, c->d_depth + o * px, int(n), seed, &dchunk, c->stream, cells_only, false, seg, o)) != RS_OK)
+            return rc;
+        RS_CUDA_CHECK(cudaEventRecord(ready, cells_only ? c->stream : seg));
         RS_CUDA_CHECK(cudaStreamWaitEvent(c->d2h_stream, ready, 0));
 #define RS_D2H(field, per_frame)                                                                                         \
     if (out->field)                                                                                                      \
@@ -428,7 +469,30 @@ int rs_cape_run(rs_cape_ctx* c, const float* depth_host, int batch, uint32_t see
     }
     RS_CUDA_CHECK(cudaStreamSynchronize(c->d2h_stream));
     RS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (cudaStream_t ss : c->seg_streams) RS_CUDA_CHECK(cudaStreamSynchronize(ss));
     return RS_OK;
+}
+
+int rs_cape_run(rs_cape_ctx* c, const float* depth_host, int batch, uint32_t seed, const rs_cape_outputs* out)
+{
+    return run_host_impl(c, depth_host, nullptr, 1.0f, batch, seed, out);
+}
+
+int rs_cape_run_u16(rs_cape_ctx* c, const uint16_t* depth_host, double alpha, int batch, uint32_t seed, const rs_cape_outputs* out)
+{
+    if (!c || !depth_host) {
+        set_last_error("rs_cape_run_u16: invalid argument (null pointer)");
+        return RS_ERR_INVALID_ARG;
+    }
+    if ((size_t(c->W) * c->H) % 8 != 0) {
+        set_last_error("rs_cape_run_u16: width * height must be a multiple of 8");
+        return RS_ERR_INVALID_ARG;
+    }
+    if (!c->d_depth16) {
+        RS_CUDA_CHECK(cudaSetDevice(c->device));
+        RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_depth16), sizeof(uint16_t) * size_t(c->max_batch) * c->W * c->H));
+    }
+    return run_host_impl(c, nullptr, depth_host, static_cast<float>(alpha), batch, seed, out);
 }
 
 const char* rs_last_error(void)

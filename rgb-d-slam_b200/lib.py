@@ -36,6 +36,7 @@ def load():
     lib.rs_cape_cells_per_frame.argtypes = [vp]
     lib.rs_cape_max_boundary.argtypes = [vp]
     lib.rs_cape_run.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs)]
+    lib.rs_cape_run_u16.argtypes = [vp, vp, C.c_double, i32, u32, C.POINTER(abi.CapeOutputs)]
     lib.rs_cape_run_device.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs), vp]
     lib.rs_cape_cell_fit_device.argtypes = [vp, vp, i32, vp, vp]
     lib.rs_cape_stream_wait_fit.argtypes = [vp, vp]
@@ -124,6 +125,19 @@ class PrimitiveDetection:
         if cells_only:
             st = abi.CapeOutputs(cells=arrs["cells"].ctypes.data)
         _check(self._lib.rs_cape_run(self._ctx, depth.ctypes.data, B, seed, C.byref(st)), "rs_cape_run")
+        return arrs
+
+    def find_primitives_u16(self, depth16, alpha=1.0, seed=0, out=None):
+        """depth16: uint16 [B,H,W] raw sensor image; depth in mm = float32(depth16) * float32(alpha), as
+        cv::Mat::convertTo(CV_32F, alpha) in the reference's examples. Same outputs as find_primitives."""
+        depth16 = np.ascontiguousarray(depth16, dtype=np.uint16)
+        if depth16.ndim == 2:
+            depth16 = depth16[None]
+        B = depth16.shape[0]
+        if depth16.shape[1:] != (self.height, self.width):
+            raise ValueError("depth must be [B,%d,%d]" % (self.height, self.width))
+        arrs, st = abi.alloc_cape_outputs(B, self.n_cells, self.max_boundary) if out is None else out
+        _check(self._lib.rs_cape_run_u16(self._ctx, depth16.ctypes.data, float(alpha), B, seed, C.byref(st)), "rs_cape_run_u16")
         return arrs
 
     # --- device-resident entry points (pointers are raw CUDA device addresses, e.g. torch.Tensor.data_ptr()) ---

@@ -93,3 +93,32 @@ def test_invalid_arguments(det):
         det.find_primitives(rs.synth.scene_v0_batch(0, 9))   # batch > max_batch
     with pytest.raises(rs.RsError):
         rs.PrimitiveDetection(640, 480, 18)                    # cell side not a multiple of 4
+
+
+def test_u16_depth_matches_float_path_and_oracle(det):
+    # the raw sensor image of the reference's examples: CV_16U, 1/5 mm units, convertTo(CV_32F, 1/5) (main_TUM.cpp:242)
+    depth = rs.synth.scene_v0_batch(30, 3)
+    d16 = np.clip(np.rint(depth * 5.0), 0, 65535).astype(np.uint16)
+    as_float = d16.astype(np.float32) * np.float32(1.0 / 5.0)   # OpenCV's cvtScale 16u -> 32f works in float
+    got = det.find_primitives_u16(d16, alpha=1.0 / 5.0, seed=0)
+    same = det.find_primitives(as_float, seed=0)
+    ref = ol.cape_run(as_float, seed=0)
+    assert got["cells"].tobytes() == same["cells"].tobytes()
+    assert np.array_equal(got["plane_labels"], same["plane_labels"])
+    for b in range(3):
+        parity.assert_cells_match(ref["cells"][b], got["cells"][b])
+        parity.assert_frame_match(ref, got, b)
+
+
+def test_chunked_host_run_covers_ragged_batches():
+    # rs_cape_run streams 32-frame chunks: a batch that is not a multiple of the chunk, against per-frame runs
+    d = rs.PrimitiveDetection(640, 480, 20, max_batch=70)
+    depth = rs.synth.scene_v0_batch(40, 70)
+    full = d.find_primitives(depth, seed=3)
+    for b in (0, 31, 32, 63, 64, 69):
+        one = d.find_primitives(depth[b:b + 1], seed=3)
+        assert full["cells"][b].tobytes() == one["cells"][0].tobytes()
+        assert np.array_equal(full["plane_labels"][b], one["plane_labels"][0])
+        assert np.array_equal(full["cyl_labels"][b], one["cyl_labels"][0])
+        assert full["info"][b].tobytes() == one["info"][0].tobytes()
+    d.close()
