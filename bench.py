@@ -234,6 +234,26 @@ def main():
     ms_total = float(t.item())
     value = world * F * steps / (ms_total * 1e-3)
 
+    # ---- rectify_depth (the step in front of the path, off in the headline workload as in examples/main_TUM.cpp) ----
+    rect = None
+    if rank == 0:
+        det.set_rectification(None, enable=True)
+        d_rect = torch.empty_like(d_depth)
+        for _ in range(2):
+            det.rectify_device(d_depth.data_ptr(), F, d_rect.data_ptr(), stream=sptr)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(5):
+            det.rectify_device(d_depth.data_ptr(), F, d_rect.data_ptr(), stream=sptr)
+        r1.record(stream)
+        torch.cuda.synchronize()
+        rect_ms = r0.elapsed_time(r1) / 5
+        rect_bytes = (4 + 8 + 8 + 8 + 4) * W * H * F   # depth read, key memset, key RMW, key read, float write
+        rect = {"ms_per_batch": rect_ms, "frames": F, "algorithmic_GBps": rect_bytes / (rect_ms * 1e-3) / 1e9,
+                "bytes_per_pixel": 32, "note": "rs_cape_rectify_device: key memset + scatter (64-bit atomicMax) + resolve"}
+        det.set_rectification(None, enable=False)
+        del d_rect
+
     # sanity: the timed work produced valid poses close to the synthetic truth
     out, _ = solver.download(F)
     ok_frac = float((out["status"] == 1).mean())
@@ -362,6 +382,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "check": {"frames_with_valid_pose": ok_frac, "median_position_error_mm": pos_err},
         }
+        if rect is not None:
+            line["rectify_depth"] = rect
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

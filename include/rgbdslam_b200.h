@@ -142,6 +142,16 @@ int rs_cape_run_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, uint
  * cells_dev = B x Ncells records in device memory. Asynchronous. */
 int rs_cape_cell_fit_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, rs_cell_out* cells_dev, void* stream);
 
+/* Depth_Map_Transformation::rectify_depth (src/features/primitives/depth_map_transformation.cpp:23-87, called through
+ * RGBD_SLAM::rectify_depth, rgbd_slam.cpp:85-97, by examples/main_CAPE.cpp:186): the depth camera's image re-projected
+ * into the colour camera's image; the last source pixel in raster order wins a destination pixel, untouched pixels are 0.
+ * cam2_to_cam1 = Parameters::get_camera_2_to_camera_1_transformation(), row-major 4x4 (12 values are read).
+ * With enable != 0 every rs_cape_run* call rectifies its input on the device before the plane fit (the boundary step
+ * then reads the rectified image, as find_primitives does in the reference); rs_cape_rectify* expose the step alone. */
+int rs_cape_set_rectification(rs_cape_ctx* ctx, const double* cam2_to_cam1, int enable);
+int rs_cape_rectify(rs_cape_ctx* ctx, const float* depth_host, int batch, float* rectified_host);
+int rs_cape_rectify_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, float* rectified_dev, void* stream);
+
 /* Makes `stream` wait until the most recent plane-fit kernel (K1) launched through this context has finished.
  * The reference runs find_primitives on its own std::async thread beside the rest of the frame (rgbd_slam.cpp:288-300);
  * the device-side equivalent is a second stream: the HBM-bound K1 gets the GPU to itself and the latency-bound kernels

@@ -909,4 +909,38 @@ void cape_run(const CapeConfig& cfg, const float* depth, const uint32_t seed, Ca
     out.info.n_boundary = int(out.boundary_xyz.size() / 3);
 }
 
+// ---- Depth_Map_Transformation::rectify_depth (depth_map_transformation.cpp:23-87) ------------------------------------
+void rectify_depth(const CapeConfig& cfg, const double T[16], const float* depth, float* out)
+{
+    const int W = cfg.width, H = cfg.height;
+    std::vector<double> kx, ky;
+    backprojection_factors(cfg, kx, ky);   // ScreenCoordinate2D(col,row).to_camera_coordinates(), init_matrices :160-164
+    std::vector<float> preX(W), preY(H);   // _Xpre / _Ypre are float images; they only depend on the column / the row
+    for (int c = 0; c < W; ++c) preX[c] = static_cast<float>(kx[c]);
+    for (int r = 0; r < H; ++r) preY[r] = static_cast<float>(ky[r]);
+    std::fill(out, out + size_t(W) * H, 0.0f);
+    for (int row = 0; row < H; ++row)
+        for (int col = 0; col < W; ++col) {
+            const float originalZ = depth[size_t(row) * W + col];
+            if (originalZ <= 0) continue;
+            // vector3 original(preX * z, preY * z, z): float products, widened by the vector3 constructor
+            const double ox = static_cast<double>(preX[col] * originalZ);
+            const double oy = static_cast<double>(preY[row] * originalZ);
+            const double oz = static_cast<double>(originalZ);
+            const double px = ((T[0] * ox + T[1] * oy) + T[2] * oz) + T[3];
+            const double py = ((T[4] * ox + T[5] * oy) + T[6] * oz) + T[7];
+            const double pz = ((T[8] * ox + T[9] * oy) + T[10] * oz) + T[11];
+            // CameraCoordinate::to_screen_coordinates (point_coordinates.cpp:201-210): 1.0 / z * (K * p).head<2>()
+            const double inv = 1.0 / pz;
+            const double sx = inv * ((cfg.fx * px + 0.0 * py) + cfg.cx * pz);
+            const double sy = inv * ((0.0 * px + cfg.fy * py) + cfg.cy * pz);
+            if (sx != sx || sy != sy) continue;   // the reference exit(-1)s here; unreachable for finite inputs with z > 0
+            // static_cast<uint>(floor(.)) of a negative double: x86-64 converts through a 64-bit integer and truncates,
+            // giving a value >= 2^31 that fails the bounds test below
+            const double fxs = std::floor(sx), fys = std::floor(sy);
+            if (!(fxs > 0.0 && fys > 0.0 && fxs < double(W) && fys < double(H))) continue;
+            out[size_t(fys) * W + size_t(fxs)] = static_cast<float>(pz);
+        }
+}
+
 }  // namespace oracle

@@ -58,4 +58,11 @@ void cape_run(const CapeConfig& cfg, const float* depth, uint32_t seed, CapeFram
 
 void cell_record(const PlaneSeg& s, float tol, rs_cell_out& o);
 
+// Depth_Map_Transformation::rectify_depth (depth_map_transformation.cpp:23-87): depth image of camera 2 re-projected
+// into the image of camera 1, serial row-major scan (the MAKE_DETERMINISTIC build), last writer wins.
+// cam2_to_cam1 = Parameters::get_camera_2_to_camera_1_transformation(), row-major 4x4. out = H*W floats.
+// PARITY UNPINNED beyond the restatement: the summation order inside Eigen's 4x4 * homogeneous product is taken as
+// ((T0 x + T1 y) + T2 z) + T3; it can only matter when a projected coordinate lies within an ulp of a pixel boundary.
+void rectify_depth(const CapeConfig& cfg, const double cam2_to_cam1[16], const float* depth, float* out);
+
 }  // namespace oracle

@@ -47,6 +47,15 @@ void store_frame(const CapeFrame& f, int Nc, int maxBoundary, int b, const rs_ca
 
 extern "C" {
 
+int orc_rectify_depth(int W, int H, double fx, double fy, double cx, double cy, const double* cam2_to_cam1, const float* depth,
+                      int batch, float* out)
+{
+    CapeConfig cfg;
+    cfg.width = W, cfg.height = H, cfg.fx = fx, cfg.fy = fy, cfg.cx = cx, cfg.cy = cy;
+    for (int b = 0; b < batch; ++b) rectify_depth(cfg, cam2_to_cam1, depth + size_t(b) * W * H, out + size_t(b) * W * H);
+    return 0;
+}
+
 int orc_cape_run(int W, int H, int cell, double fx, double fy, double cx, double cy, const float* depth, int batch,
                  uint32_t seed, int max_boundary, const rs_cape_outputs* out)
 {

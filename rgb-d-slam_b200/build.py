@@ -18,6 +18,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 UNITS = [
     ("cape_cell_fit.cu", ["-fmad=false"]),
     ("cape_segment.cu", ["-fmad=false"]),
+    ("rectify.cu", ["-fmad=false"]),
     ("api_cape.cu", ["-fmad=false"]),
     ("pose_solve.cu", []),
     ("api_pose.cu", []),

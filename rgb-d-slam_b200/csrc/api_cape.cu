@@ -79,6 +79,10 @@ struct rs_cape_ctx {
     double* d_uniforms = nullptr;
     double* d_scratch = nullptr;   // per-frame scratch of the segmentation kernel
     uint16_t* d_depth16 = nullptr; // staging for rs_cape_run_u16 (allocated on first use)
+    bool rectify = false;          // rs_cape_set_rectification: rectify_depth in front of K1
+    RectifyParams rect{};
+    float* d_rect = nullptr;               // max_batch x H x W rectified depth
+    unsigned long long* d_keys = nullptr;  // max_batch x H x W scatter keys
     int n_uniforms = 0;
     uint32_t uniforms_seed = 0;
     bool uniforms_valid = false;
@@ -250,7 +254,17 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
         return RS_ERR_INVALID_ARG;
     }
     RS_CUDA_CHECK(cudaSetDevice(c->device));
-    int rc = encode_tmap(c, depth_dev, batch);
+    int rc;
+    if (c->rectify) {
+        // rectify_depth in front of the path (rgbd_slam.cpp:85-97): K1 and the boundary step then read the rectified image
+        RectifyParams rp = c->rect;
+        rp.batch = batch;
+        float* rect = c->d_rect + scratch_frame * size_t(c->W) * c->H;
+        if ((rc = launch_rectify_depth(rp, depth_dev, c->d_keys + scratch_frame * size_t(c->W) * c->H, rect, stream)) != RS_OK)
+            return rc;
+        depth_dev = rect;
+    }
+    rc = encode_tmap(c, depth_dev, batch);
     if (rc != RS_OK) return rc;
     CellFitParams fp = c->fit;
     fp.batch = batch;
@@ -338,6 +352,8 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_uniforms);
     cudaFree(c->d_scratch);
     cudaFree(c->d_depth16);
+    cudaFree(c->d_rect);
+    cudaFree(c->d_keys);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->fit_done) cudaEventDestroy(c->fit_done);
     for (cudaEvent_t e : c->chunk_events)
@@ -376,6 +392,57 @@ int rs_cape_kernel_ms(rs_cape_ctx* c, int slot, float ms[2])
     RS_CUDA_CHECK(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
     RS_CUDA_CHECK(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));
     return RS_OK;
+}
+
+int rs_cape_set_rectification(rs_cape_ctx* c, const double* cam2_to_cam1, int enable)
+{
+    if (!c || (enable && !cam2_to_cam1)) {
+        set_last_error("rs_cape_set_rectification: invalid argument");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    if (enable) {
+        const size_t px = size_t(c->max_batch) * c->W * c->H;
+        if (!c->d_rect) RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_rect), sizeof(float) * px));
+        if (!c->d_keys) RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_keys), sizeof(unsigned long long) * px));
+        c->rect.W = c->W, c->rect.H = c->H;
+        c->rect.kx = c->d_kx, c->rect.ky = c->d_ky;
+        c->rect.fx = c->fx, c->rect.fy = c->fy, c->rect.cx = c->cx, c->rect.cy = c->cy;
+        for (int i = 0; i < 12; ++i) c->rect.T[i] = cam2_to_cam1[i];
+    }
+    c->rectify = enable != 0;
+    c->tmap_ptr = nullptr;  // the plane fit reads another buffer from now on
+    return RS_OK;
+}
+
+int rs_cape_rectify(rs_cape_ctx* c, const float* depth_host, int batch, float* rectified_host)
+{
+    if (!c || !depth_host || !rectified_host || batch <= 0 || batch > c->max_batch || !c->d_rect) {
+        set_last_error("rs_cape_rectify: invalid argument, or rs_cape_set_rectification has not been called");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t px = size_t(batch) * c->W * c->H;
+    RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth, depth_host, sizeof(float) * px, cudaMemcpyHostToDevice, c->stream));
+    RectifyParams rp = c->rect;
+    rp.batch = batch;
+    const int rc = launch_rectify_depth(rp, c->d_depth, c->d_keys, c->d_rect, c->stream);
+    if (rc != RS_OK) return rc;
+    RS_CUDA_CHECK(cudaMemcpyAsync(rectified_host, c->d_rect, sizeof(float) * px, cudaMemcpyDeviceToHost, c->stream));
+    RS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return RS_OK;
+}
+
+int rs_cape_rectify_device(rs_cape_ctx* c, const float* depth_dev, int batch, float* rectified_dev, void* stream)
+{
+    if (!c || !depth_dev || !rectified_dev || batch <= 0 || batch > c->max_batch || !c->d_keys) {
+        set_last_error("rs_cape_rectify_device: invalid argument, or rs_cape_set_rectification has not been called");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    RectifyParams rp = c->rect;
+    rp.batch = batch;
+    return launch_rectify_depth(rp, depth_dev, c->d_keys, rectified_dev, static_cast<cudaStream_t>(stream));
 }
 
 int rs_cape_stream_wait_fit(rs_cape_ctx* c, void* stream)

@@ -46,6 +46,16 @@ struct SegmentBuffers {
     double* scratch;             // B x cape_segment_scratch_doubles_per_frame(Nc): projected normals / centroids of the cylinder branch
 };
 
+struct RectifyParams {
+    int W, H, batch;
+    const double* kx;   // [W] same back-projection factors as K1 (cast to float per use: _Xpre / _Ypre are float images)
+    const double* ky;   // [H]
+    double fx, fy, cx, cy;   // camera 1 intrinsics (the reference projects AND back-projects with camera 1's)
+    double T[12];            // first three rows of the camera-2 -> camera-1 transformation, row-major
+};
+// keys: batch*H*W 64-bit scratch; out: batch*H*W floats
+int launch_rectify_depth(const RectifyParams& prm, const float* depth, unsigned long long* keys, float* out, cudaStream_t stream);
+
 int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream);
 size_t cape_segment_scratch_doubles_per_frame(int n_cells);
 

@@ -40,6 +40,9 @@ def load():
     lib.rs_cape_run_device.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs), vp]
     lib.rs_cape_cell_fit_device.argtypes = [vp, vp, i32, vp, vp]
     lib.rs_cape_stream_wait_fit.argtypes = [vp, vp]
+    lib.rs_cape_set_rectification.argtypes = [vp, vp, i32]
+    lib.rs_cape_rectify.argtypes = [vp, vp, i32, vp]
+    lib.rs_cape_rectify_device.argtypes = [vp, vp, i32, vp, vp]
     lib.rs_cape_device_depth.restype = vp
     lib.rs_cape_device_depth.argtypes = [vp]
     lib.rs_cape_device_outputs.restype = C.POINTER(abi.CapeOutputs)
@@ -150,6 +153,23 @@ class PrimitiveDetection:
     def run_device(self, depth_ptr, batch, seed=0, outputs=None, stream=0):
         o = outputs if outputs is not None else self.device_outputs()
         _check(self._lib.rs_cape_run_device(self._ctx, depth_ptr, batch, seed, C.byref(o), stream), "rs_cape_run_device")
+
+    def set_rectification(self, cam2_to_cam1=None, enable=True):
+        """rectify_depth in front of every find_primitives call (cam2_to_cam1: 4x4, identity by default)."""
+        T = np.ascontiguousarray(np.eye(4) if cam2_to_cam1 is None else cam2_to_cam1, dtype=np.float64).reshape(16)
+        _check(self._lib.rs_cape_set_rectification(self._ctx, T.ctypes.data, 1 if enable else 0), "rs_cape_set_rectification")
+
+    def rectify_depth(self, depth):
+        """Depth_Map_Transformation::rectify_depth alone: float32 [B,H,W] -> rectified float32 [B,H,W]."""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        if depth.ndim == 2:
+            depth = depth[None]
+        out = np.empty_like(depth)
+        _check(self._lib.rs_cape_rectify(self._ctx, depth.ctypes.data, depth.shape[0], out.ctypes.data), "rs_cape_rectify")
+        return out
+
+    def rectify_device(self, depth_ptr, batch, out_ptr, stream=0):
+        _check(self._lib.rs_cape_rectify_device(self._ctx, depth_ptr, batch, out_ptr, stream), "rs_cape_rectify_device")
 
     def stream_wait_fit(self, stream):
         """`stream` (cudaStream_t as int) waits for the latest plane-fit kernel of this context."""

@@ -42,6 +42,7 @@ def load():
     lib.orc_pose_solve.argtypes = [vp, vp, vp, i32, i32, i32, u32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.orc_process_frames.restype = dbl
     lib.orc_process_frames.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, u32, i32, vp]
+    lib.orc_rectify_depth.argtypes = [i32, i32, dbl, dbl, dbl, dbl, vp, vp, i32, vp]
     lib.orc_ref_test_features.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32]
     _lib = lib
     return lib
@@ -57,6 +58,19 @@ def cape_run(depth, cell=20, K=(550.0, 550.0, 320.0, 240.0), seed=0):
     arrs, st = abi.alloc_cape_outputs(B, Nc, 2 * Nc)
     lib.orc_cape_run(W, H, cell, *K, depth.ctypes.data, B, seed, 2 * Nc, C.byref(st))
     return arrs
+
+
+def rectify_depth(depth, cam2_to_cam1=None, K=(550.0, 550.0, 320.0, 240.0)):
+    """Depth_Map_Transformation::rectify_depth restated (oracle/cape.cpp): depth [B,H,W] float32 -> rectified [B,H,W]."""
+    lib = load()
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    if depth.ndim == 2:
+        depth = depth[None]
+    B, H, W = depth.shape
+    T = np.ascontiguousarray(np.eye(4) if cam2_to_cam1 is None else cam2_to_cam1, dtype=np.float64).reshape(16)
+    out = np.zeros_like(depth)
+    lib.orc_rectify_depth(W, H, *K, T.ctypes.data, depth.ctypes.data, B, out.ctypes.data)
+    return out
 
 
 def cape_cell_fit(depth, cell=20, K=(550.0, 550.0, 320.0, 240.0), want_cloud=False):

@@ -152,3 +152,22 @@ def test_degenerate_frames(case):
     assert info["status"] == 0
     if case != "flat":
         assert info["n_planes"] == 0 and not r["plane_labels"].any()
+
+
+def test_rectify_depth_restatement_properties():
+    """depth_map_transformation.cpp:23-87 restated: untouched pixels are 0, first row / column are never written
+    (the reference's strict > 0 test), values are depths of the source image, and an offset camera shifts the image."""
+    import rgbd_slam_b200 as rs
+    depth = rs.synth.scene_v0_batch(0, 1)
+    r = ol.rectify_depth(depth)
+    assert r.shape == depth.shape and r.dtype == np.float32
+    assert not r[0, 0, :].any() and not r[0, :, 0].any()
+    assert np.isin(r[r > 0], depth[depth > 0]).all()          # identity transform: z is carried over unchanged
+    assert 0.5 < (r > 0).mean() < (depth > 0).mean()          # float tables: some pixels collide, some stay empty
+    assert not ol.rectify_depth(np.zeros_like(depth)).any()
+    T = np.eye(4)
+    T[0, 3] = 100.0                                            # 100 mm to the right: the scene moves right in the image
+    shifted = ol.rectify_depth(depth, T)
+    cols = np.arange(640)[None, :]
+    assert (shifted[0] > 0).sum() > 0
+    assert ((shifted[0] > 0) * cols).sum() / (shifted[0] > 0).sum() > ((r[0] > 0) * cols).sum() / (r[0] > 0).sum()
