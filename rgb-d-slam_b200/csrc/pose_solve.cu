@@ -97,9 +97,12 @@ __device__ inline void quaternion_from_coefficients(const double* x, double q[4]
     q[1] = 2.0 * x[4] * divider;
     q[2] = 2.0 * x[5] * divider;
     q[3] = (1.0 - alpha) * divider;
-    const double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    if (nn > 0.0) {
-        q[0] /= nn, q[1] /= nn, q[2] /= nn, q[3] /= nn;
+    // PoseBase normalises the quaternion it is given (pose.cpp:18-22); one reciprocal square root instead of a square
+    // root and four divisions (this runs on the serial lane-0 path of every LM iteration)
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (n2 > 0.0) {
+        const double inn = rsqrt(n2);
+        q[0] *= inn, q[1] *= inn, q[2] *= inn, q[3] *= inn;
     }
 }
 
@@ -331,7 +334,7 @@ __device__ __forceinline__ void feature_jacobian(const int type, const double (&
     const double v1 = (T.R[1] * m[0] + T.R[4] * m[1]) + T.R[7] * m[2];
     const double v2 = (T.R[2] * m[0] + T.R[5] * m[1]) + T.R[8] * m[2];
     const double z = (v0 * v0 + v1 * v1) + v2 * v2;
-    const double is = z > 0.0 ? 1.0 / sqrt(z) : 1.0;
+    const double is = z > 0.0 ? rsqrt(z) : 1.0;
     const double np[3] = {v0 * is, v1 * is, v2 * is};
     const double dp = ((T.t[0] * m[0] + T.t[1] * m[1]) + T.t[2] * m[2]) + m[3];
     const double third = 1.0 / 3.0;
@@ -744,9 +747,9 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
             double sc[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const double n = sqrt(fmax(S.A[j * 6 + j], 0.0));
-                S.wa2[j] = n;
-                sc[j] = n > 0.0 ? 1.0 / n : 1.0;
+                const double ajj = S.A[j * 6 + j];
+                sc[j] = ajj > 0.0 ? rsqrt(ajj) : 1.0;   // 1 / |J_j|
+                S.wa2[j] = ajj > 0.0 ? ajj * sc[j] : 0.0;
                 S.sc[j] = sc[j];
             }
 #pragma unroll
@@ -815,7 +818,7 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
                 }
                 const double temp1 = fmax(pAp, 0.0) * inv_fnorm * inv_fnorm;
                 const double temp2 = S.par * (pnorm * inv_fnorm) * (pnorm * inv_fnorm);
-                const double prered = temp1 + temp2 / 0.5;
+                const double prered = temp1 + temp2 * 2.0;
                 const double dirder = -(temp1 + temp2);
                 double ratio = 0.0;
                 if (prered != 0.0) ratio = actred / prered;
@@ -824,11 +827,11 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
                     if (actred >= 0.0) temp = 0.5;
                     if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
                     if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
-                    S.delta = temp * fmin(S.delta, pnorm / 0.1);
+                    S.delta = temp * fmin(S.delta, pnorm * 10.0);
                     S.par /= temp;
                 }
                 else if (!(S.par != 0.0 && ratio < 0.75)) {
-                    S.delta = pnorm / 0.5;
+                    S.delta = pnorm * 2.0;
                     S.par = 0.5 * S.par;
                 }
                 if (ratio >= 1e-4) {
