@@ -193,8 +193,8 @@ __device__ __forceinline__ void plane_to_camera(const double n0, const double n1
     double v2 = (T.R[2] * n0 + T.R[5] * n1) + T.R[8] * n2;
     const double z = (v0 * v0 + v1 * v1) + v2 * v2;
     if (z > 0.0) {
-        const double s = sqrt(z);
-        v0 /= s, v1 /= s, v2 /= s;
+        const double is = rsqrt(z);
+        v0 *= is, v1 *= is, v2 *= is;
     }
     np[0] = v0, np[1] = v1, np[2] = v2;
     dp = ((T.t[0] * n0 + T.t[1] * n1) + T.t[2] * n2) + dw;
@@ -625,7 +625,8 @@ __device__ __forceinline__ void lmpar(WarpLM& S)
             wa2[j] = S.diag[j] * x[j];
             dx2 += wa2[j] * wa2[j];
         }
-        const double dxnorm = sqrt(dx2);
+        const double idx = dx2 > 0.0 ? rsqrt(dx2) : 0.0;   // 1 / |D x|
+        const double dxnorm = dx2 * idx;
         const double temp = fp;
         fp = dxnorm - delta;
         if (iter == 0) {
@@ -635,13 +636,12 @@ __device__ __forceinline__ void lmpar(WarpLM& S)
             break;
         // Newton correction fp / delta / (w^T (C + par E^2)^-1 w), w = S D^2 x / |D x| (at par = 0 this is parl)
         double q = 0.0;
-        const double idx = 1.0 / dxnorm;
 #pragma unroll
         for (int i = 0; i < 6; ++i) z[i] = S.sc[i] * (S.diag[i] * (wa2[i] * idx));
         forward6_packed(M, z);
 #pragma unroll
         for (int i = 0; i < 6; ++i) q += z[i] * z[i] * dinv[i];
-        const double parc = fp / delta / q;
+        const double parc = fp / (delta * q);
         if (iter == 0) {
             parl = parc;
             double gn = 0.0;
