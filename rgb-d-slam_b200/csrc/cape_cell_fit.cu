@@ -4,17 +4,21 @@
 //                   Plane_Segment::init_plane_segment + fit_plane         (plane_segment.cpp:44-168,205-284)
 //                   Primitive_Detection::init_planar_cell_fitting          (primitive_detection.cpp:187-221)
 //
-// Mapping: one warp owns a run of up to 32 consecutive cells of one cell-row. The run is consumed as "items" of
-// 8 cells, FOUR LANES PER CELL: a 3-D tiled TMA box {cs px, 8 cells, R rows} (R*cs*8*4 = 6400 B) lands as
-// [row][cell][px] in a 2-slot per-warp ring guarded by mbarriers; lane (c = lane/4, j = lane%4) reads the float4
-// j, j+4, j+8, ... of cell c's part of the box (LDS.128, at most 2-way bank conflicts), back-projects in FP64
-// (cast to float, as the reference's cloud) and accumulates the nine sums of FP32 values / FP32 products in FP64.
-// The pixel loop is branch-free: an invalid pixel (z <= 0) contributes exact zeros, as its (0,0,0) cloud row does.
-// Per item the sums are reduced over the 4 lanes of a cell with two shuffle steps (instead of five for a warp-wide
-// cell) and handed to lane 8*item + c, so that after four items every lane holds one cell; the cross-shaped
-// continuity test runs from small per-warp copies of the middle row / middle column, split over the 4 lanes of
-// the cell. The 3x3 eigen-solves are then lane-parallel (one cell per lane) and every lane stores its own 160-byte
-// record with 16-byte stores.
+// Two kernels. K1a `cape_cell_fit_kernel` streams the depth image: one warp owns a run of up to 32 consecutive cells
+// of one cell-row. The run is consumed as "items" of 8 cells, FOUR LANES PER CELL: a 3-D tiled TMA box
+// {cs px, 8 cells, R rows} (R*cs*8*4 = 2560 B) lands as [row][cell][px] in a 2-slot per-warp ring guarded by
+// mbarriers; lane (c = lane/4, j = lane%4) reads the float4 j, j+4, j+8, ... of cell c's part of the box (LDS.128, at
+// most 2-way bank conflicts; exactly 5 trips per box), back-projects in FP64 and accumulates the nine sums of FP32
+// values / FP32 products in FP64. The rounding to float that the reference's cloud and products carry is done where it
+// is cheapest on sm_100: FP32<->FP64 conversions issue at a quarter of the FP64 rate (tools/microbench.cu; eleven per
+// pixel kept the XU pipe 70 % busy), so x, y and three of the six products are rounded to 24 bits inside the FP64 pipe
+// with Veltkamp's split (round_to_float, bit-identical to the conversion, tests/test_oracle_cape.py) and the rest go
+// through FMUL + F2F; the two pipes end up balanced. The pixel loop is branch-free: an invalid pixel (z <= 0)
+// contributes exact zeros, as its (0,0,0) cloud row does. Per item the sums are reduced over the 4 lanes of a cell with
+// two shuffle steps and handed to lane 8*item + c, so that after four items every lane holds one cell; the cross-shaped
+// continuity test runs from small per-warp copies of the middle row / middle column, split over the 4 lanes of the cell.
+// K1b `cape_cell_finish_kernel` then fits every cell (3x3 eigen-solve, planarity, merge tolerance), one thread per cell,
+// in place on the 160-byte record: inside the streaming kernel that serial chain cost 30 % of the time.
 //
 // Compiled with -fmad=false: products are FP32-rounded then accumulated in FP64 exactly as the reference does.
 #include <cuda.h>
@@ -30,6 +34,12 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int CELLS_PER_ITEM = 8;
 constexpr int WARPS = 4;
+#ifndef RS_K1_MIN_CTAS
+#define RS_K1_MIN_CTAS 4
+#endif
+#ifndef RS_K1_FP64_PRODUCTS
+#define RS_K1_FP64_PRODUCTS 3   // how many of the six FP32 products are formed and rounded in the FP64 pipe
+#endif
 
 // Indices e_i = base[i * stride], i in [0, n). Reference (plane_segment.cpp:44-100): last = max(e_0, e_1); fail if
 // last <= 0; for i = 1..n-1 a positive e_i must satisfy |e_i - last| <= 4 quant(e_i) and then becomes `last`.
@@ -58,22 +68,31 @@ __device__ __forceinline__ bool continuity_segment(const float* base, const int 
     return ok;
 }
 
+// v rounded to the nearest float (ties to even), as a double: Veltkamp's split, p = v (2^29 + 1), hi = p - (p - v).
+// Exact for every v whose rounded value is a normal float or zero.
+__device__ __forceinline__ double round_to_float(const double v)
+{
+    const double p = v * 536870913.0;
+    return p - (p - v);
+}
+
 template <int CS>
 struct Geometry {
     static constexpr int G = CS / 4;                                 // float4 groups per cell row
-    static constexpr int R = 6400 / (CS * CELLS_PER_ITEM * 4);       // rows per TMA box (10 @20 px, 5 @40 px)
+    static constexpr int BOX_BYTES = 2560;                           // one TMA box: R rows of 8 cells
+    static constexpr int R = BOX_BYTES / (CS * CELLS_PER_ITEM * 4);  // rows per TMA box (4 @20 px, 2 @40 px)
     static constexpr int NBOX = CS / R;                              // boxes per item
-    static constexpr int BOX_BYTES = R * CS * CELLS_PER_ITEM * 4;    // 6400
-    static constexpr int F4_PER_CELL_BOX = R * G;                    // float4 of one cell in one box (50)
-    static constexpr int ITERS = (F4_PER_CELL_BOX + 3) / 4;          // per-lane trips per box (13)
+    static constexpr int F4_PER_CELL_BOX = R * G;                    // float4 of one cell in one box (20)
+    static constexpr int ITERS = F4_PER_CELL_BOX / 4;                // per-lane trips per box (5, no padding trip)
     static constexpr int ROW_FLOATS = CS * CELLS_PER_ITEM;           // one box row in floats
     static constexpr int MID_BYTES = 2 * CELLS_PER_ITEM * CS * 4;    // middle row + middle column copies
     static constexpr int WARP_BYTES = (2 * BOX_BYTES + MID_BYTES + 16 + 127) / 128 * 128;  // TMA destinations stay 128-B aligned
-    static_assert(CS % 4 == 0 && CS % R == 0 && R * CS * CELLS_PER_ITEM * 4 == 6400, "unsupported cell size");
+    static_assert(CS % 4 == 0 && CS % R == 0 && R * CS * CELLS_PER_ITEM * 4 == BOX_BYTES && F4_PER_CELL_BOX % 4 == 0,
+                  "unsupported cell size");
 };
 
 template <int CS>
-__global__ void __launch_bounds__(WARPS * 32, (CS <= 20 ? 4 : 3))
+__global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         cape_cell_fit_kernel(const __grid_constant__ CUtensorMap tmap, const CellFitParams prm, rs_cell_out* __restrict__ cells)
 {
     using Geo = Geometry<CS>;
@@ -141,7 +160,7 @@ __global__ void __launch_bounds__(WARPS * 32, (CS <= 20 ? 4 : 3))
         }
 #pragma unroll 1
         for (int k = 0; k < Geo::ITERS; ++k) {
-            if (r < R) {
+            {
                 const float4 v = *reinterpret_cast<const float4*>(ctile + r * Geo::ROW_FLOATS + g * 4);
                 const double2 kxa = __ldg(reinterpret_cast<const double2*>(prm.kx + colbase + g * 4));
                 const double2 kxb = __ldg(reinterpret_cast<const double2*>(prm.kx + colbase + g * 4 + 2));
@@ -153,18 +172,48 @@ __global__ void __launch_bounds__(WARPS * 32, (CS <= 20 ? 4 : 3))
                     const bool valid = zz[t] > 0.f;
                     const float z = valid ? zz[t] : 0.f;
                     cnt += valid ? 1 : 0;
+                    // The reference's values are float(z kx), float(z ky) and FP32 products widened to FP64. On sm_100 the
+                    // FP32<->FP64 conversions run at a quarter of the FP64 rate (tools/microbench.cu) and eleven of them per
+                    // pixel bounded this loop, so the rounding to 24 bits is done in FP64 where that is cheaper: Veltkamp's
+                    // split with 2^29 + 1 returns exactly RN_24(v), ties to even included (tests/test_oracle_cape.py), and
+                    // the product of two 24-bit values is exact in FP64 before it is rounded.
                     const double zd = static_cast<double>(z);
-                    const float x = static_cast<float>(zd * kxr[t]);
-                    const float y = static_cast<float>(zd * kyv);
-                    S0 += static_cast<double>(x);
-                    S1 += static_cast<double>(y);
+                    const double xd = round_to_float(zd * kxr[t]);
+                    const double yd = round_to_float(zd * kyv);
+                    const float x = static_cast<float>(xd);   // exact: xd already has a 24-bit significand
+                    const float y = static_cast<float>(yd);
+                    S0 += xd;
+                    S1 += yd;
                     S2 += zd;
+#if RS_K1_FP64_PRODUCTS == 0
                     S3 += static_cast<double>(x * x);
                     S4 += static_cast<double>(y * y);
                     S5 += static_cast<double>(z * z);
                     S6 += static_cast<double>(x * y);
                     S7 += static_cast<double>(y * z);
                     S8 += static_cast<double>(x * z);
+#elif RS_K1_FP64_PRODUCTS == 2
+                    S3 += round_to_float(xd * xd);
+                    S4 += round_to_float(yd * yd);
+                    S5 += static_cast<double>(z * z);
+                    S6 += static_cast<double>(x * y);
+                    S7 += static_cast<double>(y * z);
+                    S8 += static_cast<double>(x * z);
+#elif RS_K1_FP64_PRODUCTS == 3
+                    S3 += round_to_float(xd * xd);
+                    S4 += round_to_float(yd * yd);
+                    S5 += static_cast<double>(z * z);
+                    S6 += round_to_float(xd * yd);
+                    S7 += static_cast<double>(y * z);
+                    S8 += static_cast<double>(x * z);
+#else
+                    S3 += round_to_float(xd * xd);
+                    S4 += round_to_float(yd * yd);
+                    S5 += round_to_float(zd * zd);
+                    S6 += round_to_float(xd * yd);
+                    S7 += round_to_float(yd * zd);
+                    S8 += round_to_float(xd * zd);
+#endif
                 }
             }
             g += 4;
@@ -259,43 +308,70 @@ __global__ void __launch_bounds__(WARPS * 32, (CS <= 20 ? 4 : 3))
         __syncwarp();                                   // midrow / midcol are rewritten by the next item
     }
 
-    // ---- fit phase: one cell per lane (plane_segment.cpp:102-168 after the sums, primitive_detection.cpp:201-220) ----
+    // ---- hand the cell over to the fit kernel: sums, count, continuity flag and the first / last cloud rows travel in
+    // the cell's own record (the two points in the centroid / normal slots), 16-byte stores ----
     if (lane >= ncell) return;
+    double2* dst = reinterpret_cast<double2*>(cells + (size_t(b) * prm.vc + cr) * prm.hc + c0 + lane);
+    double2 head;
+    head.x = __hiloint2double(fok, fcount);            // {int32 count, int32 planar := continuity / count test passed}
+    head.y = F0;
+    dst[0] = head;
+    dst[1] = make_double2(F1, F2);
+    dst[2] = make_double2(F3, F4);
+    dst[3] = make_double2(F5, F6);
+    dst[4] = make_double2(F7, F8);
+    dst[5] = make_double2(static_cast<double>(fp0x), static_cast<double>(fp0y));
+    dst[6] = make_double2(static_cast<double>(fp0z), static_cast<double>(fplx));
+    dst[7] = make_double2(static_cast<double>(fply), static_cast<double>(fplz));
+}
+
+// K1b: the per-cell fit (plane_segment.cpp:102-168 after the sums, primitive_detection.cpp:201-220), one THREAD per cell.
+// The 3x3 eigen-solve is a serial chain of FP64 divisions and square roots with a data-dependent trip count; inside the
+// streaming kernel it ran on warps that were holding TMA buffers and cost 30 % of K1's time for 4 % of its instructions.
+// Here every cell of the batch is in flight at once and the records (31 MB per 256 frames) are still in L2.
+__global__ void __launch_bounds__(128) cape_cell_finish_kernel(const CellFitParams prm, rs_cell_out* __restrict__ cells, const int total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    double2* rec = reinterpret_cast<double2*>(cells + i);
+    const double2 head = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4], r5 = rec[5], r6 = rec[6], r7 = rec[7];
+    const int fcount = __double2loint(head.x), fok = __double2hiint(head.x);
     PlaneModel pm;
     plane_clear(pm);
     float tol = 0.f;
     if (fok) {
         pm.count = fcount;
-        pm.S[0] = F0, pm.S[1] = F1, pm.S[2] = F2, pm.S[3] = F3, pm.S[4] = F4, pm.S[5] = F5, pm.S[6] = F6, pm.S[7] = F7, pm.S[8] = F8;
+        pm.S[0] = head.y, pm.S[1] = r1.x, pm.S[2] = r1.y, pm.S[3] = r2.x, pm.S[4] = r2.y, pm.S[5] = r3.x, pm.S[6] = r3.y;
+        pm.S[7] = r4.x, pm.S[8] = r4.y;
         if (fcount >= prm.min_zero_point_count) {
             plane_fit(pm);
             const double qz = depth_quantization(pm.c[2]);
             pm.planar = (pm.mse <= qz * qz) ? 1 : 0;
         }
         if (pm.planar) {
-            const float dx = fplx - fp0x, dy = fply - fp0y, dz = fplz - fp0z;
+            const float dx = static_cast<float>(r6.y) - static_cast<float>(r5.x);
+            const float dy = static_cast<float>(r7.x) - static_cast<float>(r5.y);
+            const float dz = static_cast<float>(r7.y) - static_cast<float>(r6.x);
             const float diameter = sqrtf((dx * dx + dy * dy) + dz * dz);
             tol = fminf(prm.merge_distance, diameter * prm.sin_merge * sqrtf(static_cast<float>(pm.count)));
         }
     }
-    // 160-byte record, ten 16-byte stores
-    double2* dst = reinterpret_cast<double2*>(cells + (size_t(b) * prm.vc + cr) * prm.hc + c0 + lane);
-    double2 head;
-    head.x = __hiloint2double(pm.planar, pm.count);    // {int32 count, int32 planar} little-endian
-    head.y = pm.S[0];
-    dst[0] = head;
-    dst[1] = make_double2(pm.S[1], pm.S[2]);
-    dst[2] = make_double2(pm.S[3], pm.S[4]);
-    dst[3] = make_double2(pm.S[5], pm.S[6]);
-    dst[4] = make_double2(pm.S[7], pm.S[8]);
-    dst[5] = make_double2(pm.c[0], pm.c[1]);
-    dst[6] = make_double2(pm.c[2], pm.n[0]);
-    dst[7] = make_double2(pm.n[1], pm.n[2]);
-    dst[8] = make_double2(pm.d, pm.mse);
+    double2 out0;
+    out0.x = __hiloint2double(pm.planar, pm.count);    // {int32 count, int32 planar} little-endian
+    out0.y = pm.S[0];
+    rec[0] = out0;
+    rec[1] = make_double2(pm.S[1], pm.S[2]);
+    rec[2] = make_double2(pm.S[3], pm.S[4]);
+    rec[3] = make_double2(pm.S[5], pm.S[6]);
+    rec[4] = make_double2(pm.S[7], pm.S[8]);
+    rec[5] = make_double2(pm.c[0], pm.c[1]);
+    rec[6] = make_double2(pm.c[2], pm.n[0]);
+    rec[7] = make_double2(pm.n[1], pm.n[2]);
+    rec[8] = make_double2(pm.d, pm.mse);
     double2 tail;
     tail.x = pm.score;
     tail.y = __hiloint2double(0, __float_as_int(tol));  // {float tol, int32 reserved}
-    dst[9] = tail;
+    rec[9] = tail;
 }
 
 template <int CS>
@@ -315,6 +391,9 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
     p.total_items = prm.batch * prm.vc * p.items_per_strip;
     const int grid = (p.total_items + WARPS - 1) / WARPS;
     kernel<<<grid, WARPS * 32, smem, stream>>>(tmap, p, cells);
+    RS_LAUNCH_CHECK();
+    const int total = prm.batch * prm.vc * prm.hc;
+    cape_cell_finish_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p, cells, total);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }

@@ -171,3 +171,28 @@ def test_rectify_depth_restatement_properties():
     cols = np.arange(640)[None, :]
     assert (shifted[0] > 0).sum() > 0
     assert ((shifted[0] > 0) * cols).sum() / (shifted[0] > 0).sum() > ((r[0] > 0) * cols).sum() / (r[0] > 0).sum()
+
+
+def test_veltkamp_split_is_the_float_rounding_k1_needs():
+    """K1 rounds z*kx, z*ky and three of the FP32 products to float precision inside the FP64 pipe (cape_cell_fit.cu,
+    round_to_float): p = v (2^29 + 1), hi = p - (p - v). It must equal double(float(v)) bit for bit, ties included."""
+    rng = np.random.default_rng(0)
+    C = np.float64(2 ** 29 + 1)
+
+    def veltkamp(v):
+        p = v * C
+        return p - (p - v)
+
+    m = rng.integers(2 ** 23, 2 ** 24, size=200000).astype(np.float64)
+    e = rng.integers(-20, 30, size=m.size)
+    ties = (m + 0.5) * np.exp2(e - 23.0)                       # exactly halfway between two floats
+    ties = np.concatenate([ties, -ties, np.nextafter(ties, np.inf), np.nextafter(ties, -np.inf), [0.0, -0.0]])
+    assert np.array_equal(veltkamp(ties), ties.astype(np.float32).astype(np.float64))
+    z = rng.uniform(300, 9000, 500000).astype(np.float32).astype(np.float64)
+    k = (rng.integers(0, 640, z.size) - 320.0) / 550.0
+    v = z * k                                                   # the back-projection products
+    assert np.array_equal(veltkamp(v), v.astype(np.float32).astype(np.float64))
+    a = v.astype(np.float32)
+    b = (z * ((rng.integers(0, 480, z.size) - 240.0) / 550.0)).astype(np.float32)
+    exact = a.astype(np.float64) * b.astype(np.float64)        # exact: 24-bit x 24-bit fits the 53-bit significand
+    assert np.array_equal(veltkamp(exact), (a * b).astype(np.float64))
