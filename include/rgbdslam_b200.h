@@ -152,7 +152,8 @@ int rs_cape_set_rectification(rs_cape_ctx* ctx, const double* cam2_to_cam1, int 
 int rs_cape_rectify(rs_cape_ctx* ctx, const float* depth_host, int batch, float* rectified_host);
 int rs_cape_rectify_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, float* rectified_dev, void* stream);
 
-/* Makes `stream` wait until the most recent plane-fit kernel (K1) launched through this context has finished.
+/* Makes `stream` wait until the streaming part of the most recent plane fit (K1a, the HBM-bound kernel) launched through
+ * this context has finished.
  * The reference runs find_primitives on its own std::async thread beside the rest of the frame (rgbd_slam.cpp:288-300);
  * the device-side equivalent is a second stream: the HBM-bound K1 gets the GPU to itself and the latency-bound kernels
  * (cell-graph segmentation here, RANSAC in the pose context) then share the SMs. */

@@ -96,7 +96,8 @@ struct rs_cape_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy legs of the chunk pipeline of rs_cape_run
     cudaStream_t seg_streams[4] = {nullptr, nullptr, nullptr, nullptr};  // segmentation of chunk k runs on [k % 4]
     std::vector<cudaEvent_t> chunk_events;                     // 2 per chunk: depth landed, results ready
-    cudaEvent_t fit_done = nullptr;   // recorded after every K1 launch (rs_cape_stream_wait_fit)
+    cudaEvent_t fit_done = nullptr;   // recorded after every K1 launch (K1a + K1b): the segmentation of a chunk waits on it
+    cudaEvent_t streamed = nullptr;   // recorded after K1a, the HBM-bound streaming kernel (rs_cape_stream_wait_fit)
     std::vector<cudaEvent_t> events;  // 3 per timing slot
     int timing_slots = 0;
     uint64_t run_counter = 0;
@@ -230,6 +231,7 @@ int create_impl(rs_cape_ctx* c)
     c->chunk_events.assign(2 * size_t((c->max_batch + kChunkFrames - 1) / kChunkFrames), nullptr);
     for (cudaEvent_t& e : c->chunk_events) RS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->fit_done, cudaEventDisableTiming));
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->streamed, cudaEventDisableTiming));
 
     const unsigned P = unsigned(c->cell) * unsigned(c->cell);
     c->fit.H = c->H, c->fit.hc = c->hc, c->fit.vc = c->vc, c->fit.cell = c->cell;
@@ -271,7 +273,7 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     cudaEvent_t* ev = (timing && c->timing_slots > 0) ? &c->events[size_t(c->run_counter % uint64_t(c->timing_slots)) * 3] : nullptr;
     if (timing) ++c->run_counter;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], stream));
-    if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream)) != RS_OK) return rc;
+    if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream, c->streamed)) != RS_OK) return rc;
     RS_CUDA_CHECK(cudaEventRecord(c->fit_done, stream));
     if (ev) {
         RS_CUDA_CHECK(cudaEventRecord(ev[1], stream));
@@ -356,6 +358,7 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_keys);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->fit_done) cudaEventDestroy(c->fit_done);
+    if (c->streamed) cudaEventDestroy(c->streamed);
     for (cudaEvent_t e : c->chunk_events)
         if (e) cudaEventDestroy(e);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
@@ -451,7 +454,7 @@ int rs_cape_stream_wait_fit(rs_cape_ctx* c, void* stream)
         set_last_error("rs_cape_stream_wait_fit: null context");
         return RS_ERR_INVALID_ARG;
     }
-    RS_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->fit_done, 0));
+    RS_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->streamed, 0));
     return RS_OK;
 }
 

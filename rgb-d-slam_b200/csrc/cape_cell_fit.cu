@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128) cape_cell_finish_kernel(const CellFitPara
 }
 
 template <int CS>
-int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream)
+int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream, cudaEvent_t streamed)
 {
     using Geo = Geometry<CS>;
     constexpr size_t smem = size_t(WARPS) * Geo::WARP_BYTES;
@@ -392,6 +392,7 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
     const int grid = (p.total_items + WARPS - 1) / WARPS;
     kernel<<<grid, WARPS * 32, smem, stream>>>(tmap, p, cells);
     RS_LAUNCH_CHECK();
+    if (streamed) RS_CUDA_CHECK(cudaEventRecord(streamed, stream));   // the HBM-bound part is over: other streams may start
     const int total = prm.batch * prm.vc * prm.hc;
     cape_cell_finish_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p, cells, total);
     RS_LAUNCH_CHECK();
@@ -404,10 +405,11 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
 int cape_cell_fit_box_rows(int cell) { return cell == 20 ? Geometry<20>::R : (cell == 40 ? Geometry<40>::R : 0); }
 int cape_cell_fit_box_cells() { return CELLS_PER_ITEM; }
 
-int launch_cape_cell_fit(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream)
+int launch_cape_cell_fit(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream,
+                         cudaEvent_t streamed)
 {
-    if (prm.cell == 20) return launch_variant<20>(tmap, prm, cells, stream);
-    if (prm.cell == 40) return launch_variant<40>(tmap, prm, cells, stream);
+    if (prm.cell == 20) return launch_variant<20>(tmap, prm, cells, stream, streamed);
+    if (prm.cell == 40) return launch_variant<40>(tmap, prm, cells, stream, streamed);
     set_last_error("cape_cell_fit: unsupported cell size (built for 20 and 40 px)");
     return RS_ERR_INVALID_ARG;
 }

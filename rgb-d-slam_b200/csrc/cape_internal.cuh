@@ -17,7 +17,9 @@ struct CellFitParams {
     int items_per_strip, total_items;  // filled by the launcher
 };
 
-int launch_cape_cell_fit(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream);
+// `streamed` (may be null) is recorded after the streaming kernel K1a, before the per-cell fit kernel K1b
+int launch_cape_cell_fit(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_out* cells, cudaStream_t stream,
+                         cudaEvent_t streamed);
 // TMA box of the plane-fit kernel: {cell px, cape_cell_fit_box_cells() cells, cape_cell_fit_box_rows(cell) rows}
 int cape_cell_fit_box_rows(int cell);
 int cape_cell_fit_box_cells();
