@@ -17,10 +17,10 @@
 // the pivoted Cholesky factor of the column-scaled J^T J (same R up to row signs, to which lmpar is invariant), and
 // Q^T r = R^-T P^T J^T r. The trust-region logic (lmpar, qrsolv, ratio tests, stop codes 1-8, nfev accounting incl.
 // the redundant f(x) of NumericalDiff) is MINPACK's, so iterates follow the reference's path up to rounding.
-//   pose_ransac_kernel   : one CTA per frame, one warp per hypothesis, chunks of WARPS hypotheses with the
-//                          reference's serial best-so-far / early-stop rule applied between chunks by thread 0
-//                          (hypotheses are independent: each LM starts from the current pose), then the final LM
-//                          on the winning inlier set.
+//   pose_ransac_kernel   : one CTA per frame, one warp per hypothesis; warps claim hypothesis indices dynamically
+//                          (hypotheses are independent: each LM starts from the current pose) and the reference's
+//                          serial best-so-far / early-stop rule is applied in iteration order as results complete;
+//                          then the final LM on the winning inlier set.
 //   pose_variance_kernel : one warp per Monte-Carlo sample (perturbed copy of the inlier set in shared memory).
 //   pose_covariance_kernel: one warp per frame, 6x6 covariance (one entry per lane, summed in sample order) + validity.
 // FP64 throughout (forward differences with h = 1.49e-8 |x| on mm-scale coordinates need it).
@@ -35,9 +35,8 @@ namespace {
 
 constexpr int WARPS = 8;             // warps per CTA of the Monte-Carlo kernel (one sample each)
 constexpr int THREADS = WARPS * 32;
-// RANSAC: hypotheses evaluated concurrently per frame. The reference never stops before iteration 3, so the first
-// chunk (iterations 0..3) is always needed; larger chunks would only add hypotheses the serial reference skips
-// after its early stop (and the CTA waits for the slowest LM of a chunk).
+// RANSAC: warps per frame, each running one hypothesis at a time. The reference never stops before iteration 3, so
+// hypotheses 0..3 are always needed; beyond them the warps run ahead of the serial early-stop rule speculatively.
 constexpr int RWARPS = 4;
 constexpr int RTHREADS = RWARPS * 32;
 constexpr unsigned FULL = 0xffffffffu;
@@ -674,7 +673,7 @@ __device__ __forceinline__ void lmpar(WarpLM& S)
 // kernel: the body is ~4k instructions and the serial lane-0 chains are latency bound, so instruction-cache residency
 // matters, and inlining lets the compiler see that S and the feature arrays live in shared memory (LDS, not generic LD).
 __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m,
-                                             const int maxfev, const int lane)
+                                             const int maxfev, const int lane, const volatile int* abort = nullptr)
 {
     if (m < 6 || maxfev <= 0) return 0;  // ImproperInputParameters
     if (lane == 0) make_xform(S.x, S.T);
@@ -691,6 +690,8 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
 
 #pragma unroll 1
     while (true) {
+        // a speculative RANSAC hypothesis is dropped as soon as the serial rule has stopped the loop before it
+        if (abort && *abort) return 0;
         // ---- Jacobian set-up: R'(x) on lane 0, R'(x + h_k e_k) on lanes 1..3, then the 27 difference quotients ----
         if (lane < 4) {
             double xx[6];
@@ -877,7 +878,8 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
 // compute_optimized_global_pose (pose_optimization.cpp:302-359) for the whole warp. x0 -> S.x; returns success and
 // leaves the optimised coefficients in S.x.
 __device__ __forceinline__ bool optimize_pose_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const double* x0,
-                                                   const int m, const double score, const int maxfev, const int lane)
+                                                   const int m, const double score, const int maxfev, const int lane,
+                                                   const volatile int* abort = nullptr)
 {
     bool finite = true;
 #pragma unroll
@@ -886,7 +888,7 @@ __device__ __forceinline__ bool optimize_pose_warp(WarpLM& S, const Problem& P, 
     if (lane == 0)
         for (int j = 0; j < 6; ++j) S.x[j] = x0[j];
     __syncwarp();
-    const int status = lm_minimize_warp(S, P, K, m, maxfev, lane);
+    const int status = lm_minimize_warp(S, P, K, m, maxfev, lane, abort);
     if (status <= 0) return false;
     // the reference rejects a pose whose [position, Euler angles] vector has a NaN: that vector is finite exactly
     // when the coefficients and the quaternion built from them are
@@ -1008,14 +1010,20 @@ __global__ void __launch_bounds__(THREADS) pose_prepare_kernel(const PoseBuffers
     }
 }
 
+constexpr int RRING = 8;   // hypotheses that may be in flight or finished-but-unapplied beyond the serial rule's position
+
 struct RansacShared {
     double best_x[6];
     double max_score;
     int best_inliers, best_iteration, can_quit, started;
-    double hyp_x[RWARPS][6];
-    double hyp_score[RWARPS];
-    int hyp_ok[RWARPS];
-    int hyp_inliers[RWARPS];
+    int next_iter;   // next hypothesis index to hand out
+    int applied;     // hypotheses whose bookkeeping has been applied, in iteration order
+    int lock;        // guards the in-order bookkeeping
+    int done[RRING]; // iteration + 1 once the slot's result is complete
+    double hyp_x[RRING][6];
+    double hyp_score[RRING];
+    int hyp_ok[RRING];
+    int hyp_inliers[RRING];
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) / 16 * 16; }
@@ -1026,7 +1034,7 @@ struct RansacSmem {
     double* obs;
     double* map;
     WarpLM* lm;
-    unsigned* hyp_mask;   // [RWARPS][words]
+    unsigned* hyp_mask;   // [RRING][words]
     unsigned* best_mask;  // [words]
     short* subset;        // [RWARPS][RS_MAX_SUBSET]
     short* inlier_idx;    // [M]
@@ -1046,7 +1054,7 @@ __host__ __device__ inline size_t ransac_carve(RansacSmem* s, unsigned char* bas
     unsigned char* lm = take(sizeof(WarpLM) * RWARPS);
     unsigned char* sh = take(sizeof(RansacShared));
     unsigned char* type = take(sizeof(int32_t) * M);
-    unsigned char* hm = take(sizeof(unsigned) * RWARPS * words);
+    unsigned char* hm = take(sizeof(unsigned) * RRING * words);
     unsigned char* bm = take(sizeof(unsigned) * words);
     unsigned char* sub = take(sizeof(short) * RWARPS * RS_MAX_SUBSET);
     unsigned char* ii = take(sizeof(short) * M);
@@ -1088,6 +1096,8 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
     if (threadIdx.x == 0) {
         sh.max_score = 1.0;
         sh.best_inliers = 0, sh.best_iteration = -1, sh.can_quit = 0, sh.started = 0;
+        sh.next_iter = 0, sh.applied = 0, sh.lock = 0;
+        for (int k = 0; k < RRING; ++k) sh.done[k] = 0;
         for (int j = 0; j < 6; ++j) sh.best_x[j] = x0[j];
     }
     for (int i = threadIdx.x; i < words; i += blockDim.x) sm.best_mask[i] = 0u;
@@ -1097,22 +1107,88 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
     const unsigned inliersToStop = unsigned(ceil(double(n) * kEarlyStopProportion));
     WarpLM& S = sm.lm[warp];
     short* subset = sm.subset + warp * RS_MAX_SUBSET;
-    unsigned* hmask = sm.hyp_mask + warp * words;
     Problem P;
     P.type = sm.type, P.obs = sm.obs, P.map = sm.map, P.M = M;
+    volatile int* v_can_quit = &sh.can_quit;
+    volatile int* v_next = &sh.next_iter;
+    volatile int* v_applied = &sh.applied;
+    volatile int* v_done = sh.done;
+
+    // The reference's serial bookkeeping (:151-227), applied strictly in iteration order by whoever holds the lock:
+    // every finished hypothesis whose predecessors have all been applied is folded into the best-so-far state; the early
+    // stop freezes the state, exactly where the serial loop would have left it.
+    auto apply_ready = [&]() {
+        while (!*v_can_quit) {
+            const int i = *v_applied;
+            if (i >= maxIterations || v_done[i % RRING] != i + 1) break;
+            __threadfence_block();
+            const int slot = i % RRING;
+            ++sh.started;
+            if (sh.hyp_ok[slot]) {
+                const double hs = sh.hyp_score[slot];
+                if (hs >= 1.0) {
+                    const bool canOverload =
+                            (hs > sh.max_score) || (fabs(hs - sh.max_score) <= 0.1 && sh.best_inliers < sh.hyp_inliers[slot]);
+                    if (canOverload) {
+                        sh.max_score = hs;
+                        for (int j = 0; j < 6; ++j) sh.best_x[j] = sh.hyp_x[slot][j];
+                        for (int k = 0; k < words; ++k) sm.best_mask[k] = sm.hyp_mask[slot * words + k];
+                        sh.best_inliers = sh.hyp_inliers[slot];
+                        sh.best_iteration = i;
+                    }
+                    if (i >= 3 && unsigned(sh.best_inliers) > inliersToStop) *v_can_quit = 1;
+                }
+            }
+            __threadfence_block();
+            *v_applied = i + 1;
+        }
+    };
 
     rs_pose_out* out = buf.out + b;
-    // One loop, one LM call site (the LM body is inlined once): passes 0.. are RANSAC chunks of RWARPS hypotheses, the
-    // last pass is the final optimisation on the winning inlier set, run by warp 0 after the others have left.
+    // One loop, one LM call site (the LM body is inlined once). Hypothesis passes: every warp keeps claiming the next
+    // iteration index (hypotheses are independent: each LM starts from the current pose) up to RRING ahead of the serial
+    // rule; a hypothesis that finishes after the early stop is simply never applied, and one still running is dropped at
+    // its next LM iteration. When nothing is left to claim the warps meet once, warp 0 runs the final optimisation on
+    // the winning inlier set and the others leave.
     bool finalPass = false;
-    for (int chunk = 0;; chunk += RWARPS) {
-        const int it = chunk + warp;
+    for (;;) {
+        int it = -1;
+        if (!finalPass) {
+            if (lane == 0) {
+                while (!*v_can_quit) {
+                    const int cur = *v_next;
+                    if (cur >= maxIterations) break;
+                    if (cur >= *v_applied + RRING) {   // ring full: help the bookkeeping catch up, or wait for it
+                        if (v_done[*v_applied % RRING] == *v_applied + 1 && atomicCAS(&sh.lock, 0, 1) == 0) {
+                            apply_ready();
+                            __threadfence_block();
+                            atomicExch(&sh.lock, 0);
+                        }
+                        else
+                            __nanosleep(200);
+                        continue;
+                    }
+                    if (atomicCAS(&sh.next_iter, cur, cur + 1) == cur) {
+                        it = cur;
+                        break;
+                    }
+                }
+            }
+            it = __shfl_sync(FULL, it, 0);
+            if (it < 0) {
+                __syncthreads();   // every warp arrives here exactly once; all claimed hypotheses are finished
+                if (threadIdx.x == 0) apply_ready();
+                __syncthreads();
+                if (warp != 0) return;
+                finalPass = true;
+            }
+        }
         int cnt = 0, m = 0;
         double cumulated = 0.0;
         double xs[6];
         if (!finalPass) {
             // ---- random subset: ransac::get_random_subset_with_score (ransac.hpp:77-103) ----
-            if (lane == 0 && it < maxIterations) {
+            if (lane == 0) {
                 int32_t* used = buf.subsets_used + (size_t(b) * buf.max_iterations + it) * RS_MAX_SUBSET;
                 if (buf.subsets_in) {
                     // host-drawn (std::mt19937 + std::shuffle), already in the reference's prepended order
@@ -1176,7 +1252,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
         if (finalPass && !ok) return;
         if (ok) {
             P.n = cnt;
-            ok = optimize_pose_warp(S, P, prm.K, xs, m, cumulated, prm.lm_max_fev, lane);
+            ok = optimize_pose_warp(S, P, prm.K, xs, m, cumulated, prm.lm_max_fev, lane, finalPass ? nullptr : v_can_quit);
         }
         if (finalPass) {
             if (!ok) {
@@ -1201,6 +1277,8 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
             for (int k = lane; k < cnt; k += 32) buf.inlier_idx[size_t(b) * M + k] = sm.inlier_idx[k];
             return;
         }
+        const int slot = it % RRING;
+        unsigned* hmask = sm.hyp_mask + slot * words;
         int nIn = 0;
         double score = 0.0;
         if (ok) {
@@ -1234,38 +1312,21 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
             }
         }
         if (lane == 0) {
-            sh.hyp_ok[warp] = ok ? 1 : 0;
-            sh.hyp_score[warp] = score;
-            sh.hyp_inliers[warp] = nIn;
-            for (int j = 0; j < 6; ++j) sh.hyp_x[warp][j] = S.x[j];
-        }
-        __syncthreads();
-        // ---- the reference's serial bookkeeping over this chunk, in iteration order (:151-227) ----
-        if (threadIdx.x == 0) {
-            for (int w = 0; w < RWARPS; ++w) {
-                const int iteration = chunk + w;
-                if (iteration >= maxIterations || sh.can_quit) break;
-                ++sh.started;
-                if (!sh.hyp_ok[w]) continue;
-                const double hs = sh.hyp_score[w];
-                if (hs < 1.0) continue;
-                const bool canOverload =
-                        (hs > sh.max_score) || (fabs(hs - sh.max_score) <= 0.1 && sh.best_inliers < sh.hyp_inliers[w]);
-                if (canOverload) {
-                    sh.max_score = hs;
-                    for (int j = 0; j < 6; ++j) sh.best_x[j] = sh.hyp_x[w][j];
-                    for (int k = 0; k < words; ++k) sm.best_mask[k] = sm.hyp_mask[w * words + k];
-                    sh.best_inliers = sh.hyp_inliers[w];
-                    sh.best_iteration = iteration;
-                }
-                if (iteration >= 3 && unsigned(sh.best_inliers) > inliersToStop) sh.can_quit = 1;
+            sh.hyp_ok[slot] = ok ? 1 : 0;
+            sh.hyp_score[slot] = score;
+            sh.hyp_inliers[slot] = nIn;
+            for (int j = 0; j < 6; ++j) sh.hyp_x[slot][j] = S.x[j];
+            __threadfence_block();
+            v_done[slot] = it + 1;
+            // fold in whatever is ready; if another warp holds the lock it re-checks after releasing it
+            while (!*v_can_quit && v_done[*v_applied % RRING] == *v_applied + 1 && *v_applied < maxIterations) {
+                if (atomicCAS(&sh.lock, 0, 1) != 0) break;
+                apply_ready();
+                __threadfence_block();
+                atomicExch(&sh.lock, 0);
             }
         }
-        __syncthreads();
-        if (sh.can_quit || chunk + RWARPS >= maxIterations) {
-            if (warp != 0) return;
-            finalPass = true;
-        }
+        __syncwarp();
     }
 }
 
