@@ -251,10 +251,14 @@ __device__ __forceinline__ void load_feature(const Problem& P, const int k, int&
 {
     const int i = P.idx ? int(P.idx[k]) : k;
     type = P.type[i];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        o[c] = P.obs[c * P.M + i];
-        m[c] = P.map[c * P.M + i];
+    o[0] = P.obs[i], o[1] = P.obs[P.M + i];
+    m[0] = P.map[i], m[1] = P.map[P.M + i], m[2] = P.map[2 * P.M + i];
+    if (type == RS_FEAT_POINT) {   // a point uses (u, v) and (X, Y, Z) only
+        o[2] = 0.0, o[3] = 0.0, m[3] = 0.0;
+    }
+    else {
+        o[2] = P.obs[2 * P.M + i], o[3] = P.obs[3 * P.M + i];
+        m[3] = P.map[3 * P.M + i];
     }
 }
 
