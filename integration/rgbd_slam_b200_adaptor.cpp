@@ -49,6 +49,27 @@ class CapeContext
     }
     ~CapeContext() { rs_cape_destroy(_ctx); }
 
+    // RGBD_SLAM::rectify_depth (rgbd_slam.cpp:85-97 -> Depth_Map_Transformation::rectify_depth): instead of rectifying on
+    // the host before track(), switch the device-side rectification on once; every find_primitives call below then
+    // re-projects its input into camera 1's image before the plane fit (same last-writer-wins result as the serial scan).
+    void enable_depth_rectification()
+    {
+        const matrix44 t = Parameters::get_camera_2_to_camera_1_transformation();
+        double rowMajor[16];
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) rowMajor[4 * r + c] = t(r, c);   // Eigen stores column-major
+        if (rs_cape_set_rectification(_ctx, rowMajor, 1) != RS_OK)
+            throw std::runtime_error(std::string("rs_cape_set_rectification: ") + rs_last_error());
+    }
+
+    // Raw sensor image (CV_16U, what cv::imread(IMREAD_ANYDEPTH) returns in examples/main_TUM.cpp:221): the
+    // convertTo(CV_32FC1, alpha) of :242 happens on the device, the PCIe copy is half the size.
+    int run_u16(const cv::Mat_<ushort>& rawDepth, const double alpha, const rs_cape_outputs& out)
+    {
+        if (not rawDepth.isContinuous()) throw std::invalid_argument("depth image must be continuous");
+        return rs_cape_run_u16(_ctx, rawDepth.ptr<ushort>(), alpha, 1, utils::Random::_seed, &out);
+    }
+
     // Drop-in body of Primitive_Detection::find_primitives (primitive_detection.cpp:119-166). The organized cloud
     // argument of the reference is not needed: the back-projection is fused into the plane-fit kernel.
     void find_primitives(const cv::Mat_<float>& depthImage,
