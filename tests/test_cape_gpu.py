@@ -157,3 +157,18 @@ def test_rectify_depth_matches_oracle_bit_exact(det, transform):
     plain = det.find_primitives(depth[:1], seed=0)
     ref_plain = ol.cape_run(depth[:1], seed=0)
     parity.assert_frame_match(ref_plain, plain, 0)
+
+
+def test_new_entry_points_fail_loudly(det):
+    depth = rs.synth.scene_v0_batch(0, 1)
+    fresh = rs.PrimitiveDetection(640, 480, 20, max_batch=1)
+    with pytest.raises(rs.RsError):
+        fresh.rectify_depth(depth)                             # rs_cape_set_rectification has never been called
+    fresh.close()
+    with pytest.raises(rs.RsError):
+        det.find_primitives_u16(np.zeros((9, 480, 640), np.uint16))   # batch > max_batch
+    with pytest.raises(ValueError):
+        det.find_primitives_u16(np.zeros((1, 100, 100), np.uint16))   # wrong geometry
+    # an all-zero sensor image is an empty frame, not an error
+    out = det.find_primitives_u16(np.zeros((1, 480, 640), np.uint16), alpha=0.2)
+    assert out["info"][0]["n_planar_cells"] == 0 and not out["plane_labels"].any()

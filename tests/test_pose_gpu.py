@@ -182,3 +182,14 @@ def test_invalid_arguments(solver):
         solver.compute_optimized_pose(cur, matches, n, solver.options(max_iterations=5000))
     with pytest.raises(rs.RsError):
         solver.solve_device(2, solver.options(rng_mode=rs.abi.RS_RNG_REFERENCE))
+
+
+def test_begin_end_split_matches_blocking_call(solver):
+    truth, cur, matches, n = rs.synth.pose_batch(700, 4, M)
+    opts = solver.options(seed=11, rng_mode=rs.abi.RS_RNG_DEVICE)
+    want, wmask = solver.compute_optimized_pose(cur, matches, n, opts)
+    solver.compute_optimized_pose_begin(cur, matches, n, opts)
+    got, gmask = solver.compute_optimized_pose_end()
+    assert want.tobytes() == got.tobytes() and wmask.tobytes() == gmask.tobytes()
+    with pytest.raises(RuntimeError):
+        solver.compute_optimized_pose_end()                    # nothing pending
