@@ -49,7 +49,7 @@ typedef struct rs_cell_out {
     double mse;         /* DBL_MAX when no fit was made                                           */
     double score;
     float tol;          /* _cellDistanceTols[cell], primitive_detection.cpp:201-220               */
-    int32_t reserved;
+    int32_t hist_bin;   /* Histogram bin of the normal (init_histogram, primitive_detection.cpp:239-265), -1 if not planar */
 } rs_cell_out;
 
 /* One plane segment (entry k of _planeSegments, primitive_detection.hpp:216) after merge_planes. */

@@ -127,7 +127,7 @@ bool PlaneSeg::can_be_merged(const PlaneSeg& p, const double maxMatchDistance) c
     return dot(normal, p.normal) > maximumMergeAngle and std::fabs(dot(normal, p.centroid) + d) < maxMatchDistance;
 }
 
-void cell_record(const PlaneSeg& s, const float tol, rs_cell_out& o)
+void cell_record(const PlaneSeg& s, const float tol, const int cellSize, rs_cell_out& o)
 {
     o.count = s.count;
     o.planar = s.planar ? 1 : 0;
@@ -140,7 +140,15 @@ void cell_record(const PlaneSeg& s, const float tol, rs_cell_out& o)
     o.mse = s.mse;
     o.score = s.score;
     o.tol = tol;
-    o.reserved = 0;
+    // bin of init_histogram (primitive_detection.cpp:239-265, histogram.hpp:35-62), Histogram<cellSize>
+    o.hist_bin = -1;
+    if (s.planar) {
+        const double theta = std::acos(-s.normal.z), phi = std::atan2(s.normal.x, s.normal.y);
+        const int xQ = static_cast<int>(std::floor((cellSize - 1) * (theta - 0.0) / (M_PI - 0.0)));
+        int yQ = 0;
+        if (xQ > 0) yQ = static_cast<int>(std::floor((cellSize - 1) * (phi - (-M_PI)) / (M_PI - (-M_PI))));
+        o.hist_bin = yQ * cellSize + xQ;
+    }
 }
 
 // point_coordinates.cpp:79-83 (static inverse of the intrinsics) applied to (u, v, 1).
@@ -789,7 +797,7 @@ void cape_run(const CapeConfig& cfg, const float* depth, const uint32_t seed, Ca
 
     // outputs
     out.cells.resize(Nc);
-    for (int i = 0; i < Nc; ++i) cell_record(det.grid[i], det.tols[i], out.cells[i]);
+    for (int i = 0; i < Nc; ++i) cell_record(det.grid[i], det.tols[i], cfg.cell, out.cells[i]);
     out.plane_grid = det.gridPlane;
     out.cyl_labels = det.gridCyl;
     out.cyl_region_seg = det.gridCylRegionSeg;

@@ -56,7 +56,7 @@ void cape_cell_fit(const CapeConfig& cfg, const float* depth, std::vector<PlaneS
 // Whole find_primitives (primitive_detection.cpp:119-166) for one frame. seed = utils::Random::_seed.
 void cape_run(const CapeConfig& cfg, const float* depth, uint32_t seed, CapeFrame& out);
 
-void cell_record(const PlaneSeg& s, float tol, rs_cell_out& o);
+void cell_record(const PlaneSeg& s, float tol, int cellSize, rs_cell_out& o);
 
 // Depth_Map_Transformation::rectify_depth (depth_map_transformation.cpp:23-87): depth image of camera 2 re-projected
 // into the image of camera 1, serial row-major scan (the MAKE_DETERMINISTIC build), last writer wins.

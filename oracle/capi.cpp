@@ -80,7 +80,7 @@ int orc_cape_cell_fit(int W, int H, int cell, double fx, double fy, double cx, d
         std::vector<PlaneSeg> grid;
         std::vector<float> tols, cl;
         cape_cell_fit(cfg, depth + size_t(b) * W * H, grid, tols, cloud ? &cl : nullptr);
-        for (int i = 0; i < Nc; ++i) cell_record(grid[i], tols[i], cells[size_t(b) * Nc + i]);
+        for (int i = 0; i < Nc; ++i) cell_record(grid[i], tols[i], cell, cells[size_t(b) * Nc + i]);
         if (cloud) std::memcpy(cloud + size_t(b) * 3 * W * H, cl.data(), sizeof(float) * cl.size());
     }
     return 0;

@@ -16,7 +16,7 @@ RS_MAX_SUBSET = 16
 # numpy structured dtypes with the exact C layout (align=True reproduces the compiler's padding)
 cell_dtype = np.dtype([("count", "<i4"), ("planar", "<i4"), ("S", "<f8", (9,)), ("centroid", "<f8", (3,)),
                        ("normal", "<f8", (3,)), ("d", "<f8"), ("mse", "<f8"), ("score", "<f8"), ("tol", "<f4"),
-                       ("reserved", "<i4")], align=True)
+                       ("hist_bin", "<i4")], align=True)
 plane_dtype = np.dtype([("merge_label", "<i4"), ("planar", "<i4"), ("is_final", "<i4"), ("count", "<i4"),
                         ("S", "<f8", (9,)), ("centroid", "<f8", (3,)), ("normal", "<f8", (3,)), ("d", "<f8"),
                         ("mse", "<f8"), ("score", "<f8"), ("n_boundary", "<i4"), ("boundary_offset", "<i4")], align=True)

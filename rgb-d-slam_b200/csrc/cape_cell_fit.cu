@@ -368,9 +368,21 @@ __global__ void __launch_bounds__(128) cape_cell_finish_kernel(const CellFitPara
     rec[6] = make_double2(pm.c[2], pm.n[0]);
     rec[7] = make_double2(pm.n[1], pm.n[2]);
     rec[8] = make_double2(pm.d, pm.mse);
+    // bin of init_histogram (primitive_detection.cpp:239-265, histogram.hpp:35-62): computed here, where every cell of the
+    // batch has its own thread, instead of serially per frame in the segmentation kernel
+    int bin = -1;
+    if (pm.planar) {
+        const int cs = prm.cell;
+        const double theta = acos(-pm.n[2]);
+        const double phi = atan2(pm.n[0], pm.n[1]);
+        const int xQ = static_cast<int>(floor((cs - 1) * (theta - 0.0) / (kPi - 0.0)));
+        int yQ = 0;
+        if (xQ > 0) yQ = static_cast<int>(floor((cs - 1) * (phi - (-kPi)) / (kPi - (-kPi))));
+        bin = yQ * cs + xQ;
+    }
     double2 tail;
     tail.x = pm.score;
-    tail.y = __hiloint2double(0, __float_as_int(tol));  // {float tol, int32 reserved}
+    tail.y = __hiloint2double(bin, __float_as_int(tol));  // {float tol, int32 hist_bin}
     rec[9] = tail;
 }
 

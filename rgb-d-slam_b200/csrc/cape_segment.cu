@@ -30,6 +30,8 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int STAGE_CELLS = 128;  // cells gathered per round of an ordered sum
 constexpr int MAX_ROWS = 64;      // cell rows / columns the bit planes can hold
+constexpr int PC_CAP = 200;       // cylinder regions up to this many cells keep their projected normals / centroids in smem
+constexpr int UBUF = 3 * RS_CYL_RANSAC_ITERS + 3;  // uniforms one RANSAC run can consume
 typedef unsigned long long u64;
 
 struct Scalars {
@@ -47,6 +49,10 @@ struct Smem {
     double* cmse;  // [Nc]
     double* val;   // [Nc] scratch values (cylinder branch)
     double* stage; // [STAGE_CELLS][10] operands of the ordered sums
+    double* pnpc;  // [2][PC_CAP][3] projected normals / centroids of the cylinder branch (HBM scratch beyond PC_CAP)
+    double* ubuf;  // [UBUF] uniforms of the current cylinder RANSAC run
+    double* ckx;   // [MAX_ROWS] back-projection factor of every cell column's centre pixel
+    double* cky;   // [MAX_ROWS] ... of every cell row's centre pixel
     double* pln;   // [RS_MAX_PLANES][3] planes (compact copy for predicates; sums live in the global record)
     double* plc;   // [RS_MAX_PLANES][3]
     double* pld;   // [RS_MAX_PLANES]
@@ -83,6 +89,10 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int Nc, in
     double* cmse = reinterpret_cast<double*>(take(sizeof(double) * Nc));
     double* val = reinterpret_cast<double*>(take(sizeof(double) * Nc));
     double* stage = reinterpret_cast<double*>(take(sizeof(double) * STAGE_CELLS * 10));
+    double* pnpc = reinterpret_cast<double*>(take(sizeof(double) * 6 * PC_CAP));
+    double* ubuf = reinterpret_cast<double*>(take(sizeof(double) * UBUF));
+    double* ckx = reinterpret_cast<double*>(take(sizeof(double) * MAX_ROWS));
+    double* cky = reinterpret_cast<double*>(take(sizeof(double) * MAX_ROWS));
     double* pln = reinterpret_cast<double*>(take(sizeof(double) * 3 * RS_MAX_PLANES));
     double* plc = reinterpret_cast<double*>(take(sizeof(double) * 3 * RS_MAX_PLANES));
     double* pld = reinterpret_cast<double*>(take(sizeof(double) * RS_MAX_PLANES));
@@ -99,7 +109,7 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int Nc, in
     unsigned char* u8[4];
     for (int i = 0; i < 4; ++i) u8[i] = take(size_t(Nc));
     if (s) {
-        s->cn = cn, s->cc = cc, s->cd = cd, s->cmse = cmse, s->val = val, s->stage = stage;
+        s->cn = cn, s->cc = cc, s->cd = cd, s->cmse = cmse, s->val = val, s->stage = stage, s->pnpc = pnpc, s->ubuf = ubuf, s->ckx = ckx, s->cky = cky;
         s->pln = pln, s->plc = plc, s->pld = pld, s->sc = sc, s->tol = tol, s->cz = cz, s->hist = hist;
         s->U = planes64, s->ACT = planes64 + MAX_ROWS, s->EL = planes64 + 2 * MAX_ROWS, s->ER = planes64 + 3 * MAX_ROWS;
         s->EU = planes64 + 4 * MAX_ROWS, s->ED = planes64 + 5 * MAX_ROWS;
@@ -220,6 +230,10 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
                                  const int Nc, const int lane)
 {
     Scalars& sc = *s.sc;
+    if (m <= PC_CAP) {   // the usual case: keep the region's projected normals / centroids in shared memory
+        pn = s.pnpc;
+        pc = s.pnpc + 3 * PC_CAP;
+    }
     if (sc.n_cyl_regions >= RS_MAX_CYL_REGIONS) {
         if (lane == 0) sc.status = RS_ERR_CAPACITY;
         __syncwarp();
@@ -292,18 +306,22 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
             const unsigned accepted = static_cast<unsigned>(floor(0.9 * nIds));
             double minHypothesisDist = static_cast<double>(maxSqrtDist * static_cast<float>(nIds));
             for (int j = lane; j < m; j += 32) best[j] = 0;
+            // this run's uniforms (3 per iteration, consumed in order from the frame's stream), one coalesced fetch
+            const int ubase = sc.uniform_cursor;
+            for (int k = lane; k < UBUF - 3; k += 32) s.ubuf[k] = (ubase + k < prm.n_uniforms) ? prm.uniforms[ubase + k] : -1.0;
             __syncwarp();
             for (int it = 0; it < RS_CYL_RANSAC_ITERS; ++it) {
                 if (lane == 0) {
                     int id[3];
                     for (int k = 0; k < 3; ++k) {
-                        double u = 0.0;
-                        if (sc.uniform_cursor < prm.n_uniforms)
-                            u = prm.uniforms[sc.uniform_cursor++];
-                        else
+                        double u = s.ubuf[3 * it + k];
+                        if (u < 0.0) {
+                            u = 0.0;
                             sc.status = RS_ERR_CAPACITY;
+                        }
                         id[k] = s.ids[static_cast<unsigned>(floor(u * static_cast<double>(static_cast<unsigned>(nIds))))];
                     }
+                    sc.uniform_cursor = ubase + 3 * (it + 1);
                     const double* n1 = pn + 3 * id[0];
                     const double* n2 = pn + 3 * id[1];
                     const double* n3 = pn + 3 * id[2];
@@ -325,6 +343,8 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
                 }
                 __syncwarp();
                 const double radius = sc.radius, invr2 = sc.inv_r2, e0 = sc.center[0], e1 = sc.center[1], e2 = sc.center[2];
+                double partial = 0.0;   // this lane's share of the MSAC cost (any order: only used to rule hypotheses out)
+                int candCount = 0;
                 for (int j = lane; j < m; j += 32) {
                     double v = -1.0;  // not part of this RANSAC round
                     unsigned char in = 0;
@@ -339,23 +359,31 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
                         }
                         else
                             v = maxSqrtDistD;
+                        partial += v;
                     }
                     s.val[j] = v;
                     cand[j] = in;
+                    candCount += in;
                 }
+                candCount = __reduce_add_sync(FULL, candCount);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(FULL, partial, o);
                 __syncwarp();
-                int better = 0, candCount = 0;
+                // The reference accumulates the cost in cell order and compares it with the best so far. A sum of at most
+                // Nc non-negative doubles in any order is within Nc * 2^-53 of it, so a hypothesis whose unordered sum is
+                // clearly above the threshold is rejected without the serial pass; otherwise the ordered sum decides.
+                int better = 0;
                 double dist = 0.0;
-                if (lane == 0) {
-                    // MSAC cost in cell order, exactly as the reference accumulates it
-                    for (int j = 0; j < m; ++j) {
-                        const double v = s.val[j];
-                        if (v >= 0.0) dist += v;
-                        candCount += cand[j];
+                if (!(partial > minHypothesisDist * (1.0 + 1e-9))) {
+                    if (lane == 0) {
+                        for (int j = 0; j < m; ++j) {
+                            const double v = s.val[j];
+                            if (v >= 0.0) dist += v;
+                        }
+                        better = dist < minHypothesisDist ? 1 : 0;
                     }
-                    better = dist < minHypothesisDist ? 1 : 0;
+                    better = __shfl_sync(FULL, better, 0);
                 }
-                better = __shfl_sync(FULL, better, 0);
                 bool stop = false;
                 if (better) {
                     minHypothesisDist = __shfl_sync(FULL, dist, 0);
@@ -363,7 +391,7 @@ __device__ void cylinder_fitting(const Smem& s, const SegmentParams& prm, const 
                     best = cand;
                     cand = tmp;
                     const int prevCount = bestCount;
-                    bestCount = __shfl_sync(FULL, candCount, 0);
+                    bestCount = candCount;
                     // quirk: the early stop looks at the PREVIOUS best set (vectors swapped before the test)
                     if (static_cast<unsigned>(prevCount) > accepted) stop = true;
                 }
@@ -523,6 +551,8 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
         const int centerY = static_cast<int>(row * pixelPerCellSide + pixelPerCellSide / 2);
         s.cz[i] = __ldg(depth + size_t(centerY) * prm.W + centerX);
     }
+    for (int x = lane; x < hc; x += 32) s.ckx[x] = prm.kx[static_cast<int>(x * pixelPerCellSide + pixelPerCellSide / 2)];
+    for (int y = lane; y < vc; y += 32) s.cky[y] = prm.ky[static_cast<int>(y * pixelPerCellSide + pixelPerCellSide / 2)];
     int nPlanar = 0;
     for (int i = lane; i < Nc; i += 32) {
         const rs_cell_out& c = cells[i];
@@ -538,12 +568,7 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
         int bin = -1;
         if (c.planar) {
             ++nPlanar;
-            const double theta = acos(-c.normal[2]);
-            const double phi = atan2(c.normal[0], c.normal[1]);
-            const int xQ = static_cast<int>(floor((cs - 1) * (theta - 0.0) / (kPi - 0.0)));
-            int yQ = 0;
-            if (xQ > 0) yQ = static_cast<int>(floor((cs - 1) * (phi - (-kPi)) / (kPi - (-kPi))));
-            bin = yQ * cs + xQ;
+            bin = c.hist_bin;   // init_histogram's bin, computed by the per-cell fit kernel
             if (bin >= 0 && bin < nbins) atomicAdd(&s.hist[bin], 1);
         }
         s.bins[i] = static_cast<short>(bin);
@@ -851,9 +876,7 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
                     bits &= bits - 1;
                     const double z = static_cast<double>(s.cz[r * hc + x]);
                     if (z > 0) {
-                        const int centerX = static_cast<int>(x * pixelPerCellSide + pixelPerCellSide / 2);
-                        const int centerY = static_cast<int>(r * pixelPerCellSide + pixelPerCellSide / 2);
-                        const double px = z * prm.kx[centerX], py = z * prm.ky[centerY];
+                        const double px = z * s.ckx[x], py = z * s.cky[r];
                         if (fabs(((n0 * px + n1 * py) + n2 * z) + dd) < maxBoundaryDistance) keepBits |= 1ull << x;
                     }
                 }
@@ -865,9 +888,7 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
                 keepBits &= keepBits - 1;
                 if (o < prm.max_boundary) {
                     const double z = static_cast<double>(s.cz[r * hc + x]);
-                    const int centerX = static_cast<int>(x * pixelPerCellSide + pixelPerCellSide / 2);
-                    const int centerY = static_cast<int>(r * pixelPerCellSide + pixelPerCellSide / 2);
-                    boundary[3 * o] = z * prm.kx[centerX], boundary[3 * o + 1] = z * prm.ky[centerY], boundary[3 * o + 2] = z;
+                    boundary[3 * o] = z * s.ckx[x], boundary[3 * o + 1] = z * s.cky[r], boundary[3 * o + 2] = z;
                 }
                 ++o;
             }

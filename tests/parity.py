@@ -24,6 +24,7 @@ def assert_cells_match(ref, got, rtol=1e-4, exact_report=None):
     """Per-cell records: integer fields bit-exact; normals / d within rtol (north_star: 1e-4 relative);
     sums / mse / score tight. Returns the fraction of cells whose FP64 fields are bit-identical."""
     assert np.array_equal(ref["count"], got["count"]), "point counts differ"
+    assert np.array_equal(ref["hist_bin"], got["hist_bin"]), "histogram bins differ"
     assert np.array_equal(ref["planar"], got["planar"]), "planar flags differ at cells %s" % np.argwhere(
         ref["planar"] != got["planar"])[:8].tolist()
     np.testing.assert_allclose(got["S"], ref["S"], rtol=1e-12, atol=1e-6)
