@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
     const int nbox = nitems * NBOX;
     const int row0 = b * prm.H + cr * CS;              // first image row of the strip in the [B*H] row dimension
 
+    const uint64_t policy = l2_policy_evict_first();   // the depth image is read once; keep L2 for the records
     if (lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         for (int q = 0; q < 2; ++q)
             if (q < nbox) {
                 mbar_arrive_expect_tx(&bars[q], Geo::BOX_BYTES);
-                tma_load_3d(wbase + q * Geo::BOX_BYTES, &tmap, 0, c0 + (q / NBOX) * CELLS_PER_ITEM, row0 + (q % NBOX) * R, &bars[q]);
+                tma_load_3d_hint(wbase + q * Geo::BOX_BYTES, &tmap, 0, c0 + (q / NBOX) * CELLS_PER_ITEM, row0 + (q % NBOX) * R, &bars[q], policy);
             }
     }
     __syncwarp();
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         if (lane == 0 && q + 2 < nbox) {
             const int qn = q + 2;
             mbar_arrive_expect_tx(&bars[slot], Geo::BOX_BYTES);
-            tma_load_3d(wbase + slot * Geo::BOX_BYTES, &tmap, 0, c0 + (qn / NBOX) * CELLS_PER_ITEM, row0 + (qn % NBOX) * R, &bars[slot]);
+            tma_load_3d_hint(wbase + slot * Geo::BOX_BYTES, &tmap, 0, c0 + (qn / NBOX) * CELLS_PER_ITEM, row0 + (qn % NBOX) * R, &bars[slot], policy);
         }
         if (bq != NBOX - 1) continue;
 

@@ -45,6 +45,26 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
             : "memory");
 }
 
+// L2 cache policy for data that is read exactly once (the depth image): evict it first, so that what the kernel WRITES
+// (the per-cell records the next two kernels read back) stays resident in the 126 MB L2 instead of being pushed out by
+// 315 MB of streamed input.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy)
+{
+    asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                    smem_u32(smem_dst)),
+            "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+            : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
