@@ -172,3 +172,19 @@ def test_new_entry_points_fail_loudly(det):
     # an all-zero sensor image is an empty frame, not an error
     out = det.find_primitives_u16(np.zeros((1, 480, 640), np.uint16), alpha=0.2)
     assert out["info"][0]["n_planar_cells"] == 0 and not out["plane_labels"].any()
+
+
+def test_rectify_depth_against_committed_golden(det):
+    import hashlib
+    import json
+    import os
+    meta = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rectify_scene_v0.json")))
+    depth = rs.synth.scene_v0_batch(0, 1)
+    T = np.array(meta["transform_row_major"]).reshape(4, 4)
+    try:
+        det.set_rectification(None, enable=True)
+        assert hashlib.sha256(det.rectify_depth(depth).tobytes()).hexdigest() == meta["identity"]["sha256"]
+        det.set_rectification(T, enable=True)
+        assert hashlib.sha256(det.rectify_depth(depth).tobytes()).hexdigest() == meta["offset"]["sha256"]
+    finally:
+        det.set_rectification(None, enable=False)

@@ -138,6 +138,21 @@ def test_golden_fixture():
     np.testing.assert_allclose(r["planes"]["d"][:, :16], g["plane_d"], rtol=1e-12)
 
 
+def test_golden_rectify_and_bins():
+    import hashlib
+    import json
+    meta = json.load(open(os.path.join(GOLDEN, "rectify_scene_v0.json")))
+    depth = rs.synth.scene_v0_batch(0, 4)
+    T = np.array(meta["transform_row_major"]).reshape(4, 4)
+    ident = ol.rectify_depth(depth[:1])
+    moved = ol.rectify_depth(depth[:1], T)
+    assert hashlib.sha256(ident.tobytes()).hexdigest() == meta["identity"]["sha256"]
+    assert hashlib.sha256(moved.tobytes()).hexdigest() == meta["offset"]["sha256"]
+    assert int((moved > 0).sum()) == meta["offset"]["valid"]
+    r = ol.cape_run(depth, seed=0)
+    assert hashlib.sha256(np.ascontiguousarray(r["cells"]["hist_bin"]).tobytes()).hexdigest() == meta["hist_bin_sha256"]
+
+
 @pytest.mark.parametrize("case", ["empty", "flat", "noise"])
 def test_degenerate_frames(case):
     H, W = 480, 640

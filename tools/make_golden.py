@@ -42,6 +42,24 @@ def main():
     np.savez_compressed(os.path.join(OUT, "pose_synth_v0.npz"), frames=np.arange(4), pose=np.array(poses),
                         status=np.array(status), n_inliers=np.array(n_inl), iterations_run=np.array(iters),
                         best_iteration=np.array(best_it), cov=np.array(covs), mask=np.array(masks))
+    # rectify_depth (depth_map_transformation.cpp:23-87): identity and offset camera pair on frame 0; the images are kept
+    # as SHA-256 digests plus a few statistics (1.2 MB each otherwise), the histogram bins of frames 0..3 in full
+    import hashlib
+    import json
+    T = np.eye(4)
+    c, s_ = np.cos(0.01), np.sin(0.01)
+    T[:3, :3] = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])
+    T[:3, 3] = (25.0, -3.0, 4.0)
+    ident = ol.rectify_depth(depth[:1])
+    moved = ol.rectify_depth(depth[:1], T)
+    meta = {"transform_row_major": T.reshape(-1).tolist(),
+            "identity": {"sha256": hashlib.sha256(ident.tobytes()).hexdigest(), "valid": int((ident > 0).sum()),
+                         "sum": float(ident.astype(np.float64).sum())},
+            "offset": {"sha256": hashlib.sha256(moved.tobytes()).hexdigest(), "valid": int((moved > 0).sum()),
+                       "sum": float(moved.astype(np.float64).sum())},
+            "hist_bin_sha256": hashlib.sha256(np.ascontiguousarray(r["cells"]["hist_bin"]).tobytes()).hexdigest()}
+    with open(os.path.join(OUT, "rectify_scene_v0.json"), "w") as f:
+        json.dump(meta, f, indent=1)
     print("wrote", os.listdir(OUT))
 
 
