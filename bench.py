@@ -254,6 +254,48 @@ def main():
         det.set_rectification(None, enable=False)
         del d_rect
 
+    # ---- Kalman update of the matched map features (the step after the pose solve) ----
+    kalman = None
+    if rank == 0:
+        lib = rs.load()
+        rng = np.random.default_rng(0)
+        npt, npl = F * N_POINTS, F * N_PLANES
+
+        def spd(n, d, scale, floor):
+            a = rng.standard_normal((n, d, d)) * scale
+            return a @ a.transpose(0, 2, 1) + np.eye(d) * floor
+        px = rng.uniform(-3000, 3000, (npt, 3))
+        pz = px + rng.standard_normal((npt, 3)) * 4
+        host = [px, spd(npt, 3, 2.0, 0.1), pz, spd(npt, 3, 2.0, 0.1)]
+        nrm = rng.standard_normal((npl, 3))
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        qx = np.concatenate([nrm, rng.uniform(500, 3000, (npl, 1))], axis=1)
+        hostp = [qx, spd(npl, 4, 0.05, 1e-3), qx + rng.standard_normal((npl, 4)) * 0.01, spd(npl, 4, 0.05, 1e-3)]
+        dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in host]
+        devp = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in hostp]
+        o_x, o_P, o_s = torch.empty_like(dev[0]), torch.empty_like(dev[1]), torch.empty(npt, dtype=torch.float64, device="cuda")
+        o_m, o_st = torch.empty(npt, dtype=torch.uint8, device="cuda"), torch.empty(npt, dtype=torch.int32, device="cuda")
+        q_x, q_P, q_s = torch.empty_like(devp[0]), torch.empty_like(devp[1]), torch.empty(npl, dtype=torch.float64, device="cuda")
+        q_st = torch.empty(npl, dtype=torch.int32, device="cuda")
+
+        def kalman_step():
+            lib.rs_kalman_track_points_device(npt, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), 0.001,
+                                              o_x.data_ptr(), o_P.data_ptr(), o_s.data_ptr(), o_m.data_ptr(), o_st.data_ptr(), sptr)
+            lib.rs_kalman_track_planes_device(npl, devp[0].data_ptr(), devp[1].data_ptr(), devp[2].data_ptr(), devp[3].data_ptr(), 1e-6,
+                                              q_x.data_ptr(), q_P.data_ptr(), q_s.data_ptr(), q_st.data_ptr(), sptr)
+        for _ in range(3):
+            kalman_step()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(10):
+            kalman_step()
+        k1.record(stream)
+        torch.cuda.synchronize()
+        kal_ms = k0.elapsed_time(k1) / 10
+        kalman = {"ms_per_batch": kal_ms, "points": npt, "planes": npl, "features_per_s": (npt + npl) / (kal_ms * 1e-3),
+                  "valid": float((o_st == 0).float().mean().item()),
+                  "note": "rs_kalman_track_points_device + rs_kalman_track_planes_device on the matched features of one %d-frame batch" % F}
+
     # sanity: the timed work produced valid poses close to the synthetic truth
     out, _ = solver.download(F)
     ok_frac = float((out["status"] == 1).mean())
@@ -384,6 +426,8 @@ def main():
         }
         if rect is not None:
             line["rectify_depth"] = rect
+        if kalman is not None:
+            line["kalman_update"] = kalman
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

@@ -259,6 +259,30 @@ const char* rs_version(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t rs_launch_count(void);
 
+/* ---- Kalman update of matched map features (the step after the pose solve) -------------------
+ * Replaces tracking::SharedKalmanFilter<N, N>::get_new_state (src/tracking/kalman_filter.hpp:46-118) as called by
+ *   tracking::Point::track  (src/tracking/point_with_tracking.cpp:32-84; N = 3, Q = process_noise * I, 0.001 there) and
+ *   tracking::Plane::track  (src/tracking/plane_with_tracking.cpp:16-59,81-95; N = 4, 1e-6 there; without the polygon merge),
+ * for n features at once (one thread each). Arrays are row-major, [n][N] / [n][N][N]; points: state = world position,
+ * planes: state = (nx, ny, nz, d) with the filtered normal re-normalised. Per feature: out_status 0, or -1 / -2 when the
+ * state / measurement covariance is not a valid covariance (is_covariance_valid, covariances.hpp:13-44), -3 when the
+ * innovation covariance is singular (the reference falls back to a pseudo-inverse there; not provided), -4 when the
+ * result is not a valid covariance (the reference throws); in those cases the feature is returned unchanged and
+ * out_score = -1, as Point::track reports a refused update. out_score = |state - new state| otherwise; out_moving (points,
+ * may be NULL) = the detection left the point's position by more than its own standard deviation on some axis.
+ * Host-pointer entry points copy in and out on `device`; the _device variants take device pointers and are asynchronous. */
+int rs_kalman_track_points(int device, int n, const double* state, const double* cov, const double* meas, const double* meas_cov,
+                           double process_noise, double* out_state, double* out_cov, double* out_score, uint8_t* out_moving,
+                           int32_t* out_status);
+int rs_kalman_track_planes(int device, int n, const double* state, const double* cov, const double* meas, const double* meas_cov,
+                           double process_noise, double* out_state, double* out_cov, double* out_score, int32_t* out_status);
+int rs_kalman_track_points_device(int n, const double* state, const double* cov, const double* meas, const double* meas_cov,
+                                  double process_noise, double* out_state, double* out_cov, double* out_score,
+                                  uint8_t* out_moving, int32_t* out_status, void* stream);
+int rs_kalman_track_planes_device(int n, const double* state, const double* cov, const double* meas, const double* meas_cov,
+                                  double process_noise, double* out_state, double* out_cov, double* out_score,
+                                  int32_t* out_status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

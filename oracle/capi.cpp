@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "cape.hpp"
+#include "kalman.hpp"
 #include "pose.hpp"
 
 using namespace oracle;
@@ -46,6 +47,30 @@ void store_frame(const CapeFrame& f, int Nc, int maxBoundary, int b, const rs_ca
 }  // namespace
 
 extern "C" {
+
+int orc_kalman_new_state(int N, int M, const double* F, const double* H, const double* Q, const double* x, const double* P,
+                         const double* z, const double* R, double* x_out, double* P_out)
+{
+    if (N < 1 || N > KF_MAX || M < 1 || M > KF_MAX) return -100;
+    return kalman_new_state(N, M, F, H, Q, x, P, z, R, x_out, P_out);
+}
+
+int orc_kalman_track_points(int n, const double* x, const double* P, const double* z, const double* R, double q, double* x_out,
+                            double* P_out, double* score, uint8_t* moving, int32_t* status)
+{
+    for (int i = 0; i < n; ++i)
+        kalman_track_point(x + 3 * i, P + 9 * i, z + 3 * i, R + 9 * i, q, x_out + 3 * i, P_out + 9 * i, score + i, moving + i,
+                           status + i);
+    return 0;
+}
+
+int orc_kalman_track_planes(int n, const double* x, const double* P, const double* z, const double* R, double q, double* x_out,
+                            double* P_out, double* score, int32_t* status)
+{
+    for (int i = 0; i < n; ++i)
+        kalman_track_plane(x + 4 * i, P + 16 * i, z + 4 * i, R + 16 * i, q, x_out + 4 * i, P_out + 16 * i, score + i, status + i);
+    return 0;
+}
 
 int orc_rectify_depth(int W, int H, double fx, double fy, double cx, double cy, const double* cam2_to_cam1, const float* depth,
                       int batch, float* out)

@@ -3,7 +3,8 @@ CAPE depth-cell plane/cylinder segmentation + RANSAC/Levenberg-Marquardt pose so
 (include/rgbdslam_b200.h). The directory name contains hyphens; import it through the root shim `rgbd_slam_b200`."""
 from . import abi, sharding, synth  # noqa: F401
 from .pipeline import FramePipeline  # noqa: F401
-from .lib import PoseOptimization, PrimitiveDetection, RsError, last_error, launch_count, load, make_matches  # noqa: F401
+from .lib import (PoseOptimization, PrimitiveDetection, RsError, kalman_track_planes, kalman_track_points, last_error,  # noqa: F401
+                  launch_count, load, make_matches)
 
 __all__ = ["abi", "sharding", "synth", "FramePipeline", "PrimitiveDetection", "PoseOptimization", "RsError", "load", "last_error", "launch_count",
-           "make_matches"]
+           "make_matches", "kalman_track_points", "kalman_track_planes"]

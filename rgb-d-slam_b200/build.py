@@ -20,6 +20,8 @@ UNITS = [
     ("cape_segment.cu", ["-fmad=false"]),
     ("rectify.cu", ["-fmad=false"]),
     ("api_cape.cu", ["-fmad=false"]),
+    ("kalman.cu", ["-fmad=false"]),
+    ("api_kalman.cu", []),
     ("pose_solve.cu", []),
     ("api_pose.cu", []),
 ]

@@ -49,6 +49,10 @@ def load():
     lib.rs_cape_device_outputs.argtypes = [vp]
     lib.rs_cape_set_timing.argtypes = [vp, i32]
     lib.rs_cape_kernel_ms.argtypes = [vp, i32, vp]
+    lib.rs_kalman_track_points.argtypes = [i32, i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
+    lib.rs_kalman_track_planes.argtypes = [i32, i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+    lib.rs_kalman_track_points_device.argtypes = [i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp]
+    lib.rs_kalman_track_planes_device.argtypes = [i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
     lib.rs_last_error.restype = C.c_char_p
     lib.rs_version.restype = C.c_char_p
     lib.rs_launch_count.restype = C.c_uint64
@@ -188,6 +192,37 @@ class PrimitiveDetection:
         if cells_ptr is None:
             cells_ptr = self.device_outputs().cells
         _check(self._lib.rs_cape_cell_fit_device(self._ctx, depth_ptr, batch, cells_ptr, stream), "rs_cape_cell_fit_device")
+
+
+def kalman_track_points(state, cov, meas, meas_cov, process_noise=0.001, device=0):
+    """tracking::Point::track for n matched map points at once (point_with_tracking.cpp:32-84).
+    state / meas [n,3], cov / meas_cov [n,3,3]. Returns (new_state, new_cov, score, is_moving, status)."""
+    lib = load()
+    state, cov, meas, meas_cov = (np.ascontiguousarray(a, dtype=np.float64) for a in (state, cov, meas, meas_cov))
+    n = state.shape[0]
+    if state.shape != (n, 3) or cov.shape != (n, 3, 3) or meas.shape != (n, 3) or meas_cov.shape != (n, 3, 3):
+        raise ValueError("expected state/meas [n,3] and cov/meas_cov [n,3,3]")
+    out_state, out_cov, score = np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros(n)
+    moving, status = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    _check(lib.rs_kalman_track_points(device, n, state.ctypes.data, cov.ctypes.data, meas.ctypes.data, meas_cov.ctypes.data,
+                                      process_noise, out_state.ctypes.data, out_cov.ctypes.data, score.ctypes.data,
+                                      moving.ctypes.data, status.ctypes.data), "rs_kalman_track_points")
+    return out_state, out_cov, score, moving, status
+
+
+def kalman_track_planes(state, cov, meas, meas_cov, process_noise=1e-6, device=0):
+    """tracking::Plane::track's filter step for n matched map planes (plane_with_tracking.cpp:16-59): state = (n, d).
+    Returns (new_state with unit normal, new_cov, score, status)."""
+    lib = load()
+    state, cov, meas, meas_cov = (np.ascontiguousarray(a, dtype=np.float64) for a in (state, cov, meas, meas_cov))
+    n = state.shape[0]
+    if state.shape != (n, 4) or cov.shape != (n, 4, 4) or meas.shape != (n, 4) or meas_cov.shape != (n, 4, 4):
+        raise ValueError("expected state/meas [n,4] and cov/meas_cov [n,4,4]")
+    out_state, out_cov, score, status = np.zeros((n, 4)), np.zeros((n, 4, 4)), np.zeros(n), np.zeros(n, np.int32)
+    _check(lib.rs_kalman_track_planes(device, n, state.ctypes.data, cov.ctypes.data, meas.ctypes.data, meas_cov.ctypes.data,
+                                      process_noise, out_state.ctypes.data, out_cov.ctypes.data, score.ctypes.data,
+                                      status.ctypes.data), "rs_kalman_track_planes")
+    return out_state, out_cov, score, status
 
 
 def make_matches(n):

@@ -42,6 +42,9 @@ def load():
     lib.orc_pose_solve.argtypes = [vp, vp, vp, i32, i32, i32, u32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.orc_process_frames.restype = dbl
     lib.orc_process_frames.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, u32, i32, vp]
+    lib.orc_kalman_new_state.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.orc_kalman_track_points.argtypes = [i32, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp]
+    lib.orc_kalman_track_planes.argtypes = [i32, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
     lib.orc_rectify_depth.argtypes = [i32, i32, dbl, dbl, dbl, dbl, vp, vp, i32, vp]
     lib.orc_ref_test_features.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32]
     _lib = lib
@@ -58,6 +61,40 @@ def cape_run(depth, cell=20, K=(550.0, 550.0, 320.0, 240.0), seed=0):
     arrs, st = abi.alloc_cape_outputs(B, Nc, 2 * Nc)
     lib.orc_cape_run(W, H, cell, *K, depth.ctypes.data, B, seed, 2 * Nc, C.byref(st))
     return arrs
+
+
+def kalman_new_state(F, H, Q, x, P, z, R):
+    """SharedKalmanFilter<N, M>::get_new_state restated (oracle/kalman.cpp). Returns (status, x_new, P_new)."""
+    lib = load()
+    F, H, Q, P, R = (np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in (F, H, Q, P, R))
+    x = np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64)
+    z = np.ascontiguousarray(np.atleast_1d(z), dtype=np.float64)
+    N, M = len(x), len(z)
+    xo, Po = np.zeros(N), np.zeros((N, N))
+    rc = lib.orc_kalman_new_state(N, M, F.ctypes.data, H.ctypes.data, Q.ctypes.data, x.ctypes.data, P.ctypes.data,
+                                  z.ctypes.data, R.ctypes.data, xo.ctypes.data, Po.ctypes.data)
+    return rc, xo, Po
+
+
+def kalman_track_points(x, P, z, R, process_noise=0.001):
+    lib = load()
+    x, P, z, R = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, P, z, R))
+    n = len(x)
+    xo, Po, score = np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros(n)
+    moving, status = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    lib.orc_kalman_track_points(n, x.ctypes.data, P.ctypes.data, z.ctypes.data, R.ctypes.data, process_noise, xo.ctypes.data,
+                                Po.ctypes.data, score.ctypes.data, moving.ctypes.data, status.ctypes.data)
+    return xo, Po, score, moving, status
+
+
+def kalman_track_planes(x, P, z, R, process_noise=1e-6):
+    lib = load()
+    x, P, z, R = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, P, z, R))
+    n = len(x)
+    xo, Po, score, status = np.zeros((n, 4)), np.zeros((n, 4, 4)), np.zeros(n), np.zeros(n, np.int32)
+    lib.orc_kalman_track_planes(n, x.ctypes.data, P.ctypes.data, z.ctypes.data, R.ctypes.data, process_noise, xo.ctypes.data,
+                                Po.ctypes.data, score.ctypes.data, status.ctypes.data)
+    return xo, Po, score, status
 
 
 def rectify_depth(depth, cam2_to_cam1=None, K=(550.0, 550.0, 320.0, 240.0)):
