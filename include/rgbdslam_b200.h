@@ -174,14 +174,21 @@ int rs_cape_kernel_ms(rs_cape_ctx* ctx, int slot, float ms[2]);
 /* ---- pose solve ------------------------------------------------------------------------- */
 #define RS_FEAT_POINT 0    /* PointOptimizationFeature  (map_point.cpp:16-65)    2 residuals, score 1/5 */
 #define RS_FEAT_PLANE 1    /* PlaneOptimizationFeature  (map_primitive.cpp:15-85) 3 residuals, score 1/3 */
+#define RS_FEAT_POINT2D 2  /* Point2dOptimizationFeature (map_point2d.cpp:15-81): inverse-depth map point, the "line" residual:
+                              signed distance of the matched pixel to the screen line through the projections of the point's
+                              furthest / closest depth estimates; 2 residuals, score 1/5, weight 0.3 / 2 */
 
 /* One matched feature (an IOptimizationFeature flattened; matches_containers.hpp:122-180). */
 typedef struct rs_match {
     int32_t type;
     int32_t reserved;
-    double obs[4];    /* point: (u, v, -, -) screen px.  plane: camera-frame (nx, ny, nz, d)          */
-    double map[4];    /* point: world (X, Y, Z, -) mm.   plane: world-frame (nx, ny, nz, d)           */
-    double sigma[4];  /* standard deviation of the map side (Monte-Carlo variation)                 */
+    double obs[4];    /* point: (u, v, -, -) screen px.  plane: camera-frame (nx, ny, nz, d).
+                         point2d: (u, v, theta, phi): matched pixel + the map point's bearing angles (rad)          */
+    double map[4];    /* point: world (X, Y, Z, -) mm.   plane: world-frame (nx, ny, nz, d).
+                         point2d: (first observation X, Y, Z in mm, inverse depth in 1/mm)                           */
+    double sigma[4];  /* standard deviation of the map side (Monte-Carlo variation).
+                         point2d: (sigma inverse depth, sigma theta, sigma phi, -) = _mapPointStandardDev(3..5); the
+                         first observation is not varied by the reference (map_point2d.cpp:50-52)                    */
 } rs_match;
 
 #define RS_RNG_REFERENCE 0 /* host std::mt19937 + libstdc++ shuffle/normal_distribution, one stream, as random.hpp/ransac.hpp */

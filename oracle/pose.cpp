@@ -19,6 +19,8 @@ constexpr float kInlierProportion = 0.65f;
 constexpr float kFeatureTrustCount = 10.0f;
 constexpr unsigned kMinimumPointForOptimization = 5;
 constexpr unsigned kMinimumPlanesForOptimization = 3;
+constexpr unsigned kMinimumPoint2dForOptimization = 5;                    // parameters.hpp:41-42
+constexpr float kMaxRetroprojectionErrorForPoint2DInliers_px = 3.0f;      // parameters.hpp:23-24
 
 // ---- small dense helpers for the m x 6 problem ------------------------------------------------
 constexpr int N = 6;
@@ -538,13 +540,17 @@ void pose_vector6(const Pose7& p, double v[6])
 double feature_score(const rs_match& f)
 {
     if (f.type == RS_FEAT_POINT) return 1.0 / kMinimumPointForOptimization;
+    if (f.type == RS_FEAT_POINT2D) return 1.0 / kMinimumPoint2dForOptimization;  // map_point2d.cpp:27-31
     return 1.0 / kMinimumPlanesForOptimization;
 }
+
+// get_feature_part_count (map_point.cpp:25, map_point2d.cpp:25, map_primitive.cpp:25)
+int feature_parts(const rs_match& f) { return f.type == RS_FEAT_PLANE ? 3 : 2; }
 
 int residual_count(const std::vector<rs_match>& feats)
 {
     int m = 0;
-    for (const rs_match& f : feats) m += (f.type == RS_FEAT_POINT) ? 2 : 3;
+    for (const rs_match& f : feats) m += feature_parts(f);
     return m;
 }
 
@@ -568,6 +574,52 @@ void point_signed_distance(const Intrinsics& K, const rs_match& f, const Mat4& w
     }
     out[0] = f.obs[0] - u;
     out[1] = f.obs[1] - v;
+}
+
+// WorldCoordinate::to_screen_coordinates (point_coordinates.cpp:227-231,201-210): false when the projection has a NaN
+bool world_to_screen(const Intrinsics& K, const double P[3], const Mat4& w2c, double uv[2])
+{
+    double h[4];
+    for (int i = 0; i < 4; ++i) h[i] = ((w2c(i, 0) * P[0] + w2c(i, 1) * P[1]) + w2c(i, 2) * P[2]) + w2c(i, 3) * 1.0;
+    const double xc = h[0] / h[3], yc = h[1] / h[3], zc = h[2] / h[3];
+    const double inv = 1.0 / zc;
+    uv[0] = inv * ((K.fx * xc + 0.0 * yc) + K.cx * zc);
+    uv[1] = inv * ((0.0 * xc + K.fy * yc) + K.cy * zc);
+    return !(uv[0] != uv[0] || uv[1] != uv[1]);
+}
+
+// InverseDepthWorldPoint::compute_signed_screen_distance (inverse_depth_coordinates.cpp:58-68) as called by
+// Point2dOptimizationFeature::get_distance (map_point2d.cpp:40-45) with the inverse-depth STANDARD DEVIATION in the place
+// of the covariance (so its square root is taken once more, :159), get_furthest/closest_estimation with the
+// std::min(., 1e-9) of :146,153, Segment<2>::distance (line.hpp:27-41,95-99).
+void point2d_signed_distance(const Intrinsics& K, const rs_match& f, const Mat4& w2c, double out[2])
+{
+    const double theta = f.obs[2], phi = f.obs[3];
+    // _bearingVector = Cartesian::from(Spherical(1.0, theta, phi)) (basis_changes.cpp:5-10)
+    const double sinTheta = std::sin(theta);
+    const double b[3] = {1.0 * sinTheta * std::cos(phi), 1.0 * sinTheta * std::sin(phi), 1.0 * std::cos(theta)};
+    const double depthStandardDev = std::sqrt(f.sigma[0]);
+    const double depthVariation = depthStandardDev * 3;
+    const double dFar = std::min(f.map[3] - depthVariation, 1e-9);
+    const double dNear = std::min(f.map[3] + depthVariation, 1e-9);
+    const double pFar[3] = {f.map[0] + b[0] / dFar, f.map[1] + b[1] / dFar, f.map[2] + b[2] / dFar};
+    const double pNear[3] = {f.map[0] + b[0] / dNear, f.map[1] + b[1] / dNear, f.map[2] + b[2] / dNear};
+    double s[2], e[2];
+    if (!(world_to_screen(K, pFar, w2c, s) and world_to_screen(K, pNear, w2c, e))) {
+        out[0] = DBL_MAX;
+        out[1] = DBL_MAX;
+        return;
+    }
+    // normal = (end - start).normalized(); closest = start + normal * ((p - start) . normal); distance = p - closest
+    double n[2] = {e[0] - s[0], e[1] - s[1]};
+    const double z = n[0] * n[0] + n[1] * n[1];
+    if (z > 0) {
+        const double l = std::sqrt(z);
+        n[0] /= l, n[1] /= l;
+    }
+    const double along = (f.obs[0] - s[0]) * n[0] + (f.obs[1] - s[1]) * n[1];
+    out[0] = f.obs[0] - (s[0] + n[0] * along);
+    out[1] = f.obs[1] - (s[1] + n[1] * along);
 }
 
 // PlaneWorldCoordinates::to_camera_coordinates (plane_coordinates.cpp:20-24) + PlaneCoordinates(vector4) ctor
@@ -623,6 +675,15 @@ void pose_residuals(const Intrinsics& K, const std::vector<rs_match>& feats, con
             }
             idx += 2;
         }
+        else if (f.type == RS_FEAT_POINT2D) {
+            double dist[2];
+            point2d_signed_distance(K, f, w2c, dist);
+            if (!has_nan(dist, 2)) {   // get_alpha_reduction() = 0.3 (map_point2d.cpp:47), 2 parts
+                fvec[idx] = dist[0] * 0.3 / 2.0;
+                fvec[idx + 1] = dist[1] * 0.3 / 2.0;
+            }
+            idx += 2;
+        }
         else {
             if (!havePlaneM) {
                 planeM = plane_world_to_camera(w2c);  // identical for every plane (map_primitive.cpp:51-62)
@@ -654,6 +715,12 @@ bool feature_is_inlier(const Intrinsics& K, const rs_match& f, const Mat4& w2c, 
             distance = std::fabs(dist[0]) + std::fabs(dist[1]);
         return distance <= kMaxRetroprojectionErrorForPointInliers_px;
     }
+    if (f.type == RS_FEAT_POINT2D) {
+        // map_point2d.cpp:33-38: (get_distance(w2c).array() <= threshold).all() on the SIGNED distance
+        double dist[2];
+        point2d_signed_distance(K, f, w2c, dist);
+        return dist[0] <= kMaxRetroprojectionErrorForPoint2DInliers_px and dist[1] <= kMaxRetroprojectionErrorForPoint2DInliers_px;
+    }
     // map_primitive.cpp:33-49 + get_signed_distance (plane_coordinates.cpp:26-37)
     Vec3 np;
     double dp;
@@ -678,7 +745,7 @@ bool optimized_global_pose(const Intrinsics& K, const Pose7& cur, const std::vec
     double optimizationScore = 0.0;
     size_t optiParts = 0;
     for (const rs_match& f : feats) {
-        optiParts += (f.type == RS_FEAT_POINT) ? 2 : 3;
+        optiParts += size_t(feature_parts(f));
         optimizationScore += feature_score(f);
     }
     if (optiParts <= 1) return false;  // `optiParts <= input.cols()` with a column vector (:322)
@@ -809,10 +876,12 @@ PoseSolveResult pose_solve(const Intrinsics& K, const Pose7& cur, const std::vec
 
     // compute_optimized_pose: every feature must be valid (:269-282)
     for (const rs_match& f : feats) {
+        // is_valid: map_point.cpp:60-64, map_primitive.cpp:79-83, map_point2d.cpp:75-79 (bearing = f(theta, phi))
         const int k = (f.type == RS_FEAT_POINT) ? 3 : 4;
         const int ko = (f.type == RS_FEAT_POINT) ? 2 : 4;
-        if (has_nan(f.obs, ko) or has_nan(f.map, k) or has_nan(f.sigma, k)) return R;
-        for (int i = 0; i < k; ++i)
+        const int ks = (f.type == RS_FEAT_POINT2D) ? 3 : k;
+        if (has_nan(f.obs, ko) or has_nan(f.map, k) or has_nan(f.sigma, ks)) return R;
+        for (int i = 0; i < ks; ++i)
             if (!(f.sigma[i] >= 0)) return R;
     }
 
@@ -913,7 +982,7 @@ PoseSolveResult pose_solve(const Intrinsics& K, const Pose7& cur, const std::vec
         for (size_t k = 0; k < inliers.size(); ++k) {
             rs_match f = inliers[k];
             double g[4] = {0, 0, 0, 0};
-            const int nd = (f.type == RS_FEAT_POINT) ? 3 : 4;
+            const int nd = (f.type == RS_FEAT_POINT) ? 3 : (f.type == RS_FEAT_POINT2D ? 2 : 4);
             for (int i = 0; i < nd; ++i) {
                 if (rnd.normals)
                     g[i] = rnd.normals[(size_t(it) * rnd.max_matches + inlierIdx[k]) * 4 + i];
@@ -923,6 +992,11 @@ PoseSolveResult pose_solve(const Intrinsics& K, const Pose7& cur, const std::vec
             if (f.type == RS_FEAT_POINT) {
                 // map_point.cpp:49-58
                 for (int i = 0; i < 3; ++i) f.map[i] += g[i] * f.sigma[i];
+            }
+            else if (f.type == RS_FEAT_POINT2D) {
+                // map_point2d.cpp:49-73: theta then phi, clamped; observation point and inverse depth are kept
+                f.obs[2] = std::clamp(f.obs[2] + g[0] * f.sigma[1], 0.0, M_PI);
+                f.obs[3] = std::clamp(f.obs[3] + g[1] * f.sigma[2], -M_PI, M_PI);
             }
             else {
                 // map_primitive.cpp:66-77 (+ the PlaneCoordinates copy ctor normalisation in make_shared)

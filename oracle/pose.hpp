@@ -58,6 +58,7 @@ int residual_count(const std::vector<rs_match>& feats);
 // IOptimizationFeature::is_inlier for one feature
 bool feature_is_inlier(const Intrinsics& K, const rs_match& f, const Mat4& w2c, const Mat4& planeW2c);
 double feature_score(const rs_match& f);
+int feature_parts(const rs_match& f);
 
 // Random source: the reference's thread-local engine + distributions (random.hpp:17-39). When the explicit
 // lists are set they are consumed instead (parity against the library's RS_RNG_DEVICE mode).

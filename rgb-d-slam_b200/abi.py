@@ -9,7 +9,7 @@ RS_MAX_PLANES = 128
 RS_MAX_CYL_REGIONS = 32
 RS_MAX_CYL_SEGS = 8
 RS_CYL_RANSAC_ITERS = 43
-RS_FEAT_POINT, RS_FEAT_PLANE = 0, 1
+RS_FEAT_POINT, RS_FEAT_PLANE, RS_FEAT_POINT2D = 0, 1, 2
 RS_RNG_REFERENCE, RS_RNG_DEVICE = 0, 1
 RS_MAX_SUBSET = 16
 

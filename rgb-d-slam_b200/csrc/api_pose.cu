@@ -26,6 +26,7 @@ struct rs_pose_ctx {
     // host mirrors kept for the reference RNG mode and for export
     std::vector<int32_t> h_n;
     std::vector<int32_t> h_type;  // B x M
+    bool has_point2d = false;     // the uploaded batch carries an inverse-depth (RS_FEAT_POINT2D) feature
     PoseLaunch last{};
     int last_batch = 0;
     std::vector<cudaEvent_t> events;  // 5 per timing slot
@@ -58,6 +59,7 @@ int create_impl(rs_pose_ctx* c)
     if ((rc = dev_alloc(&b.obs, B * 4 * M))) return rc;
     if ((rc = dev_alloc(&b.map, B * 4 * M))) return rc;
     if ((rc = dev_alloc(&b.sigma, B * 4 * M))) return rc;
+    if ((rc = dev_alloc(&b.aux, B * 4 * M))) return rc;
     if ((rc = dev_alloc(&b.state, B))) return rc;
     if ((rc = dev_alloc(&b.out, B))) return rc;
     if ((rc = dev_alloc(&b.mask, B * M))) return rc;
@@ -91,6 +93,7 @@ int resolve_launch(const rs_pose_ctx* c, const rs_pose_opts* opts, int batch, Po
     prm.lm_max_fev = o.lm_max_fev > 0 ? o.lm_max_fev : 400;
     prm.rng_mode = o.rng_mode;
     prm.seed = o.seed;
+    prm.has_point2d = c->has_point2d ? 1 : 0;
     if (o.fx == 0 && o.fy == 0 && o.cx == 0 && o.cy == 0)
         prm.K = PoseIntrinsics{550.0, 550.0, 320.0, 240.0};  // Parameters::load_defaut (parameters.cpp:59-74)
     else
@@ -122,6 +125,10 @@ int upload_impl(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches,
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_cur, cur_pose, sizeof(double) * 7 * batch, cudaMemcpyHostToDevice, s));
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_matches, matches, sizeof(rs_match) * size_t(batch) * c->M, cudaMemcpyHostToDevice, s));
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_n, n_matches, sizeof(int32_t) * batch, cudaMemcpyHostToDevice, s));
+    bool p2d = false;
+    for (int b = 0; b < batch; ++b)
+        for (int i = 0; i < n_matches[b]; ++i) p2d = p2d || matches[size_t(b) * c->M + i].type == RS_FEAT_POINT2D;
+    c->has_point2d = p2d;
     for (int b = 0; b < batch; ++b) {
         c->h_n[b] = n_matches[b];
         if (host_types)  // only the host-side reference RNG (std::shuffle / normal draws per inlier) reads the types
@@ -130,7 +137,7 @@ int upload_impl(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches,
     return RS_OK;
 }
 
-inline double feature_score(int type) { return type == RS_FEAT_POINT ? 1.0 / 5.0 : 1.0 / 3.0; }
+inline double feature_score(int type) { return type == RS_FEAT_PLANE ? 1.0 / 3.0 : 1.0 / 5.0; }  // point and point2d: 1/5
 
 // ransac::get_random_subset_with_score (ransac.hpp:77-103) with the reference's engine: std::shuffle over the
 // whole list, shuffled prefix until the score reaches 1, every pick prepended.
@@ -175,7 +182,7 @@ void reference_normals(const rs_pose_ctx* c, int b, uint32_t seed, int started, 
     for (int s = 0; s < n_variance; ++s)
         for (int i = 0; i < n; ++i) {
             if (!mask[i]) continue;
-            const int nd = type[i] == RS_FEAT_POINT ? 3 : 4;
+            const int nd = type[i] == RS_FEAT_POINT ? 3 : (type[i] == RS_FEAT_POINT2D ? 2 : 4);
             double* dst = out + (size_t(s) * c->M + i) * 4;
             for (int k = 0; k < nd; ++k) dst[k] = normal(engine);
         }
@@ -288,6 +295,7 @@ void rs_pose_destroy(rs_pose_ctx* c)
     cudaFree(b.obs);
     cudaFree(b.map);
     cudaFree(b.sigma);
+    cudaFree(b.aux);
     cudaFree(b.state);
     cudaFree(b.out);
     cudaFree(b.mask);
@@ -340,6 +348,7 @@ int rs_pose_solve_batched_begin(rs_pose_ctx* c, const double* cur_pose, const rs
     if (rc != RS_OK) return rc;
     const bool reference_rng = prm.rng_mode == RS_RNG_REFERENCE;
     if ((rc = upload_impl(c, cur_pose, matches, n_matches, batch, c->stream, reference_rng)) != RS_OK) return rc;
+    prm.has_point2d = c->has_point2d ? 1 : 0;   // known only once this batch's feature types have been seen
     if ((rc = solve_impl(c, batch, prm, c->stream, reference_rng)) != RS_OK) return rc;
     RS_CUDA_CHECK(cudaMemcpyAsync(out, c->buf.out, sizeof(rs_pose_out) * batch, cudaMemcpyDeviceToHost, c->stream));
     if (inlier_mask)

@@ -33,6 +33,7 @@ struct PoseBuffers {
     double* obs;                   // B x 4 x M
     double* map;                   // B x 4 x M
     double* sigma;                 // B x 4 x M
+    double* aux;                   // B x 4 x M : first observation + inverse depth of the inverse-depth (point2d) features
     PoseFrameState* state;         // B
     rs_pose_out* out;              // B
     uint8_t* mask;                 // B x M
@@ -51,6 +52,7 @@ struct PoseLaunch {
     int n_variance;       // Monte-Carlo solves
     int lm_max_fev;       // 400
     int rng_mode;
+    int has_point2d;      // some frame of the batch carries an RS_FEAT_POINT2D feature: run the kernels that know the type
     uint32_t seed;
     PoseIntrinsics K;
 };

@@ -50,6 +50,16 @@ constexpr double kPlaneInlierNormal = 0.20000000298023224;   // float 0.2f
 constexpr double kEarlyStopProportion = 0.800000011920929;   // double initialised from 0.80f
 constexpr double kPointScore = 1.0 / 5.0;                    // 1 / minimumPointForOptimization
 constexpr double kPlaneScore = 1.0 / 3.0;                    // 1 / minimumPlanesForOptimization
+constexpr double kPoint2dScore = 1.0 / 5.0;                  // 1 / minimumPoint2dForOptimization
+constexpr double kPoint2dInlierPx = 3.0;                     // float 3.0f
+constexpr double kPoint2dWeight = 0.3 / 2.0;                 // get_alpha_reduction() / parts (map_point2d.cpp:25,47)
+
+// IOptimizationFeature::get_score / get_feature_part_count per feature type
+__device__ __forceinline__ double score_of(const int type)
+{
+    return type == RS_FEAT_PLANE ? kPlaneScore : (type == RS_FEAT_POINT2D ? kPoint2dScore : kPointScore);
+}
+__device__ __forceinline__ int parts_of(const int type) { return type == RS_FEAT_PLANE ? 3 : 2; }
 
 // world <- camera rotation of the pose: R' = C * R(q), t' = C * t with C = [[0,0,1],[-1,0,0],[0,-1,0]]
 // (camera_transformation.cpp:11-23). world->camera is then p_c = R'^T (P - t') and the plane world->camera map
@@ -77,6 +87,7 @@ struct Problem {
     const int32_t* type;  // [M]
     const double* obs;    // [4][M]
     const double* map;    // [4][M]
+    const double* aux;    // [4][M] global: first observation + inverse depth of the inverse-depth (point2d) features
     int M;
 };
 
@@ -199,16 +210,72 @@ __device__ __forceinline__ void plane_to_camera(const double n0, const double n1
     dp = ((T.t[0] * n0 + T.t[1] * n1) + T.t[2] * n2) + dw;
 }
 
+// Point2dOptimizationFeature::get_distance (map_point2d.cpp:40-45) -> InverseDepthWorldPoint::compute_signed_screen_distance
+// (inverse_depth_coordinates.cpp:58-68,142-173) -> Segment<2>::distance (line.hpp:27-41,95-99): the matched pixel against
+// the screen line through the projections of the point's furthest / closest depth estimates. Device layout of the feature:
+// o = (u, v, dFar, dNear) with d* = min(inverse depth -/+ 3 sqrt(sigma), 1e-9) formed once by the preparation step,
+// m = (theta, phi) (the part the Monte-Carlo variation perturbs), ax = (first observation X, Y, Z).
+__device__ __forceinline__ void point2d_distance(const double o[4], const double m[4], const double ax[3], const Xform& T,
+                                                 const PoseIntrinsics& K, double& du, double& dv)
+{
+    double st, ct, sp, cp;
+    sincos(m[0], &st, &ct);
+    sincos(m[1], &sp, &cp);
+    const double b0 = 1.0 * st * cp, b1 = 1.0 * st * sp, b2 = 1.0 * ct;
+    double s[2], e[2];
+    bool ok = true;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const double den = o[2 + w];
+        const double d0 = (ax[0] + b0 / den) - T.t[0], d1 = (ax[1] + b1 / den) - T.t[1], d2 = (ax[2] + b2 / den) - T.t[2];
+        const double xc = (T.R[0] * d0 + T.R[3] * d1) + T.R[6] * d2;
+        const double yc = (T.R[1] * d0 + T.R[4] * d1) + T.R[7] * d2;
+        const double zc = (T.R[2] * d0 + T.R[5] * d1) + T.R[8] * d2;
+        const double inv = 1.0 / zc;
+        const double u = inv * (K.fx * xc + K.cx * zc), v = inv * (K.fy * yc + K.cy * zc);
+        ok = ok && !(u != u || v != v);
+        if (w == 0)
+            s[0] = u, s[1] = v;
+        else
+            e[0] = u, e[1] = v;
+    }
+    if (!ok) {
+        du = DBL_MAX, dv = DBL_MAX;
+        return;
+    }
+    double n0 = e[0] - s[0], n1 = e[1] - s[1];
+    const double z = n0 * n0 + n1 * n1;
+    if (z > 0.0) {
+        const double l = sqrt(z);
+        n0 /= l, n1 /= l;
+    }
+    const double along = (o[0] - s[0]) * n0 + (o[1] - s[1]) * n1;
+    du = o[0] - (s[0] + n0 * along);
+    dv = o[1] - (s[1] + n1 * along);
+}
+
 // One feature's residual entries (Global_Pose_Estimator::operator(), levenberg_marquardt_functors.cpp:128-169):
 // point -> 1/2 (du, dv); plane -> 1/3 (d_c n_c - d_p n_p). Returns the entry count.
+// `aux` / `M` / `gi`: where an inverse-depth feature finds its first observation (global memory, component-major).
+template <bool P2D>
 __device__ __forceinline__ int feature_residual(const int type, const double o[4], const double m[4], const Xform& T,
-                                                const PoseIntrinsics& K, double r[3])
+                                                const PoseIntrinsics& K, double r[3], const double* aux, const int M,
+                                                const int gi)
 {
     if (type == RS_FEAT_POINT) {
         double du, dv;
         point_distance(o[0], o[1], m[0], m[1], m[2], T, K, du, dv);
         r[0] = du * 1.0 / 2.0;
         r[1] = dv * 1.0 / 2.0;
+        r[2] = 0.0;
+        return 2;
+    }
+    if (P2D && type == RS_FEAT_POINT2D) {
+        const double ax[3] = {aux[gi], aux[M + gi], aux[2 * M + gi]};
+        double du, dv;
+        point2d_distance(o, m, ax, T, K, du, dv);
+        r[0] = du * kPoint2dWeight;
+        r[1] = dv * kPoint2dWeight;
         r[2] = 0.0;
         return 2;
     }
@@ -232,8 +299,9 @@ __device__ __forceinline__ bool angle_within(const double a, const double b, con
 }
 
 // IOptimizationFeature::is_inlier (map_point.cpp:34-38, map_primitive.cpp:33-49)
+template <bool P2D>
 __device__ __forceinline__ bool feature_is_inlier(const int type, const double o[4], const double m[4], const Xform& T,
-                                                  const PoseIntrinsics& K)
+                                                  const PoseIntrinsics& K, const double* aux, const int M, const int gi)
 {
     if (type == RS_FEAT_POINT) {
         double du, dv;
@@ -241,13 +309,20 @@ __device__ __forceinline__ bool feature_is_inlier(const int type, const double o
         const double dist = (du >= DBL_MAX || dv >= DBL_MAX) ? DBL_MAX : fabs(du) + fabs(dv);
         return dist <= kPointInlierPx;
     }
+    if (P2D && type == RS_FEAT_POINT2D) {
+        // map_point2d.cpp:33-38: (get_distance().array() <= threshold).all() - on the SIGNED distance
+        const double ax[3] = {aux[gi], aux[M + gi], aux[2 * M + gi]};
+        double du, dv;
+        point2d_distance(o, m, ax, T, K, du, dv);
+        return du <= kPoint2dInlierPx && dv <= kPoint2dInlierPx;
+    }
     double np[3], dp;
     plane_to_camera(m[0], m[1], m[2], m[3], T, np, dp);
     return angle_within(o[0], np[0], kPlaneInlierNormal) && angle_within(o[1], np[1], kPlaneInlierNormal) &&
            angle_within(o[2], np[2], kPlaneInlierNormal) && fabs(o[3] - dp) <= kPlaneInlierMm;
 }
 
-__device__ __forceinline__ void load_feature(const Problem& P, const int k, int& type, double o[4], double m[4])
+__device__ __forceinline__ int load_feature(const Problem& P, const int k, int& type, double o[4], double m[4])
 {
     const int i = P.idx ? int(P.idx[k]) : k;
     type = P.type[i];
@@ -260,17 +335,19 @@ __device__ __forceinline__ void load_feature(const Problem& P, const int k, int&
         o[2] = P.obs[2 * P.M + i], o[3] = P.obs[3 * P.M + i];
         m[3] = P.map[3 * P.M + i];
     }
+    return i;
 }
 
 // |f(x)|^2 over the problem's features with transform T (warp-wide result)
+template <bool P2D>
 __device__ inline double eval_sumsq(const Problem& P, const Xform& T, const PoseIntrinsics& K, const int lane)
 {
     double ss = 0.0;
     for (int k = lane; k < P.n; k += 32) {
         int type;
         double o[4], m[4], r[3];
-        load_feature(P, k, type, o, m);
-        feature_residual(type, o, m, T, K, r);
+        const int gi = load_feature(P, k, type, o, m);
+        feature_residual<P2D>(type, o, m, T, K, r, P.aux, P.M, gi);
         ss += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
     }
     return warp_sum(ss);
@@ -298,6 +375,45 @@ __device__ __forceinline__ void accumulate_row(const double (&J)[6], const doubl
 }
 
 // rows of one feature at S.T / S.dR, accumulated into a[0..20] (upper triangle of J^T J, row-major) and a[21..26] (J^T r)
+// Inverse-depth features keep NumericalDiff's own scheme (seven residual evaluations): their residual is a point-to-line
+// distance through two projections, they are rare (the live pipeline never produces them), and S still holds what the
+// perturbed transforms are made of.
+__device__ __noinline__ void point2d_jacobian(const double (&o)[4], const double (&m)[4], const double* aux, const int M,
+                                              const int gi, const WarpLM& S, const PoseIntrinsics& K, double* c /* [27] contribution */)
+{
+    const double ax[3] = {aux[gi], aux[M + gi], aux[2 * M + gi]};
+    double du, dv;
+    point2d_distance(o, m, ax, S.T, K, du, dv);
+    const double r0 = du * kPoint2dWeight, r1 = dv * kPoint2dWeight;
+    double J0[6], J1[6];
+    for (int j = 0; j < 6; ++j) {
+        Xform Tj = S.T;
+        double ih;
+        if (j < 3) {
+            double h = kSqrtEps * fabs(S.x[j]);
+            if (h == 0.0) h = kSqrtEps;
+            const double xj = S.x[j] + h;
+            if (j == 0) Tj.t[1] = -xj;       // t' = (x2, -x0, -x1)
+            else if (j == 1) Tj.t[2] = -xj;
+            else Tj.t[0] = xj;
+            ih = 1.0 / h;
+        }
+        else {
+            for (int i = 0; i < 9; ++i) Tj.R[i] = S.Rk[j - 3][i];
+            ih = S.ih[j - 3];
+        }
+        double eu, ev;
+        point2d_distance(o, m, ax, Tj, K, eu, ev);
+        J0[j] = (eu * kPoint2dWeight - r0) * ih;
+        J1[j] = (ev * kPoint2dWeight - r1) * ih;
+    }
+    int t = 0;
+    for (int i = 0; i < 6; ++i) {
+        c[21 + i] = J0[i] * r0 + J1[i] * r1;
+        for (int j = i; j < 6; ++j) c[t++] = J0[i] * J0[j] + J1[i] * J1[j];
+    }
+}
+
 __device__ __forceinline__ void feature_jacobian(const int type, const double (&o)[4], const double (&m)[4], const Xform& T,
                                                  const double* __restrict__ dR, const PoseIntrinsics& K, double (&a)[32])
 {
@@ -676,6 +792,7 @@ __device__ __forceinline__ void lmpar(WarpLM& S)
 // Eigen status (<= 0 failure, 1..8 MINPACK info). m = residual count of the problem. Inlined at exactly ONE call site per
 // kernel: the body is ~4k instructions and the serial lane-0 chains are latency bound, so instruction-cache residency
 // matters, and inlining lets the compiler see that S and the feature arrays live in shared memory (LDS, not generic LD).
+template <bool P2D>
 __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m,
                                              const int maxfev, const int lane, const volatile int* abort = nullptr)
 {
@@ -683,7 +800,7 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
     if (lane == 0) make_xform(S.x, S.T);
     __syncwarp();
     {
-        const double ss = eval_sumsq(P, S.T, K, lane);
+        const double ss = eval_sumsq<P2D>(P, S.T, K, lane);
         if (lane == 0) {
             S.fnorm = sqrt(ss);
             S.par = 0.0, S.delta = 0.0, S.xnorm = 0.0;
@@ -732,8 +849,15 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
         for (int k = lane; k < P.n; k += 32) {
             int type;
             double o[4], mm[4];
-            load_feature(P, k, type, o, mm);
-            feature_jacobian(type, o, mm, S.T, S.dR, K, a);
+            const int gi = load_feature(P, k, type, o, mm);
+            if (P2D && type == RS_FEAT_POINT2D) {
+                double c[27];   // out of line and through local memory, so that a[] stays in registers
+                point2d_jacobian(o, mm, P.aux, P.M, gi, S, K, c);
+#pragma unroll
+                for (int i = 0; i < 27; ++i) a[i] += c[i];
+            }
+            else
+                feature_jacobian(type, o, mm, S.T, S.dR, K, a);
         }
         const double mine = reduce_scatter32(a, lane);
         if (lane < 21) {
@@ -805,7 +929,7 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
                 make_xform(S.xt, S.T);
             }
             __syncwarp();
-            const double ss1 = eval_sumsq(P, S.T, K, lane);
+            const double ss1 = eval_sumsq<P2D>(P, S.T, K, lane);
             if (lane == 0) {
                 ++S.nfev;
                 const double fnorm = S.fnorm, fnorm1 = sqrt(ss1), pnorm = S.pnorm;
@@ -881,6 +1005,7 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
 
 // compute_optimized_global_pose (pose_optimization.cpp:302-359) for the whole warp. x0 -> S.x; returns success and
 // leaves the optimised coefficients in S.x.
+template <bool P2D>
 __device__ __forceinline__ bool optimize_pose_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const double* x0,
                                                    const int m, const double score, const int maxfev, const int lane,
                                                    const volatile int* abort = nullptr)
@@ -892,7 +1017,7 @@ __device__ __forceinline__ bool optimize_pose_warp(WarpLM& S, const Problem& P, 
     if (lane == 0)
         for (int j = 0; j < 6; ++j) S.x[j] = x0[j];
     __syncwarp();
-    const int status = lm_minimize_warp(S, P, K, m, maxfev, lane, abort);
+    const int status = lm_minimize_warp<P2D>(S, P, K, m, maxfev, lane, abort);
     if (status <= 0) return false;
     // the reference rejects a pose whose [position, Euler angles] vector has a NaN: that vector is finite exactly
     // when the coefficients and the quaternion built from them are
@@ -957,33 +1082,53 @@ __global__ void __launch_bounds__(THREADS) pose_prepare_kernel(const PoseBuffers
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         if (i < n) {
             const rs_match f = src[i];
-            const int ty = (f.type == RS_FEAT_POINT) ? RS_FEAT_POINT : RS_FEAT_PLANE;
+            const int ty = (f.type == RS_FEAT_POINT) ? RS_FEAT_POINT : (f.type == RS_FEAT_POINT2D ? RS_FEAT_POINT2D : RS_FEAT_PLANE);
             double o[4] = {f.obs[0], f.obs[1], f.obs[2], f.obs[3]};
             double m[4] = {f.map[0], f.map[1], f.map[2], f.map[3]};
+            double sg[4] = {0.0, 0.0, 0.0, 0.0}, ax[4] = {0.0, 0.0, 0.0, 0.0};
+            // is_valid: map_point.cpp:60-64, map_primitive.cpp:79-83, map_point2d.cpp:75-79
             const int k = (ty == RS_FEAT_POINT) ? 3 : 4;
             const int ko = (ty == RS_FEAT_POINT) ? 2 : 4;
+            const int ks = (ty == RS_FEAT_POINT2D) ? 3 : k;
             bool bad = false;
             for (int c = 0; c < ko; ++c) bad = bad || (o[c] != o[c]);
-            for (int c = 0; c < k; ++c) bad = bad || (m[c] != m[c]) || !(f.sigma[c] >= 0.0);
+            for (int c = 0; c < k; ++c) bad = bad || (m[c] != m[c]);
+            for (int c = 0; c < ks; ++c) bad = bad || !(f.sigma[c] >= 0.0);
             if (bad) atomicOr(&s_invalid, 1);
             if (ty == RS_FEAT_PLANE) {
                 normalize3(o);
                 normalize3(m);
+                for (int c = 0; c < 4; ++c) sg[c] = f.sigma[c];
+            }
+            else if (ty == RS_FEAT_POINT) {
+                o[2] = 0.0, o[3] = 0.0, m[3] = 0.0;
+                for (int c = 0; c < 3; ++c) sg[c] = f.sigma[c];
             }
             else {
-                o[2] = 0.0, o[3] = 0.0, m[3] = 0.0;
+                // inverse-depth point: device layout o = (u, v, dFar, dNear), m = (theta, phi), ax = first observation
+                // (+ inverse depth), sg = (sigma theta, sigma phi). get_furthest/closest_estimation
+                // (inverse_depth_coordinates.cpp:142-154) with the square root taken of the STANDARD DEVIATION, as
+                // Point2dOptimizationFeature::get_distance passes it in the covariance's place (map_point2d.cpp:42-43, :159).
+                const double depthVariation = sqrt(f.sigma[0]) * 3;
+                ax[0] = f.map[0], ax[1] = f.map[1], ax[2] = f.map[2], ax[3] = f.map[3];
+                m[0] = f.obs[2], m[1] = f.obs[3], m[2] = 0.0, m[3] = 0.0;
+                o[2] = fmin(f.map[3] - depthVariation, 1e-9);
+                o[3] = fmin(f.map[3] + depthVariation, 1e-9);
+                sg[0] = f.sigma[1], sg[1] = f.sigma[2];
             }
             type[i] = ty;
             for (int c = 0; c < 4; ++c) {
                 obs[c * M + i] = o[c];
                 map[c * M + i] = m[c];
-                sig[c * M + i] = (c < k) ? f.sigma[c] : 0.0;
+                sig[c * M + i] = sg[c];
+                buf.aux[(size_t(b) * 4 + c) * M + i] = ax[c];
             }
             buf.mask[size_t(b) * M + i] = 0;
         }
         else {
             type[i] = RS_FEAT_POINT;
-            for (int c = 0; c < 4; ++c) obs[c * M + i] = 0.0, map[c * M + i] = 0.0, sig[c * M + i] = 0.0;
+            for (int c = 0; c < 4; ++c)
+                obs[c * M + i] = 0.0, map[c * M + i] = 0.0, sig[c * M + i] = 0.0, buf.aux[(size_t(b) * 4 + c) * M + i] = 0.0;
             buf.mask[size_t(b) * M + i] = 0;
         }
     }
@@ -995,9 +1140,9 @@ __global__ void __launch_bounds__(THREADS) pose_prepare_kernel(const PoseBuffers
         double score = 0.0;
         int res = 0;
         for (int i = 0; i < n; ++i) {
-            const bool pt = src[i].type == RS_FEAT_POINT;
-            score += pt ? kPointScore : kPlaneScore;
-            res += pt ? 2 : 3;
+            const int ty = type[i];
+            score += score_of(ty);
+            res += parts_of(ty);
         }
         st.total_score = score;
         st.residuals = res;
@@ -1073,6 +1218,7 @@ __host__ __device__ inline size_t ransac_carve(RansacSmem* s, unsigned char* bas
 }
 
 // compute_pose_with_ransac (pose_optimization.cpp:107-262): one CTA per frame.
+template <bool P2D>
 __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1113,6 +1259,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
     short* subset = sm.subset + warp * RS_MAX_SUBSET;
     Problem P;
     P.type = sm.type, P.obs = sm.obs, P.map = sm.map, P.M = M;
+    P.aux = buf.aux + size_t(b) * 4 * M;
     volatile int* v_can_quit = &sh.can_quit;
     volatile int* v_next = &sh.next_iter;
     volatile int* v_applied = &sh.applied;
@@ -1201,7 +1348,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                         const int idx = in[k];
                         if (idx >= 0 && idx < n) subset[cnt++] = short(idx);
                     }
-                    for (int k = cnt - 1; k >= 0; --k) cumulated += sm.type[subset[k]] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
+                    for (int k = cnt - 1; k >= 0; --k) cumulated += score_of(sm.type[subset[k]]);
                 }
                 else {
                     // distinct uniform picks until the cumulated score reaches 1, each pick PREPENDED
@@ -1214,12 +1361,12 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                         for (int k = 0; k < cnt; ++k) dup = dup || (picks[k] == idx);
                         if (dup) continue;
                         picks[cnt++] = short(idx);
-                        cumulated += sm.type[idx] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
+                        cumulated += score_of(sm.type[idx]);
                     }
                     for (int k = 0; k < cnt; ++k) subset[k] = picks[cnt - 1 - k];
                 }
                 for (int k = 0; k < RS_MAX_SUBSET; ++k) used[k] = k < cnt ? int(subset[k]) : -1;
-                for (int k = 0; k < cnt; ++k) m += sm.type[subset[k]] == RS_FEAT_POINT ? 2 : 3;
+                for (int k = 0; k < cnt; ++k) m += parts_of(sm.type[subset[k]]);
             }
             P.idx = subset;
 #pragma unroll
@@ -1234,9 +1381,8 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                         const int i = w * 32 + (__ffs(bits) - 1);
                         bits &= bits - 1;
                         sm.inlier_idx[cnt++] = short(i);
-                        const bool pt = sm.type[i] == RS_FEAT_POINT;
-                        cumulated += pt ? kPointScore : kPlaneScore;
-                        m += pt ? 2 : 3;
+                        cumulated += score_of(sm.type[i]);
+                        m += parts_of(sm.type[i]);
                     }
                 }
                 out->n_inliers = sh.best_inliers;
@@ -1256,7 +1402,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
         if (finalPass && !ok) return;
         if (ok) {
             P.n = cnt;
-            ok = optimize_pose_warp(S, P, prm.K, xs, m, cumulated, prm.lm_max_fev, lane, finalPass ? nullptr : v_can_quit);
+            ok = optimize_pose_warp<P2D>(S, P, prm.K, xs, m, cumulated, prm.lm_max_fev, lane, finalPass ? nullptr : v_can_quit);
         }
         if (finalPass) {
             if (!ok) {
@@ -1296,7 +1442,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                     double o[4], mm[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) o[c] = sm.obs[c * M + i], mm[c] = sm.map[c * M + i];
-                    in = feature_is_inlier(sm.type[i], o, mm, S.T, prm.K);
+                    in = feature_is_inlier<P2D>(sm.type[i], o, mm, S.T, prm.K, P.aux, M, i);
                 }
                 const unsigned bits = __ballot_sync(FULL, in);
                 if (lane == 0) hmask[w] = bits;
@@ -1310,7 +1456,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                     while (bits) {
                         const int i = w * 32 + (__ffs(bits) - 1);
                         bits &= bits - 1;
-                        score += sm.type[i] == RS_FEAT_POINT ? kPointScore : kPlaneScore;
+                        score += score_of(sm.type[i]);
                     }
                 }
             }
@@ -1336,6 +1482,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
 
 // compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
 // grid (ceil(n_variance / WARPS), B), one warp per Monte-Carlo sample.
+template <bool P2D>
 __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1380,6 +1527,14 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
             for (int c = 0; c < 3; ++c) pmap[c * M + i] = gmap[c * M + i] + g[c] * gsig[c * M + i];
             pmap[3 * M + i] = 0.0;
         }
+        else if (P2D && s_type[i] == RS_FEAT_POINT2D) {
+            // map_point2d.cpp:49-73: theta then phi, clamped to [0, pi] / [-pi, pi]; nothing else varies
+            const double th = gmap[i] + g[0] * gsig[i], ph = gmap[M + i] + g[1] * gsig[M + i];
+            pmap[i] = th < 0.0 ? 0.0 : (kPi < th ? kPi : th);
+            pmap[M + i] = ph < -kPi ? -kPi : (kPi < ph ? kPi : ph);
+            pmap[2 * M + i] = 0.0;
+            pmap[3 * M + i] = 0.0;
+        }
         else {
             // map_primitive.cpp:66-77: perturbed normal renormalised (twice: vector + PlaneCoordinates ctor)
             double nn[3];
@@ -1395,11 +1550,12 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
     __syncwarp();
     Problem P;
     P.n = cnt, P.idx = s_idx, P.type = s_type, P.obs = s_obs, P.map = pmap, P.M = M;
+    P.aux = buf.aux + size_t(b) * 4 * M;
     WarpLM& S = s_lm[warp];
     double x0[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) x0[j] = st.final_x[j];
-    const bool ok = optimize_pose_warp(S, P, prm.K, x0, st.inlier_residuals, st.inlier_score, prm.lm_max_fev, lane);
+    const bool ok = optimize_pose_warp<P2D>(S, P, prm.K, x0, st.inlier_residuals, st.inlier_score, prm.lm_max_fev, lane);
     if (lane == 0) {
         double v[6] = {0, 0, 0, 0, 0, 0};
         if (ok) pose_vector6(S.x, v);
@@ -1543,15 +1699,22 @@ int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStrea
     return RS_OK;
 }
 
+// Two instantiations of the RANSAC / Monte-Carlo kernels: the usual one knows only points and planes; the other also
+// carries the inverse-depth ("line") residual, whose sincos / two-projection / seven-evaluation code would otherwise cost
+// the hot loops registers (measured: +50 % on the Monte-Carlo kernel when merely compiled in). prm.has_point2d selects.
 int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
 {
     const size_t smem = ransac_carve(nullptr, nullptr, buf.max_matches);
     static size_t configured = 0;
     if (smem > configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
     }
-    pose_ransac_kernel<<<prm.batch, RTHREADS, smem, stream>>>(buf, prm);
+    if (prm.has_point2d)
+        pose_ransac_kernel<true><<<prm.batch, RTHREADS, smem, stream>>>(buf, prm);
+    else
+        pose_ransac_kernel<false><<<prm.batch, RTHREADS, smem, stream>>>(buf, prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }
@@ -1562,11 +1725,15 @@ int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStre
     const size_t smem = variance_smem_bytes(buf.max_matches);
     static size_t configured = 0;
     if (smem > configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
     }
     const dim3 grid((prm.n_variance + WARPS - 1) / WARPS, prm.batch);
-    pose_variance_kernel<<<grid, THREADS, smem, stream>>>(buf, prm);
+    if (prm.has_point2d)
+        pose_variance_kernel<true><<<grid, THREADS, smem, stream>>>(buf, prm);
+    else
+        pose_variance_kernel<false><<<grid, THREADS, smem, stream>>>(buf, prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }

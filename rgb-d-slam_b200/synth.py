@@ -90,9 +90,10 @@ def camera_to_world(pose7):
     return Cm @ T
 
 
-def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.1, scale=1, guess=0.9):
-    """Matched features of one frame: returns (true_pose7, guess_pose7, matches[n_points+n_planes]).
-    The last outlier_frac of each kind are outliers built like the reference's tests build them."""
+def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.1, scale=1, guess=0.9, n_points2d=0):
+    """Matched features of one frame: returns (true_pose7, guess_pose7, matches[n_points+n_planes(+n_points2d)]).
+    The last outlier_frac of each kind are outliers built like the reference's tests build them. n_points2d > 0 appends
+    inverse-depth features (RS_FEAT_POINT2D, the "line" residual), first observed from the true camera position."""
     rng = np.random.default_rng(1000 + frame_index)
     fx, fy, cx, cy = intrinsics(scale)
     d2r = np.pi / 180.0
@@ -101,7 +102,7 @@ def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.
     guess_pose = np.concatenate([np.array([10.0, 10.0, 10.0]) * guess, quat_from_euler(yaw * guess, pitch * guess, roll * guess)])
     c2w = camera_to_world(true_pose)
     w2c = np.linalg.inv(c2w)
-    m = np.zeros((n_points + n_planes,), dtype=abi.match_dtype)
+    m = np.zeros((n_points + n_planes + n_points2d,), dtype=abi.match_dtype)
 
     # points: uniform in a 2 m x 2 m x (1..3 m) frustum in front of the true pose
     pc = np.stack([rng.uniform(-1000, 1000, n_points), rng.uniform(-1000, 1000, n_points), rng.uniform(1000, 3000, n_points)], 1)
@@ -136,6 +137,35 @@ def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.
     m["map"][sl, :3] = nw
     m["map"][sl, 3] = dw
     m["sigma"][sl] = np.array([0.01, 0.01, 0.01, 1.0])
+    if n_points2d:
+        # inverse-depth points: bearing (theta, phi) from the first observation towards a world point, inverse depth
+        # 1 / distance; two thirds with a small inverse-depth sigma (both depth estimates collapse on the far point,
+        # inverse_depth_coordinates.cpp:142-154), one third with a large one (the furthest estimate falls behind the
+        # first observation, so the screen line really is a line)
+        q = np.stack([rng.uniform(-1000, 1000, n_points2d), rng.uniform(-1000, 1000, n_points2d),
+                      rng.uniform(1000, 3000, n_points2d)], 1)
+        qw = (c2w[:3, :3] @ q.T).T + c2w[:3, 3]
+        origin = c2w[:3, 3]
+        v = qw - origin
+        dist = np.linalg.norm(v, axis=1)
+        theta = np.arccos(v[:, 2] / dist)
+        phi = np.arctan2(v[:, 1], v[:, 0])
+        uv2 = np.stack([fx * q[:, 0] / q[:, 2] + cx, fy * q[:, 1] / q[:, 2] + cy], 1) + rng.normal(0, 0.5, (n_points2d, 2))
+        n_out = int(round(n_points2d * outlier_frac))
+        if n_out:
+            uv2[n_points2d - n_out:, 0] = rng.uniform(0, 640 * scale, n_out)
+            uv2[n_points2d - n_out:, 1] = rng.uniform(0, 480 * scale, n_out)
+        sl2 = slice(n_points + n_planes, n_points + n_planes + n_points2d)
+        m["type"][sl2] = abi.RS_FEAT_POINT2D
+        m["obs"][sl2, :2] = uv2
+        m["obs"][sl2, 2] = theta
+        m["obs"][sl2, 3] = phi
+        m["map"][sl2, :3] = origin
+        m["map"][sl2, 3] = 1.0 / dist
+        sig_d = np.where(np.arange(n_points2d) % 3 == 2, 1e-6, 1e-8)
+        m["sigma"][sl2, 0] = sig_d
+        m["sigma"][sl2, 1] = 0.002
+        m["sigma"][sl2, 2] = 0.002
     del w2c
     return true_pose, guess_pose, m
 

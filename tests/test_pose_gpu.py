@@ -193,3 +193,47 @@ def test_begin_end_split_matches_blocking_call(solver):
     assert want.tobytes() == got.tobytes() and wmask.tobytes() == gmask.tobytes()
     with pytest.raises(RuntimeError):
         solver.compute_optimized_pose_end()                    # nothing pending
+
+
+def test_point2d_line_residual_matches_oracle(solver):
+    """RS_FEAT_POINT2D (Point2dOptimizationFeature, the "line" residual of the north star): mixed sets in both RNG modes.
+    PARITY UNPINNED beyond the restatement - the reference has no test that builds this feature type."""
+    B = 6
+    truth, cur, matches, n = rs.synth.pose_batch(800, B, M, n_points=200, n_planes=12, n_points2d=60)
+    assert (matches["type"] == rs.abi.RS_FEAT_POINT2D).sum() == B * 60
+    opts = solver.options(seed=21, rng_mode=rs.abi.RS_RNG_REFERENCE)
+    out, mask = solver.compute_optimized_pose(cur, matches, n, opts)
+    for b in range(B):
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], seed=21 + b)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
+        assert rout["status"] == 1 and np.linalg.norm(out[b]["pose"][:3] - truth[b][:3]) < 5.0
+        assert mask[b][212:272].sum() > 40                      # the inverse-depth features take part as inliers
+    opts = solver.options(seed=22, rng_mode=rs.abi.RS_RNG_DEVICE)
+    out, mask = solver.compute_optimized_pose(cur, matches, n, opts)
+    subsets, normals = solver.export_random(B, 119, 100)
+    for b in range(B):
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], subsets=subsets[b], normals=normals[b], max_matches=M)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
+    # a batch without the type runs the lean kernels again and still agrees
+    truth, cur, matches, n = rs.synth.pose_batch(810, 2, M)
+    opts = solver.options(seed=23, rng_mode=rs.abi.RS_RNG_REFERENCE)
+    out, mask = solver.compute_optimized_pose(cur, matches, n, opts)
+    for b in range(2):
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], seed=23 + b)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
+
+
+def test_point2d_invalid_feature_rejects_the_frame(solver):
+    # is_valid (map_point2d.cpp:75-79): a negative standard deviation on an inverse-depth feature fails the whole frame
+    # (compute_optimized_pose :269-282), the other frames of the batch are unaffected
+    truth, cur, matches, n = rs.synth.pose_batch(820, 3, M, n_points=150, n_planes=10, n_points2d=40)
+    opts = solver.options(seed=5, rng_mode=rs.abi.RS_RNG_REFERENCE)
+    bad = matches.copy()
+    bad["sigma"][0, 170, 1] = -1.0
+    assert bad["type"][0, 170] == rs.abi.RS_FEAT_POINT2D
+    out, mask = solver.compute_optimized_pose(cur, bad, n, opts)
+    rout, rmask = ol.pose_solve(cur[0], bad[0][:n[0]], seed=5)
+    assert out[0]["status"] == rout["status"] == 0
+    for b in (1, 2):
+        rout, rmask = ol.pose_solve(cur[b], bad[b][:n[b]], seed=5 + b)
+        assert_out_match(rout, out[b], rmask, mask[b], n[b])
