@@ -7,7 +7,7 @@
 // Required reference-side patch (3 small changes):
 //   1. Plane_Segment: public ctor `Plane_Segment(uint pointCount, const double sums[9])` that fills _pointCount and
 //      _Sx.._Szx and calls fit_plane()   (members are private: plane_segment.hpp:118-140)
-//   2. PointOptimizationFeature / PlaneOptimizationFeature: `friend struct rs_adaptor::Flatten;`
+//   2. PointOptimizationFeature / PlaneOptimizationFeature / Point2dOptimizationFeature: `friend struct rs_adaptor::Flatten;`
 //      (their _matchedPoint/_mapPoint/... members are protected: map_point.hpp:40-43, map_primitive.hpp:40-43)
 //   3. CMake: link rgbdslam_b200 into `primitives` and `poseOptimization` (CMakeLists.txt:117-123,136-139)
 #include <rgbdslam_b200.h>
@@ -19,6 +19,7 @@
 #include "features/primitives/primitive_detection.hpp"
 #include "features/primitives/shape_primitives.hpp"
 #include "map_management/map_features/map_point.hpp"
+#include "map_management/map_features/map_point2d.hpp"
 #include "map_management/map_features/map_primitive.hpp"
 #include "outputs/logger.hpp"
 #include "parameters.hpp"
@@ -163,7 +164,25 @@ struct Flatten  // befriended by the two optimisation-feature classes (patch 2)
             for (int i = 0; i < 4; ++i) m.obs[i] = o(i), m.map[i] = w(i), m.sigma[i] = p._mapPlaneStandardDev(i);
             return true;
         }
-        return false;  // Point2d (inverse depth): not on the B200 path yet
+        if (f->get_feature_type() == FeatureType::Point2d)
+        {
+            // inverse-depth map point (map_point2d.hpp; also befriended): packing documented at rs_match in the header
+            const auto& p = static_cast<const map_management::Point2dOptimizationFeature&>(*f);
+            m.type = RS_FEAT_POINT2D;
+            m.obs[0] = p._matchedPoint.x(), m.obs[1] = p._matchedPoint.y();
+            m.obs[2] = p._mapPoint.get_theta(), m.obs[3] = p._mapPoint.get_phi();
+            const WorldCoordinate first = p._mapPoint.get_first_observation();
+            for (int i = 0; i < 3; ++i) m.map[i] = first(i);
+            m.map[3] = p._mapPoint.get_inverse_depth();
+            // is_valid also wants the first observation's standard deviations finite and >= 0 (map_point2d.cpp:75-79)
+            for (int i = 0; i < 3; ++i)
+                if (not(p._mapPointStandardDev(i) >= 0)) return false;
+            m.sigma[0] = p._mapPointStandardDev(InverseDepthWorldPoint::inverseDepthIndex);
+            m.sigma[1] = p._mapPointStandardDev(InverseDepthWorldPoint::thetaIndex);
+            m.sigma[2] = p._mapPointStandardDev(InverseDepthWorldPoint::phiIndex);
+            return true;
+        }
+        return false;
     }
 };
 
