@@ -4,8 +4,9 @@
 //                   Plane_Segment::init_plane_segment + fit_plane         (plane_segment.cpp:44-168,205-284)
 //                   Primitive_Detection::init_planar_cell_fitting          (primitive_detection.cpp:187-221)
 //
-// Two kernels. K1a `cape_cell_fit_kernel` streams the depth image: one warp owns a run of up to 32 consecutive cells
-// of one cell-row. The run is consumed as "items" of 8 cells, FOUR LANES PER CELL: a 3-D tiled TMA box
+// Two kernels. K1a `cape_cell_fit_kernel` streams the depth image on a persistent grid (one CTA per resident slot): the
+// work unit is an "item" of 8 adjacent cells of one cell-row, items are dealt to the warps with a grid stride, FOUR LANES
+// PER CELL: a 3-D tiled TMA box
 // {cs px, 8 cells, R rows} (R*cs*8*4 = 2560 B) lands as [row][cell][px] in a 2-slot per-warp ring guarded by
 // mbarriers; lane (c = lane/4, j = lane%4) reads the float4 j, j+4, j+8, ... of cell c's part of the box (LDS.128, at
 // most 2-way bank conflicts; exactly 5 trips per box), back-projects in FP64 and accumulates the nine sums of FP32
@@ -15,13 +16,15 @@
 // with Veltkamp's split (round_to_float, bit-identical to the conversion, tests/test_oracle_cape.py) and the rest go
 // through FMUL + F2F; the two pipes end up balanced. The pixel loop is branch-free: an invalid pixel (z <= 0)
 // contributes exact zeros, as its (0,0,0) cloud row does. Per item the sums are reduced over the 4 lanes of a cell with
-// two shuffle steps and handed to lane 8*item + c, so that after four items every lane holds one cell; the cross-shaped
+// two shuffle steps (all four lanes end up with the totals and each writes a quarter of the record); the cross-shaped
 // continuity test runs from small per-warp copies of the middle row / middle column, split over the 4 lanes of the cell.
 // K1b `cape_cell_finish_kernel` then fits every cell (3x3 eigen-solve, planarity, merge tolerance), one thread per cell,
 // in place on the 160-byte record: inside the streaming kernel that serial chain cost 30 % of the time.
 //
 // Compiled with -fmad=false: products are FP32-rounded then accumulated in FP64 exactly as the reference does.
 #include <cuda.h>
+
+#include <algorithm>
 
 #include "cape_internal.cuh"
 #include "plane_fit.cuh"
@@ -106,17 +109,23 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
     float* midcol = midrow + CELLS_PER_ITEM * CS;                            // [8][CS] (CS-1 used)
     uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + 2 * Geo::BOX_BYTES + Geo::MID_BYTES);
 
-    const int unit = blockIdx.x * WARPS + warp;
-    if (unit >= prm.total_items) return;
-    const int ips = prm.items_per_strip;               // 32-cell runs per cell-row
-    const int b = unit / (prm.vc * ips);
-    const int rem = unit - b * prm.vc * ips;
-    const int cr = rem / ips;
-    const int c0 = (rem - cr * ips) * 32;
-    const int ncell = min(32, prm.hc - c0);
-    const int nitems = (ncell + CELLS_PER_ITEM - 1) / CELLS_PER_ITEM;
+    // Work unit = one item (8 adjacent cells of a cell row). The grid is sized to the resident warp slots and every warp
+    // walks the item list with a grid stride: ~10 items per warp at 256 frames, so the last round is 94 % full instead of
+    // the 59 % that one 32-cell strip per warp left (2.59 waves). The 2-slot TMA ring runs straight through item boundaries.
+    const int gwarp = blockIdx.x * WARPS + warp, nwarps = gridDim.x * WARPS;
+    if (gwarp >= prm.total_items) return;
+    const int nitems = (prm.total_items - gwarp + nwarps - 1) / nwarps;     // items of this warp
     const int nbox = nitems * NBOX;
-    const int row0 = b * prm.H + cr * CS;              // first image row of the strip in the [B*H] row dimension
+    const int ipr = prm.items_per_strip;                                    // items per cell row
+    // item -> (first image row in the [B*H] dimension, first cell column)
+    auto item_origin = [&](const int k, int& row0, int& c0, int& cr, int& b) {
+        const int item = gwarp + k * nwarps;
+        b = item / (prm.vc * ipr);
+        const int rem = item - b * prm.vc * ipr;
+        cr = rem / ipr;
+        c0 = (rem - cr * ipr) * CELLS_PER_ITEM;
+        row0 = b * prm.H + cr * CS;
+    };
 
     const uint64_t policy = l2_policy_evict_first();   // the depth image is read once; keep L2 for the records
     if (lane == 0) {
@@ -127,19 +136,15 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
 #pragma unroll
         for (int q = 0; q < 2; ++q)
             if (q < nbox) {
+                int row0, c0, cr, b;
+                item_origin(q / NBOX, row0, c0, cr, b);
                 mbar_arrive_expect_tx(&bars[q], Geo::BOX_BYTES);
-                tma_load_3d_hint(wbase + q * Geo::BOX_BYTES, &tmap, 0, c0 + (q / NBOX) * CELLS_PER_ITEM, row0 + (q % NBOX) * R, &bars[q], policy);
+                tma_load_3d_hint(wbase + q * Geo::BOX_BYTES, &tmap, 0, c0, row0 + (q % NBOX) * R, &bars[q], policy);
             }
     }
     __syncwarp();
 
     const int c = lane >> 2, j = lane & 3;             // cell inside the item, lane inside the cell
-    const double* kyrow = prm.ky + cr * CS;
-
-    // this lane's final cell (lane = 8 * item + cell): sums, count, flags, first / last cloud rows
-    double F0 = 0, F1 = 0, F2 = 0, F3 = 0, F4 = 0, F5 = 0, F6 = 0, F7 = 0, F8 = 0;
-    int fcount = 0, fok = 0;
-    float fp0x = 0.f, fp0y = 0.f, fp0z = 0.f, fplx = 0.f, fply = 0.f, fplz = 0.f;
 
     double S0 = 0, S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0, S6 = 0, S7 = 0, S8 = 0;
     int cnt = 0;
@@ -147,10 +152,13 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
 
     for (int q = 0; q < nbox; ++q) {
         const int slot = q & 1;
-        const int item = q / NBOX, bq = q - item * NBOX;
+        const int k = q / NBOX, bq = q - k * NBOX;
+        int row0, c0, cr, b;
+        item_origin(k, row0, c0, cr, b);
+        const double* kyrow = prm.ky + cr * CS;
         const float* tile = reinterpret_cast<const float*>(wbase + slot * Geo::BOX_BYTES);
         const float* ctile = tile + c * CS;            // this cell's columns inside a box row
-        const int colbase = (c0 + item * CELLS_PER_ITEM + c) * CS;
+        const int colbase = (c0 + c) * CS;
         mbar_wait(&bars[slot], (q >> 1) & 1);
 
         // ---- branch-free accumulation of this lane's float4s of the box ----
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
             ++r;
         }
 #pragma unroll 1
-        for (int k = 0; k < Geo::ITERS; ++k) {
+        for (int it = 0; it < Geo::ITERS; ++it) {
             {
                 const float4 v = *reinterpret_cast<const float4*>(ctile + r * Geo::ROW_FLOATS + g * 4);
                 const double2 kxa = __ldg(reinterpret_cast<const double2*>(prm.kx + colbase + g * 4));
@@ -253,12 +261,14 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         // the box is consumed: refill the slot with box q + 2
         if (lane == 0 && q + 2 < nbox) {
             const int qn = q + 2;
+            int nrow0, nc0, ncr, nb;
+            item_origin(qn / NBOX, nrow0, nc0, ncr, nb);
             mbar_arrive_expect_tx(&bars[slot], Geo::BOX_BYTES);
-            tma_load_3d_hint(wbase + slot * Geo::BOX_BYTES, &tmap, 0, c0 + (qn / NBOX) * CELLS_PER_ITEM, row0 + (qn % NBOX) * R, &bars[slot], policy);
+            tma_load_3d_hint(wbase + slot * Geo::BOX_BYTES, &tmap, 0, nc0, nrow0 + (qn % NBOX) * R, &bars[slot], policy);
         }
         if (bq != NBOX - 1) continue;
 
-        // ---- item finished: reduce the 4 lanes of each cell, run the continuity test, hand over to lane 8*item+c ----
+        // ---- item finished: reduce the 4 lanes of each cell (all four end up with the totals), continuity test ----
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {
             cnt += __shfl_xor_sync(FULL, cnt, o);
@@ -287,20 +297,34 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         }
         const unsigned bad = __ballot_sync(FULL, !cont);
         const int okc = (((bad >> (lane & ~3)) & 0xfu) == 0u && cnt >= P / 2) ? 1 : 0;
+        // the first / last cloud rows live on the cell's lane 0: hand them to its three neighbours
+        const int lead = lane & ~3;
+        const float a0 = __shfl_sync(FULL, p0x, lead), a1 = __shfl_sync(FULL, p0y, lead), a2 = __shfl_sync(FULL, p0z, lead);
+        const float b0 = __shfl_sync(FULL, plx, lead), b1 = __shfl_sync(FULL, ply, lead), b2 = __shfl_sync(FULL, plz, lead);
 
-        const int src = (lane & 7) * 4;                // leader lane of cell (lane & 7) of this item
-        const bool mine = (lane >> 3) == item;
-        {
-            const double t0 = __shfl_sync(FULL, S0, src), t1 = __shfl_sync(FULL, S1, src), t2 = __shfl_sync(FULL, S2, src);
-            const double t3 = __shfl_sync(FULL, S3, src), t4 = __shfl_sync(FULL, S4, src), t5 = __shfl_sync(FULL, S5, src);
-            const double t6 = __shfl_sync(FULL, S6, src), t7 = __shfl_sync(FULL, S7, src), t8 = __shfl_sync(FULL, S8, src);
-            const int tc = __shfl_sync(FULL, cnt, src), tk = __shfl_sync(FULL, okc, src);
-            const float a0 = __shfl_sync(FULL, p0x, src), a1 = __shfl_sync(FULL, p0y, src), a2 = __shfl_sync(FULL, p0z, src);
-            const float b0 = __shfl_sync(FULL, plx, src), b1 = __shfl_sync(FULL, ply, src), b2 = __shfl_sync(FULL, plz, src);
-            if (mine) {
-                F0 = t0, F1 = t1, F2 = t2, F3 = t3, F4 = t4, F5 = t5, F6 = t6, F7 = t7, F8 = t8;
-                fcount = tc, fok = tk;
-                fp0x = a0, fp0y = a1, fp0z = a2, fplx = b0, fply = b1, fplz = b2;
+        // ---- hand the cell over to the fit kernel: sums, count, continuity flag and the first / last cloud rows travel
+        // in the cell's own record (the two points in the centroid / normal slots); the four lanes of a cell write two
+        // 16-byte pieces each ----
+        if (c0 + c < prm.hc) {
+            double2* dst = reinterpret_cast<double2*>(cells + (size_t(b) * prm.vc + cr) * prm.hc + c0 + c);
+            if (j == 0) {
+                double2 head;
+                head.x = __hiloint2double(okc, cnt);   // {int32 count, int32 planar := continuity / count test passed}
+                head.y = S0;
+                dst[0] = head;
+                dst[1] = make_double2(S1, S2);
+            }
+            else if (j == 1) {
+                dst[2] = make_double2(S3, S4);
+                dst[3] = make_double2(S5, S6);
+            }
+            else if (j == 2) {
+                dst[4] = make_double2(S7, S8);
+                dst[5] = make_double2(static_cast<double>(a0), static_cast<double>(a1));
+            }
+            else {
+                dst[6] = make_double2(static_cast<double>(a2), static_cast<double>(b0));
+                dst[7] = make_double2(static_cast<double>(b1), static_cast<double>(b2));
             }
         }
         S0 = S1 = S2 = S3 = S4 = S5 = S6 = S7 = S8 = 0.0;
@@ -308,22 +332,6 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         p0x = p0y = p0z = plx = ply = plz = 0.f;
         __syncwarp();                                   // midrow / midcol are rewritten by the next item
     }
-
-    // ---- hand the cell over to the fit kernel: sums, count, continuity flag and the first / last cloud rows travel in
-    // the cell's own record (the two points in the centroid / normal slots), 16-byte stores ----
-    if (lane >= ncell) return;
-    double2* dst = reinterpret_cast<double2*>(cells + (size_t(b) * prm.vc + cr) * prm.hc + c0 + lane);
-    double2 head;
-    head.x = __hiloint2double(fok, fcount);            // {int32 count, int32 planar := continuity / count test passed}
-    head.y = F0;
-    dst[0] = head;
-    dst[1] = make_double2(F1, F2);
-    dst[2] = make_double2(F3, F4);
-    dst[3] = make_double2(F5, F6);
-    dst[4] = make_double2(F7, F8);
-    dst[5] = make_double2(static_cast<double>(fp0x), static_cast<double>(fp0y));
-    dst[6] = make_double2(static_cast<double>(fp0z), static_cast<double>(fplx));
-    dst[7] = make_double2(static_cast<double>(fply), static_cast<double>(fplz));
 }
 
 // K1b: the per-cell fit (plane_segment.cpp:102-168 after the sums, primitive_detection.cpp:201-220), one THREAD per cell.
@@ -400,9 +408,11 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
         configured = true;
     }
     CellFitParams p = prm;
-    p.items_per_strip = (prm.hc + 31) / 32;
+    p.items_per_strip = (prm.hc + CELLS_PER_ITEM - 1) / CELLS_PER_ITEM;   // items (8 cells) per cell row
     p.total_items = prm.batch * prm.vc * p.items_per_strip;
-    const int grid = (p.total_items + WARPS - 1) / WARPS;
+    // persistent grid: one CTA per resident slot (148 SMs x RS_K1_MIN_CTAS), fewer when the batch is small
+    const int slots = 148 * RS_K1_MIN_CTAS;
+    const int grid = std::min(slots, (p.total_items + WARPS - 1) / WARPS);
     kernel<<<grid, WARPS * 32, smem, stream>>>(tmap, p, cells);
     RS_LAUNCH_CHECK();
     if (streamed) RS_CUDA_CHECK(cudaEventRecord(streamed, stream));   // the HBM-bound part is over: other streams may start
