@@ -34,10 +34,13 @@ class FramePipeline:
         """This rank's shard: depth [F,H,W] float32, cur_pose [F,7], matches [F,max_matches], n_matches [F] (host).
         Returns (primitives dict, pose_out[F], inlier_mask[F,max_matches], all_poses [n_frames_global,7] tensor)."""
         F = len(depth)
-        prims = self.detector.find_primitives(depth, seed=seed)
         opts = self.solver.options(max_iterations=self.max_iterations, n_variance=self.n_variance, rng_mode=rng_mode,
                                    seed=seed, intrinsics=self.intrinsics)
-        out, mask = self.solver.compute_optimized_pose(cur_pose, matches, n_matches, opts)
+        # the reference runs find_primitives on a std::async thread beside the rest of the frame (rgbd_slam.cpp:288-300):
+        # the pose solve is enqueued first, the depth batch streams through the GPU meanwhile, then the solve is joined
+        self.solver.compute_optimized_pose_begin(cur_pose, matches, n_matches, opts)
+        prims = self.detector.find_primitives(depth, seed=seed)
+        out, mask = self.solver.compute_optimized_pose_end()
         poses = torch.as_tensor(_DevicePtr(self.solver.device_poses_ptr(), (F, 7), "<f8"), device="cuda:%d" % self.device)
         total = F if n_frames_global is None else n_frames_global
         all_poses = sharding.gather_poses(poses, total)
