@@ -106,3 +106,21 @@ def test_pose_batch_256_properties_and_determinism():
     out2, mask2 = solver.compute_optimized_pose(cur, m, n, opts)
     assert out.tobytes() == out2.tobytes() and mask.tobytes() == mask2.tobytes()
     solver.close()
+
+
+def test_frame_pipeline_track_batch_matches_separate_calls():
+    """FramePipeline.track_batch (pose solve enqueued, depth streamed meanwhile, solve joined) == the two blocking calls."""
+    F, M = 6, 320
+    depth = rs.synth.scene_v0_batch(500, F)
+    truth, cur, m, n = rs.synth.pose_batch(500, F, M)
+    pipe = rs.FramePipeline(max_frames=F, max_matches=M)
+    prims, out, mask, all_poses = pipe.track_batch(depth, cur, m, n, seed=3, rng_mode=rs.abi.RS_RNG_DEVICE)
+    det = rs.PrimitiveDetection(640, 480, 20, max_batch=F)
+    solver = rs.PoseOptimization(max_batch=F, max_matches=M)
+    want_prims = det.find_primitives(depth, seed=3)
+    want_out, want_mask = solver.compute_optimized_pose(cur, m, n, solver.options(seed=3, rng_mode=rs.abi.RS_RNG_DEVICE))
+    assert prims["cells"].tobytes() == want_prims["cells"].tobytes()
+    assert np.array_equal(prims["plane_labels"], want_prims["plane_labels"])
+    assert out.tobytes() == want_out.tobytes() and mask.tobytes() == want_mask.tobytes()
+    assert np.array_equal(all_poses.cpu().numpy(), out["pose"])
+    pipe.close(), det.close(), solver.close()
