@@ -58,6 +58,73 @@ def scene_v0_batch(first_frame, batch, width=640, height=480):
     return np.stack([scene_v0_depth(first_frame + i, width, height) for i in range(batch)])
 
 
+def random_scene_depth(seed, width=640, height=480):
+    """A randomly furnished room for parity sweeps: a back wall, 2-5 further random planes, 0-3 cylinders with random
+    axes and 0-1 sphere; range noise N(0, sigma) with sigma in [0.5, 3] mm and 0-6 % invalid pixels, all drawn from
+    default_rng(seed). Returns float32 [H, W]. The geometry is arbitrary on purpose (slanted cylinders, small regions,
+    planes that nearly merge): it is there to walk the region-growing / cylinder / merge branches, not to look real."""
+    rng = np.random.default_rng(1_000_003 * 7 + seed)
+    scale = width / 640.0
+    fx, fy, cx, cy = intrinsics(scale)
+    u = np.arange(width, dtype=np.float64)
+    v = np.arange(height, dtype=np.float64)
+    dx = np.broadcast_to(((u - cx) / fx)[None, :], (height, width))
+    dy = np.broadcast_to(((v - cy) / fy)[:, None], (height, width))
+    depth = np.full((height, width), np.inf)
+
+    def take(t, ok):
+        nonlocal depth
+        depth = np.where(ok & (t > 200.0) & (t < depth), t, depth)
+
+    planes = [(np.array([0.0, 0.0, -1.0]) + rng.normal(0, 0.08, 3), rng.uniform(2500.0, 4500.0))]
+    for _ in range(int(rng.integers(2, 6))):
+        n = rng.normal(0, 1, 3)
+        n[2] = -abs(n[2]) - 0.15
+        planes.append((n, rng.uniform(700.0, 2500.0)))
+    for n, d0 in planes:
+        n = n / np.linalg.norm(n)
+        nr = n[0] * dx + n[1] * dy + n[2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = -d0 / nr
+        take(t, nr < 0)
+    for _ in range(int(rng.integers(0, 4))):
+        # |(o + t r - c) - ((o + t r - c) . a) a|^2 = R^2 with o = 0
+        c = np.array([rng.uniform(-900, 900), rng.uniform(-600, 600), rng.uniform(1200, 2600)])
+        a = rng.normal(0, 1, 3)
+        a /= np.linalg.norm(a)
+        R = rng.uniform(120.0, 450.0)
+        ra = dx * a[0] + dy * a[1] + a[2]
+        ca = float(c @ a)
+        A = (dx * dx + dy * dy + 1.0) - ra * ra
+        B = -2.0 * ((dx * c[0] + dy * c[1] + c[2]) - ra * ca)
+        C = float(c @ c) - ca * ca - R * R
+        disc = B * B - 4 * A * C
+        with np.errstate(invalid="ignore", divide="ignore"):
+            t = (-B - np.sqrt(disc)) / (2 * A)
+        take(t, disc > 0)
+    if rng.random() < 0.5:
+        c = np.array([rng.uniform(-700, 700), rng.uniform(-500, 500), rng.uniform(1200, 2400)])
+        R = rng.uniform(150.0, 400.0)
+        A = dx * dx + dy * dy + 1.0
+        B = -2.0 * (dx * c[0] + dy * c[1] + c[2])
+        C = float(c @ c) - R * R
+        disc = B * B - 4 * A * C
+        with np.errstate(invalid="ignore"):
+            t = (-B - np.sqrt(disc)) / (2 * A)
+        take(t, disc > 0)
+    valid = np.isfinite(depth)
+    sigma = rng.uniform(0.5, 3.0)
+    zero_prob = rng.uniform(0.0, 0.06)
+    noise = rng.normal(0.0, sigma, (height, width))
+    drop = rng.random((height, width)) < zero_prob
+    depth = np.where(valid & ~drop, depth + noise, 0.0)
+    return depth.astype(np.float32)
+
+
+def random_scene_batch(first_seed, batch, width=640, height=480):
+    return np.stack([random_scene_depth(first_seed + i, width, height) for i in range(batch)])
+
+
 # ---- pose helpers (numpy restatement used only to BUILD synthetic correspondences) --------------------
 def quat_from_euler(yaw, pitch, roll):
     """AngleAxis(roll,X)*AngleAxis(pitch,Y)*AngleAxis(yaw,Z) as (w,x,y,z) (angle_utils.cpp:6-11)."""

@@ -69,6 +69,23 @@ def test_edge_cases(det):
         parity.assert_frame_match(ref, got, b)
 
 
+@pytest.mark.parametrize("first,seed", [(0, 0), (48, 7), (96, 2024)])
+def test_random_scenes_match_oracle(first, seed):
+    """48 randomly furnished rooms per case (synth.random_scene_depth: 0-6 planes, slanted cylinders, a sphere, varying
+    noise and holes): labels bit-exact, every plane / cylinder / boundary point within tolerance."""
+    depth = rs.synth.random_scene_batch(first, 48)
+    d = rs.PrimitiveDetection(640, 480, 20, max_batch=48)
+    got = d.find_primitives(depth, seed=seed)
+    d.close()
+    ref = ol.cape_run(depth, seed=seed)
+    assert np.array_equal(ref["plane_labels"], got["plane_labels"])
+    assert np.array_equal(ref["cyl_labels"], got["cyl_labels"])
+    for b in range(48):
+        parity.assert_cells_match(ref["cells"][b], got["cells"][b])
+        parity.assert_frame_match(ref, got, b)
+    assert ref["info"]["n_cylinders"].sum() > 10 and ref["info"]["n_seeds"].max() >= 8   # the sweep is not trivial
+
+
 def test_large_cells_1280x960():
     d = rs.PrimitiveDetection(1280, 960, 40, *rs.synth.intrinsics(2), max_batch=2)
     depth = rs.synth.scene_v0_batch(0, 2, 1280, 960)
