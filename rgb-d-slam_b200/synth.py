@@ -157,16 +157,18 @@ def camera_to_world(pose7):
     return Cm @ T
 
 
-def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.1, scale=1, guess=0.9, n_points2d=0):
+def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.1, scale=1, guess=0.9, n_points2d=0,
+                         position=(10.0, 10.0, 10.0), euler_deg=(45.0, -45.0, 20.0), pixel_sigma=0.5):
     """Matched features of one frame: returns (true_pose7, guess_pose7, matches[n_points+n_planes(+n_points2d)]).
     The last outlier_frac of each kind are outliers built like the reference's tests build them. n_points2d > 0 appends
     inverse-depth features (RS_FEAT_POINT2D, the "line" residual), first observed from the true camera position."""
     rng = np.random.default_rng(1000 + frame_index)
     fx, fy, cx, cy = intrinsics(scale)
     d2r = np.pi / 180.0
-    yaw, pitch, roll = 45 * d2r, -45 * d2r, 20 * d2r
-    true_pose = np.concatenate([[10.0, 10.0, 10.0], quat_from_euler(yaw, pitch, roll)])
-    guess_pose = np.concatenate([np.array([10.0, 10.0, 10.0]) * guess, quat_from_euler(yaw * guess, pitch * guess, roll * guess)])
+    yaw, pitch, roll = euler_deg[0] * d2r, euler_deg[1] * d2r, euler_deg[2] * d2r
+    position = np.asarray(position, dtype=np.float64)
+    true_pose = np.concatenate([position, quat_from_euler(yaw, pitch, roll)])
+    guess_pose = np.concatenate([position * guess, quat_from_euler(yaw * guess, pitch * guess, roll * guess)])
     c2w = camera_to_world(true_pose)
     w2c = np.linalg.inv(c2w)
     m = np.zeros((n_points + n_planes + n_points2d,), dtype=abi.match_dtype)
@@ -174,7 +176,7 @@ def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.
     # points: uniform in a 2 m x 2 m x (1..3 m) frustum in front of the true pose
     pc = np.stack([rng.uniform(-1000, 1000, n_points), rng.uniform(-1000, 1000, n_points), rng.uniform(1000, 3000, n_points)], 1)
     pw = (c2w[:3, :3] @ pc.T).T + c2w[:3, 3]
-    uv = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1) + rng.normal(0, 0.5, (n_points, 2))
+    uv = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1) + rng.normal(0, pixel_sigma, (n_points, 2))
     n_out_pt = int(round(n_points * outlier_frac))
     if n_out_pt:
         uv[n_points - n_out_pt:, 0] = rng.uniform(0, 640 * scale, n_out_pt)
@@ -235,6 +237,23 @@ def pose_correspondences(frame_index, n_points=300, n_planes=20, outlier_frac=0.
         m["sigma"][sl2, 2] = 0.002
     del w2c
     return true_pose, guess_pose, m
+
+
+def random_pose_problem(index):
+    """A random pose problem for parity sweeps: 5-300 points, 0-20 planes, sometimes 1-12 inverse-depth points, 0-45 %
+    outliers, true pose up to 2 m / 60 degrees per axis away, initial guess 0.5-1.0 x truth, pixel noise 0.2-1.5 px. About
+    a third are 'hard' (0-24 points, 0-4 planes, 30-90 % outliers): rejected frames, early exits, thin consensus sets.
+    Returns (true_pose7, guess_pose7, matches); at most 336 matches."""
+    rng = np.random.default_rng(77_000 + index)
+    hard = rng.random() < 0.35
+    kw = dict(n_points=int(rng.integers(0, 25)) if hard else int(rng.integers(5, 301)),
+              n_planes=int(rng.integers(0, 5)) if hard else int(rng.integers(0, 21)),
+              n_points2d=int(rng.integers(0, 13)) if rng.random() < 0.3 else 0,
+              outlier_frac=float(rng.uniform(0.3, 0.9)) if hard else float(rng.uniform(0, 0.45)),
+              guess=float(rng.uniform(0.5, 1.0)),
+              position=rng.uniform(-2000, 2000, 3), euler_deg=rng.uniform(-60, 60, 3),
+              pixel_sigma=float(rng.uniform(0.2, 1.5)))
+    return pose_correspondences(index, **kw)
 
 
 def pose_batch(first_frame, batch, max_matches, **kw):

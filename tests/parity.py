@@ -93,3 +93,28 @@ def pose_close(ref_pose, got_pose, rtol=1e-4, qtol=1e-8):
     dt = np.linalg.norm(ref_pose[:3] - got_pose[:3])
     qd = abs(float(np.dot(ref_pose[3:], got_pose[3:])))
     return dt <= max(rtol * tn, 1e-3) and qd >= 1 - qtol, dt, qd
+
+
+def oracle_pose_is_determined(pose_solve, cur, matches, seed, scales=(1e-12, 1e-10, -1e-10, 1e-9)):
+    """Is the reference algorithm's answer on this frame determined at all? Re-runs the oracle (`pose_solve` =
+    oracle_lib.pose_solve) with the observations scaled by 1 + s for a few s far below any sensor resolution. A frame where
+    that flips an integer output (winning hypothesis, inlier set), moves the pose by more than 1e-7 mm or the covariance by
+    more than 1e-6 relative amplifies rounding noise by > 1e8 - a hypothesis sitting on an inlier threshold, a consensus set
+    that barely constrains the pose - and no two builds of the reference itself would agree on it. Returns (determined, why)."""
+    ref, rmask = pose_solve(cur, matches, seed=seed)
+    for s in scales:
+        m2 = matches.copy()
+        m2["obs"][:, :2] *= 1.0 + s
+        out, mask = pose_solve(cur, m2, seed=seed)
+        for k in ("status", "best_iteration", "iterations_run", "n_inliers", "n_variance_ok"):
+            if out[k] != ref[k]:
+                return False, "%s flips under a %g relative input change" % (k, s)
+        if not np.array_equal(mask, rmask):
+            return False, "inlier set flips under a %g relative input change" % s
+        moved = np.linalg.norm(out["pose"][:3] - ref["pose"][:3])
+        if moved > max(1e-7, 1e3 * abs(s) * np.linalg.norm(ref["pose"][:3])):
+            return False, "pose moves %g mm under a %g relative input change" % (moved, s)
+        rc, pc = ref["cov"].reshape(6, 6), out["cov"].reshape(6, 6)
+        if np.abs(pc - rc).max() > max(1e-6, 1e4 * abs(s)) * max(np.abs(np.diag(rc)).max(), 1e-300):
+            return False, "covariance moves under a %g relative input change" % s
+    return True, ""

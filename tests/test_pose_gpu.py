@@ -132,6 +132,38 @@ def test_reference_scenarios(scenario):
         assert not failures, failures
 
 
+def test_random_problems_match_oracle():
+    """192 random problems (synth.random_pose_problem: sizes 0-336, up to 90 % outliers, inverse-depth features mixed in,
+    poses up to 2 m / 60 degrees away). Every frame must match the oracle, except frames whose oracle answer is itself
+    undetermined (parity.oracle_pose_is_determined: scaling the observations by 1 +- 1e-12..1e-9 flips the ORACLE's winning
+    hypothesis / inlier set or moves its pose or covariance out of proportion); there only the status has to agree.
+    tools/sweep_random_pose.py runs the same check on thousands of frames."""
+    Mx, B, first = 336, 32, 20_000
+    s = rs.PoseOptimization(max_batch=B, max_matches=Mx, max_iterations=119, max_variance=100)
+    undetermined = 0
+    for s0 in range(first, first + 192, B):
+        cur = np.zeros((B, 7))
+        matches = np.zeros((B, Mx), dtype=rs.abi.match_dtype)
+        n = np.zeros((B,), np.int32)
+        for b in range(B):
+            _, cur[b], m = rs.synth.random_pose_problem(s0 + b)
+            n[b] = len(m)
+            matches[b, :len(m)] = m
+        out, mask = s.compute_optimized_pose(cur, matches, n, s.options(seed=s0, rng_mode=rs.abi.RS_RNG_REFERENCE))
+        for b in range(B):
+            rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], seed=s0 + b)
+            try:
+                assert_out_match(rout, out[b], rmask, mask[b], n[b], cov_rtol=2e-2)
+            except AssertionError:
+                determined, why = parity.oracle_pose_is_determined(ol.pose_solve, cur[b], matches[b][:n[b]], s0 + b)
+                if determined:
+                    raise
+                assert out[b]["status"] == rout["status"]
+                undetermined += 1
+    s.close()
+    assert undetermined <= 8, undetermined
+
+
 def test_failure_and_ragged_batches(solver):
     """Ragged n_matches, a frame with too little score, a frame with a NaN feature, an all-outlier frame."""
     B = 5
