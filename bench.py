@@ -296,6 +296,42 @@ def main():
                   "valid": float((o_st == 0).float().mean().item()),
                   "note": "rs_kalman_track_points_device + rs_kalman_track_planes_device on the matched features of one %d-frame batch" % F}
 
+    # ---- informational: two batches in flight (a second context pair, steps dealt alternately, no cross-lane sync):
+    # the throughput-bound kernels of one batch (K1, Monte-Carlo LM) fill the SMs the latency-bound ones of the other
+    # (segmentation, RANSAC) leave idle. Not the headline: a step's latency doubles and K1 no longer runs alone. ----
+    pipelined = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        det2 = rs.PrimitiveDetection(W, H, CELL, max_batch=F, device=local_rank)
+        solver2 = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=119, max_variance=100, device=local_rank)
+        solver2.upload(cur, matches, n)
+        d_depth2 = d_depth.clone()
+        s2, p2 = torch.cuda.Stream(), torch.cuda.Stream()
+        lanes = [(det, solver, d_depth, stream, pose_stream), (det2, solver2, d_depth2, s2, p2)]
+
+        def lane_step(i):
+            dt, sv, dd, ms_, ps_ = lanes[i & 1]
+            dt.run_device(dd.data_ptr(), F, seed=0, stream=ms_.cuda_stream)
+            dt.stream_wait_fit(ps_.cuda_stream)
+            sv.solve_device(F, opts, stream=ps_.cuda_stream)
+            ms_.wait_stream(ps_)
+        for i in range(6):
+            lane_step(i)
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        s2.wait_stream(stream)
+        nsteps2 = steps + (steps & 1)
+        for i in range(nsteps2):
+            lane_step(i)
+        stream.wait_stream(s2)
+        q1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = q0.elapsed_time(q1)
+        pipelined = {"value": F * nsteps2 / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / nsteps2, "steps": nsteps2,
+                     "note": "two %d-frame batches in flight on two context / stream pairs, inputs resident" % F}
+        det2.close()
+        solver2.close()
+
     # sanity: the timed work produced valid poses close to the synthetic truth
     out, _ = solver.download(F)
     ok_frac = float((out["status"] == 1).mean())
@@ -428,6 +464,8 @@ def main():
             line["rectify_depth"] = rect
         if kalman is not None:
             line["kalman_update"] = kalman
+        if pipelined is not None:
+            line["two_batches_in_flight"] = pipelined
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
