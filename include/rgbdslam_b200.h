@@ -219,6 +219,9 @@ typedef struct rs_pose_out {
 
 typedef struct rs_pose_ctx rs_pose_ctx;
 
+/* Capacities of a solver context. max_matches: longest match list of one frame, 1..3175 (the RANSAC and Monte-Carlo kernels
+ * stage one frame's matches in the 227 KB of shared memory of an SM; up to 370 matches eight Monte-Carlo samples share a
+ * CTA, beyond that the launcher trades samples per CTA for room). NULL + rs_last_error() on invalid capacities. */
 rs_pose_ctx* rs_pose_create(int max_batch, int max_matches, int max_iterations, int max_variance, int device);
 void rs_pose_destroy(rs_pose_ctx* ctx);
 

@@ -266,8 +266,9 @@ extern "C" {
 
 rs_pose_ctx* rs_pose_create(int max_batch, int max_matches, int max_iterations, int max_variance, int device)
 {
-    if (max_batch <= 0 || max_matches <= 0 || max_matches > 32767) {
-        set_last_error("rs_pose_create: invalid capacities (max_matches must be in 1..32767)");
+    if (max_batch <= 0 || max_matches <= 0 || max_matches > pose_max_matches_supported()) {
+        set_last_error("rs_pose_create: invalid capacities (max_matches must be in 1.." + std::to_string(pose_max_matches_supported()) +
+                       ": one frame's match list is staged in shared memory)");
         return nullptr;
     }
     rs_pose_ctx* c = new rs_pose_ctx();

@@ -57,6 +57,7 @@ struct PoseLaunch {
     PoseIntrinsics K;
 };
 
+int pose_max_matches_supported();   // longest match list whose staging fits the shared memory of one SM
 int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
 int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
 int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);

@@ -26,6 +26,8 @@
 // FP64 throughout (forward differences with h = 1.49e-8 |x| on mm-scale coordinates need it).
 #include <float.h>
 
+#include <algorithm>
+
 #include "plane_fit.cuh"  // normalize3
 #include "pose_internal.cuh"
 
@@ -1481,7 +1483,8 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
 }
 
 // compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
-// grid (ceil(n_variance / WARPS), B), one warp per Monte-Carlo sample.
+// grid (ceil(n_variance / warps), B), one warp per Monte-Carlo sample; warps per CTA = blockDim.x / 32 (8 unless the
+// perturbed copies of a very long match list would not fit in shared memory, see launch_pose_variance).
 template <bool P2D>
 __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
@@ -1492,11 +1495,12 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
     const PoseFrameState st = buf.state[b];
     if (st.stage != 1) return;
     const int n = st.n;
-    // carve: obs[4][M] | pmap[WARPS][4][M] | WarpLM[WARPS] | type[M] | idx[M] | count
+    // carve: obs[4][M] | pmap[warps][4][M] | WarpLM[warps] | type[M] | idx[M] | count
+    const int nwarps = blockDim.x >> 5;
     double* s_obs = reinterpret_cast<double*>(smem_raw);
     double* s_pmap = s_obs + 4 * M;
-    WarpLM* s_lm = reinterpret_cast<WarpLM*>(s_pmap + size_t(WARPS) * 4 * M);
-    int32_t* s_type = reinterpret_cast<int32_t*>(s_lm + WARPS);
+    WarpLM* s_lm = reinterpret_cast<WarpLM*>(s_pmap + size_t(nwarps) * 4 * M);
+    int32_t* s_type = reinterpret_cast<int32_t*>(s_lm + nwarps);
     short* s_idx = reinterpret_cast<short*>(s_type + M);
     const int cnt = st.n_inliers;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
@@ -1506,7 +1510,7 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
         for (int c = 0; c < 4; ++c) s_obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
     }
     __syncthreads();
-    const int sample = blockIdx.x * WARPS + warp;
+    const int sample = blockIdx.x * nwarps + warp;
     if (sample >= prm.n_variance) return;
     double* pmap = s_pmap + size_t(warp) * 4 * M;
     const double* gmap = buf.map + size_t(b) * 4 * M;
@@ -1684,13 +1688,55 @@ __global__ void pose_export_normals_kernel(const PoseLaunch prm, const int M, do
     }
 }
 
-size_t variance_smem_bytes(const int M)
+size_t variance_smem_bytes(const int M, const int warps)
 {
-    return sizeof(double) * 4 * M + sizeof(double) * size_t(WARPS) * 4 * M + sizeof(WarpLM) * WARPS + sizeof(int32_t) * M +
+    return sizeof(double) * 4 * M + sizeof(double) * size_t(warps) * 4 * M + sizeof(WarpLM) * warps + sizeof(int32_t) * M +
            sizeof(short) * M + 16;
 }
 
+constexpr size_t kSmemPerCta = 232448;   // 227 KB opt-in limit of sm_100
+constexpr size_t kSmemPerSm = 233472;    // 228 KB, 1 KB reserved per resident CTA
+
+// Warps per CTA of the Monte-Carlo kernel for a match capacity M: the choice that keeps the most warps resident per SM
+// (8 warps, two CTAs per SM, up to M = 370; fewer, fatter samples per CTA beyond). 0 = even one warp does not fit.
+int variance_warps_for(const int M)
+{
+    int best = 0, best_resident = 0;
+    for (int w = WARPS; w >= 1; w >>= 1) {
+        const size_t smem = variance_smem_bytes(M, w);
+        if (smem > kSmemPerCta) continue;
+        const int ctas = int(std::min<size_t>(kSmemPerSm / (smem + 1024), size_t(64 / w)));
+        if (w * ctas > best_resident) best = w, best_resident = w * ctas;
+    }
+    return best;
+}
+
+// per-device "already raised the dynamic shared memory limit to" bookkeeping (function attributes are per context)
+struct SmemConfigured {
+    size_t v[64] = {};
+    size_t& here()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return v[dev & 63];
+    }
+};
+
 }  // namespace
+
+int pose_max_matches_supported()
+{
+    static int limit = 0;
+    if (limit == 0) {
+        int lo = 1, hi = 32767;   // both kernels stage one frame's match list in shared memory
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) / 2;
+            if (ransac_carve(nullptr, nullptr, mid) <= kSmemPerCta && variance_warps_for(mid) > 0) lo = mid; else hi = mid - 1;
+        }
+        limit = lo;
+    }
+    return limit;
+}
 
 int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
 {
@@ -1705,7 +1751,9 @@ int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStrea
 int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
 {
     const size_t smem = ransac_carve(nullptr, nullptr, buf.max_matches);
-    static size_t configured = 0;
+    if (smem > kSmemPerCta) return RS_ERR_INVALID_ARG;   // rs_pose_create refuses such capacities (pose_max_matches_supported)
+    static SmemConfigured cfg;
+    size_t& configured = cfg.here();
     if (smem > configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1722,18 +1770,21 @@ int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream
 int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
 {
     if (prm.n_variance <= 0) return RS_OK;
-    const size_t smem = variance_smem_bytes(buf.max_matches);
-    static size_t configured = 0;
+    const int warps = variance_warps_for(buf.max_matches);
+    if (warps == 0) return RS_ERR_INVALID_ARG;
+    const size_t smem = variance_smem_bytes(buf.max_matches, warps);
+    static SmemConfigured cfg;
+    size_t& configured = cfg.here();
     if (smem > configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
     }
-    const dim3 grid((prm.n_variance + WARPS - 1) / WARPS, prm.batch);
+    const dim3 grid((prm.n_variance + warps - 1) / warps, prm.batch);
     if (prm.has_point2d)
-        pose_variance_kernel<true><<<grid, THREADS, smem, stream>>>(buf, prm);
+        pose_variance_kernel<true><<<grid, warps * 32, smem, stream>>>(buf, prm);
     else
-        pose_variance_kernel<false><<<grid, THREADS, smem, stream>>>(buf, prm);
+        pose_variance_kernel<false><<<grid, warps * 32, smem, stream>>>(buf, prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }

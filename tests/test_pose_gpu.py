@@ -216,6 +216,27 @@ def test_invalid_arguments(solver):
         solver.solve_device(2, solver.options(rng_mode=rs.abi.RS_RNG_REFERENCE))
 
 
+@pytest.mark.parametrize("n_points,n_planes", [(700, 40), (1500, 100), (3000, 60)])
+def test_long_match_lists(n_points, n_planes):
+    """Match lists beyond the 370 that fit eight Monte-Carlo samples per CTA: the launcher trades warps per CTA for shared
+    memory (4, 2, 1 samples per CTA), results still equal the oracle; beyond what one SM can stage the constructor refuses."""
+    Mx = n_points + n_planes
+    truth, guess, m = rs.synth.pose_correspondences(4242, n_points=n_points, n_planes=n_planes)
+    s = rs.PoseOptimization(max_batch=2, max_matches=Mx, max_iterations=119, max_variance=100)
+    for rng_mode in (rs.abi.RS_RNG_REFERENCE, rs.abi.RS_RNG_DEVICE):
+        out, mask = s.compute_optimized_pose(np.stack([guess, guess]), np.stack([m, m]), opts=s.options(seed=3, rng_mode=rng_mode))
+        if rng_mode == rs.abi.RS_RNG_REFERENCE:
+            rout, rmask = ol.pose_solve(guess, m, seed=3)
+        else:
+            subsets, normals = s.export_random(2, 119, 100)
+            rout, rmask = ol.pose_solve(guess, m, subsets=subsets[0], normals=normals[0], max_matches=Mx)
+        assert_out_match(rout, out[0], rmask, mask[0], Mx)
+        assert rout["status"] == 1 and rout["n_variance_ok"] == 100
+    s.close()
+    with pytest.raises(rs.RsError):
+        rs.PoseOptimization(max_batch=1, max_matches=6000)
+
+
 def test_begin_end_split_matches_blocking_call(solver):
     truth, cur, matches, n = rs.synth.pose_batch(700, 4, M)
     opts = solver.options(seed=11, rng_mode=rs.abi.RS_RNG_DEVICE)
