@@ -64,7 +64,16 @@ __device__ __forceinline__ bool continuity_segment(const float* base, const int 
         const float z = base[i * stride];
         if (z > 0.f) {
             const float diff = fabsf(z - prev);
-            if (!(static_cast<double>(diff) <= 4.0 * depth_quantization(static_cast<double>(z)))) ok = false;
+            // jump <= 4 quant(z), decided in FP32 whenever the FP32 estimate of the bound is further from `diff` than its
+            // own error (a few 1e-7 relative, plus the cancellation against the -0.53 offset); the reference's FP64
+            // expression only runs for the rare jump that lands within 1e-5 of the bound
+            const float qf = fmaxf(0.5f, fmaf(2.73e-6f * z, z, fmaf(0.74e-3f, z, -0.53f)));
+            const float bound = 4.0f * qf, slack = fmaf(bound, 1e-5f, 1e-5f);
+            if (diff > bound + slack)
+                ok = false;
+            else if (diff >= bound - slack) {
+                if (!(static_cast<double>(diff) <= 4.0 * depth_quantization(static_cast<double>(z)))) ok = false;
+            }
             prev = z;
         }
     }
@@ -150,11 +159,17 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
     int cnt = 0;
     float p0x = 0.f, p0y = 0.f, p0z = 0.f, plx = 0.f, ply = 0.f, plz = 0.f;
 
+    // (item, box) of the box being consumed and of the box two ahead (the one the ring is refilled with); the item
+    // coordinates cost two integer divisions, so they are only recomputed when an item boundary is crossed
+    int k = 0, bq = 0, row0, c0, cr, b;
+    item_origin(0, row0, c0, cr, b);
+    int kn = 2 / NBOX, bqn = 2 % NBOX, nrow0 = row0, nc0 = c0;
+    if (kn != 0 && 2 < nbox) {
+        int ncr, nb;
+        item_origin(kn, nrow0, nc0, ncr, nb);
+    }
     for (int q = 0; q < nbox; ++q) {
         const int slot = q & 1;
-        const int k = q / NBOX, bq = q - k * NBOX;
-        int row0, c0, cr, b;
-        item_origin(k, row0, c0, cr, b);
         const double* kyrow = prm.ky + cr * CS;
         const float* tile = reinterpret_cast<const float*>(wbase + slot * Geo::BOX_BYTES);
         const float* ctile = tile + c * CS;            // this cell's columns inside a box row
@@ -260,13 +275,27 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         __syncwarp();
         // the box is consumed: refill the slot with box q + 2
         if (lane == 0 && q + 2 < nbox) {
-            const int qn = q + 2;
-            int nrow0, nc0, ncr, nb;
-            item_origin(qn / NBOX, nrow0, nc0, ncr, nb);
             mbar_arrive_expect_tx(&bars[slot], Geo::BOX_BYTES);
-            tma_load_3d_hint(wbase + slot * Geo::BOX_BYTES, &tmap, 0, nc0, nrow0 + (qn % NBOX) * R, &bars[slot], policy);
+            tma_load_3d_hint(wbase + slot * Geo::BOX_BYTES, &tmap, 0, nc0, nrow0 + bqn * R, &bars[slot], policy);
         }
-        if (bq != NBOX - 1) continue;
+        // advance the refill cursor (box q + 3 next time)
+        if (++bqn == NBOX) {
+            bqn = 0;
+            ++kn;
+            if (kn < nitems) {
+                int ncr, nb;
+                item_origin(kn, nrow0, nc0, ncr, nb);
+            }
+        }
+        const bool item_done = bq == NBOX - 1;
+        const int cur_c0 = c0, cur_cr = cr, cur_b = b;
+        // advance the consume cursor
+        if (++bq == NBOX) {
+            bq = 0;
+            ++k;
+            if (k < nitems) item_origin(k, row0, c0, cr, b);
+        }
+        if (!item_done) continue;
 
         // ---- item finished: reduce the 4 lanes of each cell (all four end up with the totals), continuity test ----
 #pragma unroll
@@ -305,8 +334,8 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         // ---- hand the cell over to the fit kernel: sums, count, continuity flag and the first / last cloud rows travel
         // in the cell's own record (the two points in the centroid / normal slots); the four lanes of a cell write two
         // 16-byte pieces each ----
-        if (c0 + c < prm.hc) {
-            double2* dst = reinterpret_cast<double2*>(cells + (size_t(b) * prm.vc + cr) * prm.hc + c0 + c);
+        if (cur_c0 + c < prm.hc) {
+            double2* dst = reinterpret_cast<double2*>(cells + (size_t(cur_b) * prm.vc + cur_cr) * prm.hc + cur_c0 + c);
             if (j == 0) {
                 double2 head;
                 head.x = __hiloint2double(okc, cnt);   // {int32 count, int32 planar := continuity / count test passed}
@@ -401,7 +430,8 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
     using Geo = Geometry<CS>;
     constexpr size_t smem = size_t(WARPS) * Geo::WARP_BYTES;
     auto kernel = cape_cell_fit_kernel<CS>;
-    static bool configured = false;
+    static PerDevice<bool> cfg;
+    bool& configured = cfg.here();
     if (!configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         RS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -988,7 +988,8 @@ int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cud
         set_last_error("cape_segment: at most 64 x 64 cells (one 64-bit word per cell row and merge direction)");
         return RS_ERR_INVALID_ARG;
     }
-    static size_t configured = 0;
+    static PerDevice<size_t> cfg;
+    size_t& configured = cfg.here();
     if (smem > configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(cape_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;

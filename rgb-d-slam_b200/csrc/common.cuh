@@ -31,6 +31,19 @@ extern std::atomic<uint64_t> g_launch_count;
         RS_CUDA_CHECK(cudaGetLastError());                                                               \
     } while (0)
 
+// Per-device bookkeeping for cudaFuncSetAttribute (function attributes belong to a device's context, so a process that
+// drives several GPUs has to raise the dynamic shared memory limit once per device).
+template <typename T>
+struct PerDevice {
+    T v[64] = {};
+    T& here()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return v[dev & 63];
+    }
+};
+
 // ---- constants of the reference (src/parameters.hpp) ---------------------------------------
 // depth quantisation model, parameters.hpp:16-18 / covariances.cpp:12-19
 __host__ __device__ inline double depth_quantization(const double depth)

@@ -1711,17 +1711,6 @@ int variance_warps_for(const int M)
     return best;
 }
 
-// per-device "already raised the dynamic shared memory limit to" bookkeeping (function attributes are per context)
-struct SmemConfigured {
-    size_t v[64] = {};
-    size_t& here()
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        return v[dev & 63];
-    }
-};
-
 }  // namespace
 
 int pose_max_matches_supported()
@@ -1752,7 +1741,7 @@ int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream
 {
     const size_t smem = ransac_carve(nullptr, nullptr, buf.max_matches);
     if (smem > kSmemPerCta) return RS_ERR_INVALID_ARG;   // rs_pose_create refuses such capacities (pose_max_matches_supported)
-    static SmemConfigured cfg;
+    static PerDevice<size_t> cfg;
     size_t& configured = cfg.here();
     if (smem > configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1773,7 +1762,7 @@ int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStre
     const int warps = variance_warps_for(buf.max_matches);
     if (warps == 0) return RS_ERR_INVALID_ARG;
     const size_t smem = variance_smem_bytes(buf.max_matches, warps);
-    static SmemConfigured cfg;
+    static PerDevice<size_t> cfg;
     size_t& configured = cfg.here();
     if (smem > configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
