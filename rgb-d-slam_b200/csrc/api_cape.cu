@@ -207,6 +207,10 @@ int create_impl(rs_cape_ctx* c)
     std::vector<double> kx, ky;
     backprojection_factors(c, kx, ky);
     const size_t B = size_t(c->max_batch), Nc = size_t(c->Nc);
+    // second half of each table: the factors times 2^896 (exact), for K1a's XU-free widening
+    const size_t nkx = kx.size(), nky = ky.size();
+    for (size_t i = 0; i < nkx; ++i) kx.push_back(std::ldexp(kx[i], 896));
+    for (size_t i = 0; i < nky; ++i) ky.push_back(std::ldexp(ky[i], 896));
     if ((rc = dev_alloc(&c->d_kx, kx.size()))) return rc;
     if ((rc = dev_alloc(&c->d_ky, ky.size()))) return rc;
     RS_CUDA_CHECK(cudaMemcpy(c->d_kx, kx.data(), sizeof(double) * kx.size(), cudaMemcpyHostToDevice));
@@ -236,6 +240,7 @@ int create_impl(rs_cape_ctx* c)
     const unsigned P = unsigned(c->cell) * unsigned(c->cell);
     c->fit.H = c->H, c->fit.hc = c->hc, c->fit.vc = c->vc, c->fit.cell = c->cell;
     c->fit.kx = c->d_kx, c->fit.ky = c->d_ky;
+    c->fit.kxs = c->d_kx + nkx, c->fit.kys = c->d_ky + nky;
     c->fit.min_zero_point_count = int(static_cast<unsigned>(std::floor(static_cast<float>(P) * 0.7f)));
     c->fit.sin_merge = sinf(static_cast<float>(18.0f * M_PI / 180.0));
     c->fit.merge_distance = 50.0f;

@@ -40,9 +40,14 @@ constexpr int WARPS = 4;
 #ifndef RS_K1_MIN_CTAS
 #define RS_K1_MIN_CTAS 4
 #endif
-#ifndef RS_K1_FP64_PRODUCTS
-#define RS_K1_FP64_PRODUCTS 3   // how many of the six FP32 products are formed and rounded in the FP64 pipe
+#ifndef RS_K1_UNROLL
+#define RS_K1_UNROLL 5          // trips of the per-box float4 loop unrolled
 #endif
+#ifndef RS_K1_FP64_PRODUCTS
+#define RS_K1_FP64_PRODUCTS 8   // 8: integer widening folded into DFMA (default); 3: Veltkamp rounding in the FP64 pipe (round-1 original)
+#endif
+
+constexpr int kUnroll = RS_K1_UNROLL;
 
 // Indices e_i = base[i * stride], i in [0, n). Reference (plane_segment.cpp:44-100): last = max(e_0, e_1); fail if
 // last <= 0; for i = 1..n-1 a positive e_i must satisfy |e_i - last| <= 4 quant(e_i) and then becomes `last`.
@@ -86,6 +91,18 @@ __device__ __forceinline__ double round_to_float(const double v)
 {
     const double p = v * 536870913.0;
     return p - (p - v);
+}
+
+// f * 2^-896 for a float f >= 0 (zero and subnormals included): the bits of f times 2^29, read as a double.
+__device__ __forceinline__ double widen_scaled(const float f)
+{
+    return __longlong_as_double(static_cast<long long>(static_cast<unsigned long long>(__float_as_uint(f)) * 0x20000000ull));
+}
+constexpr double kTwo896 = 0x1p896;
+// d >= 0 with the sign bit of the 32-bit pattern b
+__device__ __forceinline__ double with_sign_of(const double d, const unsigned b)
+{
+    return __hiloint2double(__double2hiint(d) | static_cast<int>(b & 0x80000000u), __double2loint(d));
 }
 
 template <int CS>
@@ -154,6 +171,13 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
     __syncwarp();
 
     const int c = lane >> 2, j = lane & 3;             // cell inside the item, lane inside the cell
+#if RS_K1_FP64_PRODUCTS == 8
+    const double* const kxtab = prm.kxs;               // factors pre-scaled by 2^896 (see the pixel loop)
+    const double* const kytab = prm.kys;
+#else
+    const double* const kxtab = prm.kx;
+    const double* const kytab = prm.ky;
+#endif
 
     double S0 = 0, S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0, S6 = 0, S7 = 0, S8 = 0;
     int cnt = 0;
@@ -182,25 +206,55 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
             g -= G;
             ++r;
         }
-#pragma unroll 1
+#pragma unroll kUnroll
         for (int it = 0; it < Geo::ITERS; ++it) {
             {
                 const float4 v = *reinterpret_cast<const float4*>(ctile + r * Geo::ROW_FLOATS + g * 4);
-                const double2 kxa = __ldg(reinterpret_cast<const double2*>(prm.kx + colbase + g * 4));
-                const double2 kxb = __ldg(reinterpret_cast<const double2*>(prm.kx + colbase + g * 4 + 2));
-                const double kyv = __ldg(kyrow + bq * R + r);
+                const double2 kxa = __ldg(reinterpret_cast<const double2*>(kxtab + colbase + g * 4));
+                const double2 kxb = __ldg(reinterpret_cast<const double2*>(kxtab + colbase + g * 4 + 2));
+                const double kyv = __ldg(kytab + cr * CS + bq * R + r);
                 const float zz[4] = {v.x, v.y, v.z, v.w};
+#if RS_K1_FP64_PRODUCTS == 8
+                const double cy = __hiloint2double((__double2hiint(kyv) & 0x80000000) | 0x77f00000, 0);   // copysign(2^896, ky)
+#endif
                 const double kxr[4] = {kxa.x, kxa.y, kxb.x, kxb.y};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const bool valid = zz[t] > 0.f;
-                    const float z = valid ? zz[t] : 0.f;
-                    cnt += valid ? 1 : 0;
+                    // z = zz > 0 ? zz : 0, cnt += zz > 0: one FSETP, one FSEL and one predicated add (the compiler's own
+                    // rendering of the count is an add plus a predicated move)
+                    float z;
+                    asm("{\n.reg .pred p;\nsetp.gt.f32 p, %2, 0f00000000;\nselp.f32 %1, %2, 0f00000000, p;\n@p add.s32 %0, %0, 1;\n}"
+                        : "+r"(cnt), "=f"(z)
+                        : "f"(zz[t]));
                     // The reference's values are float(z kx), float(z ky) and FP32 products widened to FP64. On sm_100 the
                     // FP32<->FP64 conversions run at a quarter of the FP64 rate (tools/microbench.cu) and eleven of them per
                     // pixel bounded this loop, so the rounding to 24 bits is done in FP64 where that is cheaper: Veltkamp's
                     // split with 2^29 + 1 returns exactly RN_24(v), ties to even included (tests/test_oracle_cape.py), and
                     // the product of two 24-bit values is exact in FP64 before it is rounded.
+#if RS_K1_FP64_PRODUCTS == 8
+                    // Exact widening without the XU pipe: for a float f >= 0 with bits b, the 64-bit integer b * 2^29 read as
+                    // a double is f * 2^-896 (exponent field not rebiased; zero and subnormals included), one IMAD.WIDE.
+                    // The 2^896 is folded, exactly, into the multiplier of the operation that consumes it: the
+                    // back-projection factors are stored pre-scaled (kxs = kx 2^896) and the sums use S = fma(D, 2^896, S),
+                    // bit-identical to S += (double)f. Signed products are formed from |x|, |y|: the sign of x is OR-ed
+                    // into D, the sign of y (that of ky: one value per box row) rides on the multiplier cy = +-2^896. Only x and y cross the XU pipe (RN24 of the FP64 back-projection, and back).
+                    const double Dz = widen_scaled(z);
+                    const float x = static_cast<float>(Dz * kxr[t]);
+                    const float y = static_cast<float>(Dz * kyv);
+                    S0 += static_cast<double>(x);
+                    S1 += static_cast<double>(y);
+                    S2 = fma(Dz, kTwo896, S2);
+                    const float ax = fabsf(x), ay = fabsf(y);
+                    const unsigned bx = __float_as_uint(x);
+                    S3 = fma(widen_scaled(__fmul_rn(ax, ax)), kTwo896, S3);
+                    S4 = fma(widen_scaled(__fmul_rn(ay, ay)), kTwo896, S4);
+                    S5 = fma(widen_scaled(__fmul_rn(z, z)), kTwo896, S5);
+                    S6 = fma(with_sign_of(widen_scaled(__fmul_rn(ax, ay)), bx), cy, S6);
+                    S7 = fma(widen_scaled(__fmul_rn(ay, z)), cy, S7);
+                    S8 = fma(with_sign_of(widen_scaled(__fmul_rn(ax, z)), bx), kTwo896, S8);
+#else
+                    // round-1 original: x, y and three of the six products are rounded to 24 bits inside the FP64 pipe
+                    // (Veltkamp split, bit-identical to the conversion), the other three go through FMUL + F2F
                     const double zd = static_cast<double>(z);
                     const double xd = round_to_float(zd * kxr[t]);
                     const double yd = round_to_float(zd * kyv);
@@ -209,34 +263,12 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
                     S0 += xd;
                     S1 += yd;
                     S2 += zd;
-#if RS_K1_FP64_PRODUCTS == 0
-                    S3 += static_cast<double>(x * x);
-                    S4 += static_cast<double>(y * y);
-                    S5 += static_cast<double>(z * z);
-                    S6 += static_cast<double>(x * y);
-                    S7 += static_cast<double>(y * z);
-                    S8 += static_cast<double>(x * z);
-#elif RS_K1_FP64_PRODUCTS == 2
-                    S3 += round_to_float(xd * xd);
-                    S4 += round_to_float(yd * yd);
-                    S5 += static_cast<double>(z * z);
-                    S6 += static_cast<double>(x * y);
-                    S7 += static_cast<double>(y * z);
-                    S8 += static_cast<double>(x * z);
-#elif RS_K1_FP64_PRODUCTS == 3
                     S3 += round_to_float(xd * xd);
                     S4 += round_to_float(yd * yd);
                     S5 += static_cast<double>(z * z);
                     S6 += round_to_float(xd * yd);
                     S7 += static_cast<double>(y * z);
                     S8 += static_cast<double>(x * z);
-#else
-                    S3 += round_to_float(xd * xd);
-                    S4 += round_to_float(yd * yd);
-                    S5 += round_to_float(zd * zd);
-                    S6 += round_to_float(xd * yd);
-                    S7 += round_to_float(yd * zd);
-                    S8 += round_to_float(xd * zd);
 #endif
                 }
             }

@@ -11,6 +11,8 @@ struct CellFitParams {
     int H, hc, vc, batch, cell;
     const double* kx;  // [W]  back-projection factor per image column (device)
     const double* ky;  // [H]  per image row
+    const double* kxs; // [W]  kx * 2^896 (exact scaling; K1a widens floats without the 2^896, see cape_cell_fit.cu)
+    const double* kys; // [H]
     int min_zero_point_count;   // floor(P * 0.7f), plane_segment.hpp:33-34
     float sin_merge;            // sinf(float(18 deg)), primitive_detection.cpp:189-190
     float merge_distance;       // 50 mm
