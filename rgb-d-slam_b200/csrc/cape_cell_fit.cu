@@ -10,14 +10,19 @@
 // {cs px, 8 cells, R rows} (R*cs*8*4 = 2560 B) lands as [row][cell][px] in a 2-slot per-warp ring guarded by
 // mbarriers; lane (c = lane/4, j = lane%4) reads the float4 j, j+4, j+8, ... of cell c's part of the box (LDS.128, at
 // most 2-way bank conflicts; exactly 5 trips per box), back-projects in FP64 and accumulates the nine sums of FP32
-// values / FP32 products in FP64. The rounding to float that the reference's cloud and products carry is done where it
-// is cheapest on sm_100: FP32<->FP64 conversions issue at a quarter of the FP64 rate (tools/microbench.cu; eleven per
-// pixel kept the XU pipe 70 % busy), so x, y and three of the six products are rounded to 24 bits inside the FP64 pipe
-// with Veltkamp's split (round_to_float, bit-identical to the conversion, tests/test_oracle_cape.py) and the rest go
-// through FMUL + F2F; the two pipes end up balanced. The pixel loop is branch-free: an invalid pixel (z <= 0)
-// contributes exact zeros, as its (0,0,0) cloud row does. Per item the sums are reduced over the 4 lanes of a cell with
-// two shuffle steps (all four lanes end up with the totals and each writes a quarter of the record); the cross-shaped
-// continuity test runs from small per-warp copies of the middle row / middle column, split over the 4 lanes of the cell.
+// values / FP32 products in FP64, value for value what the reference's cloud + init_plane_segment compute. What bounds
+// the loop on sm_100 is instruction issue (tools/microbench2.cu: an FP64 instruction holds the issue port ~2.2 cycles,
+// F2F runs at a quarter of that rate on the XU pipe, everything else ~1 cycle), so the arithmetic is arranged for the
+// fewest instructions per pixel: a float f >= 0 is widened without a conversion - its bit pattern shifted by 29 is the
+// double f 2^-896 - and the 2^896 is folded, exactly, into the multiplier of the DFMA that consumes it (sums) or into
+// pre-scaled back-projection factors (kxs, kys); products are FMUL on |x|, |y|, z with the sign restored on the widened
+// operand (x) or on the multiplier (y: one sign per box row). Only x and y themselves cross the XU pipe (RN24 of the
+// FP64 back-projection and back). 35 instructions per pixel, 11 of them FP64 (the first version of this kernel:
+// 49 / 29, Veltkamp rounding inside the FP64 pipe, kept under RS_K1_FP64_PRODUCTS == 3). The pixel loop is branch-free:
+// an invalid pixel (z <= 0) contributes exact zeros, as its (0,0,0) cloud row does. Per item the sums are reduced over
+// the 4 lanes of a cell with two shuffle steps (all four lanes end up with the totals and each writes a quarter of the
+// record); the cross-shaped continuity test runs from small per-warp copies of the middle row / middle column, split
+// over the 4 lanes of the cell.
 // K1b `cape_cell_finish_kernel` then fits every cell (3x3 eigen-solve, planarity, merge tolerance), one thread per cell,
 // in place on the 160-byte record: inside the streaming kernel that serial chain cost 30 % of the time.
 //
@@ -42,6 +47,12 @@ constexpr int WARPS = 4;
 #endif
 #ifndef RS_K1_UNROLL
 #define RS_K1_UNROLL 5          // trips of the per-box float4 loop unrolled
+#endif
+#ifndef RS_K1B_MIN_CTAS
+#define RS_K1B_MIN_CTAS 6       // K1b: 80 registers, 24 warps / SM (measured best of 4 / 6 / 8)
+#endif
+#ifndef RS_K1_F2F_PRODUCTS
+#define RS_K1_F2F_PRODUCTS 0    // how many of the signed products (xz, xy, yz) are widened by F2F instead of the integer route
 #endif
 #ifndef RS_K1_FP64_PRODUCTS
 #define RS_K1_FP64_PRODUCTS 8   // 8: integer widening folded into DFMA (default); 3: Veltkamp rounding in the FP64 pipe (round-1 original)
@@ -96,7 +107,9 @@ __device__ __forceinline__ double round_to_float(const double v)
 // f * 2^-896 for a float f >= 0 (zero and subnormals included): the bits of f times 2^29, read as a double.
 __device__ __forceinline__ double widen_scaled(const float f)
 {
-    return __longlong_as_double(static_cast<long long>(static_cast<unsigned long long>(__float_as_uint(f)) * 0x20000000ull));
+    // two shifts; the single-instruction form (IMAD.WIDE.U32 by 2^29) measured 5 % slower over the whole kernel (dispatch stalls)
+    const unsigned b = __float_as_uint(f);
+    return __hiloint2double(static_cast<int>(b >> 3), static_cast<int>(b << 29));
 }
 constexpr double kTwo896 = 0x1p896;
 // d >= 0 with the sign bit of the 32-bit pattern b
@@ -237,7 +250,8 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
                     // The 2^896 is folded, exactly, into the multiplier of the operation that consumes it: the
                     // back-projection factors are stored pre-scaled (kxs = kx 2^896) and the sums use S = fma(D, 2^896, S),
                     // bit-identical to S += (double)f. Signed products are formed from |x|, |y|: the sign of x is OR-ed
-                    // into D, the sign of y (that of ky: one value per box row) rides on the multiplier cy = +-2^896. Only x and y cross the XU pipe (RN24 of the FP64 back-projection, and back).
+                    // into D, the sign of y (that of ky: one value per box row) rides on the multiplier cy = +-2^896.
+                    // Only x and y cross the XU pipe (RN24 of the FP64 back-projection, and back).
                     const double Dz = widen_scaled(z);
                     const float x = static_cast<float>(Dz * kxr[t]);
                     const float y = static_cast<float>(Dz * kyv);
@@ -249,9 +263,21 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
                     S3 = fma(widen_scaled(__fmul_rn(ax, ax)), kTwo896, S3);
                     S4 = fma(widen_scaled(__fmul_rn(ay, ay)), kTwo896, S4);
                     S5 = fma(widen_scaled(__fmul_rn(z, z)), kTwo896, S5);
+#if RS_K1_F2F_PRODUCTS >= 2
+                    S6 += static_cast<double>(__fmul_rn(x, y));
+#else
                     S6 = fma(with_sign_of(widen_scaled(__fmul_rn(ax, ay)), bx), cy, S6);
+#endif
+#if RS_K1_F2F_PRODUCTS >= 3
+                    S7 += static_cast<double>(__fmul_rn(y, z));
+#else
                     S7 = fma(widen_scaled(__fmul_rn(ay, z)), cy, S7);
+#endif
+#if RS_K1_F2F_PRODUCTS >= 1
+                    S8 += static_cast<double>(__fmul_rn(x, z));
+#else
                     S8 = fma(with_sign_of(widen_scaled(__fmul_rn(ax, z)), bx), kTwo896, S8);
+#endif
 #else
                     // round-1 original: x, y and three of the six products are rounded to 24 bits inside the FP64 pipe
                     // (Veltkamp split, bit-identical to the conversion), the other three go through FMUL + F2F
@@ -399,7 +425,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
 // The 3x3 eigen-solve is a serial chain of FP64 divisions and square roots with a data-dependent trip count; inside the
 // streaming kernel it ran on warps that were holding TMA buffers and cost 30 % of K1's time for 4 % of its instructions.
 // Here every cell of the batch is in flight at once and the records (31 MB per 256 frames) are still in L2.
-__global__ void __launch_bounds__(128) cape_cell_finish_kernel(const CellFitParams prm, rs_cell_out* __restrict__ cells, const int total)
+__global__ void __launch_bounds__(128, RS_K1B_MIN_CTAS) cape_cell_finish_kernel(const CellFitParams prm, rs_cell_out* __restrict__ cells, const int total)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;

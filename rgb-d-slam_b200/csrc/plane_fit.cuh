@@ -100,14 +100,16 @@ __device__ inline void self_adjoint_eigen3(const double a00, const double a10, c
     const double m00 = a00 / scale, m10 = a10 / scale, m11 = a11 / scale, m20 = a20 / scale, m21 = a21 / scale,
                  m22 = a22 / scale;
 
-    double diag[3], subdiag[2];
-    diag[0] = m00;
+    // The tridiagonal QL below is Eigen's loop (SelfAdjointEigenSolver.h: computeFromTridiagonal_impl +
+    // tridiagonal_qr_step) written out for n = 3 with every index a compile-time constant: diag / subdiag / q stay in
+    // registers (the dynamically indexed version lived in local memory), the operations and their order are unchanged.
+    double d0 = m00, d1, d2, e0, e1;
     const double v1norm2 = m20 * m20;
     if (v1norm2 <= DBL_MIN) {
-        diag[1] = m11;
-        diag[2] = m22;
-        subdiag[0] = m10;
-        subdiag[1] = m21;
+        d1 = m11;
+        d2 = m22;
+        e0 = m10;
+        e1 = m21;
         q[0][0] = 1, q[0][1] = 0, q[0][2] = 0;
         q[1][0] = 0, q[1][1] = 1, q[1][2] = 0;
         q[2][0] = 0, q[2][1] = 0, q[2][2] = 1;
@@ -118,10 +120,10 @@ __device__ inline void self_adjoint_eigen3(const double a00, const double a10, c
         const double m01 = m10 * invBeta;
         const double m02 = m20 * invBeta;
         const double qq = 2.0 * m01 * m21 + m02 * (m22 - m11);
-        diag[1] = m11 + m02 * qq;
-        diag[2] = m22 - m02 * qq;
-        subdiag[0] = beta;
-        subdiag[1] = m21 - m01 * qq;
+        d1 = m11 + m02 * qq;
+        d2 = m22 - m02 * qq;
+        e0 = beta;
+        e1 = m21 - m01 * qq;
         q[0][0] = 1, q[0][1] = 0, q[0][2] = 0;
         q[1][0] = 0, q[1][1] = m01, q[1][2] = m02;
         q[2][0] = 0, q[2][1] = m02, q[2][2] = -m01;
@@ -131,26 +133,52 @@ __device__ inline void self_adjoint_eigen3(const double a00, const double a10, c
     const int maxIterations = 30;
     int end = n - 1, start = 0, iter = 0;
     const double precision_inv = 1.0 / DBL_EPSILON;
+// subdiag[i] -> 0 when negligible against its diagonal neighbours
+#define RS_DEFLATE(E, DA, DB)                                                         \
+    {                                                                                 \
+        if (fabs(E) < DBL_MIN) {                                                      \
+            E = 0.0;                                                                  \
+        }                                                                             \
+        else {                                                                        \
+            const double scaled_subdiag = precision_inv * E;                          \
+            if (scaled_subdiag * scaled_subdiag <= (fabs(DA) + fabs(DB))) E = 0.0;    \
+        }                                                                             \
+    }
+// one Givens step of the implicit QR sweep on rows / columns K, K+1 (DK = diag[K], DK1 = diag[K+1], EK = subdiag[K])
+#define RS_GIVENS_STEP(K, DK, DK1, EK, PREV_STMT, NEXT_STMT)                          \
+    {                                                                                 \
+        double c, s;                                                                  \
+        make_givens(x, z, c, s);                                                      \
+        const double sdk = s * DK + c * EK;                                           \
+        const double dkp1 = s * EK + c * DK1;                                         \
+        DK = c * (c * DK - s * EK) - s * (c * EK - s * DK1);                          \
+        DK1 = s * sdk + c * dkp1;                                                     \
+        EK = c * sdk - s * dkp1;                                                      \
+        PREV_STMT;                                                                    \
+        x = EK;                                                                       \
+        NEXT_STMT;                                                                    \
+        _Pragma("unroll") for (int i = 0; i < 3; ++i)                                 \
+        {                                                                             \
+            const double xi = q[i][K], yi = q[i][K + 1];                              \
+            q[i][K] = c * xi - s * yi;                                                \
+            q[i][K + 1] = s * xi + c * yi;                                            \
+        }                                                                             \
+    }
     while (end > 0) {
-        for (int i = start; i < end; ++i) {
-            if (fabs(subdiag[i]) < DBL_MIN) {
-                subdiag[i] = 0.0;
-            }
-            else {
-                const double scaled_subdiag = precision_inv * subdiag[i];
-                if (scaled_subdiag * scaled_subdiag <= (fabs(diag[i]) + fabs(diag[i + 1]))) subdiag[i] = 0.0;
-            }
-        }
-        while (end > 0 && subdiag[end - 1] == 0.0) end--;
+        if (start <= 0 && 0 < end) RS_DEFLATE(e0, d0, d1)
+        if (start <= 1 && 1 < end) RS_DEFLATE(e1, d1, d2)
+        if (end == 2 && e1 == 0.0) end = 1;
+        if (end == 1 && e0 == 0.0) end = 0;
         if (end <= 0) break;
         iter++;
         if (iter > maxIterations * n) break;
         start = end - 1;
-        while (start > 0 && subdiag[start - 1] != 0.0) start--;
+        if (start == 1 && e0 != 0.0) start = 0;
 
-        const double td = (diag[end - 1] - diag[end]) * 0.5;
-        const double e = subdiag[end - 1];
-        double mu = diag[end];
+        const double dem1 = end == 2 ? d1 : d0, de = end == 2 ? d2 : d1;
+        const double td = (dem1 - de) * 0.5;
+        const double e = end == 2 ? e1 : e0;
+        double mu = de;
         if (td == 0.0) {
             mu -= fabs(e);
         }
@@ -162,51 +190,58 @@ __device__ inline void self_adjoint_eigen3(const double a00, const double a10, c
             else
                 mu -= e2 / (td + (td > 0.0 ? h : -h));
         }
-        double x = diag[start] - mu;
-        double z = subdiag[start];
-        for (int k = start; k < end && z != 0.0; ++k) {
-            double c, s;
-            make_givens(x, z, c, s);
-            const double sdk = s * diag[k] + c * subdiag[k];
-            const double dkp1 = s * subdiag[k] + c * diag[k + 1];
-            diag[k] = c * (c * diag[k] - s * subdiag[k]) - s * (c * subdiag[k] - s * diag[k + 1]);
-            diag[k + 1] = s * sdk + c * dkp1;
-            subdiag[k] = c * sdk - s * dkp1;
-            if (k > start) subdiag[k - 1] = c * subdiag[k - 1] - s * z;
-            x = subdiag[k];
-            if (k < end - 1) {
-                z = -s * subdiag[k + 1];
-                subdiag[k + 1] = c * subdiag[k + 1];
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double xi = q[i][k], yi = q[i][k + 1];
-                q[i][k] = c * xi - s * yi;
-                q[i][k + 1] = s * xi + c * yi;
-            }
+        double x = (start == 0 ? d0 : d1) - mu;
+        double z = start == 0 ? e0 : e1;
+        if (start == 0) {
+            // k = 0 (k > start: no; k < end - 1 iff end == 2), then k = 1 when end == 2 and the bulge is still there
+            if (z != 0.0) RS_GIVENS_STEP(0, d0, d1, e0, (void)0, if (end == 2) { z = -s * e1; e1 = c * e1; })
+            if (end == 2 && z != 0.0) RS_GIVENS_STEP(1, d1, d2, e1, e0 = c * e0 - s * z, (void)0)
+        }
+        else if (z != 0.0) {
+            // start == 1, end == 2: the single step k = 1
+            RS_GIVENS_STEP(1, d1, d2, e1, (void)0, (void)0)
         }
     }
+#undef RS_DEFLATE
+#undef RS_GIVENS_STEP
     if (iter <= maxIterations * n) {
-        for (int i = 0; i < n - 1; ++i) {
-            int k = 0;
-            double mn = diag[i];
-            for (int j = 1; j < n - i; ++j)
-                if (diag[i + j] < mn) {
-                    mn = diag[i + j];
-                    k = j;
-                }
-            if (k > 0) {
-                const double t = diag[i];
-                diag[i] = diag[k + i];
-                diag[k + i] = t;
-                for (int r = 0; r < 3; ++r) {
-                    const double u = q[r][i];
-                    q[r][i] = q[r][k + i];
-                    q[r][k + i] = u;
-                }
+        // ascending selection sort (Eigen: for i, k = argmin of the tail, strict <), eigenvector columns follow
+        int k = 0;
+        double mn = d0;
+        if (d1 < mn) {
+            mn = d1;
+            k = 1;
+        }
+        if (d2 < mn) k = 2;
+        if (k == 1) {
+            const double t = d0;
+            d0 = d1, d1 = t;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double u = q[r][0];
+                q[r][0] = q[r][1], q[r][1] = u;
+            }
+        }
+        else if (k == 2) {
+            const double t = d0;
+            d0 = d2, d2 = t;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double u = q[r][0];
+                q[r][0] = q[r][2], q[r][2] = u;
+            }
+        }
+        if (d2 < d1) {
+            const double t = d1;
+            d1 = d2, d2 = t;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double u = q[r][1];
+                q[r][1] = q[r][2], q[r][2] = u;
             }
         }
     }
+    const double diag[3] = {d0, d1, d2};
     ev[0] = diag[0] * scale;
     ev[1] = diag[1] * scale;
     ev[2] = diag[2] * scale;

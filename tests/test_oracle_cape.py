@@ -211,3 +211,30 @@ def test_veltkamp_split_is_the_float_rounding_k1_needs():
     b = (z * ((rng.integers(0, 480, z.size) - 240.0) / 550.0)).astype(np.float32)
     exact = a.astype(np.float64) * b.astype(np.float64)        # exact: 24-bit x 24-bit fits the 53-bit significand
     assert np.array_equal(veltkamp(exact), (a * b).astype(np.float64))
+
+
+def test_shifted_float_bits_are_the_scaled_double_k1_accumulates():
+    """K1 widens a float f >= 0 without a conversion (cape_cell_fit.cu, widen_scaled): the 64-bit pattern
+    (bits(f) >> 3, bits(f) << 29) read as a double is exactly f * 2^-896 - zero and subnormal floats included - so
+    fma(D, 2^896, S) equals S + double(f), and D * (k * 2^896) equals double(f) * k, bit for bit."""
+    rng = np.random.default_rng(1)
+    f = np.concatenate([
+        rng.uniform(0, 1e4, 100000).astype(np.float32),
+        np.exp2(rng.uniform(-149, 127, 100000)).astype(np.float32),            # the whole exponent range
+        np.array([0.0, np.float32(1e-45), np.float32(1.1754942e-38), np.float32(1.17549435e-38), np.finfo(np.float32).max],
+                 np.float32)])
+    b = f.view(np.uint32).astype(np.uint64)
+    hi = b >> np.uint64(3)
+    lo = (b << np.uint64(29)) & np.uint64(0xFFFFFFFF)
+    D = ((hi << np.uint64(32)) | lo).view(np.float64)
+    assert np.array_equal(D * np.float64(2.0 ** 896), f.astype(np.float64))
+    assert np.all(np.isfinite(D)) and np.all(D >= 0)
+    # pre-scaled back-projection factor: same product, same rounding
+    k = (rng.integers(0, 640, f.size) - 319.5) / 550.0
+    with np.errstate(over="ignore"):
+        assert np.array_equal(D * np.ldexp(k, 896), f.astype(np.float64) * k)
+    # the sign of a product restored on the widened operand or on the multiplier
+    s = rng.choice([-1.0, 1.0], f.size)
+    Dneg = (D.view(np.uint64) | np.where(s < 0, np.uint64(1) << np.uint64(63), np.uint64(0))).view(np.float64)
+    assert np.array_equal(Dneg * np.float64(2.0 ** 896), s * f.astype(np.float64))
+    assert np.array_equal(D * (s * np.float64(2.0 ** 896)), s * f.astype(np.float64))
