@@ -5,7 +5,11 @@ rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[2:] if len(r) == len(hdr) and r[ix["Instructions Executed"]].isdigit()]
+body, seen = [], set()
+for r in rows[2:]:
+    if len(r) == len(hdr) and r[ix["Instructions Executed"]].isdigit() and r[ix["Address"]] not in seen:
+        seen.add(r[ix["Address"]])     # a report with several results of one kernel lists its SASS once per result
+        body.append(r)
 tot = sum(int(r[ix["Instructions Executed"]]) for r in body)
 samples = sum(int(r[ix["# Samples"]]) for r in body)
 print("instructions executed: %d, samples: %d, SASS lines: %d" % (tot, samples, len(body)))
