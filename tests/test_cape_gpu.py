@@ -221,3 +221,33 @@ def test_rectify_depth_against_committed_golden(det):
         assert hashlib.sha256(det.rectify_depth(depth).tobytes()).hexdigest() == meta["offset"]["sha256"]
     finally:
         det.set_rectification(None, enable=False)
+
+
+def test_two_contexts_on_two_host_threads_match_serial_runs():
+    """Two batches in flight (bench.py's e2e two_lanes mode): the blocking host API called from two host threads, each on
+    its own context, returns what the same calls return one after the other."""
+    import threading
+    a = rs.PrimitiveDetection(640, 480, 20, max_batch=8)
+    b = rs.PrimitiveDetection(640, 480, 20, max_batch=8)
+    da, db = rs.synth.scene_v0_batch(0, 8), rs.synth.scene_v0_batch(8, 8)
+    want = [a.find_primitives(da, seed=3), b.find_primitives(db, seed=4)]
+    got = [None, None]
+    gate = threading.Barrier(2)
+
+    def work(i, det_, d, seed):
+        gate.wait()
+        for _ in range(4):
+            got[i] = det_.find_primitives(d, seed=seed)
+
+    th = [threading.Thread(target=work, args=(0, a, da, 3)), threading.Thread(target=work, args=(1, b, db, 4))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for w, g in zip(want, got):
+        for k in ("plane_labels", "cyl_labels", "plane_grid", "cyl_region_seg"):
+            assert np.array_equal(w[k], g[k]), k
+        assert w["cells"].tobytes() == g["cells"].tobytes()
+        assert w["info"].tobytes() == g["info"].tobytes()
+    a.close()
+    b.close()
