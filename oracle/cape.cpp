@@ -722,6 +722,13 @@ std::vector<unsigned char> morph(const std::vector<unsigned char>& m, int rows, 
 
 }  // namespace
 
+// test hook: the morphology restatement above, checked against the real cv2.erode / cv2.dilate in tests/test_oracle_cape.py
+std::vector<unsigned char> cape_morphology(const std::vector<unsigned char>& m, int rows, int cols, bool erode, bool cross,
+                                           bool borderZero)
+{
+    return morph(m, rows, cols, erode, cross, borderZero);
+}
+
 // primitive_detection.cpp:119-166
 void cape_run(const CapeConfig& cfg, const float* depth, const uint32_t seed, CapeFrame& out)
 {

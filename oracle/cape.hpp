@@ -65,4 +65,11 @@ void cell_record(const PlaneSeg& s, float tol, int cellSize, rs_cell_out& o);
 // ((T0 x + T1 y) + T2 z) + T3; it can only matter when a projected coordinate lies within an ulp of a pixel boundary.
 void rectify_depth(const CapeConfig& cfg, const double cam2_to_cam1[16], const float* depth, float* out);
 
+// The restatement of cv::erode / cv::dilate (3x3 square or cross kernel, anchor at the centre, one iteration) that the
+// boundary and cylinder-opening steps use (primitive_detection.cpp:48-54,596-598,678-680,719-721). borderZero = the
+// reference's explicit BORDER_CONSTANT / Scalar(0) erode; otherwise OpenCV's default morphology border. Pinned against
+// the real OpenCV (cv2 wheel) in tests/test_oracle_cape.py.
+std::vector<unsigned char> cape_morphology(const std::vector<unsigned char>& m, int rows, int cols, bool erode, bool cross,
+                                           bool borderZero);
+
 }  // namespace oracle

@@ -111,6 +111,13 @@ int orc_cape_cell_fit(int W, int H, int cell, double fx, double fy, double cx, d
     return 0;
 }
 
+void orc_morphology(const unsigned char* mask, int rows, int cols, int erode, int cross, int border_zero, unsigned char* out)
+{
+    const std::vector<unsigned char> m(mask, mask + size_t(rows) * cols);
+    const std::vector<unsigned char> r = cape_morphology(m, rows, cols, erode != 0, cross != 0, border_zero != 0);
+    std::copy(r.begin(), r.end(), out);
+}
+
 void orc_eigen3(const double a[9], double evals[3], double evecs[9])
 {
     Mat3 m, v;

@@ -25,13 +25,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB):
-        build()
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".hpp", "Makefile"))]
+    if not os.path.exists(LIB) or any(os.path.getmtime(f) > os.path.getmtime(LIB) for f in srcs):
+        build()   # make rebuilds only what is stale
     lib = C.CDLL(LIB)
     vp, i32, u32, dbl = C.c_void_p, C.c_int, C.c_uint32, C.c_double
     lib.orc_cape_run.argtypes = [i32, i32, i32, dbl, dbl, dbl, dbl, vp, i32, u32, i32, C.POINTER(abi.CapeOutputs)]
     lib.orc_cape_cell_fit.argtypes = [i32, i32, i32, dbl, dbl, dbl, dbl, vp, i32, vp, vp]
     lib.orc_eigen3.argtypes = [vp, vp, vp]
+    lib.orc_morphology.argtypes = [vp, i32, i32, i32, i32, i32, vp]
     lib.orc_world_to_camera.argtypes = [vp, vp, vp]
     lib.orc_pose_coefficients.argtypes = [vp, vp]
     lib.orc_pose_from_coefficients.argtypes = [vp, vp, vp]
@@ -164,3 +166,12 @@ def quaternion_from_euler(yaw, pitch, roll):
     q = np.zeros(4)
     load().orc_quaternion_from_euler(yaw, pitch, roll, q.ctypes.data)
     return q
+
+
+def morphology(mask, erode, cross, border_zero):
+    """The oracle's restatement of cv::erode / cv::dilate with a 3x3 square or cross kernel (oracle/cape.cpp: morph)."""
+    lib = load()
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty_like(m)
+    lib.orc_morphology(m.ctypes.data, m.shape[0], m.shape[1], int(erode), int(cross), int(border_zero), out.ctypes.data)
+    return out

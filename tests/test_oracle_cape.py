@@ -238,3 +238,50 @@ def test_shifted_float_bits_are_the_scaled_double_k1_accumulates():
     Dneg = (D.view(np.uint64) | np.where(s < 0, np.uint64(1) << np.uint64(63), np.uint64(0))).view(np.float64)
     assert np.array_equal(Dneg * np.float64(2.0 ** 896), s * f.astype(np.float64))
     assert np.array_equal(D * (s * np.float64(2.0 ** 896)), s * f.astype(np.float64))
+
+
+def test_morphology_restatement_matches_opencv():
+    """The boundary and cylinder-opening steps call cv::erode / cv::dilate on the 24x32 cell masks
+    (primitive_detection.cpp:48-54,596-598,678-680,719-721). OpenCV's C++ headers are not on this machine but its Python wheel
+    is: the oracle's restatement is pinned against the real cv2 calls with the reference's kernels, anchors and borders."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    cross = np.ones((3, 3), np.uint8)
+    cross[0, 0] = cross[2, 2] = cross[0, 2] = cross[2, 0] = 0
+    square = np.ones((3, 3), np.uint8)
+    masks = [(rng.random((24, 32)) < p).astype(np.uint8) for p in (0.05, 0.3, 0.5, 0.7, 0.95) for _ in range(8)]
+    masks += [np.zeros((24, 32), np.uint8), np.ones((24, 32), np.uint8)]
+    blob = np.zeros((24, 32), np.uint8)
+    blob[0:6, 0:9] = 1          # touches the image border: this is where the two border conventions differ
+    blob[10:20, 25:32] = 1
+    masks.append(blob)
+    for m in masks:
+        # compute_plane_segment_boundary: erode(cross, BORDER_CONSTANT, Scalar(0)), dilate(square)
+        want = cv2.erode(m, cross, anchor=(-1, -1), iterations=1, borderType=cv2.BORDER_CONSTANT, borderValue=0)
+        assert np.array_equal(ol.morphology(m, erode=True, cross=True, border_zero=True), want)
+        assert np.array_equal(ol.morphology(m, erode=False, cross=False, border_zero=False), cv2.dilate(m, square))
+        # add_cylinders_to_primitives: dilate(cross), erode(cross), erode(cross), default border
+        d = cv2.dilate(m, cross)
+        assert np.array_equal(ol.morphology(m, erode=False, cross=True, border_zero=False), d)
+        e = cv2.erode(d, cross)
+        assert np.array_equal(ol.morphology(d, erode=True, cross=True, border_zero=False), e)
+        assert np.array_equal(ol.morphology(e, erode=True, cross=True, border_zero=False), cv2.erode(e, cross))
+    # the two erode borders do differ on a mask that touches the frame (so the test can tell them apart)
+    assert not np.array_equal(ol.morphology(blob, True, True, True), ol.morphology(blob, True, True, False))
+
+
+def test_u16_conversion_formula_matches_opencv_convertTo():
+    """rs_cape_run_u16 replaces cv::Mat::convertTo(CV_32F, alpha) of the examples (main_TUM.cpp:242) with
+    float(src) * float(alpha) on the device (api_cape.cu: depth_u16_to_f32_kernel; tests/test_cape_gpu.py builds its
+    expectation with the same formula). cv2 does not bind convertTo itself, but cv2.normalize(NORM_MINMAX, dtype=CV_32F) ends
+    in src.convertTo(dst, CV_32F, scale, shift) with scale = beta / max(src) and shift = 0 when min(src) = 0: with
+    max(src) = 65535 and beta = 13107 the scale is exactly the reference's 1/5. The real OpenCV agrees with the FP32
+    formula on every pixel and disagrees with an FP64 product rounded to float."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    d16 = rng.integers(0, 65536, (480, 640), dtype=np.uint16)
+    d16[0, 0], d16[0, 1] = 0, 65535
+    assert 13107.0 / 65535.0 == 1.0 / 5.0
+    want = cv2.normalize(d16, None, 0, 13107.0, cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+    assert np.array_equal(want, d16.astype(np.float32) * np.float32(1.0 / 5.0))
+    assert not np.array_equal(want, (d16.astype(np.float64) * (1.0 / 5.0)).astype(np.float32))
