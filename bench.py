@@ -195,7 +195,9 @@ def main():
         # CAPE and the pose solve of a frame are independent (the reference runs find_primitives on its own thread):
         # K1 (HBM bound) runs alone, then the latency-bound segmentation (main stream) and RANSAC / LM (pose stream)
         # share the SMs; the main stream joins the pose stream before the collective / the next step. (Measured: starting
-        # the pose chain beside K1a instead costs 3 % - K1a's issue pressure stretches the latency-bound RANSAC 0.61 -> 0.87 ms.)
+        # the pose chain beside K1a instead costs 3 % - K1a's issue pressure stretches the latency-bound RANSAC 0.61 -> 0.87 ms; holding the
+        # segmentation back until RANSAC is over (cell_fit_device / stream_wait_ransac / segment_device) gives RANSAC its 0.53 ms
+        # but the one-warp segmentation CTAs then queue behind the Monte-Carlo kernel's shared memory: 1.95 ms per step.)
         det.run_device(d_depth.data_ptr(), F, seed=0, stream=sptr)
         det.stream_wait_fit(pptr)
         solver.solve_device(F, opts, stream=pptr)

@@ -142,6 +142,14 @@ int rs_cape_run_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, uint
  * cells_dev = B x Ncells records in device memory. Asynchronous. */
 int rs_cape_cell_fit_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, rs_cell_out* cells_dev, void* stream);
 
+/* The other half of rs_cape_run_device: histogram seeding, region growing, cylinder RANSAC, merging and boundary points
+ * (Primitive_Detection::find_primitives after init_planar_cell_fitting, primitive_detection.cpp:131-165) on the records a
+ * preceding rs_cape_cell_fit_device call left in out_dev->cells (same depth image, same batch). Lets a caller place other
+ * work between the two halves: bench.py holds the latency-bound segmentation back until the pose context's RANSAC kernel has
+ * finished (rs_pose_stream_wait_ransac), so that the two do not compete for shared memory. Asynchronous. */
+int rs_cape_segment_device(rs_cape_ctx* ctx, const float* depth_dev, int batch, uint32_t seed,
+                           const rs_cape_outputs* out_dev, void* stream);
+
 /* Depth_Map_Transformation::rectify_depth (src/features/primitives/depth_map_transformation.cpp:23-87, called through
  * RGBD_SLAM::rectify_depth, rgbd_slam.cpp:85-97, by examples/main_CAPE.cpp:186): the depth camera's image re-projected
  * into the colour camera's image; the last source pixel in raster order wins a destination pixel, untouched pixels are 0.
@@ -249,6 +257,11 @@ int rs_pose_solve(rs_pose_ctx* ctx, const double cur_pose[7], const rs_match* ma
 int rs_pose_upload(rs_pose_ctx* ctx, const double* cur_pose, const rs_match* matches, const int32_t* n_matches, int batch);
 int rs_pose_solve_device(rs_pose_ctx* ctx, int batch, const rs_pose_opts* opts, void* stream);
 int rs_pose_download(rs_pose_ctx* ctx, int batch, rs_pose_out* out, uint8_t* inlier_mask);
+/* Makes `stream` wait until the RANSAC + final LM kernel of the most recent solve launched through this context has
+ * finished (the Monte-Carlo covariance kernels may still be running): the counterpart of rs_cape_stream_wait_fit. The
+ * RANSAC kernel is a latency chain that suffers when other kernels take shared memory and issue slots from it; the
+ * Monte-Carlo kernel that follows is throughput bound and shares the SMs well. */
+int rs_pose_stream_wait_ransac(rs_pose_ctx* ctx, void* stream);
 double* rs_pose_device_poses(rs_pose_ctx* ctx); /* B x 7 doubles on the device (the all-gather payload) */
 
 /* Per-kernel device timing, as rs_cape_set_timing (replaces the static timing doubles of Pose_Optimization,

@@ -98,7 +98,7 @@ struct rs_cape_ctx {
     std::vector<cudaEvent_t> chunk_events;                     // 2 per chunk: depth landed, results ready
     cudaEvent_t fit_done = nullptr;   // recorded after every K1 launch (K1a + K1b): the segmentation of a chunk waits on it
     cudaEvent_t streamed = nullptr;   // recorded after K1a, the HBM-bound streaming kernel (rs_cape_stream_wait_fit)
-    std::vector<cudaEvent_t> events;  // 3 per timing slot
+    std::vector<cudaEvent_t> events;  // 4 per timing slot: fit start, fit end, segmentation start, segmentation end
     int timing_slots = 0;
     uint64_t run_counter = 0;
 };
@@ -252,8 +252,10 @@ int create_impl(rs_cape_ctx* c)
     return RS_OK;
 }
 
+// fit = launch K1 (rectification first when enabled), segment = launch K2-K4 on the records in o->cells. A run with
+// fit && segment is find_primitives; rs_cape_cell_fit_device and rs_cape_segment_device are its two halves.
 int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t seed, const rs_cape_outputs* o,
-                    cudaStream_t stream, bool cells_only, bool timing = true, cudaStream_t seg_stream = nullptr,
+                    cudaStream_t stream, bool fit, bool segment, bool timing = true, cudaStream_t seg_stream = nullptr,
                     size_t scratch_frame = 0)
 {
     if (!c || !depth_dev || batch <= 0 || batch > c->max_batch || !o || !o->cells) {
@@ -264,27 +266,39 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     int rc;
     if (c->rectify) {
         // rectify_depth in front of the path (rgbd_slam.cpp:85-97): K1 and the boundary step then read the rectified image
-        RectifyParams rp = c->rect;
-        rp.batch = batch;
         float* rect = c->d_rect + scratch_frame * size_t(c->W) * c->H;
-        if ((rc = launch_rectify_depth(rp, depth_dev, c->d_keys + scratch_frame * size_t(c->W) * c->H, rect, stream)) != RS_OK)
-            return rc;
-        depth_dev = rect;
+        if (fit) {
+            RectifyParams rp = c->rect;
+            rp.batch = batch;
+            if ((rc = launch_rectify_depth(rp, depth_dev, c->d_keys + scratch_frame * size_t(c->W) * c->H, rect, stream)) != RS_OK)
+                return rc;
+        }
+        depth_dev = rect;   // a segmentation-only call reads what the preceding fit call rectified
     }
-    rc = encode_tmap(c, depth_dev, batch);
-    if (rc != RS_OK) return rc;
-    CellFitParams fp = c->fit;
-    fp.batch = batch;
-    cudaEvent_t* ev = (timing && c->timing_slots > 0) ? &c->events[size_t(c->run_counter % uint64_t(c->timing_slots)) * 3] : nullptr;
-    if (timing) ++c->run_counter;
-    if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], stream));
-    if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream, c->streamed)) != RS_OK) return rc;
-    RS_CUDA_CHECK(cudaEventRecord(c->fit_done, stream));
-    if (ev) {
-        RS_CUDA_CHECK(cudaEventRecord(ev[1], stream));
-        if (cells_only) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+    cudaEvent_t* ev = nullptr;
+    if (timing && c->timing_slots > 0) {
+        // a segmentation-only call completes the slot its fit call opened
+        const uint64_t run = fit ? c->run_counter : (c->run_counter ? c->run_counter - 1 : 0);
+        ev = &c->events[size_t(run % uint64_t(c->timing_slots)) * 4];
     }
-    if (cells_only) return RS_OK;
+    if (fit) {
+        rc = encode_tmap(c, depth_dev, batch);
+        if (rc != RS_OK) return rc;
+        CellFitParams fp = c->fit;
+        fp.batch = batch;
+        if (timing) ++c->run_counter;
+        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+        if ((rc = launch_cape_cell_fit(c->tmap, fp, o->cells, stream, c->streamed)) != RS_OK) return rc;
+        RS_CUDA_CHECK(cudaEventRecord(c->fit_done, stream));
+        if (ev) {
+            RS_CUDA_CHECK(cudaEventRecord(ev[1], stream));
+            if (!segment) {   // until a segmentation-only call overwrites them
+                RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+                RS_CUDA_CHECK(cudaEventRecord(ev[3], stream));
+            }
+        }
+    }
+    if (!segment) return RS_OK;
     if (!o->plane_grid || !o->plane_labels || !o->cyl_labels || !o->cyl_region_seg || !o->planes || !o->cyls ||
         !o->boundary_xyz || !o->info) {
         set_last_error("rs_cape_run_device: all device output buffers are required");
@@ -310,8 +324,9 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
         RS_CUDA_CHECK(cudaStreamWaitEvent(seg_stream, c->fit_done, 0));
         return launch_cape_segment(sp, sb, seg_stream);
     }
-    if ((rc = launch_cape_segment(sp, sb, stream)) != RS_OK) return rc;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+    if ((rc = launch_cape_segment(sp, sb, stream)) != RS_OK) return rc;
+    if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[3], stream));
     return RS_OK;
 }
 
@@ -382,7 +397,7 @@ int rs_cape_set_timing(rs_cape_ctx* c, int n_slots)
     }
     RS_CUDA_CHECK(cudaSetDevice(c->device));
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
-    c->events.assign(size_t(n_slots) * 3, nullptr);
+    c->events.assign(size_t(n_slots) * 4, nullptr);
     for (cudaEvent_t& e : c->events) RS_CUDA_CHECK(cudaEventCreate(&e));
     c->timing_slots = n_slots;
     c->run_counter = 0;
@@ -395,10 +410,10 @@ int rs_cape_kernel_ms(rs_cape_ctx* c, int slot, float ms[2])
         set_last_error("rs_cape_kernel_ms: timing is off or that slot has not been recorded");
         return RS_ERR_INVALID_ARG;
     }
-    cudaEvent_t* ev = &c->events[size_t(slot) * 3];
-    RS_CUDA_CHECK(cudaEventSynchronize(ev[2]));
+    cudaEvent_t* ev = &c->events[size_t(slot) * 4];
+    RS_CUDA_CHECK(cudaEventSynchronize(ev[3]));
     RS_CUDA_CHECK(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
-    RS_CUDA_CHECK(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));
+    RS_CUDA_CHECK(cudaEventElapsedTime(&ms[1], ev[2], ev[3]));
     return RS_OK;
 }
 
@@ -472,13 +487,19 @@ int rs_cape_cell_fit_device(rs_cape_ctx* c, const float* depth_dev, int batch, r
 {
     rs_cape_outputs o{};
     o.cells = cells_dev;
-    return run_device_impl(c, depth_dev, batch, 0, &o, static_cast<cudaStream_t>(stream), true);
+    return run_device_impl(c, depth_dev, batch, 0, &o, static_cast<cudaStream_t>(stream), true, false);
 }
 
 int rs_cape_run_device(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t seed, const rs_cape_outputs* out_dev,
                        void* stream)
 {
-    return run_device_impl(c, depth_dev, batch, seed, out_dev, static_cast<cudaStream_t>(stream), false);
+    return run_device_impl(c, depth_dev, batch, seed, out_dev, static_cast<cudaStream_t>(stream), true, true);
+}
+
+int rs_cape_segment_device(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t seed, const rs_cape_outputs* out_dev,
+                           void* stream)
+{
+    return run_device_impl(c, depth_dev, batch, seed, out_dev, static_cast<cudaStream_t>(stream), false, true);
 }
 
 static int run_host_impl(rs_cape_ctx* c, const float* depth_host, const uint16_t* depth16_host, float alpha, int batch,
@@ -523,7 +544,7 @@ static int run_host_impl(rs_cape_ctx* c, const float* depth_host, const uint16_t
         dchunk.boundary_xyz = d.boundary_xyz + o * mb * 3;
         dchunk.info = d.info + o;
         cudaStream_t seg = c->seg_streams[k % 4];
-        if ((rc = run_device_impl(c, c->d_depth + o * px, int(n), seed, &dchunk, c->stream, cells_only, false, seg, o)) != RS_OK)
+        if ((rc = run_device_impl(c, c->d_depth + o * px, int(n), seed, &dchunk, c->stream, true, !cells_only, false, seg, o)) != RS_OK)
             return rc;
         RS_CUDA_CHECK(cudaEventRecord(ready, cells_only ? c->stream : seg));
         RS_CUDA_CHECK(cudaStreamWaitEvent(c->d2h_stream, ready, 0));

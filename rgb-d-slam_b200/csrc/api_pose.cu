@@ -30,6 +30,7 @@ struct rs_pose_ctx {
     PoseLaunch last{};
     int last_batch = 0;
     std::vector<cudaEvent_t> events;  // 5 per timing slot
+    cudaEvent_t ransac_done = nullptr;   // recorded after the RANSAC + final LM kernel (rs_pose_stream_wait_ransac)
     int timing_slots = 0;
     uint64_t run_counter = 0;
 };
@@ -71,6 +72,7 @@ int create_impl(rs_pose_ctx* c)
     b.matches_aos = c->d_matches, b.cur_pose = c->d_cur, b.n_matches = c->d_n;
     b.subsets_in = nullptr, b.normals_in = nullptr;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->ransac_done, cudaEventDisableTiming));
     c->h_n.assign(B, 0);
     c->h_type.assign(B * M, 0);
     return RS_OK;
@@ -208,6 +210,7 @@ int solve_impl(rs_pose_ctx* c, int batch, const PoseLaunch& prm, cudaStream_t s,
     if ((rc = launch_pose_prepare(buf, prm, s)) != RS_OK) return rc;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[1], s));
     if ((rc = launch_pose_ransac(buf, prm, s)) != RS_OK) return rc;
+    RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
     if (ev) {
         RS_CUDA_CHECK(cudaEventRecord(ev[2], s));
         if (prm.n_variance <= 0) {
@@ -306,6 +309,7 @@ void rs_pose_destroy(rs_pose_ctx* c)
     cudaFree(b.v6);
     cudaFree(b.v_ok);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    if (c->ransac_done) cudaEventDestroy(c->ransac_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -420,6 +424,17 @@ int rs_pose_solve_device(rs_pose_ctx* c, int batch, const rs_pose_opts* opts, vo
     }
     RS_CUDA_CHECK(cudaSetDevice(c->device));
     return solve_impl(c, batch, prm, static_cast<cudaStream_t>(stream), false);
+}
+
+int rs_pose_stream_wait_ransac(rs_pose_ctx* c, void* stream)
+{
+    if (!c) {
+        set_last_error("rs_pose_stream_wait_ransac: null context");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    RS_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->ransac_done, 0));
+    return RS_OK;
 }
 
 int rs_pose_download(rs_pose_ctx* c, int batch, rs_pose_out* out, uint8_t* inlier_mask)

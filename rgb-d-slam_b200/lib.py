@@ -40,6 +40,8 @@ def load():
     lib.rs_cape_run_device.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs), vp]
     lib.rs_cape_cell_fit_device.argtypes = [vp, vp, i32, vp, vp]
     lib.rs_cape_stream_wait_fit.argtypes = [vp, vp]
+    lib.rs_cape_segment_device.argtypes = [vp, vp, i32, u32, C.POINTER(abi.CapeOutputs), vp]
+    lib.rs_pose_stream_wait_ransac.argtypes = [vp, vp]
     lib.rs_cape_set_rectification.argtypes = [vp, vp, i32]
     lib.rs_cape_rectify.argtypes = [vp, vp, i32, vp]
     lib.rs_cape_rectify_device.argtypes = [vp, vp, i32, vp, vp]
@@ -193,6 +195,11 @@ class PrimitiveDetection:
             cells_ptr = self.device_outputs().cells
         _check(self._lib.rs_cape_cell_fit_device(self._ctx, depth_ptr, batch, cells_ptr, stream), "rs_cape_cell_fit_device")
 
+    def segment_device(self, depth_ptr, batch, seed=0, outputs=None, stream=0):
+        """The second half of run_device (K2-K4) on the records a preceding cell_fit_device call left in outputs.cells."""
+        o = outputs if outputs is not None else self.device_outputs()
+        _check(self._lib.rs_cape_segment_device(self._ctx, depth_ptr, batch, seed, C.byref(o), stream), "rs_cape_segment_device")
+
 
 def kalman_track_points(state, cov, meas, meas_cov, process_noise=0.001, device=0):
     """tracking::Point::track for n matched map points at once (point_with_tracking.cpp:32-84).
@@ -314,6 +321,10 @@ class PoseOptimization:
 
     def solve_device(self, batch, opts, stream=0):
         _check(self._lib.rs_pose_solve_device(self._ctx, batch, C.byref(opts), stream), "rs_pose_solve_device")
+
+    def stream_wait_ransac(self, stream):
+        """`stream` (cudaStream_t as int) waits for the RANSAC + final LM kernel of the latest solve of this context."""
+        _check(self._lib.rs_pose_stream_wait_ransac(self._ctx, stream), "rs_pose_stream_wait_ransac")
 
     def download(self, batch):
         out = np.zeros((batch,), dtype=abi.pose_out_dtype)

@@ -251,3 +251,41 @@ def test_two_contexts_on_two_host_threads_match_serial_runs():
         assert w["info"].tobytes() == g["info"].tobytes()
     a.close()
     b.close()
+
+
+def test_split_fit_and_segment_equal_the_fused_device_run(det):
+    """rs_cape_cell_fit_device + rs_cape_segment_device (with a pose solve and rs_pose_stream_wait_ransac between them, as a
+    scheduler would place them) produce what rs_cape_run_device produces."""
+    import torch
+    depth = rs.synth.scene_v0_batch(50, 4)
+    want = det.find_primitives(depth, seed=9)
+    d = torch.from_numpy(depth).cuda()
+    truth, cur, m = rs.synth.pose_correspondences(0)
+    solver = rs.PoseOptimization(max_batch=1, max_matches=len(m))
+    solver.upload(cur[None], m[None], np.array([len(m)], np.int32))
+    opts = solver.options(seed=0, rng_mode=rs.abi.RS_RNG_DEVICE)
+    s = torch.cuda.current_stream().cuda_stream
+    p = torch.cuda.Stream()
+    det.cell_fit_device(d.data_ptr(), 4, stream=s)
+    det.stream_wait_fit(p.cuda_stream)
+    solver.solve_device(1, opts, stream=p.cuda_stream)
+    solver.stream_wait_ransac(s)
+    det.segment_device(d.data_ptr(), 4, seed=9, stream=s)
+    torch.cuda.synchronize()
+
+    class _DevPtr:   # torch view of a device buffer owned by the library
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    host, _ = rs.abi.alloc_cape_outputs(4, det.n_cells, det.max_boundary)
+    dev = det.device_outputs()
+    got = {}
+    for k in ("cells", "plane_labels", "cyl_labels", "plane_grid", "cyl_region_seg", "info"):
+        raw = torch.as_tensor(_DevPtr(getattr(dev, k), host[k].nbytes), device="cuda").cpu().numpy()
+        got[k] = raw.view(host[k].dtype).reshape(host[k].shape)
+    for k in ("plane_labels", "cyl_labels", "plane_grid", "cyl_region_seg"):
+        assert np.array_equal(want[k], got[k]), k
+    assert want["cells"].tobytes() == got["cells"].tobytes()
+    assert want["info"].tobytes() == got["info"].tobytes()
+    out, _ = solver.download(1)
+    assert out[0]["status"] == 1
+    solver.close()
