@@ -60,38 +60,45 @@ constexpr int WARPS = 4;
 
 constexpr int kUnroll = RS_K1_UNROLL;
 
-// Indices e_i = base[i * stride], i in [0, n). Reference (plane_segment.cpp:44-100): last = max(e_0, e_1); fail if
-// last <= 0; for i = 1..n-1 a positive e_i must satisfy |e_i - last| <= 4 quant(e_i) and then becomes `last`.
-// Because any failure rejects the cell, `last` at step i is the nearest positive element in [1, i-1] (or the initial
-// max when there is none): this checks the elements [lo, hi) only, looking backwards for their predecessor.
-__device__ __forceinline__ bool continuity_segment(const float* base, const int stride, const int lo, const int hi,
-                                                   const float init)
+// Continuity scan of one middle row / column, e_i = base[i], i in [0, n). Reference (plane_segment.cpp:44-100):
+// last = max(e_0, e_1); fail if last <= 0; for i = 1..n-1 a positive e_i must satisfy |e_i - last| <= 4 quant(e_i) and
+// then becomes `last`. Because any failure rejects the cell, `last` at step i is the nearest positive element in
+// [1, i-1] (or the initial max when there is none). The four lanes of a cell take SEG consecutive elements each
+// ([lo, hi), hi - lo <= SEG): a lane first finds the last positive element of its own segment, the predecessor of its
+// first element then comes from the earlier lanes by shuffle, and the scan itself is branch-free but for the rare jump
+// that lands within 1e-5 of the bound. Must be called by all four lanes of the cell (`lead` = its first lane).
+template <int SEG>
+__device__ __forceinline__ bool continuity_lane(const float* base, const int lo, const int hi, const float init, const int j,
+                                                const int lead)
 {
-    float prev = init;
-    for (int i = lo - 1; i >= 1; --i) {
-        const float z = base[i * stride];
-        if (z > 0.f) {
-            prev = z;
-            break;
-        }
+    float z[SEG];
+    float last = 0.f;
+#pragma unroll
+    for (int t = 0; t < SEG; ++t) {
+        z[t] = lo + t < hi ? base[lo + t] : 0.f;      // past the end reads as an empty pixel
+        last = z[t] > 0.f ? z[t] : last;
     }
+    const float l0 = __shfl_sync(FULL, last, lead), l1 = __shfl_sync(FULL, last, lead + 1), l2 = __shfl_sync(FULL, last, lead + 2);
+    float prev = init;
+    if (j > 0 && l0 > 0.f) prev = l0;
+    if (j > 1 && l1 > 0.f) prev = l1;
+    if (j > 2 && l2 > 0.f) prev = l2;
     bool ok = true;
-    for (int i = lo; i < hi; ++i) {
-        const float z = base[i * stride];
-        if (z > 0.f) {
-            const float diff = fabsf(z - prev);
-            // jump <= 4 quant(z), decided in FP32 whenever the FP32 estimate of the bound is further from `diff` than its
-            // own error (a few 1e-7 relative, plus the cancellation against the -0.53 offset); the reference's FP64
-            // expression only runs for the rare jump that lands within 1e-5 of the bound
-            const float qf = fmaxf(0.5f, fmaf(2.73e-6f * z, z, fmaf(0.74e-3f, z, -0.53f)));
-            const float bound = 4.0f * qf, slack = fmaf(bound, 1e-5f, 1e-5f);
-            if (diff > bound + slack)
-                ok = false;
-            else if (diff >= bound - slack) {
-                if (!(static_cast<double>(diff) <= 4.0 * depth_quantization(static_cast<double>(z)))) ok = false;
-            }
-            prev = z;
+#pragma unroll
+    for (int t = 0; t < SEG; ++t) {
+        const float zt = z[t];
+        const bool valid = zt > 0.f;
+        const float diff = fabsf(zt - prev);
+        // jump <= 4 quant(z), decided in FP32 whenever the FP32 estimate of the bound is further from `diff` than its
+        // own error (a few 1e-7 relative, plus the cancellation against the -0.53 offset); the reference's FP64
+        // expression only runs for the rare jump that lands within 1e-5 of the bound
+        const float qf = fmaxf(0.5f, fmaf(2.73e-6f * zt, zt, fmaf(0.74e-3f, zt, -0.53f)));
+        const float bound = 4.0f * qf, slack = fmaf(bound, 1e-5f, 1e-5f);
+        if (valid && diff > bound + slack) ok = false;
+        if (valid && diff >= bound - slack && diff <= bound + slack) {
+            if (!(static_cast<double>(diff) <= 4.0 * depth_quantization(static_cast<double>(zt)))) ok = false;
         }
+        prev = valid ? zt : prev;
     }
     return ok;
 }
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
             S7 += __shfl_xor_sync(FULL, S7, o);
             S8 += __shfl_xor_sync(FULL, S8, o);
         }
-        bool cont = true;
+        bool cont;
         {
             // horizontal: CS elements of the middle row; vertical: CS-1 elements of the middle column
             const float* hr = midrow + c * CS;
@@ -379,8 +386,9 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
             constexpr int HSEG = (CS - 1 + 3) / 4, VSEG = (CS - 2 + 3) / 4;
             const int hlo = 1 + j * HSEG, hhi = min(hlo + HSEG, CS);
             const int vlo = 1 + j * VSEG, vhi = min(vlo + VSEG, CS - 1);
-            cont = hinit > 0.f && vinit > 0.f;
-            if (cont) cont = continuity_segment(hr, 1, hlo, hhi, hinit) && continuity_segment(vcq, 1, vlo, vhi, vinit);
+            const bool hok = continuity_lane<HSEG>(hr, hlo, hhi, hinit, j, lane & ~3);
+            const bool vok = continuity_lane<VSEG>(vcq, vlo, vhi, vinit, j, lane & ~3);
+            cont = hinit > 0.f && vinit > 0.f && hok && vok;
         }
         const unsigned bad = __ballot_sync(FULL, !cont);
         const int okc = (((bad >> (lane & ~3)) & 0xfu) == 0u && cnt >= P / 2) ? 1 : 0;

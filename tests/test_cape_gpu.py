@@ -289,3 +289,20 @@ def test_split_fit_and_segment_equal_the_fused_device_run(det):
     out, _ = solver.download(1)
     assert out[0]["status"] == 1
     solver.close()
+
+
+@pytest.mark.parametrize("W,H,cell", [(400, 300, 20), (320, 240, 20), (640, 480, 40), (1000, 720, 40), (180, 100, 20)])
+def test_other_geometries_match_oracle(W, H, cell):
+    """Grids whose width is not a multiple of K1a's 8-cell work item (20, 16, 25 and 9 cells per row: the last item of a
+    cell row hangs over the image and its TMA box is zero-filled), other aspect ratios, 40 px cells on a small image."""
+    K = rs.synth.intrinsics(W / 640.0)
+    d = rs.PrimitiveDetection(W, H, cell, *K, max_batch=3)
+    depth = rs.synth.scene_v0_batch(70, 3, width=W, height=H)
+    got = d.find_primitives(depth, seed=2)
+    ref = ol.cape_run(depth, cell=cell, K=K, seed=2)
+    for b in range(3):
+        parity.assert_cells_match(ref["cells"][b], got["cells"][b])
+        parity.assert_frame_match(ref, got, b)
+    assert np.array_equal(ref["plane_labels"], got["plane_labels"])
+    assert np.array_equal(ref["cyl_labels"], got["cyl_labels"])
+    d.close()
