@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         row0 = b * prm.H + cr * CS;
     };
 
+    const uint32_t bar_a = smem_u32(bars), tile_a = smem_u32(wbase);   // shared-window addresses of the ring, converted once
     const uint64_t policy = l2_policy_evict_first();   // the depth image is read once; keep L2 for the records
     if (lane == 0) {
         mbar_init(&bars[0], 1);
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
             if (q < nbox) {
                 int row0, c0, cr, b;
                 item_origin(q / NBOX, row0, c0, cr, b);
-                mbar_arrive_expect_tx(&bars[q], Geo::BOX_BYTES);
-                tma_load_3d_hint(wbase + q * Geo::BOX_BYTES, &tmap, 0, c0, row0 + (q % NBOX) * R, &bars[q], policy);
+                mbar_arrive_expect_tx_a(bar_a + q * 8, Geo::BOX_BYTES);
+                tma_load_3d_hint_a(tile_a + q * Geo::BOX_BYTES, &tmap, 0, c0, row0 + (q % NBOX) * R, bar_a + q * 8, policy);
             }
     }
     __syncwarp();
@@ -203,22 +204,20 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
     int cnt = 0;
     float p0x = 0.f, p0y = 0.f, p0z = 0.f, plx = 0.f, ply = 0.f, plz = 0.f;
 
-    // (item, box) of the box being consumed and of the box two ahead (the one the ring is refilled with); the item
-    // coordinates cost two integer divisions, so they are only recomputed when an item boundary is crossed
+    // (item, box) of the box being consumed and of the box two ahead (the one the ring is refilled with). The item
+    // coordinates cost two integer divisions: they are computed once per item, by the refill cursor, and the consume
+    // cursor inherits them when it crosses into that item (NBOX >= 3: the refill cursor is then inside the same item).
+    static_assert(NBOX >= 3, "the consume cursor takes its item coordinates from the refill cursor");
     int k = 0, bq = 0, row0, c0, cr, b;
     item_origin(0, row0, c0, cr, b);
-    int kn = 2 / NBOX, bqn = 2 % NBOX, nrow0 = row0, nc0 = c0;
-    if (kn != 0 && 2 < nbox) {
-        int ncr, nb;
-        item_origin(kn, nrow0, nc0, ncr, nb);
-    }
+    int kn = 0, bqn = 2, nrow0 = row0, nc0 = c0, ncr = cr, nb = b;
     for (int q = 0; q < nbox; ++q) {
         const int slot = q & 1;
         const double* kyrow = prm.ky + cr * CS;
         const float* tile = reinterpret_cast<const float*>(wbase + slot * Geo::BOX_BYTES);
         const float* ctile = tile + c * CS;            // this cell's columns inside a box row
         const int colbase = (c0 + c) * CS;
-        mbar_wait(&bars[slot], (q >> 1) & 1);
+        mbar_wait_a(bar_a + slot * 8, (q >> 1) & 1);
 
         // ---- branch-free accumulation of this lane's float4s of the box ----
         int r = 0, g = j;                              // flat index j + 4k -> (row r, group g); G >= 5 > 4
@@ -340,17 +339,14 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         __syncwarp();
         // the box is consumed: refill the slot with box q + 2
         if (lane == 0 && q + 2 < nbox) {
-            mbar_arrive_expect_tx(&bars[slot], Geo::BOX_BYTES);
-            tma_load_3d_hint(wbase + slot * Geo::BOX_BYTES, &tmap, 0, nc0, nrow0 + bqn * R, &bars[slot], policy);
+            mbar_arrive_expect_tx_a(bar_a + slot * 8, Geo::BOX_BYTES);
+            tma_load_3d_hint_a(tile_a + slot * Geo::BOX_BYTES, &tmap, 0, nc0, nrow0 + bqn * R, bar_a + slot * 8, policy);
         }
         // advance the refill cursor (box q + 3 next time)
         if (++bqn == NBOX) {
             bqn = 0;
             ++kn;
-            if (kn < nitems) {
-                int ncr, nb;
-                item_origin(kn, nrow0, nc0, ncr, nb);
-            }
+            if (kn < nitems) item_origin(kn, nrow0, nc0, ncr, nb);
         }
         const bool item_done = bq == NBOX - 1;
         const int cur_c0 = c0, cur_cr = cr, cur_b = b;
@@ -358,7 +354,7 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         if (++bq == NBOX) {
             bq = 0;
             ++k;
-            if (k < nitems) item_origin(k, row0, c0, cr, b);
+            row0 = nrow0, c0 = nc0, cr = ncr, b = nb;   // kn == k here (stale, and unused, after the last item)
         }
         if (!item_done) continue;
 

@@ -65,6 +65,35 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorM
             : "memory");
 }
 
+// Variants that take shared-memory addresses already converted with smem_u32 (hot loops convert once).
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(const uint32_t bar, const uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(const uint32_t bar, const uint32_t parity)
+{
+    asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint_a(const uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                                   const uint32_t bar, uint64_t policy)
+{
+    asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                    smem_dst),
+            "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+            : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
