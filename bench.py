@@ -238,6 +238,36 @@ def main():
     ms_total = float(t.item())
     value = world * F * steps / (ms_total * 1e-3)
 
+    # ---- one frame at a time (BASELINE configs[1] / [2] at batch = 1: what the reference's per-frame track() call sees) ----
+    single = None
+    if rank == 0:
+        def one_frame(cape=True, pose=True):
+            if cape:
+                det.run_device(d_depth.data_ptr(), 1, seed=0, stream=sptr)
+            if pose:
+                if cape:
+                    det.stream_wait_fit(pptr)
+                else:
+                    pose_stream.wait_stream(stream)
+                solver.solve_device(1, opts, stream=pptr)
+                stream.wait_stream(pose_stream)
+
+        def time_frames(n, **kw):
+            for _ in range(5):
+                one_frame(**kw)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(n):
+                one_frame(**kw)
+            b_.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / n
+        ms_cape, ms_pose, ms_full = time_frames(50, pose=False), time_frames(50, cape=False), time_frames(50)
+        single = {"cape_ms": ms_cape, "pose_ms": ms_pose, "full_frame_ms": ms_full, "frames_per_s": 1e3 / ms_full,
+                  "note": "batch = 1, inputs resident, back-to-back frames on one GPU: CAPE plane + cylinder extraction (configs[1]), "
+                          "the 300-point / 20-plane RANSAC-LM solve with its covariance, and both overlapped (configs[2])"}
+
     # ---- rectify_depth (the step in front of the path, off in the headline workload as in examples/main_TUM.cpp) ----
     rect = None
     if rank == 0:
@@ -533,6 +563,8 @@ def main():
         }
         if rect is not None:
             line["rectify_depth"] = rect
+        if single is not None:
+            line["single_frame"] = single
         if kalman is not None:
             line["kalman_update"] = kalman
         if pipelined is not None:
