@@ -447,7 +447,8 @@ def main():
                "u16_depth": {"value": world * F * e2e_steps / sec16, "unit": "frames/s",
                              "h2d_bytes_per_step": int(h_d16_np.nbytes + h_matches_np.nbytes + cur.nbytes + n.nbytes),
                              "note": "rs_cape_run_u16: CV_16U sensor image, convertTo(CV_32F) on the device"},
-               "timing": "host wall clock around the C-ABI calls (pose solve begin -> find_primitives, chunk-pipelined copies -> pose solve end), max over ranks"}
+               "timing": "host wall clock around the C-ABI calls (pose solve begin -> find_primitives, chunk-pipelined copies -> pose solve end), max over ranks",
+               "mode": "one blocking call at a time"}
 
         # ---- the same host API with two batches in flight: two host threads, each with its own contexts and pinned
         # buffers, call the blocking entry points (ctypes releases the GIL); the upload of one batch overlaps the
