@@ -39,6 +39,8 @@ def parse_args():
     p.add_argument("--frames-per-gpu", type=int, default=256)
     p.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 10))")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--pose-groups", type=int, default=1,
+                   help="rs_pose_opts.sub_batches: frame groups whose RANSAC -> Monte-Carlo chains run on separate streams")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-e2e-lanes", action="store_true", help="skip the two-batches-in-flight variant of the host-buffer leg")
     return p.parse_args()
@@ -174,7 +176,7 @@ def main():
 
     det = rs.PrimitiveDetection(W, H, CELL, max_batch=F, device=local_rank)
     solver = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=119, max_variance=100, device=local_rank)
-    opts = solver.options(seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE)
+    opts = solver.options(seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE, sub_batches=args.pose_groups)
 
     # ---- HBM-resident leg: inputs live on the device before the timed region ----
     stream = torch.cuda.current_stream()
@@ -551,6 +553,7 @@ def main():
                 "frames_per_gpu": F, "cell_px": CELL, "cells_per_frame": N_CELLS, "ransac_hypotheses": 119, "n_variance": 100,
                 "l2": "inputs larger than L2 (%.0f MB of depth per step per GPU vs 126 MB)" % (depth.nbytes / 1e6),
                 "rng": "RS_RNG_DEVICE (counter-based on-device draws)",
+                "pose_groups": args.pose_groups,
                 "streams": "K1 alone, then cape_segment (main stream) beside pose_prepare/ransac/variance/covariance (pose stream); kernels_ms_per_step are per-kernel event times and overlap", "collective": "all-gather of [frames x 7] f64 poses" if world > 1 else "none",
             },
             "roofline": {"kernel": "cape_cell_fit (K1)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

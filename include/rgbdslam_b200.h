@@ -209,7 +209,10 @@ typedef struct rs_pose_opts {
     uint32_t seed;
     double fx, fy, cx, cy;      /* camera-1 intrinsics; all 0 -> reference defaults 550,550,320,240  */
     int32_t lm_max_fev;         /* <=0 -> 400 (Eigen LevenbergMarquardt default)                     */
-    int32_t reserved;
+    int32_t sub_batches;        /* RS_RNG_DEVICE only: > 1 splits the batch into that many groups of frames (at most 8)
+                                   whose RANSAC -> Monte-Carlo kernel chains run on separate streams, so that a group's
+                                   Monte-Carlo solves start as soon as its own slowest RANSAC frame is through. Frames are
+                                   independent: the results are identical. <= 1 -> one group                            */
 } rs_pose_opts;
 
 typedef struct rs_pose_out {

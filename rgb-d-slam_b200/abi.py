@@ -48,7 +48,7 @@ class CapeOutputs(C.Structure):
 class PoseOpts(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("n_variance", C.c_int32), ("rng_mode", C.c_int32),
                 ("seed", C.c_uint32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
-                ("lm_max_fev", C.c_int32), ("reserved", C.c_int32)]
+                ("lm_max_fev", C.c_int32), ("sub_batches", C.c_int32)]
 
 
 def alloc_cape_outputs(batch, n_cells, max_boundary):

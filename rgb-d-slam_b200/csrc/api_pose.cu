@@ -31,6 +31,11 @@ struct rs_pose_ctx {
     int last_batch = 0;
     std::vector<cudaEvent_t> events;  // 5 per timing slot
     cudaEvent_t ransac_done = nullptr;   // recorded after the RANSAC + final LM kernel (rs_pose_stream_wait_ransac)
+    // rs_pose_opts::sub_batches > 1: side streams of the frame groups 1.. (group 0 runs on the caller's stream)
+    static constexpr int kMaxGroups = 8;
+    cudaStream_t group_stream[kMaxGroups - 1] = {};
+    cudaEvent_t group_fork = nullptr, group_ransac[kMaxGroups - 1] = {}, group_done[kMaxGroups - 1] = {};
+    int groups_last = 1;                 // groups of the most recent solve (how many group_ransac events are live)
     int timing_slots = 0;
     uint64_t run_counter = 0;
 };
@@ -73,6 +78,12 @@ int create_impl(rs_pose_ctx* c)
     b.subsets_in = nullptr, b.normals_in = nullptr;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->ransac_done, cudaEventDisableTiming));
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->group_fork, cudaEventDisableTiming));
+    for (int g = 0; g < rs_pose_ctx::kMaxGroups - 1; ++g) {
+        RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->group_stream[g], cudaStreamNonBlocking));
+        RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->group_ransac[g], cudaEventDisableTiming));
+        RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->group_done[g], cudaEventDisableTiming));
+    }
     c->h_n.assign(B, 0);
     c->h_type.assign(B * M, 0);
     return RS_OK;
@@ -96,6 +107,7 @@ int resolve_launch(const rs_pose_ctx* c, const rs_pose_opts* opts, int batch, Po
     prm.rng_mode = o.rng_mode;
     prm.seed = o.seed;
     prm.has_point2d = c->has_point2d ? 1 : 0;
+    prm.sub_batches = o.sub_batches < 1 ? 1 : (o.sub_batches > rs_pose_ctx::kMaxGroups ? rs_pose_ctx::kMaxGroups : o.sub_batches);
     if (o.fx == 0 && o.fy == 0 && o.cx == 0 && o.cy == 0)
         prm.K = PoseIntrinsics{550.0, 550.0, 320.0, 240.0};  // Parameters::load_defaut (parameters.cpp:59-74)
     else
@@ -206,6 +218,45 @@ int solve_impl(rs_pose_ctx* c, int batch, const PoseLaunch& prm, cudaStream_t s,
     }
     cudaEvent_t* ev = c->timing_slots > 0 ? &c->events[size_t(c->run_counter % uint64_t(c->timing_slots)) * 5] : nullptr;
     ++c->run_counter;
+    const int groups = (!reference_rng && prm.n_variance > 0) ? std::min(prm.sub_batches, batch) : 1;
+    c->groups_last = groups;
+    if (groups > 1) {
+        // Frame groups: the RANSAC kernel of the whole batch lasts as long as its slowest frame (a latency chain), and the
+        // throughput-bound Monte-Carlo kernel cannot start before it ends. Split into groups of frames whose
+        // prepare -> RANSAC -> Monte-Carlo -> covariance chains run on their own streams, a group's Monte-Carlo solves start as
+        // soon as ITS slowest frame is through and fill the SMs while the other groups' RANSAC chains are still running.
+        // Frames are independent and the random draws are keyed by the frame index: the results do not change.
+        // Timing slots in this mode: [0,1] prepare of group 0, [1,2] RANSAC of group 0, [2,3] first group's Monte-Carlo
+        // kernel ... the whole solve is [0,4] (ev[4] is recorded after the join).
+        RS_CUDA_CHECK(cudaEventRecord(c->group_fork, s));
+        const int per = (batch + groups - 1) / groups;
+        for (int g = 0; g < groups; ++g) {
+            cudaStream_t gs = g == 0 ? s : c->group_stream[g - 1];
+            PoseLaunch gp = prm;
+            gp.frame0 = g * per;
+            gp.batch = std::min(per, batch - gp.frame0);
+            if (gp.batch <= 0) {
+                c->groups_last = g;
+                break;
+            }
+            if (g > 0) RS_CUDA_CHECK(cudaStreamWaitEvent(gs, c->group_fork, 0));
+            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], gs));
+            if ((rc = launch_pose_prepare(buf, gp, gs)) != RS_OK) return rc;
+            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[1], gs));
+            if ((rc = launch_pose_ransac(buf, gp, gs)) != RS_OK) return rc;
+            RS_CUDA_CHECK(cudaEventRecord(g == 0 ? c->ransac_done : c->group_ransac[g - 1], gs));
+            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], gs));
+            if ((rc = launch_pose_variance(buf, gp, gs)) != RS_OK) return rc;
+            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[3], gs));
+            if ((rc = launch_pose_covariance(buf, gp, gs)) != RS_OK) return rc;
+            if (g > 0) RS_CUDA_CHECK(cudaEventRecord(c->group_done[g - 1], gs));
+        }
+        for (int g = 1; g < c->groups_last; ++g) RS_CUDA_CHECK(cudaStreamWaitEvent(s, c->group_done[g - 1], 0));
+        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[4], s));
+        c->last = prm;
+        c->last_batch = batch;
+        return RS_OK;
+    }
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], s));
     if ((rc = launch_pose_prepare(buf, prm, s)) != RS_OK) return rc;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[1], s));
@@ -310,6 +361,12 @@ void rs_pose_destroy(rs_pose_ctx* c)
     cudaFree(b.v_ok);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->ransac_done) cudaEventDestroy(c->ransac_done);
+    if (c->group_fork) cudaEventDestroy(c->group_fork);
+    for (int g = 0; g < rs_pose_ctx::kMaxGroups - 1; ++g) {
+        if (c->group_ransac[g]) cudaEventDestroy(c->group_ransac[g]);
+        if (c->group_done[g]) cudaEventDestroy(c->group_done[g]);
+        if (c->group_stream[g]) cudaStreamDestroy(c->group_stream[g]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -434,6 +491,8 @@ int rs_pose_stream_wait_ransac(rs_pose_ctx* c, void* stream)
     }
     RS_CUDA_CHECK(cudaSetDevice(c->device));
     RS_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->ransac_done, 0));
+    for (int g = 1; g < c->groups_last; ++g)
+        RS_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->group_ransac[g - 1], 0));
     return RS_OK;
 }
 

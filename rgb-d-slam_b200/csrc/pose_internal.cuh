@@ -47,7 +47,9 @@ struct PoseBuffers {
 };
 
 struct PoseLaunch {
-    int batch;
+    int batch;            // frames this launch covers: [frame0, frame0 + batch)
+    int frame0 = 0;       // first frame (the host splits a batch into groups whose kernel chains run on separate streams)
+    int sub_batches = 1;  // host side only: number of such groups (rs_pose_opts::sub_batches)
     int max_iterations;   // RANSAC hypotheses (119 default)
     int n_variance;       // Monte-Carlo solves
     int lm_max_fev;       // 400

@@ -1069,7 +1069,7 @@ __device__ inline void device_normals(const uint32_t seed, const int frame, cons
 // total score in list order. One CTA per frame.
 __global__ void __launch_bounds__(THREADS) pose_prepare_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
-    const int b = blockIdx.x;
+    const int b = prm.frame0 + blockIdx.x;
     const int M = buf.max_matches;
     int n = buf.n_matches[b];
     n = n < 0 ? 0 : (n > M ? M : n);
@@ -1224,7 +1224,7 @@ template <bool P2D>
 __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.x;
+    const int b = prm.frame0 + blockIdx.x;
     const int M = buf.max_matches;
     const int words = (M + 31) / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1489,7 +1489,7 @@ template <bool P2D>
 __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.y;
+    const int b = prm.frame0 + blockIdx.y;
     const int M = buf.max_matches;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PoseFrameState st = buf.state[b];
@@ -1621,9 +1621,9 @@ __device__ bool covariance_valid(const double* c)
 // the mean, then lane e < 21 owns one entry of the upper triangle and sums it over the samples in sample order.
 __global__ void __launch_bounds__(128) pose_covariance_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int b = prm.frame0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (b >= prm.batch) return;
+    if (b >= prm.frame0 + prm.batch) return;
     if (buf.state[b].stage != 1 || prm.n_variance <= 0) return;
     const double* v6 = buf.v6 + size_t(b) * buf.max_variance * 6;
     const int32_t* vok = buf.v_ok + size_t(b) * buf.max_variance;

@@ -262,9 +262,11 @@ class PoseOptimization:
             pass
 
     @staticmethod
-    def options(max_iterations=0, n_variance=-1, rng_mode=abi.RS_RNG_REFERENCE, seed=0, intrinsics=None, lm_max_fev=0):
+    def options(max_iterations=0, n_variance=-1, rng_mode=abi.RS_RNG_REFERENCE, seed=0, intrinsics=None, lm_max_fev=0,
+                sub_batches=0):
         o = abi.PoseOpts()
         o.max_iterations, o.n_variance, o.rng_mode, o.seed, o.lm_max_fev = max_iterations, n_variance, rng_mode, seed, lm_max_fev
+        o.sub_batches = sub_batches   # RS_RNG_DEVICE: frame groups on separate streams (same results)
         if intrinsics is not None:
             o.fx, o.fy, o.cx, o.cy = intrinsics
         return o

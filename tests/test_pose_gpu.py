@@ -290,3 +290,19 @@ def test_point2d_invalid_feature_rejects_the_frame(solver):
     for b in (1, 2):
         rout, rmask = ol.pose_solve(cur[b], bad[b][:n[b]], seed=5 + b)
         assert_out_match(rout, out[b], rmask, mask[b], n[b])
+
+
+@pytest.mark.parametrize("groups", [2, 3, 4, 8])
+def test_frame_groups_on_separate_streams_change_nothing(groups):
+    """rs_pose_opts.sub_batches: the batch split into groups of frames whose kernel chains run on their own streams returns,
+    byte for byte, what the single-group solve returns (ragged group sizes, rejected frames included)."""
+    B = 13
+    s = rs.PoseOptimization(max_batch=B, max_matches=M)
+    truth, cur, matches, n = rs.synth.pose_batch(900, B, M)
+    n = n.copy()
+    n[5] = 2                                                   # a frame RANSAC rejects
+    want, wmask = s.compute_optimized_pose(cur, matches, n, s.options(seed=21, rng_mode=rs.abi.RS_RNG_DEVICE))
+    got, gmask = s.compute_optimized_pose(cur, matches, n, s.options(seed=21, rng_mode=rs.abi.RS_RNG_DEVICE, sub_batches=groups))
+    assert (want["status"] == 1).sum() >= B - 1 and want["status"][5] != 1
+    assert want.tobytes() == got.tobytes() and wmask.tobytes() == gmask.tobytes()
+    s.close()
