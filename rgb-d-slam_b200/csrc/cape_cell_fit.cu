@@ -216,7 +216,10 @@ __global__ void __launch_bounds__(WARPS * 32, RS_K1_MIN_CTAS)
         const double* kyrow = prm.ky + cr * CS;
         const float* tile = reinterpret_cast<const float*>(wbase + slot * Geo::BOX_BYTES);
         const float* ctile = tile + c * CS;            // this cell's columns inside a box row
-        const int colbase = (c0 + c) * CS;
+        // first image column of this lane's cell. When the cell grid is not a multiple of the 8-cell item, the cells of the last
+        // item that hang over the image (TMA zero-fills their pixels, their records are never written) must not index the
+        // factor tables past their end: they borrow the last real cell's columns.
+        const int colbase = min(c0 + c, prm.hc - 1) * CS;
         mbar_wait_a(bar_a + slot * 8, (q >> 1) & 1);
 
         // ---- branch-free accumulation of this lane's float4s of the box ----
