@@ -1,3 +1,5 @@
+"""Times K1 alone (K1a cape_cell_fit_kernel + K1b cape_cell_finish_kernel) on 256 resident 640x480 frames: 20 launches between two
+CUDA events after 3 warm-up launches. Usage (GPU box): python tools/k1_time.py. Used by tools/exp_k1_variants.sh."""
 import sys; sys.path.insert(0,'.')
 import numpy as np, torch, rgbd_slam_b200 as rs
 F=256

@@ -1,3 +1,7 @@
+// NOTE (round 1, later): probes 0 and 9-11 below feed the converted / multiplied values from registers that never change inside
+// the loop, so the compiler hoists the conversion / FMUL / IMAD out of it and only the FP64 op is timed; they read too
+// optimistic. tools/microbench2.cu (inline PTX, loop-carried dependencies) is the probe the design relies on.
+//
 // Pipe-throughput probe for the K1 design decision (SURVEY.md §7 "Instruction budget"): how fast are
 // F2F.F64.F32 / F2F.F32.F64 / DADD / DMUL / DFMA / FFMA per SM on this B200? Run under gpurun.
 #include <cuda_runtime.h>
