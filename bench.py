@@ -3,11 +3,13 @@
 
   python bench.py --gpus N --steps K --warmup W            # this framework on N B200s (torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  # the CPU path (restated oracle) on the host cores
+  python bench.py --config 5 ...                           # BASELINE configs[4]: 1280x960 / 40 px cells / 1024 hypotheses
 
-A "step" = one pass of the hot path over one batch of synthetic 640x480 RGB-D frames per GPU (BASELINE.json
-configs[2]/[3]: full frame = CAPE plane + cylinder extraction, then the 300-point / 20-plane RANSAC-LM pose solve
-with its 100-sample Monte-Carlo covariance). Frames shard across ranks with no data-path collective; the single
-collective is the all-gather of the per-frame poses (weak scaling: frames per GPU fixed).
+A "step" = one pass of the hot path over one batch of synthetic RGB-D frames per GPU. The headline workload is BASELINE.json
+configs[2] on configs[3]'s batch (640x480, 20 px cells, 300-point / 20-plane RANSAC-LM solve with its 100-sample
+Monte-Carlo covariance, 256 frames per GPU per step); `--config 5` times configs[4] as the headline instead, and a default
+run carries a shorter measurement of it under the `config5` key. Frames shard across ranks with no data-path collective;
+the single collective is the all-gather of the per-frame poses (weak scaling: frames per GPU fixed).
 Prints ONE JSON line on rank 0 (see README / DESIGN.md "Measurement")."""
 import argparse
 import ctypes as C
@@ -16,6 +18,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -23,11 +26,49 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, CELL = 640, 480, 20
-N_CELLS = (W // CELL) * (H // CELL)
 N_POINTS, N_PLANES = 300, 20
 MAX_MATCHES = N_POINTS + N_PLANES
-K1_BYTES_PER_FRAME = 4 * W * H + 160 * N_CELLS  # depth read once + one 160 B record per cell
+
+
+class Workload:
+    """Geometry + solver sizes of one BASELINE config."""
+
+    def __init__(self, name, width, height, cell, hypotheses, frames_per_gpu, outlier_frac=0.1):
+        self.name, self.W, self.H, self.cell, self.hypotheses, self.F = name, width, height, cell, hypotheses, frames_per_gpu
+        # share of wrong matches among the correspondences. The reference's RANSAC stops as soon as (from the fourth
+        # hypothesis on) one has more than 80 % inliers: with 10 % outliers that is after 4-7 hypotheses whatever the cap is,
+        # so the "1024 hypotheses per frame" config is given 30 % outliers - the early stop can then never fire and every
+        # frame evaluates all 1024 hypotheses (check.mean_ransac_iterations in the output says what ran).
+        self.outlier_frac = outlier_frac
+        self.scale = width / 640.0
+        self.K = (550.0 * self.scale, 550.0 * self.scale, 320.0 * self.scale, 240.0 * self.scale)
+        self.n_cells = (width // cell) * (height // cell)
+        # SURVEY.md §8(d): depth read once + one 160-byte record per cell
+        self.k1_bytes_per_frame = 4 * width * height + 160 * self.n_cells
+
+    def config(self):
+        """The `config` object of the JSON line: the workload only, identical for both arms (--impl b200 / reference)."""
+        return {
+            "workload": "%dx%d full frame: CAPE plane+cylinder extraction (%d px cells) + %d-point/%d-plane RANSAC-LM pose solve "
+                        "(%d hypotheses) + 100-sample covariance (%s), batch of %d frames per GPU per step"
+                        % (self.W, self.H, self.cell, N_POINTS, N_PLANES, self.hypotheses, self.name, self.F),
+            "width": self.W, "height": self.H, "cell_px": self.cell, "cells_per_frame": self.n_cells,
+            "points": N_POINTS, "planes": N_PLANES, "outlier_fraction": self.outlier_frac,
+            "ransac_hypotheses": self.hypotheses, "n_variance": 100,
+            "frames_per_gpu": self.F,
+            "l2": "inputs larger than L2 (%.0f MB of depth per step per GPU vs 126 MB)" % (4e-6 * self.W * self.H * self.F),
+        }
+
+
+def workload_for(args):
+    if args.config == 5:
+        wl = Workload("BASELINE configs[4]", 1280, 960, 40, 1024, args.frames_per_gpu or 64, outlier_frac=0.3)
+    else:
+        wl = Workload("BASELINE configs[2] on configs[3]'s batch", 640, 480, 20, 119, args.frames_per_gpu or 256)
+    if args.width or args.height or args.cell or args.hypotheses:
+        wl = Workload("custom", args.width or wl.W, args.height or wl.H, args.cell or wl.cell, args.hypotheses or wl.hypotheses, wl.F,
+                      wl.outlier_frac)
+    return wl
 
 
 def parse_args():
@@ -36,23 +77,38 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--frames-per-gpu", type=int, default=256)
+    p.add_argument("--config", type=int, default=4, choices=[4, 5],
+                   help="BASELINE.md §4 row: 4 = 640x480 / 20 px / 119 hypotheses / 256 frames per GPU (default), "
+                        "5 = 1280x960 / 40 px / 1024 hypotheses / 64 frames per GPU")
+    p.add_argument("--width", type=int, default=0)
+    p.add_argument("--height", type=int, default=0)
+    p.add_argument("--cell", type=int, default=0)
+    p.add_argument("--hypotheses", type=int, default=0)
+    p.add_argument("--frames-per-gpu", type=int, default=0)
     p.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 10))")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--pose-groups", type=int, default=1,
                    help="rs_pose_opts.sub_batches: frame groups whose RANSAC -> Monte-Carlo chains run on separate streams")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-e2e-lanes", action="store_true", help="skip the two-batches-in-flight variant of the host-buffer leg")
+    p.add_argument("--no-config5", action="store_true", help="skip the secondary configs[4] measurement of a default run")
+    p.add_argument("--no-extras", action="store_true", help="skip the informational legs (single frame, rectify, Kalman, lanes)")
     return p.parse_args()
 
 
-def make_inputs(first_frame, n_frames):
+def make_inputs(wl, first_frame, n_frames):
     import rgbd_slam_b200 as rs
-    depth = np.empty((n_frames, H, W), dtype=np.float32)
+    depth = np.empty((n_frames, wl.H, wl.W), dtype=np.float32)
     for i in range(n_frames):
-        depth[i] = rs.synth.scene_v0_depth(first_frame + i)
-    truth, cur, matches, n = rs.synth.pose_batch(first_frame, n_frames, MAX_MATCHES, n_points=N_POINTS, n_planes=N_PLANES)
+        depth[i] = rs.synth.scene_v0_depth(first_frame + i, wl.W, wl.H)
+    truth, cur, matches, n = pose_inputs(wl, first_frame, n_frames)
     return depth, truth, cur, matches, n
+
+
+def pose_inputs(wl, first_frame, n_frames):
+    import rgbd_slam_b200 as rs
+    return rs.synth.pose_batch(first_frame, n_frames, MAX_MATCHES, n_points=N_POINTS, n_planes=N_PLANES, scale=wl.scale,
+                               outlier_frac=wl.outlier_frac)
 
 
 class ClockSampler:
@@ -105,48 +161,232 @@ class ClockSampler:
         return out
 
 
-def cpu_port_frames_per_s(depth, cur, matches, n, n_threads, frames=None):
+def cpu_port_frames_per_s(wl, depth, cur, matches, n, n_threads, frames=None):
     """Times the CPU oracle (restated reference path: CAPE + RANSAC/LM pose + covariance) on `frames` frames."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     lib = ol.load()
     B = len(depth) if frames is None else min(frames, len(depth))
-    K = np.array([550.0, 550.0, 320.0, 240.0])
+    K = np.array(wl.K)
     poses = np.zeros((B, 7))
-    sec = lib.orc_process_frames(W, H, CELL, K.ctypes.data, depth.ctypes.data, cur.ctypes.data, matches.ctypes.data,
-                                 n.ctypes.data, MAX_MATCHES, B, 1, 1, 119, 100, 0, n_threads, poses.ctypes.data)
+    sec = lib.orc_process_frames(wl.W, wl.H, wl.cell, K.ctypes.data, depth.ctypes.data, cur.ctypes.data, matches.ctypes.data,
+                                 n.ctypes.data, MAX_MATCHES, B, 1, 1, wl.hypotheses, 100, 0, n_threads, poses.ctypes.data)
     return B / sec, sec, B
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path. The reference binary cannot be built
     (Eigen / OpenCV C++ / TBB / boost / flann absent, no network), so this is the restated oracle, all host threads
-    over the frame loop (the reference's TBB build parallelises the RANSAC / variance loops instead)."""
+    over the frame loop (the reference's TBB build parallelises the RANSAC / variance loops instead).
+    Protocol: >= 10 warm-up frames, then `steps` timed samples whose MEDIAN gives the value, >= 100 timed
+    frames in total; a sample = `sample` frames of the arm's workload, sized so that the run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = workload_for(args)
     threads = os.cpu_count() or 1
-    sample = min(args.frames_per_gpu, 64)
-    depth, truth, cur, matches, n = make_inputs(0, sample)
-    for _ in range(max(args.warmup, 1)):
-        cpu_port_frames_per_s(depth, cur, matches, n, threads)
+    sample = min(wl.F, 64 if wl.W <= 640 else 16)
+    steps = max(args.steps, (100 + sample - 1) // sample)
+    depth, truth, cur, matches, n = make_inputs(wl, 0, sample)
+    for _ in range(max(args.warmup, (10 + sample - 1) // sample)):
+        cpu_port_frames_per_s(wl, depth, cur, matches, n, threads)
+    secs = []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_port_frames_per_s(depth, cur, matches, n, threads)
-    sec = time.perf_counter() - t0
-    fps = sample * args.steps / sec
+    for _ in range(steps):
+        secs.append(cpu_port_frames_per_s(wl, depth, cur, matches, n, threads)[1])
+    wall = time.perf_counter() - t0
+    med = float(np.median(secs))
+    fps = sample / med
     line = {
-        "impl": "reference", "metric": "RGB-D frames/sec (640x480)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+        "impl": "reference", "metric": "RGB-D frames/sec (%dx%d)" % (wl.W, wl.H), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * med, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "640x480 full frame: CAPE plane+cylinder extraction + 300-point/20-plane RANSAC-LM pose "
-                               "solve + 100-sample covariance (BASELINE configs[2])", "frames_per_step": sample},
+        "config": wl.config(),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d synthetic frames per step, frame loop over %d host threads" % (sample, threads)},
+                         "sample": "%d synthetic frames per timed sample, frame loop over %d host threads; median of %d samples "
+                                   "(%d timed frames, %.1f s wall; mean-based value %.1f frames/s)"
+                                   % (sample, threads, steps, sample * steps, wall, sample * steps / float(np.sum(secs)))},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+class _DevPtr:  # zero-copy torch view of a library-owned device buffer
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def bind_host_threads(local_rank, world):
+    """Spreads the ranks of one box over disjoint sets of host cores (the e2e leg is fed by host threads: pinned-buffer
+    writers, the copy engines' submission threads). Returns the cores this rank may use."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(len(cores) // max(world, 1), 1)
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+def measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, warmup, extras):
+    """The HBM-resident leg of one workload: inputs live on the device before the timed region. Returns a dict."""
+    F = wl.F
+    depth, truth, cur, matches, n = make_inputs(wl, rank * F, F)
+    det = rs.PrimitiveDetection(wl.W, wl.H, wl.cell, *wl.K, max_batch=F, device=local_rank)
+    solver = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=wl.hypotheses, max_variance=100, device=local_rank)
+    opts = solver.options(max_iterations=wl.hypotheses, seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE, sub_batches=args.pose_groups,
+                          intrinsics=wl.K)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    d_depth = torch.from_numpy(depth).cuda()
+    solver.upload(cur, matches, n)
+    poses_view = torch.as_tensor(_DevPtr(solver.device_poses_ptr(), (F, 7)), device="cuda")
+    pose_stream = torch.cuda.Stream()
+    pptr = pose_stream.cuda_stream
+    # The collective is off the step's critical path: the poses of step i are copied (7 doubles per frame) into one of two
+    # staging buffers at the end of the pose chain, and the all-gather of that buffer is issued on a side stream that
+    # nothing waits for until the buffer comes round again two steps later - the next step's K1 starts at once.
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    staged = [torch.zeros((F, 7), dtype=torch.float64, device="cuda") for _ in range(2)]
+    gathered = [torch.zeros((world, F, 7), dtype=torch.float64, device="cuda") for _ in range(2)]
+    comm_done = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    comm_start = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    counter = [0]
+    comm_ms = []
+
+    def step():
+        # CAPE and the pose solve of a frame are independent (the reference runs find_primitives on its own thread):
+        # K1 (HBM bound) runs alone, then the latency-bound segmentation (main stream) and the pose chain (pose stream)
+        # share the SMs; the main stream joins the pose stream before the next step.
+        i = counter[0] & 1
+        counter[0] += 1
+        det.run_device(d_depth.data_ptr(), F, seed=0, stream=sptr)
+        det.stream_wait_fit(pptr)
+        solver.solve_device(F, opts, stream=pptr)
+        if world > 1:
+            with torch.cuda.stream(pose_stream):
+                if counter[0] > 2:
+                    pose_stream.wait_event(comm_done[i])   # the gather that read staged[i] two steps ago
+                staged[i].copy_(poses_view)
+            comm_stream.wait_stream(pose_stream)
+            with torch.cuda.stream(comm_stream):
+                comm_start[i].record(comm_stream)
+                dist.all_gather_into_tensor(gathered[i].view(-1), staged[i].view(-1))
+                comm_done[i].record(comm_stream)
+        stream.wait_stream(pose_stream)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    det.set_timing(steps)
+    solver.set_timing(steps)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = rs.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    if world > 1:
+        stream.wait_stream(comm_stream)   # the timed region ends when the last gather has landed
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = rs.launch_count() - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        comm_ms = [comm_start[k].elapsed_time(comm_done[k]) for k in range(2)]
+    k1_ms = float(np.mean([det.kernel_ms(s)[0] for s in range(steps)]))
+    seg_ms = float(np.mean([det.kernel_ms(s)[1] for s in range(steps)]))
+    pose_ms = np.mean([solver.kernel_ms(s) for s in range(steps)], axis=0)
+    det.set_timing(0)
+    solver.set_timing(0)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * F * steps / (ms_total * 1e-3)
+
+    # sanity: the timed work produced valid poses close to the synthetic truth
+    out, _ = solver.download(F)
+    ok_frac = float((out["status"] == 1).mean())
+    pos_err = float(np.median(np.linalg.norm(out["pose"][:, :3] - truth[:, :3], axis=1)))
+    check = {"frames_with_valid_pose": ok_frac, "median_position_error_mm": pos_err,
+             "mean_ransac_iterations": float(out["iterations_run"].mean())}
+
+    # ---- N > 1: the collective delivered what the ranks computed, and a shard equals a single-GPU run of the same frames ----
+    if world > 1:
+        last = (counter[0] - 1) & 1
+        mine_ok = bool(torch.equal(gathered[last][rank], poses_view))
+        # every rank holds the same gathered tensor (bitwise): compare a checksum of the bytes across ranks
+        bits = gathered[last].view(torch.int64)
+        digest = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device="cuda").view_as(bits)).sum()])
+        dmin, dmax = digest.clone(), digest.clone()
+        dist.all_reduce(dmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        same_everywhere = bool(torch.equal(dmin, dmax))
+        flags = torch.tensor([int(mine_ok)], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        shard_ok = None
+        if rank == 0:
+            # rank 0 re-solves the shard of the LAST rank (its frame indices, its seed) on its own GPU: byte-identical poses
+            r = world - 1
+            _, cur_r, m_r, n_r = pose_inputs(wl, r * F, F)
+            solver.upload(cur_r, m_r, n_r)
+            opts_r = solver.options(max_iterations=wl.hypotheses, seed=1234 + r, rng_mode=rs.abi.RS_RNG_DEVICE,
+                                    sub_batches=args.pose_groups, intrinsics=wl.K)
+            solver.solve_device(F, opts_r, stream=pptr)
+            torch.cuda.synchronize()
+            shard_ok = bool(torch.equal(gathered[last][r], poses_view))
+            solver.upload(cur, matches, n)
+        check["multi_gpu"] = {"gathered_rank_slices_equal_local_poses_on_every_rank": bool(flags.item() == 1),
+                              "gathered_tensor_bitwise_equal_on_every_rank": same_everywhere,
+                              "last_rank_shard_equals_single_gpu_rerun_on_rank0": shard_ok}
+        if not (flags.item() == 1 and same_everywhere and shard_ok in (None, True)):
+            raise SystemExit("multi-GPU correctness check failed: %r" % (check["multi_gpu"],))
+
+    res = {"wl": wl, "value": value, "ms_per_step": ms_total / steps, "steps": steps, "launches": int(launches), "clocks": clocks,
+           "k1_ms": k1_ms, "seg_ms": seg_ms, "pose_ms": [float(v) for v in pose_ms], "check": check,
+           "comm_ms": comm_ms, "F": F}
+    ctx = dict(det=det, solver=solver, opts=opts, d_depth=d_depth, depth=depth, truth=truth, cur=cur, matches=matches, n=n,
+               stream=stream, pose_stream=pose_stream, poses_view=poses_view)
+    if extras:
+        return res, ctx
+    det.close()
+    solver.close()
+    del d_depth
+    return res, None
+
+
+def roofline_of(wl, res):
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = wl.k1_bytes_per_frame * res["F"] / (res["k1_ms"] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json" if wl.cell == 20 else "k1_traffic_cell%d.json" % wl.cell)
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("frames_per_launch") == res["F"]:
+            traffic = tj.get("dram_bytes_per_launch")
+    return {"kernel": "cape_cell_fit (K1a + K1b)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "bytes_per_launch": wl.k1_bytes_per_frame * res["F"], "ms_per_launch": res["k1_ms"]}
+
+
+def kernels_of(res):
+    p = res["pose_ms"]
+    return {"cape_cell_fit": res["k1_ms"], "cape_segment": res["seg_ms"], "pose_prepare": p[0], "pose_ransac_final_lm": p[1],
+            "pose_variance": p[2], "pose_covariance": p[3]}
 
 
 def main():
@@ -166,83 +406,25 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    host_cores = bind_host_threads(local_rank, world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    F = args.frames_per_gpu
+    wl = workload_for(args)
+    F = wl.F
+    W, H = wl.W, wl.H
     steps, warmup = args.steps, max(args.warmup, 3)
-    depth, truth, cur, matches, n = make_inputs(rank * F, F)
-
-    det = rs.PrimitiveDetection(W, H, CELL, max_batch=F, device=local_rank)
-    solver = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=119, max_variance=100, device=local_rank)
-    opts = solver.options(seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE, sub_batches=args.pose_groups)
-
-    # ---- HBM-resident leg: inputs live on the device before the timed region ----
-    stream = torch.cuda.current_stream()
-    sptr = stream.cuda_stream
-    d_depth = torch.from_numpy(depth).cuda()
-    solver.upload(cur, matches, n)
-    gathered = torch.zeros((world, F, 7), dtype=torch.float64, device="cuda")
-
-    class _DevPtr:  # zero-copy torch view of the library's pose buffer (the all-gather payload)
-        def __init__(self, ptr, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3}
-    poses_view = torch.as_tensor(_DevPtr(solver.device_poses_ptr(), (F, 7)), device="cuda")
-
-    pose_stream = torch.cuda.Stream()
-    pptr = pose_stream.cuda_stream
-
-    def step():
-        # CAPE and the pose solve of a frame are independent (the reference runs find_primitives on its own thread):
-        # K1 (HBM bound) runs alone, then the latency-bound segmentation (main stream) and RANSAC / LM (pose stream)
-        # share the SMs; the main stream joins the pose stream before the collective / the next step. (Measured: starting
-        # the pose chain beside K1a instead costs 3 % - K1a's issue pressure stretches the latency-bound RANSAC 0.61 -> 0.87 ms; holding the
-        # segmentation back until RANSAC is over (cell_fit_device / stream_wait_ransac / segment_device) gives RANSAC its 0.53 ms
-        # but the one-warp segmentation CTAs then queue behind the Monte-Carlo kernel's shared memory: 1.95 ms per step.)
-        det.run_device(d_depth.data_ptr(), F, seed=0, stream=sptr)
-        det.stream_wait_fit(pptr)
-        solver.solve_device(F, opts, stream=pptr)
-        stream.wait_stream(pose_stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), poses_view.view(-1))
-
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    det.set_timing(steps)
-    solver.set_timing(steps)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = rs.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = rs.launch_count() - launches0
-    clocks = sampler.stop()
-    k1_ms = float(np.mean([det.kernel_ms(s)[0] for s in range(steps)]))
-    seg_ms = float(np.mean([det.kernel_ms(s)[1] for s in range(steps)]))
-    pose_ms = np.mean([solver.kernel_ms(s) for s in range(steps)], axis=0)
-    det.set_timing(0)
-    solver.set_timing(0)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * F * steps / (ms_total * 1e-3)
+    res, ctx = measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, warmup, extras=True)
+    det, solver, opts, d_depth = ctx["det"], ctx["solver"], ctx["opts"], ctx["d_depth"]
+    depth, cur, matches, n = ctx["depth"], ctx["cur"], ctx["matches"], ctx["n"]
+    stream, pose_stream = ctx["stream"], ctx["pose_stream"]
+    sptr, pptr = stream.cuda_stream, pose_stream.cuda_stream
+    extras = rank == 0 and not args.no_extras
 
     # ---- one frame at a time (BASELINE configs[1] / [2] at batch = 1: what the reference's per-frame track() call sees) ----
     single = None
-    if rank == 0:
+    if extras:
         def one_frame(cape=True, pose=True):
             if cape:
                 det.run_device(d_depth.data_ptr(), 1, seed=0, stream=sptr)
@@ -254,25 +436,25 @@ def main():
                 solver.solve_device(1, opts, stream=pptr)
                 stream.wait_stream(pose_stream)
 
-        def time_frames(n, **kw):
+        def time_frames(nf, **kw):
             for _ in range(5):
                 one_frame(**kw)
             torch.cuda.synchronize()
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            for _ in range(n):
+            for _ in range(nf):
                 one_frame(**kw)
             b_.record(stream)
             torch.cuda.synchronize()
-            return a.elapsed_time(b_) / n
+            return a.elapsed_time(b_) / nf
         ms_cape, ms_pose, ms_full = time_frames(50, pose=False), time_frames(50, cape=False), time_frames(50)
         single = {"cape_ms": ms_cape, "pose_ms": ms_pose, "full_frame_ms": ms_full, "frames_per_s": 1e3 / ms_full,
                   "note": "batch = 1, inputs resident, back-to-back frames on one GPU: CAPE plane + cylinder extraction (configs[1]), "
-                          "the 300-point / 20-plane RANSAC-LM solve with its covariance, and both overlapped (configs[2])"}
+                          "the RANSAC-LM solve with its covariance, and both overlapped (configs[2])"}
 
     # ---- rectify_depth (the step in front of the path, off in the headline workload as in examples/main_TUM.cpp) ----
     rect = None
-    if rank == 0:
+    if extras:
         det.set_rectification(None, enable=True)
         d_rect = torch.empty_like(d_depth)
         for _ in range(2):
@@ -284,21 +466,26 @@ def main():
         r1.record(stream)
         torch.cuda.synchronize()
         rect_ms = r0.elapsed_time(r1) / 5
-        rect_bytes = (4 + 8 + 8 + 8 + 4) * W * H * F   # depth read, key memset, key RMW, key read, float write
-        rect = {"ms_per_batch": rect_ms, "frames": F, "algorithmic_GBps": rect_bytes / (rect_ms * 1e-3) / 1e9,
-                "bytes_per_pixel": 32, "note": "rs_cape_rectify_device: key memset + scatter (64-bit atomicMax) + resolve"}
+        rect_alg = 8 * W * H * F   # algorithmic: the depth image read once, the rectified image written once
+        rect = {"ms_per_batch": rect_ms, "frames": F, "algorithmic_bytes_per_pixel": 8,
+                "algorithmic_GBps": rect_alg / (rect_ms * 1e-3) / 1e9,
+                "note": "rs_cape_rectify_device; achieved = 8 B/pixel (depth read + rectified depth written) / time; the scatter's own "
+                        "key traffic is implementation cost, not counted"}
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            rect["frac_of_hbm_peak"] = rect["algorithmic_GBps"] / float(json.load(open(peaks_path))["hbm_gbs"])
         det.set_rectification(None, enable=False)
         del d_rect
 
     # ---- Kalman update of the matched map features (the step after the pose solve) ----
     kalman = None
-    if rank == 0:
+    if extras:
         lib = rs.load()
         rng = np.random.default_rng(0)
         npt, npl = F * N_POINTS, F * N_PLANES
 
-        def spd(n, d, scale, floor):
-            a = rng.standard_normal((n, d, d)) * scale
+        def spd(cnt, d, scale, floor):
+            a = rng.standard_normal((cnt, d, d)) * scale
             return a @ a.transpose(0, 2, 1) + np.eye(d) * floor
         px = rng.uniform(-3000, 3000, (npt, 3))
         pz = px + rng.standard_normal((npt, 3)) * 4
@@ -333,12 +520,12 @@ def main():
                   "note": "rs_kalman_track_points_device + rs_kalman_track_planes_device on the matched features of one %d-frame batch" % F}
 
     # ---- informational: two batches in flight (a second context pair, steps dealt alternately, no cross-lane sync):
-    # the throughput-bound kernels of one batch (K1, Monte-Carlo LM) fill the SMs the latency-bound ones of the other
-    # (segmentation, RANSAC) leave idle. Not the headline: a step's latency doubles and K1 no longer runs alone. ----
+    # the throughput-bound kernels of one batch fill the SMs the latency-bound ones of the other leave idle. Not the
+    # headline: a step's latency doubles and K1 no longer runs alone. ----
     pipelined = None
-    if rank == 0 and world == 1 and not args.no_e2e:
-        det2 = rs.PrimitiveDetection(W, H, CELL, max_batch=F, device=local_rank)
-        solver2 = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=119, max_variance=100, device=local_rank)
+    if extras and world == 1 and not args.no_e2e:
+        det2 = rs.PrimitiveDetection(W, H, wl.cell, *wl.K, max_batch=F, device=local_rank)
+        solver2 = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=wl.hypotheses, max_variance=100, device=local_rank)
         solver2.upload(cur, matches, n)
         d_depth2 = d_depth.clone()
         s2, p2 = torch.cuda.Stream(), torch.cuda.Stream()
@@ -367,204 +554,197 @@ def main():
                      "note": "two %d-frame batches in flight on two context / stream pairs, inputs resident" % F}
         det2.close()
         solver2.close()
+        del d_depth2
 
-    # sanity: the timed work produced valid poses close to the synthetic truth
-    out, _ = solver.download(F)
-    ok_frac = float((out["status"] == 1).mean())
-    pos_err = float(np.median(np.linalg.norm(out["pose"][:, :3] - truth[:, :3], axis=1)))
-
-    # ---- end-to-end leg: host (pinned) buffers through the public host API, copies inside the timed region ----
+    # ---- end-to-end leg: host (pinned) buffers through the public host API, copies inside the timed region.
+    # The SAME two modes are measured at every N: one blocking call at a time, and two batches in flight (two host threads per
+    # rank, each calling the blocking entry points on its own contexts and pinned buffers); e2e.value is the larger. ----
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps or min(steps, 10)
-        h_depth = torch.from_numpy(depth).pin_memory()
-        h_depth_np = h_depth.numpy()
-        arrs, st = rs.abi.alloc_cape_outputs(F, det.n_cells, det.max_boundary)
         wanted = ("plane_labels", "cyl_labels", "planes", "cyls", "boundary_xyz", "info")
-        pinned = {}
-        for k in wanted:  # results land in pinned host memory
-            tns = torch.empty(arrs[k].nbytes, dtype=torch.uint8).pin_memory()
-            pinned[k] = tns
-            arrs[k] = tns.numpy().view(arrs[k].dtype).reshape(arrs[k].shape)
-        st = rs.abi.CapeOutputs(**{k: arrs[k].ctypes.data for k in wanted})
-        h_matches = torch.from_numpy(matches.view(np.uint8).reshape(F, -1)).pin_memory()
-        h_matches_np = h_matches.numpy().view(rs.abi.match_dtype).reshape(F, MAX_MATCHES)
 
-        h_pose_out = torch.empty(F * rs.abi.pose_out_dtype.itemsize, dtype=torch.uint8).pin_memory()
-        h_pose_out_np = h_pose_out.numpy().view(rs.abi.pose_out_dtype)
-        h_mask = torch.empty((F, MAX_MATCHES), dtype=torch.uint8).pin_memory()
-        h_mask_np = h_mask.numpy()
+        class Lane:
+            def __init__(self, dt, sv):
+                self.det, self.solver = dt, sv
+                self.h_depth = torch.from_numpy(depth).pin_memory()
+                self.h_depth_np = self.h_depth.numpy()
+                self.h_d16 = torch.from_numpy(np.clip(np.rint(depth), 0, 65535).astype(np.uint16)).pin_memory()
+                self.h_d16_np = self.h_d16.numpy()
+                arrs, _ = rs.abi.alloc_cape_outputs(F, dt.n_cells, dt.max_boundary)
+                self.pinned = {}
+                for k in wanted:  # results land in pinned host memory
+                    tns = torch.empty(arrs[k].nbytes, dtype=torch.uint8).pin_memory()
+                    self.pinned[k] = tns
+                    arrs[k] = tns.numpy().view(arrs[k].dtype).reshape(arrs[k].shape)
+                self.arrs = arrs
+                self.st = rs.abi.CapeOutputs(**{k: arrs[k].ctypes.data for k in wanted})
+                self.h_matches = torch.from_numpy(matches.view(np.uint8).reshape(F, -1).copy()).pin_memory()
+                self.h_matches_np = self.h_matches.numpy().view(rs.abi.match_dtype).reshape(F, MAX_MATCHES)
+                self.h_pose_out = torch.empty(F * rs.abi.pose_out_dtype.itemsize, dtype=torch.uint8).pin_memory()
+                self.h_pose_out_np = self.h_pose_out.numpy().view(rs.abi.pose_out_dtype)
+                self.h_mask = torch.empty((F, MAX_MATCHES), dtype=torch.uint8).pin_memory()
+                self.h_mask_np = self.h_mask.numpy()
 
-        def e2e_step():
-            # the public host API: the pose solve is enqueued first (its copies and kernels run in the shadow of the
-            # depth upload), find_primitives streams the batch through the GPU in chunks, then the solve is joined
-            solver.compute_optimized_pose_begin(cur, h_matches_np, n, opts, out=h_pose_out_np, mask=h_mask_np)
-            det.find_primitives(h_depth_np, seed=0, out=(arrs, st))
-            o, m = solver.compute_optimized_pose_end()
+            def step(self, u16, o=opts):
+                # the public host API: the pose solve is enqueued first (its copies and kernels run in the shadow of the
+                # depth upload), find_primitives streams the batch through the GPU in chunks, then the solve is joined
+                self.solver.compute_optimized_pose_begin(cur, self.h_matches_np, n, o, out=self.h_pose_out_np, mask=self.h_mask_np)
+                if u16:
+                    self.det.find_primitives_u16(self.h_d16_np, alpha=1.0, seed=0, out=(self.arrs, self.st))
+                else:
+                    self.det.find_primitives(self.h_depth_np, seed=0, out=(self.arrs, self.st))
+                return self.solver.compute_optimized_pose_end()[0]
+
+        lane_a = Lane(det, solver)
+
+        def timed(fn, nsteps):
+            torch.cuda.synchronize()
             if world > 1:
-                dist.all_gather_into_tensor(gathered.view(-1), poses_view.view(-1))
-                torch.cuda.synchronize()
-            return o
+                dist.barrier()
+            t0 = time.perf_counter()
+            fn(nsteps)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
 
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            o = e2e_step()
-        torch.cuda.synchronize()
-        sec = time.perf_counter() - t0
-        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
-        # same leg from the raw CV_16U sensor image (the reference's examples convertTo(CV_32F) on the host first)
-        h_d16 = torch.from_numpy(np.clip(np.rint(depth), 0, 65535).astype(np.uint16)).pin_memory()
-        h_d16_np = h_d16.numpy()
-
-        def e2e_u16_step():
-            solver.compute_optimized_pose_begin(cur, h_matches_np, n, opts, out=h_pose_out_np, mask=h_mask_np)
-            det.find_primitives_u16(h_d16_np, alpha=1.0, seed=0, out=(arrs, st))
-            return solver.compute_optimized_pose_end()[0]
-
-        for _ in range(2):
-            e2e_u16_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_u16_step()
-        torch.cuda.synchronize()
-        t16 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
-        sec16 = float(t16.item())
-        h2d = int(h_depth_np.nbytes + h_matches_np.nbytes + cur.nbytes + n.nbytes)
-        d2h = int(sum(arrs[k].nbytes for k in wanted) + o.nbytes + F * MAX_MATCHES)
-        e2e = {"value": world * F * e2e_steps / sec, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e2e_steps,
-               "u16_depth": {"value": world * F * e2e_steps / sec16, "unit": "frames/s",
-                             "h2d_bytes_per_step": int(h_d16_np.nbytes + h_matches_np.nbytes + cur.nbytes + n.nbytes),
-                             "note": "rs_cape_run_u16: CV_16U sensor image, convertTo(CV_32F) on the device"},
-               "timing": "host wall clock around the C-ABI calls (pose solve begin -> find_primitives, chunk-pipelined copies -> pose solve end), max over ranks",
-               "mode": "one blocking call at a time"}
-
-        # ---- the same host API with two batches in flight: two host threads, each with its own contexts and pinned
-        # buffers, call the blocking entry points (ctypes releases the GIL); the upload of one batch overlaps the
-        # compute / download tail of the other. Every step still copies its inputs up and its results down. ----
-        if world == 1 and not args.no_e2e_lanes:
-            import threading
-            det_b = rs.PrimitiveDetection(W, H, CELL, max_batch=F, device=local_rank)
-            solver_b = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=119, max_variance=100, device=local_rank)
-            h_depth_b = h_depth.clone().pin_memory()
-            h_d16_b = h_d16.clone().pin_memory()
-            arrs_b, _ = rs.abi.alloc_cape_outputs(F, det_b.n_cells, det_b.max_boundary)
-            pinned_b = {}
-            for k in wanted:
-                tns = torch.empty(arrs_b[k].nbytes, dtype=torch.uint8).pin_memory()
-                pinned_b[k] = tns
-                arrs_b[k] = tns.numpy().view(arrs_b[k].dtype).reshape(arrs_b[k].shape)
-            st_b = rs.abi.CapeOutputs(**{k: arrs_b[k].ctypes.data for k in wanted})
-            h_matches_b = h_matches.clone().pin_memory()
-            h_matches_b_np = h_matches_b.numpy().view(rs.abi.match_dtype).reshape(F, MAX_MATCHES)
-            h_pose_out_b = torch.empty(F * rs.abi.pose_out_dtype.itemsize, dtype=torch.uint8).pin_memory()
-            h_mask_b = torch.empty((F, MAX_MATCHES), dtype=torch.uint8).pin_memory()
-            lanes_h = [
-                (det, solver, h_depth_np, h_d16_np, (arrs, st), h_matches_np, h_pose_out_np, h_mask_np),
-                (det_b, solver_b, h_depth_b.numpy(), h_d16_b.numpy(), (arrs_b, st_b), h_matches_b_np,
-                 h_pose_out_b.numpy().view(rs.abi.pose_out_dtype), h_mask_b.numpy()),
-            ]
-
-            def lane_worker(lane, u16, nsteps, gate):
-                dt, sv, hd, hd16, outp, hm, hpo, hmk = lanes_h[lane]
-                torch.cuda.set_device(local_rank)
-                gate.wait()
+        def one_at_a_time(u16, o=opts):
+            def run(nsteps):
                 for _ in range(nsteps):
-                    sv.compute_optimized_pose_begin(cur, hm, n, opts, out=hpo, mask=hmk)
-                    if u16:
-                        dt.find_primitives_u16(hd16, alpha=1.0, seed=0, out=outp)
-                    else:
-                        dt.find_primitives(hd, seed=0, out=outp)
-                    sv.compute_optimized_pose_end()
+                    lane_a.step(u16, o)
+            return run
 
-            def run_lanes(u16, nsteps):
-                gate = threading.Barrier(3)
-                th = [threading.Thread(target=lane_worker, args=(i, u16, nsteps, gate)) for i in range(2)]
-                for t_ in th:
-                    t_.start()
-                gate.wait()
-                t0_ = time.perf_counter()
-                for t_ in th:
-                    t_.join()
-                torch.cuda.synchronize()
-                return time.perf_counter() - t0_
+        timed(one_at_a_time(False), 2)
+        sec = timed(one_at_a_time(False), e2e_steps)
+        timed(one_at_a_time(True), 2)
+        sec16 = timed(one_at_a_time(True), e2e_steps)
+        h2d = int(lane_a.h_depth_np.nbytes + lane_a.h_matches_np.nbytes + cur.nbytes + n.nbytes)
+        h2d16 = int(lane_a.h_d16_np.nbytes + lane_a.h_matches_np.nbytes + cur.nbytes + n.nbytes)
+        d2h = int(sum(lane_a.arrs[k].nbytes for k in wanted) + lane_a.h_pose_out_np.nbytes + F * MAX_MATCHES)
+        one = {"value": world * F * e2e_steps / sec, "u16_depth": world * F * e2e_steps / sec16,
+               "h2d_GBps_per_rank": h2d * e2e_steps / sec / 1e9, "u16_h2d_GBps_per_rank": h2d16 * e2e_steps / sec16 / 1e9}
+        # the adaptor's default RNG mode (RS_RNG_REFERENCE: host std::mt19937 draws, one host round trip between the RANSAC
+        # and the Monte-Carlo kernels) through the same call sequence, float depth
+        opts_ref = solver.options(max_iterations=wl.hypotheses, seed=1234 + rank, rng_mode=rs.abi.RS_RNG_REFERENCE, intrinsics=wl.K)
+        timed(one_at_a_time(False, opts_ref), 1)
+        sec_ref = timed(one_at_a_time(False, opts_ref), max(e2e_steps // 2, 2))
+        one["rng_reference_mode"] = {"value": world * F * max(e2e_steps // 2, 2) / sec_ref,
+                                     "note": "RS_RNG_REFERENCE (the integration adaptor's default: the reference's own mt19937 "
+                                             "shuffle / normal draws on the host, one host round trip inside the solve), float depth, one call at a time"}
 
-            run_lanes(False, 2)
-            run_lanes(True, 2)
-            sec_l = run_lanes(False, e2e_steps)
-            sec_l16 = run_lanes(True, e2e_steps)
-            e2e["two_lanes"] = {"value": 2 * F * e2e_steps / sec_l, "unit": "frames/s", "steps": 2 * e2e_steps,
-                                "u16_depth": 2 * F * e2e_steps / sec_l16,
-                                "note": "two host threads, each calling the blocking host API on its own contexts and pinned buffers "
-                                        "(two batches in flight); same bytes per step"}
-            e2e["one_call_at_a_time"] = {"value": e2e["value"], "u16_depth": e2e["u16_depth"]["value"]}
-            if e2e["two_lanes"]["value"] > e2e["value"]:
-                e2e["value"] = e2e["two_lanes"]["value"]
-                e2e["mode"] = "two batches in flight (two host threads on the blocking host API); one call at a time: see one_call_at_a_time"
-            else:
-                e2e["mode"] = "one blocking call at a time"
+        # link roofline of this box at this N: every rank copies its pinned depth batch to its GPU at the same time
+        d_sink = torch.empty_like(d_depth)
+
+        def pure_h2d(nsteps):
+            for _ in range(nsteps):
+                d_sink.copy_(lane_a.h_depth, non_blocking=True)
+        timed(pure_h2d, 2)
+        sec_link = timed(pure_h2d, e2e_steps)
+        link = lane_a.h_depth_np.nbytes * e2e_steps / sec_link / 1e9
+        del d_sink
+
+        e2e = {"value": one["value"], "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "mode": "one blocking call at a time", "one_call_at_a_time": one,
+               "u16_depth": {"value": one["u16_depth"], "unit": "frames/s", "h2d_bytes_per_step": h2d16,
+                             "note": "rs_cape_run_u16: CV_16U sensor image, convertTo(CV_32F) on the device"},
+               "h2d_link": {"GBps_per_rank_all_ranks_copying": link, "aggregate_GBps": link * world,
+                            "note": "plain cudaMemcpyAsync of the pinned depth batch on every rank at once (max over ranks): what the "
+                                    "box's host memory / PCIe path delivers at this N, the ceiling of any host-fed leg"},
+               "host_cores_per_rank": host_cores,
+               "timing": "host wall clock around the C-ABI calls (pose solve begin -> find_primitives, chunk-pipelined copies -> pose solve end), max over ranks"}
+
+        if not args.no_e2e_lanes:
+            det_b = rs.PrimitiveDetection(W, H, wl.cell, *wl.K, max_batch=F, device=local_rank)
+            solver_b = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=wl.hypotheses, max_variance=100,
+                                           device=local_rank)
+            lanes_h = [lane_a, Lane(det_b, solver_b)]
+
+            def two_lanes(u16):
+                def run(nsteps):
+                    def worker(lane):
+                        torch.cuda.set_device(local_rank)
+                        for _ in range(nsteps):
+                            lane.step(u16)
+                    th = [threading.Thread(target=worker, args=(ln,)) for ln in lanes_h]
+                    for t_ in th:
+                        t_.start()
+                    for t_ in th:
+                        t_.join()
+                return run
+
+            timed(two_lanes(False), 2)
+            sec_l = timed(two_lanes(False), e2e_steps)
+            timed(two_lanes(True), 2)
+            sec_l16 = timed(two_lanes(True), e2e_steps)
+            two = {"value": world * 2 * F * e2e_steps / sec_l, "u16_depth": world * 2 * F * e2e_steps / sec_l16,
+                   "h2d_GBps_per_rank": 2 * h2d * e2e_steps / sec_l / 1e9, "u16_h2d_GBps_per_rank": 2 * h2d16 * e2e_steps / sec_l16 / 1e9,
+                   "steps": 2 * e2e_steps,
+                   "note": "two host threads per rank, each calling the blocking host API on its own contexts and pinned buffers "
+                           "(two batches in flight); same bytes per step"}
+            e2e["two_lanes"] = two
+            if two["value"] > e2e["value"]:
+                e2e["value"] = two["value"]
+                e2e["mode"] = "two batches in flight (two host threads per rank on the blocking host API); one call at a time: see one_call_at_a_time"
+            if two["u16_depth"] > e2e["u16_depth"]["value"]:
+                e2e["u16_depth"]["value"] = two["u16_depth"]
+            e2e["frac_of_h2d_link"] = (e2e["value"] / world) * (h2d / F) / 1e9 / link
+            lanes_h[1] = None
             det_b.close()
             solver_b.close()
+        lane_a = None
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        fps_all, sec_all, nf = cpu_port_frames_per_s(depth, cur, matches, n, threads)
-        fps_1, sec_1, nf1 = cpu_port_frames_per_s(depth, cur, matches, n, 1, frames=32)
+        nsample = F if W <= 640 else min(F, 32)
+        fps_all, sec_all, nf = cpu_port_frames_per_s(wl, depth, cur, matches, n, threads, frames=nsample)
+        fps_1, sec_1, nf1 = cpu_port_frames_per_s(wl, depth, cur, matches, n, 1, frames=32 if W <= 640 else 8)
         cpu = {"value": fps_all, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "the %d frames of one step, frame loop over %d host threads (%.2f s); 1 thread on %d frames: %.1f frames/s"
+               "sample": "%d frames of one step, frame loop over %d host threads (%.2f s); 1 thread on %d frames: %.1f frames/s"
                          % (nf, threads, sec_all, nf1, fps_1),
                "value_1_thread": fps_1}
 
+    det.close()
+    solver.close()
+    del d_depth, ctx
+
+    # ---- BASELINE configs[4] (1280x960, 40 px cells, 1024 hypotheses) beside the headline, same ranks, shorter run ----
+    config5 = None
+    if args.config == 4 and not args.no_config5 and not (args.width or args.height or args.cell or args.hypotheses):
+        wl5 = Workload("BASELINE configs[4]", 1280, 960, 40, 1024, 64, outlier_frac=0.3)
+        steps5 = max(min(steps, 10), 3)
+        r5, _ = measure_resident(wl5, args, rs, torch, dist, rank, world, local_rank, steps5, 3, extras=False)
+        config5 = {"metric": "RGB-D frames/sec (1280x960)", "value": r5["value"], "unit": "frames/s", "n_gpus": world,
+                   "ms_per_step": r5["ms_per_step"], "steps": steps5, "warmup": 3, "config": wl5.config(),
+                   "roofline": roofline_of(wl5, r5), "kernels_ms_per_step": kernels_of(r5), "gpu_launches": r5["launches"],
+                   "check": r5["check"], "clocks": r5["clocks"]}
+        if world > 1:
+            config5["comm_ms"] = r5["comm_ms"]
+
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = K1_BYTES_PER_FRAME * F / (k1_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if tj.get("frames_per_launch") == F:
-                traffic = tj.get("dram_bytes_per_launch")
         line = {
-            "metric": "RGB-D frames/sec (640x480)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "RGB-D frames/sec (%dx%d)" % (W, H), "value": res["value"], "unit": "frames/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": "640x480 full frame: CAPE plane+cylinder extraction + 300-point/20-plane RANSAC-LM pose solve + "
-                            "100-sample covariance (BASELINE configs[2]), batch of %d frames per GPU per step (configs[3] batch)" % F,
-                "frames_per_gpu": F, "cell_px": CELL, "cells_per_frame": N_CELLS, "ransac_hypotheses": 119, "n_variance": 100,
-                "l2": "inputs larger than L2 (%.0f MB of depth per step per GPU vs 126 MB)" % (depth.nbytes / 1e6),
-                "rng": "RS_RNG_DEVICE (counter-based on-device draws)",
-                "pose_groups": args.pose_groups,
-                "streams": "K1 alone, then cape_segment (main stream) beside pose_prepare/ransac/variance/covariance (pose stream); kernels_ms_per_step are per-kernel event times and overlap", "collective": "all-gather of [frames x 7] f64 poses" if world > 1 else "none",
+            "config": wl.config(),
+            "notes": {
+                "rng": "RS_RNG_DEVICE (counter-based on-device draws)", "pose_groups": args.pose_groups,
+                "streams": "K1 alone, then cape_segment (main stream) beside the pose chain (pose stream); kernels_ms_per_step are "
+                           "per-kernel event times and overlap",
+                "collective": ("all-gather of [frames x 7] f64 poses per step, issued on a side stream from a double-buffered copy of "
+                               "the poses (nothing waits for it until the buffer is reused two steps later)") if world > 1 else "none",
             },
-            "roofline": {"kernel": "cape_cell_fit (K1)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_launch": K1_BYTES_PER_FRAME * F, "ms_per_launch": k1_ms},
-            "kernels_ms_per_step": {"cape_cell_fit": k1_ms, "cape_segment": seg_ms, "pose_prepare": float(pose_ms[0]),
-                                    "pose_ransac_final_lm": float(pose_ms[1]), "pose_variance": float(pose_ms[2]),
-                                    "pose_covariance": float(pose_ms[3])},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "check": {"frames_with_valid_pose": ok_frac, "median_position_error_mm": pos_err},
+            "roofline": roofline_of(wl, res),
+            "kernels_ms_per_step": kernels_of(res),
+            "gpu_launches": res["launches"], "clocks": res["clocks"],
+            "check": res["check"],
         }
+        if world > 1:
+            line["comm_ms"] = {"all_gather_last_two_steps": res["comm_ms"],
+                               "note": "NCCL all-gather on the side stream (start -> done events); includes waiting for the slowest rank"}
         if rect is not None:
             line["rectify_depth"] = rect
         if single is not None:
@@ -577,6 +757,8 @@ def main():
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if config5 is not None:
+            line["config5"] = config5
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

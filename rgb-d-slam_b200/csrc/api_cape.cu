@@ -76,7 +76,23 @@ struct rs_cape_ctx {
     double* d_ky = nullptr;
     float* d_depth = nullptr;
     rs_cape_outputs d_out{};       // device pointers sized for max_batch
-    double* d_uniforms = nullptr;
+    // Cylinder-RANSAC draw tables (canonical doubles of mt19937(seed)), one slot per recently used seed. A table is copied
+    // stream-ordered from the slot's own pinned staging buffer, never rewritten while a launch that reads it may be in
+    // flight (a seed change takes another slot; the slot it evicts is first waited for), and every launch that reads a
+    // table records an event on the slot.
+    static constexpr int kUniformSlots = 4, kUniformUses = 8;
+    struct UniformSlot {
+        double* d = nullptr;          // device table
+        double* h = nullptr;          // pinned staging
+        uint32_t seed = 0;
+        bool valid = false;
+        uint64_t stamp = 0;           // LRU
+        cudaEvent_t copied = nullptr; // the H2D copy of the table has landed
+        cudaEvent_t used[kUniformUses] = {};
+        int next_use = 0;
+    } uniforms[kUniformSlots];
+    uint64_t uniform_clock = 0;
+    std::mutex uniform_mutex;
     double* d_scratch = nullptr;   // per-frame scratch of the segmentation kernel
     uint16_t* d_depth16 = nullptr; // staging for rs_cape_run_u16 (allocated on first use)
     bool rectify = false;          // rs_cape_set_rectification: rectify_depth in front of K1
@@ -84,8 +100,6 @@ struct rs_cape_ctx {
     float* d_rect = nullptr;               // max_batch x H x W rectified depth
     unsigned long long* d_keys = nullptr;  // max_batch x H x W scatter keys
     int n_uniforms = 0;
-    uint32_t uniforms_seed = 0;
-    bool uniforms_valid = false;
     CellFitParams fit{};
     SegmentParams seg{};
     // cached tensor map
@@ -178,17 +192,44 @@ int encode_tmap(rs_cape_ctx* c, const float* depth_dev, int batch)
 }
 
 // canonical doubles of std::mt19937(seed) through std::uniform_real_distribution<double>(0,1), i.e. what
-// utils::Random::get_random_double() returns on a fresh thread (random.hpp:17-31).
-int ensure_uniforms(rs_cape_ctx* c, uint32_t seed)
+// utils::Random::get_random_double() returns on a fresh thread (random.hpp:17-31). Returns the slot holding the table of
+// `seed`, ordered before anything enqueued on `stream` after this call; the caller records uniforms_used() after the
+// launch that reads it.
+int ensure_uniforms(rs_cape_ctx* c, uint32_t seed, cudaStream_t stream, int* slot_out)
 {
-    if (c->uniforms_valid && c->uniforms_seed == seed) return RS_OK;
-    std::vector<double> u(c->n_uniforms);
+    std::lock_guard<std::mutex> lock(c->uniform_mutex);
+    int pick = -1;
+    for (int k = 0; k < rs_cape_ctx::kUniformSlots; ++k)
+        if (c->uniforms[k].valid && c->uniforms[k].seed == seed) pick = k;
+    if (pick >= 0) {
+        rs_cape_ctx::UniformSlot& u = c->uniforms[pick];
+        u.stamp = ++c->uniform_clock;
+        RS_CUDA_CHECK(cudaStreamWaitEvent(stream, u.copied, 0));   // the copy may have been enqueued on another stream
+        *slot_out = pick;
+        return RS_OK;
+    }
+    for (int k = 0; k < rs_cape_ctx::kUniformSlots; ++k)
+        if (pick < 0 || c->uniforms[k].stamp < c->uniforms[pick].stamp) pick = k;
+    rs_cape_ctx::UniformSlot& u = c->uniforms[pick];
+    u.valid = false;
+    RS_CUDA_CHECK(cudaEventSynchronize(u.copied));                 // the staging buffer is free to be rewritten
+    for (cudaEvent_t e : u.used) RS_CUDA_CHECK(cudaStreamWaitEvent(stream, e, 0));   // launches still reading the old table
     std::mt19937 eng(seed);
     std::uniform_real_distribution<double> dist(0.0, 1.0);
-    for (double& v : u) v = dist(eng);
-    RS_CUDA_CHECK(cudaMemcpy(c->d_uniforms, u.data(), sizeof(double) * u.size(), cudaMemcpyHostToDevice));
-    c->uniforms_seed = seed;
-    c->uniforms_valid = true;
+    for (int i = 0; i < c->n_uniforms; ++i) u.h[i] = dist(eng);
+    RS_CUDA_CHECK(cudaMemcpyAsync(u.d, u.h, sizeof(double) * size_t(c->n_uniforms), cudaMemcpyHostToDevice, stream));
+    RS_CUDA_CHECK(cudaEventRecord(u.copied, stream));
+    u.seed = seed, u.valid = true, u.stamp = ++c->uniform_clock;
+    *slot_out = pick;
+    return RS_OK;
+}
+
+int uniforms_used(rs_cape_ctx* c, int slot, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(c->uniform_mutex);
+    rs_cape_ctx::UniformSlot& u = c->uniforms[slot];
+    RS_CUDA_CHECK(cudaEventRecord(u.used[u.next_use], stream));
+    u.next_use = (u.next_use + 1) % rs_cape_ctx::kUniformUses;
     return RS_OK;
 }
 
@@ -227,7 +268,12 @@ int create_impl(rs_cape_ctx* c)
     if ((rc = dev_alloc(&c->d_out.info, B))) return rc;
     if ((rc = dev_alloc(&c->d_scratch, B * cape_segment_scratch_doubles_per_frame(c->Nc)))) return rc;
     c->n_uniforms = 3 * RS_CYL_RANSAC_ITERS * RS_MAX_CYL_REGIONS * RS_MAX_CYL_SEGS;
-    if ((rc = dev_alloc(&c->d_uniforms, size_t(c->n_uniforms)))) return rc;
+    for (rs_cape_ctx::UniformSlot& u : c->uniforms) {
+        if ((rc = dev_alloc(&u.d, size_t(c->n_uniforms)))) return rc;
+        RS_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&u.h), sizeof(double) * size_t(c->n_uniforms), cudaHostAllocDefault));
+        RS_CUDA_CHECK(cudaEventCreateWithFlags(&u.copied, cudaEventDisableTiming));
+        for (cudaEvent_t& e : u.used) RS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
@@ -247,7 +293,7 @@ int create_impl(rs_cape_ctx* c)
     c->seg.W = c->W, c->seg.H = c->H, c->seg.hc = c->hc, c->seg.vc = c->vc, c->seg.cell = c->cell;
     c->seg.kx = c->d_kx, c->seg.ky = c->d_ky;
     c->seg.cos_merge = std::cos(18.0f * M_PI / 180.0);
-    c->seg.uniforms = c->d_uniforms, c->seg.n_uniforms = c->n_uniforms;
+    c->seg.uniforms = nullptr, c->seg.n_uniforms = c->n_uniforms;   // the table of a run's seed is bound per launch
     c->seg.max_boundary = c->max_boundary;
     return RS_OK;
 }
@@ -304,9 +350,12 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
         set_last_error("rs_cape_run_device: all device output buffers are required");
         return RS_ERR_INVALID_ARG;
     }
-    if ((rc = ensure_uniforms(c, seed)) != RS_OK) return rc;
+    cudaStream_t launch_stream = (seg_stream && seg_stream != stream) ? seg_stream : stream;
+    int uslot = 0;
+    if ((rc = ensure_uniforms(c, seed, launch_stream, &uslot)) != RS_OK) return rc;
     SegmentParams sp = c->seg;
     sp.batch = batch;
+    sp.uniforms = c->uniforms[uslot].d;
     SegmentBuffers sb;
     sb.depth = depth_dev;
     sb.cells = o->cells;
@@ -322,12 +371,13 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
     if (seg_stream && seg_stream != stream) {
         // the latency-bound segmentation of this chunk runs beside the plane fit / segmentation of the next ones
         RS_CUDA_CHECK(cudaStreamWaitEvent(seg_stream, c->fit_done, 0));
-        return launch_cape_segment(sp, sb, seg_stream);
+        if ((rc = launch_cape_segment(sp, sb, seg_stream)) != RS_OK) return rc;
+        return uniforms_used(c, uslot, seg_stream);
     }
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], stream));
     if ((rc = launch_cape_segment(sp, sb, stream)) != RS_OK) return rc;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[3], stream));
-    return RS_OK;
+    return uniforms_used(c, uslot, stream);
 }
 
 }  // namespace
@@ -342,6 +392,11 @@ rs_cape_ctx* rs_cape_create(int width, int height, int cell_px, double fx, doubl
         set_last_error("rs_cape_create: invalid geometry (cell_px and width must be multiples of 4)");
         return nullptr;
     }
+    if (cape_cell_fit_box_rows(cell_px) <= 0) {
+        set_last_error("rs_cape_create: unsupported cell size (the plane-fit kernel is built for 20 and 40 px cells)");
+        return nullptr;
+    }
+    if (cape_segment_validate(width / cell_px, height / cell_px, cell_px) != RS_OK) return nullptr;   // rs_last_error() says why
     rs_cape_ctx* c = new rs_cape_ctx();
     c->W = width, c->H = height, c->cell = cell_px;
     c->hc = width / cell_px, c->vc = height / cell_px, c->Nc = c->hc * c->vc;
@@ -371,7 +426,13 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_out.cyls);
     cudaFree(c->d_out.boundary_xyz);
     cudaFree(c->d_out.info);
-    cudaFree(c->d_uniforms);
+    for (rs_cape_ctx::UniformSlot& u : c->uniforms) {
+        cudaFree(u.d);
+        if (u.h) cudaFreeHost(u.h);
+        if (u.copied) cudaEventDestroy(u.copied);
+        for (cudaEvent_t e : u.used)
+            if (e) cudaEventDestroy(e);
+    }
     cudaFree(c->d_scratch);
     cudaFree(c->d_depth16);
     cudaFree(c->d_rect);
@@ -515,7 +576,6 @@ static int run_host_impl(rs_cape_ctx* c, const float* depth_host, const uint16_t
                             !out->planes && !out->cyls && !out->boundary_xyz && !out->info;
     const rs_cape_outputs& d = c->d_out;
     int rc;
-    if (!cells_only && (rc = ensure_uniforms(c, seed)) != RS_OK) return rc;
     int k = 0;
     for (int f0 = 0; f0 < batch; f0 += kChunkFrames, ++k) {
         const size_t n = size_t(std::min(kChunkFrames, batch - f0)), o = size_t(f0);

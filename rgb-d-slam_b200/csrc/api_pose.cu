@@ -135,13 +135,23 @@ int upload_impl(rs_pose_ctx* c, const double* cur_pose, const rs_match* matches,
             set_last_error("rs_pose: n_matches out of range");
             return RS_ERR_INVALID_ARG;
         }
+    // one pass over the match lists: feature types must be ones both sides of the solve know (the device scoring and the
+    // host-drawn reference subsets would otherwise disagree silently), and the batch says which kernel instantiation runs
+    bool p2d = false;
+    for (int b = 0; b < batch; ++b)
+        for (int i = 0; i < n_matches[b]; ++i) {
+            const int32_t ty = matches[size_t(b) * c->M + i].type;
+            if (ty != RS_FEAT_POINT && ty != RS_FEAT_PLANE && ty != RS_FEAT_POINT2D) {
+                set_last_error("rs_pose: rs_match.type " + std::to_string(ty) + " of frame " + std::to_string(b) + ", match " +
+                               std::to_string(i) + " is not RS_FEAT_POINT / RS_FEAT_PLANE / RS_FEAT_POINT2D");
+                return RS_ERR_INVALID_ARG;
+            }
+            p2d = p2d || ty == RS_FEAT_POINT2D;
+        }
     RS_CUDA_CHECK(cudaSetDevice(c->device));
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_cur, cur_pose, sizeof(double) * 7 * batch, cudaMemcpyHostToDevice, s));
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_matches, matches, sizeof(rs_match) * size_t(batch) * c->M, cudaMemcpyHostToDevice, s));
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_n, n_matches, sizeof(int32_t) * batch, cudaMemcpyHostToDevice, s));
-    bool p2d = false;
-    for (int b = 0; b < batch; ++b)
-        for (int i = 0; i < n_matches[b]; ++i) p2d = p2d || matches[size_t(b) * c->M + i].type == RS_FEAT_POINT2D;
     c->has_point2d = p2d;
     for (int b = 0; b < batch; ++b) {
         c->h_n[b] = n_matches[b];

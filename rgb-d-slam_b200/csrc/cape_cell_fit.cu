@@ -495,13 +495,8 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
     using Geo = Geometry<CS>;
     constexpr size_t smem = size_t(WARPS) * Geo::WARP_BYTES;
     auto kernel = cape_cell_fit_kernel<CS>;
-    static PerDevice<bool> cfg;
-    bool& configured = cfg.here();
-    if (!configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        RS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    RS_CUDA_CHECK(optin.ensure(kernel, true));
     CellFitParams p = prm;
     p.items_per_strip = (prm.hc + CELLS_PER_ITEM - 1) / CELLS_PER_ITEM;   // items (8 cells) per cell row
     p.total_items = prm.batch * prm.vc * p.items_per_strip;

@@ -61,6 +61,7 @@ struct RectifyParams {
 int launch_rectify_depth(const RectifyParams& prm, const float* depth, unsigned long long* keys, float* out, cudaStream_t stream);
 
 int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream);
+int cape_segment_validate(int hc, int vc, int cell);   // RS_OK, or RS_ERR_INVALID_ARG + rs_last_error() for a grid the kernel cannot take
 size_t cape_segment_scratch_doubles_per_frame(int n_cells);
 
 }  // namespace rs

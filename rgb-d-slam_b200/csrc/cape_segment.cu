@@ -976,24 +976,31 @@ __global__ void __launch_bounds__(32) cape_segment_kernel(const SegmentParams pr
 
 size_t cape_segment_scratch_doubles_per_frame(int n_cells) { return size_t(n_cells) * 6; }
 
-int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream)
+// Geometries the segmentation kernel can take (checked by rs_cape_create, so that an unsupported grid fails at creation
+// instead of on the first run).
+int cape_segment_validate(const int hc, const int vc, const int cell)
 {
-    const int Nc = prm.hc * prm.vc;
-    const size_t smem = carve(nullptr, nullptr, Nc, prm.cell * prm.cell);
-    if (smem > 227 * 1024) {
-        set_last_error("cape_segment: the cell grid does not fit in shared memory (" + std::to_string(smem) + " B > 227 KB)");
-        return RS_ERR_INVALID_ARG;
-    }
-    if (prm.hc > MAX_ROWS || prm.vc > MAX_ROWS || Nc > 32767 || prm.cell * prm.cell > 32767) {
+    const int Nc = hc * vc;
+    if (hc > MAX_ROWS || vc > MAX_ROWS || Nc > 32767 || cell * cell > 32767) {
         set_last_error("cape_segment: at most 64 x 64 cells (one 64-bit word per cell row and merge direction)");
         return RS_ERR_INVALID_ARG;
     }
-    static PerDevice<size_t> cfg;
-    size_t& configured = cfg.here();
-    if (smem > configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(cape_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
+    const size_t smem = carve(nullptr, nullptr, Nc, cell * cell);
+    if (smem > size_t(kMaxDynamicSmem)) {
+        set_last_error("cape_segment: the cell grid does not fit in shared memory (" + std::to_string(smem) + " B > 227 KB)");
+        return RS_ERR_INVALID_ARG;
     }
+    return RS_OK;
+}
+
+int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream)
+{
+    const int Nc = prm.hc * prm.vc;
+    const int rc = cape_segment_validate(prm.hc, prm.vc, prm.cell);
+    if (rc != RS_OK) return rc;
+    const size_t smem = carve(nullptr, nullptr, Nc, prm.cell * prm.cell);
+    static SmemOptIn optin;
+    RS_CUDA_CHECK(optin.ensure(cape_segment_kernel));
     // the plane/cylinder record arrays are zeroed so that unused entries read as empty
     RS_CUDA_CHECK(cudaMemsetAsync(buf.planes, 0, sizeof(rs_plane_out) * size_t(prm.batch) * RS_MAX_PLANES, stream));
     RS_CUDA_CHECK(cudaMemsetAsync(buf.cyls, 0, sizeof(rs_cyl_out) * size_t(prm.batch) * RS_MAX_CYL_REGIONS, stream));

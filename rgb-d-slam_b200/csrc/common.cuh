@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "../../include/rgbdslam_b200.h"
@@ -31,16 +32,26 @@ extern std::atomic<uint64_t> g_launch_count;
         RS_CUDA_CHECK(cudaGetLastError());                                                               \
     } while (0)
 
-// Per-device bookkeeping for cudaFuncSetAttribute (function attributes belong to a device's context, so a process that
-// drives several GPUs has to raise the dynamic shared memory limit once per device).
-template <typename T>
-struct PerDevice {
-    T v[64] = {};
-    T& here()
+// Raises a kernel's dynamic shared-memory limit to the sm_100 opt-in maximum (227 KB) exactly once per device, under a
+// lock: the library is driven from several host threads (two batches in flight, concurrent contexts), and a limit that
+// only ever holds the maximum cannot be lowered between another thread's check and its launch. The limit is a ceiling,
+// not a reservation: occupancy follows the bytes each launch actually asks for.
+constexpr int kMaxDynamicSmem = 232448;
+struct SmemOptIn {
+    std::mutex m;
+    bool done[64] = {};
+    template <class Kernel>
+    cudaError_t ensure(Kernel kernel, const bool prefer_shared_carveout = false)
     {
         int dev = 0;
         cudaGetDevice(&dev);
-        return v[dev & 63];
+        std::lock_guard<std::mutex> lock(m);
+        if (done[dev & 63]) return cudaSuccess;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+        if (e == cudaSuccess && prefer_shared_carveout)
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) done[dev & 63] = true;
+        return e;
     }
 };
 

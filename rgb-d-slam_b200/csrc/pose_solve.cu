@@ -1741,13 +1741,9 @@ int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream
 {
     const size_t smem = ransac_carve(nullptr, nullptr, buf.max_matches);
     if (smem > kSmemPerCta) return RS_ERR_INVALID_ARG;   // rs_pose_create refuses such capacities (pose_max_matches_supported)
-    static PerDevice<size_t> cfg;
-    size_t& configured = cfg.here();
-    if (smem > configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_ransac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
+    static SmemOptIn optin[2];
+    RS_CUDA_CHECK(optin[0].ensure(pose_ransac_kernel<false>));
+    RS_CUDA_CHECK(optin[1].ensure(pose_ransac_kernel<true>));
     if (prm.has_point2d)
         pose_ransac_kernel<true><<<prm.batch, RTHREADS, smem, stream>>>(buf, prm);
     else
@@ -1762,13 +1758,9 @@ int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStre
     const int warps = variance_warps_for(buf.max_matches);
     if (warps == 0) return RS_ERR_INVALID_ARG;
     const size_t smem = variance_smem_bytes(buf.max_matches, warps);
-    static PerDevice<size_t> cfg;
-    size_t& configured = cfg.here();
-    if (smem > configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        RS_CUDA_CHECK(cudaFuncSetAttribute(pose_variance_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
+    static SmemOptIn optin[2];
+    RS_CUDA_CHECK(optin[0].ensure(pose_variance_kernel<false>));
+    RS_CUDA_CHECK(optin[1].ensure(pose_variance_kernel<true>));
     const dim3 grid((prm.n_variance + warps - 1) / warps, prm.batch);
     if (prm.has_point2d)
         pose_variance_kernel<true><<<grid, warps * 32, smem, stream>>>(buf, prm);

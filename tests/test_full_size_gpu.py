@@ -60,7 +60,7 @@ def test_cape_batch_256_invariants_permutation_and_sampled_parity():
     again = det.find_primitives(depth, seed=5)
     assert out["planes"].tobytes() == again["planes"].tobytes()
     # oracle parity on a sample of the batch
-    sample = [0, 63, 128, 255]
+    sample = list(range(0, F, 8))                                  # 32 of the 256 frames
     ref = ol.cape_run(depth[sample], seed=5)
     for i, b in enumerate(sample):
         got_b = {k: v[b:b + 1] for k, v in out.items()}
@@ -78,9 +78,44 @@ def test_cape_1280x960_batch_invariants():
     out = det.find_primitives(depth, seed=0)
     for b in range(F):
         _check_frame_invariants(out, b, det.n_cells)
-    ref = ol.cape_run(depth[3:4], cell=40, K=K, seed=0)
-    parity.assert_frame_match(ref, {k: v[3:4] for k, v in out.items()}, 0)
+    sample = list(range(0, F, 2))                                  # 8 of the 16 frames
+    ref = ol.cape_run(depth[sample], cell=40, K=K, seed=0)
+    for i, b in enumerate(sample):
+        parity.assert_cells_match(ref["cells"][i], out["cells"][b])
+        parity.assert_frame_match({k: v[i:i + 1] for k, v in ref.items()}, {k: v[b:b + 1] for k, v in out.items()}, 0)
     det.close()
+
+
+def test_config5_full_frames_through_frame_pipeline_match_oracle():
+    """BASELINE configs[4] end to end: 1280x960 depth / 40 px cells / 1024 RANSAC hypotheses per frame, CAPE and the pose
+    solve together through FramePipeline.track_batch on 8 frames, every output against the oracle (reference RNG streams).
+    Half of the frames carry 30-45 % outliers so that the hypothesis loop runs well past the fourth iteration."""
+    F, M = 8, 320
+    K = rs.synth.intrinsics(2)
+    depth = rs.synth.scene_v0_batch(700, F, 1280, 960)
+    cur, matches, n = np.zeros((F, 7)), np.zeros((F, M), dtype=rs.abi.match_dtype), np.zeros(F, dtype=np.int32)
+    for b in range(F):
+        frac = 0.1 if b % 2 == 0 else 0.3 + 0.05 * (b // 2)
+        truth, guess, m = rs.synth.pose_correspondences(700 + b, outlier_frac=frac, scale=2)
+        cur[b], matches[b, :len(m)], n[b] = guess, m, len(m)
+    pipe = rs.FramePipeline(1280, 960, 40, intrinsics=K, max_frames=F, max_matches=M, max_iterations=1024, n_variance=100)
+    prims, out, mask, all_poses = pipe.track_batch(depth, cur, matches, n, seed=40, rng_mode=rs.abi.RS_RNG_REFERENCE)
+    ref = ol.cape_run(depth, cell=40, K=K, seed=40)
+    iterations = []
+    for b in range(F):
+        parity.assert_cells_match(ref["cells"][b], prims["cells"][b])
+        parity.assert_frame_match({k: v[b:b + 1] for k, v in ref.items()}, {k: v[b:b + 1] for k, v in prims.items()}, 0)
+        rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], K=K, max_iterations=1024, seed=40 + b)
+        assert out[b]["status"] == rout["status"] == 1
+        for f in ("n_inliers", "iterations_run", "best_iteration", "n_variance_ok"):
+            assert out[b][f] == rout[f], (b, f, out[b][f], rout[f])
+        assert np.array_equal(mask[b][:n[b]], rmask)
+        ok, dt, qd = parity.pose_close(rout["pose"], out[b]["pose"])
+        assert ok, (b, dt, qd)
+        iterations.append(int(out[b]["iterations_run"]))
+    assert max(iterations) > 4, iterations                          # the loop really ran past the early-stop minimum somewhere
+    assert np.array_equal(all_poses.cpu().numpy(), out["pose"])
+    pipe.close()
 
 
 def test_pose_batch_256_properties_and_determinism():
