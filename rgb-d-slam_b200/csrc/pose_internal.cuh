@@ -23,6 +23,37 @@ struct PoseFrameState {
     double inlier_score;
 };
 
+// ---- work state of the fused solve kernel (global memory, reset by the prepare kernel) -------------------------------------
+// Hypotheses of one frame may be run by the warps of several CTAs, so the reference's serial best-so-far bookkeeping
+// lives in global memory: a ring of finished-but-unapplied hypotheses, folded in strictly in iteration order under a lock.
+constexpr int kRansacRing = 64;   // hypotheses that may be in flight or finished-but-unapplied beyond the serial rule's position
+struct RansacFrame {
+    double best_x[6];
+    double max_score;
+    int best_inliers, best_iteration, can_quit, started;
+    int next_iter;    // next hypothesis index to hand out
+    int applied;      // hypotheses whose bookkeeping has been applied, in iteration order
+    int lock;         // guards the in-order bookkeeping
+    int closed;       // the hypothesis stage is over (early stop, or every iteration applied): the final LM has an owner
+    int joiners;      // CTAs working on this frame's hypotheses
+    int opened;       // the frame has been put on the help list (the minimum of four hypotheses did not stop the loop)
+    int pad[2];
+    int done[kRansacRing];         // iteration + 1 once the slot's result is complete
+    int hyp_ok[kRansacRing];
+    int hyp_inliers[kRansacRing];
+    double hyp_score[kRansacRing];
+    double hyp_x[kRansacRing][6];
+};
+struct PoseWork {
+    int join_ticket;   // frames handed to a first CTA so far
+    int frames_done;   // frames whose RANSAC + final LM stage is over (whatever the outcome)
+    int n_ready;       // frames published for their Monte-Carlo solves (completion order)
+    int mc_head;       // next Monte-Carlo task: frame slot = mc_head / groups, sample group = mc_head % groups
+    int n_open;        // frames on the help list
+    int pad[3];
+    unsigned long long t_first, t_ransac_end, t_last;   // %globaltimer stamps: first CTA in, last final LM out, last CTA out
+};
+
 // Device buffers of one pose context (SoA feature layout: component-major, stride = max_matches).
 struct PoseBuffers {
     int max_matches, max_iterations, max_variance;
@@ -44,6 +75,13 @@ struct PoseBuffers {
     const double* normals_in;      // B x n_variance x M x 4 (RS_RNG_REFERENCE), or null
     double* v6;                    // B x max_variance x 6 : [pos, eulerAngles(0,1,2)] per Monte-Carlo solve
     int32_t* v_ok;                 // B x max_variance
+    // fused solve kernel
+    PoseWork* work;                // 1
+    RansacFrame* rframe;           // B
+    unsigned* ring_mask;           // B x (kRansacRing + 1) x words : inlier masks of the ring slots, then of the best hypothesis
+    int32_t* ready;                // B : frame + 1, in the order the frames finished their RANSAC stage
+    int32_t* open_list;            // B : frame + 1, frames whose hypothesis loop went past the minimum and takes helpers
+    int32_t* mc_done;              // B : Monte-Carlo sample groups finished per frame (the last one reduces the covariance)
 };
 
 struct PoseLaunch {
@@ -55,15 +93,18 @@ struct PoseLaunch {
     int lm_max_fev;       // 400
     int rng_mode;
     int has_point2d;      // some frame of the batch carries an RS_FEAT_POINT2D feature: run the kernels that know the type
+    int phase = 0;        // 0 = RANSAC + Monte-Carlo in one launch; 1 = RANSAC + final LM only; 2 = Monte-Carlo + covariance only
+                          // (RS_RNG_REFERENCE: the host draws the Gaussian stream between the two halves)
     uint32_t seed;
     PoseIntrinsics K;
 };
 
 int pose_max_matches_supported();   // longest match list whose staging fits the shared memory of one SM
 int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
-int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
-int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
-int launch_pose_covariance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
+// RANSAC hypotheses, final LM, Monte-Carlo solves and covariance of a batch in ONE persistent kernel (prm.phase selects halves)
+int launch_pose_fused(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
+// device-timer view of the last fused launch: ms from the first CTA's start to the last final LM / to the last CTA's exit
+int pose_work_times(const PoseBuffers& buf, float* ransac_phase_ms, float* total_ms, cudaStream_t stream);
 // fills normals[B][n_variance][M][4] with the Gaussian draws the RS_RNG_DEVICE variance kernel uses
 int launch_pose_export_normals(const PoseBuffers& buf, const PoseLaunch& prm, double* normals, cudaStream_t stream);
 
