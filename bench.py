@@ -87,8 +87,8 @@ def parse_args():
     p.add_argument("--frames-per-gpu", type=int, default=0)
     p.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 10))")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--pose-groups", type=int, default=1,
-                   help="rs_pose_opts.sub_batches: frame groups whose RANSAC -> Monte-Carlo chains run on separate streams")
+    p.add_argument("--solver", default="auto", choices=["auto", "chain", "fused"],
+                   help="rs_pose_opts.solver of the timed step: the three-launch chain, the fused persistent kernel, or by shape")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-e2e-lanes", action="store_true", help="skip the two-batches-in-flight variant of the host-buffer leg")
     p.add_argument("--no-config5", action="store_true", help="skip the secondary configs[4] measurement of a default run")
@@ -236,8 +236,6 @@ def measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, 
     depth, truth, cur, matches, n = make_inputs(wl, rank * F, F)
     det = rs.PrimitiveDetection(wl.W, wl.H, wl.cell, *wl.K, max_batch=F, device=local_rank)
     solver = rs.PoseOptimization(max_batch=F, max_matches=MAX_MATCHES, max_iterations=wl.hypotheses, max_variance=100, device=local_rank)
-    opts = solver.options(max_iterations=wl.hypotheses, seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE, sub_batches=args.pose_groups,
-                          intrinsics=wl.K)
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     d_depth = torch.from_numpy(depth).cuda()
@@ -256,10 +254,15 @@ def measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, 
     counter = [0]
     comm_ms = []
 
+    solver_choice = {"auto": rs.abi.RS_SOLVER_AUTO, "chain": rs.abi.RS_SOLVER_CHAIN, "fused": rs.abi.RS_SOLVER_FUSED}[args.solver]
+    opts = solver.options(max_iterations=wl.hypotheses, seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE, intrinsics=wl.K,
+                          solver=solver_choice)
+
     def step():
         # CAPE and the pose solve of a frame are independent (the reference runs find_primitives on its own thread):
-        # K1 (HBM bound) runs alone, then the latency-bound segmentation (main stream) and the pose chain (pose stream)
-        # share the SMs; the main stream joins the pose stream before the next step.
+        # K1a (HBM bound) runs alone, then the latency-bound segmentation (main stream) and the pose solve (pose stream)
+        # share the SMs; the main stream joins the pose stream before the next step. (Measured and not done: enqueueing the
+        # solve's preparation kernel ahead of K1a - the RANSAC kernel then starts beside K1b and loses more than the 0.04 ms.)
         i = counter[0] & 1
         counter[0] += 1
         det.run_device(d_depth.data_ptr(), F, seed=0, stream=sptr)
@@ -308,6 +311,8 @@ def measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, 
     pose_ms = np.mean([solver.kernel_ms(s) for s in range(steps)], axis=0)
     det.set_timing(0)
     solver.set_timing(0)
+    phase_ms = solver.phase_ms()   # device-timer view of the last step's solve kernel
+    work_counters = solver.work_counters()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -340,8 +345,8 @@ def measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, 
             r = world - 1
             _, cur_r, m_r, n_r = pose_inputs(wl, r * F, F)
             solver.upload(cur_r, m_r, n_r)
-            opts_r = solver.options(max_iterations=wl.hypotheses, seed=1234 + r, rng_mode=rs.abi.RS_RNG_DEVICE,
-                                    sub_batches=args.pose_groups, intrinsics=wl.K)
+            opts_r = solver.options(max_iterations=wl.hypotheses, seed=1234 + r, rng_mode=rs.abi.RS_RNG_DEVICE, intrinsics=wl.K,
+                                    solver=solver_choice)
             solver.solve_device(F, opts_r, stream=pptr)
             torch.cuda.synchronize()
             shard_ok = bool(torch.equal(gathered[last][r], poses_view))
@@ -353,7 +358,7 @@ def measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, 
             raise SystemExit("multi-GPU correctness check failed: %r" % (check["multi_gpu"],))
 
     res = {"wl": wl, "value": value, "ms_per_step": ms_total / steps, "steps": steps, "launches": int(launches), "clocks": clocks,
-           "k1_ms": k1_ms, "seg_ms": seg_ms, "pose_ms": [float(v) for v in pose_ms], "check": check,
+           "k1_ms": k1_ms, "seg_ms": seg_ms, "pose_ms": [float(v) for v in pose_ms], "phase_ms": phase_ms, "work_counters": work_counters, "check": check,
            "comm_ms": comm_ms, "F": F}
     ctx = dict(det=det, solver=solver, opts=opts, d_depth=d_depth, depth=depth, truth=truth, cur=cur, matches=matches, n=n,
                stream=stream, pose_stream=pose_stream, poses_view=poses_view)
@@ -385,8 +390,13 @@ def roofline_of(wl, res):
 
 def kernels_of(res):
     p = res["pose_ms"]
-    return {"cape_cell_fit": res["k1_ms"], "cape_segment": res["seg_ms"], "pose_prepare": p[0], "pose_ransac_final_lm": p[1],
-            "pose_variance": p[2], "pose_covariance": p[3]}
+    if p[2] > 0:   # the three-launch chain
+        return {"cape_cell_fit": res["k1_ms"], "cape_segment": res["seg_ms"], "pose_prepare (enqueued ahead of K1a)": p[0],
+                "pose_ransac_final_lm": p[1], "pose_variance_covariance": p[2]}
+    return {"cape_cell_fit": res["k1_ms"], "cape_segment": res["seg_ms"], "pose_prepare": p[0],
+            "pose_solve (RANSAC + final LM + Monte-Carlo + covariance, one persistent kernel)": p[1],
+            "pose_solve_ransac_phase (device timer, last step: first CTA in -> last final LM out)": res["phase_ms"][0],
+            "pose_solve_device_timer_total (last step)": res["phase_ms"][1], "pose_solve_work_counters (last step)": res["work_counters"]}
 
 
 def main():
@@ -451,6 +461,27 @@ def main():
         single = {"cape_ms": ms_cape, "pose_ms": ms_pose, "full_frame_ms": ms_full, "frames_per_s": 1e3 / ms_full,
                   "note": "batch = 1, inputs resident, back-to-back frames on one GPU: CAPE plane + cylinder extraction (configs[1]), "
                           "the RANSAC-LM solve with its covariance, and both overlapped (configs[2])"}
+
+    # ---- the pose solve alone, inputs resident: the three-launch chain against the fused persistent kernel ----
+    pose_alone = None
+    if extras:
+        pose_alone = {}
+        for name, choice in (("chain", rs.abi.RS_SOLVER_CHAIN), ("fused", rs.abi.RS_SOLVER_FUSED)):
+            o = solver.options(max_iterations=wl.hypotheses, seed=1234, rng_mode=rs.abi.RS_RNG_DEVICE, intrinsics=wl.K, solver=choice)
+            for _ in range(3):
+                solver.solve_device(F, o, stream=pptr)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(pose_stream)
+            for _ in range(10):
+                solver.solve_device(F, o, stream=pptr)
+            b_.record(pose_stream)
+            torch.cuda.synchronize()
+            pose_alone[name + "_ms_per_batch"] = a.elapsed_time(b_) / 10
+            if name == "fused":
+                pose_alone["fused_ransac_phase_ms"] = solver.phase_ms()[0]
+        pose_alone["note"] = ("rs_pose_solve_device alone (preparation included), %d frames: three launches (per-frame RANSAC kernel, then the "
+                              "Monte-Carlo kernel) against one persistent kernel with per-frame hand-over" % F)
 
     # ---- rectify_depth (the step in front of the path, off in the headline workload as in examples/main_TUM.cpp) ----
     rect = None
@@ -731,7 +762,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": wl.config(),
             "notes": {
-                "rng": "RS_RNG_DEVICE (counter-based on-device draws)", "pose_groups": args.pose_groups,
+                "rng": "RS_RNG_DEVICE (counter-based on-device draws)", "solver": args.solver,
                 "streams": "K1 alone, then cape_segment (main stream) beside the pose chain (pose stream); kernels_ms_per_step are "
                            "per-kernel event times and overlap",
                 "collective": ("all-gather of [frames x 7] f64 poses per step, issued on a side stream from a double-buffered copy of "
@@ -749,6 +780,8 @@ def main():
             line["rectify_depth"] = rect
         if single is not None:
             line["single_frame"] = single
+        if pose_alone is not None:
+            line["pose_solve_alone"] = pose_alone
         if kalman is not None:
             line["kalman_update"] = kalman
         if pipelined is not None:

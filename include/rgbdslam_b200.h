@@ -209,10 +209,22 @@ typedef struct rs_pose_opts {
     uint32_t seed;
     double fx, fy, cx, cy;      /* camera-1 intrinsics; all 0 -> reference defaults 550,550,320,240  */
     int32_t lm_max_fev;         /* <=0 -> 400 (Eigen LevenbergMarquardt default)                     */
-    int32_t sub_batches;        /* RS_RNG_DEVICE only: > 1 splits the batch into that many groups of frames (at most 8)
-                                   whose RANSAC -> Monte-Carlo kernel chains run on separate streams, so that a group's
-                                   Monte-Carlo solves start as soon as its own slowest RANSAC frame is through. Frames are
-                                   independent: the results are identical. <= 1 -> one group                            */
+    int32_t sub_batches;        /* accepted for compatibility, no effect: the solve kernel hands every frame over from its final
+                                   LM to its Monte-Carlo solves on its own (it used to split the batch into groups of frames
+                                   whose kernel chains ran on separate streams)                                           */
+    int32_t worker_ctas_per_sm; /* resident CTAs per SM the solve kernel is launched with; <= 0 -> as many as fit (4 at up to 400
+                                   matches). A caller that runs another kernel beside the solve (bench.py: the cell-graph
+                                   segmentation, 111 KB of shared memory per CTA) starts with fewer and adds the rest with
+                                   rs_pose_add_workers once that kernel has drained. < 0 (rs_pose_solve_device only): launch
+                                   the frame role alone (hypotheses + final LM; a CTA per frame that leaves when its frame is
+                                   done) - the Monte-Carlo solves then run on the CTAs the caller adds with rs_pose_add_workers,
+                                   and the solve is complete when those have finished                                      */
+    int32_t solver;             /* 0 = chosen by shape, 1 = the three-launch chain (per-frame RANSAC kernel with its state in shared
+                                   memory, then the Monte-Carlo kernel: small or short-lived CTAs that leave room for kernels the
+                                   caller runs beside the solve; the default up to 256 hypotheses per frame), 2 = the fused
+                                   persistent kernel (per-frame hand-over from the final LM to the Monte-Carlo solves, any number
+                                   of CTAs per frame: fastest for a solve running alone - 1.2 against 1.5 ms per 256 frames - and
+                                   for hundreds of hypotheses per frame, the default beyond 256)                            */
 } rs_pose_opts;
 
 typedef struct rs_pose_out {
@@ -259,19 +271,39 @@ int rs_pose_solve(rs_pose_ctx* ctx, const double cur_pose[7], const rs_match* ma
  * until rs_pose_download). Asynchronous on `stream`. RS_RNG_DEVICE only. */
 int rs_pose_upload(rs_pose_ctx* ctx, const double* cur_pose, const rs_match* matches, const int32_t* n_matches, int batch);
 int rs_pose_solve_device(rs_pose_ctx* ctx, int batch, const rs_pose_opts* opts, void* stream);
+/* The preparation step of rs_pose_solve_device alone (AoS -> SoA of the uploaded match lists, validity, reset of the work
+ * state): a caller whose `stream` will be held up by other work (bench.py: the pose stream waits for the plane-fit kernel)
+ * enqueues it ahead of that wait; the following rs_pose_solve_device call for the same batch then launches the solve kernel
+ * only. Asynchronous. */
+int rs_pose_prepare_device(rs_pose_ctx* ctx, int batch, const rs_pose_opts* opts, void* stream);
+/* More CTAs for the solve kernel most recently launched through this context (its work lives in global-memory queues, any
+ * number of launches may feed on them): `ctas_per_sm` <= 0 -> as many as fit. They leave at once when no work is left.
+ * `stream` must not be one that runs ahead of that solve launch or behind the next one. Asynchronous. */
+int rs_pose_add_workers(rs_pose_ctx* ctx, int ctas_per_sm, void* stream);
 int rs_pose_download(rs_pose_ctx* ctx, int batch, rs_pose_out* out, uint8_t* inlier_mask);
-/* Makes `stream` wait until the RANSAC + final LM kernel of the most recent solve launched through this context has
- * finished (the Monte-Carlo covariance kernels may still be running): the counterpart of rs_cape_stream_wait_fit. The
- * RANSAC kernel is a latency chain that suffers when other kernels take shared memory and issue slots from it; the
- * Monte-Carlo kernel that follows is throughput bound and shares the SMs well. */
+/* Makes `stream` wait until the solve kernel of the most recent solve launched through this context has finished (with
+ * RS_RNG_REFERENCE: its first half, hypotheses + final LM): the counterpart of rs_cape_stream_wait_fit. */
 int rs_pose_stream_wait_ransac(rs_pose_ctx* ctx, void* stream);
 double* rs_pose_device_poses(rs_pose_ctx* ctx); /* B x 7 doubles on the device (the all-gather payload) */
 
 /* Per-kernel device timing, as rs_cape_set_timing (replaces the static timing doubles of Pose_Optimization,
- * pose_optimization.hpp:97-102). ms[0] = prepare, ms[1] = RANSAC + final LM, ms[2] = Monte-Carlo LM solves,
- * ms[3] = covariance reduction. */
+ * pose_optimization.hpp:97-102). ms[0] = prepare, ms[1] = the solve kernel (RANSAC hypotheses, final LM, Monte-Carlo LM solves
+ * and covariance of the batch in one persistent launch; with RS_RNG_REFERENCE its first half: hypotheses + final LM),
+ * ms[2] = its second half with RS_RNG_REFERENCE (Monte-Carlo solves + covariance; the host's random draws between the halves
+ * are not counted), else 0, ms[3] = 0. */
 int rs_pose_set_timing(rs_pose_ctx* ctx, int n_slots);
 int rs_pose_kernel_ms(rs_pose_ctx* ctx, int slot, float ms[4]);
+/* Inside view of the most recent solve-kernel launch of this context, from the device's own timer (waits for the device):
+ * ms[0] = first CTA in -> last frame's final LM out (the RANSAC phase; the Monte-Carlo solves of finished frames already run
+ * beside it), ms[1] = first CTA in -> last CTA out. */
+int rs_pose_phase_ms(rs_pose_ctx* ctx, float ms[2]);
+/* Work counters of the most recent solve-kernel launch (waits for the device): [0] hypotheses run by a frame's first CTA,
+ * [1] by CTAs that joined a frame later, [2] bookkeeping rounds, [3] hypotheses applied by the serial rule, [4] joins,
+ * [5] Monte-Carlo tasks, [6] hypotheses dropped by the early stop, [7] reserved. */
+int rs_pose_debug_counters(rs_pose_ctx* ctx, uint64_t out[8]);
+/* Per-frame timeline of the most recent solve-kernel launch, ms since its first CTA started (-1: did not happen):
+ * ms[b][0] hypotheses started, [1] hypothesis stage closed, [2] final LM done, [3] covariance done. */
+int rs_pose_debug_frame_times(rs_pose_ctx* ctx, int batch, double* ms);
 
 /* Debug/parity taps (RS_RNG_DEVICE): the random inputs the last solve used, so that the checker
  * can feed the same ones to the oracle. subsets = B x max_iterations x RS_MAX_SUBSET int32 (-1 padded);

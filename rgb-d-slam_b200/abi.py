@@ -11,6 +11,7 @@ RS_MAX_CYL_SEGS = 8
 RS_CYL_RANSAC_ITERS = 43
 RS_FEAT_POINT, RS_FEAT_PLANE, RS_FEAT_POINT2D = 0, 1, 2
 RS_RNG_REFERENCE, RS_RNG_DEVICE = 0, 1
+RS_SOLVER_AUTO, RS_SOLVER_CHAIN, RS_SOLVER_FUSED = 0, 1, 2
 RS_MAX_SUBSET = 16
 
 # numpy structured dtypes with the exact C layout (align=True reproduces the compiler's padding)
@@ -48,7 +49,7 @@ class CapeOutputs(C.Structure):
 class PoseOpts(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("n_variance", C.c_int32), ("rng_mode", C.c_int32),
                 ("seed", C.c_uint32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
-                ("lm_max_fev", C.c_int32), ("sub_batches", C.c_int32)]
+                ("lm_max_fev", C.c_int32), ("sub_batches", C.c_int32), ("worker_ctas_per_sm", C.c_int32), ("solver", C.c_int32)]
 
 
 def alloc_cape_outputs(batch, n_cells, max_boundary):

@@ -23,6 +23,7 @@ UNITS = [
     ("kalman.cu", ["-fmad=false"]),
     ("api_kalman.cu", []),
     ("pose_solve.cu", []),
+    ("pose_chain.cu", []),
     ("api_pose.cu", []),
 ]
 

@@ -4,10 +4,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pose_internal.cuh"
@@ -21,6 +23,10 @@ struct rs_pose_ctx {
     int32_t* d_n = nullptr;
     int32_t* d_subsets_in = nullptr;
     double* d_normals = nullptr;  // lazily allocated: B x max_variance x M x 4
+    double* h_normals = nullptr;  // pinned staging of the same size (RS_RNG_REFERENCE)
+    std::vector<int32_t> h_subsets;
+    std::vector<rs_pose_out> h_out;
+    std::vector<uint8_t> h_mask;
     PoseBuffers buf{};
     cudaStream_t stream = nullptr;
     // host mirrors kept for the reference RNG mode and for export
@@ -29,6 +35,8 @@ struct rs_pose_ctx {
     bool has_point2d = false;     // the uploaded batch carries an inverse-depth (RS_FEAT_POINT2D) feature
     PoseLaunch last{};
     int last_batch = 0;
+    bool last_fused = false;             // the most recent solve ran the fused kernel (rs_pose_add_workers / rs_pose_phase_ms apply)
+    bool last_mc_only = false;           // the most recent solve-kernel launch was the second half of an RS_RNG_REFERENCE solve
     std::vector<cudaEvent_t> events;  // 5 per timing slot
     cudaEvent_t ransac_done = nullptr;   // recorded after the RANSAC + final LM kernel (rs_pose_stream_wait_ransac)
     // rs_pose_opts::sub_batches > 1: side streams of the frame groups 1.. (group 0 runs on the caller's stream)
@@ -38,6 +46,8 @@ struct rs_pose_ctx {
     int groups_last = 1;                 // groups of the most recent solve (how many group_ransac events are live)
     int timing_slots = 0;
     uint64_t run_counter = 0;
+    int prepared_batch = 0;              // rs_pose_prepare_device ran for this batch size and no solve has consumed it yet
+    cudaEvent_t prepared = nullptr;      // recorded after that preparation kernel
 };
 
 namespace {
@@ -74,11 +84,19 @@ int create_impl(rs_pose_ctx* c)
     if ((rc = dev_alloc(&b.subsets_used, B * size_t(c->max_iterations) * RS_MAX_SUBSET))) return rc;
     if ((rc = dev_alloc(&b.v6, B * size_t(c->max_variance) * 6))) return rc;
     if ((rc = dev_alloc(&b.v_ok, B * size_t(c->max_variance)))) return rc;
+    if ((rc = dev_alloc(&b.work, 1))) return rc;
+    if ((rc = dev_alloc(&b.rframe, B))) return rc;
+    if ((rc = dev_alloc(&b.ring_mask, B * size_t(kRansacRing + 1) * ((M + 31) / 32)))) return rc;
+    if ((rc = dev_alloc(&b.ready, B))) return rc;
+    if ((rc = dev_alloc(&b.open_list, B))) return rc;
+    if ((rc = dev_alloc(&b.mc_done, B))) return rc;
+    if ((rc = dev_alloc(&b.frame_times, B * 4))) return rc;
     b.matches_aos = c->d_matches, b.cur_pose = c->d_cur, b.n_matches = c->d_n;
     b.subsets_in = nullptr, b.normals_in = nullptr;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->ransac_done, cudaEventDisableTiming));
     RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->group_fork, cudaEventDisableTiming));
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->prepared, cudaEventDisableTiming));
     for (int g = 0; g < rs_pose_ctx::kMaxGroups - 1; ++g) {
         RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->group_stream[g], cudaStreamNonBlocking));
         RS_CUDA_CHECK(cudaEventCreateWithFlags(&c->group_ransac[g], cudaEventDisableTiming));
@@ -91,8 +109,29 @@ int create_impl(rs_pose_ctx* c)
 
 int ensure_normals(rs_pose_ctx* c)
 {
+    const size_t n = size_t(c->max_batch) * c->max_variance * c->M * 4;
+    if (!c->h_normals) RS_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_normals), sizeof(double) * n, cudaHostAllocDefault));
     if (c->d_normals) return RS_OK;
-    return dev_alloc(&c->d_normals, size_t(c->max_batch) * c->max_variance * c->M * 4);
+    return dev_alloc(&c->d_normals, n);
+}
+
+// Runs fn(frame) for every frame of the batch on the host's hardware threads (the reference's random draws of different
+// frames are independent: each frame owns an engine).
+template <class F>
+void parallel_frames(const int batch, F fn)
+{
+    const int nt = int(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), unsigned(batch)));
+    if (nt <= 1) {
+        for (int b = 0; b < batch; ++b) fn(b);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&] {
+            for (int b = next.fetch_add(1); b < batch; b = next.fetch_add(1)) fn(b);
+        });
+    for (std::thread& t : th) t.join();
 }
 
 int resolve_launch(const rs_pose_ctx* c, const rs_pose_opts* opts, int batch, PoseLaunch& prm)
@@ -107,6 +146,15 @@ int resolve_launch(const rs_pose_ctx* c, const rs_pose_opts* opts, int batch, Po
     prm.rng_mode = o.rng_mode;
     prm.seed = o.seed;
     prm.has_point2d = c->has_point2d ? 1 : 0;
+    prm.ctas_per_sm = o.worker_ctas_per_sm;
+    prm.solver = o.solver;
+    if (prm.solver < 0 || prm.solver > 2) {
+        set_last_error("rs_pose: unknown solver (0 = by shape, 1 = chain, 2 = fused)");
+        return RS_ERR_INVALID_ARG;
+    }
+    if (const char* e = std::getenv("RS_POSE_SPLIT")) prm.split = std::atoi(e);
+    if (const char* e = std::getenv("RS_POSE_MC_CAP")) prm.mc_cap = std::atoi(e);       // experiment knobs (tools/exp_pose_timeline.py)
+    if (const char* e = std::getenv("RS_POSE_HELP_MIN")) prm.help_min = std::atoi(e);
     prm.sub_batches = o.sub_batches < 1 ? 1 : (o.sub_batches > rs_pose_ctx::kMaxGroups ? rs_pose_ctx::kMaxGroups : o.sub_batches);
     if (o.fx == 0 && o.fy == 0 && o.cx == 0 && o.cy == 0)
         prm.K = PoseIntrinsics{550.0, 550.0, 320.0, 240.0};  // Parameters::load_defaut (parameters.cpp:59-74)
@@ -212,102 +260,143 @@ void reference_normals(const rs_pose_ctx* c, int b, uint32_t seed, int started, 
         }
 }
 
+// RS_RNG_REFERENCE, between the two halves of a solve: the Gaussian stream of a frame continues where its RANSAC loop left
+// the engine, so the host fetches iterations_run and the inlier masks, draws what the reference would draw (host threads, a
+// frame each) and uploads the draws; buf.normals_in then points at them.
+int reference_round_trip(rs_pose_ctx* c, int batch, const PoseLaunch& lp, cudaStream_t s, PoseBuffers& buf)
+{
+    int rc;
+    std::vector<rs_pose_out>& h_out = c->h_out;
+    std::vector<uint8_t>& h_mask = c->h_mask;
+    h_out.resize(batch);
+    h_mask.resize(size_t(batch) * c->M);
+    RS_CUDA_CHECK(cudaMemcpyAsync(h_out.data(), buf.out, sizeof(rs_pose_out) * batch, cudaMemcpyDeviceToHost, s));
+    RS_CUDA_CHECK(cudaMemcpyAsync(h_mask.data(), buf.mask, h_mask.size(), cudaMemcpyDeviceToHost, s));
+    RS_CUDA_CHECK(cudaStreamSynchronize(s));
+    if ((rc = ensure_normals(c)) != RS_OK) return rc;
+    const size_t per_frame = size_t(lp.n_variance) * c->M * 4;
+    double* h_normals = c->h_normals;
+    parallel_frames(batch, [&](int b) {
+        double* dst = h_normals + size_t(b) * per_frame;
+        std::fill(dst, dst + per_frame, 0.0);
+        if (h_out[b].status == -2)  // final pose available, covariance pending
+            reference_normals(c, b, lp.seed + uint32_t(b), h_out[b].iterations_run, lp.n_variance,
+                              h_mask.data() + size_t(b) * c->M, dst);
+    });
+    RS_CUDA_CHECK(cudaMemcpyAsync(c->d_normals, h_normals, sizeof(double) * per_frame * batch, cudaMemcpyHostToDevice, s));
+    buf.normals_in = c->d_normals;
+    return RS_OK;
+}
+
 int solve_impl(rs_pose_ctx* c, int batch, const PoseLaunch& prm, cudaStream_t s, bool reference_rng)
 {
     int rc;
     PoseBuffers buf = c->buf;
-    std::vector<int32_t> h_subsets;
     if (reference_rng) {
-        h_subsets.resize(size_t(batch) * c->max_iterations * RS_MAX_SUBSET, -1);
-        for (int b = 0; b < batch; ++b)
+        // the reference's draws, frame by frame (every frame has its own engine, mt19937(seed + frame)): host threads
+        std::vector<int32_t>& h_subsets = c->h_subsets;
+        h_subsets.resize(size_t(batch) * c->max_iterations * RS_MAX_SUBSET);
+        parallel_frames(batch, [&](int b) {
             reference_subsets(c, b, prm.seed + uint32_t(b), prm.max_iterations,
                               h_subsets.data() + size_t(b) * c->max_iterations * RS_MAX_SUBSET);
+        });
         RS_CUDA_CHECK(cudaMemcpyAsync(c->d_subsets_in, h_subsets.data(), sizeof(int32_t) * h_subsets.size(),
                                       cudaMemcpyHostToDevice, s));
+        RS_CUDA_CHECK(cudaStreamSynchronize(s));   // pageable source: the copy has been staged when this returns
         buf.subsets_in = c->d_subsets_in;
     }
     cudaEvent_t* ev = c->timing_slots > 0 ? &c->events[size_t(c->run_counter % uint64_t(c->timing_slots)) * 5] : nullptr;
     ++c->run_counter;
-    const int groups = (!reference_rng && prm.n_variance > 0) ? std::min(prm.sub_batches, batch) : 1;
-    c->groups_last = groups;
-    if (groups > 1) {
-        // Frame groups: the RANSAC kernel of the whole batch lasts as long as its slowest frame (a latency chain), and the
-        // throughput-bound Monte-Carlo kernel cannot start before it ends. Split into groups of frames whose
-        // prepare -> RANSAC -> Monte-Carlo -> covariance chains run on their own streams, a group's Monte-Carlo solves start as
-        // soon as ITS slowest frame is through and fill the SMs while the other groups' RANSAC chains are still running.
-        // Frames are independent and the random draws are keyed by the frame index: the results do not change.
-        // Timing slots in this mode: [0,1] prepare of group 0, [1,2] RANSAC of group 0, [2,3] first group's Monte-Carlo
-        // kernel ... the whole solve is [0,4] (ev[4] is recorded after the join).
-        RS_CUDA_CHECK(cudaEventRecord(c->group_fork, s));
-        const int per = (batch + groups - 1) / groups;
-        for (int g = 0; g < groups; ++g) {
-            cudaStream_t gs = g == 0 ? s : c->group_stream[g - 1];
-            PoseLaunch gp = prm;
-            gp.frame0 = g * per;
-            gp.batch = std::min(per, batch - gp.frame0);
-            if (gp.batch <= 0) {
-                c->groups_last = g;
-                break;
-            }
-            if (g > 0) RS_CUDA_CHECK(cudaStreamWaitEvent(gs, c->group_fork, 0));
-            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], gs));
-            if ((rc = launch_pose_prepare(buf, gp, gs)) != RS_OK) return rc;
-            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[1], gs));
-            if ((rc = launch_pose_ransac(buf, gp, gs)) != RS_OK) return rc;
-            RS_CUDA_CHECK(cudaEventRecord(g == 0 ? c->ransac_done : c->group_ransac[g - 1], gs));
-            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], gs));
-            if ((rc = launch_pose_variance(buf, gp, gs)) != RS_OK) return rc;
-            if (g == 0 && ev) RS_CUDA_CHECK(cudaEventRecord(ev[3], gs));
-            if ((rc = launch_pose_covariance(buf, gp, gs)) != RS_OK) return rc;
-            if (g > 0) RS_CUDA_CHECK(cudaEventRecord(c->group_done[g - 1], gs));
-        }
-        for (int g = 1; g < c->groups_last; ++g) RS_CUDA_CHECK(cudaStreamWaitEvent(s, c->group_done[g - 1], 0));
-        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[4], s));
-        c->last = prm;
-        c->last_batch = batch;
-        return RS_OK;
-    }
+    c->groups_last = 1;   // rs_pose_opts.sub_batches is accepted and has no effect: the fused kernel hands over per frame
+    PoseLaunch lp = prm;
+    lp.frame0 = 0;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[0], s));
-    if ((rc = launch_pose_prepare(buf, prm, s)) != RS_OK) return rc;
+    if (c->prepared_batch == batch && !reference_rng) {
+        // rs_pose_prepare_device already ran the preparation kernel for this batch (possibly on another stream)
+        RS_CUDA_CHECK(cudaStreamWaitEvent(s, c->prepared, 0));
+    }
+    else if ((rc = launch_pose_prepare(buf, lp, s)) != RS_OK)
+        return rc;
+    c->prepared_batch = 0;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[1], s));
-    if ((rc = launch_pose_ransac(buf, prm, s)) != RS_OK) return rc;
-    RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
-    if (ev) {
-        RS_CUDA_CHECK(cudaEventRecord(ev[2], s));
-        if (prm.n_variance <= 0) {
+    const bool fused = lp.solver == 2 || (lp.solver == 0 && lp.max_iterations > 256) || !pose_chain_supports(c->M);
+    c->last_fused = fused;
+    if (!fused) {
+        // the three-launch chain (pose_chain.cu)
+        if ((rc = launch_pose_chain_ransac(buf, lp, s)) != RS_OK) return rc;
+        RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
+        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], s));
+        if (lp.n_variance > 0) {
+            if (reference_rng) {
+                if ((rc = reference_round_trip(c, batch, lp, s, buf)) != RS_OK) return rc;
+                if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], s));  // exclude the host RNG round trip
+            }
+            if ((rc = launch_pose_chain_variance(buf, lp, s)) != RS_OK) return rc;
+        }
+        if (ev) {
             RS_CUDA_CHECK(cudaEventRecord(ev[3], s));
             RS_CUDA_CHECK(cudaEventRecord(ev[4], s));
         }
+        if (reference_rng && lp.n_variance > 0) RS_CUDA_CHECK(cudaStreamSynchronize(s));  // the pinned Gaussian staging buffer is reused
     }
-    if (prm.n_variance > 0) {
-        std::vector<double> h_normals;
-        if (reference_rng) {
-            // the Gaussian stream continues where the RANSAC loop stopped: needs iterations_run and the inlier mask
-            std::vector<rs_pose_out> h_out(batch);
-            std::vector<uint8_t> h_mask(size_t(batch) * c->M);
-            RS_CUDA_CHECK(cudaMemcpyAsync(h_out.data(), buf.out, sizeof(rs_pose_out) * batch, cudaMemcpyDeviceToHost, s));
-            RS_CUDA_CHECK(cudaMemcpyAsync(h_mask.data(), buf.mask, h_mask.size(), cudaMemcpyDeviceToHost, s));
-            RS_CUDA_CHECK(cudaStreamSynchronize(s));
-            if ((rc = ensure_normals(c)) != RS_OK) return rc;
-            h_normals.assign(size_t(batch) * prm.n_variance * c->M * 4, 0.0);
-            for (int b = 0; b < batch; ++b)
-                if (h_out[b].status == -2)  // final pose available, covariance pending
-                    reference_normals(c, b, prm.seed + uint32_t(b), h_out[b].iterations_run, prm.n_variance,
-                                      h_mask.data() + size_t(b) * c->M,
-                                      h_normals.data() + size_t(b) * prm.n_variance * c->M * 4);
-            RS_CUDA_CHECK(cudaMemcpyAsync(c->d_normals, h_normals.data(), sizeof(double) * h_normals.size(),
-                                          cudaMemcpyHostToDevice, s));
-            buf.normals_in = c->d_normals;
+    else if (!reference_rng || lp.n_variance <= 0) {
+        // Hypotheses, final LM, Monte-Carlo solves and covariance of the batch feed on one set of work queues. Two launches of
+        // the same kernel work them, side by side: one with the frame role only (a CTA per frame, 28 KB of shared memory: it
+        // fits beside whatever else the caller runs, and its CTAs leave as their frames finish), one with the Monte-Carlo role
+        // (58 KB per CTA: a sample per warp holds a perturbed copy of the map side) whose CTAs move in as the first ones leave
+        // and start on a frame's samples the moment its final LM is done.
+        const bool frames_only = lp.n_variance > 0 && lp.ctas_per_sm < 0;   // the caller launches the Monte-Carlo role (rs_pose_add_workers)
+        const bool split = lp.n_variance > 0 && lp.split != 0 && !frames_only;
+        cudaStream_t aux = c->group_stream[0];
+        if (split) {
+            RS_CUDA_CHECK(cudaEventRecord(c->group_fork, s));
+            RS_CUDA_CHECK(cudaStreamWaitEvent(aux, c->group_fork, 0));
+            PoseLaunch fr = lp;
+            fr.run_ransac = 1, fr.run_mc = 0, fr.linger = lp.max_iterations >= 256 ? 1 : 0, fr.ctas_per_sm = 0;
+            if ((rc = launch_pose_fused(buf, fr, s)) != RS_OK) return rc;
+            RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
+            PoseLaunch mc = lp;
+            // both roles: whichever launch the hardware dispatches first, every resident CTA can take whatever work there is
+            // (CTAs that could only wait for frames would starve the frames' own CTAs of registers if they got there first)
+            mc.run_ransac = 1, mc.run_mc = 1;
+            if ((rc = launch_pose_fused(buf, mc, aux)) != RS_OK) return rc;
+            RS_CUDA_CHECK(cudaEventRecord(c->group_done[0], aux));
+            RS_CUDA_CHECK(cudaStreamWaitEvent(s, c->group_done[0], 0));
         }
-        if (ev && reference_rng) RS_CUDA_CHECK(cudaEventRecord(ev[2], s));  // exclude the host RNG round trip
-        if ((rc = launch_pose_variance(buf, prm, s)) != RS_OK) return rc;
-        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[3], s));
-        if ((rc = launch_pose_covariance(buf, prm, s)) != RS_OK) return rc;
-        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[4], s));
-        if (reference_rng) RS_CUDA_CHECK(cudaStreamSynchronize(s));  // h_normals must outlive the copy
+        else if (frames_only) {
+            PoseLaunch fr = lp;
+            fr.run_ransac = 1, fr.run_mc = 0, fr.linger = lp.max_iterations >= 256 ? 1 : 0, fr.ctas_per_sm = 0;
+            if ((rc = launch_pose_fused(buf, fr, s)) != RS_OK) return rc;
+            RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
+        }
+        else {
+            lp.run_ransac = 1, lp.run_mc = 1;
+            if ((rc = launch_pose_fused(buf, lp, s)) != RS_OK) return rc;
+            RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
+        }
+        if (ev)
+            for (int k = 2; k <= 4; ++k) RS_CUDA_CHECK(cudaEventRecord(ev[k], s));
+    }
+    else {
+        // RS_RNG_REFERENCE: the Gaussian stream of a frame continues where its RANSAC loop left the engine, so the host
+        // needs iterations_run and the inlier mask between the two halves of the kernel
+        lp.run_ransac = 1, lp.run_mc = 0, lp.linger = 1;
+        if ((rc = launch_pose_fused(buf, lp, s)) != RS_OK) return rc;
+        RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
+        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], s));
+        if ((rc = reference_round_trip(c, batch, lp, s, buf)) != RS_OK) return rc;
+        if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], s));  // exclude the host RNG round trip
+        lp.run_ransac = 0, lp.run_mc = 1, lp.publish_all = 1;
+        if ((rc = launch_pose_fused(buf, lp, s)) != RS_OK) return rc;
+        if (ev) {
+            RS_CUDA_CHECK(cudaEventRecord(ev[3], s));
+            RS_CUDA_CHECK(cudaEventRecord(ev[4], s));
+        }
+        RS_CUDA_CHECK(cudaStreamSynchronize(s));  // the pinned Gaussian staging buffer is reused by the next solve
     }
     c->last = prm;
     c->last_batch = batch;
+    c->last_mc_only = lp.run_ransac == 0;
     return RS_OK;
 }
 
@@ -355,6 +444,7 @@ void rs_pose_destroy(rs_pose_ctx* c)
     cudaFree(c->d_n);
     cudaFree(c->d_subsets_in);
     cudaFree(c->d_normals);
+    if (c->h_normals) cudaFreeHost(c->h_normals);
     PoseBuffers& b = c->buf;
     cudaFree(b.type);
     cudaFree(b.obs);
@@ -369,9 +459,17 @@ void rs_pose_destroy(rs_pose_ctx* c)
     cudaFree(b.subsets_used);
     cudaFree(b.v6);
     cudaFree(b.v_ok);
+    cudaFree(b.work);
+    cudaFree(b.rframe);
+    cudaFree(b.ring_mask);
+    cudaFree(b.ready);
+    cudaFree(b.open_list);
+    cudaFree(b.mc_done);
+    cudaFree(b.frame_times);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->ransac_done) cudaEventDestroy(c->ransac_done);
     if (c->group_fork) cudaEventDestroy(c->group_fork);
+    if (c->prepared) cudaEventDestroy(c->prepared);
     for (int g = 0; g < rs_pose_ctx::kMaxGroups - 1; ++g) {
         if (c->group_ransac[g]) cudaEventDestroy(c->group_ransac[g]);
         if (c->group_done[g]) cudaEventDestroy(c->group_done[g]);
@@ -493,6 +591,41 @@ int rs_pose_solve_device(rs_pose_ctx* c, int batch, const rs_pose_opts* opts, vo
     return solve_impl(c, batch, prm, static_cast<cudaStream_t>(stream), false);
 }
 
+int rs_pose_prepare_device(rs_pose_ctx* c, int batch, const rs_pose_opts* opts, void* stream)
+{
+    if (!c || batch <= 0 || batch > c->max_batch) {
+        set_last_error("rs_pose_prepare_device: invalid argument");
+        return RS_ERR_INVALID_ARG;
+    }
+    PoseLaunch prm;
+    int rc = resolve_launch(c, opts, batch, prm);
+    if (rc != RS_OK) return rc;
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    prm.frame0 = 0;
+    if ((rc = launch_pose_prepare(c->buf, prm, static_cast<cudaStream_t>(stream))) != RS_OK) return rc;
+    RS_CUDA_CHECK(cudaEventRecord(c->prepared, static_cast<cudaStream_t>(stream)));
+    c->prepared_batch = batch;
+    return RS_OK;
+}
+
+int rs_pose_add_workers(rs_pose_ctx* c, int ctas_per_sm, void* stream)
+{
+    if (!c || c->last_batch <= 0) {
+        set_last_error("rs_pose_add_workers: no solve has been launched through this context");
+        return RS_ERR_INVALID_ARG;
+    }
+    if (!c->last_fused) return RS_OK;   // the chain has no work queues to feed on
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    PoseLaunch prm = c->last;
+    prm.batch = c->last_batch;
+    prm.frame0 = 0;
+    prm.ctas_per_sm = ctas_per_sm;
+    prm.run_ransac = c->last_mc_only ? 0 : 1, prm.run_mc = 1, prm.publish_all = 0;
+    PoseBuffers buf = c->buf;
+    if (c->last_mc_only) buf.normals_in = c->d_normals;
+    return launch_pose_fused(buf, prm, static_cast<cudaStream_t>(stream));
+}
+
 int rs_pose_stream_wait_ransac(rs_pose_ctx* c, void* stream)
 {
     if (!c) {
@@ -518,6 +651,47 @@ int rs_pose_download(rs_pose_ctx* c, int batch, rs_pose_out* out, uint8_t* inlie
 }
 
 double* rs_pose_device_poses(rs_pose_ctx* c) { return c ? c->buf.poses : nullptr; }
+
+int rs_pose_debug_counters(rs_pose_ctx* c, uint64_t out[8])
+{
+    if (!c || !out) {
+        set_last_error("rs_pose_debug_counters: invalid argument");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    RS_CUDA_CHECK(cudaDeviceSynchronize());
+    PoseWork w;
+    RS_CUDA_CHECK(cudaMemcpy(&w, c->buf.work, sizeof(PoseWork), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) out[k] = w.dbg[k];
+    return RS_OK;
+}
+
+int rs_pose_debug_frame_times(rs_pose_ctx* c, int batch, double* ms /* batch x 4 */)
+{
+    if (!c || !ms || batch <= 0 || batch > c->max_batch) {
+        set_last_error("rs_pose_debug_frame_times: invalid argument");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    RS_CUDA_CHECK(cudaDeviceSynchronize());
+    PoseWork w;
+    RS_CUDA_CHECK(cudaMemcpy(&w, c->buf.work, sizeof(PoseWork), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> t(size_t(batch) * 4);
+    RS_CUDA_CHECK(cudaMemcpy(t.data(), c->buf.frame_times, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < t.size(); ++i) ms[i] = t[i] >= w.t_first && w.t_first != ~0ull ? double(t[i] - w.t_first) * 1e-6 : -1.0;
+    return RS_OK;
+}
+
+int rs_pose_phase_ms(rs_pose_ctx* c, float ms[2])
+{
+    if (!c || !ms) {
+        set_last_error("rs_pose_phase_ms: invalid argument");
+        return RS_ERR_INVALID_ARG;
+    }
+    RS_CUDA_CHECK(cudaSetDevice(c->device));
+    RS_CUDA_CHECK(cudaDeviceSynchronize());
+    return pose_work_times(c->buf, &ms[0], &ms[1], c->stream);
+}
 
 int rs_pose_export_random(rs_pose_ctx* c, int batch, int32_t* subsets, double* normals)
 {

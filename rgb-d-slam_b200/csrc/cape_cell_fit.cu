@@ -496,7 +496,7 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
     constexpr size_t smem = size_t(WARPS) * Geo::WARP_BYTES;
     auto kernel = cape_cell_fit_kernel<CS>;
     static SmemOptIn optin;
-    RS_CUDA_CHECK(optin.ensure(kernel, true));
+    RS_CUDA_CHECK(optin.ensure(kernel, smem, true));
     CellFitParams p = prm;
     p.items_per_strip = (prm.hc + CELLS_PER_ITEM - 1) / CELLS_PER_ITEM;   // items (8 cells) per cell row
     p.total_items = prm.batch * prm.vc * p.items_per_strip;

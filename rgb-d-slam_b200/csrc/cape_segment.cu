@@ -1000,7 +1000,7 @@ int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cud
     if (rc != RS_OK) return rc;
     const size_t smem = carve(nullptr, nullptr, Nc, prm.cell * prm.cell);
     static SmemOptIn optin;
-    RS_CUDA_CHECK(optin.ensure(cape_segment_kernel));
+    RS_CUDA_CHECK(optin.ensure(cape_segment_kernel, smem));
     // the plane/cylinder record arrays are zeroed so that unused entries read as empty
     RS_CUDA_CHECK(cudaMemsetAsync(buf.planes, 0, sizeof(rs_plane_out) * size_t(prm.batch) * RS_MAX_PLANES, stream));
     RS_CUDA_CHECK(cudaMemsetAsync(buf.cyls, 0, sizeof(rs_cyl_out) * size_t(prm.batch) * RS_MAX_CYL_REGIONS, stream));

@@ -32,25 +32,32 @@ extern std::atomic<uint64_t> g_launch_count;
         RS_CUDA_CHECK(cudaGetLastError());                                                               \
     } while (0)
 
-// Raises a kernel's dynamic shared-memory limit to the sm_100 opt-in maximum (227 KB) exactly once per device, under a
-// lock: the library is driven from several host threads (two batches in flight, concurrent contexts), and a limit that
-// only ever holds the maximum cannot be lowered between another thread's check and its launch. The limit is a ceiling,
-// not a reservation: occupancy follows the bytes each launch actually asks for.
+// Raises a kernel's dynamic shared-memory limit to what a launch needs, per device and under a lock: the library is driven
+// from several host threads (two batches in flight, concurrent contexts), and a limit that only ever grows cannot be lowered
+// between another thread's check and its launch. (Not simply the 227 KB maximum once: measured on B200, a kernel whose limit
+// is far above what it uses runs its L1-resident traffic - register spills, local arrays - 15 % slower; the driver appears to
+// size the L1 / shared memory split by the limit.)
 constexpr int kMaxDynamicSmem = 232448;
 struct SmemOptIn {
     std::mutex m;
-    bool done[64] = {};
+    size_t configured[64] = {};
+    bool carveout_set[64] = {};
     template <class Kernel>
-    cudaError_t ensure(Kernel kernel, const bool prefer_shared_carveout = false)
+    cudaError_t ensure(Kernel kernel, const size_t bytes, const bool prefer_shared_carveout = false)
     {
         int dev = 0;
         cudaGetDevice(&dev);
+        dev &= 63;
         std::lock_guard<std::mutex> lock(m);
-        if (done[dev & 63]) return cudaSuccess;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
-        if (e == cudaSuccess && prefer_shared_carveout)
+        cudaError_t e = cudaSuccess;
+        if (bytes > configured[dev]) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+            if (e == cudaSuccess) configured[dev] = bytes;
+        }
+        if (e == cudaSuccess && prefer_shared_carveout && !carveout_set[dev]) {
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess) done[dev & 63] = true;
+            if (e == cudaSuccess) carveout_set[dev] = true;
+        }
         return e;
     }
 };

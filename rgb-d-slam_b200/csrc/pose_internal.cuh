@@ -27,22 +27,27 @@ struct PoseFrameState {
 // Hypotheses of one frame may be run by the warps of several CTAs, so the reference's serial best-so-far bookkeeping
 // lives in global memory: a ring of finished-but-unapplied hypotheses, folded in strictly in iteration order under a lock.
 constexpr int kRansacRing = 64;   // hypotheses that may be in flight or finished-but-unapplied beyond the serial rule's position
+struct RansacSlot {               // result of one hypothesis (64 bytes)
+    double x[6];
+    double score;
+    int inliers;
+    int ok;
+};
 struct RansacFrame {
-    double best_x[6];
-    double max_score;
-    int best_inliers, best_iteration, can_quit, started;
-    int next_iter;    // next hypothesis index to hand out
-    int applied;      // hypotheses whose bookkeeping has been applied, in iteration order
-    int lock;         // guards the in-order bookkeeping
+    // read together by every warp that looks for work on the frame (one 16-byte load)
+    int can_quit;     // the early stop has fired
     int closed;       // the hypothesis stage is over (early stop, or every iteration applied): the final LM has an owner
-    int joiners;      // CTAs working on this frame's hypotheses
-    int opened;       // the frame has been put on the help list (the minimum of four hypotheses did not stop the loop)
-    int pad[2];
-    int done[kRansacRing];         // iteration + 1 once the slot's result is complete
-    int hyp_ok[kRansacRing];
-    int hyp_inliers[kRansacRing];
-    double hyp_score[kRansacRing];
-    double hyp_x[kRansacRing][6];
+    int opened;       // the loop went past the minimum of four hypotheses: more warps pay off, the frame is on the help list
+    int applied;      // hypotheses whose bookkeeping has been applied, in iteration order
+    int next_iter;    // next hypothesis index to hand out
+    int lock;         // guards the in-order bookkeeping
+    int joiners;      // other CTAs working on this frame's hypotheses
+    int started;      // iterations the serial loop would have started (rs_pose_out.iterations_run)
+    double max_score;
+    int best_inliers, best_iteration;
+    double best_x[6];
+    int done[kRansacRing];          // iteration + 1 once the slot's result is complete
+    RansacSlot slot[kRansacRing];
 };
 struct PoseWork {
     int join_ticket;   // frames handed to a first CTA so far
@@ -50,7 +55,9 @@ struct PoseWork {
     int n_ready;       // frames published for their Monte-Carlo solves (completion order)
     int mc_head;       // next Monte-Carlo task: frame slot = mc_head / groups, sample group = mc_head % groups
     int n_open;        // frames on the help list
-    int pad[3];
+    int mc_done_tasks; // Monte-Carlo tasks finished
+    int pad[2];
+    unsigned long long dbg[8];   // counters: hypotheses run by a frame's first CTA / by helpers, bookkeeping batches, hypotheses applied, ...
     unsigned long long t_first, t_ransac_end, t_last;   // %globaltimer stamps: first CTA in, last final LM out, last CTA out
 };
 
@@ -82,6 +89,7 @@ struct PoseBuffers {
     int32_t* ready;                // B : frame + 1, in the order the frames finished their RANSAC stage
     int32_t* open_list;            // B : frame + 1, frames whose hypothesis loop went past the minimum and takes helpers
     int32_t* mc_done;              // B : Monte-Carlo sample groups finished per frame (the last one reduces the covariance)
+    unsigned long long* frame_times;   // B x 4 %globaltimer stamps: hypotheses started, hypothesis stage closed, final LM done, covariance done
 };
 
 struct PoseLaunch {
@@ -93,13 +101,28 @@ struct PoseLaunch {
     int lm_max_fev;       // 400
     int rng_mode;
     int has_point2d;      // some frame of the batch carries an RS_FEAT_POINT2D feature: run the kernels that know the type
-    int phase = 0;        // 0 = RANSAC + Monte-Carlo in one launch; 1 = RANSAC + final LM only; 2 = Monte-Carlo + covariance only
-                          // (RS_RNG_REFERENCE: the host draws the Gaussian stream between the two halves)
+    int mc_cap = 1 << 30; // Monte-Carlo tasks that may be in flight while frames are still in their RANSAC stage
+    int help_min = 64;    // a CTA joins an opened frame when that leaves at least this many iterations per CTA on it (at 119
+                          // iterations nobody joins: measured, the hypotheses helpers run there are mostly dropped by the early stop)
+    int solver = 0;       // host side: 0 = by shape (the three-launch chain up to 256 hypotheses per frame, the fused kernel beyond),
+                          // 1 = chain, 2 = fused kernel (rs_pose_opts.solver)
+    int split = 1;        // host side: frame role and Monte-Carlo role in two launches side by side (0: one launch with both)
+    int ctas_per_sm = 0;  // resident CTAs per SM the fused kernel is launched with (<= 0: what fits)
+    // roles of one launch of the fused kernel (any number of launches may feed on the same work queues)
+    int run_ransac = 1;   // its CTAs take frames (hypotheses + final LM)
+    int run_mc = 1;       // its CTAs take Monte-Carlo tasks (and reduce covariances)
+    int linger = 1;       // CTAs of a launch without the Monte-Carlo role stay to help frames whose hypothesis loop runs long
+    int publish_all = 0;  // before the launch, put every frame whose final pose is available on the hand-over list
+                          // (RS_RNG_REFERENCE: the host draws the Gaussian stream between the two halves of a solve)
     uint32_t seed;
     PoseIntrinsics K;
 };
 
-int pose_max_matches_supported();   // longest match list whose staging fits the shared memory of one SM
+int pose_max_matches_supported();
+// the three-launch chain (pose_chain.cu): RANSAC + final LM per frame, then the Monte-Carlo solves with the covariance folded in
+bool pose_chain_supports(int max_matches);
+int launch_pose_chain_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
+int launch_pose_chain_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);   // longest match list whose staging fits the shared memory of one SM
 int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
 // RANSAC hypotheses, final LM, Monte-Carlo solves and covariance of a batch in ONE persistent kernel (prm.phase selects halves)
 int launch_pose_fused(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);

@@ -17,1051 +17,26 @@
 // the pivoted Cholesky factor of the column-scaled J^T J (same R up to row signs, to which lmpar is invariant), and
 // Q^T r = R^-T P^T J^T r. The trust-region logic (lmpar, qrsolv, ratio tests, stop codes 1-8, nfev accounting incl.
 // the redundant f(x) of NumericalDiff) is MINPACK's, so iterates follow the reference's path up to rounding.
-//   pose_ransac_kernel   : one CTA per frame, one warp per hypothesis; warps claim hypothesis indices dynamically
-//                          (hypotheses are independent: each LM starts from the current pose) and the reference's
-//                          serial best-so-far / early-stop rule is applied in iteration order as results complete;
-//                          then the final LM on the winning inlier set.
-//   pose_variance_kernel : one warp per Monte-Carlo sample (perturbed copy of the inlier set in shared memory).
-//   pose_covariance_kernel: one warp per frame, 6x6 covariance (one entry per lane, summed in sample order) + validity.
+//   pose_prepare_kernel  : AoS -> SoA of the match lists, validity, total score, reset of the per-frame work state.
+//   pose_fused_kernel    : persistent CTAs; a frame's hypotheses are claimed dynamically by the warps working on it
+//                          (hypotheses are independent: each LM starts from the current pose) and the reference's serial
+//                          best-so-far / early-stop rule is applied in iteration order as results complete; the warp that
+//                          applies the terminal hypothesis runs the final LM on the winning inlier set and publishes the
+//                          frame's Monte-Carlo solves (one warp per sample, perturbed copy of the inlier set in shared
+//                          memory), which any CTA picks up; the CTA finishing a frame's last samples reduces its 6x6
+//                          covariance (one entry per lane, summed in sample order) and validates it.
 // FP64 throughout (forward differences with h = 1.49e-8 |x| on mm-scale coordinates need it).
-#include <float.h>
-
-#include <algorithm>
-
-#include "plane_fit.cuh"  // normalize3
-#include "pose_internal.cuh"
+#include "pose_lm.cuh"
 
 namespace rs {
 
 namespace {
 
-constexpr int WARPS = 8;             // warps per CTA of the Monte-Carlo kernel (one sample each)
+#ifndef RS_POSE_CTAS_PER_SM
+#define RS_POSE_CTAS_PER_SM 3        // 3 x 4 warps at 168 registers; 4 would cap the LM body at 128 registers (spills on the serial chains)
+#endif
+constexpr int WARPS = 4;             // warps per CTA of the fused kernel (one hypothesis / one Monte-Carlo sample each)
 constexpr int THREADS = WARPS * 32;
-// RANSAC: warps per frame, each running one hypothesis at a time. The reference never stops before iteration 3, so
-// hypotheses 0..3 are always needed; beyond them the warps run ahead of the serial early-stop rule speculatively.
-constexpr int RWARPS = 4;
-constexpr int RTHREADS = RWARPS * 32;
-constexpr unsigned FULL = 0xffffffffu;
-constexpr double kSqrtEps = 1.4901161193847656e-08;  // sqrt(DBL_EPSILON): ftol, xtol and the difference step
-constexpr int kRunning = -100;
-
-// parameters.hpp:23-44
-constexpr double kPointInlierPx = 3.0;                       // float 3.0f
-constexpr double kPlaneInlierMm = 50.0;                      // float 50.0f
-constexpr double kPlaneInlierNormal = 0.20000000298023224;   // float 0.2f
-constexpr double kEarlyStopProportion = 0.800000011920929;   // double initialised from 0.80f
-constexpr double kPointScore = 1.0 / 5.0;                    // 1 / minimumPointForOptimization
-constexpr double kPlaneScore = 1.0 / 3.0;                    // 1 / minimumPlanesForOptimization
-constexpr double kPoint2dScore = 1.0 / 5.0;                  // 1 / minimumPoint2dForOptimization
-constexpr double kPoint2dInlierPx = 3.0;                     // float 3.0f
-constexpr double kPoint2dWeight = 0.3 / 2.0;                 // get_alpha_reduction() / parts (map_point2d.cpp:25,47)
-
-// IOptimizationFeature::get_score / get_feature_part_count per feature type
-__device__ __forceinline__ double score_of(const int type)
-{
-    return type == RS_FEAT_PLANE ? kPlaneScore : (type == RS_FEAT_POINT2D ? kPoint2dScore : kPointScore);
-}
-__device__ __forceinline__ int parts_of(const int type) { return type == RS_FEAT_PLANE ? 3 : 2; }
-
-// world <- camera rotation of the pose: R' = C * R(q), t' = C * t with C = [[0,0,1],[-1,0,0],[0,-1,0]]
-// (camera_transformation.cpp:11-23). world->camera is then p_c = R'^T (P - t') and the plane world->camera map
-// (inverse of [[R',0],[-t'^T R',1]], :52-71) is n_c = R'^T n_w, d_c = t'.n_w + d_w.
-struct Xform {
-    double R[9];
-    double t[3];
-};
-
-struct WarpLM {
-    double x[6], xt[6], diag[6], p[6], wa2[6], sc[6], g[6], xs[6];
-    double A[36];     // J^T J (full, symmetric)
-    double C[21];     // packed lower triangle of the column-scaled S A S
-    Xform T;          // transform at the point being evaluated (x, then the trial points)
-    double Rk[3][9];  // R'(x + h_k e_k) for the three rotation coefficients (scratch of the Jacobian set-up)
-    double dR[27];    // forward-difference derivative of R' along the three rotation coefficients
-    double ih[3];     // 1 / h_k of those differences
-    double fnorm, par, delta, xnorm, gnorm, pnorm;
-    int status, nfev, iter, again;
-};
-
-struct Problem {
-    int n;
-    const short* idx;
-    const int32_t* type;  // [M]
-    const double* obs;    // [4][M]
-    const double* map;    // [4][M]
-    const double* aux;    // [4][M] global: first observation + inverse depth of the inverse-depth (point2d) features
-    int M;
-};
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-
-// levenberg_marquardt_functors.cpp:29-38,82-86 + PoseBase normalisation (pose.cpp:18-22)
-__device__ inline void quaternion_from_coefficients(const double* x, double q[4])
-{
-    const double alpha = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
-    const double divider = 1.0 / (alpha + 1.0);
-    q[0] = 2.0 * x[3] * divider;
-    q[1] = 2.0 * x[4] * divider;
-    q[2] = 2.0 * x[5] * divider;
-    q[3] = (1.0 - alpha) * divider;
-    // PoseBase normalises the quaternion it is given (pose.cpp:18-22); one reciprocal square root instead of a square
-    // root and four divisions (this runs on the serial lane-0 path of every LM iteration)
-    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
-    if (n2 > 0.0) {
-        const double inn = rsqrt(n2);
-        q[0] *= inn, q[1] *= inn, q[2] *= inn, q[3] *= inn;
-    }
-}
-
-// Quaternion (w,x,y,z) -> rotation (Eigen toRotationMatrix), row-major
-__device__ inline void quat_to_rot(const double q[4], double r[9])
-{
-    const double w = q[0], x = q[1], y = q[2], z = q[3];
-    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
-    const double twx = tx * w, twy = ty * w, twz = tz * w;
-    const double txx = tx * x, txy = ty * x, txz = tz * x;
-    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    r[0] = 1.0 - (tyy + tzz), r[1] = txy - twz, r[2] = txz + twy;
-    r[3] = txy + twz, r[4] = 1.0 - (txx + tzz), r[5] = tyz - twx;
-    r[6] = txz - twy, r[7] = tyz + twx, r[8] = 1.0 - (txx + tyy);
-}
-
-__device__ inline void make_xform(const double* x, Xform& T)
-{
-    double q[4], r[9];
-    quaternion_from_coefficients(x, q);
-    quat_to_rot(q, r);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        T.R[0 + j] = r[6 + j];
-        T.R[3 + j] = -r[0 + j];
-        T.R[6 + j] = -r[3 + j];
-    }
-    T.t[0] = x[2], T.t[1] = -x[0], T.t[2] = -x[1];
-}
-
-// levenberg_marquardt_functors.cpp:14-27,74-80
-__device__ inline void coefficients_from_pose(const double* pose7, double x[6])
-{
-    x[0] = pose7[0], x[1] = pose7[1], x[2] = pose7[2];
-    const double divider = 1.0 / fmax(1.0 + pose7[6], 0.001);
-    x[3] = pose7[3] * divider;
-    x[4] = pose7[4] * divider;
-    x[5] = pose7[5] * divider;
-}
-
-// MatrixBase::eulerAngles(0,1,2) of R(q) (PoseBase::get_vector, pose.hpp:30-35)
-__device__ inline void pose_vector6(const double* x, double v[6])
-{
-    double q[4], m[9];
-    quaternion_from_coefficients(x, q);
-    quat_to_rot(q, m);
-    v[0] = x[0], v[1] = x[1], v[2] = x[2];
-    double r0 = atan2(m[5], m[8]), r1;
-    const double c2 = sqrt(m[0] * m[0] + m[1] * m[1]);
-    if (r0 > 0.0) {
-        r0 -= kPi;
-        r1 = atan2(-m[2], -c2);
-    }
-    else {
-        r1 = atan2(-m[2], c2);
-    }
-    const double s1 = sin(r0), c1 = cos(r0);
-    const double r2 = atan2(s1 * m[6] - c1 * m[3], c1 * m[4] - s1 * m[7]);
-    v[3] = -r0, v[4] = -r1, v[5] = -r2;
-}
-
-// WorldCoordinate::get_signed_distance_2D_px (point_coordinates.cpp:245-260)
-__device__ __forceinline__ void point_distance(const double o0, const double o1, const double X, const double Y,
-                                               const double Z, const Xform& T, const PoseIntrinsics& K, double& du,
-                                               double& dv)
-{
-    const double d0 = X - T.t[0], d1 = Y - T.t[1], d2 = Z - T.t[2];
-    const double xc = (T.R[0] * d0 + T.R[3] * d1) + T.R[6] * d2;
-    const double yc = (T.R[1] * d0 + T.R[4] * d1) + T.R[7] * d2;
-    const double zc = (T.R[2] * d0 + T.R[5] * d1) + T.R[8] * d2;
-    const double inv = 1.0 / zc;
-    const double u = inv * (K.fx * xc + K.cx * zc);
-    const double v = inv * (K.fy * yc + K.cy * zc);
-    if (u != u || v != v) {
-        du = DBL_MAX, dv = DBL_MAX;
-        return;
-    }
-    du = o0 - u;
-    dv = o1 - v;
-}
-
-// PlaneWorldCoordinates::to_camera_coordinates (plane_coordinates.cpp:20-24): n renormalised, d kept
-__device__ __forceinline__ void plane_to_camera(const double n0, const double n1, const double n2, const double dw,
-                                                const Xform& T, double np[3], double& dp)
-{
-    double v0 = (T.R[0] * n0 + T.R[3] * n1) + T.R[6] * n2;
-    double v1 = (T.R[1] * n0 + T.R[4] * n1) + T.R[7] * n2;
-    double v2 = (T.R[2] * n0 + T.R[5] * n1) + T.R[8] * n2;
-    const double z = (v0 * v0 + v1 * v1) + v2 * v2;
-    if (z > 0.0) {
-        const double is = rsqrt(z);
-        v0 *= is, v1 *= is, v2 *= is;
-    }
-    np[0] = v0, np[1] = v1, np[2] = v2;
-    dp = ((T.t[0] * n0 + T.t[1] * n1) + T.t[2] * n2) + dw;
-}
-
-// Point2dOptimizationFeature::get_distance (map_point2d.cpp:40-45) -> InverseDepthWorldPoint::compute_signed_screen_distance
-// (inverse_depth_coordinates.cpp:58-68,142-173) -> Segment<2>::distance (line.hpp:27-41,95-99): the matched pixel against
-// the screen line through the projections of the point's furthest / closest depth estimates. Device layout of the feature:
-// o = (u, v, dFar, dNear) with d* = min(inverse depth -/+ 3 sqrt(sigma), 1e-9) formed once by the preparation step,
-// m = (theta, phi) (the part the Monte-Carlo variation perturbs), ax = (first observation X, Y, Z).
-__device__ __forceinline__ void point2d_distance(const double o[4], const double m[4], const double ax[3], const Xform& T,
-                                                 const PoseIntrinsics& K, double& du, double& dv)
-{
-    double st, ct, sp, cp;
-    sincos(m[0], &st, &ct);
-    sincos(m[1], &sp, &cp);
-    const double b0 = 1.0 * st * cp, b1 = 1.0 * st * sp, b2 = 1.0 * ct;
-    double s[2], e[2];
-    bool ok = true;
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        const double den = o[2 + w];
-        const double d0 = (ax[0] + b0 / den) - T.t[0], d1 = (ax[1] + b1 / den) - T.t[1], d2 = (ax[2] + b2 / den) - T.t[2];
-        const double xc = (T.R[0] * d0 + T.R[3] * d1) + T.R[6] * d2;
-        const double yc = (T.R[1] * d0 + T.R[4] * d1) + T.R[7] * d2;
-        const double zc = (T.R[2] * d0 + T.R[5] * d1) + T.R[8] * d2;
-        const double inv = 1.0 / zc;
-        const double u = inv * (K.fx * xc + K.cx * zc), v = inv * (K.fy * yc + K.cy * zc);
-        ok = ok && !(u != u || v != v);
-        if (w == 0)
-            s[0] = u, s[1] = v;
-        else
-            e[0] = u, e[1] = v;
-    }
-    if (!ok) {
-        du = DBL_MAX, dv = DBL_MAX;
-        return;
-    }
-    double n0 = e[0] - s[0], n1 = e[1] - s[1];
-    const double z = n0 * n0 + n1 * n1;
-    if (z > 0.0) {
-        const double l = sqrt(z);
-        n0 /= l, n1 /= l;
-    }
-    const double along = (o[0] - s[0]) * n0 + (o[1] - s[1]) * n1;
-    du = o[0] - (s[0] + n0 * along);
-    dv = o[1] - (s[1] + n1 * along);
-}
-
-// One feature's residual entries (Global_Pose_Estimator::operator(), levenberg_marquardt_functors.cpp:128-169):
-// point -> 1/2 (du, dv); plane -> 1/3 (d_c n_c - d_p n_p). Returns the entry count.
-// `aux` / `M` / `gi`: where an inverse-depth feature finds its first observation (global memory, component-major).
-template <bool P2D>
-__device__ __forceinline__ int feature_residual(const int type, const double o[4], const double m[4], const Xform& T,
-                                                const PoseIntrinsics& K, double r[3], const double* aux, const int M,
-                                                const int gi)
-{
-    if (type == RS_FEAT_POINT) {
-        double du, dv;
-        point_distance(o[0], o[1], m[0], m[1], m[2], T, K, du, dv);
-        r[0] = du * 1.0 / 2.0;
-        r[1] = dv * 1.0 / 2.0;
-        r[2] = 0.0;
-        return 2;
-    }
-    if (P2D && type == RS_FEAT_POINT2D) {
-        const double ax[3] = {aux[gi], aux[M + gi], aux[2 * M + gi]};
-        double du, dv;
-        point2d_distance(o, m, ax, T, K, du, dv);
-        r[0] = du * kPoint2dWeight;
-        r[1] = dv * kPoint2dWeight;
-        r[2] = 0.0;
-        return 2;
-    }
-    double np[3], dp;
-    plane_to_camera(m[0], m[1], m[2], m[3], T, np, dp);
-    r[0] = (o[3] * o[0] - dp * np[0]) * 1.0 / 3.0;
-    r[1] = (o[3] * o[1] - dp * np[1]) * 1.0 / 3.0;
-    r[2] = (o[3] * o[2] - dp * np[2]) * 1.0 / 3.0;
-    return 3;
-}
-
-// distance_utils.cpp:6-9: atan2(sin(a - b), cos(a - b)). The arguments are components of unit normals, so |a - b| <= 2 < pi
-// and the expression is a - b up to a few ulp; the libm chain (three FP64 transcendentals per component) is only
-// evaluated when that could decide the comparison with the threshold.
-__device__ __noinline__ double angle_distance_exact(const double a, const double b) { return atan2(sin(a - b), cos(a - b)); }
-__device__ __forceinline__ bool angle_within(const double a, const double b, const double thr)
-{
-    const double d = fabs(a - b);
-    if (fabs(d - thr) > 1e-9) return d <= thr;
-    return fabs(angle_distance_exact(a, b)) <= thr;
-}
-
-// IOptimizationFeature::is_inlier (map_point.cpp:34-38, map_primitive.cpp:33-49)
-template <bool P2D>
-__device__ __forceinline__ bool feature_is_inlier(const int type, const double o[4], const double m[4], const Xform& T,
-                                                  const PoseIntrinsics& K, const double* aux, const int M, const int gi)
-{
-    if (type == RS_FEAT_POINT) {
-        double du, dv;
-        point_distance(o[0], o[1], m[0], m[1], m[2], T, K, du, dv);
-        const double dist = (du >= DBL_MAX || dv >= DBL_MAX) ? DBL_MAX : fabs(du) + fabs(dv);
-        return dist <= kPointInlierPx;
-    }
-    if (P2D && type == RS_FEAT_POINT2D) {
-        // map_point2d.cpp:33-38: (get_distance().array() <= threshold).all() - on the SIGNED distance
-        const double ax[3] = {aux[gi], aux[M + gi], aux[2 * M + gi]};
-        double du, dv;
-        point2d_distance(o, m, ax, T, K, du, dv);
-        return du <= kPoint2dInlierPx && dv <= kPoint2dInlierPx;
-    }
-    double np[3], dp;
-    plane_to_camera(m[0], m[1], m[2], m[3], T, np, dp);
-    return angle_within(o[0], np[0], kPlaneInlierNormal) && angle_within(o[1], np[1], kPlaneInlierNormal) &&
-           angle_within(o[2], np[2], kPlaneInlierNormal) && fabs(o[3] - dp) <= kPlaneInlierMm;
-}
-
-__device__ __forceinline__ int load_feature(const Problem& P, const int k, int& type, double o[4], double m[4])
-{
-    const int i = P.idx ? int(P.idx[k]) : k;
-    type = P.type[i];
-    o[0] = P.obs[i], o[1] = P.obs[P.M + i];
-    m[0] = P.map[i], m[1] = P.map[P.M + i], m[2] = P.map[2 * P.M + i];
-    if (type == RS_FEAT_POINT) {   // a point uses (u, v) and (X, Y, Z) only
-        o[2] = 0.0, o[3] = 0.0, m[3] = 0.0;
-    }
-    else {
-        o[2] = P.obs[2 * P.M + i], o[3] = P.obs[3 * P.M + i];
-        m[3] = P.map[3 * P.M + i];
-    }
-    return i;
-}
-
-// |f(x)|^2 over the problem's features with transform T (warp-wide result)
-template <bool P2D>
-__device__ inline double eval_sumsq(const Problem& P, const Xform& T, const PoseIntrinsics& K, const int lane)
-{
-    double ss = 0.0;
-    for (int k = lane; k < P.n; k += 32) {
-        int type;
-        double o[4], m[4], r[3];
-        const int gi = load_feature(P, k, type, o, m);
-        feature_residual<P2D>(type, o, m, T, K, r, P.aux, P.M, gi);
-        ss += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    }
-    return warp_sum(ss);
-}
-
-// ---- Jacobian -------------------------------------------------------------------------------------------------------
-// Eigen::NumericalDiff<F, Forward> differentiates the residual vector: column j = (f(x + h_j e_j) - f(x)) / h_j with
-// h_j = sqrt(eps) |x_j|. The residuals depend on x only through the transform (R', t'), t' is LINEAR in x0..x2 and R'
-// depends on x3..x5 only, so the same forward difference is taken here one level down - on the transform instead of on
-// every residual:  dR'_k = (R'(x + h_k e_k) - R'(x)) / h_k  (three 3x3 matrices per Jacobian, built once per iteration by
-// three lanes) - and carried to the residual rows by the chain rule per feature. The translation columns are exact; the
-// rotation columns differ from the reference's by its O(h) truncation term (1e-8 relative) which is two orders below
-// the rounding noise (1e-6 relative: residuals of ~100 px known to 1e-14, divided by h ~ 1e-8) that ANY evaluation order
-// of the reference's own difference quotient carries. Cost per point: one projection + ~60 FMA instead of seven
-// projections. nfev still counts the 7 evaluations NumericalDiff would have made, so stop code 5 fires at the same place.
-__device__ __forceinline__ void accumulate_row(const double (&J)[6], const double r, double (&a)[32])
-{
-    int t = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        a[21 + i] += J[i] * r;
-#pragma unroll
-        for (int j = i; j < 6; ++j) a[t++] += J[i] * J[j];
-    }
-}
-
-// rows of one feature at S.T / S.dR, accumulated into a[0..20] (upper triangle of J^T J, row-major) and a[21..26] (J^T r)
-// Inverse-depth features keep NumericalDiff's own scheme (seven residual evaluations): their residual is a point-to-line
-// distance through two projections, they are rare (the live pipeline never produces them), and S still holds what the
-// perturbed transforms are made of.
-__device__ __noinline__ void point2d_jacobian(const double (&o)[4], const double (&m)[4], const double* aux, const int M,
-                                              const int gi, const WarpLM& S, const PoseIntrinsics& K, double* c /* [27] contribution */)
-{
-    const double ax[3] = {aux[gi], aux[M + gi], aux[2 * M + gi]};
-    double du, dv;
-    point2d_distance(o, m, ax, S.T, K, du, dv);
-    const double r0 = du * kPoint2dWeight, r1 = dv * kPoint2dWeight;
-    double J0[6], J1[6];
-    for (int j = 0; j < 6; ++j) {
-        Xform Tj = S.T;
-        double ih;
-        if (j < 3) {
-            double h = kSqrtEps * fabs(S.x[j]);
-            if (h == 0.0) h = kSqrtEps;
-            const double xj = S.x[j] + h;
-            if (j == 0) Tj.t[1] = -xj;       // t' = (x2, -x0, -x1)
-            else if (j == 1) Tj.t[2] = -xj;
-            else Tj.t[0] = xj;
-            ih = 1.0 / h;
-        }
-        else {
-            for (int i = 0; i < 9; ++i) Tj.R[i] = S.Rk[j - 3][i];
-            ih = S.ih[j - 3];
-        }
-        double eu, ev;
-        point2d_distance(o, m, ax, Tj, K, eu, ev);
-        J0[j] = (eu * kPoint2dWeight - r0) * ih;
-        J1[j] = (ev * kPoint2dWeight - r1) * ih;
-    }
-    int t = 0;
-    for (int i = 0; i < 6; ++i) {
-        c[21 + i] = J0[i] * r0 + J1[i] * r1;
-        for (int j = i; j < 6; ++j) c[t++] = J0[i] * J0[j] + J1[i] * J1[j];
-    }
-}
-
-__device__ __forceinline__ void feature_jacobian(const int type, const double (&o)[4], const double (&m)[4], const Xform& T,
-                                                 const double* __restrict__ dR, const PoseIntrinsics& K, double (&a)[32])
-{
-    if (type == RS_FEAT_POINT) {
-        const double d0 = m[0] - T.t[0], d1 = m[1] - T.t[1], d2 = m[2] - T.t[2];
-        const double xc = (T.R[0] * d0 + T.R[3] * d1) + T.R[6] * d2;
-        const double yc = (T.R[1] * d0 + T.R[4] * d1) + T.R[7] * d2;
-        const double zc = (T.R[2] * d0 + T.R[5] * d1) + T.R[8] * d2;
-        const double inv = 1.0 / zc;
-        const double u = inv * (K.fx * xc + K.cx * zc);
-        const double v = inv * (K.fy * yc + K.cy * zc);
-        if (u != u || v != v) return;  // residual DBL_MAX at x and at every x + h: a zero row in the reference too
-        const double r0 = (o[0] - u) * 0.5, r1 = (o[1] - v) * 0.5;
-        // d r0 = A0 dxc + B0 dzc, d r1 = A1 dyc + B1 dzc
-        const double A0 = -0.5 * K.fx * inv, B0 = (0.5 * K.fx * xc) * (inv * inv);
-        const double A1 = -0.5 * K.fy * inv, B1 = (0.5 * K.fy * yc) * (inv * inv);
-        double J0[6], J1[6];
-        // x0 -> d1 += 1, x1 -> d2 += 1, x2 -> d0 -= 1  (t' = (x2, -x0, -x1))
-        J0[0] = A0 * T.R[3] + B0 * T.R[5], J1[0] = A1 * T.R[4] + B1 * T.R[5];
-        J0[1] = A0 * T.R[6] + B0 * T.R[8], J1[1] = A1 * T.R[7] + B1 * T.R[8];
-        J0[2] = -(A0 * T.R[0] + B0 * T.R[2]), J1[2] = -(A1 * T.R[1] + B1 * T.R[2]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double* D = dR + 9 * k;
-            const double dx = (D[0] * d0 + D[3] * d1) + D[6] * d2;
-            const double dy = (D[1] * d0 + D[4] * d1) + D[7] * d2;
-            const double dz = (D[2] * d0 + D[5] * d1) + D[8] * d2;
-            J0[3 + k] = A0 * dx + B0 * dz;
-            J1[3 + k] = A1 * dy + B1 * dz;
-        }
-        accumulate_row(J0, r0, a);
-        accumulate_row(J1, r1, a);
-        return;
-    }
-    // plane: r = (d_o n_o - d_p n_p) / 3, n_p = R'^T n / |R'^T n|, d_p = t'.n + d_w
-    const double v0 = (T.R[0] * m[0] + T.R[3] * m[1]) + T.R[6] * m[2];
-    const double v1 = (T.R[1] * m[0] + T.R[4] * m[1]) + T.R[7] * m[2];
-    const double v2 = (T.R[2] * m[0] + T.R[5] * m[1]) + T.R[8] * m[2];
-    const double z = (v0 * v0 + v1 * v1) + v2 * v2;
-    const double is = z > 0.0 ? rsqrt(z) : 1.0;
-    const double np[3] = {v0 * is, v1 * is, v2 * is};
-    const double dp = ((T.t[0] * m[0] + T.t[1] * m[1]) + T.t[2] * m[2]) + m[3];
-    const double third = 1.0 / 3.0;
-    double J[3][6], r[3];
-    // d d_p / d x0 = -n1, / d x1 = -n2, / d x2 = +n0
-    const double c0 = m[1] * third, c1 = m[2] * third, c2 = -m[0] * third;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        r[c] = (o[3] * o[c] - dp * np[c]) * third;
-        J[c][0] = c0 * np[c];
-        J[c][1] = c1 * np[c];
-        J[c][2] = c2 * np[c];
-    }
-    const double f = -dp * is * third;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double* D = dR + 9 * k;
-        const double w0 = (D[0] * m[0] + D[3] * m[1]) + D[6] * m[2];
-        const double w1 = (D[1] * m[0] + D[4] * m[1]) + D[7] * m[2];
-        const double w2 = (D[2] * m[0] + D[5] * m[1]) + D[8] * m[2];
-        const double along = (np[0] * w0 + np[1] * w1) + np[2] * w2;  // removed by the renormalisation
-        J[0][3 + k] = f * (w0 - along * np[0]);
-        J[1][3 + k] = f * (w1 - along * np[1]);
-        J[2][3 + k] = f * (w2 - along * np[2]);
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) accumulate_row(J[c], r[c], a);
-}
-
-// Sum over the warp of 32 per-lane values each, by recursive halving: after the five exchange levels lane L holds the
-// warp total of entry L in v[0] (31 exchanges instead of the 32 x 5 of a butterfly all-reduce).
-__device__ __forceinline__ double reduce_scatter32(double (&v)[32], const int lane)
-{
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool up = (lane & half) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const double send = up ? v[i] : v[i + half];
-            const double keep = up ? v[i + half] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, half);
-        }
-    }
-    return v[0];
-}
-
-// ---- lane-0 algebra on the shared 6x6 state ---------------------------------------------------------------------
-// MINPACK's lmder/lmpar work on the triangular factor R of J P = Q R and on Q^T r. Every quantity they need is a
-// function of A = J^T J = P R^T R P^T and g = J^T r = P R^T (Q^T r):   the Gauss-Newton step solves A x = g, the
-// damped step solves (A + par D^2) x = g, |J p|^2 = p^T A p, (R^T Q^T r)_j = g_perm(j), and the Newton correction of
-// lmpar is w^T (A + par D^2)^-1 w. They are evaluated here with LDL^T factorisations (no square roots, six
-// reciprocals) of the column-scaled matrix C = S A S, S = diag(1/|J_j|), which removes the mm-vs-quaternion scale
-// disparity of the columns before the squared condition number can hurt. Same iterates as lmpar/qrsolv up to rounding.
-__device__ __forceinline__ double norm6(const double* v)
-{
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) s += v[i] * v[i];
-    return sqrt(s);
-}
-
-// Packed lower-triangular index; with fully unrolled loops every index is a compile-time constant, so the 6x6
-// working set below lives in registers (no local-memory round trips on the serial lane-0 path).
-#define RS_T(i, j) ((i) * ((i) + 1) / 2 + (j))
-
-// In-place LDL^T of a packed symmetric positive definite 6x6: m(i,j), j < i, becomes l_ij; dinv = 1 / pivots.
-// Returns false when a pivot is not above `tiny`.
-__device__ __forceinline__ bool ldl6_packed(double (&m)[21], double (&dinv)[6], const double tiny)
-{
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const double dk = m[RS_T(k, k)];
-        ok = ok && (dk > tiny);
-        const double inv = 1.0 / dk;
-        dinv[k] = inv;
-        double col[6];
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i) col[i] = m[RS_T(i, k)];
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i) {
-            const double lik = col[i] * inv;
-#pragma unroll
-            for (int j = k + 1; j <= i; ++j) m[RS_T(i, j)] -= lik * col[j];
-            m[RS_T(i, k)] = lik;
-        }
-    }
-    return ok;
-}
-
-// z <- L^-1 z (unit lower factor, packed)
-__device__ __forceinline__ void forward6_packed(const double (&m)[21], double (&z)[6])
-{
-#pragma unroll
-    for (int i = 1; i < 6; ++i) {
-        double sum = z[i];
-#pragma unroll
-        for (int j = 0; j < i; ++j) sum -= m[RS_T(i, j)] * z[j];
-        z[i] = sum;
-    }
-}
-
-// z <- L^-T D^-1 z
-__device__ __forceinline__ void backward6_packed(const double (&m)[21], const double (&dinv)[6], double (&z)[6])
-{
-#pragma unroll
-    for (int i = 5; i >= 0; --i) {
-        double sum = z[i] * dinv[i];
-#pragma unroll
-        for (int j = i + 1; j < 6; ++j) sum -= m[RS_T(j, i)] * z[j];
-        z[i] = sum;
-    }
-}
-
-// Rank-deficient / ill-conditioned J (a pivot of the unpivoted factorisation collapsed): MINPACK's pivoted path.
-// Diagonally pivoted LDL^T of C gives the rank and the basic Gauss-Newton solution (zeros on the dependent columns);
-// parl = 0 when the rank is deficient. Rare (degenerate subsets, a frozen coordinate), so plain loops on local arrays.
-__device__ __noinline__ void lmpar_deficient(WarpLM& S)
-{
-    const double dwarf = DBL_MIN, delta = S.delta;
-    double M[36], dinv[6], sg[6], e2[6], z[6], x[6], wa2[6];
-    int perm[6];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j <= i; ++j) M[i * 6 + j] = M[j * 6 + i] = S.C[RS_T(i, j)];
-    for (int j = 0; j < 6; ++j) {
-        perm[j] = j;
-        sg[j] = S.sc[j] * S.g[j];
-        const double e = S.diag[j] * S.sc[j];
-        e2[j] = e * e;
-    }
-    int rank = 6;
-    for (int k = 0; k < 6; ++k) {
-        int piv = k;
-        double best = M[k * 6 + k];
-        for (int i = k + 1; i < 6; ++i)
-            if (M[i * 6 + i] > best) best = M[i * 6 + i], piv = i;
-        if (piv != k) {
-            for (int j = 0; j < 6; ++j) {
-                const double t = M[k * 6 + j];
-                M[k * 6 + j] = M[piv * 6 + j], M[piv * 6 + j] = t;
-            }
-            for (int i = 0; i < 6; ++i) {
-                const double t = M[i * 6 + k];
-                M[i * 6 + k] = M[i * 6 + piv], M[i * 6 + piv] = t;
-            }
-            const int t = perm[k];
-            perm[k] = perm[piv], perm[piv] = t;
-        }
-        // C has a unit diagonal: a pivot at rounding level means a column that depends on the previous ones
-        if (!(best > 64.0 * DBL_EPSILON)) {
-            rank = k;
-            break;
-        }
-        dinv[k] = 1.0 / best;
-        for (int i = k + 1; i < 6; ++i) {
-            const double lik = M[i * 6 + k] * dinv[k];
-            for (int j = k + 1; j <= i; ++j) M[i * 6 + j] -= lik * M[j * 6 + k];
-        }
-        for (int i = k + 1; i < 6; ++i) M[i * 6 + k] *= dinv[k];
-    }
-    // basic solution on the leading `rank` pivots
-    for (int i = 0; i < rank; ++i) {
-        double sum = sg[perm[i]];
-        for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
-        z[i] = sum;
-    }
-    for (int i = rank - 1; i >= 0; --i) {
-        double sum = z[i] * dinv[i];
-        for (int j = i + 1; j < rank; ++j) sum -= M[j * 6 + i] * z[j];
-        z[i] = sum;
-    }
-    for (int i = 0; i < 6; ++i) x[perm[i]] = i < rank ? S.sc[perm[i]] * z[i] : 0.0;
-    for (int j = 0; j < 6; ++j) wa2[j] = S.diag[j] * x[j];
-    double dxnorm = norm6(wa2);
-    double fp = dxnorm - delta;
-    if (fp <= 0.1 * delta) {
-        S.par = 0.0;
-        for (int j = 0; j < 6; ++j) S.xs[j] = x[j];
-        return;
-    }
-    double parl = 0.0;
-    if (rank == 6) {
-        double q = 0.0;
-        for (int i = 0; i < 6; ++i) {
-            const int pi = perm[i];
-            double sum = S.sc[pi] * (S.diag[pi] * wa2[pi] / dxnorm);
-            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
-            z[i] = sum;
-            q += sum * sum * dinv[i];
-        }
-        parl = fp / delta / q;
-    }
-    double gn = 0.0;
-    for (int j = 0; j < 6; ++j) {
-        const double t = S.g[j] / S.diag[j];
-        gn += t * t;
-    }
-    const double gnorm = sqrt(gn);
-    double paru = gnorm / delta;
-    if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
-    double par = fmin(fmax(S.par, parl), paru);
-    if (par == 0.0) par = gnorm / dxnorm;
-    for (int iter = 1;; ++iter) {
-        if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-        // unpivoted LDL^T of C + par E^2 (positive definite for par > 0)
-        for (int i = 0; i < 6; ++i) {
-            for (int j = 0; j < i; ++j) M[i * 6 + j] = S.C[RS_T(i, j)];
-            M[i * 6 + i] = S.C[RS_T(i, i)] + par * e2[i];
-        }
-        for (int k = 0; k < 6; ++k) {
-            dinv[k] = 1.0 / M[k * 6 + k];
-            for (int i = k + 1; i < 6; ++i) {
-                const double lik = M[i * 6 + k] * dinv[k];
-                for (int j = k + 1; j <= i; ++j) M[i * 6 + j] -= lik * M[j * 6 + k];
-            }
-            for (int i = k + 1; i < 6; ++i) M[i * 6 + k] *= dinv[k];
-        }
-        for (int i = 0; i < 6; ++i) {
-            double sum = sg[i];
-            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
-            z[i] = sum;
-        }
-        for (int i = 5; i >= 0; --i) {
-            double sum = z[i] * dinv[i];
-            for (int j = i + 1; j < 6; ++j) sum -= M[j * 6 + i] * z[j];
-            z[i] = sum;
-        }
-        for (int j = 0; j < 6; ++j) {
-            x[j] = S.sc[j] * z[j];
-            wa2[j] = S.diag[j] * x[j];
-        }
-        dxnorm = norm6(wa2);
-        const double temp = fp;
-        fp = dxnorm - delta;
-        if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-        double q = 0.0;
-        for (int i = 0; i < 6; ++i) {
-            double sum = S.sc[i] * (S.diag[i] * (wa2[i] / dxnorm));
-            for (int j = 0; j < i; ++j) sum -= M[i * 6 + j] * z[j];
-            z[i] = sum;
-            q += sum * sum * dinv[i];
-        }
-        const double parc = fp / delta / q;
-        if (fp > 0.0) parl = fmax(parl, par);
-        if (fp < 0.0) paru = fmin(paru, par);
-        par = fmax(parl, par + parc);
-    }
-    S.par = par;
-    for (int j = 0; j < 6; ++j) S.xs[j] = x[j];
-}
-
-// unsupported/Eigen/src/NonLinearOptimization/lmpar.h (lmpar2): trust-region parameter S.par and step S.xs.
-// One factorise-and-solve body serves the Gauss-Newton step (pass 0, par = 0) and the damped steps (passes 1..10).
-__device__ __forceinline__ void lmpar(WarpLM& S)
-{
-    const double dwarf = DBL_MIN;
-    const double delta = S.delta;
-    double sg[6], e2[6], x[6], wa2[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        sg[j] = S.sc[j] * S.g[j];
-        const double e = S.diag[j] * S.sc[j];
-        e2[j] = e * e;
-    }
-    double par = 0.0, parl = 0.0, paru = 0.0, fp = 0.0;
-    int iter = 0;
-#pragma unroll 1
-    while (true) {
-        double M[21], dinv[6], z[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int j = 0; j < i; ++j) M[RS_T(i, j)] = S.C[RS_T(i, j)];
-            M[RS_T(i, i)] = S.C[RS_T(i, i)] + par * e2[i];
-            z[i] = sg[i];
-        }
-        const bool ok = ldl6_packed(M, dinv, 64.0 * DBL_EPSILON);
-        if (iter == 0 && !ok) {
-            lmpar_deficient(S);
-            return;
-        }
-        forward6_packed(M, z);
-        backward6_packed(M, dinv, z);
-        double dx2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            x[j] = S.sc[j] * z[j];
-            wa2[j] = S.diag[j] * x[j];
-            dx2 += wa2[j] * wa2[j];
-        }
-        const double idx = dx2 > 0.0 ? rsqrt(dx2) : 0.0;   // 1 / |D x|
-        const double dxnorm = dx2 * idx;
-        const double temp = fp;
-        fp = dxnorm - delta;
-        if (iter == 0) {
-            if (fp <= 0.1 * delta) break;  // the Gauss-Newton step is inside the trust region: par = 0
-        }
-        else if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10)
-            break;
-        // Newton correction fp / delta / (w^T (C + par E^2)^-1 w), w = S D^2 x / |D x| (at par = 0 this is parl)
-        double q = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) z[i] = S.sc[i] * (S.diag[i] * (wa2[i] * idx));
-        forward6_packed(M, z);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) q += z[i] * z[i] * dinv[i];
-        const double parc = fp / (delta * q);
-        if (iter == 0) {
-            parl = parc;
-            double gn = 0.0;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const double t = S.g[j] / S.diag[j];
-                gn += t * t;
-            }
-            const double gnorm = sqrt(gn);
-            paru = gnorm / delta;
-            if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
-            par = fmin(fmax(S.par, parl), paru);
-            if (par == 0.0) par = gnorm / dxnorm;
-        }
-        else {
-            if (fp > 0.0) parl = fmax(parl, par);
-            if (fp < 0.0) paru = fmin(paru, par);
-            par = fmax(parl, par + parc);
-        }
-        if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-        ++iter;
-    }
-    S.par = par;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) S.xs[j] = x[j];
-}
-
-// Eigen::LevenbergMarquardt<NumericalDiff<F,Forward>>::minimize on S.x (in/out). Whole warp must call; returns the
-// Eigen status (<= 0 failure, 1..8 MINPACK info). m = residual count of the problem. Inlined at exactly ONE call site per
-// kernel: the body is ~4k instructions and the serial lane-0 chains are latency bound, so instruction-cache residency
-// matters, and inlining lets the compiler see that S and the feature arrays live in shared memory (LDS, not generic LD).
-template <bool P2D>
-__device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const int m,
-                                             const int maxfev, const int lane, const volatile int* abort = nullptr)
-{
-    if (m < 6 || maxfev <= 0) return 0;  // ImproperInputParameters
-    if (lane == 0) make_xform(S.x, S.T);
-    __syncwarp();
-    {
-        const double ss = eval_sumsq<P2D>(P, S.T, K, lane);
-        if (lane == 0) {
-            S.fnorm = sqrt(ss);
-            S.par = 0.0, S.delta = 0.0, S.xnorm = 0.0;
-            S.iter = 1, S.nfev = 1, S.status = kRunning;
-        }
-    }
-    __syncwarp();
-
-#pragma unroll 1
-    while (true) {
-        // a speculative RANSAC hypothesis is dropped as soon as the serial rule has stopped the loop before it
-        if (abort && *abort) return 0;
-        // ---- Jacobian set-up: R'(x) on lane 0, R'(x + h_k e_k) on lanes 1..3, then the 27 difference quotients ----
-        if (lane < 4) {
-            double xx[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) xx[j] = S.x[j];
-            double h = 0.0;
-#pragma unroll
-            for (int j = 3; j < 6; ++j)
-                if (lane == j - 2) {
-                    h = kSqrtEps * fabs(xx[j]);  // NumericalDiff: h = sqrt(eps) |x_j|, or sqrt(eps) when x_j == 0
-                    if (h == 0.0) h = kSqrtEps;
-                    xx[j] += h;
-                }
-            Xform Tk;
-            make_xform(xx, Tk);
-            if (lane == 0)
-                S.T = Tk;
-            else {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) S.Rk[lane - 1][i] = Tk.R[i];
-                S.ih[lane - 1] = 1.0 / h;
-            }
-        }
-        __syncwarp();
-        if (lane < 27) {
-            const int k = lane / 9, i = lane - 9 * k;
-            S.dR[lane] = (S.Rk[k][i] - S.T.R[i]) * S.ih[k];
-        }
-        __syncwarp();
-        double a[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) a[i] = 0.0;
-#pragma unroll 1
-        for (int k = lane; k < P.n; k += 32) {
-            int type;
-            double o[4], mm[4];
-            const int gi = load_feature(P, k, type, o, mm);
-            if (P2D && type == RS_FEAT_POINT2D) {
-                double c[27];   // out of line and through local memory, so that a[] stays in registers
-                point2d_jacobian(o, mm, P.aux, P.M, gi, S, K, c);
-#pragma unroll
-                for (int i = 0; i < 27; ++i) a[i] += c[i];
-            }
-            else
-                feature_jacobian(type, o, mm, S.T, S.dR, K, a);
-        }
-        const double mine = reduce_scatter32(a, lane);
-        if (lane < 21) {
-            int i = 0, rem = lane;
-            while (rem >= 6 - i) rem -= 6 - i, ++i;
-            const int j = i + rem;
-            S.A[i * 6 + j] = mine;
-            S.A[j * 6 + i] = mine;
-        }
-        else if (lane < 27)
-            S.g[lane - 21] = mine;
-        __syncwarp();
-
-        if (lane == 0) {
-            S.nfev += 7;  // NumericalDiff re-evaluates f(x) and then one evaluation per column
-            double sc[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const double ajj = S.A[j * 6 + j];
-                sc[j] = ajj > 0.0 ? rsqrt(ajj) : 1.0;   // 1 / |J_j|
-                S.wa2[j] = ajj > 0.0 ? ajj * sc[j] : 0.0;
-                S.sc[j] = sc[j];
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) S.C[RS_T(i, j)] = S.A[i * 6 + j] * sc[i] * sc[j];
-            if (S.iter == 1) {
-                double tt[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    S.diag[j] = (S.wa2[j] == 0.0) ? 1.0 : S.wa2[j];
-                    tt[j] = S.diag[j] * S.x[j];
-                }
-                S.xnorm = norm6(tt);
-                S.delta = 100.0 * S.xnorm;
-                if (S.delta == 0.0) S.delta = 100.0;
-            }
-            // gnorm = max_j |J_j . r| / (|J_j| |r|)
-            double gnorm = 0.0;
-            if (S.fnorm != 0.0) {
-                const double ifn = 1.0 / S.fnorm;
-#pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    if (S.wa2[j] != 0.0) gnorm = fmax(gnorm, fabs((S.g[j] * ifn) * sc[j]));
-            }
-            S.gnorm = gnorm;
-            if (gnorm <= 0.0) S.status = 4;  // CosinusTooSmall (gtol = 0)
-#pragma unroll
-            for (int j = 0; j < 6; ++j) S.diag[j] = fmax(S.diag[j], S.wa2[j]);
-        }
-        __syncwarp();
-        if (S.status != kRunning) break;
-
-        // ---- inner loop: trust-region step until the ratio is acceptable ----
-#pragma unroll 1
-        while (true) {
-            if (lane == 0) {
-                lmpar(S);
-                double tt[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    S.p[j] = -S.xs[j];
-                    S.xt[j] = S.x[j] + S.p[j];
-                    tt[j] = S.diag[j] * S.p[j];
-                }
-                S.pnorm = norm6(tt);
-                if (S.iter == 1) S.delta = fmin(S.delta, S.pnorm);
-                make_xform(S.xt, S.T);
-            }
-            __syncwarp();
-            const double ss1 = eval_sumsq<P2D>(P, S.T, K, lane);
-            if (lane == 0) {
-                ++S.nfev;
-                const double fnorm = S.fnorm, fnorm1 = sqrt(ss1), pnorm = S.pnorm;
-                const double inv_fnorm = 1.0 / fnorm;
-                double actred = -1.0;
-                if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 * inv_fnorm) * (fnorm1 * inv_fnorm);
-                // |J p|^2 = p^T A p
-                double pAp = 0.0;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    double sum = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) sum += S.A[i * 6 + j] * S.p[j];
-                    pAp += sum * S.p[i];
-                }
-                const double temp1 = fmax(pAp, 0.0) * inv_fnorm * inv_fnorm;
-                const double temp2 = S.par * (pnorm * inv_fnorm) * (pnorm * inv_fnorm);
-                const double prered = temp1 + temp2 * 2.0;
-                const double dirder = -(temp1 + temp2);
-                double ratio = 0.0;
-                if (prered != 0.0) ratio = actred / prered;
-                if (ratio <= 0.25) {
-                    double temp = 0.0;
-                    if (actred >= 0.0) temp = 0.5;
-                    if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
-                    if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
-                    S.delta = temp * fmin(S.delta, pnorm * 10.0);
-                    S.par /= temp;
-                }
-                else if (!(S.par != 0.0 && ratio < 0.75)) {
-                    S.delta = pnorm * 2.0;
-                    S.par = 0.5 * S.par;
-                }
-                if (ratio >= 1e-4) {
-                    double tt[6];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        S.x[j] = S.xt[j];
-                        tt[j] = S.diag[j] * S.x[j];
-                    }
-                    S.xnorm = norm6(tt);
-                    S.fnorm = fnorm1;
-                    ++S.iter;
-                }
-                const double ftol = kSqrtEps, xtol = kSqrtEps;
-                int status = kRunning;
-                if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && S.delta <= xtol * S.xnorm)
-                    status = 3;
-                else if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0)
-                    status = 1;
-                else if (S.delta <= xtol * S.xnorm)
-                    status = 2;
-                else if (S.nfev >= maxfev)
-                    status = 5;
-                else if (fabs(actred) <= DBL_EPSILON && prered <= DBL_EPSILON && 0.5 * ratio <= 1.0)
-                    status = 6;
-                else if (S.delta <= DBL_EPSILON * S.xnorm)
-                    status = 7;
-                else if (S.gnorm <= DBL_EPSILON)
-                    status = 8;
-                S.status = status;
-                S.again = (status == kRunning && ratio < 1e-4) ? 1 : 0;
-            }
-            __syncwarp();
-            if (S.status != kRunning || !S.again) break;
-        }
-        if (S.status != kRunning) break;
-    }
-    const int status = S.status;
-    __syncwarp();
-    return status;
-}
-
-// compute_optimized_global_pose (pose_optimization.cpp:302-359) for the whole warp. x0 -> S.x; returns success and
-// leaves the optimised coefficients in S.x.
-template <bool P2D>
-__device__ __forceinline__ bool optimize_pose_warp(WarpLM& S, const Problem& P, const PoseIntrinsics& K, const double* x0,
-                                                   const int m, const double score, const int maxfev, const int lane,
-                                                   const volatile int* abort = nullptr)
-{
-    bool finite = true;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) finite = finite && isfinite(x0[j]);
-    if (!finite || m <= 1 || score < 1.0) return false;
-    if (lane == 0)
-        for (int j = 0; j < 6; ++j) S.x[j] = x0[j];
-    __syncwarp();
-    const int status = lm_minimize_warp<P2D>(S, P, K, m, maxfev, lane, abort);
-    if (status <= 0) return false;
-    // the reference rejects a pose whose [position, Euler angles] vector has a NaN: that vector is finite exactly
-    // when the coefficients and the quaternion built from them are
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) ok = ok && isfinite(S.x[j]);
-    return ok && isfinite(S.x[3] * S.x[3] + S.x[4] * S.x[4] + S.x[5] * S.x[5]);
-}
-
-// ---- counter-based generator of the RS_RNG_DEVICE mode --------------------------------------------------------------
-__host__ __device__ inline uint64_t mix64(uint64_t z)
-{
-    z += 0x9e3779b97f4a7c15ull;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
-__device__ inline uint64_t rng_key(const uint32_t seed, const uint32_t domain, const uint32_t frame)
-{
-    return mix64((uint64_t(seed) << 32) ^ (uint64_t(domain) << 24) ^ frame);
-}
-// Four standard normals for (frame, sample, feature): two Box-Muller pairs, each from one 64-bit counter hash. The pair
-// is evaluated in FP32 with the MUFU intrinsics (24-bit uniforms, |g| <= 5.8) and widened: a Monte-Carlo perturbation
-// needs the distribution, not 53 bits, and the FP64 log / sqrt / sincospi chain was 10 % of the variance kernel.
-// pose_export_normals_kernel returns exactly these values, which is how the oracle is fed the same draws.
-__device__ inline void device_normals(const uint32_t seed, const int frame, const int sample, const int feature,
-                                      double g[4])
-{
-    const uint64_t key = rng_key(seed, 2u, uint32_t(frame));
-    const uint64_t ctr = (uint64_t(uint32_t(sample)) << 32) | (uint64_t(uint32_t(feature)) << 1);
-#pragma unroll
-    for (int pair = 0; pair < 2; ++pair) {
-        const uint64_t a = mix64(key ^ mix64(ctr + uint64_t(pair)));
-        const float u1 = (float(uint32_t(a >> 40)) + 1.0f) * 5.9604644775390625e-08f;        // (0, 1]
-        const float u2 = float(uint32_t(a >> 8) & 0xffffffu) * 5.9604644775390625e-08f;     // [0, 1)
-        const float rad = sqrtf(-2.0f * __logf(u1));
-        float sn, cs;
-        __sincosf(6.2831853071795865f * u2, &sn, &cs);
-        g[2 * pair] = double(rad * cs);
-        g[2 * pair + 1] = double(rad * sn);
-    }
-}
 
 // ---- kernels ----------------------------------------------------------------------------------------------------------
 
@@ -1159,39 +134,98 @@ __global__ void __launch_bounds__(THREADS) pose_prepare_kernel(const PoseBuffers
         buf.out[b] = o;
         for (int j = 0; j < 7; ++j) buf.poses[b * 7 + j] = o.pose[j];
     }
+    // ---- work state of the fused kernel for this frame ----
+    {
+        RansacFrame* g = buf.rframe + b;
+        int* gi = reinterpret_cast<int*>(g);
+        for (int i = threadIdx.x; i < int(sizeof(RansacFrame) / sizeof(int)); i += blockDim.x) gi[i] = 0;
+        const int words = (M + 31) / 32;
+        unsigned* best = buf.ring_mask + (size_t(b) * (kRansacRing + 1) + kRansacRing) * words;
+        for (int i = threadIdx.x; i < words; i += blockDim.x) best[i] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double x0[6];
+            coefficients_from_pose(buf.cur_pose + b * 7, x0);
+            for (int j = 0; j < 6; ++j) g->best_x[j] = x0[j];
+            g->max_score = 1.0;
+            g->best_iteration = -1;
+            buf.mc_done[b] = 0;
+            for (int k = 0; k < 4; ++k) buf.frame_times[b * 4 + k] = 0ull;
+            buf.ready[blockIdx.x] = 0;
+            buf.open_list[blockIdx.x] = 0;
+            if (blockIdx.x == 0) {
+                PoseWork w;
+                w.join_ticket = 0, w.frames_done = 0, w.n_ready = 0, w.mc_head = 0, w.n_open = 0;
+                w.mc_done_tasks = 0, w.pad[0] = w.pad[1] = 0;
+                w.t_first = ~0ull, w.t_ransac_end = 0ull, w.t_last = 0ull;
+                for (int k = 0; k < 8; ++k) w.dbg[k] = 0ull;
+                *buf.work = w;
+            }
+        }
+    }
 }
 
-constexpr int RRING = 8;   // hypotheses that may be in flight or finished-but-unapplied beyond the serial rule's position
 
-struct RansacShared {
-    double best_x[6];
-    double max_score;
-    int best_inliers, best_iteration, can_quit, started;
-    int next_iter;   // next hypothesis index to hand out
-    int applied;     // hypotheses whose bookkeeping has been applied, in iteration order
-    int lock;        // guards the in-order bookkeeping
-    int done[RRING]; // iteration + 1 once the slot's result is complete
-    double hyp_x[RRING][6];
-    double hyp_score[RRING];
-    int hyp_ok[RRING];
-    int hyp_inliers[RRING];
+// ---- the fused solve kernel ------------------------------------------------------------------------------------------------
+// compute_pose_with_ransac (pose_optimization.cpp:107-262), compute_pose_variance (:361-437) and
+// compute_random_variation_of_pose (:482-501) of a whole batch in ONE persistent kernel. The three stages of a frame used
+// to be three launches, and a stage of the batch lasted as long as its slowest frame: the hypothesis stage is a latency
+// chain that leaves four fifths of the issue slots idle, and the Monte-Carlo solves (throughput bound) could not start
+// before the last frame's final LM. Here a frame's Monte-Carlo solves are published the moment ITS final LM is done and
+// are picked up by whichever CTA has nothing more urgent to do; the covariance is reduced by the CTA that finishes a
+// frame's last sample group. CTAs (four warps) are persistent and take, in this order:
+//   1. a frame nobody has started: stage its matches in shared memory and run its hypotheses (the warps claim iteration
+//      indices; iterations 0..3 are always needed - the reference cannot stop before the fourth), then the final LM on the
+//      warp that applied the terminal hypothesis;
+//   2. a Monte-Carlo task (frame, group of four samples), one sample per warp;
+//   3. a frame on the help list (its loop went past the minimum of four and has iterations left): the frame's ring of
+//      hypothesis results lives in global memory, so any number of CTAs can claim its iterations - a 1024-hypothesis
+//      frame spreads over the whole GPU;
+//   4. nothing: sleep and look again, or leave when every frame is through and no task is left.
+// Every wait is for work held by a CTA that is running (tickets are only ever taken by resident CTAs), so the kernel makes
+// progress whatever part of the grid is resident - CTAs that only become resident when another kernel's CTAs retire (the
+// cell-graph segmentation runs beside the hypothesis stage) simply join in.
+// One LM call site per kernel, as before: the three kinds of problem (hypothesis, final, Monte-Carlo sample) are set up in
+// front of it and taken apart behind it.
+// Cross-CTA state is read with volatile / .cg loads (L2) and published fence-then-flag; gpu-scope fences are kept off the
+// per-iteration paths (on sm_100 each one also invalidates the SM's L1, where register spills live).
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_volatile(int* p, const int v) { *reinterpret_cast<volatile int*>(p) = v; }
+__device__ __forceinline__ double ld_volatile(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
+__device__ __forceinline__ void st_volatile(double* p, const double v) { *reinterpret_cast<volatile double*>(p) = v; }
+__device__ __forceinline__ unsigned long long global_timer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct FrameFlags {
+    int can_quit, closed, opened, applied;
 };
+__device__ __forceinline__ FrameFlags load_flags(const RansacFrame* g)   // the first 16 bytes of the frame's state, one load
+{
+    FrameFlags f;
+    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(f.can_quit), "=r"(f.closed), "=r"(f.opened), "=r"(f.applied) : "l"(g));
+    return f;
+}
+__device__ __forceinline__ void count(PoseWork* W, const int k, const unsigned long long v = 1ull) { atomicAdd(&W->dbg[k], v); }
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) / 16 * 16; }
 
-// shared-memory carve-up of the RANSAC kernel
-struct RansacSmem {
-    int32_t* type;
-    double* obs;
-    double* map;
-    WarpLM* lm;
-    unsigned* hyp_mask;   // [RRING][words]
-    unsigned* best_mask;  // [words]
-    short* subset;        // [RWARPS][RS_MAX_SUBSET]
-    short* inlier_idx;    // [M]
-    RansacShared* sh;
+// shared-memory carve-up. Monte-Carlo task: the frame's observations, and per warp the perturbed map side of its sample.
+// Hypothesis task: the observations and, in the first warp's region, the map side.
+struct FusedSmem {
+    double* obs;        // [4][M] the frame's observations
+    double* pmap;       // [warps][4][M]
+    WarpLM* lm;         // [warps]
+    int32_t* type;      // [M]
+    short* idx;         // [M] inlier indices (final LM / Monte-Carlo)
+    unsigned* wmask;    // [warps][words] inlier mask of the hypothesis a warp is scoring
+    short* subset;      // [warps][RS_MAX_SUBSET]
+    int* ctl;           // [8] task hand-over
 };
-__host__ __device__ inline size_t ransac_carve(RansacSmem* s, unsigned char* base, const int M)
+__host__ __device__ inline size_t fused_carve(FusedSmem* s, unsigned char* base, const int M, const int warps, const bool mc_role = true)
 {
     const int words = (M + 31) / 32;
     size_t o = 0;
@@ -1201,140 +235,206 @@ __host__ __device__ inline size_t ransac_carve(RansacSmem* s, unsigned char* bas
         return p;
     };
     unsigned char* obs = take(sizeof(double) * 4 * M);
-    unsigned char* map = take(sizeof(double) * 4 * M);
-    unsigned char* lm = take(sizeof(WarpLM) * RWARPS);
-    unsigned char* sh = take(sizeof(RansacShared));
+    unsigned char* pm = take(sizeof(double) * size_t(mc_role ? warps : 1) * 4 * M);   // without the Monte-Carlo role: the map side only
+    unsigned char* lm = take(sizeof(WarpLM) * warps);
     unsigned char* type = take(sizeof(int32_t) * M);
-    unsigned char* hm = take(sizeof(unsigned) * RRING * words);
-    unsigned char* bm = take(sizeof(unsigned) * words);
-    unsigned char* sub = take(sizeof(short) * RWARPS * RS_MAX_SUBSET);
-    unsigned char* ii = take(sizeof(short) * M);
+    unsigned char* idx = take(sizeof(short) * M);
+    unsigned char* wm = take(sizeof(unsigned) * size_t(warps) * words);
+    unsigned char* sub = take(sizeof(short) * warps * RS_MAX_SUBSET);
+    unsigned char* ctl = take(sizeof(int) * 8);
     if (s) {
-        s->obs = reinterpret_cast<double*>(obs), s->map = reinterpret_cast<double*>(map);
-        s->lm = reinterpret_cast<WarpLM*>(lm), s->sh = reinterpret_cast<RansacShared*>(sh);
-        s->type = reinterpret_cast<int32_t*>(type), s->hyp_mask = reinterpret_cast<unsigned*>(hm);
-        s->best_mask = reinterpret_cast<unsigned*>(bm), s->subset = reinterpret_cast<short*>(sub);
-        s->inlier_idx = reinterpret_cast<short*>(ii);
+        s->obs = reinterpret_cast<double*>(obs), s->pmap = reinterpret_cast<double*>(pm);
+        s->lm = reinterpret_cast<WarpLM*>(lm), s->type = reinterpret_cast<int32_t*>(type);
+        s->idx = reinterpret_cast<short*>(idx), s->wmask = reinterpret_cast<unsigned*>(wm);
+        s->subset = reinterpret_cast<short*>(sub), s->ctl = reinterpret_cast<int*>(ctl);
     }
     return o;
 }
 
-// compute_pose_with_ransac (pose_optimization.cpp:107-262): one CTA per frame.
-template <bool P2D>
-__global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuffers buf, const PoseLaunch prm)
+enum { TASK_EXIT = 0, TASK_RANSAC = 1, TASK_MC = 2 };
+enum { DBG_HYP_FIRST = 0, DBG_HYP_HELPER, DBG_APPLY_BATCHES, DBG_APPLIED, DBG_HELPER_JOINS, DBG_MC_TASKS, DBG_ABORTED, DBG_IDLE_LOOPS };
+
+// The reference's serial bookkeeping (pose_optimization.cpp:151-227), applied strictly in iteration order by the warp that
+// holds the frame's lock (all 32 lanes call): every finished hypothesis whose predecessors have all been applied is folded
+// into the best-so-far state; the early stop freezes the state exactly where the serial loop would have left it.
+// Up to 32 consecutive finished hypotheses are taken per round: their results are loaded one per lane, the serial rule runs
+// over them in registers, the winner's pose and inlier mask are copied, and the frame's flags are published once.
+// Returns true when THIS call closed the hypothesis stage (early stop, or the last iteration applied): the calling warp
+// then owns the frame's final LM.
+__device__ __noinline__ bool apply_ready_warp(RansacFrame* g, unsigned* ring, const int words, const int maxIterations,
+                                             const unsigned inliersToStop, PoseWork* W, int32_t* open_list, const int frame,
+                                             const int lane)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = prm.frame0 + blockIdx.x;
+    for (;;) {
+        const FrameFlags f = load_flags(g);
+        if (f.can_quit || f.closed || f.applied >= maxIterations) return false;
+        const int ap = f.applied;
+        const int mine = ap + lane;
+        const int slot = mine % kRansacRing;
+        const bool ready = mine < maxIterations && ld_volatile(&g->done[slot]) == mine + 1;
+        const unsigned rb = __ballot_sync(FULL, ready);
+        const int cnt = rb == FULL ? 32 : __ffs(~rb) - 1;   // leading run of finished hypotheses
+        if (cnt <= 0) return false;
+        double hs = 0.0;
+        int hin = 0, hok = 0;
+        if (lane < cnt) {
+            hs = ld_volatile(&g->slot[slot].score);
+            hin = ld_volatile(&g->slot[slot].inliers);
+            hok = ld_volatile(&g->slot[slot].ok);
+        }
+        double ms = ld_volatile(&g->max_score);
+        int bi = ld_volatile(&g->best_inliers), bit = ld_volatile(&g->best_iteration), started = ld_volatile(&g->started);
+        int best_lane = -1, used = 0;
+        bool quit = false;
+        for (int j = 0; j < cnt; ++j) {
+            const double s_j = __shfl_sync(FULL, hs, j);
+            const int in_j = __shfl_sync(FULL, hin, j), ok_j = __shfl_sync(FULL, hok, j);
+            const int i = ap + j;
+            ++started, ++used;
+            if (ok_j && s_j >= 1.0) {
+                const bool canOverload = (s_j > ms) || (fabs(s_j - ms) <= 0.1 && bi < in_j);
+                if (canOverload) ms = s_j, bi = in_j, bit = i, best_lane = j;
+                if (i >= 3 && unsigned(bi) > inliersToStop) {
+                    quit = true;
+                    break;
+                }
+            }
+        }
+        if (best_lane >= 0) {   // before the slots can be handed out again
+            const int bs = (ap + best_lane) % kRansacRing;
+            if (lane < 6) st_volatile(&g->best_x[lane], ld_volatile(&g->slot[bs].x[lane]));
+            volatile unsigned* src = ring + size_t(bs) * words;
+            volatile unsigned* dst = ring + size_t(kRansacRing) * words;
+            for (int k = lane; k < words; k += 32) dst[k] = src[k];
+        }
+        __syncwarp();
+        const int nap = ap + used;
+        const bool closed_now = quit || nap == maxIterations;
+        if (lane == 0) {
+            st_volatile(&g->max_score, ms);
+            st_volatile(&g->best_inliers, bi);
+            st_volatile(&g->best_iteration, bit);
+            st_volatile(&g->started, started);
+            __threadfence();   // the state before the flags
+            if (quit) st_volatile(&g->can_quit, 1);
+            st_volatile(&g->applied, nap);
+            if (closed_now) st_volatile(&g->closed, 1);
+            else if (nap >= 4 && !f.opened) {
+                // the minimum of four hypotheses did not stop the loop: more warps pay off from here on
+                st_volatile(&g->opened, 1);
+                const int s = atomicAdd(&W->n_open, 1);
+                st_volatile(&open_list[s], frame + 1);
+            }
+            count(W, DBG_APPLY_BATCHES);
+            count(W, DBG_APPLIED, unsigned(used));
+        }
+        __syncwarp();
+        if (closed_now) return true;
+    }
+}
+
+// Takes the frame's bookkeeping lock if something is ready to be applied and applies it (all lanes call).
+// Returns 1 when this call closed the hypothesis stage, 0 otherwise; *busy = the lock was held by another warp.
+__device__ __forceinline__ int try_apply(RansacFrame* g, unsigned* ring, const int words, const int maxIterations,
+                                         const unsigned inliersToStop, PoseWork* W, int32_t* open_list, const int frame,
+                                         const int lane, const int applied)
+{
+    int got = 0;
+    if (lane == 0)
+        got = applied < maxIterations && ld_volatile(&g->done[applied % kRansacRing]) == applied + 1 && atomicCAS(&g->lock, 0, 1) == 0;
+    got = __shfl_sync(FULL, got, 0);
+    if (!got) return -1;
+    const bool closed_now = apply_ready_warp(g, ring, words, maxIterations, inliersToStop, W, open_list, frame, lane);
+    if (lane == 0) atomicExch(&g->lock, 0);
+    return closed_now ? 1 : 0;
+}
+
+// Hypotheses + final LM of frame b (pose_optimization.cpp:107-262), run by all warps of the CTA; `arg` != 0 for the frame's
+// first CTA. Called inline by the kernel instantiation that has the frame role only, out of line by the one that also
+// carries the Monte-Carlo role (there it is the fallback that keeps every resident CTA able to take whatever work there is).
+template <bool P2D>
+__device__ __forceinline__ void frame_task(const PoseBuffers& buf, const PoseLaunch& prm, const FusedSmem& sm, PoseWork* W, const int b,
+                                           const int arg, const int n, const int warp, const int lane)
+{
     const int M = buf.max_matches;
     const int words = (M + 31) / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    RansacSmem sm;
-    ransac_carve(&sm, smem_raw, M);
-    const PoseFrameState st = buf.state[b];
-    const int n = st.n;
-    if (!st.valid || st.total_score < 1.0) return;  // out[b] already says status 0, pose = current pose
-
+    const int maxIterations = prm.max_iterations;
+    const PoseFrameState* stp = buf.state + b;
+    WarpLM& S = sm.lm[warp];
+    short* subset = sm.subset + warp * RS_MAX_SUBSET;
+    unsigned* wmask = sm.wmask + size_t(warp) * words;
+    // ======================= hypotheses + final LM of frame b (pose_optimization.cpp:107-262) =======================
+    const bool first = arg != 0;
+    const bool usable = __ldcg(&stp->valid) && __ldcg(&stp->total_score) >= 1.0;
+    if (!usable) {   // out[b] already says status 0, pose = current pose (helpers never come here: the frame never opens)
+        if (threadIdx.x == 0) atomicAdd(&W->frames_done, 1);
+        __syncthreads();
+        return;
+    }
+    double* s_obs = sm.obs;
+    double* s_map = sm.pmap;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         sm.type[i] = buf.type[size_t(b) * M + i];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            sm.obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
-            sm.map[c * M + i] = buf.map[(size_t(b) * 4 + c) * M + i];
+            s_obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
+            s_map[c * M + i] = buf.map[(size_t(b) * 4 + c) * M + i];
         }
     }
     double x0[6];
     coefficients_from_pose(buf.cur_pose + b * 7, x0);
-    RansacShared& sh = *sm.sh;
-    if (threadIdx.x == 0) {
-        sh.max_score = 1.0;
-        sh.best_inliers = 0, sh.best_iteration = -1, sh.can_quit = 0, sh.started = 0;
-        sh.next_iter = 0, sh.applied = 0, sh.lock = 0;
-        for (int k = 0; k < RRING; ++k) sh.done[k] = 0;
-        for (int j = 0; j < 6; ++j) sh.best_x[j] = x0[j];
-    }
-    for (int i = threadIdx.x; i < words; i += blockDim.x) sm.best_mask[i] = 0u;
+    RansacFrame* g = buf.rframe + b;
+    unsigned* ring = buf.ring_mask + size_t(b) * (kRansacRing + 1) * words;
+    const unsigned inliersToStop = unsigned(ceil(double(n) * kEarlyStopProportion));
+    Problem P;
+    P.type = sm.type, P.obs = s_obs, P.map = s_map, P.M = M;
+    P.aux = buf.aux + size_t(b) * 4 * M;
+    rs_pose_out* out = buf.out + b;
+    if (first && threadIdx.x == 0) buf.frame_times[b * 4 + 0] = global_timer();
     __syncthreads();
 
-    const int maxIterations = prm.max_iterations;
-    const unsigned inliersToStop = unsigned(ceil(double(n) * kEarlyStopProportion));
-    WarpLM& S = sm.lm[warp];
-    short* subset = sm.subset + warp * RS_MAX_SUBSET;
-    Problem P;
-    P.type = sm.type, P.obs = sm.obs, P.map = sm.map, P.M = M;
-    P.aux = buf.aux + size_t(b) * 4 * M;
-    volatile int* v_can_quit = &sh.can_quit;
-    volatile int* v_next = &sh.next_iter;
-    volatile int* v_applied = &sh.applied;
-    volatile int* v_done = sh.done;
-
-    // The reference's serial bookkeeping (:151-227), applied strictly in iteration order by whoever holds the lock:
-    // every finished hypothesis whose predecessors have all been applied is folded into the best-so-far state; the early
-    // stop freezes the state, exactly where the serial loop would have left it.
-    auto apply_ready = [&]() {
-        while (!*v_can_quit) {
-            const int i = *v_applied;
-            if (i >= maxIterations || v_done[i % RRING] != i + 1) break;
-            __threadfence_block();
-            const int slot = i % RRING;
-            ++sh.started;
-            if (sh.hyp_ok[slot]) {
-                const double hs = sh.hyp_score[slot];
-                if (hs >= 1.0) {
-                    const bool canOverload =
-                            (hs > sh.max_score) || (fabs(hs - sh.max_score) <= 0.1 && sh.best_inliers < sh.hyp_inliers[slot]);
-                    if (canOverload) {
-                        sh.max_score = hs;
-                        for (int j = 0; j < 6; ++j) sh.best_x[j] = sh.hyp_x[slot][j];
-                        for (int k = 0; k < words; ++k) sm.best_mask[k] = sm.hyp_mask[slot * words + k];
-                        sh.best_inliers = sh.hyp_inliers[slot];
-                        sh.best_iteration = i;
-                    }
-                    if (i >= 3 && unsigned(sh.best_inliers) > inliersToStop) *v_can_quit = 1;
-                }
-            }
-            __threadfence_block();
-            *v_applied = i + 1;
-        }
-    };
-
-    rs_pose_out* out = buf.out + b;
-    // One loop, one LM call site (the LM body is inlined once). Hypothesis passes: every warp keeps claiming the next
-    // iteration index (hypotheses are independent: each LM starts from the current pose) up to RRING ahead of the serial
-    // rule; a hypothesis that finishes after the early stop is simply never applied, and one still running is dropped at
-    // its next LM iteration. When nothing is left to claim the warps meet once, warp 0 runs the final optimisation on
-    // the winning inlier set and the others leave.
     bool finalPass = false;
     for (;;) {
         int it = -1;
         if (!finalPass) {
-            if (lane == 0) {
-                while (!*v_can_quit) {
-                    const int cur = *v_next;
-                    if (cur >= maxIterations) break;
-                    if (cur >= *v_applied + RRING) {   // ring full: help the bookkeeping catch up, or wait for it
-                        if (v_done[*v_applied % RRING] == *v_applied + 1 && atomicCAS(&sh.lock, 0, 1) == 0) {
-                            apply_ready();
-                            __threadfence_block();
-                            atomicExch(&sh.lock, 0);
-                        }
-                        else
-                            __nanosleep(200);
+            // ---- claim the next iteration index (all lanes walk this loop together) ----
+            int fin = 0;
+            unsigned backoff = 200;
+            for (;;) {
+                const FrameFlags f = load_flags(g);
+                if (f.can_quit || f.closed) {
+                    it = -1;
+                    break;
+                }
+                if (it < 0) {
+                    if (!first && !f.opened) {   // (a helper only joins opened frames; kept for safety)
+                        __nanosleep(backoff);
                         continue;
                     }
-                    if (atomicCAS(&sh.next_iter, cur, cur + 1) == cur) {
-                        it = cur;
+                    int t = -1;
+                    if (lane == 0 && ld_volatile(&g->next_iter) < maxIterations) t = atomicAdd(&g->next_iter, 1);
+                    t = __shfl_sync(FULL, t, 0);
+                    if (t < 0 || t >= maxIterations) {   // all handed out: whoever applies the last one takes the final LM
+                        it = -1;
                         break;
                     }
+                    it = t;
+                }
+                if (it < f.applied + kRansacRing) break;   // the ring slot of this iteration is free
+                // ring full: help the bookkeeping catch up, or wait for it
+                const int r = try_apply(g, ring, words, maxIterations, inliersToStop, W, buf.open_list, b, lane, f.applied);
+                if (r == 1) {
+                    fin = 1;   // the early stop fired here: the ticket is dropped, this warp runs the final LM
+                    break;
+                }
+                if (r < 0) {
+                    __nanosleep(backoff);
+                    if (backoff < 1000) backoff += 200;
                 }
             }
-            it = __shfl_sync(FULL, it, 0);
-            if (it < 0) {
-                __syncthreads();   // every warp arrives here exactly once; all claimed hypotheses are finished
-                if (threadIdx.x == 0) apply_ready();
-                __syncthreads();
-                if (warp != 0) return;
-                finalPass = true;
-            }
+            if (fin) finalPass = true;
+            else if (it < 0) break;   // nothing left for this warp
+            if (fin && lane == 0) buf.frame_times[b * 4 + 1] = global_timer();
         }
         int cnt = 0, m = 0;
         double cumulated = 0.0;
@@ -1342,6 +442,7 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
         if (!finalPass) {
             // ---- random subset: ransac::get_random_subset_with_score (ransac.hpp:77-103) ----
             if (lane == 0) {
+                count(W, first ? DBG_HYP_FIRST : DBG_HYP_HELPER);
                 int32_t* used = buf.subsets_used + (size_t(b) * buf.max_iterations + it) * RS_MAX_SUBSET;
                 if (buf.subsets_in) {
                     // host-drawn (std::mt19937 + std::shuffle), already in the reference's prepended order
@@ -1377,60 +478,76 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
         else {
             // ---- final optimisation on the winning inlier set, from the winning pose (:229-262) ----
             if (lane == 0) {
+                volatile unsigned* best = ring + size_t(kRansacRing) * words;
                 for (int w = 0; w < words; ++w) {
-                    unsigned bits = sm.best_mask[w];
+                    unsigned bits = best[w];
                     while (bits) {
                         const int i = w * 32 + (__ffs(bits) - 1);
                         bits &= bits - 1;
-                        sm.inlier_idx[cnt++] = short(i);
+                        sm.idx[cnt++] = short(i);
                         cumulated += score_of(sm.type[i]);
                         m += parts_of(sm.type[i]);
                     }
                 }
-                out->n_inliers = sh.best_inliers;
-                out->iterations_run = sh.started;
-                out->best_iteration = sh.best_iteration;
-                out->score = sh.max_score;
+                out->n_inliers = ld_volatile(&g->best_inliers);
+                out->iterations_run = ld_volatile(&g->started);
+                out->best_iteration = ld_volatile(&g->best_iteration);
+                out->score = ld_volatile(&g->max_score);
             }
-            P.idx = sm.inlier_idx;
+            P.idx = sm.idx;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) xs[j] = sh.best_x[j];
+            for (int j = 0; j < 6; ++j) xs[j] = ld_volatile(&g->best_x[j]);
         }
         cnt = __shfl_sync(FULL, cnt, 0);
         m = __shfl_sync(FULL, m, 0);
         cumulated = __shfl_sync(FULL, cumulated, 0);
         __syncwarp();
         bool ok = cumulated >= 1.0;  // a hypothesis without enough score is skipped; final: status stays 0
-        if (finalPass && !ok) return;
         if (ok) {
             P.n = cnt;
-            ok = optimize_pose_warp<P2D>(S, P, prm.K, xs, m, cumulated, prm.lm_max_fev, lane, finalPass ? nullptr : v_can_quit);
+            ok = optimize_pose_warp<P2D>(S, P, prm.K, xs, m, cumulated, prm.lm_max_fev, lane, finalPass ? nullptr : &g->can_quit);
         }
         if (finalPass) {
-            if (!ok) {
+            int stage = 0;
+            if (cumulated >= 1.0 && !ok) {
                 if (lane == 0) out->status = -1;
-                return;
             }
-            for (int i = lane; i < n; i += 32) buf.mask[size_t(b) * M + i] = (sm.best_mask[i >> 5] >> (i & 31)) & 1u;
+            else if (ok) {
+                volatile unsigned* best = ring + size_t(kRansacRing) * words;
+                for (int i = lane; i < n; i += 32) buf.mask[size_t(b) * M + i] = (best[i >> 5] >> (i & 31)) & 1u;
+                if (lane == 0) {
+                    double q[4];
+                    quaternion_from_coefficients(S.x, q);
+                    for (int j = 0; j < 3; ++j) out->pose[j] = S.x[j];
+                    for (int j = 0; j < 4; ++j) out->pose[3 + j] = q[j];
+                    for (int j = 0; j < 7; ++j) buf.poses[b * 7 + j] = out->pose[j];
+                    out->status = prm.n_variance == 0 ? 1 : -2;  // -2 until the covariance validates it
+                    PoseFrameState* sp = buf.state + b;
+                    sp->stage = 1;
+                    for (int j = 0; j < 6; ++j) sp->final_x[j] = S.x[j];
+                    sp->n_inliers = cnt;
+                    sp->inlier_residuals = m;
+                    sp->inlier_score = cumulated;
+                }
+                for (int k = lane; k < cnt; k += 32) buf.inlier_idx[size_t(b) * M + k] = sm.idx[k];
+                stage = 1;
+            }
+            // hand the frame over: its Monte-Carlo solves may start on any SM from here on
+            __syncwarp();
             if (lane == 0) {
-                double q[4];
-                quaternion_from_coefficients(S.x, q);
-                for (int j = 0; j < 3; ++j) out->pose[j] = S.x[j];
-                for (int j = 0; j < 4; ++j) out->pose[3 + j] = q[j];
-                for (int j = 0; j < 7; ++j) buf.poses[b * 7 + j] = out->pose[j];
-                out->status = prm.n_variance == 0 ? 1 : -2;  // -2 until the covariance kernel validates it
-                PoseFrameState* stp = buf.state + b;
-                stp->stage = 1;
-                for (int j = 0; j < 6; ++j) stp->final_x[j] = S.x[j];
-                stp->n_inliers = cnt;
-                stp->inlier_residuals = m;
-                stp->inlier_score = cumulated;
+                __threadfence();
+                if (stage == 1 && prm.n_variance > 0) {
+                    const int s = atomicAdd(&W->n_ready, 1);
+                    st_volatile(&buf.ready[s], b + 1);
+                }
+                buf.frame_times[b * 4 + 2] = global_timer();
+                atomicMax(&W->t_ransac_end, buf.frame_times[b * 4 + 2]);
+                __threadfence();
+                atomicAdd(&W->frames_done, 1);
             }
-            for (int k = lane; k < cnt; k += 32) buf.inlier_idx[size_t(b) * M + k] = sm.inlier_idx[k];
-            return;
+            break;
         }
-        const int slot = it % RRING;
-        unsigned* hmask = sm.hyp_mask + slot * words;
+        const int slot = it % kRansacRing;
         int nIn = 0;
         double score = 0.0;
         if (ok) {
@@ -1443,18 +560,18 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                 if (i < n) {
                     double o[4], mm[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) o[c] = sm.obs[c * M + i], mm[c] = sm.map[c * M + i];
+                    for (int c = 0; c < 4; ++c) o[c] = s_obs[c * M + i], mm[c] = s_map[c * M + i];
                     in = feature_is_inlier<P2D>(sm.type[i], o, mm, S.T, prm.K, P.aux, M, i);
                 }
                 const unsigned bits = __ballot_sync(FULL, in);
-                if (lane == 0) hmask[w] = bits;
+                if (lane == 0) wmask[w] = bits;
                 nIn += __popc(bits);
             }
             __syncwarp();
             if (lane == 0) {
                 // the score is accumulated in list order, like the reference's running double
                 for (int w = 0; w < words; ++w) {
-                    unsigned bits = hmask[w];
+                    unsigned bits = wmask[w];
                     while (bits) {
                         const int i = w * 32 + (__ffs(bits) - 1);
                         bits &= bits - 1;
@@ -1462,217 +579,292 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
                     }
                 }
             }
+            // the mask travels to the frame's ring slot (free: iteration `it` only started once it - ring was applied)
+            volatile unsigned* dst = ring + size_t(slot) * words;
+            for (int w = lane; w < words; w += 32) dst[w] = wmask[w];
         }
+        else if (lane == 0 && ld_volatile(&g->can_quit))
+            count(W, DBG_ABORTED);
+        // ---- publish the result, then fold in whatever is ready ----
+        if (lane < 6) st_volatile(&g->slot[slot].x[lane], S.x[lane]);
         if (lane == 0) {
-            sh.hyp_ok[slot] = ok ? 1 : 0;
-            sh.hyp_score[slot] = score;
-            sh.hyp_inliers[slot] = nIn;
-            for (int j = 0; j < 6; ++j) sh.hyp_x[slot][j] = S.x[j];
-            __threadfence_block();
-            v_done[slot] = it + 1;
-            // fold in whatever is ready; if another warp holds the lock it re-checks after releasing it
-            while (!*v_can_quit && v_done[*v_applied % RRING] == *v_applied + 1 && *v_applied < maxIterations) {
-                if (atomicCAS(&sh.lock, 0, 1) != 0) break;
-                apply_ready();
-                __threadfence_block();
-                atomicExch(&sh.lock, 0);
-            }
+            st_volatile(&g->slot[slot].score, score);
+            st_volatile(&g->slot[slot].inliers, nIn);
+            st_volatile(&g->slot[slot].ok, ok ? 1 : 0);
         }
         __syncwarp();
-    }
-}
-
-// compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
-// grid (ceil(n_variance / warps), B), one warp per Monte-Carlo sample; warps per CTA = blockDim.x / 32 (8 unless the
-// perturbed copies of a very long match list would not fit in shared memory, see launch_pose_variance).
-template <bool P2D>
-__global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = prm.frame0 + blockIdx.y;
-    const int M = buf.max_matches;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const PoseFrameState st = buf.state[b];
-    if (st.stage != 1) return;
-    const int n = st.n;
-    // carve: obs[4][M] | pmap[warps][4][M] | WarpLM[warps] | type[M] | idx[M] | count
-    const int nwarps = blockDim.x >> 5;
-    double* s_obs = reinterpret_cast<double*>(smem_raw);
-    double* s_pmap = s_obs + 4 * M;
-    WarpLM* s_lm = reinterpret_cast<WarpLM*>(s_pmap + size_t(nwarps) * 4 * M);
-    int32_t* s_type = reinterpret_cast<int32_t*>(s_lm + nwarps);
-    short* s_idx = reinterpret_cast<short*>(s_type + M);
-    const int cnt = st.n_inliers;
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-        s_type[i] = buf.type[size_t(b) * M + i];
-        if (i < cnt) s_idx[i] = buf.inlier_idx[size_t(b) * M + i];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) s_obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
+        if (lane == 0) {
+            __threadfence();
+            st_volatile(&g->done[slot], it + 1);
+        }
+        __syncwarp();
+        for (;;) {
+            const FrameFlags f = load_flags(g);
+            if (f.can_quit || f.closed) break;
+            // if another warp holds the lock it re-checks after releasing it
+            const int r = try_apply(g, ring, words, maxIterations, inliersToStop, W, buf.open_list, b, lane, f.applied);
+            if (r == 1) {
+                finalPass = true;
+                if (lane == 0) buf.frame_times[b * 4 + 1] = global_timer();
+            }
+            if (r != 0) break;
+        }
     }
     __syncthreads();
-    const int sample = blockIdx.x * nwarps + warp;
-    if (sample >= prm.n_variance) return;
-    double* pmap = s_pmap + size_t(warp) * 4 * M;
-    const double* gmap = buf.map + size_t(b) * 4 * M;
-    const double* gsig = buf.sigma + size_t(b) * 4 * M;
-    for (int k = lane; k < cnt; k += 32) {
-        const int i = s_idx[k];
-        double g[4];
-        if (buf.normals_in) {
-            const double* src = buf.normals_in + ((size_t(b) * prm.n_variance + sample) * M + i) * 4;
-            g[0] = src[0], g[1] = src[1], g[2] = src[2], g[3] = src[3];
-        }
-        else {
-            device_normals(prm.seed, b, sample, i, g);
-        }
-        if (s_type[i] == RS_FEAT_POINT) {
-            // map_point.cpp:49-58
-#pragma unroll
-            for (int c = 0; c < 3; ++c) pmap[c * M + i] = gmap[c * M + i] + g[c] * gsig[c * M + i];
-            pmap[3 * M + i] = 0.0;
-        }
-        else if (P2D && s_type[i] == RS_FEAT_POINT2D) {
-            // map_point2d.cpp:49-73: theta then phi, clamped to [0, pi] / [-pi, pi]; nothing else varies
-            const double th = gmap[i] + g[0] * gsig[i], ph = gmap[M + i] + g[1] * gsig[M + i];
-            pmap[i] = th < 0.0 ? 0.0 : (kPi < th ? kPi : th);
-            pmap[M + i] = ph < -kPi ? -kPi : (kPi < ph ? kPi : ph);
-            pmap[2 * M + i] = 0.0;
-            pmap[3 * M + i] = 0.0;
-        }
-        else {
-            // map_primitive.cpp:66-77: perturbed normal renormalised (twice: vector + PlaneCoordinates ctor)
-            double nn[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) nn[c] = gmap[c * M + i] + g[c] * gsig[c * M + i];
-            normalize3(nn);
-            normalize3(nn);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) pmap[c * M + i] = nn[c];
-            pmap[3 * M + i] = gmap[3 * M + i] + g[3] * gsig[3 * M + i];
-        }
-    }
-    __syncwarp();
-    Problem P;
-    P.n = cnt, P.idx = s_idx, P.type = s_type, P.obs = s_obs, P.map = pmap, P.M = M;
-    P.aux = buf.aux + size_t(b) * 4 * M;
-    WarpLM& S = s_lm[warp];
-    double x0[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) x0[j] = st.final_x[j];
-    const bool ok = optimize_pose_warp<P2D>(S, P, prm.K, x0, st.inlier_residuals, st.inlier_score, prm.lm_max_fev, lane);
-    if (lane == 0) {
-        double v[6] = {0, 0, 0, 0, 0, 0};
-        if (ok) pose_vector6(S.x, v);
-        double* dst = buf.v6 + (size_t(b) * buf.max_variance + sample) * 6;
-        for (int j = 0; j < 6; ++j) dst[j] = v[j];
-        buf.v_ok[size_t(b) * buf.max_variance + sample] = ok ? 1 : 0;
-    }
+    if (!first && threadIdx.x == 0) atomicSub(&g->joiners, 1);
 }
 
-// is_covariance_valid (covariances.hpp:13-44): finite, isApprox-symmetric, LDLT without a negative pivot
-__device__ bool covariance_valid(const double* c)
+template <bool P2D>
+__device__ __noinline__ void frame_task_outlined(const PoseBuffers& buf, const PoseLaunch& prm, const FusedSmem& sm, PoseWork* W,
+                                                const int b, const int arg, const int n, const int warp, const int lane)
 {
-    for (int i = 0; i < 36; ++i)
-        if (!isfinite(c[i])) return false;
-    double diff2 = 0.0, n2 = 0.0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-            const double dd = c[i * 6 + j] - c[j * 6 + i];
-            diff2 += dd * dd;
-            n2 += c[i * 6 + j] * c[i * 6 + j];
-        }
-    if (!(diff2 <= 1e-12 * 1e-12 * n2)) return false;
-    double a[36];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) a[i * 6 + j] = c[(i < j ? i : j) * 6 + (i < j ? j : i)];
-    bool neg = false;
-    for (int k = 0; k < 6; ++k) {
-        int p = k;
-        double best = fabs(a[k * 6 + k]);
-        for (int i = k + 1; i < 6; ++i)
-            if (fabs(a[i * 6 + i]) > best) {
-                best = fabs(a[i * 6 + i]);
-                p = i;
-            }
-        if (p != k) {
-            for (int j = 0; j < 6; ++j) {
-                const double t = a[k * 6 + j];
-                a[k * 6 + j] = a[p * 6 + j];
-                a[p * 6 + j] = t;
-            }
-            for (int i = 0; i < 6; ++i) {
-                const double t = a[i * 6 + k];
-                a[i * 6 + k] = a[i * 6 + p];
-                a[i * 6 + p] = t;
-            }
-        }
-        const double dkk = a[k * 6 + k];
-        if (dkk < 0.0) neg = true;
-        if (fabs(dkk) <= DBL_MIN) break;
-        for (int i = k + 1; i < 6; ++i) {
-            const double l = a[i * 6 + k] / dkk;
-            for (int j = k + 1; j < 6; ++j) a[i * 6 + j] -= l * a[k * 6 + j];
-        }
-    }
-    return !neg;
+    frame_task<P2D>(buf, prm, sm, W, b, arg, n, warp, lane);
 }
 
-// compute_pose_variance's reduction (pose_optimization.cpp:414-437): one warp per frame. Lanes split the samples for
-// the mean, then lane e < 21 owns one entry of the upper triangle and sums it over the samples in sample order.
-__global__ void __launch_bounds__(128) pose_covariance_kernel(const PoseBuffers buf, const PoseLaunch prm)
+// MC_ROLE = false: frame role only (28 KB of shared memory per CTA). MC_ROLE = true: Monte-Carlo role, and the frame role out
+// of line. Both at 168 registers, three CTAs per SM: 58 KB per Monte-Carlo CTA allows no fourth, and capping the LM body at
+// 128 registers costs the sample solves a third of their speed (measured).
+template <bool P2D, bool MC_ROLE>
+__global__ void __launch_bounds__(THREADS, RS_POSE_CTAS_PER_SM) pose_fused_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
-    const int b = prm.frame0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (b >= prm.frame0 + prm.batch) return;
-    if (buf.state[b].stage != 1 || prm.n_variance <= 0) return;
-    const double* v6 = buf.v6 + size_t(b) * buf.max_variance * 6;
-    const int32_t* vok = buf.v_ok + size_t(b) * buf.max_variance;
-    rs_pose_out* out = buf.out + b;
-    double medium[6] = {0, 0, 0, 0, 0, 0};
-    int cnt = 0;
-    for (int s = lane; s < prm.n_variance; s += 32)
-        if (vok[s]) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int M = buf.max_matches;
+    const int words = (M + 31) / 32;
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool do_ransac = prm.run_ransac != 0;
+    const bool do_mc = MC_ROLE && prm.n_variance > 0 && prm.run_mc != 0;
+    FusedSmem sm;
+    fused_carve(&sm, smem_raw, M, nwarps, do_mc);
+    PoseWork* W = buf.work;
+    const int B = prm.batch;
+    const int groups = do_mc ? (prm.n_variance + nwarps - 1) / nwarps : 1;   // Monte-Carlo tasks per frame
+    const int maxIterations = prm.max_iterations;
+
+    if (threadIdx.x == 0) atomicMin(&W->t_first, global_timer());
+
+    for (;;) {
+        // ================================ pick a task (warp 0) ================================
+        if (warp == 0) {
+            int kind = -1, frame = -1, arg = 0;
+            unsigned backoff = 200;
+            while (kind < 0) {
+                // 1. a frame nobody has started
+                if (do_ransac && ld_volatile(&W->join_ticket) < B) {
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(&W->join_ticket, 1);
+                    t = __shfl_sync(FULL, t, 0);
+                    if (t < B) {
+                        kind = TASK_RANSAC, frame = prm.frame0 + t, arg = 1;   // arg 1: first CTA of the frame
+                        break;
+                    }
+                }
+                // 2. a Monte-Carlo task. Tickets, not compare-and-swap: with hundreds of CTAs looking for work at once a CAS
+                // loop hands out one task per L2 round trip. A ticket is only drawn when a task is there to be had; the race
+                // may still push it past the last published frame, then the CTA waits for that frame (its hypotheses are
+                // running on some CTA: every frame has been started by the time this branch is reached).
+                if (do_mc) {
+                    int t = -1;
+                    if (lane == 0) {
+                        const int h = ld_volatile(&W->mc_head);
+                        const int s = h / groups;
+                        // while frames are still in their RANSAC stage the Monte-Carlo solves (FP64 throughput work) are held
+                        // to prm.mc_cap tasks in flight: every FP64 instruction of theirs queues in front of the one-lane
+                        // algebra of the hypothesis chains, which is what the batch is waiting for
+                        const bool throttled = ld_volatile(&W->frames_done) < B && h - ld_volatile(&W->mc_done_tasks) >= prm.mc_cap;
+                        if (!throttled && s < B && ld_volatile(&buf.ready[s]) != 0) t = atomicAdd(&W->mc_head, 1);
+                    }
+                    t = __shfl_sync(FULL, t, 0);
+                    if (t >= 0) {
+                        const int s = t / groups;
+                        int fr = 0;
+                        unsigned wait = 200;
+                        while (s < B) {
+                            fr = ld_volatile(&buf.ready[s]);
+                            if (fr != 0) break;
+                            if (ld_volatile(&W->frames_done) >= B && s >= ld_volatile(&W->n_ready)) break;   // no such frame will come
+                            __nanosleep(wait);
+                            if (wait < 2000) wait += 200;
+                        }
+                        if (fr != 0) {
+                            kind = TASK_MC, frame = fr - 1, arg = t % groups;
+                            break;
+                        }
+                        continue;   // the ticket was beyond the last frame
+                    }
+                }
+                // 3. a frame that takes helpers: the one with the most iterations left per CTA already on it
+                if (do_ransac) {
+                    const int nopen = ld_volatile(&W->n_open);
+                    int best_f = -1, best_gain = 0;
+                    for (int k = lane; k < nopen; k += 32) {
+                        const int f = ld_volatile(&buf.open_list[k]) - 1;
+                        if (f < 0) continue;
+                        const RansacFrame* g = buf.rframe + f;
+                        const FrameFlags ff = load_flags(g);
+                        if (ff.can_quit || ff.closed) continue;
+                        const int left = maxIterations - ld_volatile(&g->next_iter);
+                        const int gain = left / (ld_volatile(&g->joiners) + 2);
+                        if (gain > best_gain) best_gain = gain, best_f = f;
+                    }
 #pragma unroll
-            for (int j = 0; j < 6; ++j) medium[j] += v6[s * 6 + j];
-            ++cnt;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const int og = __shfl_xor_sync(FULL, best_gain, o), of = __shfl_xor_sync(FULL, best_f, o);
+                        if (og > best_gain || (og == best_gain && of > best_f)) best_gain = og, best_f = of;
+                    }
+                    if (best_f >= 0 && best_gain >= prm.help_min) {
+                        if (lane == 0) {
+                            atomicAdd(&buf.rframe[best_f].joiners, 1);
+                            count(W, DBG_HELPER_JOINS);
+                        }
+                        kind = TASK_RANSAC, frame = best_f, arg = 0;
+                        break;
+                    }
+                }
+                // 4. everything handed out?
+                if (!do_mc && !prm.linger && ld_volatile(&W->join_ticket) >= B) {   // every frame has its CTA: nothing left for this one
+                    kind = TASK_EXIT;
+                    break;
+                }
+                if (ld_volatile(&W->frames_done) >= B) {
+                    bool more = false;
+                    if (do_mc) {
+                        const int s = ld_volatile(&W->mc_head) / groups;
+                        more = s < B && ld_volatile(&buf.ready[s]) != 0;
+                    }
+                    if (!more) {
+                        kind = TASK_EXIT;
+                        break;
+                    }
+                    continue;
+                }
+                __nanosleep(backoff);
+                if (backoff < 2000) backoff += 200;
+            }
+            if (lane == 0) sm.ctl[0] = kind, sm.ctl[1] = frame, sm.ctl[2] = arg;
         }
-    cnt = __reduce_add_sync(FULL, cnt);
+        __syncthreads();
+        const int kind = sm.ctl[0], b = sm.ctl[1], arg = sm.ctl[2];
+        if (kind == TASK_EXIT) break;
+
+        // per-frame state: written by the prepare kernel (an earlier launch) and, for a Monte-Carlo task, completed by the
+        // frame's final LM on another SM of THIS launch - read past L1
+        const int n = __ldcg(&buf.state[b].n);
+
+        if (kind == TASK_RANSAC) {
+            if (MC_ROLE)
+                frame_task_outlined<P2D>(buf, prm, sm, W, b, arg, n, warp, lane);
+            else
+                frame_task<P2D>(buf, prm, sm, W, b, arg, n, warp, lane);
+            continue;
+        }
+
+        // ======================= Monte-Carlo task: `nwarps` samples of frame b (pose_optimization.cpp:379-412) =======================
+        if (MC_ROLE) {
+            const PoseFrameState* stp = buf.state + b;
+            WarpLM& S = sm.lm[warp];
+            const int cnt = __ldcg(&stp->n_inliers);
+            for (int i = threadIdx.x; i < M; i += blockDim.x) {
+                sm.type[i] = buf.type[size_t(b) * M + i];
+                if (i < cnt) sm.idx[i] = __ldcg(buf.inlier_idx + size_t(b) * M + i);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) medium[j] = warp_sum(medium[j]);
-    if (lane == 0) out->n_variance_ok = cnt;
-    if (unsigned(cnt) < unsigned(prm.n_variance) / 2u) {
-        if (lane == 0) out->status = -2;
-        return;
-    }
+                for (int c = 0; c < 4; ++c) sm.obs[c * M + i] = buf.obs[(size_t(b) * 4 + c) * M + i];
+            }
+            if (threadIdx.x == 0) count(W, DBG_MC_TASKS);
+            __syncthreads();
+            const int sample = arg * nwarps + warp;
+            if (sample < prm.n_variance) {
+                double* pmap = sm.pmap + size_t(warp) * 4 * M;
+                const double* gmap = buf.map + size_t(b) * 4 * M;
+                const double* gsig = buf.sigma + size_t(b) * 4 * M;
+                for (int k = lane; k < cnt; k += 32) {
+                    const int i = sm.idx[k];
+                    double gn[4];
+                    if (buf.normals_in) {
+                        const double* src = buf.normals_in + ((size_t(b) * prm.n_variance + sample) * M + i) * 4;
+                        gn[0] = src[0], gn[1] = src[1], gn[2] = src[2], gn[3] = src[3];
+                    }
+                    else {
+                        device_normals(prm.seed, b, sample, i, gn);
+                    }
+                    if (sm.type[i] == RS_FEAT_POINT) {
+                        // map_point.cpp:49-58
 #pragma unroll
-    for (int j = 0; j < 6; ++j) medium[j] /= double(cnt);
-    int ei = 0, ej = 0;
-    {
-        int rem = lane < 21 ? lane : 0;
-        while (rem >= 6 - ei) rem -= 6 - ei, ++ei;
-        ej = ei + rem;
-    }
-    double mi = 0.0, mj = 0.0;
+                        for (int c = 0; c < 3; ++c) pmap[c * M + i] = gmap[c * M + i] + gn[c] * gsig[c * M + i];
+                        pmap[3 * M + i] = 0.0;
+                    }
+                    else if (P2D && sm.type[i] == RS_FEAT_POINT2D) {
+                        // map_point2d.cpp:49-73: theta then phi, clamped to [0, pi] / [-pi, pi]; nothing else varies
+                        const double th = gmap[i] + gn[0] * gsig[i], ph = gmap[M + i] + gn[1] * gsig[M + i];
+                        pmap[i] = th < 0.0 ? 0.0 : (kPi < th ? kPi : th);
+                        pmap[M + i] = ph < -kPi ? -kPi : (kPi < ph ? kPi : ph);
+                        pmap[2 * M + i] = 0.0;
+                        pmap[3 * M + i] = 0.0;
+                    }
+                    else {
+                        // map_primitive.cpp:66-77: perturbed normal renormalised (twice: vector + PlaneCoordinates ctor)
+                        double nn[3];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        if (j == ei) mi = medium[j];
-        if (j == ej) mj = medium[j];
+                        for (int c = 0; c < 3; ++c) nn[c] = gmap[c * M + i] + gn[c] * gsig[c * M + i];
+                        normalize3(nn);
+                        normalize3(nn);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) pmap[c * M + i] = nn[c];
+                        pmap[3 * M + i] = gmap[3 * M + i] + gn[3] * gsig[3 * M + i];
+                    }
+                }
+                __syncwarp();
+                Problem P;
+                P.n = cnt, P.idx = sm.idx, P.type = sm.type, P.obs = sm.obs, P.map = pmap, P.M = M;
+                P.aux = buf.aux + size_t(b) * 4 * M;
+                double xs[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) xs[j] = __ldcg(&stp->final_x[j]);
+                const bool ok = optimize_pose_warp<P2D>(S, P, prm.K, xs, __ldcg(&stp->inlier_residuals), __ldcg(&stp->inlier_score),
+                                                        prm.lm_max_fev, lane, nullptr);
+                if (lane == 0) {
+                    double v[6] = {0, 0, 0, 0, 0, 0};
+                    if (ok) pose_vector6(S.x, v);
+                    double* dst = buf.v6 + (size_t(b) * buf.max_variance + sample) * 6;
+                    for (int j = 0; j < 6; ++j) dst[j] = v[j];
+                    buf.v_ok[size_t(b) * buf.max_variance + sample] = ok ? 1 : 0;
+                }
+            }
+            __syncthreads();
+            // the CTA that finishes a frame's last sample group reduces its covariance (pose_optimization.cpp:414-437)
+            if (threadIdx.x == 0) {
+                __threadfence();
+                sm.ctl[3] = atomicAdd(&buf.mc_done[b], 1) == groups - 1 ? 1 : 0;
+                atomicAdd(&W->mc_done_tasks, 1);
+            }
+            __syncthreads();
+            if (sm.ctl[3] && warp == 0) {
+                frame_covariance_warp(buf, prm, b, lane);
+                if (lane == 0) buf.frame_times[b * 4 + 3] = global_timer();
+            }
+            __syncthreads();
+        }
     }
-    double acc = 0.0;
-    for (int s = 0; s < prm.n_variance; ++s)
-        if (vok[s]) acc += (v6[s * 6 + ei] - mi) * (v6[s * 6 + ej] - mj);
-    acc /= double(cnt - 1);
-    if (ei == ej) acc += 0.001;
-    if (lane < 21) {
-        out->cov[ei * 6 + ej] = acc;
-        out->cov[ej * 6 + ei] = acc;
+    if (threadIdx.x == 0) atomicMax(&W->t_last, global_timer());
+}
+
+// RS_RNG_REFERENCE runs the fused kernel in two halves around the host's Gaussian draws: this fills the hand-over list of
+// the second half with every frame whose final pose is available.
+__global__ void pose_publish_all_kernel(const PoseBuffers buf, const PoseLaunch prm)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    PoseWork* W = buf.work;
+    int nr = 0;
+    for (int t = 0; t < prm.batch; ++t) {
+        const int b = prm.frame0 + t;
+        buf.mc_done[b] = 0;
+        buf.ready[t] = 0;
+        if (buf.state[b].stage == 1) buf.ready[nr++] = b + 1;
     }
-    __syncwarp();
-    if (lane == 0) {
-        double cov[36];
-        for (int i = 0; i < 36; ++i) cov[i] = out->cov[i];
-        out->status = covariance_valid(cov) ? 1 : -2;
-    }
+    W->n_ready = nr;
+    W->mc_head = 0;
+    W->frames_done = prm.batch;
+    W->join_ticket = prm.batch;
 }
 
 __global__ void pose_export_normals_kernel(const PoseLaunch prm, const int M, double* normals)
@@ -1688,22 +880,18 @@ __global__ void pose_export_normals_kernel(const PoseLaunch prm, const int M, do
     }
 }
 
-size_t variance_smem_bytes(const int M, const int warps)
-{
-    return sizeof(double) * 4 * M + sizeof(double) * size_t(warps) * 4 * M + sizeof(WarpLM) * warps + sizeof(int32_t) * M +
-           sizeof(short) * M + 16;
-}
 
 constexpr size_t kSmemPerCta = 232448;   // 227 KB opt-in limit of sm_100
 constexpr size_t kSmemPerSm = 233472;    // 228 KB, 1 KB reserved per resident CTA
 
-// Warps per CTA of the Monte-Carlo kernel for a match capacity M: the choice that keeps the most warps resident per SM
-// (8 warps, two CTAs per SM, up to M = 370; fewer, fatter samples per CTA beyond). 0 = even one warp does not fit.
-int variance_warps_for(const int M)
+// Warps per CTA of the fused kernel for a match capacity M: the choice that keeps the most warps resident per SM (four warps,
+// four CTAs per SM, up to M = 400: every warp of a Monte-Carlo task holds a perturbed copy of the frame's map side; fewer
+// warps per CTA beyond). 0 = even one warp does not fit.
+int fused_warps_for(const int M)
 {
     int best = 0, best_resident = 0;
     for (int w = WARPS; w >= 1; w >>= 1) {
-        const size_t smem = variance_smem_bytes(M, w);
+        const size_t smem = fused_carve(nullptr, nullptr, M, w);
         if (smem > kSmemPerCta) continue;
         const int ctas = int(std::min<size_t>(kSmemPerSm / (smem + 1024), size_t(64 / w)));
         if (w * ctas > best_resident) best = w, best_resident = w * ctas;
@@ -1717,10 +905,10 @@ int pose_max_matches_supported()
 {
     static int limit = 0;
     if (limit == 0) {
-        int lo = 1, hi = 32767;   // both kernels stage one frame's match list in shared memory
+        int lo = 1, hi = 32767;   // the fused kernel stages one frame's match list in shared memory
         while (lo < hi) {
             const int mid = (lo + hi + 1) / 2;
-            if (ransac_carve(nullptr, nullptr, mid) <= kSmemPerCta && variance_warps_for(mid) > 0) lo = mid; else hi = mid - 1;
+            if (fused_warps_for(mid) > 0) lo = mid; else hi = mid - 1;
         }
         limit = lo;
     }
@@ -1734,47 +922,57 @@ int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStrea
     return RS_OK;
 }
 
-// Two instantiations of the RANSAC / Monte-Carlo kernels: the usual one knows only points and planes; the other also
-// carries the inverse-depth ("line") residual, whose sincos / two-projection / seven-evaluation code would otherwise cost
-// the hot loops registers (measured: +50 % on the Monte-Carlo kernel when merely compiled in). prm.has_point2d selects.
-int launch_pose_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
+// Two instantiations of the fused kernel: the usual one knows only points and planes; the other also carries the
+// inverse-depth ("line") residual, whose sincos / two-projection / seven-evaluation code would otherwise cost the hot loops
+// registers (measured on the former Monte-Carlo kernel: +50 % when merely compiled in). prm.has_point2d selects.
+int launch_pose_fused(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
 {
-    const size_t smem = ransac_carve(nullptr, nullptr, buf.max_matches);
-    if (smem > kSmemPerCta) return RS_ERR_INVALID_ARG;   // rs_pose_create refuses such capacities (pose_max_matches_supported)
-    static SmemOptIn optin[2];
-    RS_CUDA_CHECK(optin[0].ensure(pose_ransac_kernel<false>));
-    RS_CUDA_CHECK(optin[1].ensure(pose_ransac_kernel<true>));
-    if (prm.has_point2d)
-        pose_ransac_kernel<true><<<prm.batch, RTHREADS, smem, stream>>>(buf, prm);
-    else
-        pose_ransac_kernel<false><<<prm.batch, RTHREADS, smem, stream>>>(buf, prm);
+    const int warps = fused_warps_for(buf.max_matches);
+    if (warps == 0) return RS_ERR_INVALID_ARG;   // rs_pose_create refuses such capacities (pose_max_matches_supported)
+    const bool mc_role = prm.run_mc && prm.n_variance > 0;
+    if (!prm.run_ransac && !mc_role) return RS_OK;
+    const size_t smem = fused_carve(nullptr, nullptr, buf.max_matches, warps, mc_role);
+    static SmemOptIn optin[4];
+    if (mc_role) {
+        RS_CUDA_CHECK(optin[2].ensure(pose_fused_kernel<false, true>, smem));
+        RS_CUDA_CHECK(optin[3].ensure(pose_fused_kernel<true, true>, smem));
+    }
+    else {
+        RS_CUDA_CHECK(optin[0].ensure(pose_fused_kernel<false, false>, smem));
+        RS_CUDA_CHECK(optin[1].ensure(pose_fused_kernel<true, false>, smem));
+    }
+    if (prm.publish_all) {
+        pose_publish_all_kernel<<<1, 32, 0, stream>>>(buf, prm);
+        RS_LAUNCH_CHECK();
+    }
+    // persistent grid: what is resident at once, or fewer when the batch cannot feed that many CTAs
+    int dev = 0, sms = 0, per_sm = 0;
+    RS_CUDA_CHECK(cudaGetDevice(&dev));
+    RS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    void (*kernel)(const PoseBuffers, const PoseLaunch) =
+            mc_role ? (prm.has_point2d ? pose_fused_kernel<true, true> : pose_fused_kernel<false, true>)
+                    : (prm.has_point2d ? pose_fused_kernel<true, false> : pose_fused_kernel<false, false>);
+    RS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (prm.ctas_per_sm > 0 && prm.ctas_per_sm < per_sm) per_sm = prm.ctas_per_sm;
+    const int groups = mc_role ? (prm.n_variance + warps - 1) / warps : 0;
+    long long useful = 0;
+    if (prm.run_ransac) useful += (long long)prm.batch * ((prm.linger || mc_role) ? std::max(1, (prm.max_iterations + 8 * warps - 1) / (8 * warps)) : 1);
+    if (mc_role) useful += (long long)prm.batch * groups;
+    const int grid = int(std::max<long long>(1, std::min<long long>((long long)sms * per_sm, useful)));
+    kernel<<<grid, warps * 32, smem, stream>>>(buf, prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }
 
-int launch_pose_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
+int pose_work_times(const PoseBuffers& buf, float* ransac_phase_ms, float* total_ms, cudaStream_t stream)
 {
-    if (prm.n_variance <= 0) return RS_OK;
-    const int warps = variance_warps_for(buf.max_matches);
-    if (warps == 0) return RS_ERR_INVALID_ARG;
-    const size_t smem = variance_smem_bytes(buf.max_matches, warps);
-    static SmemOptIn optin[2];
-    RS_CUDA_CHECK(optin[0].ensure(pose_variance_kernel<false>));
-    RS_CUDA_CHECK(optin[1].ensure(pose_variance_kernel<true>));
-    const dim3 grid((prm.n_variance + warps - 1) / warps, prm.batch);
-    if (prm.has_point2d)
-        pose_variance_kernel<true><<<grid, warps * 32, smem, stream>>>(buf, prm);
-    else
-        pose_variance_kernel<false><<<grid, warps * 32, smem, stream>>>(buf, prm);
-    RS_LAUNCH_CHECK();
-    return RS_OK;
-}
-
-int launch_pose_covariance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream)
-{
-    if (prm.n_variance <= 0) return RS_OK;
-    pose_covariance_kernel<<<(prm.batch + 3) / 4, 128, 0, stream>>>(buf, prm);
-    RS_LAUNCH_CHECK();
+    PoseWork w;
+    RS_CUDA_CHECK(cudaMemcpyAsync(&w, buf.work, sizeof(PoseWork), cudaMemcpyDeviceToHost, stream));
+    RS_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const bool ok = w.t_first != ~0ull && w.t_last >= w.t_first;
+    if (ransac_phase_ms) *ransac_phase_ms = ok && w.t_ransac_end >= w.t_first ? float(double(w.t_ransac_end - w.t_first) * 1e-6) : 0.f;
+    if (total_ms) *total_ms = ok ? float(double(w.t_last - w.t_first) * 1e-6) : 0.f;
     return RS_OK;
 }
 

@@ -68,12 +68,17 @@ def load():
         lib.rs_pose_solve.argtypes = [vp, vp, vp, i32, C.POINTER(abi.PoseOpts), vp, vp]
         lib.rs_pose_upload.argtypes = [vp, vp, vp, vp, i32]
         lib.rs_pose_solve_device.argtypes = [vp, i32, C.POINTER(abi.PoseOpts), vp]
+        lib.rs_pose_prepare_device.argtypes = [vp, i32, C.POINTER(abi.PoseOpts), vp]
+        lib.rs_pose_add_workers.argtypes = [vp, i32, vp]
         lib.rs_pose_download.argtypes = [vp, i32, vp, vp]
         lib.rs_pose_device_poses.restype = vp
         lib.rs_pose_device_poses.argtypes = [vp]
         lib.rs_pose_export_random.argtypes = [vp, i32, vp, vp]
         lib.rs_pose_set_timing.argtypes = [vp, i32]
         lib.rs_pose_kernel_ms.argtypes = [vp, i32, vp]
+        lib.rs_pose_phase_ms.argtypes = [vp, vp]
+        lib.rs_pose_debug_counters.argtypes = [vp, vp]
+        lib.rs_pose_debug_frame_times.argtypes = [vp, i32, vp]
     _lib = lib
     return lib
 
@@ -263,8 +268,10 @@ class PoseOptimization:
 
     @staticmethod
     def options(max_iterations=0, n_variance=-1, rng_mode=abi.RS_RNG_REFERENCE, seed=0, intrinsics=None, lm_max_fev=0,
-                sub_batches=0):
+                sub_batches=0, worker_ctas_per_sm=0, solver=0):
         o = abi.PoseOpts()
+        o.solver = solver                           # abi.RS_SOLVER_AUTO / _CHAIN / _FUSED
+        o.worker_ctas_per_sm = worker_ctas_per_sm   # <= 0: as many resident CTAs per SM as fit
         o.max_iterations, o.n_variance, o.rng_mode, o.seed, o.lm_max_fev = max_iterations, n_variance, rng_mode, seed, lm_max_fev
         o.sub_batches = sub_batches   # RS_RNG_DEVICE: frame groups on separate streams (same results)
         if intrinsics is not None:
@@ -324,6 +331,14 @@ class PoseOptimization:
     def solve_device(self, batch, opts, stream=0):
         _check(self._lib.rs_pose_solve_device(self._ctx, batch, C.byref(opts), stream), "rs_pose_solve_device")
 
+    def prepare_device(self, batch, opts, stream=0):
+        """The preparation kernel of solve_device alone; the next solve_device(batch, ...) then launches the solve kernel only."""
+        _check(self._lib.rs_pose_prepare_device(self._ctx, batch, C.byref(opts), stream), "rs_pose_prepare_device")
+
+    def add_workers(self, ctas_per_sm=0, stream=0):
+        """More CTAs for the solve kernel most recently launched through this context (they leave at once when no work is left)."""
+        _check(self._lib.rs_pose_add_workers(self._ctx, ctas_per_sm, stream), "rs_pose_add_workers")
+
     def stream_wait_ransac(self, stream):
         """`stream` (cudaStream_t as int) waits for the RANSAC + final LM kernel of the latest solve of this context."""
         _check(self._lib.rs_pose_stream_wait_ransac(self._ctx, stream), "rs_pose_stream_wait_ransac")
@@ -338,10 +353,29 @@ class PoseOptimization:
         _check(self._lib.rs_pose_set_timing(self._ctx, n_slots), "rs_pose_set_timing")
 
     def kernel_ms(self, slot):
-        """(prepare, RANSAC + final LM, Monte-Carlo LM solves, covariance) ms of the run that used this slot."""
+        """(prepare, solve kernel, its second half with RS_RNG_REFERENCE, 0) ms of the run that used this slot."""
         ms = (C.c_float * 4)()
         _check(self._lib.rs_pose_kernel_ms(self._ctx, slot, ms), "rs_pose_kernel_ms")
         return tuple(float(v) for v in ms)
+
+    def phase_ms(self):
+        """(RANSAC phase ms, whole solve kernel ms) of the most recent solve-kernel launch, from the device's own timer."""
+        ms = (C.c_float * 2)()
+        _check(self._lib.rs_pose_phase_ms(self._ctx, ms), "rs_pose_phase_ms")
+        return float(ms[0]), float(ms[1])
+
+    def work_counters(self):
+        """Work counters of the most recent solve-kernel launch (see rs_pose_debug_counters)."""
+        out = (C.c_uint64 * 8)()
+        _check(self._lib.rs_pose_debug_counters(self._ctx, out), "rs_pose_debug_counters")
+        names = ("hyp_first_cta", "hyp_helper_ctas", "bookkeeping_rounds", "hyp_applied", "helper_joins", "mc_tasks", "hyp_dropped", "reserved")
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def frame_times(self, batch):
+        """[batch, 4] ms since the solve kernel's first CTA: hypotheses started, stage closed, final LM done, covariance done."""
+        ms = np.zeros((batch, 4))
+        _check(self._lib.rs_pose_debug_frame_times(self._ctx, batch, ms.ctypes.data), "rs_pose_debug_frame_times")
+        return ms
 
     def device_poses_ptr(self):
         return self._lib.rs_pose_device_poses(self._ctx)

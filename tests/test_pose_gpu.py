@@ -306,3 +306,48 @@ def test_frame_groups_on_separate_streams_change_nothing(groups):
     assert (want["status"] == 1).sum() >= B - 1 and want["status"][5] != 1
     assert want.tobytes() == got.tobytes() and wmask.tobytes() == gmask.tobytes()
     s.close()
+
+
+def same_solution(a, b):
+    """Two solver shapes on the same draws: every integer output and the inlier masks identical; poses / covariances to the
+    rounding of two separately compiled copies of the LM body (FMA contraction differs between the kernels)."""
+    (ao, am), (bo, bm) = a, b
+    for f in ("status", "n_inliers", "iterations_run", "best_iteration", "n_variance_ok"):
+        assert np.array_equal(ao[f], bo[f]), f
+    assert np.array_equal(am, bm)
+    np.testing.assert_allclose(bo["score"], ao["score"], rtol=1e-12)
+    np.testing.assert_allclose(bo["pose"], ao["pose"], rtol=1e-6, atol=1e-7)   # LM stops at ftol = xtol = 1.5e-8 relative
+    ok = ao["status"] == 1
+    scale = np.sqrt(np.einsum("bii->bi", ao["cov"].reshape(-1, 6, 6)))
+    np.testing.assert_allclose(bo["cov"][ok].reshape(-1, 6, 6), ao["cov"][ok].reshape(-1, 6, 6), rtol=0,
+                               atol=1e-4 * float((scale[ok][:, :, None] * scale[ok][:, None, :]).max()))
+
+
+def test_chain_and_fused_solvers_agree():
+    """rs_pose_opts.solver: the three-launch chain (frame state in shared memory) and the fused persistent kernel (frame state in
+    global memory, per-frame hand-over to the Monte-Carlo solves, CTAs joining frames) run the same algorithm on the same draws
+    (keyed by frame / iteration / sample): same decisions everywhere, ragged and rejected frames included, at 119 and at 600
+    hypotheses."""
+    B = 37
+    s = rs.PoseOptimization(max_batch=B, max_matches=M, max_iterations=600)
+    for frac, iters in ((0.1, 119), (0.35, 600)):
+        truth, cur, matches, n = rs.synth.pose_batch(1200, B, M, outlier_frac=frac)
+        n = n.copy()
+        n[5] = 3                                                   # a frame RANSAC rejects
+        n[9] = 150                                                 # ragged
+        matches[11]["map"][3, 0] = np.nan                          # an invalid feature
+        outs = {}
+        for name, choice in (("chain", rs.abi.RS_SOLVER_CHAIN), ("fused", rs.abi.RS_SOLVER_FUSED)):
+            o = s.options(max_iterations=iters, seed=77, rng_mode=rs.abi.RS_RNG_DEVICE, solver=choice)
+            outs[name] = s.compute_optimized_pose(cur, matches, n, o)
+        (co, cm), (fo, fm) = outs["chain"], outs["fused"]
+        assert (co["status"] == 1).sum() >= B - 2 and co["status"][5] != 1 and co["status"][11] == 0
+        same_solution(outs["chain"], outs["fused"])
+        if iters == 600:
+            assert co["iterations_run"].max() == 600               # the early stop never fired somewhere: hundreds of hypotheses ran
+    # and the reference RNG stream (two halves around the host draws) through both
+    truth, cur, matches, n = rs.synth.pose_batch(1300, 5, M)
+    a = s.compute_optimized_pose(cur, matches, n, s.options(seed=3, rng_mode=rs.abi.RS_RNG_REFERENCE, solver=rs.abi.RS_SOLVER_CHAIN))
+    b = s.compute_optimized_pose(cur, matches, n, s.options(seed=3, rng_mode=rs.abi.RS_RNG_REFERENCE, solver=rs.abi.RS_SOLVER_FUSED))
+    same_solution(a, b)
+    s.close()
