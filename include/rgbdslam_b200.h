@@ -323,9 +323,9 @@ uint64_t rs_launch_count(void);
  *   tracking::Plane::track  (src/tracking/plane_with_tracking.cpp:16-59,81-95; N = 4, 1e-6 there; without the polygon merge),
  * for n features at once (one thread each). Arrays are row-major, [n][N] / [n][N][N]; points: state = world position,
  * planes: state = (nx, ny, nz, d) with the filtered normal re-normalised. Per feature: out_status 0, or -1 / -2 when the
- * state / measurement covariance is not a valid covariance (is_covariance_valid, covariances.hpp:13-44), -3 when the
- * innovation covariance is singular (the reference falls back to a pseudo-inverse there; not provided), -4 when the
- * result is not a valid covariance (the reference throws); in those cases the feature is returned unchanged and
+ * state / measurement covariance is not a valid covariance (is_covariance_valid, covariances.hpp:13-44), -4 when the
+ * result is not a valid covariance (the reference throws). An innovation covariance whose determinant is within DBL_EPSILON of
+ * zero takes the reference's pseudo-inverse branch (kalman_filter.hpp:73-77; Moore-Penrose inverse, Eigen's rank threshold); in those cases the feature is returned unchanged and
  * out_score = -1, as Point::track reports a refused update. out_score = |state - new state| otherwise; out_moving (points,
  * may be NULL) = the detection left the point's position by more than its own standard deviation on some axis.
  * Host-pointer entry points copy in and out on `device`; the _device variants take device pointers and are asynchronous. */
@@ -340,6 +340,43 @@ int rs_kalman_track_points_device(int n, const double* state, const double* cov,
 int rs_kalman_track_planes_device(int n, const double* state, const double* cov, const double* meas, const double* meas_cov,
                                   double process_noise, double* out_state, double* out_cov, double* out_score,
                                   int32_t* out_status, void* stream);
+
+/* ---- plane matching against the local map (the step between find_primitives and the pose solve) ---------------------
+ * Replaces the body of MapPlane::find_matches (src/map_management/map_features/map_primitive.cpp:91-161) for every map plane
+ * of every frame at once: the map plane and its boundary polygon go to camera space (PlaneWorldCoordinates::
+ * to_camera_coordinates, plane_coordinates.cpp:20-24; WorldPolygon::to_camera_space, polygon_coordinates.cpp:135-162), every
+ * detected plane of the frame that passes Plane::is_distance_similar / is_normal_similar (shape_primitives.cpp:66-84; 100 mm,
+ * 20 degrees) gets the map polygon projected into its own frame (Polygon::project, polygon.cpp:349-382) and intersected with
+ * its boundary polygon (Polygon::inter_area, polygon.cpp:542-561: the summed area of boost::geometry::intersection); the
+ * detection with the greatest intersection area whose share of the detection's own area reaches
+ * minimumPlaneOverlapToConsiderMatch (0.4f; half of it with advanced_search) is selected. As in the reference, detection 0 of
+ * a frame can never be selected (`if (selectedIndex <= 0) return`, :146).
+ * A plane with its polygon: the parametrisation (camera frame for detections, world frame for map planes), the polygon's
+ * frame (Polygon::_center / _xAxis / _yAxis) and its ring in that frame (open or closed, either orientation, simple). The
+ * polygons themselves are built on the host (CameraPolygon's concave hull / correct / simplify are flann + boost::geometry
+ * third-party code) from the boundary points rs_cape_run returns. */
+typedef struct rs_polygon_plane {
+    double normal[3];
+    double d;
+    double center[3];
+    double x_axis[3];
+    double y_axis[3];
+    int32_t first_vertex;   /* index of the ring's first (x, y) pair in the xy array */
+    int32_t n_vertices;
+} rs_polygon_plane;
+
+/* Frame f owns detections [det_first[f], det_first[f+1]) and map planes [map_first[f], map_first[f+1]) (batched sequences:
+ * every frame has its own local map). world_to_camera: n_frames row-major 4x4. det_matched (may be NULL): per detection, the
+ * reference's isDetectedFeatureMatched. Outputs per map plane: selected = index of the detection INSIDE its frame's list or
+ * -1, inter_area = the winning intersection area (0 if none). Host pointers; runs on `device`. */
+int rs_plane_match(int device, int n_frames, const double* world_to_camera, const rs_polygon_plane* det,
+                   const int32_t* det_first, const double* det_xy, const rs_polygon_plane* map, const int32_t* map_first,
+                   const double* map_xy, const uint8_t* det_matched, int advanced_search, int32_t* selected,
+                   double* inter_area);
+/* The intersection area alone, for n_pairs polygon pairs given in a common 2-D frame (a = ring a_first[i]..a_first[i+1] of
+ * a_xy, same for b): what Polygon::inter_area returns once `other` has been projected. */
+int rs_polygon_inter_area(int device, int n_pairs, const double* a_xy, const int32_t* a_first, const double* b_xy,
+                          const int32_t* b_first, double* area);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@
 
 #include <memory>
 #include <stdexcept>
+#include <limits>
 #include <vector>
 
 #include "features/primitives/primitive_detection.hpp"
@@ -131,7 +132,23 @@ class CapeContext
     }
 
   private:
-    static features::primitives::Cylinder make_cylinder(const rs_cyl_out& c, const int segment);
+    // One reference Cylinder per kept (region, sub-segment) pair, as add_cylinders_to_primitives emplaces one per surviving
+    // cylinder id (primitive_detection.cpp:705-734). The reference builds it from a COPY of the region's Cylinder_Segment whose
+    // segment count the copy constructor resets to 0 (cylinder_segment.cpp:23-33), so Cylinder::Cylinder averages the radius
+    // over zero segments: _radius = 0.0 / 0 = NaN, and only _normal (the region's axis) carries information
+    // (shape_primitives.cpp:17-25). Drop-in means the same object: axis + NaN radius. Building with
+    // -DRS_B200_CYLINDER_RADIUS hands the sub-segment's fitted radius over instead (what the reference presumably meant).
+    // Needs patch 4 of INTEGRATION.md: the value constructor Cylinder(const vector3& normal, double radius).
+    static features::primitives::Cylinder make_cylinder(const rs_cyl_out& c, const int segment)
+    {
+        const vector3 axis(c.axis[0], c.axis[1], c.axis[2]);
+#ifdef RS_B200_CYLINDER_RADIUS
+        return features::primitives::Cylinder(axis, c.radius[segment]);
+#else
+        (void)segment;
+        return features::primitives::Cylinder(axis, std::numeric_limits<double>::quiet_NaN());
+#endif
+    }
 
     rs_cape_ctx* _ctx = nullptr;
     std::vector<int32_t> _planeLabels, _cylLabels;
@@ -206,7 +223,15 @@ inline bool compute_optimized_pose(rs_pose_ctx* ctx,
     const quaternion q = currentPose.get_orientation_quaternion();
     const double cur[7] = {t.x(), t.y(), t.z(), q.w(), q.x(), q.y(), q.z()};
     rs_pose_opts opts {};
-    opts.rng_mode = RS_RNG_REFERENCE;  // the reference's own std::mt19937 stream
+    // The reference seeds its engines with time(0) unless it is built with MAKE_DETERMINISTIC (utils/random.hpp:57-64): only
+    // the deterministic build promises a particular random stream, and only there is the reference's own std::mt19937
+    // sequence reproduced (host draws on all host threads, one host round trip inside the solve: 6 k frames/s in batches).
+    // The default build gets the counter-based on-device generator (no round trip: 38 k frames/s through the same call).
+#ifdef MAKE_DETERMINISTIC
+    opts.rng_mode = RS_RNG_REFERENCE;
+#else
+    opts.rng_mode = RS_RNG_DEVICE;
+#endif
     opts.seed = utils::Random::_seed;
     opts.fx = Parameters::get_camera_1_focal_x(), opts.fy = Parameters::get_camera_1_focal_y();
     opts.cx = Parameters::get_camera_1_center_x(), opts.cy = Parameters::get_camera_1_center_y();

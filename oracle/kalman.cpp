@@ -100,6 +100,60 @@ double invert(const double* a, int M, double* inv)
         for (int j = 0; j < M; ++j) inv[i * M + j] = w[i][M + j];
     return det;
 }
+
+// Moore-Penrose inverse of the symmetric M x M matrix read through a's lower triangle. The reference calls
+// completeOrthogonalDecomposition().pseudoInverse() (kalman_filter.hpp:73-77) when the innovation covariance has a determinant
+// within DBL_EPSILON of zero - which covers the truly singular case and every well-conditioned covariance whose entries are
+// simply small (plane normals: variances of 1e-6 give a 4 x 4 determinant below 1e-16). The pseudo-inverse is unique once the
+// rank is decided; here the rank is decided on the eigenvalues (spectral decomposition by cyclic Jacobi) with Eigen's
+// relative threshold, which agrees with the pivoted-QR decision except for eigenvalues within a factor ~M of the threshold.
+// The CUDA kernel (rgb-d-slam_b200/csrc/kalman.cu) runs the same operations in the same order.
+void pinv_sym(const double* a, int M, double* out)
+{
+    // cyclic Jacobi on the symmetric matrix read through the lower triangle; V accumulates the rotations
+    double A[KF_MAX][KF_MAX], V[KF_MAX][KF_MAX];
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < M; ++j) A[i][j] = symL(a, M, i, j), V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < M; ++p)
+            for (int q = p + 1; q < M; ++q) off += A[p][q] * A[p][q];
+        if (off == 0.0) break;
+        for (int p = 0; p < M; ++p)
+            for (int q = p + 1; q < M; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < M; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < M; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < M; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double lmax = 0.0;
+    for (int i = 0; i < M; ++i) lmax = std::fmax(lmax, std::fabs(A[i][i]));
+    const double tol = DBL_EPSILON * double(M) * lmax;   // Eigen's default rank threshold: epsilon * size, relative to the largest pivot
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < M; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < M; ++k)
+                if (std::fabs(A[k][k]) > tol) s += V[i][k] * (1.0 / A[k][k]) * V[j][k];
+            out[i * M + j] = s;
+        }
+}
 }  // namespace
 
 int kalman_new_state(const int N, const int M, const double* F, const double* H, const double* Q, const double* x,
@@ -118,7 +172,7 @@ int kalman_new_state(const int N, const int M, const double* F, const double* H,
     propagate(Pp, H, N, M, S);
     for (int i = 0; i < M * M; ++i) S[i] += R[i];
     const double det = invert(S, M, Si);
-    if (std::fabs(det - 0.0) <= DBL_EPSILON) return -3;   // the reference switches to a pseudo-inverse here
+    if (std::fabs(det - 0.0) <= DBL_EPSILON) pinv_sym(S, M, Si);   // utils::double_equal(det, 0): the pseudo-inverse branch
     // K = symL(Pp) H^T S^-1
     double PHt[KF_MAX * KF_MAX], Kg[KF_MAX * KF_MAX];
     for (int i = 0; i < N; ++i)

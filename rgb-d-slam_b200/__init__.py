@@ -4,7 +4,7 @@ CAPE depth-cell plane/cylinder segmentation + RANSAC/Levenberg-Marquardt pose so
 from . import abi, sharding, synth  # noqa: F401
 from .pipeline import FramePipeline  # noqa: F401
 from .lib import (PoseOptimization, PrimitiveDetection, RsError, kalman_track_planes, kalman_track_points, last_error,  # noqa: F401
-                  launch_count, load, make_matches)
+                  launch_count, load, make_matches, plane_match, polygon_inter_area)
 
 __all__ = ["abi", "sharding", "synth", "FramePipeline", "PrimitiveDetection", "PoseOptimization", "RsError", "load", "last_error", "launch_count",
-           "make_matches", "kalman_track_points", "kalman_track_planes"]
+           "make_matches", "kalman_track_points", "kalman_track_planes", "plane_match", "polygon_inter_area"]

@@ -35,6 +35,10 @@ pose_out_dtype = np.dtype([("status", "<i4"), ("n_inliers", "<i4"), ("iterations
                            ("best_iteration", "<i4"), ("n_variance_ok", "<i4"), ("reserved", "<i4"), ("score", "<f8"),
                            ("pose", "<f8", (7,)), ("cov", "<f8", (36,))], align=True)
 
+polygon_plane_dtype = np.dtype([("normal", "<f8", (3,)), ("d", "<f8"), ("center", "<f8", (3,)), ("x_axis", "<f8", (3,)),
+                                ("y_axis", "<f8", (3,)), ("first_vertex", "<i4"), ("n_vertices", "<i4")], align=True)
+
+assert polygon_plane_dtype.itemsize == 112
 assert cell_dtype.itemsize == 160, cell_dtype.itemsize
 assert match_dtype.itemsize == 104
 assert info_dtype.itemsize == 32

@@ -22,6 +22,7 @@ UNITS = [
     ("api_cape.cu", ["-fmad=false"]),
     ("kalman.cu", ["-fmad=false"]),
     ("api_kalman.cu", []),
+    ("plane_match.cu", ["-fmad=false"]),
     ("pose_solve.cu", []),
     ("pose_chain.cu", []),
     ("api_pose.cu", []),

@@ -121,6 +121,58 @@ __device__ double invert(const double* a, double* inv)
     return det;
 }
 
+// Moore-Penrose inverse of the symmetric matrix read through a's lower triangle: the reference's pseudo-inverse branch
+// (kalman_filter.hpp:73-77, taken when |det| <= DBL_EPSILON - singular innovations, and well-conditioned ones with small
+// entries such as plane normals). Spectral decomposition by cyclic Jacobi, Eigen's relative rank threshold; operation for
+// operation what the oracle's pinv_sym does.
+template <int N>
+__device__ void pinv_sym(const double* a, double* out)
+{
+    // cyclic Jacobi on the symmetric matrix read through the lower triangle; V accumulates the rotations
+    double A[N][N], V[N][N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) A[i][j] = symL<N>(a, i, j), V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < N; ++p)
+            for (int q = p + 1; q < N; ++q) off += A[p][q] * A[p][q];
+        if (off == 0.0) break;
+        for (int p = 0; p < N; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < N; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < N; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < N; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double lmax = 0.0;
+    for (int i = 0; i < N; ++i) lmax = fmax(lmax, fabs(A[i][i]));
+    const double tol = DBL_EPSILON * double(N) * lmax;   // Eigen's default rank threshold: epsilon * size, relative to the largest pivot
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < N; ++k)
+                if (fabs(A[k][k]) > tol) s += V[i][k] * (1.0 / A[k][k]) * V[j][k];
+            out[i * N + j] = s;
+        }
+}
+
 // get_new_state with F = H = I, Q = q I. Returns 0 or a negative status (see the header).
 template <int N>
 __device__ int new_state_identity(const double* x, const double* P, const double* z, const double* R, const double q,
@@ -140,7 +192,7 @@ __device__ int new_state_identity(const double* x, const double* P, const double
     propagate_identity<N>(Pp, S);
     for (int i = 0; i < N * N; ++i) S[i] += R[i];
     const double det = invert<N>(S, Si);
-    if (fabs(det - 0.0) <= DBL_EPSILON) return -3;
+    if (fabs(det - 0.0) <= DBL_EPSILON) pinv_sym<N>(S, Si);   // utils::double_equal(det, 0): the pseudo-inverse branch
     double PHt[N * N], Kg[N * N];
     for (int i = 0; i < N; ++i)
         for (int j = 0; j < N; ++j) {

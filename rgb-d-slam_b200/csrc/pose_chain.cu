@@ -12,6 +12,7 @@
 // short-lived, so the segmentation's 108 KB CTAs find room between them, which persistent 58 KB CTAs do not leave
 // (measured: 1.69 ms per 256-frame step with the chain, 1.78-2.0 ms with the fused kernel; 1.50 against 1.20 ms for the solve
 // alone). api_pose.cu picks by hypothesis count and by what the caller says runs beside the solve.
+#define RS_ABORT_AT_TOP   // the early-stop flag of a frame lives in shared memory here: test it where the loop starts
 #include "pose_lm.cuh"
 
 namespace rs {

@@ -55,6 +55,8 @@ def load():
     lib.rs_kalman_track_planes.argtypes = [i32, i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
     lib.rs_kalman_track_points_device.argtypes = [i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp]
     lib.rs_kalman_track_planes_device.argtypes = [i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
+    lib.rs_plane_match.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.rs_polygon_inter_area.argtypes = [i32, i32, vp, vp, vp, vp, vp]
     lib.rs_last_error.restype = C.c_char_p
     lib.rs_version.restype = C.c_char_p
     lib.rs_launch_count.restype = C.c_uint64
@@ -235,6 +237,49 @@ def kalman_track_planes(state, cov, meas, meas_cov, process_noise=1e-6, device=0
                                       process_noise, out_state.ctypes.data, out_cov.ctypes.data, score.ctypes.data,
                                       status.ctypes.data), "rs_kalman_track_planes")
     return out_state, out_cov, score, status
+
+
+def plane_match(w2c, det, det_first, det_xy, map_planes, map_first, map_xy, det_matched=None, advanced_search=False, device=0):
+    """MapPlane::find_matches (map_primitive.cpp:91-161) for every map plane of every frame at once.
+    w2c [F,4,4]; det / map_planes: abi.polygon_plane_dtype records; det_first / map_first [F+1] offsets; det_xy / map_xy [V,2]
+    polygon vertices. Returns (selected [n_map] = index of the matched detection inside its frame's list or -1, inter_area)."""
+    lib = load()
+    w2c = np.ascontiguousarray(w2c, dtype=np.float64)
+    det = np.ascontiguousarray(det, dtype=abi.polygon_plane_dtype)
+    mp = np.ascontiguousarray(map_planes, dtype=abi.polygon_plane_dtype)
+    det_first, map_first = np.ascontiguousarray(det_first, dtype=np.int32), np.ascontiguousarray(map_first, dtype=np.int32)
+    det_xy, map_xy = np.ascontiguousarray(det_xy, dtype=np.float64), np.ascontiguousarray(map_xy, dtype=np.float64)
+    n_frames = len(det_first) - 1
+    if len(map_first) != n_frames + 1 or w2c.size != 16 * n_frames or det_first[-1] != len(det) or map_first[-1] != len(mp):
+        raise ValueError("offset arrays do not describe the plane arrays")
+    sel, inter = np.full(len(mp), -1, np.int32), np.zeros(len(mp))
+    dm = None if det_matched is None else np.ascontiguousarray(det_matched, dtype=np.uint8)
+    _check(lib.rs_plane_match(device, n_frames, w2c.ctypes.data, det.ctypes.data, det_first.ctypes.data, det_xy.ctypes.data,
+                              mp.ctypes.data, map_first.ctypes.data, map_xy.ctypes.data, None if dm is None else dm.ctypes.data,
+                              int(advanced_search), sel.ctypes.data, inter.ctypes.data), "rs_plane_match")
+    return sel, inter
+
+
+def polygon_inter_area(a_rings, b_rings, device=0):
+    """Polygon::inter_area (polygon.cpp:542-561) for pairs of rings given in a common 2-D frame: lists of [n,2] arrays."""
+    lib = load()
+    n = len(a_rings)
+    if len(b_rings) != n:
+        raise ValueError("need as many b rings as a rings")
+    a_first = np.zeros(n + 1, np.int32)
+    b_first = np.zeros(n + 1, np.int32)
+    a_first[1:] = np.cumsum([len(r) for r in a_rings])
+    b_first[1:] = np.cumsum([len(r) for r in b_rings])
+    a_xy = np.ascontiguousarray(np.concatenate([np.asarray(r, np.float64).reshape(-1, 2) for r in a_rings]) if n else np.zeros((0, 2)))
+    b_xy = np.ascontiguousarray(np.concatenate([np.asarray(r, np.float64).reshape(-1, 2) for r in b_rings]) if n else np.zeros((0, 2)))
+    area = np.zeros(n)
+    if a_xy.size == 0:
+        a_xy = np.zeros((1, 2))
+    if b_xy.size == 0:
+        b_xy = np.zeros((1, 2))
+    _check(lib.rs_polygon_inter_area(device, n, a_xy.ctypes.data, a_first.ctypes.data, b_xy.ctypes.data, b_first.ctypes.data,
+                                     area.ctypes.data), "rs_polygon_inter_area")
+    return area
 
 
 def make_matches(n):

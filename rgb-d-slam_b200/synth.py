@@ -267,3 +267,83 @@ def pose_batch(first_frame, batch, max_matches, **kw):
         matches[b, :len(m)] = m
         n[b] = len(m)
     return truth, cur, matches, n
+
+
+def star_polygon(rng, n, r_min=200.0, r_max=900.0, center=(0.0, 0.0), clockwise=False, closed=False):
+    """A simple (star-shaped, generally concave) ring of n vertices around `center`, mm."""
+    ang = np.sort(rng.uniform(0.0, 2 * np.pi, n))
+    ang += np.arange(n) * 1e-9   # no two vertices on one ray
+    r = rng.uniform(r_min, r_max, n)
+    ring = np.stack([center[0] + r * np.cos(ang), center[1] + r * np.sin(ang)], axis=1)
+    if clockwise:
+        ring = ring[::-1]
+    if closed:
+        ring = np.concatenate([ring, ring[:1]])
+    return np.ascontiguousarray(ring)
+
+
+def _plane_frame(normal):
+    """x / y axes spanning the plane of `normal` (the role of utils::get_plane_coordinate_system, polygon.cpp:74-115)."""
+    r = np.array([1.0, 0.0, 0.0]) if abs(normal[0]) < 0.9 else np.array([0.0, 1.0, 0.0])
+    x = np.cross(normal, r)
+    x /= np.linalg.norm(x)
+    y = np.cross(normal, x)
+    return x, y / np.linalg.norm(y)
+
+
+def plane_match_problem(seed, n_frames=4, n_det=6, n_extra_map=2, max_vertices=24):
+    """Synthetic input of rs_plane_match: per frame a camera pose, n_det detected planes (camera frame) with star-shaped
+    boundary polygons, and a local map holding a perturbed world-space copy of most detections plus unrelated planes.
+    Returns (w2c [F,4,4], det, det_first, det_xy, map, map_first, map_xy, det_matched)."""
+    rng = np.random.default_rng(seed)
+    det, mp, det_xy, map_xy, det_first, map_first, w2cs, matched = [], [], [], [], [0], [0], [], []
+
+    def add(lst, xy_list, normal, d, center, xa, ya, ring):
+        rec = np.zeros((), dtype=abi.polygon_plane_dtype)
+        rec["normal"], rec["d"], rec["center"], rec["x_axis"], rec["y_axis"] = normal, d, center, xa, ya
+        rec["first_vertex"], rec["n_vertices"] = sum(len(r) for r in xy_list), len(ring)
+        lst.append(rec)
+        xy_list.append(ring)
+
+    for f in range(n_frames):
+        q = quat_from_euler(*rng.uniform(-0.6, 0.6, 3))
+        pose = np.concatenate([rng.uniform(-1500, 1500, 3), q])
+        c2w = camera_to_world(pose)
+        w2c = np.linalg.inv(c2w)
+        w2cs.append(w2c)
+        R, t = c2w[:3, :3], c2w[:3, 3]
+        nd = int(rng.integers(max(1, n_det - 2), n_det + 1))
+        for k in range(nd):
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+            center = rng.uniform(-800, 800, 3) + np.array([0, 0, 2500.0])
+            d = -float(n @ center)
+            xa, ya = _plane_frame(n)
+            nv = int(rng.integers(3, max_vertices + 1))
+            ring = star_polygon(rng, nv, clockwise=bool(rng.integers(2)), closed=bool(rng.integers(2)))
+            add(det, det_xy, n, d, center, xa, ya, ring)
+            matched.append(rng.random() < 0.1)
+            if rng.random() < 0.8:   # the map's view of this plane: shifted / rotated in-plane / slightly tilted, other polygon
+                tilt = rng.normal(scale=0.05, size=3)
+                nm = n + tilt
+                nm /= np.linalg.norm(nm)
+                cm = center + rng.uniform(-250, 250, 3)
+                cm -= nm * (nm @ cm + d + rng.uniform(-60, 60))   # onto the (offset) plane
+                xm, ym = _plane_frame(nm)
+                a = rng.uniform(0, 2 * np.pi)
+                xm, ym = np.cos(a) * xm + np.sin(a) * ym, -np.sin(a) * xm + np.cos(a) * ym
+                ring_m = star_polygon(rng, int(rng.integers(3, max_vertices + 1)), r_min=150.0, r_max=1100.0,
+                                      clockwise=bool(rng.integers(2)), closed=bool(rng.integers(2)))
+                nw, cw = R @ nm, R @ cm + t
+                add(mp, map_xy, nw, -float(nw @ cw), cw, R @ xm, R @ ym, ring_m)
+        for k in range(n_extra_map):
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+            cw = rng.uniform(-3000, 3000, 3)
+            xa, ya = _plane_frame(n)
+            add(mp, map_xy, n, -float(n @ cw), cw, xa, ya, star_polygon(rng, int(rng.integers(3, max_vertices + 1))))
+        det_first.append(len(det))
+        map_first.append(len(mp))
+    return (np.stack(w2cs), np.array(det, dtype=abi.polygon_plane_dtype), np.array(det_first, np.int32), np.concatenate(det_xy),
+            np.array(mp, dtype=abi.polygon_plane_dtype), np.array(map_first, np.int32), np.concatenate(map_xy),
+            np.array(matched, np.uint8))

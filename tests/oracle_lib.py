@@ -47,6 +47,11 @@ def load():
     lib.orc_kalman_new_state.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.orc_kalman_track_points.argtypes = [i32, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp]
     lib.orc_kalman_track_planes.argtypes = [i32, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
+    lib.orc_polygon_inter_area.restype = dbl
+    lib.orc_polygon_inter_area.argtypes = [vp, i32, vp, i32]
+    lib.orc_polygon_area.restype = dbl
+    lib.orc_polygon_area.argtypes = [vp, i32]
+    lib.orc_plane_match.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     lib.orc_rectify_depth.argtypes = [i32, i32, dbl, dbl, dbl, dbl, vp, vp, i32, vp]
     lib.orc_ref_test_features.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32]
     _lib = lib
@@ -175,3 +180,32 @@ def morphology(mask, erode, cross, border_zero):
     out = np.empty_like(m)
     lib.orc_morphology(m.ctypes.data, m.shape[0], m.shape[1], int(erode), int(cross), int(border_zero), out.ctypes.data)
     return out
+
+
+def polygon_inter_area(a, b):
+    """Polygon::inter_area once `other` is projected (polygon.cpp:542-561): area of the intersection of two simple rings."""
+    lib = load()
+    a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+    return lib.orc_polygon_inter_area(a.ctypes.data, len(a), b.ctypes.data, len(b))
+
+
+def polygon_area(a):
+    lib = load()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return lib.orc_polygon_area(a.ctypes.data, len(a))
+
+
+def plane_match(w2c, det, det_first, det_xy, mp, map_first, map_xy, det_matched=None, advanced_search=False):
+    """MapPlane::find_matches for every map plane of every frame (oracle/polygon.cpp). Same arguments as rs.plane_match."""
+    lib = load()
+    w2c = np.ascontiguousarray(w2c, dtype=np.float64)
+    det, mp = np.ascontiguousarray(det, dtype=abi.polygon_plane_dtype), np.ascontiguousarray(mp, dtype=abi.polygon_plane_dtype)
+    det_first, map_first = np.ascontiguousarray(det_first, dtype=np.int32), np.ascontiguousarray(map_first, dtype=np.int32)
+    det_xy, map_xy = np.ascontiguousarray(det_xy, dtype=np.float64), np.ascontiguousarray(map_xy, dtype=np.float64)
+    n_frames = len(det_first) - 1
+    sel, inter = np.full(len(mp), -1, np.int32), np.zeros(len(mp))
+    dm = None if det_matched is None else np.ascontiguousarray(det_matched, dtype=np.uint8)
+    lib.orc_plane_match(n_frames, w2c.ctypes.data, det.ctypes.data, det_first.ctypes.data, det_xy.ctypes.data, mp.ctypes.data,
+                        map_first.ctypes.data, map_xy.ctypes.data, None if dm is None else dm.ctypes.data, int(advanced_search),
+                        sel.ctypes.data, inter.ctypes.data)
+    return sel, inter

@@ -55,13 +55,14 @@ def test_refused_updates_and_edge_cases():
     R[2][0, 1] += 0.5                                                  # asymmetric measurement covariance
     P[3][1, 1] = np.nan
     P[4] = 0.0
-    R[4] = 0.0                                                         # singular innovation (only the process noise left)
+    R[4] = 0.0                                                         # zero innovation covariance: pseudo-inverse 0, nothing moves
     got = rs.kalman_track_points(x, P, z, R, process_noise=0.0)
     ref = ol.kalman_track_points(x, P, z, R, process_noise=0.0)
     assert np.array_equal(got[4], ref[4])
-    assert got[4][1] == -1 and got[4][2] == -2 and got[4][3] == -1 and got[4][4] == -3
-    for i in (1, 2, 4):                                                # refused: feature unchanged, score -1
+    assert got[4][1] == -1 and got[4][2] == -2 and got[4][3] == -1 and got[4][4] == 0
+    for i in (1, 2):                                                   # refused: feature unchanged, score -1
         assert np.array_equal(got[0][i], x[i]) and got[2][i] == -1.0
+    assert np.array_equal(got[0][4], x[4]) and got[2][4] == 0.0        # accepted, gain 0
     ok = got[4] == 0
     assert got[0][ok].tobytes() == ref[0][ok].tobytes() and got[1][ok].tobytes() == ref[1][ok].tobytes()
     # empty batch is a no-op; wrong shapes are rejected on the host
@@ -81,3 +82,41 @@ def test_repeated_updates_converge_like_the_reference_filter():
         x, P, score, moving, status = rs.kalman_track_points(x, P, np.full((4, 3), m), R, process_noise=0.0)
         assert (status == 0).all()
     assert np.abs(x - 50).max() < 0.05
+
+
+def test_pseudo_inverse_branch_matches_the_oracle_bit_for_bit():
+    """kalman_filter.hpp:73-77: |det(innovation)| <= DBL_EPSILON -> completeOrthogonalDecomposition().pseudoInverse().
+    Rank-deficient innovations (an axis with no uncertainty at all) and well-conditioned ones with small entries (plane
+    normals) both go there; GPU == oracle bit for bit, oracle == numpy.linalg.pinv in tests/test_oracle_kalman.py."""
+    rng = np.random.default_rng(9)
+    n = 256
+    x = rng.uniform(-500, 500, (n, 3))
+    z = x + rng.standard_normal((n, 3))
+    P, R = np.zeros((n, 3, 3)), np.zeros((n, 3, 3))
+    for i in range(n):
+        rank = 1 + i % 2                                                # rank-1 and rank-2 covariances, null space on coordinate axes
+        a = rng.standard_normal((rank, rank))
+        axes = rng.permutation(3)[:rank]
+        blk = a @ a.T + np.eye(rank) * 0.5
+        P[i][np.ix_(axes, axes)] = blk
+        R[i][np.ix_(axes, axes)] = blk * rng.uniform(0.5, 2.0)
+    got = rs.kalman_track_points(x, P, z, R, process_noise=0.0)
+    ref = ol.kalman_track_points(x, P, z, R, process_noise=0.0)
+    assert np.array_equal(got[4], ref[4])
+    ok = ref[4] == 0
+    assert ok.all()
+    assert got[0][ok].tobytes() == ref[0][ok].tobytes() and got[1][ok].tobytes() == ref[1][ok].tobytes()
+    # planes with realistic (small) covariances: det ~ 1e-20, full rank
+    npl = 512
+    nrm = rng.standard_normal((npl, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    xp = np.concatenate([nrm, rng.uniform(500, 3000, (npl, 1))], axis=1)
+    zp = xp + np.concatenate([rng.standard_normal((npl, 3)) * 1e-3, rng.standard_normal((npl, 1))], axis=1)
+    C = rng.standard_normal((npl, 4, 4)) * np.array([5e-4, 5e-4, 5e-4, 1.0])[None, :, None]
+    Pq = C @ C.transpose(0, 2, 1) + np.diag([1e-7, 1e-7, 1e-7, 1e-2])
+    assert (np.abs(np.linalg.det(2 * Pq)) < 2.2e-16).mean() > 0.5     # most of them take the branch
+    gp = rs.kalman_track_planes(xp, Pq, zp, Pq, process_noise=1e-9)
+    rp = ol.kalman_track_planes(xp, Pq, zp, Pq, process_noise=1e-9)
+    assert np.array_equal(gp[3], rp[3]) and (rp[3] == 0).mean() > 0.95
+    okp = rp[3] == 0
+    assert gp[0][okp].tobytes() == rp[0][okp].tobytes() and gp[1][okp].tobytes() == rp[1][okp].tobytes()

@@ -127,3 +127,48 @@ def test_point_and_plane_tracking_semantics():
     xo, Po, score, status = ol.kalman_track_planes(xp, Pq, zp, Pq)
     assert (status == 0).all()
     np.testing.assert_allclose(np.linalg.norm(xo[:, :3], axis=1), 1.0, atol=1e-12)
+
+
+def _rank_deficient(rng, rank):
+    """3x3 covariance of the given rank whose null space is spanned by coordinate axes: the determinant is an exact 0 (a
+    rotated null space leaves det ~ 1e-14 > DBL_EPSILON, and the reference then inverts a numerically singular matrix)."""
+    a = rng.standard_normal((rank, rank))
+    blk = a @ a.T + np.eye(rank) * 0.5
+    m = np.zeros((3, 3))
+    axes = rng.permutation(3)[:rank]
+    m[np.ix_(axes, axes)] = blk
+    return (m + m.T) / 2, axes
+
+
+def test_pseudo_inverse_branch_against_numpy():
+    """kalman_filter.hpp:73-77. (a) a rank-deficient innovation covariance: the update equals the textbook one with
+    numpy.linalg.pinv; (b) a well-conditioned covariance with small entries (|det| <= DBL_EPSILON all the same): the
+    pseudo-inverse is the inverse."""
+    rng = np.random.default_rng(4)
+    I3 = np.eye(3)
+    for trial in range(50):
+        P, axes = _rank_deficient(rng, 1 + trial % 2)
+        R = P * 1.7
+        x, z = rng.uniform(-10, 10, 3), rng.uniform(-10, 10, 3)
+        rc, xo, Po = ol.kalman_new_state(I3, I3, I3 * 0.0, x, P, z, R)
+        assert rc == 0
+        S = P + R
+        assert abs(np.linalg.det(S)) <= 2.2e-16
+        K = P @ np.linalg.pinv(S, rcond=3 * 2.2e-16, hermitian=True)
+        np.testing.assert_allclose(xo, x + K @ (z - x), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(Po, (I3 - K) @ P, rtol=1e-9, atol=1e-9)
+    I4 = np.eye(4)
+    in_branch = 0
+    for trial in range(50):
+        C = rng.standard_normal((4, 4)) * np.array([5e-4, 5e-4, 5e-4, 1.0])[:, None]
+        P = C @ C.T + np.diag([1e-7, 1e-7, 1e-7, 1e-2])
+        x, z = rng.standard_normal(4), rng.standard_normal(4)
+        rc, xo, Po = ol.kalman_new_state(I4, I4, I4 * 1e-9, x, P, z, P)
+        assert rc == 0
+        Pp = P + I4 * 1e-9
+        S = Pp + P
+        in_branch += abs(np.linalg.det(S)) <= 2.2e-16
+        K = Pp @ np.linalg.inv(S)
+        np.testing.assert_allclose(xo, x + K @ (z - x), rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(Po, (I4 - K) @ Pp, rtol=1e-6, atol=1e-14)
+    assert in_branch > 25
