@@ -271,7 +271,10 @@ def pose_batch(first_frame, batch, max_matches, **kw):
 
 def star_polygon(rng, n, r_min=200.0, r_max=900.0, center=(0.0, 0.0), clockwise=False, closed=False):
     """A simple (star-shaped, generally concave) ring of n vertices around `center`, mm."""
-    ang = np.sort(rng.uniform(0.0, 2 * np.pi, n))
+    while True:   # every angular gap below pi: the ring is star-shaped about `center`, hence simple
+        ang = np.sort(rng.uniform(0.0, 2 * np.pi, n))
+        if np.max(np.diff(np.concatenate([ang, ang[:1] + 2 * np.pi]))) < 0.9 * np.pi:
+            break
     ang += np.arange(n) * 1e-9   # no two vertices on one ray
     r = rng.uniform(r_min, r_max, n)
     ring = np.stack([center[0] + r * np.cos(ang), center[1] + r * np.sin(ang)], axis=1)
