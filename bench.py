@@ -87,7 +87,7 @@ def parse_args():
     p.add_argument("--frames-per-gpu", type=int, default=0)
     p.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 10))")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--solver", default="auto", choices=["auto", "chain", "fused"],
+    p.add_argument("--solver", default="auto", choices=["auto", "chain", "fused", "wide"],
                    help="rs_pose_opts.solver of the timed step: the three-launch chain, the fused persistent kernel, or by shape")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-e2e-lanes", action="store_true", help="skip the two-batches-in-flight variant of the host-buffer leg")
@@ -254,7 +254,8 @@ def measure_resident(wl, args, rs, torch, dist, rank, world, local_rank, steps, 
     counter = [0]
     comm_ms = []
 
-    solver_choice = {"auto": rs.abi.RS_SOLVER_AUTO, "chain": rs.abi.RS_SOLVER_CHAIN, "fused": rs.abi.RS_SOLVER_FUSED}[args.solver]
+    solver_choice = {"auto": rs.abi.RS_SOLVER_AUTO, "chain": rs.abi.RS_SOLVER_CHAIN, "fused": rs.abi.RS_SOLVER_FUSED,
+                     "wide": rs.abi.RS_SOLVER_WIDE}[args.solver]
     opts = solver.options(max_iterations=wl.hypotheses, seed=1234 + rank, rng_mode=rs.abi.RS_RNG_DEVICE, intrinsics=wl.K,
                           solver=solver_choice)
 

@@ -11,7 +11,7 @@ RS_MAX_CYL_SEGS = 8
 RS_CYL_RANSAC_ITERS = 43
 RS_FEAT_POINT, RS_FEAT_PLANE, RS_FEAT_POINT2D = 0, 1, 2
 RS_RNG_REFERENCE, RS_RNG_DEVICE = 0, 1
-RS_SOLVER_AUTO, RS_SOLVER_CHAIN, RS_SOLVER_FUSED = 0, 1, 2
+RS_SOLVER_AUTO, RS_SOLVER_CHAIN, RS_SOLVER_FUSED, RS_SOLVER_WIDE = 0, 1, 2, 3
 RS_MAX_SUBSET = 16
 
 # numpy structured dtypes with the exact C layout (align=True reproduces the compiler's padding)

@@ -25,6 +25,7 @@ UNITS = [
     ("plane_match.cu", ["-fmad=false"]),
     ("pose_solve.cu", []),
     ("pose_chain.cu", []),
+    ("pose_wide.cu", []),
     ("api_pose.cu", []),
 ]
 

@@ -18,6 +18,7 @@ using namespace rs;
 
 struct rs_pose_ctx {
     int max_batch, M, max_iterations, max_variance, device;
+    int sm_count = 148;
     rs_match* d_matches = nullptr;
     double* d_cur = nullptr;
     int32_t* d_n = nullptr;
@@ -60,6 +61,8 @@ int dev_alloc(T** p, size_t n)
     return RS_OK;
 }
 
+constexpr int kWideMinIterations = 256;   // beyond this many hypotheses per frame the one-hypothesis-per-lane kernel is the default
+
 int create_impl(rs_pose_ctx* c)
 {
     int rc = require_blackwell(c->device);
@@ -91,6 +94,15 @@ int create_impl(rs_pose_ctx* c)
     if ((rc = dev_alloc(&b.open_list, B))) return rc;
     if ((rc = dev_alloc(&b.mc_done, B))) return rc;
     if ((rc = dev_alloc(&b.frame_times, B * 4))) return rc;
+    b.hyp = nullptr, b.hyp_mask = nullptr, b.fold = nullptr, b.fold_mask = nullptr;
+    if (c->max_iterations > kWideMinIterations && pose_wide_supports(c->M) && pose_chain_supports(c->M)) {
+        // one hypothesis per lane (pose_wide.cu): a record and an inlier mask per hypothesis
+        if ((rc = dev_alloc(&b.hyp, B * size_t(c->max_iterations)))) return rc;
+        if ((rc = dev_alloc(&b.hyp_mask, B * size_t(c->max_iterations) * ((M + 31) / 32)))) return rc;
+        if ((rc = dev_alloc(&b.fold, B))) return rc;
+        if ((rc = dev_alloc(&b.fold_mask, B * ((M + 31) / 32)))) return rc;
+    }
+    RS_CUDA_CHECK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     b.matches_aos = c->d_matches, b.cur_pose = c->d_cur, b.n_matches = c->d_n;
     b.subsets_in = nullptr, b.normals_in = nullptr;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -148,8 +160,8 @@ int resolve_launch(const rs_pose_ctx* c, const rs_pose_opts* opts, int batch, Po
     prm.has_point2d = c->has_point2d ? 1 : 0;
     prm.ctas_per_sm = o.worker_ctas_per_sm;
     prm.solver = o.solver;
-    if (prm.solver < 0 || prm.solver > 2) {
-        set_last_error("rs_pose: unknown solver (0 = by shape, 1 = chain, 2 = fused)");
+    if (prm.solver < 0 || prm.solver > 3) {
+        set_last_error("rs_pose: unknown solver (0 = by shape, 1 = chain, 2 = fused, 3 = one hypothesis per lane)");
         return RS_ERR_INVALID_ARG;
     }
     if (const char* e = std::getenv("RS_POSE_SPLIT")) prm.split = std::atoi(e);
@@ -319,10 +331,21 @@ int solve_impl(rs_pose_ctx* c, int batch, const PoseLaunch& prm, cudaStream_t s,
         return rc;
     c->prepared_batch = 0;
     if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[1], s));
-    const bool fused = lp.solver == 2 || (lp.solver == 0 && lp.max_iterations > 256) || !pose_chain_supports(c->M);
+    // one hypothesis per lane (pose_wide.cu) when a frame has hundreds of hypotheses; it knows points and planes only
+    const bool wide_ok = buf.hyp != nullptr && !lp.has_point2d;
+    if (lp.solver == 3 && !wide_ok) {
+        set_last_error("rs_pose: solver 3 needs a context created with max_iterations > 256 and a batch without RS_FEAT_POINT2D features");
+        return RS_ERR_INVALID_ARG;
+    }
+    const bool wide = lp.solver == 3 || (lp.solver == 0 && wide_ok && lp.max_iterations > kWideMinIterations);
+    const bool fused = !wide && (lp.solver == 2 || (lp.solver == 0 && lp.max_iterations > 256) || !pose_chain_supports(c->M));
     c->last_fused = fused;
     if (!fused) {
-        // the three-launch chain (pose_chain.cu)
+        // the three-launch chain (pose_chain.cu), or the hypotheses one per lane and the chain's kernels for the rest
+        if (wide) {
+            if ((rc = launch_pose_wide_hypotheses(buf, lp, s, c->sm_count)) != RS_OK) return rc;
+            lp.final_only = 1;
+        }
         if ((rc = launch_pose_chain_ransac(buf, lp, s)) != RS_OK) return rc;
         RS_CUDA_CHECK(cudaEventRecord(c->ransac_done, s));
         if (ev) RS_CUDA_CHECK(cudaEventRecord(ev[2], s));
@@ -466,6 +489,10 @@ void rs_pose_destroy(rs_pose_ctx* c)
     cudaFree(b.open_list);
     cudaFree(b.mc_done);
     cudaFree(b.frame_times);
+    cudaFree(b.hyp);
+    cudaFree(b.hyp_mask);
+    cudaFree(b.fold);
+    cudaFree(b.fold_mask);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->ransac_done) cudaEventDestroy(c->ransac_done);
     if (c->group_fork) cudaEventDestroy(c->group_fork);

@@ -119,8 +119,19 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
     }
     for (int i = threadIdx.x; i < words; i += blockDim.x) sm.best_mask[i] = 0u;
     __syncthreads();
+    if (prm.final_only) {
+        // the hypotheses were evaluated and folded elsewhere (pose_wide.cu): take the serial loop's end state from there
+        const HypFold& f = buf.fold[b];
+        if (threadIdx.x == 0) {
+            sh.max_score = f.max_score;
+            sh.best_inliers = f.best_inliers, sh.best_iteration = f.best_iteration, sh.started = f.started;
+            for (int j = 0; j < 6; ++j) sh.best_x[j] = f.best_x[j];
+        }
+        for (int i = threadIdx.x; i < words; i += blockDim.x) sm.best_mask[i] = buf.fold_mask[size_t(b) * words + i];
+        __syncthreads();
+    }
 
-    const int maxIterations = prm.max_iterations;
+    const int maxIterations = prm.final_only ? 0 : prm.max_iterations;
     const unsigned inliersToStop = unsigned(ceil(double(n) * kEarlyStopProportion));
     WarpLM& S = sm.lm[warp];
     short* subset = sm.subset + warp * RS_MAX_SUBSET;

@@ -49,6 +49,14 @@ struct RansacFrame {
     int done[kRansacRing];          // iteration + 1 once the slot's result is complete
     RansacSlot slot[kRansacRing];
 };
+// ---- one hypothesis per lane (pose_wide.cu): every hypothesis of a chunk leaves a record, the serial rule is folded over them
+using HypRecord = RansacSlot;
+struct HypFold {       // best-so-far state of a frame's serial RANSAC loop between chunks (pose_optimization.cpp:151-227)
+    double max_score;
+    double best_x[6];
+    int best_inliers, best_iteration, started, can_quit;
+};
+
 struct PoseWork {
     int join_ticket;   // frames handed to a first CTA so far
     int frames_done;   // frames whose RANSAC + final LM stage is over (whatever the outcome)
@@ -89,6 +97,11 @@ struct PoseBuffers {
     int32_t* ready;                // B : frame + 1, in the order the frames finished their RANSAC stage
     int32_t* open_list;            // B : frame + 1, frames whose hypothesis loop went past the minimum and takes helpers
     int32_t* mc_done;              // B : Monte-Carlo sample groups finished per frame (the last one reduces the covariance)
+    // one hypothesis per lane (allocated when the context's max_iterations makes that path eligible)
+    HypRecord* hyp;                // B x max_iterations
+    unsigned* hyp_mask;            // B x max_iterations x words
+    HypFold* fold;                 // B
+    unsigned* fold_mask;           // B x words : inlier mask of the best hypothesis so far
     unsigned long long* frame_times;   // B x 4 %globaltimer stamps: hypotheses started, hypothesis stage closed, final LM done, covariance done
 };
 
@@ -106,6 +119,8 @@ struct PoseLaunch {
                           // iterations nobody joins: measured, the hypotheses helpers run there are mostly dropped by the early stop)
     int solver = 0;       // host side: 0 = by shape (the three-launch chain up to 256 hypotheses per frame, the fused kernel beyond),
                           // 1 = chain, 2 = fused kernel (rs_pose_opts.solver)
+    int iter0 = 0, iter_count = 0;   // pose_wide.cu: the chunk of RANSAC iterations a launch covers
+    int final_only = 0;   // chain RANSAC kernel: skip the hypotheses, run the final optimisation from the HypFold state
     int split = 1;        // host side: frame role and Monte-Carlo role in two launches side by side (0: one launch with both)
     int ctas_per_sm = 0;  // resident CTAs per SM the fused kernel is launched with (<= 0: what fits)
     // roles of one launch of the fused kernel (any number of launches may feed on the same work queues)
@@ -123,6 +138,9 @@ int pose_max_matches_supported();
 bool pose_chain_supports(int max_matches);
 int launch_pose_chain_ransac(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
 int launch_pose_chain_variance(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);   // longest match list whose staging fits the shared memory of one SM
+// hundreds of hypotheses per frame: one hypothesis per lane, in chunks with the serial rule folded in between (pose_wide.cu)
+bool pose_wide_supports(int max_matches);
+int launch_pose_wide_hypotheses(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream, int sm_count);
 int launch_pose_prepare(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);
 // RANSAC hypotheses, final LM, Monte-Carlo solves and covariance of a batch in ONE persistent kernel (prm.phase selects halves)
 int launch_pose_fused(const PoseBuffers& buf, const PoseLaunch& prm, cudaStream_t stream);

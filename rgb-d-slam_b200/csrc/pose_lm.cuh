@@ -546,7 +546,11 @@ __device__ __forceinline__ void backward6_packed(const double (&m)[21], const do
 // Rank-deficient / ill-conditioned J (a pivot of the unpivoted factorisation collapsed): MINPACK's pivoted path.
 // Diagonally pivoted LDL^T of C gives the rank and the basic Gauss-Newton solution (zeros on the dependent columns);
 // parl = 0 when the rank is deficient. Rare (degenerate subsets, a frozen coordinate), so plain loops on local arrays.
-__device__ __noinline__ void lmpar_deficient(WarpLM& S)
+struct LmparIO {
+    double C[21], sc[6], g[6], diag[6], xs[6];
+    double delta, par;
+};
+__device__ __noinline__ void lmpar_deficient(LmparIO& S)
 {
     const double dwarf = DBL_MIN, delta = S.delta;
     double M[36], dinv[6], sg[6], e2[6], z[6], x[6], wa2[6];
@@ -682,7 +686,8 @@ __device__ __noinline__ void lmpar_deficient(WarpLM& S)
 
 // unsupported/Eigen/src/NonLinearOptimization/lmpar.h (lmpar2): trust-region parameter S.par and step S.xs.
 // One factorise-and-solve body serves the Gauss-Newton step (pass 0, par = 0) and the damped steps (passes 1..10).
-__device__ __forceinline__ void lmpar(WarpLM& S)
+template <class St>
+__device__ __forceinline__ void lmpar(St& S)
 {
     const double dwarf = DBL_MIN;
     const double delta = S.delta;
@@ -707,7 +712,14 @@ __device__ __forceinline__ void lmpar(WarpLM& S)
         }
         const bool ok = ldl6_packed(M, dinv, 64.0 * DBL_EPSILON);
         if (iter == 0 && !ok) {
-            lmpar_deficient(S);
+            // out of line, on a copy of what it needs: the caller's state may live in registers (one LM per lane)
+            LmparIO io;
+            for (int i = 0; i < 21; ++i) io.C[i] = S.C[i];
+            for (int j = 0; j < 6; ++j) io.sc[j] = S.sc[j], io.g[j] = S.g[j], io.diag[j] = S.diag[j];
+            io.delta = S.delta, io.par = S.par;
+            lmpar_deficient(io);
+            S.par = io.par;
+            for (int j = 0; j < 6; ++j) S.xs[j] = io.xs[j];
             return;
         }
         forward6_packed(M, z);
@@ -761,6 +773,134 @@ __device__ __forceinline__ void lmpar(WarpLM& S)
     S.par = par;
 #pragma unroll
     for (int j = 0; j < 6; ++j) S.xs[j] = x[j];
+}
+
+// ---- the serial part of one LM iteration, on whatever holds the 6x6 state (shared memory for a warp-wide LM, registers for
+// one LM per lane): same member names, same arithmetic.
+// After the Jacobian pass (S.A = J^T J, S.g = J^T r): column scaling, the scaled matrix C, MINPACK's diag / gnorm bookkeeping.
+template <class St>
+__device__ __forceinline__ void lm_after_jacobian(St& S)
+{
+    S.nfev += 7;  // NumericalDiff re-evaluates f(x) and then one evaluation per column
+    double sc[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const double ajj = S.A[j * 6 + j];
+        sc[j] = ajj > 0.0 ? rsqrt(ajj) : 1.0;   // 1 / |J_j|
+        S.wa2[j] = ajj > 0.0 ? ajj * sc[j] : 0.0;
+        S.sc[j] = sc[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) S.C[RS_T(i, j)] = S.A[i * 6 + j] * sc[i] * sc[j];
+    if (S.iter == 1) {
+        double tt[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            S.diag[j] = (S.wa2[j] == 0.0) ? 1.0 : S.wa2[j];
+            tt[j] = S.diag[j] * S.x[j];
+        }
+        S.xnorm = norm6(tt);
+        S.delta = 100.0 * S.xnorm;
+        if (S.delta == 0.0) S.delta = 100.0;
+    }
+    // gnorm = max_j |J_j . r| / (|J_j| |r|)
+    double gnorm = 0.0;
+    if (S.fnorm != 0.0) {
+        const double ifn = 1.0 / S.fnorm;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            if (S.wa2[j] != 0.0) gnorm = fmax(gnorm, fabs((S.g[j] * ifn) * sc[j]));
+    }
+    S.gnorm = gnorm;
+    if (gnorm <= 0.0) S.status = 4;  // CosinusTooSmall (gtol = 0)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) S.diag[j] = fmax(S.diag[j], S.wa2[j]);
+}
+
+// Trust-region step: lmpar, the trial point S.xt and its transform S.T.
+template <class St>
+__device__ __forceinline__ void lm_propose(St& S)
+{
+    lmpar(S);
+    double tt[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        S.p[j] = -S.xs[j];
+        S.xt[j] = S.x[j] + S.p[j];
+        tt[j] = S.diag[j] * S.p[j];
+    }
+    S.pnorm = norm6(tt);
+    if (S.iter == 1) S.delta = fmin(S.delta, S.pnorm);
+    make_xform(S.xt, S.T);
+}
+
+// The trial point's |f|^2 is in: actual / predicted reduction, trust-region update, acceptance, stop codes (lmder's tail).
+template <class St>
+__device__ __forceinline__ void lm_judge(St& S, const double ss1, const int maxfev)
+{
+    ++S.nfev;
+    const double fnorm = S.fnorm, fnorm1 = sqrt(ss1), pnorm = S.pnorm;
+    const double inv_fnorm = 1.0 / fnorm;
+    double actred = -1.0;
+    if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 * inv_fnorm) * (fnorm1 * inv_fnorm);
+    // |J p|^2 = p^T A p
+    double pAp = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) sum += S.A[i * 6 + j] * S.p[j];
+        pAp += sum * S.p[i];
+    }
+    const double temp1 = fmax(pAp, 0.0) * inv_fnorm * inv_fnorm;
+    const double temp2 = S.par * (pnorm * inv_fnorm) * (pnorm * inv_fnorm);
+    const double prered = temp1 + temp2 * 2.0;
+    const double dirder = -(temp1 + temp2);
+    double ratio = 0.0;
+    if (prered != 0.0) ratio = actred / prered;
+    if (ratio <= 0.25) {
+        double temp = 0.0;
+        if (actred >= 0.0) temp = 0.5;
+        if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
+        if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+        S.delta = temp * fmin(S.delta, pnorm * 10.0);
+        S.par /= temp;
+    }
+    else if (!(S.par != 0.0 && ratio < 0.75)) {
+        S.delta = pnorm * 2.0;
+        S.par = 0.5 * S.par;
+    }
+    if (ratio >= 1e-4) {
+        double tt[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            S.x[j] = S.xt[j];
+            tt[j] = S.diag[j] * S.x[j];
+        }
+        S.xnorm = norm6(tt);
+        S.fnorm = fnorm1;
+        ++S.iter;
+    }
+    const double ftol = kSqrtEps, xtol = kSqrtEps;
+    int status = kRunning;
+    if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && S.delta <= xtol * S.xnorm)
+        status = 3;
+    else if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0)
+        status = 1;
+    else if (S.delta <= xtol * S.xnorm)
+        status = 2;
+    else if (S.nfev >= maxfev)
+        status = 5;
+    else if (fabs(actred) <= DBL_EPSILON && prered <= DBL_EPSILON && 0.5 * ratio <= 1.0)
+        status = 6;
+    else if (S.delta <= DBL_EPSILON * S.xnorm)
+        status = 7;
+    else if (S.gnorm <= DBL_EPSILON)
+        status = 8;
+    S.status = status;
+    S.again = (status == kRunning && ratio < 1e-4) ? 1 : 0;
 }
 
 // Eigen::LevenbergMarquardt<NumericalDiff<F,Forward>>::minimize on S.x (in/out). Whole warp must call; returns the
@@ -853,128 +993,17 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
             S.g[lane - 21] = mine;
         __syncwarp();
 
-        if (lane == 0) {
-            S.nfev += 7;  // NumericalDiff re-evaluates f(x) and then one evaluation per column
-            double sc[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const double ajj = S.A[j * 6 + j];
-                sc[j] = ajj > 0.0 ? rsqrt(ajj) : 1.0;   // 1 / |J_j|
-                S.wa2[j] = ajj > 0.0 ? ajj * sc[j] : 0.0;
-                S.sc[j] = sc[j];
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) S.C[RS_T(i, j)] = S.A[i * 6 + j] * sc[i] * sc[j];
-            if (S.iter == 1) {
-                double tt[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    S.diag[j] = (S.wa2[j] == 0.0) ? 1.0 : S.wa2[j];
-                    tt[j] = S.diag[j] * S.x[j];
-                }
-                S.xnorm = norm6(tt);
-                S.delta = 100.0 * S.xnorm;
-                if (S.delta == 0.0) S.delta = 100.0;
-            }
-            // gnorm = max_j |J_j . r| / (|J_j| |r|)
-            double gnorm = 0.0;
-            if (S.fnorm != 0.0) {
-                const double ifn = 1.0 / S.fnorm;
-#pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    if (S.wa2[j] != 0.0) gnorm = fmax(gnorm, fabs((S.g[j] * ifn) * sc[j]));
-            }
-            S.gnorm = gnorm;
-            if (gnorm <= 0.0) S.status = 4;  // CosinusTooSmall (gtol = 0)
-#pragma unroll
-            for (int j = 0; j < 6; ++j) S.diag[j] = fmax(S.diag[j], S.wa2[j]);
-        }
+        if (lane == 0) lm_after_jacobian(S);
         __syncwarp();
         if (S.status != kRunning) break;
 
         // ---- inner loop: trust-region step until the ratio is acceptable ----
 #pragma unroll 1
         while (true) {
-            if (lane == 0) {
-                lmpar(S);
-                double tt[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    S.p[j] = -S.xs[j];
-                    S.xt[j] = S.x[j] + S.p[j];
-                    tt[j] = S.diag[j] * S.p[j];
-                }
-                S.pnorm = norm6(tt);
-                if (S.iter == 1) S.delta = fmin(S.delta, S.pnorm);
-                make_xform(S.xt, S.T);
-            }
+            if (lane == 0) lm_propose(S);
             __syncwarp();
             const double ss1 = eval_sumsq<P2D>(P, S.T, K, lane);
-            if (lane == 0) {
-                ++S.nfev;
-                const double fnorm = S.fnorm, fnorm1 = sqrt(ss1), pnorm = S.pnorm;
-                const double inv_fnorm = 1.0 / fnorm;
-                double actred = -1.0;
-                if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 * inv_fnorm) * (fnorm1 * inv_fnorm);
-                // |J p|^2 = p^T A p
-                double pAp = 0.0;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    double sum = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) sum += S.A[i * 6 + j] * S.p[j];
-                    pAp += sum * S.p[i];
-                }
-                const double temp1 = fmax(pAp, 0.0) * inv_fnorm * inv_fnorm;
-                const double temp2 = S.par * (pnorm * inv_fnorm) * (pnorm * inv_fnorm);
-                const double prered = temp1 + temp2 * 2.0;
-                const double dirder = -(temp1 + temp2);
-                double ratio = 0.0;
-                if (prered != 0.0) ratio = actred / prered;
-                if (ratio <= 0.25) {
-                    double temp = 0.0;
-                    if (actred >= 0.0) temp = 0.5;
-                    if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
-                    if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
-                    S.delta = temp * fmin(S.delta, pnorm * 10.0);
-                    S.par /= temp;
-                }
-                else if (!(S.par != 0.0 && ratio < 0.75)) {
-                    S.delta = pnorm * 2.0;
-                    S.par = 0.5 * S.par;
-                }
-                if (ratio >= 1e-4) {
-                    double tt[6];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        S.x[j] = S.xt[j];
-                        tt[j] = S.diag[j] * S.x[j];
-                    }
-                    S.xnorm = norm6(tt);
-                    S.fnorm = fnorm1;
-                    ++S.iter;
-                }
-                const double ftol = kSqrtEps, xtol = kSqrtEps;
-                int status = kRunning;
-                if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && S.delta <= xtol * S.xnorm)
-                    status = 3;
-                else if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0)
-                    status = 1;
-                else if (S.delta <= xtol * S.xnorm)
-                    status = 2;
-                else if (S.nfev >= maxfev)
-                    status = 5;
-                else if (fabs(actred) <= DBL_EPSILON && prered <= DBL_EPSILON && 0.5 * ratio <= 1.0)
-                    status = 6;
-                else if (S.delta <= DBL_EPSILON * S.xnorm)
-                    status = 7;
-                else if (S.gnorm <= DBL_EPSILON)
-                    status = 8;
-                S.status = status;
-                S.again = (status == kRunning && ratio < 1e-4) ? 1 : 0;
-            }
+            if (lane == 0) lm_judge(S, ss1, maxfev);
             __syncwarp();
             if (S.status != kRunning || !S.again) break;
         }

@@ -315,7 +315,7 @@ class PoseOptimization:
     def options(max_iterations=0, n_variance=-1, rng_mode=abi.RS_RNG_REFERENCE, seed=0, intrinsics=None, lm_max_fev=0,
                 sub_batches=0, worker_ctas_per_sm=0, solver=0):
         o = abi.PoseOpts()
-        o.solver = solver                           # abi.RS_SOLVER_AUTO / _CHAIN / _FUSED
+        o.solver = solver                           # abi.RS_SOLVER_AUTO / _CHAIN / _FUSED / _WIDE
         o.worker_ctas_per_sm = worker_ctas_per_sm   # <= 0: as many resident CTAs per SM as fit
         o.max_iterations, o.n_variance, o.rng_mode, o.seed, o.lm_max_fev = max_iterations, n_variance, rng_mode, seed, lm_max_fev
         o.sub_batches = sub_batches   # RS_RNG_DEVICE: frame groups on separate streams (same results)

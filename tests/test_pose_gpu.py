@@ -199,6 +199,48 @@ def test_many_hypotheses_1024():
     s.close()
 
 
+@pytest.mark.parametrize("rng_mode", [rs.abi.RS_RNG_DEVICE, rs.abi.RS_RNG_REFERENCE])
+def test_one_hypothesis_per_lane_matches_oracle_and_the_other_solvers(rng_mode):
+    """rs_pose_opts.solver = 3 (pose_wide.cu): every lane runs the LM of one minimal subset; the serial best-so-far / early-stop
+    rule is folded over the records afterwards. Same integers as the oracle and as the warp-per-hypothesis kernels, on
+    frames that use all their hypotheses (30 % outliers: the early stop cannot fire), frames that stop early (10 %), a frame
+    that fails and ragged match counts; with 64, 300 (not a multiple of a chunk or a warp) and 1024 hypotheses."""
+    B = 6
+    truth, cur, matches, n = rs.synth.pose_batch(900, B, M, outlier_frac=0.3)
+    t2, c2, m2, n2 = rs.synth.pose_batch(950, 2, M, outlier_frac=0.1)
+    cur[2:4], matches[2:4], n[2:4] = c2, m2, n2     # two frames whose loop stops after a handful of iterations
+    n[4] = 4                                          # score 0.8 < 1: no RANSAC
+    n[5] = 150                                        # ragged
+    for iters in (64, 300, 1024):
+        s = rs.PoseOptimization(max_batch=B, max_matches=M, max_iterations=1024, max_variance=100)
+        seed = 5 + iters
+        wide = s.options(max_iterations=iters, seed=seed, rng_mode=rng_mode, solver=rs.abi.RS_SOLVER_WIDE)
+        out, mask = s.compute_optimized_pose(cur, matches, n, wide)
+        if rng_mode == rs.abi.RS_RNG_DEVICE:
+            subsets, normals = s.export_random(B, iters, 100)
+        for b in range(B):
+            if rng_mode == rs.abi.RS_RNG_DEVICE:
+                rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], max_iterations=iters, subsets=subsets[b],
+                                            normals=normals[b], max_matches=M)
+            else:
+                rout, rmask = ol.pose_solve(cur[b], matches[b][:n[b]], max_iterations=iters, seed=seed + b)
+            assert_out_match(rout, out[b], rmask, mask[b], n[b], cov_rtol=2e-2 if rng_mode == rs.abi.RS_RNG_REFERENCE else 2e-3)
+        assert out[4]["status"] == 0 and out[0]["status"] == 1
+        assert out[0]["iterations_run"] == iters and out[2]["iterations_run"] < 64
+        for other in (rs.abi.RS_SOLVER_CHAIN, rs.abi.RS_SOLVER_FUSED):
+            o2, m2_ = s.compute_optimized_pose(cur, matches, n, s.options(max_iterations=iters, seed=seed, rng_mode=rng_mode, solver=other))
+            for f in ("status", "n_inliers", "iterations_run", "best_iteration"):
+                assert np.array_equal(o2[f], out[f]), (f, other, iters)
+            assert np.array_equal(m2_, mask)
+        s.close()
+
+
+def test_one_hypothesis_per_lane_needs_its_buffers(solver):
+    truth, cur, matches, n = rs.synth.pose_batch(0, 2, M)
+    with pytest.raises(rs.RsError):   # the module-wide context was created for 119 hypotheses: no per-hypothesis records
+        solver.compute_optimized_pose(cur, matches, n, solver.options(solver=rs.abi.RS_SOLVER_WIDE))
+
+
 def test_batch_size_independent(solver):
     truth, cur, matches, n = rs.synth.pose_batch(500, 8, M)
     opts = solver.options(seed=0, rng_mode=rs.abi.RS_RNG_REFERENCE)
