@@ -167,6 +167,7 @@ int resolve_launch(const rs_pose_ctx* c, const rs_pose_opts* opts, int batch, Po
     if (const char* e = std::getenv("RS_POSE_SPLIT")) prm.split = std::atoi(e);
     if (const char* e = std::getenv("RS_POSE_MC_CAP")) prm.mc_cap = std::atoi(e);       // experiment knobs (tools/exp_pose_timeline.py)
     if (const char* e = std::getenv("RS_POSE_HELP_MIN")) prm.help_min = std::atoi(e);
+    if (const char* e = std::getenv("RS_POSE_MC_BATCHED")) prm.mc_batched = std::atoi(e);
     prm.sub_batches = o.sub_batches < 1 ? 1 : (o.sub_batches > rs_pose_ctx::kMaxGroups ? rs_pose_ctx::kMaxGroups : o.sub_batches);
     if (o.fx == 0 && o.fy == 0 && o.cx == 0 && o.cy == 0)
         prm.K = PoseIntrinsics{550.0, 550.0, 320.0, 240.0};  // Parameters::load_defaut (parameters.cpp:59-74)

@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(RTHREADS, 3) pose_ransac_kernel(const PoseBuff
 // compute_pose_variance's loop body (pose_optimization.cpp:379-412) + compute_random_variation_of_pose (:482-501):
 // grid (ceil(n_variance / warps), B), one warp per Monte-Carlo sample; warps per CTA = blockDim.x / 32 (8 unless the
 // perturbed copies of a very long match list would not fit in shared memory, see launch_pose_variance).
-template <bool P2D>
+// BATCHED: the serial 6x6 parts of the CTA's samples run together on the lanes of warp 0 (lm_minimize_cta).
+template <bool P2D, bool BATCHED>
 __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuffers buf, const PoseLaunch prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -387,11 +388,12 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
     }
     __syncthreads();
     const int sample = blockIdx.x * nwarps + warp;
-    if (sample >= prm.n_variance) return;
+    const bool mine = sample < prm.n_variance;
+    if (!BATCHED && !mine) return;
     double* pmap = s_pmap + size_t(warp) * 4 * M;
     const double* gmap = buf.map + size_t(b) * 4 * M;
     const double* gsig = buf.sigma + size_t(b) * 4 * M;
-    for (int k = lane; k < cnt; k += 32) {
+    for (int k = lane; mine && k < cnt; k += 32) {
         const int i = s_idx[k];
         double g[4];
         if (buf.normals_in) {
@@ -435,8 +437,12 @@ __global__ void __launch_bounds__(THREADS, 2) pose_variance_kernel(const PoseBuf
     double x0[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) x0[j] = st.final_x[j];
-    const bool ok = optimize_pose_warp<P2D>(S, P, prm.K, x0, st.inlier_residuals, st.inlier_score, prm.lm_max_fev, lane);
-    if (lane == 0) {
+    bool ok;
+    if (BATCHED)
+        ok = optimize_pose_cta<P2D>(s_lm, nwarps, P, prm.K, x0, st.inlier_residuals, st.inlier_score, prm.lm_max_fev, warp, lane, mine);
+    else
+        ok = optimize_pose_warp<P2D>(S, P, prm.K, x0, st.inlier_residuals, st.inlier_score, prm.lm_max_fev, lane);
+    if (mine && lane == 0) {
         double v[6] = {0, 0, 0, 0, 0, 0};
         if (ok) pose_vector6(S.x, v);
         double* dst = buf.v6 + (size_t(b) * buf.max_variance + sample) * 6;
@@ -556,14 +562,25 @@ int launch_pose_chain_variance(const PoseBuffers& buf, const PoseLaunch& prm, cu
     const int warps = variance_warps_for(buf.max_matches);
     if (warps == 0) return RS_ERR_INVALID_ARG;
     const size_t smem = variance_smem_bytes(buf.max_matches, warps);
-    static SmemOptIn optin[2];
-    RS_CUDA_CHECK(optin[0].ensure(pose_variance_kernel<false>, smem));
-    RS_CUDA_CHECK(optin[1].ensure(pose_variance_kernel<true>, smem));
+    static SmemOptIn optin[4];
+    RS_CUDA_CHECK(optin[0].ensure(pose_variance_kernel<false, false>, smem));
+    RS_CUDA_CHECK(optin[1].ensure(pose_variance_kernel<true, false>, smem));
+    RS_CUDA_CHECK(optin[2].ensure(pose_variance_kernel<false, true>, smem));
+    RS_CUDA_CHECK(optin[3].ensure(pose_variance_kernel<true, true>, smem));
     const dim3 grid((prm.n_variance + warps - 1) / warps, prm.batch);
-    if (prm.has_point2d)
-        pose_variance_kernel<true><<<grid, warps * 32, smem, stream>>>(buf, prm);
-    else
-        pose_variance_kernel<false><<<grid, warps * 32, smem, stream>>>(buf, prm);
+    const bool batched = prm.mc_batched && warps > 1;
+    if (prm.has_point2d) {
+        if (batched)
+            pose_variance_kernel<true, true><<<grid, warps * 32, smem, stream>>>(buf, prm);
+        else
+            pose_variance_kernel<true, false><<<grid, warps * 32, smem, stream>>>(buf, prm);
+    }
+    else {
+        if (batched)
+            pose_variance_kernel<false, true><<<grid, warps * 32, smem, stream>>>(buf, prm);
+        else
+            pose_variance_kernel<false, false><<<grid, warps * 32, smem, stream>>>(buf, prm);
+    }
     RS_LAUNCH_CHECK();
     pose_covariance_kernel<<<(prm.batch + 3) / 4, 128, 0, stream>>>(buf, prm);
     RS_LAUNCH_CHECK();

@@ -120,6 +120,7 @@ struct PoseLaunch {
     int solver = 0;       // host side: 0 = by shape (the three-launch chain up to 256 hypotheses per frame, the fused kernel beyond),
                           // 1 = chain, 2 = fused kernel (rs_pose_opts.solver)
     int iter0 = 0, iter_count = 0;   // pose_wide.cu: the chunk of RANSAC iterations a launch covers
+    int mc_batched = 1;   // chain Monte-Carlo kernel: serial 6x6 parts of a CTA's samples batched on one warp (lm_minimize_cta)
     int final_only = 0;   // chain RANSAC kernel: skip the hypotheses, run the final optimisation from the HypFold state
     int split = 1;        // host side: frame role and Monte-Carlo role in two launches side by side (0: one launch with both)
     int ctas_per_sm = 0;  // resident CTAs per SM the fused kernel is launched with (<= 0: what fits)

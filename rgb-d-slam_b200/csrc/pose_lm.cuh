@@ -53,6 +53,7 @@ struct WarpLM {
     double dR[27];    // forward-difference derivative of R' along the three rotation coefficients
     double ih[3];     // 1 / h_k of those differences
     double fnorm, par, delta, xnorm, gnorm, pnorm;
+    double ss1;       // |f|^2 at the trial point (hand-over between the warp that evaluates it and the lane that judges it)
     int status, nfev, iter, again;
 };
 
@@ -1032,6 +1033,148 @@ __device__ __forceinline__ bool optimize_pose_warp(WarpLM& S, const Problem& P, 
     if (status <= 0) return false;
     // the reference rejects a pose whose [position, Euler angles] vector has a NaN: that vector is finite exactly
     // when the coefficients and the quaternion built from them are
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ok = ok && isfinite(S.x[j]);
+    return ok && isfinite(S.x[3] * S.x[3] + S.x[4] * S.x[4] + S.x[5] * S.x[5]);
+}
+
+// ---- the same solve for the W warps of a CTA at once, serial parts batched -----------------------------------------------
+// Every warp of the CTA owns one LM problem (the Monte-Carlo kernel: eight samples of one frame); the passes over the
+// features stay warp-wide, but the serial 6x6 parts of ALL the CTA's problems run together on lanes 0..W-1 of warp 0 -
+// one instruction stream for W problems instead of W streams at 1/32 lane utilisation (a third of the instructions the
+// one-warp version issues). The price is a CTA barrier around each serial part, which the other CTA resident on the SM
+// fills. Same arithmetic per problem, bit for bit: only the lane that executes it changes.
+// All threads of the CTA must call; `mine` = this warp has a problem (P, lm[warp].x = start point). Status in lm[warp].status.
+template <bool P2D>
+__device__ __forceinline__ void lm_minimize_cta(WarpLM* lm, const int nwarps, const Problem& P, const PoseIntrinsics& K,
+                                                const int m, const int maxfev, const int warp, const int lane, const bool mine)
+{
+    WarpLM& S = lm[warp];
+    const bool leader = warp == 0 && lane < nwarps;   // lane l of warp 0 runs the serial parts of problem l
+    if (lane == 0) {
+        if (!mine || m < 6 || maxfev <= 0)
+            S.status = 0;   // ImproperInputParameters (or no problem)
+        else {
+            make_xform(S.x, S.T);
+            S.status = kRunning;
+        }
+    }
+    __syncwarp();
+    if (S.status == kRunning) {
+        const double ss = eval_sumsq<P2D>(P, S.T, K, lane);
+        if (lane == 0) {
+            S.fnorm = sqrt(ss);
+            S.par = 0.0, S.delta = 0.0, S.xnorm = 0.0;
+            S.iter = 1, S.nfev = 1;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    while (true) {
+        if (S.status == kRunning) {
+            // ---- Jacobian set-up and pass, as in lm_minimize_warp ----
+            if (lane < 4) {
+                double xx[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) xx[j] = S.x[j];
+                double h = 0.0;
+#pragma unroll
+                for (int j = 3; j < 6; ++j)
+                    if (lane == j - 2) {
+                        h = kSqrtEps * fabs(xx[j]);
+                        if (h == 0.0) h = kSqrtEps;
+                        xx[j] += h;
+                    }
+                Xform Tk;
+                make_xform(xx, Tk);
+                if (lane == 0)
+                    S.T = Tk;
+                else {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) S.Rk[lane - 1][i] = Tk.R[i];
+                    S.ih[lane - 1] = 1.0 / h;
+                }
+            }
+            __syncwarp();
+            if (lane < 27) {
+                const int k = lane / 9, i = lane - 9 * k;
+                S.dR[lane] = (S.Rk[k][i] - S.T.R[i]) * S.ih[k];
+            }
+            __syncwarp();
+            double a[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = 0.0;
+#pragma unroll 1
+            for (int k = lane; k < P.n; k += 32) {
+                int type;
+                double o[4], mm[4];
+                const int gi = load_feature(P, k, type, o, mm);
+                if (P2D && type == RS_FEAT_POINT2D) {
+                    double c[27];
+                    point2d_jacobian(o, mm, P.aux, P.M, gi, S, K, c);
+#pragma unroll
+                    for (int i = 0; i < 27; ++i) a[i] += c[i];
+                }
+                else
+                    feature_jacobian(type, o, mm, S.T, S.dR, K, a);
+            }
+            const double mine_v = reduce_scatter32(a, lane);
+            if (lane < 21) {
+                int i = 0, rem = lane;
+                while (rem >= 6 - i) rem -= 6 - i, ++i;
+                const int j = i + rem;
+                S.A[i * 6 + j] = mine_v;
+                S.A[j * 6 + i] = mine_v;
+            }
+            else if (lane < 27)
+                S.g[lane - 21] = mine_v;
+        }
+        __syncthreads();
+        if (leader) {
+            WarpLM& Q = lm[lane];
+            if (Q.status == kRunning) lm_after_jacobian(Q);
+            Q.again = Q.status == kRunning ? 1 : 0;   // takes part in the trust-region steps below
+        }
+        __syncthreads();
+        // ---- trust-region steps until every problem of the CTA has an acceptable ratio (or has stopped) ----
+#pragma unroll 1
+        while (true) {
+            if (leader && lm[lane].again) lm_propose(lm[lane]);
+            __syncthreads();
+            if (S.again) {
+                const double ss1 = eval_sumsq<P2D>(P, S.T, K, lane);
+                if (lane == 0) S.ss1 = ss1;
+            }
+            __syncthreads();
+            int more = 0;
+            if (leader && lm[lane].again) {
+                lm_judge(lm[lane], lm[lane].ss1, maxfev);
+                more = lm[lane].again;
+            }
+            if (!__syncthreads_or(more)) break;
+        }
+        if (!__syncthreads_or(S.status == kRunning)) break;
+    }
+}
+
+// optimize_pose_warp for the warps of a CTA working on problems of the SAME frame (x0, m and score are the frame's: the
+// guards below take every warp the same way). Success per warp; the optimised coefficients are left in lm[warp].x.
+template <bool P2D>
+__device__ __forceinline__ bool optimize_pose_cta(WarpLM* lm, const int nwarps, const Problem& P, const PoseIntrinsics& K,
+                                                  const double* x0, const int m, const double score, const int maxfev,
+                                                  const int warp, const int lane, const bool mine)
+{
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) finite = finite && isfinite(x0[j]);
+    if (!finite || m <= 1 || score < 1.0) return false;
+    WarpLM& S = lm[warp];
+    if (lane == 0)
+        for (int j = 0; j < 6; ++j) S.x[j] = x0[j];
+    __syncwarp();
+    lm_minimize_cta<P2D>(lm, nwarps, P, K, m, maxfev, warp, lane, mine);
+    if (!mine || S.status <= 0) return false;
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; ++j) ok = ok && isfinite(S.x[j]);

@@ -241,6 +241,32 @@ def test_one_hypothesis_per_lane_needs_its_buffers(solver):
         solver.compute_optimized_pose(cur, matches, n, solver.options(solver=rs.abi.RS_SOLVER_WIDE))
 
 
+@pytest.mark.parametrize("rng_mode", [rs.abi.RS_RNG_DEVICE, rs.abi.RS_RNG_REFERENCE])
+def test_batched_serial_parts_change_nothing(solver, rng_mode, monkeypatch):
+    """The Monte-Carlo kernel runs the 6x6 trust-region algebra of a CTA's eight samples together on the lanes of one warp
+    (lm_minimize_cta); RS_POSE_MC_BATCHED=0 selects the one-warp-per-sample flow. Same arithmetic per sample: the outputs
+    are the same bytes - covariances included - on frames that succeed, fail, and have ragged match counts."""
+    B = 7
+    truth, cur, matches, n = rs.synth.pose_batch(1200, B, M)
+    n[1] = 4
+    n[3] = 97
+    n[5] = 31
+    opts = solver.options(seed=77, rng_mode=rng_mode, solver=rs.abi.RS_SOLVER_CHAIN)
+    monkeypatch.setenv("RS_POSE_MC_BATCHED", "0")
+    want, wmask = solver.compute_optimized_pose(cur, matches, n, opts)
+    monkeypatch.setenv("RS_POSE_MC_BATCHED", "1")
+    got, gmask = solver.compute_optimized_pose(cur, matches, n, opts)
+    assert want.tobytes() == got.tobytes() and wmask.tobytes() == gmask.tobytes()
+    assert (got["status"] == 1).sum() >= 5 and got["n_variance_ok"][0] == 100
+    # an odd sample count leaves warps of the last CTA without a sample
+    o2 = solver.options(seed=78, rng_mode=rng_mode, n_variance=37, solver=rs.abi.RS_SOLVER_CHAIN)
+    monkeypatch.setenv("RS_POSE_MC_BATCHED", "0")
+    want, _ = solver.compute_optimized_pose(cur, matches, n, o2)
+    monkeypatch.setenv("RS_POSE_MC_BATCHED", "1")
+    got, _ = solver.compute_optimized_pose(cur, matches, n, o2)
+    assert want.tobytes() == got.tobytes() and got["n_variance_ok"][0] == 37
+
+
 def test_batch_size_independent(solver):
     truth, cur, matches, n = rs.synth.pose_batch(500, 8, M)
     opts = solver.options(seed=0, rng_mode=rs.abi.RS_RNG_REFERENCE)
