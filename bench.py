@@ -509,6 +509,20 @@ def main():
         det.set_rectification(None, enable=False)
         del d_rect
 
+    # ---- plane matching against the local map (the step between find_primitives and the pose solve) ----
+    plane_match = None
+    if extras:
+        pm = rs.synth.plane_match_problem(11, n_frames=F, n_det=8, n_extra_map=3, max_vertices=32)
+        rs.plane_match(*pm[:-1], det_matched=pm[-1], device=local_rank)   # warm-up
+        t0 = time.perf_counter()
+        for _ in range(3):
+            sel, _inter = rs.plane_match(*pm[:-1], det_matched=pm[-1], device=local_rank)
+        pm_ms = (time.perf_counter() - t0) / 3 * 1e3
+        plane_match = {"ms_per_batch": pm_ms, "frames": F, "map_planes": int(len(pm[4])), "detections": int(len(pm[1])),
+                       "matched": int((sel >= 0).sum()),
+                       "note": "rs_plane_match with host pointers (uploads, kernel and downloads inside): MapPlane::find_matches for "
+                               "every map plane of a %d-frame batch, polygons of 3-32 vertices" % F}
+
     # ---- Kalman update of the matched map features (the step after the pose solve) ----
     kalman = None
     if extras:
@@ -783,6 +797,8 @@ def main():
             line["single_frame"] = single
         if pose_alone is not None:
             line["pose_solve_alone"] = pose_alone
+        if plane_match is not None:
+            line["plane_match"] = plane_match
         if kalman is not None:
             line["kalman_update"] = kalman
         if pipelined is not None:
