@@ -479,7 +479,10 @@ int launch_pose_wide_hypotheses(const PoseBuffers& buf, const PoseLaunch& prm, c
         const int want = (2 * sm_count + prm.batch - 1) / prm.batch;
         const int cap = (lp.iter_count + 2 * HTHREADS - 1) / (2 * HTHREADS);
         // (measured at 64 frames x 1024 hypotheses: 4 CTAs per frame 1.94 ms, 2 / 3 / 8 CTAs 2.13 / 2.08 / 2.19 ms; three CTAs per SM
-        // at 168 registers 2.64 ms - the spills cost more than the extra warps hide)
+        // at 168 registers 2.64 ms - the spills cost more than the extra warps hide. Also tried: parking a solve that is still
+        // running after 8 .. 28 LM iterations (its persistent MINPACK state to global memory) and finishing the parked ones in a
+        // second pass, one per lane - 2.01 .. 2.25 ms against 1.91 .. 1.97: what a lock-step tick costs is the divergence INSIDE
+        // it (lmpar's Newton loop runs at 6 of 32 lanes, plane features at 2), not the tail of long solves)
         const int ctas = std::max(1, std::min(want, cap));
         pose_hypotheses_kernel<<<dim3(ctas, prm.batch), HTHREADS, smem, stream>>>(buf, lp);
         RS_LAUNCH_CHECK();

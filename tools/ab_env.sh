@@ -1,7 +1,7 @@
-# A/B on the GPU box: tools/ab_env.sh <out dir> <ENV_NAME> <values...>  - runs the default bench (device-timed legs only) per value, twice
-OUT=gpurun_out/$1; VAR=$2; shift 2
+# A/B on the GPU box: tools/ab_env.sh <out dir> <ENV_NAME> "<bench args>" <values...>  - device-timed legs only, per value, twice
+OUT=gpurun_out/$1; VAR=$2; ARGS=$3; shift 3
 mkdir -p $OUT
-B="python bench.py --no-e2e --no-cpu-baseline --no-extras --no-config5"
+B="python bench.py --no-e2e --no-cpu-baseline --no-extras --no-config5 $ARGS"
 for i in 1 2; do for v in "$@"; do env $VAR=$v $B > $OUT/bench_${VAR}_${v}_$i.json 2>> $OUT/err.txt; done; done
 python - $OUT <<'PY'
 import json,glob,sys
