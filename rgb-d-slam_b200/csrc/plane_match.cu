@@ -227,14 +227,48 @@ __global__ void __launch_bounds__(WARPS * 32) polygon_inter_area_kernel(const in
     if (lane == 0) area[p] = v;
 }
 
+// Device scratch of one call, from the device's stream-ordered memory pool (cudaMallocAsync): after the first call of a process
+// the pool hands the same blocks back without touching the driver (a cudaMalloc / cudaFree pair per array cost 100 ms per
+// call beside a process's other allocations - cudaFree synchronises the whole device).
+struct CallStream {
+    cudaStream_t s = nullptr;
+    ~CallStream()
+    {
+        if (s) cudaStreamDestroy(s);
+    }
+    int open(const int device)
+    {
+        static std::mutex m;
+        static bool pool_kept[64] = {};
+        RS_CUDA_CHECK(cudaSetDevice(device));
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (!pool_kept[device & 63]) {
+                cudaMemPool_t pool;
+                RS_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+                uint64_t keep = UINT64_MAX;   // freed blocks stay in the pool for the next call
+                RS_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+                pool_kept[device & 63] = true;
+            }
+        }
+        RS_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        return RS_OK;
+    }
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    int upload(const T* host, size_t n)
+    cudaStream_t s = nullptr;
+    ~DevBuf()
     {
-        RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * (n ? n : 1)));
-        if (n && host) RS_CUDA_CHECK(cudaMemcpy(p, host, sizeof(T) * n, cudaMemcpyHostToDevice));
+        if (p) cudaFreeAsync(p, s);
+    }
+    int upload(const T* host, size_t n, cudaStream_t stream)
+    {
+        s = stream;
+        RS_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(T) * (n ? n : 1), s));
+        if (n && host) RS_CUDA_CHECK(cudaMemcpyAsync(p, host, sizeof(T) * n, cudaMemcpyHostToDevice, s));
         return RS_OK;
     }
 };
@@ -283,28 +317,31 @@ int rs_plane_match(int device, int n_frames, const double* world_to_camera, cons
         }
         map_vertices = std::max(map_vertices, size_t(map[m].first_vertex) + map[m].n_vertices);
     }
+    CallStream cs;   // declared first: destroyed after the buffers below have queued their frees on it
+    if ((rc = cs.open(device))) return rc;
     DevBuf<double> d_T, d_dxy, d_mxy, d_inter;
     DevBuf<rs_polygon_plane> d_det, d_map;
     DevBuf<int32_t> d_df, d_mf, d_sel;
     DevBuf<uint8_t> d_matched;
-    if ((rc = d_T.upload(world_to_camera, size_t(n_frames) * 16))) return rc;
-    if ((rc = d_det.upload(det, n_det))) return rc;
-    if ((rc = d_map.upload(map, n_map))) return rc;
-    if ((rc = d_df.upload(det_first, size_t(n_frames) + 1))) return rc;
-    if ((rc = d_mf.upload(map_frame.data(), n_map))) return rc;
-    if ((rc = d_dxy.upload(det_xy, 2 * det_vertices))) return rc;
-    if ((rc = d_mxy.upload(map_xy, 2 * map_vertices))) return rc;
-    if (det_matched && (rc = d_matched.upload(det_matched, n_det))) return rc;
-    if ((rc = d_sel.upload(nullptr, n_map))) return rc;
-    if ((rc = d_inter.upload(nullptr, n_map))) return rc;
+    if ((rc = d_T.upload(world_to_camera, size_t(n_frames) * 16, cs.s))) return rc;
+    if ((rc = d_det.upload(det, n_det, cs.s))) return rc;
+    if ((rc = d_map.upload(map, n_map, cs.s))) return rc;
+    if ((rc = d_df.upload(det_first, size_t(n_frames) + 1, cs.s))) return rc;
+    if ((rc = d_mf.upload(map_frame.data(), n_map, cs.s))) return rc;
+    if ((rc = d_dxy.upload(det_xy, 2 * det_vertices, cs.s))) return rc;
+    if ((rc = d_mxy.upload(map_xy, 2 * map_vertices, cs.s))) return rc;
+    if (det_matched && (rc = d_matched.upload(det_matched, n_det, cs.s))) return rc;
+    if ((rc = d_sel.upload(nullptr, n_map, cs.s))) return rc;
+    if ((rc = d_inter.upload(nullptr, n_map, cs.s))) return rc;
     MatchArgs g;
     g.n_frames = n_frames, g.w2c = d_T.p, g.det = d_det.p, g.det_first = d_df.p, g.det_xy = d_dxy.p, g.map = d_map.p;
     g.map_first = nullptr, g.map_xy = d_mxy.p, g.det_matched = det_matched ? d_matched.p : nullptr, g.map_frame = d_mf.p;
     g.n_map = n_map, g.advanced = advanced_search, g.selected = d_sel.p, g.inter = d_inter.p;
-    plane_match_kernel<<<(n_map + WARPS - 1) / WARPS, WARPS * 32>>>(g);
+    plane_match_kernel<<<(n_map + WARPS - 1) / WARPS, WARPS * 32, 0, cs.s>>>(g);
     RS_LAUNCH_CHECK();
-    RS_CUDA_CHECK(cudaMemcpy(selected, d_sel.p, sizeof(int32_t) * n_map, cudaMemcpyDeviceToHost));
-    RS_CUDA_CHECK(cudaMemcpy(inter_area, d_inter.p, sizeof(double) * n_map, cudaMemcpyDeviceToHost));
+    RS_CUDA_CHECK(cudaMemcpyAsync(selected, d_sel.p, sizeof(int32_t) * n_map, cudaMemcpyDeviceToHost, cs.s));
+    RS_CUDA_CHECK(cudaMemcpyAsync(inter_area, d_inter.p, sizeof(double) * n_map, cudaMemcpyDeviceToHost, cs.s));
+    RS_CUDA_CHECK(cudaStreamSynchronize(cs.s));
     return RS_OK;
 }
 
@@ -318,16 +355,19 @@ int rs_polygon_inter_area(int device, int n_pairs, const double* a_xy, const int
         return RS_ERR_INVALID_ARG;
     }
     if (n_pairs == 0) return RS_OK;
+    CallStream cs;
+    if ((rc = cs.open(device))) return rc;
     DevBuf<double> d_a, d_b, d_area;
     DevBuf<int32_t> d_af, d_bf;
-    if ((rc = d_a.upload(a_xy, 2 * size_t(a_first[n_pairs])))) return rc;
-    if ((rc = d_b.upload(b_xy, 2 * size_t(b_first[n_pairs])))) return rc;
-    if ((rc = d_af.upload(a_first, size_t(n_pairs) + 1))) return rc;
-    if ((rc = d_bf.upload(b_first, size_t(n_pairs) + 1))) return rc;
-    if ((rc = d_area.upload(nullptr, n_pairs))) return rc;
-    polygon_inter_area_kernel<<<(n_pairs + WARPS - 1) / WARPS, WARPS * 32>>>(n_pairs, d_a.p, d_af.p, d_b.p, d_bf.p, d_area.p);
+    if ((rc = d_a.upload(a_xy, 2 * size_t(a_first[n_pairs]), cs.s))) return rc;
+    if ((rc = d_b.upload(b_xy, 2 * size_t(b_first[n_pairs]), cs.s))) return rc;
+    if ((rc = d_af.upload(a_first, size_t(n_pairs) + 1, cs.s))) return rc;
+    if ((rc = d_bf.upload(b_first, size_t(n_pairs) + 1, cs.s))) return rc;
+    if ((rc = d_area.upload(nullptr, n_pairs, cs.s))) return rc;
+    polygon_inter_area_kernel<<<(n_pairs + WARPS - 1) / WARPS, WARPS * 32, 0, cs.s>>>(n_pairs, d_a.p, d_af.p, d_b.p, d_bf.p, d_area.p);
     RS_LAUNCH_CHECK();
-    RS_CUDA_CHECK(cudaMemcpy(area, d_area.p, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost));
+    RS_CUDA_CHECK(cudaMemcpyAsync(area, d_area.p, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, cs.s));
+    RS_CUDA_CHECK(cudaStreamSynchronize(cs.s));
     return RS_OK;
 }
 
