@@ -293,6 +293,11 @@ int rs_plane_match(int device, int n_frames, const double* world_to_camera, cons
         set_last_error("rs_plane_match: invalid argument");
         return RS_ERR_INVALID_ARG;
     }
+    for (int f = 0; f < n_frames; ++f)
+        if (det_first[f] < 0 || map_first[f] < 0 || det_first[f + 1] < det_first[f] || map_first[f + 1] < map_first[f]) {
+            set_last_error("rs_plane_match: det_first / map_first must be non-decreasing offsets starting at or above 0");
+            return RS_ERR_INVALID_ARG;
+        }
     const int n_det = det_first[n_frames], n_map = map_first[n_frames];
     if (n_map == 0) return RS_OK;
     if ((n_det && (!det || !det_xy)) || !map || !map_xy) {
@@ -355,6 +360,11 @@ int rs_polygon_inter_area(int device, int n_pairs, const double* a_xy, const int
         return RS_ERR_INVALID_ARG;
     }
     if (n_pairs == 0) return RS_OK;
+    for (int p = 0; p < n_pairs; ++p)
+        if (a_first[p] < 0 || b_first[p] < 0 || a_first[p + 1] < a_first[p] || b_first[p + 1] < b_first[p]) {
+            set_last_error("rs_polygon_inter_area: a_first / b_first must be non-decreasing offsets");
+            return RS_ERR_INVALID_ARG;
+        }
     CallStream cs;
     if ((rc = cs.open(device))) return rc;
     DevBuf<double> d_a, d_b, d_area;

@@ -63,3 +63,7 @@ def test_plane_match_rejects_oversized_map_polygon():
     args[4]["n_vertices"][0] = 300
     with pytest.raises(rs.RsError):
         rs.plane_match(*args[:-1])
+    args = list(rs.synth.plane_match_problem(1, n_frames=2))
+    args[2] = np.array([0, 5, 3], np.int32)     # offsets that go backwards
+    with pytest.raises((rs.RsError, ValueError)):
+        rs.plane_match(*args[:-1])
