@@ -4,7 +4,7 @@
 //
 // NOT compiled in this repository: it needs the reference's own headers (Eigen, OpenCV, boost), which are not
 // available here. It is written against the reference at 183011f; every call names the member it replaces.
-// Required reference-side patch (3 small changes):
+// Required reference-side patches (five small changes; the first three:)
 //   1. Plane_Segment: public ctor `Plane_Segment(uint pointCount, const double sums[9])` that fills _pointCount and
 //      _Sx.._Szx and calls fit_plane()   (members are private: plane_segment.hpp:118-140)
 //   2. PointOptimizationFeature / PlaneOptimizationFeature / Point2dOptimizationFeature: `friend struct rs_adaptor::Flatten;`
@@ -255,5 +255,68 @@ inline bool compute_optimized_pose(rs_pose_ctx* ctx,
     optimizedPose.set_position_variance(cov);
     return true;
 }
+
+// ---- plane matching: the loop over the local map's planes that calls MapPlane::find_matches (map_primitive.cpp:91-161) -----
+// One rs_plane_match call for the whole local map of the frame instead of one find_matches per map plane. Needs patch 5
+// (INTEGRATION.md): `friend struct rs_adaptor::PlaneMatcher;` in utils::Polygon (the boost ring `_polygon` is protected,
+// polygon.hpp:198-199) - the public get_unprojected_boundary() would round-trip the ring through 3-D and back.
+struct PlaneMatcher
+{
+    // (n, d), the polygon's frame and its outer ring, as rs_polygon_plane + (x, y) pairs appended to `xy`
+    static void flatten(const vector4& parametrization, const utils::Polygon& polygon, rs_polygon_plane& out, std::vector<double>& xy)
+    {
+        for (int i = 0; i < 3; ++i)
+        {
+            out.normal[i] = parametrization(i);
+            out.center[i] = polygon.get_center()(i);
+            out.x_axis[i] = polygon.get_x_axis()(i);
+            out.y_axis[i] = polygon.get_y_axis()(i);
+        }
+        out.d = parametrization(3);
+        out.first_vertex = int32_t(xy.size() / 2);
+        const auto& ring = polygon._polygon.outer();   // closed ring (first == last), clockwise after boost::geometry::correct
+        out.n_vertices = int32_t(ring.size());
+        for (const auto& p: ring)
+        {
+            xy.push_back(p.x());
+            xy.push_back(p.y());
+        }
+    }
+
+    // selected[m] = index in `detectedPlanes` matched by mapPlanes[m], or -1: exactly what find_matches leaves in
+    // matchIndexes for each map plane when it is called with the same isDetectedFeatureMatched (the caller's loop marks a
+    // detection as matched between two map planes; to keep that sequential rule, call this again for the map planes that
+    // selected an already-taken detection - or pass one map plane at a time, which is the reference's order of work).
+    static std::vector<int> find_matches(const map_management::DetectedPlaneObject& detectedPlanes,
+                                         const std::vector<const map_management::MapPlane*>& mapPlanes,
+                                         const WorldToCameraMatrix& worldToCamera,
+                                         const vectorb& isDetectedFeatureMatched,
+                                         const bool useAdvancedSearch)
+    {
+        std::vector<rs_polygon_plane> det(detectedPlanes.size()), map(mapPlanes.size());
+        std::vector<double> detXY, mapXY;
+        std::vector<uint8_t> matched(detectedPlanes.size());
+        for (size_t k = 0; k < detectedPlanes.size(); ++k)
+        {
+            flatten(detectedPlanes[k].get_parametrization().get_parametrization(), detectedPlanes[k].get_boundary_polygon(), det[k], detXY);
+            matched[k] = isDetectedFeatureMatched[long(k)] ? 1 : 0;
+        }
+        for (size_t m = 0; m < mapPlanes.size(); ++m)
+            flatten(mapPlanes[m]->get_parametrization().get_parametrization(), mapPlanes[m]->get_boundary_polygon(), map[m], mapXY);
+        double w2c[16];
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) w2c[4 * r + c] = worldToCamera(r, c);   // Eigen stores column-major
+        const int32_t detFirst[2] = {0, int32_t(det.size())}, mapFirst[2] = {0, int32_t(map.size())};
+        std::vector<int32_t> selected(map.size(), -1);
+        std::vector<double> interArea(map.size(), 0.0);
+        if (rs_plane_match(/*device*/ 0, 1, w2c, det.data(), detFirst, detXY.data(), map.data(), mapFirst, mapXY.data(),
+                           matched.data(), useAdvancedSearch ? 1 : 0, selected.data(), interArea.data()) != RS_OK)
+        {
+            outputs::log_error(std::string("rs_plane_match failed: ") + rs_last_error());
+            return std::vector<int>(map.size(), -1);
+        }
+        return std::vector<int>(selected.begin(), selected.end());
+    }
+};
 
 }  // namespace rgbd_slam::rs_adaptor
