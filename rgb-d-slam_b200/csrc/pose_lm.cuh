@@ -390,8 +390,15 @@ __device__ __noinline__ void point2d_jacobian(const double (&o)[4], const double
     }
 }
 
+// dR' entry i of rotation coefficient k, wherever the caller keeps the 27 of them (an array; per-lane strided shared memory)
+struct DRArray {
+    const double* p;
+    __device__ __forceinline__ double at(const int k, const int i) const { return p[9 * k + i]; }
+};
+
+template <class DR>
 __device__ __forceinline__ void feature_jacobian(const int type, const double (&o)[4], const double (&m)[4], const Xform& T,
-                                                 const double* __restrict__ dR, const PoseIntrinsics& K, double (&a)[32])
+                                                 const DR& dR, const PoseIntrinsics& K, double (&a)[32])
 {
     if (type == RS_FEAT_POINT) {
         const double d0 = m[0] - T.t[0], d1 = m[1] - T.t[1], d2 = m[2] - T.t[2];
@@ -413,10 +420,9 @@ __device__ __forceinline__ void feature_jacobian(const int type, const double (&
         J0[2] = -(A0 * T.R[0] + B0 * T.R[2]), J1[2] = -(A1 * T.R[1] + B1 * T.R[2]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double* D = dR + 9 * k;
-            const double dx = (D[0] * d0 + D[3] * d1) + D[6] * d2;
-            const double dy = (D[1] * d0 + D[4] * d1) + D[7] * d2;
-            const double dz = (D[2] * d0 + D[5] * d1) + D[8] * d2;
+            const double dx = (dR.at(k, 0) * d0 + dR.at(k, 3) * d1) + dR.at(k, 6) * d2;
+            const double dy = (dR.at(k, 1) * d0 + dR.at(k, 4) * d1) + dR.at(k, 7) * d2;
+            const double dz = (dR.at(k, 2) * d0 + dR.at(k, 5) * d1) + dR.at(k, 8) * d2;
             J0[3 + k] = A0 * dx + B0 * dz;
             J1[3 + k] = A1 * dy + B1 * dz;
         }
@@ -446,10 +452,9 @@ __device__ __forceinline__ void feature_jacobian(const int type, const double (&
     const double f = -dp * is * third;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double* D = dR + 9 * k;
-        const double w0 = (D[0] * m[0] + D[3] * m[1]) + D[6] * m[2];
-        const double w1 = (D[1] * m[0] + D[4] * m[1]) + D[7] * m[2];
-        const double w2 = (D[2] * m[0] + D[5] * m[1]) + D[8] * m[2];
+        const double w0 = (dR.at(k, 0) * m[0] + dR.at(k, 3) * m[1]) + dR.at(k, 6) * m[2];
+        const double w1 = (dR.at(k, 1) * m[0] + dR.at(k, 4) * m[1]) + dR.at(k, 7) * m[2];
+        const double w2 = (dR.at(k, 2) * m[0] + dR.at(k, 5) * m[1]) + dR.at(k, 8) * m[2];
         const double along = (np[0] * w0 + np[1] * w1) + np[2] * w2;  // removed by the renormalisation
         J[0][3 + k] = f * (w0 - along * np[0]);
         J[1][3 + k] = f * (w1 - along * np[1]);
@@ -980,7 +985,7 @@ __device__ __forceinline__ int lm_minimize_warp(WarpLM& S, const Problem& P, con
                 for (int i = 0; i < 27; ++i) a[i] += c[i];
             }
             else
-                feature_jacobian(type, o, mm, S.T, S.dR, K, a);
+                feature_jacobian(type, o, mm, S.T, DRArray{S.dR}, K, a);
         }
         const double mine = reduce_scatter32(a, lane);
         if (lane < 21) {
@@ -1117,7 +1122,7 @@ __device__ __forceinline__ void lm_minimize_cta(WarpLM* lm, const int nwarps, co
                     for (int i = 0; i < 27; ++i) a[i] += c[i];
                 }
                 else
-                    feature_jacobian(type, o, mm, S.T, S.dR, K, a);
+                    feature_jacobian(type, o, mm, S.T, DRArray{S.dR}, K, a);
             }
             const double mine_v = reduce_scatter32(a, lane);
             if (lane < 21) {

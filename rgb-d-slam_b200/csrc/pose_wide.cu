@@ -18,7 +18,7 @@
 // iterations so that frames whose loop has stopped early cost nothing in the following chunks. The final optimisation on
 // the winning inlier set and the Monte-Carlo solves are the chain's (pose_chain.cu: pose_ransac_kernel in its final-only
 // mode, pose_variance_kernel).
-#include "pose_lm.cuh"
+#include "pose_lm_lane.cuh"
 
 namespace rs {
 
@@ -28,109 +28,24 @@ constexpr int HTHREADS = 128;   // lanes = concurrent hypotheses per CTA
 constexpr int HWARPS = HTHREADS / 32;
 constexpr int HQUEUE = 64;      // finished poses a warp may hold before it must test them (>= 32 + the 32 that may end at once)
 
-// The LM state of one lane (registers / local memory): the members lm_after_jacobian / lm_propose / lm_judge / lmpar use.
-struct LaneLM {
-    double x[6], xt[6], diag[6], p[6], wa2[6], sc[6], g[6], xs[6];
-    double A[36];
-    double C[21];
-    Xform T;
-    double fnorm, par, delta, xnorm, gnorm, pnorm;
-    int status, nfev, iter, again;
-};
-
-struct LaneSubset {
-    const short* idx;   // the lane's subset in shared memory
+// The features of a lane's hypothesis: its minimal subset (indices in shared memory) of the frame's match list
+struct SubsetSource {
+    const short* idx;
     int n;
-};
-
-// |f(x)|^2 over the lane's subset
-__device__ __forceinline__ double lane_sumsq(const Problem& P, const LaneSubset& sub, const Xform& T, const PoseIntrinsics& K)
-{
-    double ss = 0.0;
-    for (int k = 0; k < sub.n; ++k) {
-        const int i = sub.idx[k];
-        const int type = P.type[i];
-        double o[4], m[4], r[3];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[c] = P.obs[c * P.M + i], m[c] = P.map[c * P.M + i];
-        feature_residual<false>(type, o, m, T, K, r, nullptr, P.M, i);
-        ss += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    }
-    return ss;
-}
-
-// LevenbergMarquardt::minimizeInit + the first residual evaluation
-__device__ __forceinline__ void lane_lm_begin(LaneLM& S, const Problem& P, const LaneSubset& sub, const PoseIntrinsics& K,
-                                              const double* x0, const int m, const int maxfev)
-{
-#pragma unroll
-    for (int j = 0; j < 6; ++j) S.x[j] = x0[j];
-    if (m < 6 || maxfev <= 0) {
-        S.status = 0;   // ImproperInputParameters
-        return;
-    }
-    make_xform(S.x, S.T);
-    S.fnorm = sqrt(lane_sumsq(P, sub, S.T, K));
-    S.par = 0.0, S.delta = 0.0, S.xnorm = 0.0;
-    S.iter = 1, S.nfev = 1, S.status = kRunning;
-}
-
-// One outer iteration of minimizeOneStep: Jacobian (forward differences of the transform, chain rule per feature, as the
-// warp-wide LM does), then trust-region steps until one is accepted or the solve stops.
-__device__ __forceinline__ void lane_lm_step(LaneLM& S, const Problem& P, const LaneSubset& sub, const PoseIntrinsics& K,
-                                             const int maxfev)
-{
-    double dR[27];
-    make_xform(S.x, S.T);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double xx[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) xx[j] = S.x[j];
-        double h = kSqrtEps * fabs(xx[3 + k]);   // NumericalDiff: h = sqrt(eps) |x_j|, or sqrt(eps) when x_j == 0
-        if (h == 0.0) h = kSqrtEps;
-        xx[3 + k] += h;
-        Xform Tk;
-        make_xform(xx, Tk);
-        const double ih = 1.0 / h;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) dR[9 * k + i] = (Tk.R[i] - S.T.R[i]) * ih;
-    }
-    double a[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] = 0.0;
-#pragma unroll 1
-    for (int k = 0; k < sub.n; ++k) {
-        const int i = sub.idx[k];
-        const int type = P.type[i];
-        double o[4], mm[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[c] = P.obs[c * P.M + i], mm[c] = P.map[c * P.M + i];
-        feature_jacobian(type, o, mm, S.T, dR, K, a);
-    }
+    const int32_t* type;
+    const double* obs;
+    const double* map;
+    int M;
+    __device__ __forceinline__ int count() const { return n; }
+    __device__ __forceinline__ int load(const int k, int& ty, double o[4], double m[4]) const
     {
-        int t = 0;
+        const int i = idx[k];
+        ty = type[i];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            S.g[i] = a[21 + i];
-#pragma unroll
-            for (int j = i; j < 6; ++j) {
-                S.A[i * 6 + j] = a[t];
-                S.A[j * 6 + i] = a[t];
-                ++t;
-            }
-        }
+        for (int c = 0; c < 4; ++c) o[c] = obs[c * M + i], m[c] = map[c * M + i];
+        return i;
     }
-    lm_after_jacobian(S);
-    if (S.status != kRunning) return;
-#pragma unroll 1
-    while (true) {
-        lm_propose(S);
-        const double ss1 = lane_sumsq(P, sub, S.T, K);
-        lm_judge(S, ss1, maxfev);
-        if (S.status != kRunning || !S.again) break;
-    }
-}
+};
 
 struct WideSmem {
     int32_t* type;
@@ -217,9 +132,10 @@ __global__ void __launch_bounds__(HTHREADS, 2) pose_hypotheses_kernel(const Pose
 
     double x0[6];
     coefficients_from_pose(buf.cur_pose + b * 7, x0);
-    Problem P;
-    P.type = sm.type, P.obs = sm.obs, P.map = sm.map, P.M = M, P.idx = nullptr, P.aux = nullptr, P.n = 0;
     short* my_subset = sm.subset + threadIdx.x * RS_MAX_SUBSET;
+    SubsetSource sub;
+    sub.idx = my_subset, sub.n = 0, sub.type = sm.type, sub.obs = sm.obs, sub.map = sm.map, sub.M = M;
+    DRLocal dR;
     double* q_x = sm.q_x + size_t(warp) * HQUEUE * 6;
     int* q_it = sm.q_it + warp * HQUEUE;
     unsigned* q_mask = sm.q_mask + size_t(warp) * 32 * words;
@@ -289,8 +205,6 @@ __global__ void __launch_bounds__(HTHREADS, 2) pose_hypotheses_kernel(const Pose
     };
 
     LaneLM S;
-    LaneSubset sub;
-    sub.idx = my_subset, sub.n = 0;
     S.status = 0;
     bool active = false, exhausted = false;
     int it = -1;
@@ -339,7 +253,7 @@ __global__ void __launch_bounds__(HTHREADS, 2) pose_hypotheses_kernel(const Pose
                 for (int j = 0; j < 6; ++j) finite = finite && isfinite(x0[j]);
                 // compute_optimized_global_pose's guards (pose_optimization.cpp:302-321)
                 if (cumulated >= 1.0 && finite && m > 1) {
-                    lane_lm_begin(S, P, sub, prm.K, x0, m, prm.lm_max_fev);
+                    lane_lm_begin(S, sub, prm.K, x0, m, prm.lm_max_fev);
                     active = true;   // a solve that stopped inside begin is retired below
                 }
                 else {
@@ -353,7 +267,7 @@ __global__ void __launch_bounds__(HTHREADS, 2) pose_hypotheses_kernel(const Pose
             continue;
         }
         // ---- one LM iteration for every lane that has a solve running ----
-        if (active && S.status == kRunning) lane_lm_step(S, P, sub, prm.K, prm.lm_max_fev);
+        if (active && S.status == kRunning) lane_lm_step(S, sub, dR, prm.K, prm.lm_max_fev);
         // ---- retire finished solves ----
         if (active && S.status != kRunning) {
             active = false;
