@@ -372,12 +372,16 @@ typedef struct rs_polygon_plane {
 
 /* Frame f owns detections [det_first[f], det_first[f+1]) and map planes [map_first[f], map_first[f+1]) (batched sequences:
  * every frame has its own local map). world_to_camera: n_frames row-major 4x4. det_matched (may be NULL): per detection, the
- * reference's isDetectedFeatureMatched. Outputs per map plane: selected = index of the detection INSIDE its frame's list or
- * -1, inter_area = the winning intersection area (0 if none). Host pointers; runs on `device`. */
+ * reference's isDetectedFeatureMatched when the call is made. Outputs per map plane: selected = index of the detection INSIDE
+ * its frame's list or -1, inter_area = the winning intersection area (0 if none).
+ * sequential != 0 reproduces the caller's loop as well (Feature_Map::get_matches, feature_map.hpp:652-669): the map planes of
+ * a frame are served in list order and a detection taken by one is marked matched for those after it; det_matched_out (may be
+ * NULL; per detection) returns the mask as the loop leaves it. sequential == 0: every map plane is matched against the mask as
+ * given (what a single find_matches call sees). Host pointers; runs on `device`. */
 int rs_plane_match(int device, int n_frames, const double* world_to_camera, const rs_polygon_plane* det,
                    const int32_t* det_first, const double* det_xy, const rs_polygon_plane* map, const int32_t* map_first,
-                   const double* map_xy, const uint8_t* det_matched, int advanced_search, int32_t* selected,
-                   double* inter_area);
+                   const double* map_xy, const uint8_t* det_matched, int advanced_search, int sequential, int32_t* selected,
+                   double* inter_area, uint8_t* det_matched_out);
 /* The intersection area alone, for n_pairs polygon pairs given in a common 2-D frame (a = ring a_first[i]..a_first[i+1] of
  * a_xy, same for b): what Polygon::inter_area returns once `other` has been projected. */
 int rs_polygon_inter_area(int device, int n_pairs, const double* a_xy, const int32_t* a_first, const double* b_xy,

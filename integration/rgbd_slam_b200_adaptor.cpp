@@ -283,10 +283,8 @@ struct PlaneMatcher
         }
     }
 
-    // selected[m] = index in `detectedPlanes` matched by mapPlanes[m], or -1: exactly what find_matches leaves in
-    // matchIndexes for each map plane when it is called with the same isDetectedFeatureMatched (the caller's loop marks a
-    // detection as matched between two map planes; to keep that sequential rule, call this again for the map planes that
-    // selected an already-taken detection - or pass one map plane at a time, which is the reference's order of work).
+    // selected[m] = index in `detectedPlanes` matched by mapPlanes[m], or -1: what the loop over the map's planes leaves in
+    // each plane's matchIndexes (find_matches per plane, isDetectedFeatureMatched updated between two planes).
     static std::vector<int> find_matches(const map_management::DetectedPlaneObject& detectedPlanes,
                                          const std::vector<const map_management::MapPlane*>& mapPlanes,
                                          const WorldToCameraMatrix& worldToCamera,
@@ -309,8 +307,11 @@ struct PlaneMatcher
         const int32_t detFirst[2] = {0, int32_t(det.size())}, mapFirst[2] = {0, int32_t(map.size())};
         std::vector<int32_t> selected(map.size(), -1);
         std::vector<double> interArea(map.size(), 0.0);
+        // sequential = 1: the map planes are served in the order given and a detection taken by one is marked matched for the
+        // next, as the loop of Feature_Map::get_matches does (feature_map.hpp:652-669); `matched` returns the updated mask
         if (rs_plane_match(/*device*/ 0, 1, w2c, det.data(), detFirst, detXY.data(), map.data(), mapFirst, mapXY.data(),
-                           matched.data(), useAdvancedSearch ? 1 : 0, selected.data(), interArea.data()) != RS_OK)
+                           matched.data(), useAdvancedSearch ? 1 : 0, /*sequential*/ 1, selected.data(), interArea.data(),
+                           matched.data()) != RS_OK)
         {
             outputs::log_error(std::string("rs_plane_match failed: ") + rs_last_error());
             return std::vector<int>(map.size(), -1);

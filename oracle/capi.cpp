@@ -79,12 +79,13 @@ double orc_polygon_area(const double* a, int n) { return polygon_area(a, n); }
 // batched like rs_plane_match: frame f owns detections [det_first[f], det_first[f+1]) and map planes [map_first[f], map_first[f+1])
 int orc_plane_match(int n_frames, const double* w2c, const rs_polygon_plane* det, const int32_t* det_first, const double* det_xy,
                     const rs_polygon_plane* map, const int32_t* map_first, const double* map_xy, const uint8_t* det_matched,
-                    int advanced_search, int32_t* selected, double* inter)
+                    int advanced_search, int sequential, int32_t* selected, double* inter, uint8_t* matched_out)
 {
     for (int f = 0; f < n_frames; ++f) {
         const int d0 = det_first[f], m0 = map_first[f];
         plane_match_frame(w2c + 16 * size_t(f), det + d0, det_first[f + 1] - d0, det_xy, map + m0, map_first[f + 1] - m0, map_xy,
-                          det_matched ? det_matched + d0 : nullptr, advanced_search, selected + m0, inter + m0);
+                          det_matched ? det_matched + d0 : nullptr, advanced_search, sequential, selected + m0, inter + m0,
+                          matched_out ? matched_out + d0 : nullptr);
     }
     return 0;
 }

@@ -105,9 +105,12 @@ inline V3 xform(const double* T, V3 p) { return rot(T, p) + V3{T[3], T[7], T[11]
 }  // namespace
 
 void plane_match_frame(const double* w2c, const rs_polygon_plane* det, int n_det, const double* det_xy, const rs_polygon_plane* map,
-                       int n_map, const double* map_xy, const unsigned char* det_matched, int advanced_search, int* selected,
-                       double* inter)
+                       int n_map, const double* map_xy, const unsigned char* det_matched, int advanced_search, int sequential,
+                       int* selected, double* inter, unsigned char* matched_out)
 {
+    // _isDetectedFeatureMatched as the caller's loop carries it (feature_map.hpp:652-669)
+    std::vector<unsigned char> matched(size_t(n_det), 0);
+    for (int k = 0; k < n_det; ++k) matched[k] = det_matched ? det_matched[k] : 0;
     const double minimumNormalDotDiff = std::fabs(std::cos(20.0 * M_PI / 180.0));   // maximumAngleForPlaneMatch_d
     const double maximumPlaneMatchDistance = 100.0;                                 // maximumDistanceForPlaneMatch_mm
     const double planeMinimalOverlap = static_cast<double>(0.4f);                   // minimumPlaneOverlapToConsiderMatch (float)
@@ -134,7 +137,7 @@ void plane_match_frame(const double* w2c, const rs_polygon_plane* det, int n_det
         double greatest = 0.0;
         int sel = -1;
         for (int k = 0; k < n_det; ++k) {
-            if (det_matched && det_matched[k]) continue;
+            if (matched[k]) continue;
             const rs_polygon_plane& dp = det[k];
             if (!(std::fabs(dp.d - dc) < maximumPlaneMatchDistance)) continue;
             if (!(std::fabs(dot(v3(dp.normal), nc)) > minimumNormalDotDiff)) continue;
@@ -152,7 +155,10 @@ void plane_match_frame(const double* w2c, const rs_polygon_plane* det, int n_det
         }
         if (sel <= 0) continue;   // sic (map_primitive.cpp:146): detection 0 can never be matched
         selected[m] = sel, inter[m] = greatest;
+        if (sequential) matched[sel] = 1;   // feature_map.hpp:666-667
     }
+    if (matched_out)
+        for (int k = 0; k < n_det; ++k) matched_out[k] = matched[k];
 }
 
 }  // namespace oracle

@@ -18,8 +18,10 @@ double polygon_area(const double* a, int n);
 
 // One find_matches call per map plane of one frame. w2c: row-major 4x4 world-to-camera. selected[m] = index of the matched
 // detected plane inside the frame's detection list or -1; inter[m] = its intersection area (0 if none).
+// sequential: the caller's loop too (Feature_Map::get_matches, feature_map.hpp:652-669) - a detection taken by a map plane is
+// marked matched for the map planes after it; matched_out (n_det entries, may be null) = the mask as the loop leaves it.
 void plane_match_frame(const double* w2c, const rs_polygon_plane* det, int n_det, const double* det_xy,
                        const rs_polygon_plane* map, int n_map, const double* map_xy, const unsigned char* det_matched,
-                       int advanced_search, int* selected, double* inter);
+                       int advanced_search, int sequential, int* selected, double* inter, unsigned char* matched_out);
 
 }  // namespace oracle

@@ -127,8 +127,12 @@ struct MatchArgs {
     const int32_t* map_frame;   // frame of every map plane
     int n_map;
     int advanced;
+    int sequential;
+    double* cand;               // per map plane, one entry per detection of its frame: the intersection area if the pair
+    const int32_t* cand_first;  // qualifies (distance, normal, overlap share), else 0; map plane m owns [cand_first[m], +n_det(frame))
     int32_t* selected;
     double* inter;
+    uint8_t* matched_out;       // per detection: det_matched with this call's selections added (sequential mode), or null
 };
 
 __device__ __forceinline__ void rot3(const double* T, const double* p, double* o)
@@ -153,8 +157,10 @@ __global__ void __launch_bounds__(WARPS * 32) plane_match_kernel(const MatchArgs
     const rs_polygon_plane mp = g.map[m];
     const int f = g.map_frame[m];
     const double* T = g.w2c + size_t(f) * 16;
-    int sel = -1;
-    double greatest = 0.0;
+    const int k0 = g.det_first[f], k1 = g.det_first[f + 1];
+    double* cand = g.cand + g.cand_first[m];
+    for (int k = k0 + lane; k < k1; k += 32) cand[k - k0] = 0.0;
+    __syncwarp();
     const int nv = mp.n_vertices;
     if (nv >= 3 && nv <= kMaxVertices) {
         const double minimumNormalDotDiff = fabs(cos(20.0 * kPi / 180.0));
@@ -189,9 +195,8 @@ __global__ void __launch_bounds__(WARPS * 32) plane_match_kernel(const MatchArgs
         __syncwarp();
         const double projectedArea = fabs(ring_signed_area(cam, nv, lane));
         if (projectedArea > 0.0) {
-            const int k0 = g.det_first[f], k1 = g.det_first[f + 1];
             for (int k = k0; k < k1; ++k) {
-                if (g.det_matched && g.det_matched[k]) continue;
+                if (!g.sequential && g.det_matched && g.det_matched[k]) continue;   // (sequential: the selection pass decides)
                 const rs_polygon_plane& dp = g.det[k];
                 if (!(fabs(dp.d - dc) < maximumPlaneMatchDistance)) continue;
                 if (!(fabs(dp.normal[0] * nc[0] + dp.normal[1] * nc[1] + dp.normal[2] * nc[2]) > minimumNormalDotDiff)) continue;
@@ -207,13 +212,37 @@ __global__ void __launch_bounds__(WARPS * 32) plane_match_kernel(const MatchArgs
                 const double* dxy = g.det_xy + 2 * size_t(dp.first_vertex);
                 const double newPlaneArea = fabs(ring_signed_area(dxy, dp.n_vertices, lane));
                 const double interArea = inter_area_warp(dxy, dp.n_vertices, prj, nv, lane);
-                if (interArea > greatest && interArea / newPlaneArea >= threshold) sel = k - k0, greatest = interArea;
+                if (lane == 0 && interArea / newPlaneArea >= threshold) cand[k - k0] = interArea;
                 __syncwarp();
             }
         }
     }
-    if (sel <= 0) sel = -1, greatest = 0.0;   // sic (map_primitive.cpp:146): detection 0 can never be matched
-    if (lane == 0) g.selected[m] = sel, g.inter[m] = greatest;
+}
+
+// The selection of MapPlane::find_matches (map_primitive.cpp:114-147) and the caller's loop over the map's planes
+// (feature_map.hpp:652-669): one thread per frame walks its map planes IN ORDER; a map plane takes the unmatched detection
+// with the greatest qualifying intersection area (the first one on ties: `interArea > greatestSimilarity`), never detection 0
+// (`if (selectedIndex <= 0) return`, sic), and in sequential mode that detection is marked matched for the map planes after it.
+__global__ void plane_select_kernel(const MatchArgs g)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= g.n_frames) return;
+    const int k0 = g.det_first[f], nd = g.det_first[f + 1] - k0;
+    if (g.matched_out)
+        for (int k = 0; k < nd; ++k) g.matched_out[k0 + k] = g.det_matched ? g.det_matched[k0 + k] : 0;
+    for (int m = g.map_first[f]; m < g.map_first[f + 1]; ++m) {
+        const double* cand = g.cand + g.cand_first[m];
+        int sel = -1;
+        double greatest = 0.0;
+        for (int k = 0; k < nd; ++k) {
+            const bool taken = g.sequential ? (g.matched_out[k0 + k] != 0) : (g.det_matched && g.det_matched[k0 + k]);
+            if (taken) continue;
+            if (cand[k] > greatest) sel = k, greatest = cand[k];
+        }
+        if (sel <= 0) sel = -1, greatest = 0.0;
+        g.selected[m] = sel, g.inter[m] = greatest;
+        if (sel > 0 && g.sequential) g.matched_out[k0 + sel] = 1;
+    }
 }
 
 __global__ void __launch_bounds__(WARPS * 32) polygon_inter_area_kernel(const int n_pairs, const double* a_xy, const int32_t* a_first,
@@ -285,7 +314,8 @@ extern "C" {
 
 int rs_plane_match(int device, int n_frames, const double* world_to_camera, const rs_polygon_plane* det, const int32_t* det_first,
                    const double* det_xy, const rs_polygon_plane* map, const int32_t* map_first, const double* map_xy,
-                   const uint8_t* det_matched, int advanced_search, int32_t* selected, double* inter_area)
+                   const uint8_t* det_matched, int advanced_search, int sequential, int32_t* selected, double* inter_area,
+                   uint8_t* det_matched_out)
 {
     int rc = require_blackwell(device);
     if (rc != RS_OK) return rc;
@@ -312,9 +342,12 @@ int rs_plane_match(int device, int n_frames, const double* world_to_camera, cons
         }
         det_vertices = std::max(det_vertices, size_t(det[k].first_vertex) + det[k].n_vertices);
     }
-    std::vector<int32_t> map_frame(n_map);
+    std::vector<int32_t> map_frame(n_map), cand_first(size_t(n_map) + 1, 0);
     for (int f = 0; f < n_frames; ++f)
-        for (int m = map_first[f]; m < map_first[f + 1]; ++m) map_frame[m] = f;
+        for (int m = map_first[f]; m < map_first[f + 1]; ++m) {
+            map_frame[m] = f;
+            cand_first[m + 1] = cand_first[m] + (det_first[f + 1] - det_first[f]);
+        }
     for (int m = 0; m < n_map; ++m) {
         if (map[m].first_vertex < 0 || map[m].n_vertices < 0 || map[m].n_vertices > kMaxVertices) {
             set_last_error("rs_plane_match: a map polygon has more than 256 vertices (or a negative range)");
@@ -338,12 +371,25 @@ int rs_plane_match(int device, int n_frames, const double* world_to_camera, cons
     if (det_matched && (rc = d_matched.upload(det_matched, n_det, cs.s))) return rc;
     if ((rc = d_sel.upload(nullptr, n_map, cs.s))) return rc;
     if ((rc = d_inter.upload(nullptr, n_map, cs.s))) return rc;
+    DevBuf<double> d_cand;
+    DevBuf<int32_t> d_cf, d_mfirst;
+    DevBuf<uint8_t> d_mout;
+    if ((rc = d_cand.upload(nullptr, size_t(cand_first[n_map]), cs.s))) return rc;
+    if ((rc = d_cf.upload(cand_first.data(), size_t(n_map) + 1, cs.s))) return rc;
+    if ((rc = d_mfirst.upload(map_first, size_t(n_frames) + 1, cs.s))) return rc;
+    const bool want_mask = sequential || det_matched_out;
+    if (want_mask && (rc = d_mout.upload(nullptr, n_det, cs.s))) return rc;
     MatchArgs g;
     g.n_frames = n_frames, g.w2c = d_T.p, g.det = d_det.p, g.det_first = d_df.p, g.det_xy = d_dxy.p, g.map = d_map.p;
-    g.map_first = nullptr, g.map_xy = d_mxy.p, g.det_matched = det_matched ? d_matched.p : nullptr, g.map_frame = d_mf.p;
-    g.n_map = n_map, g.advanced = advanced_search, g.selected = d_sel.p, g.inter = d_inter.p;
+    g.map_first = d_mfirst.p, g.map_xy = d_mxy.p, g.det_matched = det_matched ? d_matched.p : nullptr, g.map_frame = d_mf.p;
+    g.n_map = n_map, g.advanced = advanced_search, g.sequential = sequential ? 1 : 0, g.selected = d_sel.p, g.inter = d_inter.p;
+    g.cand = d_cand.p, g.cand_first = d_cf.p, g.matched_out = want_mask ? d_mout.p : nullptr;
     plane_match_kernel<<<(n_map + WARPS - 1) / WARPS, WARPS * 32, 0, cs.s>>>(g);
     RS_LAUNCH_CHECK();
+    plane_select_kernel<<<(n_frames + 127) / 128, 128, 0, cs.s>>>(g);
+    RS_LAUNCH_CHECK();
+    if (det_matched_out && n_det)
+        RS_CUDA_CHECK(cudaMemcpyAsync(det_matched_out, d_mout.p, size_t(n_det), cudaMemcpyDeviceToHost, cs.s));
     RS_CUDA_CHECK(cudaMemcpyAsync(selected, d_sel.p, sizeof(int32_t) * n_map, cudaMemcpyDeviceToHost, cs.s));
     RS_CUDA_CHECK(cudaMemcpyAsync(inter_area, d_inter.p, sizeof(double) * n_map, cudaMemcpyDeviceToHost, cs.s));
     RS_CUDA_CHECK(cudaStreamSynchronize(cs.s));

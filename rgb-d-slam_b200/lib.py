@@ -55,7 +55,7 @@ def load():
     lib.rs_kalman_track_planes.argtypes = [i32, i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
     lib.rs_kalman_track_points_device.argtypes = [i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp]
     lib.rs_kalman_track_planes_device.argtypes = [i32, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
-    lib.rs_plane_match.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.rs_plane_match.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
     lib.rs_polygon_inter_area.argtypes = [i32, i32, vp, vp, vp, vp, vp]
     lib.rs_last_error.restype = C.c_char_p
     lib.rs_version.restype = C.c_char_p
@@ -239,10 +239,13 @@ def kalman_track_planes(state, cov, meas, meas_cov, process_noise=1e-6, device=0
     return out_state, out_cov, score, status
 
 
-def plane_match(w2c, det, det_first, det_xy, map_planes, map_first, map_xy, det_matched=None, advanced_search=False, device=0):
+def plane_match(w2c, det, det_first, det_xy, map_planes, map_first, map_xy, det_matched=None, advanced_search=False, device=0,
+                sequential=False, return_matched=False):
     """MapPlane::find_matches (map_primitive.cpp:91-161) for every map plane of every frame at once.
     w2c [F,4,4]; det / map_planes: abi.polygon_plane_dtype records; det_first / map_first [F+1] offsets; det_xy / map_xy [V,2]
-    polygon vertices. Returns (selected [n_map] = index of the matched detection inside its frame's list or -1, inter_area)."""
+    polygon vertices. sequential: also the caller's loop (feature_map.hpp:652-669) - the map planes of a frame are served in
+    order and a detection taken by one is unavailable to those after it. Returns (selected [n_map] = index of the matched
+    detection inside its frame's list or -1, inter_area) and, with return_matched, the matched mask as the loop leaves it."""
     lib = load()
     w2c = np.ascontiguousarray(w2c, dtype=np.float64)
     det = np.ascontiguousarray(det, dtype=abi.polygon_plane_dtype)
@@ -254,10 +257,12 @@ def plane_match(w2c, det, det_first, det_xy, map_planes, map_first, map_xy, det_
         raise ValueError("offset arrays do not describe the plane arrays")
     sel, inter = np.full(len(mp), -1, np.int32), np.zeros(len(mp))
     dm = None if det_matched is None else np.ascontiguousarray(det_matched, dtype=np.uint8)
+    mout = np.zeros(max(len(det), 1), np.uint8)
     _check(lib.rs_plane_match(device, n_frames, w2c.ctypes.data, det.ctypes.data, det_first.ctypes.data, det_xy.ctypes.data,
                               mp.ctypes.data, map_first.ctypes.data, map_xy.ctypes.data, None if dm is None else dm.ctypes.data,
-                              int(advanced_search), sel.ctypes.data, inter.ctypes.data), "rs_plane_match")
-    return sel, inter
+                              int(advanced_search), int(sequential), sel.ctypes.data, inter.ctypes.data,
+                              mout.ctypes.data if return_matched else None), "rs_plane_match")
+    return (sel, inter, mout[:len(det)]) if return_matched else (sel, inter)
 
 
 def polygon_inter_area(a_rings, b_rings, device=0):

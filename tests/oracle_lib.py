@@ -51,7 +51,7 @@ def load():
     lib.orc_polygon_inter_area.argtypes = [vp, i32, vp, i32]
     lib.orc_polygon_area.restype = dbl
     lib.orc_polygon_area.argtypes = [vp, i32]
-    lib.orc_plane_match.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.orc_plane_match.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
     lib.orc_rectify_depth.argtypes = [i32, i32, dbl, dbl, dbl, dbl, vp, vp, i32, vp]
     lib.orc_ref_test_features.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32]
     _lib = lib
@@ -195,7 +195,8 @@ def polygon_area(a):
     return lib.orc_polygon_area(a.ctypes.data, len(a))
 
 
-def plane_match(w2c, det, det_first, det_xy, mp, map_first, map_xy, det_matched=None, advanced_search=False):
+def plane_match(w2c, det, det_first, det_xy, mp, map_first, map_xy, det_matched=None, advanced_search=False, sequential=False,
+                return_matched=False):
     """MapPlane::find_matches for every map plane of every frame (oracle/polygon.cpp). Same arguments as rs.plane_match."""
     lib = load()
     w2c = np.ascontiguousarray(w2c, dtype=np.float64)
@@ -205,7 +206,8 @@ def plane_match(w2c, det, det_first, det_xy, mp, map_first, map_xy, det_matched=
     n_frames = len(det_first) - 1
     sel, inter = np.full(len(mp), -1, np.int32), np.zeros(len(mp))
     dm = None if det_matched is None else np.ascontiguousarray(det_matched, dtype=np.uint8)
+    mout = np.zeros(max(len(det), 1), np.uint8)
     lib.orc_plane_match(n_frames, w2c.ctypes.data, det.ctypes.data, det_first.ctypes.data, det_xy.ctypes.data, mp.ctypes.data,
                         map_first.ctypes.data, map_xy.ctypes.data, None if dm is None else dm.ctypes.data, int(advanced_search),
-                        sel.ctypes.data, inter.ctypes.data)
-    return sel, inter
+                        int(sequential), sel.ctypes.data, inter.ctypes.data, mout.ctypes.data)
+    return (sel, inter, mout[:len(det)]) if return_matched else (sel, inter)

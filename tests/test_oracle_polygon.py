@@ -66,10 +66,12 @@ def test_concave_pairs_against_raster():
         assert got == pytest.approx(ol.polygon_inter_area(b, a), rel=1e-10, abs=1e-6)            # symmetric
 
 
-def numpy_find_matches(w2c, det, det_xy, mp, map_xy, det_matched, advanced):
-    """MapPlane::find_matches written from the reference with numpy; the intersection area comes from the oracle."""
+def numpy_find_matches(w2c, det, det_xy, mp, map_xy, det_matched, advanced, sequential=False):
+    """MapPlane::find_matches written from the reference with numpy; the intersection area comes from the oracle.
+    sequential: with the caller's loop (feature_map.hpp:652-669) marking taken detections between two map planes."""
     R, t = w2c[:3, :3], w2c[:3, 3]
     out = []
+    det_matched = np.zeros(len(det), bool) if det_matched is None else np.array(det_matched, bool)
     thr = np.float64(np.float32(0.4)) / (2 if advanced else 1)
     for m in mp:
         pw = np.array([*m["normal"], m["d"]])
@@ -92,7 +94,7 @@ def numpy_find_matches(w2c, det, det_xy, mp, map_xy, det_matched, advanced):
         sel, best = -1, 0.0
         if ol.polygon_area(cam) > 0:
             for k, dpl in enumerate(det):
-                if det_matched is not None and det_matched[k]:
+                if det_matched[k]:
                     continue
                 if not abs(dpl["d"] - dc) < 100.0 or not abs(dpl["normal"] @ nc) > abs(np.cos(np.deg2rad(20.0))):
                     continue
@@ -103,6 +105,8 @@ def numpy_find_matches(w2c, det, det_xy, mp, map_xy, det_matched, advanced):
                 if inter > best and inter / ol.polygon_area(dring) >= thr:
                     sel, best = k, inter
         out.append((sel, best) if sel > 0 else (-1, 0.0))
+        if sequential and sel > 0:
+            det_matched[sel] = True
     return out
 
 
@@ -120,3 +124,31 @@ def test_plane_match_against_numpy_restatement(advanced):
         n_sel += int((sel >= 0).sum())
         assert not (sel == 0).any()   # the reference's `selectedIndex <= 0` quirk
     assert n_sel > 10   # the scenario does produce matches
+
+
+def test_sequential_matching_reproduces_the_callers_loop():
+    """sequential=True: the map planes of a frame are served in order and a taken detection is marked matched for the next ones
+    (Feature_Map::get_matches). Map planes that compete for one detection must come out differently from the one-shot mode."""
+    differs = 0
+    for seed in range(8):
+        w2c, det, df, dxy, mp, mf, mxy, matched = rs.synth.plane_match_problem(40 + seed, n_frames=3, n_extra_map=0)
+        # duplicate every frame's map planes: the copies compete with the originals for the same detections
+        mp2, mf2 = [], [0]
+        for f in range(len(df) - 1):
+            mp2 += list(mp[mf[f]:mf[f + 1]]) * 2
+            mf2.append(len(mp2))
+        mp2 = np.array(mp2, dtype=mp.dtype)
+        sel, inter, mout = ol.plane_match(w2c, det, df, dxy, mp2, mf2, mxy, matched, sequential=True, return_matched=True)
+        one, _ = ol.plane_match(w2c, det, df, dxy, mp2, mf2, mxy, matched)
+        differs += int((sel != one).sum())
+        for f in range(len(df) - 1):
+            want = numpy_find_matches(w2c[f], det[df[f]:df[f + 1]], dxy, mp2[mf2[f]:mf2[f + 1]], mxy, matched[df[f]:df[f + 1]], False,
+                                      sequential=True)
+            got = sel[mf2[f]:mf2[f + 1]]
+            assert [w[0] for w in want] == list(got), (seed, f)
+            taken = got[got >= 0]
+            assert len(set(taken)) == len(taken)                          # no detection is handed out twice
+            expect = np.array(matched[df[f]:df[f + 1]], bool)
+            expect[taken] = True
+            assert np.array_equal(mout[df[f]:df[f + 1]].astype(bool), expect)
+    assert differs > 0

@@ -67,3 +67,21 @@ def test_plane_match_rejects_oversized_map_polygon():
     args[2] = np.array([0, 5, 3], np.int32)     # offsets that go backwards
     with pytest.raises((rs.RsError, ValueError)):
         rs.plane_match(*args[:-1])
+
+
+def test_sequential_matching_matches_oracle():
+    """The caller's loop on the device (plane_select_kernel): same selections and matched mask as the oracle's sequential walk."""
+    for seed in range(6):
+        w2c, det, df, dxy, mp, mf, mxy, matched = rs.synth.plane_match_problem(300 + seed, n_frames=12, n_extra_map=1)
+        mp2, mf2 = [], [0]
+        for f in range(len(df) - 1):
+            mp2 += list(mp[mf[f]:mf[f + 1]]) * 2   # competing copies
+            mf2.append(len(mp2))
+        mp2 = np.array(mp2, dtype=mp.dtype)
+        dm = matched if seed & 1 else None
+        sel, inter, mout = rs.plane_match(w2c, det, df, dxy, mp2, mf2, mxy, det_matched=dm, sequential=True, return_matched=True)
+        rsel, rinter, rmout = ol.plane_match(w2c, det, df, dxy, mp2, mf2, mxy, det_matched=dm, sequential=True, return_matched=True)
+        assert np.array_equal(sel, rsel) and np.array_equal(mout, rmout), seed
+        assert np.allclose(inter, rinter, rtol=1e-9, atol=1e-6)
+        one, _ = rs.plane_match(w2c, det, df, dxy, mp2, mf2, mxy, det_matched=dm)
+        assert (one != sel).any()
