@@ -95,12 +95,15 @@ def pose_close(ref_pose, got_pose, rtol=1e-4, qtol=1e-8):
     return dt <= max(rtol * tn, 1e-3) and qd >= 1 - qtol, dt, qd
 
 
-def oracle_pose_is_determined(pose_solve, cur, matches, seed, scales=(1e-12, 1e-10, -1e-10, 1e-9)):
+def oracle_pose_is_determined(pose_solve, cur, matches, seed, scales=(1e-12, 1e-10, -1e-10, 1e-9, 1e-8, -1e-8, 1e-7)):
     """Is the reference algorithm's answer on this frame determined at all? Re-runs the oracle (`pose_solve` =
     oracle_lib.pose_solve) with the observations scaled by 1 + s for a few s far below any sensor resolution. A frame where
     that flips an integer output (winning hypothesis, inlier set), moves the pose by more than 1e-7 mm or the covariance by
     more than 1e-6 relative amplifies rounding noise by > 1e8 - a hypothesis sitting on an inlier threshold, a consensus set
-    that barely constrains the pose - and no two builds of the reference itself would agree on it. Returns (determined, why)."""
+    that barely constrains the pose - and no two builds of the reference itself would agree on it. The probes go up to 1e-7
+    (1e-5 px): the device's Jacobian differs from NumericalDiff's by its O(h) truncation term, 1e-8 relative, so
+    a frame whose oracle answer flips between two attractors under a 1e-8..1e-7 input change cannot be expected to agree either
+    (found by the round-2 sweep: a converged minimal-subset solve in a flat valley, 106 or 117 inliers). Returns (determined, why)."""
     ref, rmask = pose_solve(cur, matches, seed=seed)
     for s in scales:
         m2 = matches.copy()
