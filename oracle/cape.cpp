@@ -1,4 +1,5 @@
-// TEST INFRASTRUCTURE — CPU oracle (see cape.hpp). PARITY UNPINNED (no reference test/golden for CAPE).
+// TEST INFRASTRUCTURE — CPU oracle (see cape.hpp). Pinned bit for bit by the reference's own sources compiled against stand-in
+// third-party headers (oracle/ref_shim, tests/test_reference_build.py); no reference test / golden vector exists for CAPE.
 // Every function cites the reference lines it restates; quirks are kept on purpose.
 #include "cape.hpp"
 

@@ -1,8 +1,11 @@
 // TEST INFRASTRUCTURE — CPU oracle (see linalg.hpp header). Restates the reference's CAPE path:
 //   src/features/primitives/{depth_map_transformation,plane_segment,histogram,primitive_detection,
 //   cylinder_segment}.* and src/utils/covariances.cpp:12-19.
-// PARITY UNPINNED: the reference has no test, golden vector or dataset for this path and
-// cannot be compiled here (Eigen/OpenCV/TBB/boost absent). This restatement is the only pin.
+// PIN: the reference has no test, golden vector or dataset for this path; its own translation units do
+// compile here against stand-in third-party headers (oracle/ref_shim -> oracle/_ref/libref_cape.so), and this restatement must
+// equal that build bit for bit (tests/test_reference_build.py: cell fits, label grids, planes, boundary points, cylinders,
+// rectify_depth on scene v0, edge cases, 96 random rooms). Unpinned: the arithmetic inside Eigen / OpenCV beyond the
+// cross-checks of tests/test_oracle_cape.py (LAPACK eigh, cv2 morphology) - the stand-ins share this oracle's restatements there.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -61,8 +64,9 @@ void cell_record(const PlaneSeg& s, float tol, int cellSize, rs_cell_out& o);
 // Depth_Map_Transformation::rectify_depth (depth_map_transformation.cpp:23-87): depth image of camera 2 re-projected
 // into the image of camera 1, serial row-major scan (the MAKE_DETERMINISTIC build), last writer wins.
 // cam2_to_cam1 = Parameters::get_camera_2_to_camera_1_transformation(), row-major 4x4. out = H*W floats.
-// PARITY UNPINNED beyond the restatement: the summation order inside Eigen's 4x4 * homogeneous product is taken as
-// ((T0 x + T1 y) + T2 z) + T3; it can only matter when a projected coordinate lies within an ulp of a pixel boundary.
+// Pinned by the compiled reference source (tests/test_reference_build.py::test_rectify_depth) up to the summation order inside
+// Eigen's 4x4 * homogeneous product, taken as ((T0 x + T1 y) + T2 z) + T3 here and in the stand-in; it can only matter when a
+// projected coordinate lies within an ulp of a pixel boundary.
 void rectify_depth(const CapeConfig& cfg, const double cam2_to_cam1[16], const float* depth, float* out);
 
 // The restatement of cv::erode / cv::dilate (3x3 square or cross kernel, anchor at the centre, one iteration) that the

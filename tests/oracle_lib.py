@@ -211,3 +211,58 @@ def plane_match(w2c, det, det_first, det_xy, mp, map_first, map_xy, det_matched=
                         map_first.ctypes.data, map_xy.ctypes.data, None if dm is None else dm.ctypes.data, int(advanced_search),
                         int(sequential), sel.ctypes.data, inter.ctypes.data, mout.ctypes.data)
     return (sel, inter, mout[:len(det)]) if return_matched else (sel, inter)
+
+
+# ---- the reference's own CAPE sources, compiled against stand-in third-party headers (oracle/ref_shim -> oracle/_ref) ----
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_cape.so")
+_ref = None
+
+
+def ref_available():
+    """True when oracle/_ref/libref_cape.so exists; it is (re)built from the reference tree wherever that is present
+    (/root/reference: this container - the GPU box gets the prebuilt file with the snapshot)."""
+    if os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-C", os.path.join(ORACLE_DIR, "ref_shim")], capture_output=True)
+    return os.path.exists(REF_LIB)
+
+
+def _ref_load():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_LIB)
+        vp, i32 = C.c_void_p, C.c_int
+        lib.ref_cape_run.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, i32]
+        lib.ref_rectify_depth.argtypes = [vp, i32, i32, vp, vp]
+        _ref = lib
+    return _ref
+
+
+def ref_cape_run(depth):
+    """One 640x480 frame through the REFERENCE's get_organized_cloud_array + find_primitives (MAKE_DETERMINISTIC: seed 0)."""
+    lib = _ref_load()
+    d = np.ascontiguousarray(depth, dtype=np.float32)
+    H, W = d.shape
+    cell = lib.ref_cape_cell_px()
+    Nc = (W // cell) * (H // cell)
+    out = dict(plane_grid=np.zeros(Nc, np.int32), cyl_grid=np.zeros(Nc, np.int32), planar=np.zeros(Nc, np.int32),
+               cell=np.zeros((Nc, 5)), count=np.zeros(Nc, np.int32))
+    planes, cyls, boundary = np.zeros((128, 6)), np.zeros((64, 4)), np.zeros((4 * Nc, 3))
+    npl, ncy = C.c_int32(0), C.c_int32(0)
+    rc = lib.ref_cape_run(d.ctypes.data, W, H, out["plane_grid"].ctypes.data, out["cyl_grid"].ctypes.data, out["planar"].ctypes.data,
+                          out["cell"].ctypes.data, out["count"].ctypes.data, planes.ctypes.data, 128, C.byref(npl), cyls.ctypes.data,
+                          64, C.byref(ncy), boundary.ctypes.data, len(boundary))
+    if rc != 0:
+        raise RuntimeError("reference get_organized_cloud_array failed")
+    out["planes"], out["cyls"] = planes[:npl.value], cyls[:ncy.value]
+    out["boundary"] = boundary[:int(planes[:npl.value, 5].sum())]
+    return out
+
+
+def ref_rectify_depth(depth, cam2_to_cam1):
+    lib = _ref_load()
+    d = np.ascontiguousarray(depth, dtype=np.float32)
+    T = np.ascontiguousarray(cam2_to_cam1, dtype=np.float64)
+    out = np.zeros_like(d)
+    if lib.ref_rectify_depth(d.ctypes.data, d.shape[1], d.shape[0], T.ctypes.data, out.ctypes.data) != 0:
+        raise RuntimeError("reference rectify_depth failed")
+    return out
