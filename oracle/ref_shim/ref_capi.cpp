@@ -72,6 +72,12 @@ int ref_cape_run(const float* depth, int width, int height, int32_t* plane_grid,
         const unsigned cell = parameters::detection::depthMapPatchSize_px;
         features::primitives::Depth_Map_Transformation depthOps(width, height, cell);
         features::primitives::Primitive_Detection detector(width, height);
+        // The reference keeps ONE detector for the whole sequence, so after the first frames its segment vectors never
+        // reallocate. That matters at the last bit: Plane_Segment has a copy constructor but no move constructor, a
+        // reallocating push_back copies every stored segment, and every copy re-normalises its normal (PlaneCoordinates'
+        // copy constructor) - a fresh detector per frame would add growth-dependent 1-ulp changes (seen on 4 of 1024 rooms).
+        detector._planeSegments.reserve(1024);
+        detector._cylinderSegments.reserve(1024);
         cv::Mat_<float> image(height, width);
         std::memcpy(image.data, depth, sizeof(float) * size_t(width) * height);
         matrixf cloud;
