@@ -193,6 +193,15 @@ int orc_pose_lm(const double K[4], const rs_match* m, int n, double x[6], int ma
     return r.status;
 }
 
+// IOptimizationFeature::is_inlier of every match under a pose (features as given: no normalisation)
+void orc_pose_inliers(const double K[4], const double pose[7], const rs_match* m, int n, uint8_t* mask)
+{
+    Intrinsics I{K[0], K[1], K[2], K[3]};
+    const Mat4 w2c = world_to_camera(pose + 3, pose);
+    const Mat4 pw2c = plane_world_to_camera(w2c);
+    for (int i = 0; i < n; ++i) mask[i] = feature_is_inlier(I, m[i], w2c, pw2c) ? 1 : 0;
+}
+
 int orc_ransac_default_iterations() { return ransac_default_iterations(); }
 
 // One compute_optimized_pose. subsets/normals: optional explicit random inputs (layout of rs_pose_export_random,

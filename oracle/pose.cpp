@@ -760,6 +760,12 @@ bool optimized_global_pose(const Intrinsics& K, const Pose7& cur, const std::vec
     pose_vector6(p, v6);
     if (has_nan(v6, 6)) return false;
     out = p;
+    // optimizedPose.set_parameters(outputPose.get_position(), outputPose.get_orientation_quaternion()) (:357) normalises the
+    // quaternion the PoseBase constructor has already normalised (pose.cpp:16-22): up to one more ulp on q. Observed against
+    // the compiled reference sources (oracle/ref_shim, tests/test_reference_pose_build.py).
+    const double nn = std::sqrt(p.q[0] * p.q[0] + p.q[1] * p.q[1] + p.q[2] * p.q[2] + p.q[3] * p.q[3]);
+    if (nn > 0)
+        for (double& v : out.q) v /= nn;
     return true;
 }
 

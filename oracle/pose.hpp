@@ -6,8 +6,11 @@
 // which are NOT vendored by the reference (find_package(Eigen3), CMakeLists.txt:35) and not on this machine:
 // restated from the published algorithms (MINPACK lmdif/lmpar/qrsolv). PINS: (1) the 40 scenarios of
 // tests/test_pose_optimization.cpp re-run against this oracle with the reference's own tolerances
-// (tests/test_oracle_pose.py); (2) the LM cross-checked against scipy.optimize.leastsq (MINPACK).
-// The LM iterate path itself is "parity unpinned" beyond that.
+// (tests/test_oracle_pose.py); (2) the LM cross-checked against scipy.optimize.leastsq (MINPACK); (3) the reference's own
+// pose-solve translation units compiled against stand-in Eigen headers (oracle/ref_shim -> oracle/_ref/libref_pose.so): this
+// restatement equals that build BIT FOR BIT - status, inlier mask, pose, Monte-Carlo covariance - on the 40 scenarios and on
+// random mixed point / plane / point2d problems (tests/test_reference_pose_build.py).
+// The arithmetic inside Eigen's LM / QR itself stays "parity unpinned" beyond (2).
 #pragma once
 #include <cstdint>
 #include <functional>

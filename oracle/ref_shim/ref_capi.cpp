@@ -18,34 +18,7 @@
 #include <cstring>
 #include <thread>
 
-namespace rgbd_slam::outputs {
-void log(const std::string_view&, const std::source_location&) noexcept {}
-void log_warning(const std::string_view&, const std::source_location&) noexcept {}
-void log_error(const std::string_view& message, const std::source_location& location) noexcept
-{
-    std::fprintf(stderr, "[reference] %s:%u %.*s\n", location.file_name(), location.line(), int(message.size()), message.data());
-}
-}  // namespace rgbd_slam::outputs
-
-namespace rgbd_slam {
-// parameters.cpp:59-74 (the default camera: 640 x 480, f = 550, principal point at the image centre, cameras coincident)
-void Parameters::load_defaut() noexcept
-{
-    _camera1ImageSize = vector2_uint(640, 480);
-    _camera1Focal = vector2(550, 550);
-    _camera1Center.x() = static_cast<float>(_camera1ImageSize.x()) / 2;
-    _camera1Center.y() = static_cast<float>(_camera1ImageSize.y()) / 2;
-    _camera2ImageSize = vector2_uint(640, 480);
-    _camera2Focal = vector2(550, 550);
-    _camera2Center.x() = static_cast<float>(_camera2ImageSize.x()) / 2;
-    _camera2Center.y() = static_cast<float>(_camera2ImageSize.y()) / 2;
-    _camera2toCamera1transformation = matrix44::Identity();
-    _isValid = true;
-}
-namespace utils {
-#include "gen_depth_quantization.inc"
-}  // namespace utils
-}  // namespace rgbd_slam
+#include "ref_common.inc"
 
 using namespace rgbd_slam;
 

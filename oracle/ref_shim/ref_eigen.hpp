@@ -15,10 +15,14 @@
 #include <xmmintrin.h>
 
 #include <array>
+#include <atomic>
 #include <cassert>
 #include <cmath>
 #include <cstddef>
 #include <initializer_list>
+#include <memory>
+#include <mutex>
+#include <ostream>
 #include <stdexcept>
 #include <type_traits>
 #include <vector>
@@ -172,6 +176,13 @@ class Matrix : public MatBase<Matrix<T, R, C>> {
         for (Index i = 0; i < m.rows() && i < m.cols(); ++i) m(i, i) = T(1);
         return m;
     }
+    static Matrix Constant(T v)
+    {
+        static_assert(kFixed, "Constant(value) on a fixed-size matrix");
+        Matrix m;
+        m.setConstant(v);
+        return m;
+    }
     static Matrix Constant(Index n, T v)
     {
         Matrix m(n);
@@ -231,6 +242,17 @@ class Matrix : public MatBase<Matrix<T, R, C>> {
         return m;
     }
     template <int N>
+    View<T> head() { return View<T>(d_.data(), N, 1, r_ * c_); }
+    template <int N>
+    View<T> tail() { return View<T>(d_.data() + (size() - N), N, 1, r_ * c_); }
+    template <int N>
+    Matrix<T, N, 1> tail() const
+    {
+        Matrix<T, N, 1> v;
+        for (int i = 0; i < N; ++i) v(i) = d_[size_t(size() - N + i)];
+        return v;
+    }
+    template <int N>
     Matrix<T, N, 1> head() const
     {
         Matrix<T, N, 1> v;
@@ -238,13 +260,43 @@ class Matrix : public MatBase<Matrix<T, R, C>> {
         return v;
     }
 
-    // the comma initialiser as the sources use it: `coordinate << vector;`
+    // the comma initialiser on vectors, as the sources use it: `v << a;`, `v6 << position, angles;`, `v << x, y, z;`
+    // Eigen's CommaInitializer: items are placed left to right, a row of blocks at a time (a scalar is a 1 x 1 block)
+    struct CommaInit {
+        Matrix& m;
+        Index row = 0, col = 0, block_rows = 0;
+        void place(const T* src, Index br, Index bc, Index ld)
+        {
+            if (col >= m.c_) row += block_rows, col = 0, block_rows = 0;
+            if (col == 0) block_rows = br;
+            for (Index j = 0; j < bc; ++j)
+                for (Index i = 0; i < br; ++i) m(row + i, col + j) = src[i + j * ld];
+            col += bc;
+        }
+        template <int R2, int C2>
+        CommaInit& operator,(const Matrix<T, R2, C2>& o)
+        {
+            place(o.data(), o.rows(), o.cols(), o.rows());
+            return *this;
+        }
+        CommaInit& operator,(const T v)
+        {
+            place(&v, 1, 1, 1);
+            return *this;
+        }
+    };
     template <int R2, int C2>
-    Matrix& operator<<(const Matrix<T, R2, C2>& o)
+    CommaInit operator<<(const Matrix<T, R2, C2>& o)
     {
-        assert(o.size() == size());
-        for (size_t k = 0; k < d_.size(); ++k) d_[k] = o.data()[k];
-        return *this;
+        CommaInit c{*this};
+        c, o;
+        return c;
+    }
+    CommaInit operator<<(const T v)
+    {
+        CommaInit c{*this};
+        c, v;
+        return c;
     }
 
     Matrix<T, C, R> transpose() const
@@ -322,6 +374,28 @@ class Matrix : public MatBase<Matrix<T, R, C>> {
         for (const T v : d_) n += v ? 1 : 0;
         return n;
     }
+    template <int R2, int C2>
+    Matrix cwiseProduct(const Matrix<T, R2, C2>& o) const
+    {
+        assert(o.size() == size());
+        Matrix m = *this;
+        for (size_t k = 0; k < d_.size(); ++k) m.d_[k] = d_[k] * o.data()[k];
+        return m;
+    }
+    Matrix cwiseSqrt() const
+    {
+        Matrix m = *this;
+        for (T& v : m.d_) v = std::sqrt(v);
+        return m;
+    }
+    bool isApproxToConstant(const T value, const T prec = T(1e-12)) const
+    {
+        // Eigen: isApprox(Constant(value)) = |this - c|^2 <= prec^2 min(|this|^2, |c|^2)
+        T diff = T(), a = T(), b = T();
+        for (const T v : d_) diff += (v - value) * (v - value), a += v * v, b += value * value;
+        return diff <= prec * prec * std::min(a, b);
+    }
+    View<T> segment(Index start, Index n) { return View<T>(d_.data() + start, n, 1, r_ * c_); }
     Matrix cwiseAbs() const
     {
         Matrix m = *this;
@@ -338,6 +412,31 @@ class Matrix : public MatBase<Matrix<T, R, C>> {
         for (int i = 0; i < R; ++i) h(i) = d_[size_t(i)];
         h(R) = T(1);
         return h;
+    }
+    // diagonal() as an assignable view (`cov.diagonal() += v`) and as a value
+    struct Diagonal {
+        Matrix& m;
+        template <int R2, int C2>
+        Diagonal& operator+=(const Matrix<T, R2, C2>& v)
+        {
+            for (Index i = 0; i < std::min(m.rows(), m.cols()); ++i) m(i, i) += v(i);
+            return *this;
+        }
+        operator Matrix<T, R, 1>() const
+        {
+            Matrix<T, R, 1> d;
+            d.resize_for(std::min(m.rows(), m.cols()), 1);
+            for (Index i = 0; i < d.rows(); ++i) d(i) = m(i, i);
+            return d;
+        }
+    };
+    Diagonal diagonal() { return Diagonal{*this}; }
+    Matrix<T, R, 1> diagonal() const
+    {
+        Matrix<T, R, 1> d;
+        d.resize_for(std::min(r_, c_), 1);
+        for (Index i = 0; i < d.rows(); ++i) d(i) = (*this)(i, i);
+        return d;
     }
     // colwise().norm(): the Euclidean norm of every column, as a row
     struct Colwise {
@@ -379,12 +478,31 @@ class Matrix : public MatBase<Matrix<T, R, C>> {
     }
     Matrix inverse() const
     {
-        static_assert(R == 3 && C == 3, "inverse of a 3x3");
-        const oracle::Mat3 inv = oracle::inverse3(to_mat3());
+        static_assert((R == 3 && C == 3) || (R == 4 && C == 4), "inverse of a 3x3 or a 4x4");
         Matrix m;
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) m(i, j) = inv.m[i][j];
+        if constexpr (R == 3) {
+            const oracle::Mat3 inv = oracle::inverse3(to_mat3());
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) m(i, j) = inv.m[i][j];
+        }
+        else {
+            oracle::Mat4 a;
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) a.m[i][j] = (*this)(i, j);
+            const oracle::Mat4 inv = oracle::inverse4(a);
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) m(i, j) = inv.m[i][j];
+        }
         return m;
+    }
+    // MatrixBase::eulerAngles(0, 1, 2) (oracle/linalg.hpp: euler_angles_012, Eigen's algorithm)
+    Matrix<T, 3, 1> eulerAngles(int a0, int a1, int a2) const
+    {
+        static_assert(R == 3 && C == 3, "eulerAngles of a rotation matrix");
+        if (a0 != 0 || a1 != 1 || a2 != 2) throw std::logic_error("eulerAngles: only (0, 1, 2)");
+        double res[3];
+        oracle::euler_angles_012(to_mat3(), res);
+        return Matrix<T, 3, 1>(res[0], res[1], res[2]);
     }
     oracle::Mat3 to_mat3() const
     {
@@ -504,6 +622,36 @@ struct Arr {
     T sum() const { return m.sum(); }
     Index count() const { return m.count(); }
     Arr<unsigned char> operator>(const T s) const { return Arr<unsigned char>{m > s}; }
+    Arr<unsigned char> operator>=(const T s) const
+    {
+        Arr<unsigned char> out{DynMat<unsigned char>(m.rows(), m.cols())};
+        for (Index k = 0; k < m.size(); ++k) out.m.data()[k] = m.data()[k] >= s ? 1 : 0;
+        return out;
+    }
+    Arr<unsigned char> operator<=(const T s) const
+    {
+        Arr<unsigned char> out{DynMat<unsigned char>(m.rows(), m.cols())};
+        for (Index k = 0; k < m.size(); ++k) out.m.data()[k] = m.data()[k] <= s ? 1 : 0;
+        return out;
+    }
+    Arr<unsigned char> operator<=(const Arr& o) const
+    {
+        Arr<unsigned char> out{DynMat<unsigned char>(m.rows(), m.cols())};
+        for (Index k = 0; k < m.size(); ++k) out.m.data()[k] = m.data()[k] <= o.m.data()[k] ? 1 : 0;
+        return out;
+    }
+    bool all() const
+    {
+        for (Index k = 0; k < m.size(); ++k)
+            if (!m.data()[k]) return false;
+        return true;
+    }
+    bool any() const
+    {
+        for (Index k = 0; k < m.size(); ++k)
+            if (m.data()[k]) return true;
+        return false;
+    }
     Arr abs() const { return Arr{m.cwiseAbs()}; }
     DynMat<T> matrix() const { return m; }
     template <int R, int C>
@@ -547,6 +695,91 @@ using Vector4d = Matrix<double, 4, 1>;
 using Matrix2d = Matrix<double, 2, 2>;
 using Matrix3d = Matrix<double, 3, 3>;
 using Matrix4d = Matrix<double, 4, 4>;
+
+template <class T, int R, int C>
+std::ostream& operator<<(std::ostream& os, const Matrix<T, R, C>& m)
+{
+    for (Index i = 0; i < m.rows(); ++i) {
+        for (Index j = 0; j < m.cols(); ++j) os << (j ? " " : "") << m(i, j);
+        if (i + 1 < m.rows()) os << "\n";
+    }
+    return os;
+}
+
+template <class T>
+using aligned_allocator = std::allocator<T>;
+
+// Quaternion<double> with Eigen's conventions: coefficients stored (x, y, z, w), constructor (w, x, y, z), Hamilton product,
+// toRotationMatrix() by Eigen's formula (oracle/linalg.hpp: quat_to_rot)
+template <class T>
+class Quaternion {
+    T x_ = 0, y_ = 0, z_ = 0, w_ = 1;
+
+  public:
+    Quaternion() = default;
+    Quaternion(T w, T x, T y, T z) : x_(x), y_(y), z_(z), w_(w) {}
+    static Quaternion Identity() { return Quaternion(1, 0, 0, 0); }
+    void setIdentity() { *this = Identity(); }
+    Quaternion& operator*=(const Quaternion& b) { return *this = *this * b; }
+    T w() const { return w_; }
+    T x() const { return x_; }
+    T y() const { return y_; }
+    T z() const { return z_; }
+    T& w() { return w_; }
+    T& x() { return x_; }
+    T& y() { return y_; }
+    T& z() { return z_; }
+    Matrix<T, 4, 1> coeffs() const { return Matrix<T, 4, 1>(x_, y_, z_, w_); }
+    // summed w, x, y, z: the order oracle/pose.cpp documents for PoseBase::set_parameters (Eigen's own packet reduction is
+    // (x^2 + z^2) + (y^2 + w^2) with SSE2; a <= 1 ulp effect on q either way, third-party arithmetic)
+    T squaredNorm() const { return ((w_ * w_ + x_ * x_) + y_ * y_) + z_ * z_; }
+    T norm() const { return std::sqrt(squaredNorm()); }
+    void normalize()
+    {
+        // Eigen: coeffs().normalize() -> divide by sqrt(squaredNorm) when positive
+        const T n2 = squaredNorm();
+        if (n2 > T(0)) {
+            const T n = std::sqrt(n2);
+            x_ /= n, y_ /= n, z_ /= n, w_ /= n;
+        }
+    }
+    Quaternion normalized() const
+    {
+        Quaternion q = *this;
+        q.normalize();
+        return q;
+    }
+    Quaternion conjugate() const { return Quaternion(w_, -x_, -y_, -z_); }
+    Quaternion inverse() const
+    {
+        const T n2 = squaredNorm();
+        return Quaternion(w_ / n2, -x_ / n2, -y_ / n2, -z_ / n2);
+    }
+    Quaternion operator*(const Quaternion& b) const
+    {
+        const Quaternion& a = *this;
+        return Quaternion(a.w_ * b.w_ - a.x_ * b.x_ - a.y_ * b.y_ - a.z_ * b.z_, a.w_ * b.x_ + a.x_ * b.w_ + a.y_ * b.z_ - a.z_ * b.y_,
+                          a.w_ * b.y_ + a.y_ * b.w_ + a.z_ * b.x_ - a.x_ * b.z_, a.w_ * b.z_ + a.z_ * b.w_ + a.x_ * b.y_ - a.y_ * b.x_);
+    }
+    Matrix<T, 3, 3> toRotationMatrix() const
+    {
+        const double q[4] = {w_, x_, y_, z_};
+        const oracle::Mat3 r = oracle::quat_to_rot(q);
+        Matrix<T, 3, 3> m;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) m(i, j) = r.m[i][j];
+        return m;
+    }
+    Matrix<T, 3, 3> matrix() const { return toRotationMatrix(); }
+    T angularDistance(const Quaternion& o) const
+    {
+        const Quaternion d = *this * o.conjugate();
+        const T vn = std::sqrt(d.x_ * d.x_ + d.y_ * d.y_ + d.z_ * d.z_);
+        return T(2) * std::atan2(vn, std::abs(d.w_));
+    }
+    bool isApprox(const Quaternion& o, const T prec = T(1e-12)) const { return coeffs().isApprox(o.coeffs(), prec); }
+};
+using Quaterniond = Quaternion<double>;
 
 // Affine3d as coordinates/point_coordinates.cpp::get_transformation_matrix uses it (a function outside the CAPE path, present
 // in a translation unit the CAPE path needs): `T.linear() << a, b, c;` fills the columns, `T.translation() << t;`

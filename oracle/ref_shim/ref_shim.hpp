@@ -3,6 +3,7 @@
 //   src/types.hpp (Eigen typedefs + Eigen-internal functor traits)  ->  the same type names on oracle/ref_shim/ref_eigen.hpp
 #pragma once
 #include <cmath>
+#include <string>
 #include <vector>
 
 #include "ref_cv.hpp"
@@ -29,9 +30,7 @@ using matrix33 = Eigen::Matrix3d;
 using matrix34 = Eigen::Matrix<double, 3, 4>;
 using matrix43 = Eigen::Matrix<double, 4, 3>;
 using matrix44 = Eigen::Matrix4d;
-struct quaternion {
-    double w_ = 1, x_ = 0, y_ = 0, z_ = 0;
-};
+using quaternion = Eigen::Quaternion<double>;
 using vector6 = Eigen::Matrix<double, 6, 1>;
 using vector7 = Eigen::Matrix<double, 7, 1>;
 using matrix66 = Eigen::Matrix<double, 6, 6>;
@@ -44,6 +43,8 @@ struct WorldCoordinateCovariance : public matrix33 {};
 
 struct TransitionMatrix : public matrix44 {
     using matrix44::matrix44;
+    [[nodiscard]] matrix33 rotation() const noexcept { return this->block<3, 3>(0, 0); }
+    [[nodiscard]] vector3 translation() const noexcept { return vector3((*this)(0, 3), (*this)(1, 3), (*this)(2, 3)); }
 };
 struct WorldToCameraMatrix : public TransitionMatrix {};
 struct CameraToWorldMatrix : public TransitionMatrix {};
@@ -70,14 +71,61 @@ using vector3_vector = std::vector<vector3>;
 #endif
 namespace rgbd_slam::utils {
 [[nodiscard]] double get_depth_quantization(const double depht) noexcept;   // defined from the reference's own text: see Makefile
+// is_covariance_valid<N> (covariances.hpp:13-50): finite; N == 1: non-negative; symmetric in Eigen's isApprox sense
+// (|C - C^T|^2 <= 1e-24 min(|C|^2, |C^T|^2)); selfadjointView<Upper>().ldlt() without a negative pivot (Eigen's diagonally
+// pivoted LDL^T, as oracle/kalman.cpp restates it)
 template <class M>
-bool is_covariance_valid(const M& m)
+bool is_covariance_valid(const M& c, std::string& reason)
 {
-    if (!m.allFinite()) return false;
-    for (Eigen::Index i = 0; i < m.rows(); ++i)
-        for (Eigen::Index j = 0; j < i; ++j)
-            if (std::abs(m(i, j) - m(j, i)) > 1e-9 * (std::abs(m(i, j)) + std::abs(m(j, i)) + 1e-300)) return false;
+    const int N = int(c.rows());
+    if (c.hasNaN() || !c.allFinite()) {
+        reason = "invalid values";
+        return false;
+    }
+    if (N == 1) return c(0, 0) >= 0;
+    double diff2 = 0, n2 = 0;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            const double dd = c(i, j) - c(j, i);
+            diff2 += dd * dd;
+            n2 += c(i, j) * c(i, j);
+        }
+    if (!(diff2 <= 1e-12 * 1e-12 * n2)) {
+        reason = "not symetrical";
+        return false;
+    }
+    std::vector<double> a(size_t(N) * N);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) a[size_t(i) * N + j] = c(std::min(i, j), std::max(i, j));
+    bool neg = false;
+    for (int k = 0; k < N; ++k) {
+        int p = k;
+        double best = std::fabs(a[size_t(k) * N + k]);
+        for (int i = k + 1; i < N; ++i)
+            if (std::fabs(a[size_t(i) * N + i]) > best) best = std::fabs(a[size_t(i) * N + i]), p = i;
+        if (p != k) {
+            for (int j = 0; j < N; ++j) std::swap(a[size_t(k) * N + j], a[size_t(p) * N + j]);
+            for (int i = 0; i < N; ++i) std::swap(a[size_t(i) * N + k], a[size_t(i) * N + p]);
+        }
+        const double dkk = a[size_t(k) * N + k];
+        if (dkk < 0) neg = true;
+        if (std::fabs(dkk) <= 2.2250738585072014e-308) break;
+        for (int i = k + 1; i < N; ++i) {
+            const double l = a[size_t(i) * N + k] / dkk;
+            for (int j = k + 1; j < N; ++j) a[size_t(i) * N + j] -= l * a[size_t(k) * N + j];
+        }
+    }
+    if (neg) {
+        reason = "not positive semi definite";
+        return false;
+    }
     return true;
+}
+template <class M>
+bool is_covariance_valid(const M& c)
+{
+    std::string reason;
+    return is_covariance_valid(c, reason);
 }
 }  // namespace rgbd_slam::utils
 
@@ -142,3 +190,22 @@ class Cylinder {
 using plane_container = std::vector<Plane>;
 using cylinder_container = std::vector<Cylinder>;
 }  // namespace rgbd_slam::features::primitives
+
+
+//   src/features/keypoints/keypoint_handler.hpp, src/features/lines/line_detection.hpp (OpenCV features2d / LSD)  ->  the type names
+//   matches_containers.hpp mentions; nothing on the pose path touches them
+#ifndef RGBDSLAM_FEATURES_KEYPOINTS_KEYPOINTS_HANDLER_HPP
+#define RGBDSLAM_FEATURES_KEYPOINTS_KEYPOINTS_HANDLER_HPP
+#endif
+#ifndef RGBDSLAM_FEATURES_LINES_LINE_DETECTION_HPP
+#define RGBDSLAM_FEATURES_LINES_LINE_DETECTION_HPP
+#endif
+#include "coordinates/point_coordinates.hpp"   // (the real header: keypoint_handler.hpp is how matches_containers.hpp gets it)
+namespace rgbd_slam::features::keypoints {
+struct Keypoint_Handler {};
+struct KeypointsWithIdStruct {};
+}  // namespace rgbd_slam::features::keypoints
+namespace rgbd_slam::features::lines {
+struct line_stub {};
+using line_container = std::vector<line_stub>;
+}  // namespace rgbd_slam::features::lines

@@ -40,6 +40,7 @@ def load():
     lib.orc_quaternion_from_euler.argtypes = [dbl, dbl, dbl, vp]
     lib.orc_residual_count.argtypes = [vp, i32]
     lib.orc_pose_residuals.argtypes = [vp, vp, i32, vp, vp]
+    lib.orc_pose_inliers.argtypes = [vp, vp, vp, i32, vp]
     lib.orc_pose_lm.argtypes = [vp, vp, i32, vp, i32, vp]
     lib.orc_pose_solve.argtypes = [vp, vp, vp, i32, i32, i32, u32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.orc_process_frames.restype = dbl
@@ -158,6 +159,27 @@ def pose_solve(cur_pose, matches, K=(550.0, 550.0, 320.0, 240.0), max_iterations
     return out[0], mask
 
 
+def pose_residuals(matches, x6, K=(550.0, 550.0, 320.0, 240.0)):
+    """Global_Pose_Estimator::operator() as the oracle restates it (features taken as given)."""
+    lib = load()
+    Kc = np.asarray(K, dtype=np.float64)
+    m = np.ascontiguousarray(matches)
+    x = np.ascontiguousarray(x6, dtype=np.float64)
+    out = np.zeros(lib.orc_residual_count(m.ctypes.data, len(m)))
+    lib.orc_pose_residuals(Kc.ctypes.data, m.ctypes.data, len(m), x.ctypes.data, out.ctypes.data)
+    return out
+
+
+def pose_inliers(pose7, matches, K=(550.0, 550.0, 320.0, 240.0)):
+    lib = load()
+    Kc = np.asarray(K, dtype=np.float64)
+    p = np.ascontiguousarray(pose7, dtype=np.float64)
+    m = np.ascontiguousarray(matches)
+    mask = np.zeros(len(m), np.uint8)
+    lib.orc_pose_inliers(Kc.ctypes.data, p.ctypes.data, m.ctypes.data, len(m), mask.ctypes.data)
+    return mask
+
+
 def ref_test_features(true_pose, point_error=5.0, point_outliers=0.0, plane_error=5.0, plane_outliers=-1.0):
     """Scenario builder of tests/test_pose_optimization.cpp. outliers < 0 disables that feature kind."""
     lib = load()
@@ -266,3 +288,107 @@ def ref_rectify_depth(depth, cam2_to_cam1):
     if lib.ref_rectify_depth(d.ctypes.data, d.shape[1], d.shape[0], T.ctypes.data, out.ctypes.data) != 0:
         raise RuntimeError("reference rectify_depth failed")
     return out
+
+
+# ---- the reference's own pose-solve sources, compiled the same way (oracle/_ref/libref_pose.so) ----
+REF_POSE_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_pose.so")
+_ref_pose = None
+
+
+def ref_pose_available():
+    ref_available()          # runs the recipe where /root/reference exists
+    return os.path.exists(REF_POSE_LIB)
+
+
+def _ref_pose_load():
+    global _ref_pose
+    if _ref_pose is None:
+        lib = C.CDLL(REF_POSE_LIB)
+        vp, i32 = C.c_void_p, C.c_int
+        lib.ref_pose_solve.argtypes = [vp, vp, i32, vp, vp, vp]
+        lib.ref_pose_base.argtypes = [vp, vp]
+        lib.ref_pose_residuals.argtypes = [vp, i32, vp, vp]
+        lib.ref_pose_lm.argtypes = [vp, vp, i32, vp]
+        lib.ref_pose_inliers.argtypes = [vp, vp, i32, vp]
+        _ref_pose = lib
+    return _ref_pose
+
+
+def ref_pose_solve(cur_pose, matches):
+    """Pose_Optimization::compute_optimized_pose of the REFERENCE (MAKE_DETERMINISTIC: thread-local mt19937 from seed 0).
+    -> (ok, pose7, cov 6x6, inlier mask)"""
+    lib = _ref_pose_load()
+    cur = np.ascontiguousarray(cur_pose, dtype=np.float64)
+    m = np.ascontiguousarray(matches)
+    pose, cov, mask = np.zeros(7), np.zeros(36), np.zeros(len(m), np.uint8)
+    ok = lib.ref_pose_solve(cur.ctypes.data, m.ctypes.data, len(m), pose.ctypes.data, cov.ctypes.data, mask.ctypes.data)
+    return bool(ok), pose, cov.reshape(6, 6), mask
+
+
+def ref_pose_base(pose7):
+    """The pose as a utils::PoseBase of the reference holds it (quaternion normalised by set_parameters), iterated to a fixed
+    point: what a caller of compute_optimized_pose passes in."""
+    lib = _ref_pose_load()
+    p = np.ascontiguousarray(pose7, dtype=np.float64).copy()
+    for _ in range(8):
+        q = np.zeros(7)
+        lib.ref_pose_base(p.ctypes.data, q.ctypes.data)
+        if np.array_equal(p, q):
+            return p
+        p = q
+    return p
+
+
+def ref_pose_residuals(matches, x6):
+    lib = _ref_pose_load()
+    m = np.ascontiguousarray(matches)
+    x = np.ascontiguousarray(x6, dtype=np.float64)
+    out = np.zeros(3 * len(m))
+    n = lib.ref_pose_residuals(m.ctypes.data, len(m), x.ctypes.data, out.ctypes.data)
+    return out[:n]
+
+
+def ref_pose_lm(cur_pose, matches):
+    lib = _ref_pose_load()
+    cur = np.ascontiguousarray(cur_pose, dtype=np.float64)
+    m = np.ascontiguousarray(matches)
+    pose = np.zeros(7)
+    ok = lib.ref_pose_lm(cur.ctypes.data, m.ctypes.data, len(m), pose.ctypes.data)
+    return bool(ok), pose
+
+
+def ref_pose_inliers(pose7, matches):
+    lib = _ref_pose_load()
+    p = np.ascontiguousarray(pose7, dtype=np.float64)
+    m = np.ascontiguousarray(matches)
+    mask = np.zeros(len(m), np.uint8)
+    lib.ref_pose_inliers(p.ctypes.data, m.ctypes.data, len(m), mask.ctypes.data)
+    return mask
+
+
+def stable_plane_normals(matches):
+    """The reference re-normalises a plane's normal in every PlaneCoordinates constructor, COPY constructor and assignment
+    (plane_coordinates.hpp:19-38), so a normal travels through an unknown number of normalisations before it is used, and
+    x / |x| need not be idempotent in floating point (it can even alternate between two neighbours). The library and the oracle
+    normalise once. For a comparison that does not depend on the number of copies, plane normals are moved to a fixed point of
+    the normalisation first (nudged by an ulp where the iteration alternates)."""
+    m = np.array(matches, copy=True)
+    for f in m:
+        if f["type"] != abi.RS_FEAT_PLANE:
+            continue
+        for key in ("obs", "map"):
+            v = f[key][:3].copy()
+            for attempt in range(64):
+                for _ in range(8):
+                    w = v / np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+                    if np.array_equal(w, v):
+                        break
+                    v = w
+                else:
+                    v[attempt % 3] = np.nextafter(v[attempt % 3], 2.0)
+                    continue
+                break
+            else:
+                raise RuntimeError("no fixed point of the normalisation")
+            f[key][:3] = v
+    return m
