@@ -74,6 +74,7 @@ struct rs_cape_ctx {
     double fx, fy, cx, cy;
     double* d_kx = nullptr;
     double* d_ky = nullptr;
+    float* d_pre = nullptr;   // rectify_depth: the factor tables as floats, [W] then [H]
     float* d_depth = nullptr;
     rs_cape_outputs d_out{};       // device pointers sized for max_batch
     // Cylinder-RANSAC draw tables (canonical doubles of mt19937(seed)), one slot per recently used seed. A table is copied
@@ -98,7 +99,6 @@ struct rs_cape_ctx {
     bool rectify = false;          // rs_cape_set_rectification: rectify_depth in front of K1
     RectifyParams rect{};
     float* d_rect = nullptr;               // max_batch x H x W rectified depth
-    unsigned long long* d_keys = nullptr;  // max_batch x H x W scatter keys
     int n_uniforms = 0;
     CellFitParams fit{};
     SegmentParams seg{};
@@ -316,7 +316,7 @@ int run_device_impl(rs_cape_ctx* c, const float* depth_dev, int batch, uint32_t 
         if (fit) {
             RectifyParams rp = c->rect;
             rp.batch = batch;
-            if ((rc = launch_rectify_depth(rp, depth_dev, c->d_keys + scratch_frame * size_t(c->W) * c->H, rect, stream)) != RS_OK)
+            if ((rc = launch_rectify_depth(rp, depth_dev, rect, stream)) != RS_OK)
                 return rc;
         }
         depth_dev = rect;   // a segmentation-only call reads what the preceding fit call rectified
@@ -416,6 +416,7 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaSetDevice(c->device);
     cudaFree(c->d_kx);
     cudaFree(c->d_ky);
+    cudaFree(c->d_pre);
     cudaFree(c->d_depth);
     cudaFree(c->d_out.cells);
     cudaFree(c->d_out.plane_grid);
@@ -436,7 +437,6 @@ void rs_cape_destroy(rs_cape_ctx* c)
     cudaFree(c->d_scratch);
     cudaFree(c->d_depth16);
     cudaFree(c->d_rect);
-    cudaFree(c->d_keys);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->fit_done) cudaEventDestroy(c->fit_done);
     if (c->streamed) cudaEventDestroy(c->streamed);
@@ -488,9 +488,18 @@ int rs_cape_set_rectification(rs_cape_ctx* c, const double* cam2_to_cam1, int en
     if (enable) {
         const size_t px = size_t(c->max_batch) * c->W * c->H;
         if (!c->d_rect) RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_rect), sizeof(float) * px));
-        if (!c->d_keys) RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_keys), sizeof(unsigned long long) * px));
         c->rect.W = c->W, c->rect.H = c->H;
-        c->rect.kx = c->d_kx, c->rect.ky = c->d_ky;
+        if (!c->d_pre) {
+            // _Xpre / _Ypre are float images in the reference: the FP64 factors rounded once
+            std::vector<double> kx, ky;
+            backprojection_factors(c, kx, ky);
+            std::vector<float> pre;
+            for (int i = 0; i < c->W; ++i) pre.push_back(static_cast<float>(kx[i]));
+            for (int i = 0; i < c->H; ++i) pre.push_back(static_cast<float>(ky[i]));
+            RS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_pre), sizeof(float) * pre.size()));
+            RS_CUDA_CHECK(cudaMemcpy(c->d_pre, pre.data(), sizeof(float) * pre.size(), cudaMemcpyHostToDevice));
+        }
+        c->rect.preX = c->d_pre, c->rect.preY = c->d_pre + c->W;
         c->rect.fx = c->fx, c->rect.fy = c->fy, c->rect.cx = c->cx, c->rect.cy = c->cy;
         for (int i = 0; i < 12; ++i) c->rect.T[i] = cam2_to_cam1[i];
     }
@@ -510,7 +519,7 @@ int rs_cape_rectify(rs_cape_ctx* c, const float* depth_host, int batch, float* r
     RS_CUDA_CHECK(cudaMemcpyAsync(c->d_depth, depth_host, sizeof(float) * px, cudaMemcpyHostToDevice, c->stream));
     RectifyParams rp = c->rect;
     rp.batch = batch;
-    const int rc = launch_rectify_depth(rp, c->d_depth, c->d_keys, c->d_rect, c->stream);
+    const int rc = launch_rectify_depth(rp, c->d_depth, c->d_rect, c->stream);
     if (rc != RS_OK) return rc;
     RS_CUDA_CHECK(cudaMemcpyAsync(rectified_host, c->d_rect, sizeof(float) * px, cudaMemcpyDeviceToHost, c->stream));
     RS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -519,14 +528,14 @@ int rs_cape_rectify(rs_cape_ctx* c, const float* depth_host, int batch, float* r
 
 int rs_cape_rectify_device(rs_cape_ctx* c, const float* depth_dev, int batch, float* rectified_dev, void* stream)
 {
-    if (!c || !depth_dev || !rectified_dev || batch <= 0 || batch > c->max_batch || !c->d_keys) {
+    if (!c || !depth_dev || !rectified_dev || batch <= 0 || batch > c->max_batch || !c->d_rect) {
         set_last_error("rs_cape_rectify_device: invalid argument, or rs_cape_set_rectification has not been called");
         return RS_ERR_INVALID_ARG;
     }
     RS_CUDA_CHECK(cudaSetDevice(c->device));
     RectifyParams rp = c->rect;
     rp.batch = batch;
-    return launch_rectify_depth(rp, depth_dev, c->d_keys, rectified_dev, static_cast<cudaStream_t>(stream));
+    return launch_rectify_depth(rp, depth_dev, rectified_dev, static_cast<cudaStream_t>(stream));
 }
 
 int rs_cape_stream_wait_fit(rs_cape_ctx* c, void* stream)
@@ -589,7 +598,7 @@ static int run_host_impl(rs_cape_ctx* c, const float* depth_host, const uint16_t
         RS_CUDA_CHECK(cudaEventRecord(landed, c->h2d_stream));
         RS_CUDA_CHECK(cudaStreamWaitEvent(c->stream, landed, 0));
         if (depth16_host) {
-            depth_u16_to_f32_kernel<<<148 * 8, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_depth16 + o * px),
+            depth_u16_to_f32_kernel<<<sm_count() * 8, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_depth16 + o * px),
                                                                    reinterpret_cast<float4*>(c->d_depth + o * px), n * px / 8, alpha);
             RS_LAUNCH_CHECK();
         }

@@ -500,8 +500,8 @@ int launch_variant(const CUtensorMap& tmap, const CellFitParams& prm, rs_cell_ou
     CellFitParams p = prm;
     p.items_per_strip = (prm.hc + CELLS_PER_ITEM - 1) / CELLS_PER_ITEM;   // items (8 cells) per cell row
     p.total_items = prm.batch * prm.vc * p.items_per_strip;
-    // persistent grid: one CTA per resident slot (148 SMs x RS_K1_MIN_CTAS), fewer when the batch is small
-    const int slots = 148 * RS_K1_MIN_CTAS;
+    // persistent grid: one CTA per resident slot (SMs x RS_K1_MIN_CTAS), fewer when the batch is small
+    const int slots = sm_count() * RS_K1_MIN_CTAS;
     const int grid = std::min(slots, (p.total_items + WARPS - 1) / WARPS);
     kernel<<<grid, WARPS * 32, smem, stream>>>(tmap, p, cells);
     RS_LAUNCH_CHECK();

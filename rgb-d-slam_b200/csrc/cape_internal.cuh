@@ -52,13 +52,13 @@ struct SegmentBuffers {
 
 struct RectifyParams {
     int W, H, batch;
-    const double* kx;   // [W] same back-projection factors as K1 (cast to float per use: _Xpre / _Ypre are float images)
-    const double* ky;   // [H]
+    const float* preX;  // [W] the reference's _Xpre row: K1's back-projection factors as floats (init_matrices, :147-173)
+    const float* preY;  // [H] _Ypre column
     double fx, fy, cx, cy;   // camera 1 intrinsics (the reference projects AND back-projects with camera 1's)
     double T[12];            // first three rows of the camera-2 -> camera-1 transformation, row-major
 };
-// keys: batch*H*W 64-bit scratch; out: batch*H*W floats
-int launch_rectify_depth(const RectifyParams& prm, const float* depth, unsigned long long* keys, float* out, cudaStream_t stream);
+// out: batch*H*W floats (also the scratch the winners are found in)
+int launch_rectify_depth(const RectifyParams& prm, const float* depth, float* out, cudaStream_t stream);
 
 int launch_cape_segment(const SegmentParams& prm, const SegmentBuffers& buf, cudaStream_t stream);
 int cape_segment_validate(int hc, int vc, int cell);   // RS_OK, or RS_ERR_INVALID_ARG + rs_last_error() for a grid the kernel cannot take

@@ -62,6 +62,20 @@ struct SmemOptIn {
     }
 };
 
+// SM count of the current device (grids are sized in multiples of it); 148 on a B200, read once per device.
+inline int sm_count()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 // ---- constants of the reference (src/parameters.hpp) ---------------------------------------
 // depth quantisation model, parameters.hpp:16-18 / covariances.cpp:12-19
 __host__ __device__ inline double depth_quantization(const double depth)

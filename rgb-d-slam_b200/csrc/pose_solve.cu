@@ -978,7 +978,7 @@ int pose_work_times(const PoseBuffers& buf, float* ransac_phase_ms, float* total
 
 int launch_pose_export_normals(const PoseBuffers& buf, const PoseLaunch& prm, double* normals, cudaStream_t stream)
 {
-    pose_export_normals_kernel<<<148 * 4, 256, 0, stream>>>(prm, buf.max_matches, normals);
+    pose_export_normals_kernel<<<sm_count() * 4, 256, 0, stream>>>(prm, buf.max_matches, normals);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }

@@ -5,79 +5,152 @@
 //           camera-2 -> camera-1 transformation, projected with camera 1's intrinsics and written to the pixel it falls in;
 //           the serial row-major scan of the MAKE_DETERMINISTIC build makes the LAST source pixel in raster order win.
 //
-// The scatter has a defined winner, so it is order-free on the GPU: R1 does an atomicMax of the 64-bit key
-// (source raster index + 1) << 32 | float bits of the new depth per destination pixel, R2 keeps the low word of each key
-// (0 where nothing landed). Traffic per pixel: 4 B read + 8 B key RMW (+ 8 B memset) in R1, 8 B read + 4 B write in R2.
+// The scatter has a defined winner, so it is order-free on the GPU. The winner of a destination pixel is found IN the output
+// image itself: R1 does a 32-bit atomicMax of a key ordered like the source raster index, (row << 16 | column) + 1, per
+// destination word, R2 replaces every winning key by the depth that source pixel projects to - the same device function
+// evaluates that depth wherever it is needed, so the value R2 writes is bit for bit the one the scatter would have carried.
+// Round 1 carried it in a 64-bit key in a scratch image twice the size of the batch (8 B per pixel of HBM; memset 8 B + key
+// read-modify-write 16 B + key read 8 B + result 4 B of traffic per pixel); now: zero fill 4 B, depth 4 B, a 4-byte reduction
+// in L2, key read 4 B + gathered depth 4 B + result 4 B, and no scratch.
 // Compiled with -fmad=false: the pixel a point falls in is a floor() of FP64 arithmetic that must round as the reference's.
+#include <algorithm>
+
 #include "cape_internal.cuh"
 
 namespace rs {
 
 namespace {
 
-__global__ void __launch_bounds__(256) rectify_scatter_kernel(const float4* __restrict__ depth, unsigned long long* __restrict__ keys,
+// (double)f without the conversion pipe: F2F runs at a quarter of the FP64 rate on sm_100 (profiles/r01h_microbench_issue_cost.txt)
+// and three widenings per pixel kept the XU pipe 62 % busy. For a zero or a normal finite float the double has the same sign,
+// the exponent rebiased by 896 and the 23 mantissa bits on top of the 52: three integer instructions. Anything else
+// (subnormal, infinity, NaN - not produced by depth images) takes the conversion.
+__device__ __forceinline__ double widen(const float f)
+{
+    const unsigned b = __float_as_uint(f), a = b & 0x7fffffffu;
+    if (a != 0u && a - 0x00800000u >= 0x7f000000u) return static_cast<double>(f);
+    const unsigned hi = (b & 0x80000000u) | ((a >> 3) + (a ? 0x38000000u : 0u));
+    return __hiloint2double(static_cast<int>(hi), static_cast<int>(b << 29));
+}
+
+// The depth a source pixel carries to camera 1 (depth_map_transformation.cpp:52-58,73-75): z of T * (preX z, preY z, z, 1)
+__device__ __forceinline__ double rectify_depth_of(const RectifyParams& prm, const double ox, const double oy, const double oz)
+{
+    return ((prm.T[8] * ox + prm.T[9] * oy) + prm.T[10] * oz) + prm.T[11];
+}
+
+// One source pixel through depth_map_transformation.cpp:48-77: the destination pixel it falls in. false: it is dropped.
+// to_screen_coordinates multiplies by the whole intrinsics matrix, (fx px + 0 py) + cx pz: a finite py leaves fx px as it is
+// (a +-0 is added), a non-finite one makes sy NaN or out of range as well, so the zero terms are left out; floor + the
+// unsigned cast + the range test are one conversion rounding down (it saturates, NaN gives 0: both fail 0 < i < size).
+__device__ __forceinline__ bool rectify_project(const RectifyParams& prm, const float preX, const float preY, const float z,
+                                                unsigned& dst)
+{
+    const double ox = widen(preX * z), oy = widen(preY * z), oz = widen(z);
+    const double px = ((prm.T[0] * ox + prm.T[1] * oy) + prm.T[2] * oz) + prm.T[3];
+    const double py = ((prm.T[4] * ox + prm.T[5] * oy) + prm.T[6] * oz) + prm.T[7];
+    const double pz = rectify_depth_of(prm, ox, oy, oz);
+    const double inv = 1.0 / pz;
+    const double sx = inv * (prm.fx * px + prm.cx * pz);
+    const double sy = inv * (prm.fy * py + prm.cy * pz);
+    if (sx != sx || sy != sy) return false;
+    const int ix = __double2int_rd(sx), iy = __double2int_rd(sy);
+    if (!(ix > 0 && iy > 0 && ix < prm.W && iy < prm.H)) return false;
+    dst = unsigned(iy) * unsigned(prm.W) + unsigned(ix);
+    return true;
+}
+
+// Winner keys order source pixels by raster position and unpack without a division: (row << 16 | column) + 1.
+// R1: winners[dst] = max key over the source pixels landing on dst. `winners` is the output image, zeroed. One block row of the
+// grid per frame of the group (blockIdx.y), whole image rows per block (no per-pixel index arithmetic).
+__global__ void __launch_bounds__(512) rectify_scatter_kernel(const float* __restrict__ depth, unsigned* __restrict__ winners,
                                                              const RectifyParams prm)
 {
-    const int W = prm.W, H = prm.H;
-    const size_t perFrame4 = size_t(W) * H / 4;
-    const size_t total4 = perFrame4 * prm.batch;
-    for (size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x; q < total4; q += size_t(gridDim.x) * blockDim.x) {
-        const float4 v = __ldg(depth + q);
-        const size_t b = q / perFrame4;
-        const unsigned pix0 = unsigned(q - b * perFrame4) * 4u;   // raster index of the first of the four pixels
-        const int row = int(pix0 / unsigned(W)), col0 = int(pix0 - unsigned(row) * unsigned(W));
-        const float preY = static_cast<float>(prm.ky[row]);
-        unsigned long long* frameKeys = keys + b * size_t(W) * H;
-        const float zz[4] = {v.x, v.y, v.z, v.w};
+    const int W = prm.W, W4 = W >> 2;
+    const size_t frame_px = size_t(W) * prm.H;
+    const float* src = depth + blockIdx.y * frame_px;
+    unsigned* frame = winners + blockIdx.y * frame_px;
+    const int per_block = blockDim.x / W4 > 0 ? blockDim.x / W4 : 1;      // image rows a block covers per trip
+    const int lrow = threadIdx.x / W4, c0 = threadIdx.x - lrow * W4;      // once per thread
+    const int stride = blockDim.x < W4 ? blockDim.x : W4;                 // threads along a row
+    for (int row = blockIdx.x * per_block + lrow; row < prm.H && lrow < per_block; row += gridDim.x * per_block) {
+        const float preY = __ldg(prm.preY + row);
+        const float* line = src + size_t(row) * W;
+        // a warp instruction covers 32 CONSECUTIVE pixels: their destinations are (mostly) consecutive words, so the L2 sees
+        // a few sectors per reduction instead of one per pixel (a float4 per lane measured 1.0 sector per pixel)
+        for (int col = c0; col < W; col += 4 * stride) {
+            float zz[4], pre[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float z = zz[t];
-            if (!(z > 0.f)) continue;
-            const float preX = static_cast<float>(prm.kx[col0 + t]);
-            const double ox = static_cast<double>(preX * z), oy = static_cast<double>(preY * z), oz = static_cast<double>(z);
-            const double px = ((prm.T[0] * ox + prm.T[1] * oy) + prm.T[2] * oz) + prm.T[3];
-            const double py = ((prm.T[4] * ox + prm.T[5] * oy) + prm.T[6] * oz) + prm.T[7];
-            const double pz = ((prm.T[8] * ox + prm.T[9] * oy) + prm.T[10] * oz) + prm.T[11];
-            const double inv = 1.0 / pz;
-            const double sx = inv * ((prm.fx * px + 0.0 * py) + prm.cx * pz);
-            const double sy = inv * ((0.0 * px + prm.fy * py) + prm.cy * pz);
-            if (sx != sx || sy != sy) continue;
-            const double fxs = floor(sx), fys = floor(sy);
-            if (!(fxs > 0.0 && fys > 0.0 && fxs < double(W) && fys < double(H))) continue;
-            const unsigned dst = unsigned(int(fys)) * unsigned(W) + unsigned(int(fxs));
-            const unsigned long long key =
-                    (static_cast<unsigned long long>(pix0 + unsigned(t) + 1u) << 32) | __float_as_uint(static_cast<float>(pz));
-            atomicMax(frameKeys + dst, key);
+            for (int t = 0; t < 4; ++t) {
+                const int cc = col + t * stride;
+                zz[t] = cc < W ? line[cc] : 0.f;
+                pre[t] = cc < W ? __ldg(prm.preX + cc) : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float z = zz[t];
+                if (!(z > 0.f)) continue;
+                unsigned dst;
+                if (rectify_project(prm, pre[t], preY, z, dst))
+                    atomicMax(frame + dst, (unsigned(row) << 16 | unsigned(col + t * stride)) + 1u);
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(256) rectify_resolve_kernel(const ulonglong2* __restrict__ keys, float2* __restrict__ out,
-                                                             const size_t n2)
+// R2, in place on the output image: winning key -> the depth that source pixel projects to; 0 (nothing landed) -> +0.0f
+__global__ void __launch_bounds__(256) rectify_resolve_kernel(const float* __restrict__ depth, uint4* __restrict__ image,
+                                                             const RectifyParams prm)
 {
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += size_t(gridDim.x) * blockDim.x) {
-        const ulonglong2 k = keys[i];
-        float2 o;
-        o.x = __uint_as_float(static_cast<unsigned>(k.x));   // a key of 0 (nothing landed) gives +0.0f
-        o.y = __uint_as_float(static_cast<unsigned>(k.y));
-        out[i] = o;
+    const int W = prm.W;
+    const size_t frame_px = size_t(W) * prm.H;
+    const size_t perFrame4 = frame_px / 4;
+    const float* frame = depth + blockIdx.y * frame_px;
+    uint4* img = image + blockIdx.y * perFrame4;
+    for (size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x; q < perFrame4; q += size_t(gridDim.x) * blockDim.x) {
+        const uint4 k = img[q];
+        if ((k.x | k.y | k.z | k.w) == 0u) continue;   // the zero fill is already the answer
+        unsigned kk[4] = {k.x, k.y, k.z, k.w};
+        // the four gathers first (independent loads in flight together), then the arithmetic
+        float z[4], pxf[4], pyf[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const unsigned key = kk[t] - 1u, row = key >> 16, col = key & 0xffffu;
+            const bool hit = kk[t] != 0u;
+            z[t] = hit ? frame[size_t(row) * W + col] : 0.f;
+            pxf[t] = hit ? __ldg(prm.preX + col) : 0.f;
+            pyf[t] = hit ? __ldg(prm.preY + row) : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (kk[t] == 0u) continue;
+            const double pz = rectify_depth_of(prm, widen(pxf[t] * z[t]), widen(pyf[t] * z[t]), widen(z[t]));
+            kk[t] = __float_as_uint(static_cast<float>(pz));
+        }
+        img[q] = make_uint4(kk[0], kk[1], kk[2], kk[3]);
     }
 }
 
 }  // namespace
 
-int launch_rectify_depth(const RectifyParams& prm, const float* depth, unsigned long long* keys, float* out, cudaStream_t stream)
+int launch_rectify_depth(const RectifyParams& prm, const float* depth, float* out, cudaStream_t stream)
 {
-    const size_t px = size_t(prm.W) * prm.H * prm.batch;
-    if ((size_t(prm.W) * prm.H) % 4 != 0) {
-        set_last_error("rectify_depth: width * height must be a multiple of 4");
+    const size_t frame_px = size_t(prm.W) * prm.H;
+    if (prm.W % 4 != 0 || prm.W >= 65536 || prm.H >= 65535) {
+        set_last_error("rectify_depth: the width must be a multiple of 4, and width and height below 65535");
         return RS_ERR_INVALID_ARG;
     }
-    RS_CUDA_CHECK(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * px, stream));
-    const int grid = 148 * 8;
-    rectify_scatter_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(depth), keys, prm);
+    // One pass over the whole batch: walking it in groups of frames that fit the L2 (so that DRAM would see the depth once and
+    // the result once) measured slower at every group size - 0.79 ms per 256 frames at 48 MB groups against 0.72 - the
+    // kernels are bound by the FP64 pipe (R1) and by the latency of the gather (R2), not by DRAM: profiles/README.md
+    RS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * frame_px * prm.batch, stream));
+    const int blocks = sm_count() * 8;
+    const dim3 grid((blocks + prm.batch - 1) / prm.batch, prm.batch);
+    // whole image rows per block: a multiple of the row's float4 count when that fits a block
+    const int w4 = prm.W / 4, threads = w4 <= 512 ? w4 * std::max(1, 256 / w4) : 256;
+    rectify_scatter_kernel<<<grid, threads, 0, stream>>>(depth, reinterpret_cast<unsigned*>(out), prm);
     RS_LAUNCH_CHECK();
-    rectify_resolve_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const ulonglong2*>(keys), reinterpret_cast<float2*>(out), px / 2);
+    rectify_resolve_kernel<<<grid, 256, 0, stream>>>(depth, reinterpret_cast<uint4*>(out), prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }
