@@ -48,6 +48,9 @@ class LevenbergMarquardt {
         const oracle::ResidualFn fn = [&](const double xx[6], double* out) {
             Matrix<double, 6, 1> xv;
             for (int i = 0; i < 6; ++i) xv(i) = xx[i];
+            // Global_Pose_Estimator leaves a feature's entries untouched when its distance has a NaN: they keep what the LM's
+            // buffer held (Eigen hands the functor its own work vectors), so the buffer goes in as well as out
+            for (int i = 0; i < m; ++i) fvec(i) = out[i];
             functor_(xv, fvec);
             for (int i = 0; i < m; ++i) out[i] = fvec(i);
         };

@@ -167,6 +167,62 @@ int ref_pose_lm(const double* cur_pose7, const rs_match* m, int n, double* out_p
     return ok ? 1 : 0;
 }
 
+// get_optimization_coefficient_from_pose / get_pose_from_optimization_coefficients (levenberg_marquardt_functors.cpp:74-86)
+void ref_pose_coefficients(const double* pose7, double* x6)
+{
+    const utils::PoseBase p(vector3(pose7[0], pose7[1], pose7[2]), quaternion(pose7[3], pose7[4], pose7[5], pose7[6]));
+    const vector6 x = pose_optimization::get_optimization_coefficient_from_pose(p);
+    for (int k = 0; k < 6; ++k) x6[k] = x(k);
+}
+void ref_pose_from_coefficients(const double* x6, double* pose7)
+{
+    vector6 x;
+    for (int k = 0; k < 6; ++k) x(k) = x6[k];
+    store_pose(pose_optimization::get_pose_from_optimization_coefficients(x), pose7);
+}
+
+// Diagnostic: the oracle's LM driven by the REFERENCE functor from cur_pose7, with the oracle's own residual function evaluated
+// beside it at every point the LM visits. Returns the number of evaluations whose residual vectors differ in any bit;
+// first_x6 / first_pair = the first such point and (oracle value, reference value) of its first differing residual.
+int ref_pose_trace_lm(const double* cur_pose7, const rs_match* m, int n, double* first_x6, double* first_pair, int* first_index)
+{
+    load_parameters();
+    const matches_containers::match_container matches = build_features(m, n);
+    size_t parts = 0;
+    for (const auto& f : matches) parts += f->get_feature_part_count();
+    const pose_optimization::Global_Pose_Estimator estimator(parts, matches);
+    std::vector<rs_match> feats(m, m + n);
+    std::vector<double> mine(parts);
+    vectorxd theirs(parts);
+    int differing = 0;
+    const oracle::ResidualFn fn = [&](const double* xx, double* out) {
+        Eigen::Matrix<double, 6, 1> x;
+        for (int k = 0; k < 6; ++k) x(k) = xx[k];
+        estimator(x, theirs);
+        oracle::pose_residuals(oracle::Intrinsics{}, feats, xx, mine.data());
+        bool bad = false;
+        for (size_t k = 0; k < parts; ++k) {
+            out[k] = theirs(k);
+            if (mine[k] != theirs(k) && !bad) {
+                bad = true;
+                if (differing == 0) {
+                    for (int j = 0; j < 6; ++j) first_x6[j] = xx[j];
+                    first_pair[0] = mine[k], first_pair[1] = theirs(k);
+                    *first_index = int(k);
+                }
+            }
+        }
+        differing += bad;
+    };
+    oracle::Pose7 start;
+    for (int k = 0; k < 3; ++k) start.t[k] = cur_pose7[k];
+    for (int k = 0; k < 4; ++k) start.q[k] = cur_pose7[3 + k];
+    double x[6];
+    oracle::coefficients_from_pose(start, x);
+    oracle::lm_minimize(fn, int(parts), x, 400);
+    return differing;
+}
+
 // IOptimizationFeature::is_inlier of every match under pose7 (get_features_inliers_outliers, pose_optimization.cpp:33-72)
 void ref_pose_inliers(const double* pose7, const rs_match* m, int n, uint8_t* inlier_mask)
 {

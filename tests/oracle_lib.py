@@ -310,6 +310,9 @@ def _ref_pose_load():
         lib.ref_pose_residuals.argtypes = [vp, i32, vp, vp]
         lib.ref_pose_lm.argtypes = [vp, vp, i32, vp]
         lib.ref_pose_inliers.argtypes = [vp, vp, i32, vp]
+        lib.ref_pose_trace_lm.argtypes = [vp, vp, i32, vp, vp, vp]
+        lib.ref_pose_coefficients.argtypes = [vp, vp]
+        lib.ref_pose_from_coefficients.argtypes = [vp, vp]
         _ref_pose = lib
     return _ref_pose
 
@@ -326,17 +329,15 @@ def ref_pose_solve(cur_pose, matches):
 
 
 def ref_pose_base(pose7):
-    """The pose as a utils::PoseBase of the reference holds it (quaternion normalised by set_parameters), iterated to a fixed
-    point: what a caller of compute_optimized_pose passes in."""
+    """The pose as utils::PoseBase(position, orientation) of the reference holds it: set_parameters normalises the quaternion
+    (pose.cpp:16-22). ref_pose_solve / ref_pose_lm build exactly one PoseBase from the pose they are given, so the oracle has
+    to be handed ref_pose_base(pose) for the same problem. (Iterating to a fixed point does not work: q / |q| can alternate
+    between two neighbouring values for ever - problem 1097 of tools/sweep_reference_pose_build.py does.)"""
     lib = _ref_pose_load()
-    p = np.ascontiguousarray(pose7, dtype=np.float64).copy()
-    for _ in range(8):
-        q = np.zeros(7)
-        lib.ref_pose_base(p.ctypes.data, q.ctypes.data)
-        if np.array_equal(p, q):
-            return p
-        p = q
-    return p
+    p = np.ascontiguousarray(pose7, dtype=np.float64)
+    q = np.zeros(7)
+    lib.ref_pose_base(p.ctypes.data, q.ctypes.data)
+    return q
 
 
 def ref_pose_residuals(matches, x6):

@@ -9,8 +9,9 @@ LM: the RANSAC loop with its early stop and overload rule, the std::shuffle subs
 under MAKE_DETERMINISTIC), the residual functor, the three is_inlier tests, the final re-optimisation, the per-feature random
 variations and the 100-solve Monte-Carlo covariance - BIT FOR BIT: status, inlier mask, pose and the 6 x 6 covariance.
 
-Inputs are made independent of how many times the reference copies (= re-normalises) a value on its way in: the start pose goes
-through utils::PoseBase, plane normals sit on a fixed point of x / |x| (oracle_lib.stable_plane_normals).
+Inputs are made independent of how many times the reference copies (= re-normalises) a value on its way in: the oracle gets the
+start pose as the one utils::PoseBase the reference entry builds holds it, plane normals sit on a fixed point of x / |x|
+(oracle_lib.stable_plane_normals).
 Skipped when the library has not been built (no /root/reference at build time)."""
 import numpy as np
 import pytest
@@ -24,9 +25,8 @@ pytestmark = pytest.mark.skipif(not ol.ref_pose_available(), reason="oracle/_ref
 
 def compare(guess, matches, expect_ok=None):
     m = ol.stable_plane_normals(matches)
-    cur = ol.ref_pose_base(guess)
-    ok, pose, cov, mask = ol.ref_pose_solve(cur, m)
-    out, omask = ol.pose_solve(cur, m, seed=0)      # RS_RNG_REFERENCE semantics: one mt19937 stream from seed 0
+    ok, pose, cov, mask = ol.ref_pose_solve(guess, m)                  # builds one PoseBase from the guess
+    out, omask = ol.pose_solve(ol.ref_pose_base(guess), m, seed=0)     # RS_RNG_REFERENCE semantics: one mt19937 stream from seed 0
     assert ok == (out["status"] == 1)
     if expect_ok is not None:
         assert ok == expect_ok
@@ -78,12 +78,10 @@ def test_residual_functor_and_inlier_tests():
     for i in range(6):
         truth, guess, matches = rs.synth.pose_correspondences(i, n_points=50, n_planes=6, n_points2d=20)
         m = ol.stable_plane_normals(matches)
-        cur = ol.ref_pose_base(guess)
-        ok, pose = ol.ref_pose_lm(cur, m)
+        ok, pose = ol.ref_pose_lm(guess, m)
         assert ok
-        out, _ = ol.pose_solve(cur, m, seed=0, max_iterations=1, n_variance=0, subsets=None)
         # inlier tests of every feature under the reference's own LM result and under the true pose
-        for p in (pose, ol.ref_pose_base(truth)):
+        for p in (pose, truth):
             want = ol.ref_pose_inliers(p, m)
             got = ol.pose_inliers(p, m)
             assert np.array_equal(want, got)
