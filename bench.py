@@ -174,10 +174,34 @@ def cpu_port_frames_per_s(wl, depth, cur, matches, n, n_threads, frames=None):
     return B / sec, sec, B
 
 
+def cpu_compiled_reference_frames_per_s(wl, depth, cur, matches, n, frames=2):
+    """Informational: the reference's OWN CAPE and pose-solve translation units as oracle/ref_shim compiles them
+    (oracle/_ref/libref_cape.so + libref_pose.so, shipped as files), one host thread, `frames` frames. Those builds exist to pin
+    the oracle bit for bit; their stand-in Eigen (an eager matrix class on the heap) makes them several times slower than the
+    restated port, so they are NOT the CPU baseline - timing them only shows that the port is the faster (conservative) arm."""
+    if wl.W != 640 or wl.H != 480 or wl.cell != 20 or wl.hypotheses != 119:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    if not (os.path.exists(ol.REF_LIB) and os.path.exists(ol.REF_POSE_LIB)):
+        return None
+    frames = min(frames, len(depth))
+    t0 = time.perf_counter()
+    for b in range(frames):
+        ol.ref_cape_run(depth[b])
+        ol.ref_pose_solve(cur[b], matches[b][:n[b]])
+    sec = time.perf_counter() - t0
+    return {"value_1_thread": frames / sec, "frames": frames, "seconds": sec,
+            "note": "compiled reference sources against stand-in third-party headers (correctness pin, see DESIGN.md section 2); "
+                    "slower than the restated port timed above, hence not used as the baseline"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path. The reference binary cannot be built
     (Eigen / OpenCV C++ / TBB / boost / flann absent, no network), so this is the restated oracle, all host threads
-    over the frame loop (the reference's TBB build parallelises the RANSAC / variance loops instead).
+    over the frame loop (the reference's TBB build parallelises the RANSAC / variance loops instead). The reference's own
+    translation units do compile against stand-in third-party headers (oracle/_ref): that build pins the oracle bit for bit
+    but runs several times slower than the port (heap-allocating stand-in matrices), so timing it would flatter the GPU arm.
     Protocol: >= 10 warm-up frames, then `steps` timed samples whose MEDIAN gives the value, >= 100 timed
     frames in total; a sample = `sample` frames of the arm's workload, sized so that the run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
@@ -753,6 +777,12 @@ def main():
                "sample": "%d frames of one step, frame loop over %d host threads (%.2f s); 1 thread on %d frames: %.1f frames/s"
                          % (nf, threads, sec_all, nf1, fps_1),
                "value_1_thread": fps_1}
+        try:
+            ref_build = cpu_compiled_reference_frames_per_s(wl, depth, cur, matches, n)
+        except Exception as e:   # informational leg: never fails the bench
+            ref_build = {"error": str(e)[:200]}
+        if ref_build:
+            cpu["compiled_reference_sources"] = ref_build
 
     det.close()
     solver.close()
