@@ -140,6 +140,10 @@ int launch_rectify_depth(const RectifyParams& prm, const float* depth, float* ou
         set_last_error("rectify_depth: the width must be a multiple of 4, and width and height below 65535");
         return RS_ERR_INVALID_ARG;
     }
+    if (prm.batch > 65535) {   // one grid row per frame
+        set_last_error("rectify_depth: at most 65535 frames per call");
+        return RS_ERR_INVALID_ARG;
+    }
     // One pass over the whole batch: walking it in groups of frames that fit the L2 (so that DRAM would see the depth once and
     // the result once) measured slower at every group size - 0.79 ms per 256 frames at 48 MB groups against 0.72 - the
     // kernels are bound by the FP64 pipe (R1) and by the latency of the gather (R2), not by DRAM: profiles/README.md
