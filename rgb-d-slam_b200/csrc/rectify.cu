@@ -148,13 +148,16 @@ int launch_rectify_depth(const RectifyParams& prm, const float* depth, float* ou
     // the result once) measured slower at every group size - 0.79 ms per 256 frames at 48 MB groups against 0.72 - the
     // kernels are bound by the FP64 pipe (R1) and by the latency of the gather (R2), not by DRAM: profiles/README.md
     RS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * frame_px * prm.batch, stream));
-    const int blocks = sm_count() * 8;
-    const dim3 grid((blocks + prm.batch - 1) / prm.batch, prm.batch);
+    // 64 blocks per SM in all (a few image rows per block): rows with many invalid pixels finish early, and with 8 blocks per
+    // SM the scatter kernel ran at 52 % achieved occupancy. Measured 0.709 / 0.676 / 0.643 / 0.585 / 0.585 ms per 256 frames at
+    // 8 / 16 / 32 / 64 / 256 blocks per SM.
+    const dim3 grid((sm_count() * 64 + prm.batch - 1) / prm.batch, prm.batch);
+    const dim3 grid2 = grid;
     // whole image rows per block: a multiple of the row's float4 count when that fits a block
     const int w4 = prm.W / 4, threads = w4 <= 512 ? w4 * std::max(1, 256 / w4) : 256;
     rectify_scatter_kernel<<<grid, threads, 0, stream>>>(depth, reinterpret_cast<unsigned*>(out), prm);
     RS_LAUNCH_CHECK();
-    rectify_resolve_kernel<<<grid, 256, 0, stream>>>(depth, reinterpret_cast<uint4*>(out), prm);
+    rectify_resolve_kernel<<<grid2, 256, 0, stream>>>(depth, reinterpret_cast<uint4*>(out), prm);
     RS_LAUNCH_CHECK();
     return RS_OK;
 }
