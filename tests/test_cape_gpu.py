@@ -192,6 +192,27 @@ def test_rectify_depth_random_extrinsics_bit_exact(det):
         det.set_rectification(None, enable=False)
 
 
+def test_rectify_depth_extreme_depths_bit_exact(det):
+    """Depths a sensor never produces but a float image can hold: subnormal, tiny, huge (finite), negative. The kernels widen
+    float -> double with integer shifts for zero / normal values and fall back to the conversion otherwise (rectify.cu: widen);
+    the image must still equal the oracle's byte for byte. (NaN / infinite depths make the reference call exit(-1).)"""
+    depth = rs.synth.scene_v0_batch(70, 2)
+    rng = np.random.default_rng(4)
+    specials = np.array([1e-45, 1e-40, 1.1754942e-38, 1.1754944e-38, 1e-30, 1e-10, 1e10, 1e30, 3.4e38, -1.0, -0.0], np.float32)
+    rows, cols = rng.integers(0, 480, 4000), rng.integers(0, 640, 4000)
+    depth[0, rows, cols] = specials[rng.integers(0, len(specials), 4000)]
+    depth[1, 200:203, :] = np.float32(1e-41)          # whole rows of subnormals
+    T = _cam2_to_cam1(0.01, -0.02, 0.015, t=(30.0, -5.0, 8.0))
+    try:
+        for ext in (None, T):
+            det.set_rectification(ext, enable=True)
+            got = det.rectify_depth(depth)
+            ref = ol.rectify_depth(depth, ext)
+            assert got.tobytes() == ref.tobytes()
+    finally:
+        det.set_rectification(None, enable=False)
+
+
 def test_new_entry_points_fail_loudly(det):
     depth = rs.synth.scene_v0_batch(0, 1)
     fresh = rs.PrimitiveDetection(640, 480, 20, max_batch=1)
