@@ -3,7 +3,7 @@
 // Defined here: what the reference defines in translation units that cannot be built without third-party libraries and that
 // the CAPE path only touches at its edges - the logger sinks, Parameters::load_defaut (the reference's default intrinsics,
 // parameters.cpp:59-74) - and get_depth_quantization, whose body is taken verbatim from the reference's covariances.cpp at
-// build time (oracle/ref_shim/Makefile writes it to oracle/_ref/gen_depth_quantization.inc; nothing of it is committed).
+// build time (oracle/ref_shim/Makefile writes it to a scratch file under /tmp that is deleted after the compile; nothing of it is committed or kept).
 #define private public      // the label grids are private members of Primitive_Detection
 #define protected public
 #include "features/primitives/depth_map_transformation.hpp"

@@ -2,7 +2,7 @@
 // (pose_optimization.cpp, levenberg_marquardt_functors.cpp, utils/pose.cpp, utils/camera_transformation.cpp, the coordinate
 // classes, ransac.hpp, random.hpp - compiled where they lie, unmodified) plus the three optimisation-feature classes, whose
 // declarations and member definitions are cut out of map_management/map_features/map_{point,primitive,point2d}.{hpp,cpp} AT BUILD
-// TIME (oracle/ref_shim/Makefile, into oracle/_ref/gen_features_*.inc - those files also define the map classes, which drag the
+// TIME (oracle/ref_shim/Makefile, into scratch files under /tmp deleted after the compile - those files also define the map classes, which drag the
 // whole local map in; nothing of them is committed here). Third-party stand-ins: ref_eigen.hpp, and for
 // Eigen::LevenbergMarquardt<NumericalDiff<...>> the oracle's restated MINPACK lmdif (ref_eigen_lm.hpp) - so this build pins what the
 // REFERENCE wrote (RANSAC loop and early stop, std::shuffle subset draws, the residual functor, inlier tests, the per-feature random
