@@ -170,6 +170,33 @@ def pose_residuals(matches, x6, K=(550.0, 550.0, 320.0, 240.0)):
     return out
 
 
+def pose_lm_evaluations(cur_pose, matches, K=(550.0, 550.0, 320.0, 240.0), maxfev=400):
+    """Function evaluations the oracle's LM (compute_optimized_global_pose) spends on `matches` from `cur_pose`, and its status."""
+    lib = load()
+    lib.orc_pose_lm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.orc_pose_coefficients.argtypes = [C.c_void_p, C.c_void_p]
+    Kc = np.asarray(K, dtype=np.float64)
+    m = normalized_planes(matches)
+    x = np.zeros(6)
+    lib.orc_pose_coefficients(np.ascontiguousarray(cur_pose, dtype=np.float64).ctypes.data, x.ctypes.data)
+    nfev = C.c_int(0)
+    status = lib.orc_pose_lm(Kc.ctypes.data, m.ctypes.data, len(m), x.ctypes.data, maxfev, C.byref(nfev))
+    return nfev.value, status
+
+
+def normalized_planes(matches):
+    """Plane normals normalised once, as pose_solve does on entry (normalize_features)."""
+    m = np.array(matches, copy=True)
+    for f in m:
+        if f["type"] == abi.RS_FEAT_PLANE:
+            for key in ("obs", "map"):
+                v = f[key][:3]
+                z = v[0] * v[0] + v[1] * v[1] + v[2] * v[2]
+                if z > 0:
+                    f[key][:3] = v / np.sqrt(z)
+    return np.ascontiguousarray(m)
+
+
 def pose_inliers(pose7, matches, K=(550.0, 550.0, 320.0, 240.0)):
     lib = load()
     Kc = np.asarray(K, dtype=np.float64)

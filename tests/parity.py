@@ -121,3 +121,23 @@ def oracle_pose_is_determined(pose_solve, cur, matches, seed, scales=(1e-12, 1e-
         if np.abs(pc - rc).max() > max(1e-6, 1e4 * abs(s)) * max(np.abs(np.diag(rc)).max(), 1e-300):
             return False, "covariance moves under a %g relative input change" % s
     return True, ""
+
+
+def winning_hypotheses_converged(ol, cur, matches, seed, iterations, budget=400, margin=0.75):
+    """A second way in which the reference algorithm does not determine its answer: a minimal-subset LM that is still moving when
+    Eigen's evaluation budget (400) cuts it off. Its end point is wherever the cap happens to fall - a 1e-14 change of the start
+    pose moves it (found by the round-2 sweep against the compiled reference sources: problem 10357, hypothesis 113, 388
+    evaluations, LM status 3 / 5 / 2 under 1e-14 .. 1e-10 perturbations) - and whether it wins the RANSAC depends on it.
+    Returns False when the LM of any of the given RANSAC iterations, as the oracle runs it, uses more than margin * budget
+    evaluations."""
+    _, _, taps = ol.pose_solve(cur, matches, seed=seed, taps=True)
+    for it in iterations:
+        if it is None or it < 0 or it >= len(taps["subsets"]):
+            continue
+        sub = [k for k in taps["subsets"][it] if k >= 0]
+        if not sub:
+            continue
+        nfev, _ = ol.pose_lm_evaluations(cur, matches[sub], maxfev=budget)
+        if nfev > margin * budget:
+            return False
+    return True

@@ -126,7 +126,10 @@ def compare_pose(solver, guess, matches, M, expect_ok=None):
         # frames whose answer the reference algorithm itself does not determine (parity.oracle_pose_is_determined)
         determined, why = parity.oracle_pose_is_determined(ol.pose_solve, cur, m, 0)
         if determined:
-            raise
+            # ... or whose winning hypothesis (the device's or the reference's) is an LM cut off by the evaluation budget
+            rout, _ = ol.pose_solve(cur, m, seed=0)
+            if parity.winning_hypotheses_converged(ol, cur, m, 0, (int(out["best_iteration"]), int(rout["best_iteration"]))):
+                raise
         return None
     if expect_ok is not None:
         assert ok == expect_ok
