@@ -21,17 +21,11 @@ namespace rs {
 
 namespace {
 
-// (double)f without the conversion pipe: F2F runs at a quarter of the FP64 rate on sm_100 (profiles/r01h_microbench_issue_cost.txt)
-// and three widenings per pixel kept the XU pipe 62 % busy. For a zero or a normal finite float the double has the same sign,
-// the exponent rebiased by 896 and the 23 mantissa bits on top of the 52: three integer instructions. Anything else
-// (subnormal, infinity, NaN - not produced by depth images) takes the conversion.
-__device__ __forceinline__ double widen(const float f)
-{
-    const unsigned b = __float_as_uint(f), a = b & 0x7fffffffu;
-    if (a != 0u && a - 0x00800000u >= 0x7f000000u) return static_cast<double>(f);
-    const unsigned hi = (b & 0x80000000u) | ((a >> 3) + (a ? 0x38000000u : 0u));
-    return __hiloint2double(static_cast<int>(hi), static_cast<int>(b << 29));
-}
+// (double)f: the plain conversion. A shift-and-rebias widening on the integer pipe (as K1a uses) was tried here: it takes six
+// instructions and a range branch against one F2F, and once the grid was balanced both kernels turned out to be bound by
+// instruction issue, not by the conversion pipe - 0.582 ms per 256 frames with the integer widening, 0.477 with F2F
+// (0.450 without the two NaN compares the rounding-down conversion makes redundant).
+__device__ __forceinline__ double widen(const float f) { return static_cast<double>(f); }
 
 // The depth a source pixel carries to camera 1 (depth_map_transformation.cpp:52-58,73-75): z of T * (preX z, preY z, z, 1)
 __device__ __forceinline__ double rectify_depth_of(const RectifyParams& prm, const double ox, const double oy, const double oz)
@@ -53,7 +47,8 @@ __device__ __forceinline__ bool rectify_project(const RectifyParams& prm, const 
     const double inv = 1.0 / pz;
     const double sx = inv * (prm.fx * px + prm.cx * pz);
     const double sy = inv * (prm.fy * py + prm.cy * pz);
-    if (sx != sx || sy != sy) return false;
+    // no separate NaN test: a NaN converts to 0 and fails the range test (the oracle drops such a pixel; the reference itself
+    // leaves the process through exit(-1) there, depth_map_transformation.cpp:79-83)
     const int ix = __double2int_rd(sx), iy = __double2int_rd(sy);
     if (!(ix > 0 && iy > 0 && ix < prm.W && iy < prm.H)) return false;
     dst = unsigned(iy) * unsigned(prm.W) + unsigned(ix);
