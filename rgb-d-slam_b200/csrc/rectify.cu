@@ -27,23 +27,37 @@ namespace {
 // (0.450 without the two NaN compares the rounding-down conversion makes redundant).
 __device__ __forceinline__ double widen(const float f) { return static_cast<double>(f); }
 
+// RI = the rotation block of the camera-2 -> camera-1 transformation is exactly the identity (the reference's default,
+// parameters.cpp:59-74, and every pure translation): ((1 ox + 0 oy) + 0 oz) + t is ox + t bit for bit - 1 ox is exact, the
+// zero products are zeros of some sign, and a zero only changes a sum that is itself zero, where it can flip the sign of a
+// zero that the later fx px + cx pz absorbs (or that ends in column / row 0, which the range test drops either way). 15 of
+// the 35 FP64 instructions per pixel go away. The host picks the instantiation by comparing the nine coefficients.
+template <bool RI>
+__device__ __forceinline__ double transform_row(const double* T, const int r, const double ox, const double oy, const double oz)
+{
+    if (RI) return (r == 0 ? ox : (r == 1 ? oy : oz)) + T[4 * r + 3];
+    return ((T[4 * r] * ox + T[4 * r + 1] * oy) + T[4 * r + 2] * oz) + T[4 * r + 3];
+}
+
 // The depth a source pixel carries to camera 1 (depth_map_transformation.cpp:52-58,73-75): z of T * (preX z, preY z, z, 1)
+template <bool RI>
 __device__ __forceinline__ double rectify_depth_of(const RectifyParams& prm, const double ox, const double oy, const double oz)
 {
-    return ((prm.T[8] * ox + prm.T[9] * oy) + prm.T[10] * oz) + prm.T[11];
+    return transform_row<RI>(prm.T, 2, ox, oy, oz);
 }
 
 // One source pixel through depth_map_transformation.cpp:48-77: the destination pixel it falls in. false: it is dropped.
 // to_screen_coordinates multiplies by the whole intrinsics matrix, (fx px + 0 py) + cx pz: a finite py leaves fx px as it is
 // (a +-0 is added), a non-finite one makes sy NaN or out of range as well, so the zero terms are left out; floor + the
 // unsigned cast + the range test are one conversion rounding down (it saturates, NaN gives 0: both fail 0 < i < size).
+template <bool RI>
 __device__ __forceinline__ bool rectify_project(const RectifyParams& prm, const float preX, const float preY, const float z,
                                                 unsigned& dst)
 {
     const double ox = widen(preX * z), oy = widen(preY * z), oz = widen(z);
-    const double px = ((prm.T[0] * ox + prm.T[1] * oy) + prm.T[2] * oz) + prm.T[3];
-    const double py = ((prm.T[4] * ox + prm.T[5] * oy) + prm.T[6] * oz) + prm.T[7];
-    const double pz = rectify_depth_of(prm, ox, oy, oz);
+    const double px = transform_row<RI>(prm.T, 0, ox, oy, oz);
+    const double py = transform_row<RI>(prm.T, 1, ox, oy, oz);
+    const double pz = rectify_depth_of<RI>(prm, ox, oy, oz);
     const double inv = 1.0 / pz;
     const double sx = inv * (prm.fx * px + prm.cx * pz);
     const double sy = inv * (prm.fy * py + prm.cy * pz);
@@ -58,6 +72,7 @@ __device__ __forceinline__ bool rectify_project(const RectifyParams& prm, const 
 // Winner keys order source pixels by raster position and unpack without a division: (row << 16 | column) + 1.
 // R1: winners[dst] = max key over the source pixels landing on dst. `winners` is the output image, zeroed. One block row of the
 // grid per frame of the group (blockIdx.y), whole image rows per block (no per-pixel index arithmetic).
+template <bool RI>
 __global__ void __launch_bounds__(512) rectify_scatter_kernel(const float* __restrict__ depth, unsigned* __restrict__ winners,
                                                              const RectifyParams prm)
 {
@@ -86,7 +101,7 @@ __global__ void __launch_bounds__(512) rectify_scatter_kernel(const float* __res
                 const float z = zz[t];
                 if (!(z > 0.f)) continue;
                 unsigned dst;
-                if (rectify_project(prm, pre[t], preY, z, dst))
+                if (rectify_project<RI>(prm, pre[t], preY, z, dst))
                     atomicMax(frame + dst, (unsigned(row) << 16 | unsigned(col + t * stride)) + 1u);
             }
         }
@@ -94,6 +109,7 @@ __global__ void __launch_bounds__(512) rectify_scatter_kernel(const float* __res
 }
 
 // R2, in place on the output image: winning key -> the depth that source pixel projects to; 0 (nothing landed) -> +0.0f
+template <bool RI>
 __global__ void __launch_bounds__(256) rectify_resolve_kernel(const float* __restrict__ depth, uint4* __restrict__ image,
                                                              const RectifyParams prm)
 {
@@ -119,7 +135,7 @@ __global__ void __launch_bounds__(256) rectify_resolve_kernel(const float* __res
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             if (kk[t] == 0u) continue;
-            const double pz = rectify_depth_of(prm, widen(pxf[t] * z[t]), widen(pyf[t] * z[t]), widen(z[t]));
+            const double pz = rectify_depth_of<RI>(prm, widen(pxf[t] * z[t]), widen(pyf[t] * z[t]), widen(z[t]));
             kk[t] = __float_as_uint(static_cast<float>(pz));
         }
         img[q] = make_uint4(kk[0], kk[1], kk[2], kk[3]);
@@ -150,9 +166,19 @@ int launch_rectify_depth(const RectifyParams& prm, const float* depth, float* ou
     const dim3 grid2 = grid;
     // whole image rows per block: a multiple of the row's float4 count when that fits a block
     const int w4 = prm.W / 4, threads = w4 <= 512 ? w4 * std::max(1, 256 / w4) : 256;
-    rectify_scatter_kernel<<<grid, threads, 0, stream>>>(depth, reinterpret_cast<unsigned*>(out), prm);
-    RS_LAUNCH_CHECK();
-    rectify_resolve_kernel<<<grid2, 256, 0, stream>>>(depth, reinterpret_cast<uint4*>(out), prm);
+    const double* T = prm.T;
+    const bool ri = T[0] == 1.0 && T[1] == 0.0 && T[2] == 0.0 && T[4] == 0.0 && T[5] == 1.0 && T[6] == 0.0 && T[8] == 0.0 && T[9] == 0.0 &&
+                    T[10] == 1.0;
+    if (ri) {
+        rectify_scatter_kernel<true><<<grid, threads, 0, stream>>>(depth, reinterpret_cast<unsigned*>(out), prm);
+        RS_LAUNCH_CHECK();
+        rectify_resolve_kernel<true><<<grid2, 256, 0, stream>>>(depth, reinterpret_cast<uint4*>(out), prm);
+    }
+    else {
+        rectify_scatter_kernel<false><<<grid, threads, 0, stream>>>(depth, reinterpret_cast<unsigned*>(out), prm);
+        RS_LAUNCH_CHECK();
+        rectify_resolve_kernel<false><<<grid2, 256, 0, stream>>>(depth, reinterpret_cast<uint4*>(out), prm);
+    }
     RS_LAUNCH_CHECK();
     return RS_OK;
 }

@@ -9,7 +9,9 @@ det = rs.PrimitiveDetection(640, 480, 20, max_batch=F)
 d = torch.from_numpy(depth).cuda(); out = torch.empty_like(d)
 s = torch.cuda.current_stream().cuda_stream
 T = np.eye(4); T[:3, 3] = (25.0, -3.0, 4.0)
-for name, ext in (("identity", None), ("offset 25 mm", T)):
+R = np.eye(4); c, sn = np.cos(0.02), np.sin(0.02)
+R[:3, :3] = np.array([[c, 0, sn], [0, 1, 0], [-sn, 0, c]]); R[:3, 3] = (25.0, -3.0, 4.0)
+for name, ext in (("identity", None), ("offset 25 mm", T), ("rotated 0.02 rad + offset", R)):
     det.set_rectification(ext, enable=True)
     for _ in range(2): det.rectify_device(d.data_ptr(), F, out.data_ptr(), stream=s)
     torch.cuda.synchronize()
